@@ -1,0 +1,111 @@
+/* b2u.h -- C ABI of libb200unet.so: the B200 (sm_100a) kernels behind the UNet segmentation hot path of
+ * clolckliang/unet-pytorch.
+ *
+ * The reference has no FFI layer (it is pure Python on torch.nn); the boundary this library plugs into is the
+ * set of torch.nn calls made by nets/unet.py, nets/vgg.py, nets/unet_training.py and utils/utils_metrics.py.
+ * Every entry point below names the reference call it replaces (path:line under the reference repo).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless stated otherwise; the library never allocates, frees or retains
+ *     caller memory (workspaces are passed in; sizes come from the *_workspace functions);
+ *   - activations/gradients are NHWC bf16 ("void*"), C a multiple of 8 (64 for the tensor-core convs);
+ *     logits and parameters are fp32 in the reference's own layouts (NCHW, OIHW);
+ *   - `stream` is a cudaStream_t (CUstream); launches are asynchronous on it;
+ *   - return value 0 = ok, otherwise a B2U_ERR_* code; b2u_last_error() gives the message (thread-local).
+ */
+#ifndef B2U_H_
+#define B2U_H_
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2U_OK 0
+#define B2U_ERR_SHAPE 1
+#define B2U_ERR_CUDA 2
+#define B2U_ERR_DRIVER 3
+#define B2U_ERR_NCCL 4
+#define B2U_ERR_ARG 5
+
+const char* b2u_last_error(void);
+int b2u_version(void);
+int b2u_num_sms(void);
+
+/* ---- layout / packing ------------------------------------------------------------------------------------ */
+/* first conv of the encoder (nets/vgg.py:53 with in_channels=3): NCHW fp32 image -> im2col rows [N,H,W,64] bf16,
+ * column k = (r*3+s)*Cin + c, zero padded; the conv itself then is a 1x1 b2u_conv_fprop with K = 64. */
+int b2u_im2col_first(const float* x_nchw, void* col, int N, int Cin, int H, int W, void* stream);
+/* nn.Conv2d.weight (OIHW fp32, nets/vgg.py:53, nets/unet.py:11-12) -> bf16 K-major operands:
+ * wf[Cout][taps*Cin] for fprop, wd[Cin][taps*Cout] (taps flipped) for dgrad; either may be NULL. */
+int b2u_pack_weights(const float* w_oihw, void* wf, void* wd, int Cout, int Cin, int taps, void* stream);
+int b2u_pack_weights_first(const float* w_oihw, void* wf, int Cout, int Cin, void* stream);
+int b2u_nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, int H, int W, void* stream);
+int b2u_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int W, void* stream);
+
+/* ---- tensor-core convolutions (tcgen05 implicit GEMM) ------------------------------------------------------ */
+/* y = [relu](conv(cat(x0, x1), w) + bias).  Replaces nn.Conv2d(k=3,p=1 | k=1)+ReLU (nets/vgg.py:53-57,
+ * nets/unet.py:11-12,18-21) and, with x1 != NULL, torch.cat([skip, up], 1) + conv (nets/unet.py:17-18).
+ * taps = 9 (3x3, pad 1) or 1.  C0, C1, Cout multiples of 64.  bn_override: 0 = choose the N tile. */
+int b2u_conv_fprop(const void* x0, int C0, const void* x1, int C1, const void* wf, const float* bias, void* y, int N,
+                   int H, int W, int Cout, int taps, int relu, int bn_override, void* stream);
+/* dgrad of the same conv (autograd of nn.Conv2d, utils/utils_fit.py:92): dz has Cz channels; the C0+C1 input-channel
+ * gradients go to dx0 / dx1 (dx1 NULL: single input).  mask (NHWC bf16, C0 channels, single output only) applies the
+ * ReLU backward of the tensor that fed the conv: dx0 = 0 where mask <= 0. */
+int b2u_conv_dgrad(const void* dz, int Cz, const void* wd, void* dx0, int C0, void* dx1, int C1, const void* mask,
+                   int N, int H, int W, int taps, int bn_override, void* stream);
+/* wgrad: dw (OIHW fp32, overwritten) = sum over pixels of dz (x) cat(x0, x1).  first_cin > 0: x0 is the im2col tensor
+ * of b2u_im2col_first and dw is [Cout][first_cin][3][3].  flags bit0: unmerged vertical taps (debug). */
+size_t b2u_conv_wgrad_workspace(int N, int H, int W, int Cin_tot, int Cout, int taps);
+int b2u_conv_wgrad(const void* x0, int C0, const void* x1, int C1, const void* dz, int Cout, float* dw, void* ws,
+                   size_t ws_bytes, int N, int H, int W, int taps, int first_cin, int flags, void* stream);
+/* db[c] = sum over pixels of dz[.,c]  (bias gradient of nn.Conv2d) */
+size_t b2u_bias_grad_workspace(int C);
+int b2u_bias_grad(const void* dz, float* db, void* ws, size_t ws_bytes, long long P, int C, void* stream);
+
+/* ---- pooling / upsampling ---------------------------------------------------------------------------------- */
+/* nn.MaxPool2d(2, 2) (nets/vgg.py:51).  H, W = dims of the un-pooled tensor. */
+int b2u_maxpool2x2_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream);
+/* dz = (route(dpool to the first max of each window) + dskip) * (y > 0 if relu_mask); dskip may be NULL */
+int b2u_maxpool2x2_bwd(const void* dpool, const void* dskip, const void* y, void* dz, int N, int H, int W, int C,
+                       int relu_mask, void* stream);
+/* nn.UpsamplingBilinear2d(scale_factor=2) = bilinear, align_corners=True (nets/unet.py:13).  H, W = low-res dims. */
+int b2u_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream);
+/* adjoint; ylow (nullable) = the ReLU output that was upsampled: dlow = 0 where ylow <= 0 */
+int b2u_upsample2x_bwd(const void* dup, const void* ylow, void* dlow, int N, int H, int W, int C, void* stream);
+
+/* ---- classifier head (nn.Conv2d(64, num_classes, 1), nets/unet.py:58,76) ------------------------------------ */
+int b2u_head_fwd(const void* x, const float* w, const float* b, float* logits_nchw, int N, int H, int W, int Cin,
+                 int ncls, void* stream);
+size_t b2u_head_bwd_workspace(void);
+int b2u_head_bwd(const float* dlogits_nchw, const void* x, const float* w, void* dx, float* dw, float* db, void* ws,
+                 size_t ws_bytes, int N, int H, int W, int Cin, int ncls, int relu_mask, void* stream);
+
+/* ---- losses and metrics ------------------------------------------------------------------------------------ */
+/* CE_Loss / Focal_Loss / Dice_loss (nets/unet_training.py:9-56) and f_score (utils/utils_metrics.py:12-31) in one
+ * pass.  out (device, b2u_loss_out_len(C) floats): [0] CE, [1] Focal, [2] Dice loss, [3] f_score, then backward
+ * coefficients.  target: int64 [N,H,W]; onehot (nullable): fp32 [N,H,W,C+1]. */
+size_t b2u_loss_workspace(int C);
+int b2u_loss_out_len(int C);
+int b2u_loss_fwd(const float* logits, const long long* target, const float* onehot, const float* cls_w, float* out,
+                 double* stats, void* ws, size_t ws_bytes, int N, int C, int H, int W, float beta, float smooth,
+                 float focal_alpha, float focal_gamma, float thr, void* stream);
+/* dlogits = gscale[0] dCE + gscale[1] dFocal + gscale[2] dDice (gscale: 3 floats on device) */
+int b2u_loss_bwd(const float* logits, const long long* target, const float* onehot, const float* cls_w, const float* fin,
+                 const float* gscale, float* dlogits, int N, int C, int H, int W, float focal_alpha, float focal_gamma,
+                 void* stream);
+/* per-pixel class decision of the inference loop (unet.py:246-250: argmax(softmax(z)) == argmax(z)) */
+int b2u_argmax_u8(const float* logits, unsigned char* mask, int N, int C, int H, int W, void* stream);
+/* fast_hist (utils/utils_metrics.py:34-43): hist (n*n+1 uint64, accumulated) ; dtype 0=u8 1=i32 2=i64 */
+int b2u_fast_hist(const void* a, const void* b, long long len, int n, int dtype, unsigned long long* hist, void* stream);
+
+/* ---- optimizer (torch.optim.Adam / SGD step of train.py:402-405 on flat fp32 buffers) ----------------------- */
+int b2u_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+int b2u_sgd_step(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,
+                 float weight_decay, int nesterov, int first_step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2U_H_ */

@@ -1,0 +1,83 @@
+"""ctypes binding of libb200unet.so (include/b2u.h).  No fallback: a missing library is a hard error."""
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200unet.so")
+
+P, I, F, LL, SZ = c_void_p, c_int, c_float, c_longlong, c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/b2u.h declares (tests/test_abi.py checks this)
+SIGNATURES = {
+    "b2u_last_error": (c_char_p, []),
+    "b2u_version": (I, []),
+    "b2u_num_sms": (I, []),
+    "b2u_im2col_first": (I, [P, P, I, I, I, I, P]),
+    "b2u_pack_weights": (I, [P, P, P, I, I, I, P]),
+    "b2u_pack_weights_first": (I, [P, P, I, I, P]),
+    "b2u_nhwc_bf16_to_nchw_f32": (I, [P, P, I, I, I, I, P]),
+    "b2u_nchw_f32_to_nhwc_bf16": (I, [P, P, I, I, I, I, P]),
+    "b2u_conv_fprop": (I, [P, I, P, I, P, P, P, I, I, I, I, I, I, I, P]),
+    "b2u_conv_dgrad": (I, [P, I, P, P, I, P, I, P, I, I, I, I, I, P]),
+    "b2u_conv_wgrad_workspace": (SZ, [I, I, I, I, I, I]),
+    "b2u_conv_wgrad": (I, [P, I, P, I, P, I, P, P, SZ, I, I, I, I, I, I, P]),
+    "b2u_bias_grad_workspace": (SZ, [I]),
+    "b2u_bias_grad": (I, [P, P, P, SZ, LL, I, P]),
+    "b2u_maxpool2x2_fwd": (I, [P, P, I, I, I, I, P]),
+    "b2u_maxpool2x2_bwd": (I, [P, P, P, P, I, I, I, I, I, P]),
+    "b2u_upsample2x_fwd": (I, [P, P, I, I, I, I, P]),
+    "b2u_upsample2x_bwd": (I, [P, P, P, I, I, I, I, P]),
+    "b2u_head_fwd": (I, [P, P, P, P, I, I, I, I, I, P]),
+    "b2u_head_bwd_workspace": (SZ, []),
+    "b2u_head_bwd": (I, [P, P, P, P, P, P, P, SZ, I, I, I, I, I, I, P]),
+    "b2u_loss_workspace": (SZ, [I]),
+    "b2u_loss_out_len": (I, [I]),
+    "b2u_loss_fwd": (I, [P, P, P, P, P, P, P, SZ, I, I, I, I, F, F, F, F, F, P]),
+    "b2u_loss_bwd": (I, [P, P, P, P, P, P, P, I, I, I, I, F, F, P]),
+    "b2u_argmax_u8": (I, [P, P, I, I, I, I, P]),
+    "b2u_fast_hist": (I, [P, P, LL, I, I, P, P]),
+    "b2u_adam_step": (I, [P, P, P, P, LL, F, F, F, F, F, I, F, P]),
+    "b2u_sgd_step": (I, [P, P, P, LL, F, F, F, I, I, F, P]),
+}
+
+_lib = None
+
+
+class B2UError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads the CUDA library; raises if it has not been built (python unet-pytorch_b200/build.py)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B2UError(
+                f"{LIB_PATH} is missing: build it with `python unet-pytorch_b200/build.py` "
+                "(there is no CPU or PyTorch fallback for the hot path)")
+        h = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(h, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().b2u_last_error()
+        msg = msg.decode() if msg else ""
+        if rc == 1:
+            raise ValueError(f"b2u: {msg}")
+        raise B2UError(f"b2u error {rc}: {msg}")
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()

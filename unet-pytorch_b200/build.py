@@ -1,0 +1,73 @@
+"""Builds libb200unet.so (the C-ABI CUDA library, include/b2u.h) in-tree with nvcc for sm_100a.
+
+Usage: python unet-pytorch_b200/build.py [--force]
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libb200unet.so")
+SOURCES = ["runtime.cu", "conv_igemm.cu", "conv_wgrad.cu", "elementwise.cu", "head_loss.cu", "hist.cu", "optim.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xptxas=-v",  # no --use_fast_math: precise math everywhere; -v prints registers/spills
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _stale():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not _stale():
+        return OUT
+    nvcc = _nvcc()
+    objs = []
+    bdir = os.path.join(HERE, "build")
+    os.makedirs(bdir, exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        sp = os.path.join(CSRC, src)
+        if not os.path.exists(sp):
+            continue
+        obj = os.path.join(bdir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [nvcc, *NVCC_FLAGS, "-I", CSRC, "-c", sp, "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(f"== {src}\n{out}")
+        if p.returncode != 0:
+            sys.stderr.write("\n".join(log))
+            raise RuntimeError(f"nvcc failed on {src}")
+    cmd = [nvcc, "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("link failed")
+    with open(os.path.join(bdir, "ptxas.log"), "w") as f:
+        f.write("\n".join(log))
+    if verbose:
+        print("\n".join(log))
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

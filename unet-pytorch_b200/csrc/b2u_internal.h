@@ -1,0 +1,51 @@
+// b2u_internal.h -- declarations shared by the translation units of libb200unet.so
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define B2U_OK 0
+#define B2U_ERR_SHAPE 1
+#define B2U_ERR_CUDA 2
+#define B2U_ERR_DRIVER 3
+#define B2U_ERR_NCCL 4
+#define B2U_ERR_ARG 5
+
+namespace b2u {
+
+// records a thread-local message, returns `code`
+int set_error(int code, const char* fmt, ...);
+int num_sms();
+
+// NHWC bf16 tensor viewed as a rank-4 TMA tensor (C, W, H, N); `cpitch` = elements between pixels.
+int make_tmap_nhwc(CUtensorMap* out, const void* base, int N, int H, int W, int C, int boxC, int boxW, int boxH,
+                   CUtensorMapSwizzle swz, int cpitch = 0);
+// row-major bf16 matrix [rows][cols] viewed as rank-2 (cols, rows)
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, int boxCols, int boxRows,
+                 CUtensorMapSwizzle swz);
+
+struct ConvLaunch {
+  const void* x0 = nullptr; int C0 = 0;     // source 0 (NHWC bf16)
+  const void* x1 = nullptr; int C1 = 0;     // optional source 1 (virtual concat), same N,H,W
+  const void* wpacked = nullptr;            // bf16 [Cout][taps*(C0+C1)]
+  const float* bias = nullptr;              // fp32 [Cout] or null
+  void* y0 = nullptr; void* y1 = nullptr;   // outputs (NHWC bf16); y1 receives channels >= split_c
+  int split_c = 0;
+  const __nv_bfloat16* mask = nullptr; int mask_c = 0;
+  int N = 0, H = 0, W = 0, Cout = 0, taps = 9;
+  int flags = 0;                            // bit0 relu, bit1 mask
+  int bn_override = 0;
+};
+int launch_conv(const ConvLaunch& a, cudaStream_t st);
+
+struct WgradLaunch {
+  const void* x0 = nullptr; int C0 = 0;
+  const void* x1 = nullptr; int C1 = 0;
+  const void* dz = nullptr; int Cout = 0;   // NHWC bf16 gradient wrt pre-activation
+  float* partial = nullptr;                 // workspace [splits][taps][Cout][Cin] fp32
+  int N = 0, H = 0, W = 0, taps = 9;
+  int splits = 0;                           // 0: choose
+};
+
+}  // namespace b2u

@@ -1,0 +1,420 @@
+// conv_igemm.cu -- implicit-GEMM convolution (3x3 pad 1 / 1x1, stride 1) for sm_100a.
+//
+//   y[n,h,w,co] = act( sum_{r,s,ci} x[n,h+r-1,w+s-1,ci] * Wp[co,(r*3+s)*C+ci] + bias[co] ) (* mask)
+//
+// Replaces the library calls behind nn.Conv2d(k=3,p=1)+ReLU in the reference
+// (nets/vgg.py:53-57, nets/unet.py:11-12,18-21) and, with flipped/transposed packed
+// weights, their autograd dgrad (utils_fit.py:92).  The channel concat of unetUp
+// (nets/unet.py:17) is never materialised: the K loop walks source 0 (skip) then
+// source 1 (upsampled) through two tensor maps; the dgrad of that conv writes its two
+// channel ranges to two tensors.
+//
+// Mapping to the hardware (B200):
+//   * GEMM M = 128 output pixels = a 16(w) x 8(h) spatial patch of one image, N = BN output
+//     channels, K = taps x input channels in blocks of 64.
+//   * A operand: one TMA box per (channel block, horizontal tap s): (8+2) x 16 pixels x 64
+//     channels, zero-filled outside the image by TMA (this IS the padding).  The three
+//     vertical taps r re-use that box: the UMMA descriptor start address is advanced by
+//     r*16 rows (a multiple of the 8-row swizzle atom), so A is fetched 3x, not 9x.
+//   * B operand: packed weights [Cout][taps*C] (K-major), one TMA box per tap.
+//   * tcgen05.mma (cta_group::1, M=128, N=BN, K=16), fp32 accumulators in TMEM, double
+//     buffered so the epilogue of tile i overlaps the main loop of tile i+1.
+//   * Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps 2..5 =
+//     epilogue (tcgen05.ld -> bias/ReLU/mask -> bf16 -> swizzled smem -> TMA store).
+//   * Persistent: grid = min(tiles, #SM), static round-robin tile schedule.
+#include "b2u_internal.h"
+#include "b2u_ptx.cuh"
+
+namespace b2u {
+
+constexpr int kWb = 16;   // patch width  (pixels)
+constexpr int kHb = 8;    // patch height (pixels)
+constexpr int kTileM = kWb * kHb;
+constexpr int kMaxCout = 1024;
+constexpr int KB = 64;    // channels per K block = one 128-byte swizzle row
+
+struct ConvParams {
+  int N, H, W;
+  int C0, C1;        // input channels of source 0 / source 1 (C1 == 0: single source)
+  int Cout;          // GEMM N extent (multiple of BN)
+  int tiles_w, tiles_h;
+  int num_m_tiles, num_n_tiles;
+  int split_c;       // output channels >= split_c go to the second output tensor map
+  int flags;         // bit0 relu, bit1 mask
+  const float* bias; // [Cout] or null
+  const __nv_bfloat16* mask;  // NHWC [N,H,W,mask_c] or null; keeps y where mask > 0
+  int mask_c;
+};
+
+template <int BN, int TAPS, int SA, int SB>
+struct ConvCfg {
+  static constexpr int kRowBytes = KB * 2;                      // swizzle span (128 B)
+  static constexpr int kARows = (TAPS == 9 ? kHb + 2 : kHb) * kWb;
+  static constexpr int kABytes = kARows * kRowBytes;
+  static constexpr int kBBytes = BN * kRowBytes;
+  static constexpr int kEpiN = 64;
+  static constexpr int kStageBytes = kTileM * kEpiN * 2;
+  static constexpr int kOffA = 0;
+  static constexpr int kOffB = kOffA + SA * kABytes;
+  static constexpr int kOffStage = kOffB + SB * kBBytes;
+  static constexpr int kOffBias = kOffStage + 2 * kStageBytes;
+  static constexpr int kOffBar = kOffBias + kMaxCout * 4;
+  static constexpr int kNumBar = 2 * SA + 2 * SB + 4;
+  static constexpr int kOffTmem = kOffBar + kNumBar * 8;
+  static constexpr int kSmemBytes = kOffTmem + 16 + 1024;  // + alignment slack
+  static constexpr uint32_t kSBO = 8 * kRowBytes;
+  static constexpr int kTmemCols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);
+  static_assert(BN % 64 == 0 && BN <= 256, "N tile must be 64/128/192/256");
+  static_assert(kABytes % 1024 == 0 && kBBytes % 1024 == 0, "stage buffers must keep 1024B alignment");
+  static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
+};
+
+template <int BN, int TAPS, int SA, int SB>
+__global__ void __launch_bounds__(192, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC0,
+                  const __grid_constant__ CUtensorMap tmC1, const ConvParams p) {
+  using Cfg = ConvCfg<BN, TAPS, SA, SB>;
+  constexpr int S_TAPS = TAPS == 9 ? 3 : 1;
+  constexpr int R_TAPS = TAPS == 9 ? 3 : 1;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const uint32_t sA = smem_base + Cfg::kOffA;
+  const uint32_t sB = smem_base + Cfg::kOffB;
+  const uint32_t sStage = smem_base + Cfg::kOffStage;
+  float* sBias = reinterpret_cast<float*>(smem_gen + Cfg::kOffBias);
+  const uint32_t bars = smem_base + Cfg::kOffBar;
+  auto a_full = [&](int i) { return bars + 8u * i; };
+  auto a_empty = [&](int i) { return bars + 8u * (SA + i); };
+  auto b_full = [&](int i) { return bars + 8u * (2 * SA + i); };
+  auto b_empty = [&](int i) { return bars + 8u * (2 * SA + SB + i); };
+  auto t_full = [&](int i) { return bars + 8u * (2 * SA + 2 * SB + i); };
+  auto t_empty = [&](int i) { return bars + 8u * (2 * SA + 2 * SB + 2 + i); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kOffTmem);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC0);
+    tma_prefetch_desc(&tmC1);
+    for (int i = 0; i < SA; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
+    for (int i = 0; i < SB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(t_full(i), 1); mbar_init(t_empty(i), 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) sBias[i] = p.bias ? p.bias[i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int chunks0 = p.C0 / KB;
+  const int chunks = (p.C0 + p.C1) / KB;
+  const int ctot = p.C0 + p.C1;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.num_n_tiles;
+        int m_tile = tile / p.num_n_tiles;
+        const int tw = m_tile % p.tiles_w; m_tile /= p.tiles_w;
+        const int th = m_tile % p.tiles_h;
+        const int img = m_tile / p.tiles_h;
+        const int w0 = tw * kWb, h0 = th * kHb, n0 = n_tile * BN;
+        for (int c = 0; c < chunks; ++c) {
+          const CUtensorMap* tm = c < chunks0 ? &tmA0 : &tmA1;
+          const int cc = c < chunks0 ? c * KB : c * KB - p.C0;
+          for (int s = 0; s < S_TAPS; ++s) {
+            mbar_wait(a_empty(sa), pa ^ 1u);
+            mbar_expect_tx(a_full(sa), Cfg::kABytes);
+            if (TAPS == 9) tma_load_4d(sA + sa * Cfg::kABytes, tm, a_full(sa), cc, w0 + s - 1, h0 - 1, img);
+            else           tma_load_4d(sA + sa * Cfg::kABytes, tm, a_full(sa), cc, w0, h0, img);
+            if (++sa == SA) { sa = 0; pa ^= 1u; }
+            for (int r = 0; r < R_TAPS; ++r) {
+              mbar_wait(b_empty(sb), pb ^ 1u);
+              mbar_expect_tx(b_full(sb), Cfg::kBBytes);
+              tma_load_2d(sB + sb * Cfg::kBBytes, &tmB, b_full(sb), (r * S_TAPS + s) * ctot + c * KB, n0);
+              if (++sb == SB) { sb = 0; pb ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN, 0, 0);
+      int sa = 0, sb = 0, as = 0;
+      uint32_t pa = 0, pb = 0, pacc = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(t_empty(as), pacc ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+        uint32_t acc = 0;
+        for (int c = 0; c < chunks; ++c) {
+          for (int s = 0; s < S_TAPS; ++s) {
+            mbar_wait(a_full(sa), pa);
+            tc_fence_after();
+            const uint32_t a_base = sA + sa * Cfg::kABytes;
+            for (int r = 0; r < R_TAPS; ++r) {
+              mbar_wait(b_full(sb), pb);
+              tc_fence_after();
+              const uint32_t b_base = sB + sb * Cfg::kBBytes;
+#pragma unroll
+              for (int k = 0; k < KB / 16; ++k) {
+                const uint64_t ad = umma_smem_desc(a_base + r * (kWb * Cfg::kRowBytes) + k * 32, 16, Cfg::kSBO, 2u);
+                const uint64_t bd = umma_smem_desc(b_base + k * 32, 16, Cfg::kSBO, 2u);
+                tc_mma_bf16(d_tmem, ad, bd, idesc, acc);
+                acc = 1;
+              }
+              tc_commit(b_empty(sb));
+              if (++sb == SB) { sb = 0; pb ^= 1u; }
+            }
+            tc_commit(a_empty(sa));
+            if (++sa == SA) { sa = 0; pa ^= 1u; }
+          }
+        }
+        tc_commit(t_full(as));
+        if (++as == 2) { as = 0; pacc ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps, 128 threads) =====================
+    const int ew = warp & 3;  // TMEM sub-partition this warp may read
+    const int row = ew * 32 + lane;
+    const int ph = row / kWb, pw = row % kWb;
+    const bool issuer = (threadIdx.x == 64);
+    int as = 0;
+    uint32_t pacc = 0;
+    uint32_t sbuf = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.num_n_tiles;
+      int m_tile = tile / p.num_n_tiles;
+      const int tw = m_tile % p.tiles_w; m_tile /= p.tiles_w;
+      const int th = m_tile % p.tiles_h;
+      const int img = m_tile / p.tiles_h;
+      const int w0 = tw * kWb, h0 = th * kHb, n0 = n_tile * BN;
+      const int gh = h0 + ph, gw = w0 + pw;
+      const bool inb = gh < p.H && gw < p.W;
+
+      mbar_wait(t_full(as), pacc);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(as * BN);
+
+#pragma unroll 1
+      for (int j = 0; j < BN / 64; ++j) {
+        uint32_t v[64];
+        tmem_ld_32x32(t_row + j * 64, v);
+        tmem_ld_32x32(t_row + j * 64 + 32, v + 32);
+        tmem_ld_wait();
+        if (j == BN / 64 - 1) {
+          // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(t_empty(as));
+        }
+        const int cbase = n0 + j * 64;
+        uint32_t packed[32];
+        if (p.flags & 2) {
+          const uint4* mrow = reinterpret_cast<const uint4*>(
+              p.mask + ((static_cast<size_t>(img) * p.H + (inb ? gh : 0)) * p.W + (inb ? gw : 0)) * p.mask_c + cbase);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            uint4 m = inb ? __ldg(mrow + q) : make_uint4(0, 0, 0, 0);
+            const uint32_t mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float lo = __uint_as_float(v[q * 8 + 2 * e]) + sBias[cbase + q * 8 + 2 * e];
+              float hi = __uint_as_float(v[q * 8 + 2 * e + 1]) + sBias[cbase + q * 8 + 2 * e + 1];
+              lo = bf16_lo(mm[e]) > 0.f ? lo : 0.f;
+              hi = bf16_hi(mm[e]) > 0.f ? hi : 0.f;
+              packed[q * 4 + e] = pack_bf16x2(lo, hi);
+            }
+          }
+        } else {
+          const bool relu = p.flags & 1;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            float lo = __uint_as_float(v[2 * e]) + sBias[cbase + 2 * e];
+            float hi = __uint_as_float(v[2 * e + 1]) + sBias[cbase + 2 * e + 1];
+            if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+            packed[e] = pack_bf16x2(lo, hi);
+          }
+        }
+        // staging buffer `sbuf` was last read by the TMA store issued two sub-tiles ago
+        if (issuer) tma_store_wait_read<1>();
+        named_bar_sync(1, 128);
+        const uint32_t stage = sStage + sbuf * Cfg::kStageBytes;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t off = row * 128 + ((q ^ (row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + off), "r"(packed[q * 4]),
+                       "r"(packed[q * 4 + 1]), "r"(packed[q * 4 + 2]), "r"(packed[q * 4 + 3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (issuer) {
+          if (cbase < p.split_c) tma_store_4d(&tmC0, stage, cbase, w0, h0, img);
+          else                   tma_store_4d(&tmC1, stage, cbase - p.split_c, w0, h0, img);
+          tma_store_commit();
+        }
+        sbuf ^= 1u;
+      }
+      if (++as == 2) { as = 0; pacc ^= 1u; }
+    }
+    if (issuer) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ----------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------
+template <int BN, int TAPS, int SA, int SB>
+static int launch_cfg(const ConvLaunch& a, cudaStream_t st) {
+  using Cfg = ConvCfg<BN, TAPS, SA, SB>;
+  auto kern = conv_igemm_kernel<BN, TAPS, SA, SB>;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return set_error(B2U_ERR_CUDA, "cudaFuncSetAttribute(conv): %s", cudaGetErrorString(e));
+    attr_done[dev] = true;
+  }
+  const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B;
+  const int a_box_h = TAPS == 9 ? kHb + 2 : kHb;
+  CUtensorMap tmA0, tmA1, tmB, tmC0, tmC1;
+  int rc;
+  if ((rc = make_tmap_nhwc(&tmA0, a.x0, a.N, a.H, a.W, a.C0, KB, kWb, a_box_h, swz))) return rc;
+  if (a.C1 > 0) {
+    if ((rc = make_tmap_nhwc(&tmA1, a.x1, a.N, a.H, a.W, a.C1, KB, kWb, a_box_h, swz))) return rc;
+  } else {
+    tmA1 = tmA0;
+  }
+  const int ctot = a.C0 + a.C1;
+  if ((rc = make_tmap_2d(&tmB, a.wpacked, (uint64_t)TAPS * ctot, a.Cout, KB, BN, swz))) return rc;
+  const int split = (a.y1 != nullptr) ? a.split_c : a.Cout;
+  if ((rc = make_tmap_nhwc(&tmC0, a.y0, a.N, a.H, a.W, split, 64, kWb, kHb, swz))) return rc;
+  if (a.y1 != nullptr) {
+    if ((rc = make_tmap_nhwc(&tmC1, a.y1, a.N, a.H, a.W, a.Cout - split, 64, kWb, kHb, swz))) return rc;
+  } else {
+    tmC1 = tmC0;
+  }
+  ConvParams p;
+  p.N = a.N; p.H = a.H; p.W = a.W; p.C0 = a.C0; p.C1 = a.C1; p.Cout = a.Cout;
+  p.tiles_w = (a.W + kWb - 1) / kWb;
+  p.tiles_h = (a.H + kHb - 1) / kHb;
+  p.num_m_tiles = a.N * p.tiles_h * p.tiles_w;
+  p.num_n_tiles = a.Cout / BN;
+  p.split_c = split;
+  p.flags = a.flags;
+  p.bias = a.bias;
+  p.mask = a.mask;
+  p.mask_c = a.mask_c;
+  const int total = p.num_m_tiles * p.num_n_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  kern<<<grid, 192, Cfg::kSmemBytes, st>>>(tmA0, tmA1, tmB, tmC0, tmC1, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(B2U_ERR_CUDA, "conv_igemm launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int launch_conv(const ConvLaunch& a, cudaStream_t st) {
+  const int ctot = a.C0 + a.C1;
+  if (a.N <= 0 || a.H <= 0 || a.W <= 0) return set_error(B2U_ERR_SHAPE, "conv: empty tensor");
+  if (a.taps != 9 && a.taps != 1) return set_error(B2U_ERR_SHAPE, "conv: taps must be 9 or 1");
+  if (a.Cout > kMaxCout || a.Cout <= 0) return set_error(B2U_ERR_SHAPE, "conv: Cout %d outside (0,%d]", a.Cout, kMaxCout);
+  if (a.Cout % 64 != 0) return set_error(B2U_ERR_SHAPE, "conv: Cout %d must be a multiple of 64", a.Cout);
+  if ((a.flags & 2) && (a.mask == nullptr || a.mask_c % 8 != 0 || a.mask_c < a.Cout))
+    return set_error(B2U_ERR_SHAPE, "conv: mask flag needs a mask tensor with >= Cout channels, %% 8 == 0");
+  if (ctot <= 0 || a.C0 % 64 != 0 || a.C1 % 64 != 0)
+    return set_error(B2U_ERR_SHAPE, "conv: input channels (%d,%d) must be multiples of 64", a.C0, a.C1);
+  if (a.y1 != nullptr && (a.split_c <= 0 || a.split_c >= a.Cout || a.split_c % 64 != 0))
+    return set_error(B2U_ERR_SHAPE, "conv: split_c %d must be a multiple of 64 inside (0,Cout)", a.split_c);
+  int bn = 0;
+  if (a.bn_override) {
+    if (a.Cout % a.bn_override != 0) return set_error(B2U_ERR_SHAPE, "conv: bn_override does not divide Cout");
+    bn = a.bn_override;
+  } else if (a.Cout % 256 == 0) bn = 256;
+  else if (a.Cout % 192 == 0) bn = 192;
+  else if (a.Cout % 128 == 0) bn = 128;
+  else bn = 64;
+
+  if (a.taps == 9) {
+    switch (bn) {
+      case 256: return launch_cfg<256, 9, 3, 4>(a, st);
+      case 192: return launch_cfg<192, 9, 3, 5>(a, st);
+      case 128: return launch_cfg<128, 9, 3, 8>(a, st);
+      case 64:  return launch_cfg<64, 9, 4, 12>(a, st);
+    }
+  } else {
+    switch (bn) {
+      case 256: return launch_cfg<256, 1, 3, 3>(a, st);
+      case 192: return launch_cfg<192, 1, 4, 4>(a, st);
+      case 128: return launch_cfg<128, 1, 4, 4>(a, st);
+      case 64:  return launch_cfg<64, 1, 4, 4>(a, st);
+    }
+  }
+  return set_error(B2U_ERR_SHAPE, "conv: unsupported N tile %d", bn);
+}
+
+}  // namespace b2u
+
+// ----------------------------------------------------------------------------
+// C ABI (include/b2u.h)
+// ----------------------------------------------------------------------------
+extern "C" {
+
+int b2u_conv_fprop(const void* x0, int C0, const void* x1, int C1, const void* wf, const float* bias, void* y, int N,
+                   int H, int W, int Cout, int taps, int relu, int bn_override, void* stream) {
+  b2u::ConvLaunch a;
+  a.x0 = x0; a.C0 = C0; a.x1 = x1; a.C1 = x1 ? C1 : 0;
+  a.wpacked = wf; a.bias = bias; a.y0 = y;
+  a.N = N; a.H = H; a.W = W; a.Cout = Cout; a.taps = taps;
+  a.flags = relu ? 1 : 0;
+  a.bn_override = bn_override;
+  return b2u::launch_conv(a, static_cast<cudaStream_t>(stream));
+}
+
+// dx = conv(dz, flipped/transposed weights); channels [0,C0) -> dx0, [C0,C0+C1) -> dx1 (optional).
+// `mask` (NHWC bf16, C0 channels, only when dx1 == NULL): dx0 is zeroed where mask <= 0 (ReLU backward).
+int b2u_conv_dgrad(const void* dz, int Cz, const void* wd, void* dx0, int C0, void* dx1, int C1, const void* mask,
+                   int N, int H, int W, int taps, int bn_override, void* stream) {
+  b2u::ConvLaunch a;
+  a.x0 = dz; a.C0 = Cz;
+  a.wpacked = wd; a.bias = nullptr;
+  a.y0 = dx0; a.y1 = dx1; a.split_c = C0;
+  a.N = N; a.H = H; a.W = W; a.Cout = C0 + (dx1 ? C1 : 0); a.taps = taps;
+  a.flags = 0;
+  if (mask) {
+    if (dx1) return b2u::set_error(B2U_ERR_ARG, "dgrad: mask is only supported with a single output");
+    a.flags = 2; a.mask = static_cast<const __nv_bfloat16*>(mask); a.mask_c = C0;
+  }
+  a.bn_override = bn_override;
+  return b2u::launch_conv(a, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,366 @@
+// conv_wgrad.cu -- weight gradient of the 3x3 (pad 1) / 1x1 convolutions for sm_100a.
+//
+//   dW[co][(r,s)][ci] = sum_{n,h,w} dz[n,h,w,co] * x[n,h+r-1,w+s-1,ci]
+//
+// Replaces the autograd wgrad (cuDNN bwd-filter) behind loss.backward() in the reference
+// (utils_fit.py:92) for nn.Conv2d at nets/vgg.py:53, nets/unet.py:11-12.
+//
+// GEMM view: M = 128 output channels (rows of dz, MN-major), N = 3 vertical taps x 64 input
+// channels, K = pixels.  Both operands are NHWC (channels contiguous) so both are "MN-major"
+// UMMA operands: a TMA box [pixels][64 ch] with 128B swizzle IS the canonical MN-major SW128
+// tile (row = one K index, 8 rows = one swizzle atom).
+//   * K block = a 16(w) x 8(h) pixel patch; one tcgen05.mma (K=16) consumes one image row of the
+//     patch: A = dz rows [j*16, j*16+16), B = x box rows [(j+r)*16, ...) for r = 0..2.
+//   * The three vertical taps are ONE instruction with N = 192: the B descriptor's leading-dim
+//     byte offset (distance between 64-channel MN atoms) is set to one image row of the box
+//     (16 px * 128 B = 2048 B), so "atom r" is the same box shifted down by r rows.
+//   * The horizontal taps s are separate work units (separate TMA boxes shifted by s-1).
+//   * Work unit = (cout block, cin block, s, K split); fp32 partial sums go to a workspace
+//     [split][Cout][taps][Cin]; wgrad_reduce sums the splits and writes OIHW fp32 (deterministic).
+//   * Warp roles: warp0 TMA producer, warp1 MMA issuer, warps 2..5 epilogue (TMEM -> global).
+#include "b2u_internal.h"
+#include "b2u_ptx.cuh"
+
+namespace b2u {
+
+constexpr int kWb = 16, kHb = 8;
+
+struct WgradParams {
+  int N, H, W;
+  int C0, C1, Cout;
+  int tiles_w, tiles_h, kblocks;   // kblocks = N * tiles_h * tiles_w
+  int num_mblk, num_cblk, splits, units;
+  int merged;                      // 1: N=192 merged vertical taps; 0: three N=64 instructions
+  float* partial;                  // [splits][Cout][taps][C0+C1]
+};
+
+template <int TAPS, int STAGES>
+struct WgCfg {
+  static constexpr int kXRows = (TAPS == 9 ? kHb + 2 : kHb) * kWb;
+  static constexpr int kXBytes = kXRows * 128;
+  static constexpr int kDzHalf = kHb * kWb * 128;       // 64 couts x 128 px
+  static constexpr int kDzBytes = 2 * kDzHalf;
+  static constexpr int kStage = kDzBytes + kXBytes;
+  static constexpr int kOffBar = STAGES * kStage;
+  static constexpr int kNumBar = 2 * STAGES + 4;
+  static constexpr int kOffTmem = kOffBar + kNumBar * 8;
+  static constexpr int kSmemBytes = kOffTmem + 16 + 1024;
+  static constexpr int kAccN = TAPS == 9 ? 192 : 64;    // accumulator columns per unit
+  static constexpr int kTmemCols = TAPS == 9 ? 512 : 128;
+  static constexpr int kAccStride = kTmemCols / 2;
+  static_assert(kStage % 1024 == 0, "stage alignment");
+  static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
+};
+
+template <int TAPS, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
+                  const __grid_constant__ CUtensorMap tmDZ, const WgradParams p) {
+  using Cfg = WgCfg<TAPS, STAGES>;
+  constexpr int S_TAPS = TAPS == 9 ? 3 : 1;
+  constexpr int R_TAPS = TAPS == 9 ? 3 : 1;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bars = smem_base + Cfg::kOffBar;
+  auto full = [&](int i) { return bars + 8u * i; };
+  auto empty = [&](int i) { return bars + 8u * (STAGES + i); };
+  auto t_full = [&](int i) { return bars + 8u * (2 * STAGES + i); };
+  auto t_empty = [&](int i) { return bars + 8u * (2 * STAGES + 2 + i); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kOffTmem);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX0);
+    tma_prefetch_desc(&tmX1);
+    tma_prefetch_desc(&tmDZ);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(t_full(i), 1); mbar_init(t_empty(i), 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int ctot = p.C0 + p.C1;
+  const bool two_halves = p.Cout >= 128;   // cout block = 128 (two 64-channel boxes) or 64
+
+  // unit -> (split, mblk, cblk, s); units sharing the dz tile (same split, mblk) are adjacent
+  auto decode = [&](int unit, int& split, int& mblk, int& cblk, int& s) {
+    s = unit % S_TAPS; unit /= S_TAPS;
+    cblk = unit % p.num_cblk; unit /= p.num_cblk;
+    mblk = unit % p.num_mblk;
+    split = unit / p.num_mblk;
+  };
+  auto krange = [&](int split, int& k0, int& k1) {
+    const long long kb = p.kblocks;
+    k0 = static_cast<int>(kb * split / p.splits);
+    k1 = static_cast<int>(kb * (split + 1) / p.splits);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0;
+      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+        int split, mblk, cblk, s, k0, k1;
+        decode(unit, split, mblk, cblk, s);
+        krange(split, k0, k1);
+        const int cin0 = cblk * 64;
+        const CUtensorMap* tmx = cin0 < p.C0 ? &tmX0 : &tmX1;
+        const int cx = cin0 < p.C0 ? cin0 : cin0 - p.C0;
+        const int co0 = mblk * 128;
+        for (int kb = k0; kb < k1; ++kb) {
+          int t = kb;
+          const int tw = t % p.tiles_w; t /= p.tiles_w;
+          const int th = t % p.tiles_h;
+          const int img = t / p.tiles_h;
+          const int w0 = tw * kWb, h0 = th * kHb;
+          mbar_wait(empty(st), ph ^ 1u);
+          const uint32_t base = smem_base + st * Cfg::kStage;
+          mbar_expect_tx(full(st), (two_halves ? Cfg::kDzBytes : Cfg::kDzHalf) + Cfg::kXBytes);
+          tma_load_4d(base, &tmDZ, full(st), co0, w0, h0, img);
+          if (two_halves) tma_load_4d(base + Cfg::kDzHalf, &tmDZ, full(st), co0 + 64, w0, h0, img);
+          if (TAPS == 9) tma_load_4d(base + Cfg::kDzBytes, tmx, full(st), cx, w0 + s - 1, h0 - 1, img);
+          else           tma_load_4d(base + Cfg::kDzBytes, tmx, full(st), cx, w0, h0, img);
+          if (++st == STAGES) { st = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // A = dz (M x K, MN-major), B = x (N x K, MN-major)
+      constexpr uint32_t idesc_merged = umma_idesc_bf16(128, Cfg::kAccN, 1, 1);
+      constexpr uint32_t idesc_single = umma_idesc_bf16(128, 64, 1, 1);
+      const uint32_t lbo_a = two_halves ? Cfg::kDzHalf : 0u;   // Cout == 64: rows 64..127 alias rows 0..63
+      int st = 0, as = 0; uint32_t ph = 0, pacc = 0;
+      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+        int split, mblk, cblk, s, k0, k1;
+        decode(unit, split, mblk, cblk, s);
+        krange(split, k0, k1);
+        mbar_wait(t_empty(as), pacc ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * Cfg::kAccStride);
+        uint32_t acc = 0;
+        for (int kb = k0; kb < k1; ++kb) {
+          mbar_wait(full(st), ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_base + st * Cfg::kStage;
+          const uint32_t b_base = a_base + Cfg::kDzBytes;
+#pragma unroll
+          for (int j = 0; j < kHb; ++j) {
+            const uint64_t ad = umma_smem_desc(a_base + j * 2048, lbo_a, 1024, 2u);
+            if (TAPS == 1 || p.merged) {
+              const uint64_t bd = umma_smem_desc(b_base + j * 2048, 2048, 1024, 2u);
+              tc_mma_bf16(d_tmem, ad, bd, idesc_merged, acc);
+            } else {
+#pragma unroll
+              for (int r = 0; r < R_TAPS; ++r) {
+                const uint64_t bd = umma_smem_desc(b_base + (j + r) * 2048, 2048, 1024, 2u);
+                tc_mma_bf16(d_tmem + r * 64, ad, bd, idesc_single, acc);
+              }
+            }
+            acc = 1;
+          }
+          tc_commit(empty(st));
+          if (++st == STAGES) { st = 0; ph ^= 1u; }
+        }
+        if (k1 <= k0) {
+          // empty K range (more splits than K blocks): nothing was accumulated; the epilogue writes zeros
+        }
+        tc_commit(t_full(as));
+        if (++as == 2) { as = 0; pacc ^= 1u; }
+      }
+    }
+  } else {
+    const int ew = warp & 3;
+    int as = 0; uint32_t pacc = 0;
+    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+      int split, mblk, cblk, s, k0, k1;
+      decode(unit, split, mblk, cblk, s);
+      krange(split, k0, k1);
+      mbar_wait(t_full(as), pacc);
+      tc_fence_after();
+      const int co = mblk * 128 + ew * 32 + lane;
+      const bool valid = co < p.Cout && (two_halves || ew < 2);
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(as * Cfg::kAccStride);
+#pragma unroll 1
+      for (int c32 = 0; c32 < Cfg::kAccN / 32; ++c32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + c32 * 32, v);
+        tmem_ld_wait();
+        if (valid) {
+          const int r = (c32 * 32) / 64;
+          const int ci = cblk * 64 + (c32 * 32) % 64;
+          const int tap = r * S_TAPS + s;
+          float4* dst = reinterpret_cast<float4*>(
+              p.partial + ((static_cast<size_t>(split) * p.Cout + co) * TAPS + tap) * ctot + ci);
+          const bool nz = k1 > k0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 o;
+            o.x = nz ? __uint_as_float(v[q * 4 + 0]) : 0.f;
+            o.y = nz ? __uint_as_float(v[q * 4 + 1]) : 0.f;
+            o.z = nz ? __uint_as_float(v[q * 4 + 2]) : 0.f;
+            o.w = nz ? __uint_as_float(v[q * 4 + 3]) : 0.f;
+            dst[q] = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty(as));
+      if (++as == 2) { as = 0; pacc ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// out[co][ci][r][s] (OIHW fp32) = sum_split partial[split][co][tap][ci]; one thread per (co, ci).
+// cin_real < cin_pitch handles the first layer (im2col columns k = tap*cin_real + c, see layout.cu).
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int Cout,
+                                    int taps, int cin_pitch, int cin_real, int first_layer) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Cout * cin_real) return;
+  const int co = idx / cin_real, ci = idx % cin_real;
+  const size_t split_stride = static_cast<size_t>(Cout) * (first_layer ? 1 : taps) * cin_pitch;
+  if (!first_layer) {
+    for (int t = 0; t < taps; ++t) {
+      const float* src = partial + (static_cast<size_t>(co) * taps + t) * cin_pitch + ci;
+      float acc = 0.f;
+      for (int s = 0; s < splits; ++s) acc += src[s * split_stride];
+      dw[(static_cast<size_t>(co) * cin_real + ci) * taps + t] = acc;
+    }
+  } else {
+    // partial is [split][Cout][1][cin_pitch] with column k = tap*cin_real + ci
+    for (int t = 0; t < taps; ++t) {
+      const float* src = partial + static_cast<size_t>(co) * cin_pitch + t * cin_real + ci;
+      float acc = 0.f;
+      for (int s = 0; s < splits; ++s) acc += src[s * split_stride];
+      dw[(static_cast<size_t>(co) * cin_real + ci) * taps + t] = acc;
+    }
+  }
+}
+
+static int choose_splits(int base_units, int kblocks) {
+  const int sms = num_sms();
+  int splits = (2 * sms + base_units - 1) / base_units;
+  if (splits > kblocks) splits = kblocks;
+  if (splits < 1) splits = 1;
+  return splits;
+}
+
+struct WgradPlan {
+  int num_mblk, num_cblk, s_taps, splits, units, kblocks;
+  size_t ws_bytes;
+};
+
+static WgradPlan plan_wgrad(int N, int H, int W, int Cin_tot, int Cout, int taps) {
+  WgradPlan pl;
+  pl.num_mblk = (Cout + 127) / 128;
+  pl.num_cblk = Cin_tot / 64;
+  pl.s_taps = taps == 9 ? 3 : 1;
+  const int tiles_w = (W + kWb - 1) / kWb, tiles_h = (H + kHb - 1) / kHb;
+  pl.kblocks = N * tiles_h * tiles_w;
+  const int base = pl.num_mblk * pl.num_cblk * pl.s_taps;
+  pl.splits = choose_splits(base, pl.kblocks);
+  pl.units = base * pl.splits;
+  pl.ws_bytes = static_cast<size_t>(pl.splits) * Cout * taps * Cin_tot * sizeof(float);
+  return pl;
+}
+
+template <int TAPS, int STAGES>
+static int launch_wgrad_cfg(const void* x0, int C0, const void* x1, int C1, const void* dz, int Cout, float* partial,
+                            const WgradPlan& pl, int N, int H, int W, int merged, cudaStream_t st) {
+  using Cfg = WgCfg<TAPS, STAGES>;
+  auto kern = conv_wgrad_kernel<TAPS, STAGES>;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return set_error(B2U_ERR_CUDA, "cudaFuncSetAttribute(wgrad): %s", cudaGetErrorString(e));
+    attr_done[dev] = true;
+  }
+  const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B;
+  const int x_box_h = TAPS == 9 ? kHb + 2 : kHb;
+  CUtensorMap tmX0, tmX1, tmDZ;
+  int rc;
+  if ((rc = make_tmap_nhwc(&tmX0, x0, N, H, W, C0, 64, kWb, x_box_h, swz))) return rc;
+  if (C1 > 0) {
+    if ((rc = make_tmap_nhwc(&tmX1, x1, N, H, W, C1, 64, kWb, x_box_h, swz))) return rc;
+  } else {
+    tmX1 = tmX0;
+  }
+  if ((rc = make_tmap_nhwc(&tmDZ, dz, N, H, W, Cout, 64, kWb, kHb, swz))) return rc;
+  WgradParams p;
+  p.N = N; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.Cout = Cout;
+  p.tiles_w = (W + kWb - 1) / kWb; p.tiles_h = (H + kHb - 1) / kHb; p.kblocks = pl.kblocks;
+  p.num_mblk = pl.num_mblk; p.num_cblk = pl.num_cblk; p.splits = pl.splits; p.units = pl.units;
+  p.merged = merged;
+  p.partial = partial;
+  const int grid = pl.units < num_sms() ? pl.units : num_sms();
+  kern<<<grid, 192, Cfg::kSmemBytes, st>>>(tmX0, tmX1, tmDZ, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(B2U_ERR_CUDA, "conv_wgrad launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace b2u
+
+extern "C" {
+
+size_t b2u_conv_wgrad_workspace(int N, int H, int W, int Cin_tot, int Cout, int taps) {
+  if (N <= 0 || H <= 0 || W <= 0 || Cin_tot <= 0 || Cout <= 0) return 0;
+  return b2u::plan_wgrad(N, H, W, Cin_tot, Cout, taps).ws_bytes;
+}
+
+// dw: OIHW fp32 [Cout][cin_real][taps]  (cin_real = C0+C1 unless first_cin > 0)
+// first_cin > 0: x0 is the first layer's im2col tensor [N,H,W,64] (taps must be 1, C0 == 64, C1 == 0);
+//                dw then is [Cout][first_cin][3][3].
+// flags bit0: use three N=64 instructions per image row instead of the merged N=192 one.
+int b2u_conv_wgrad(const void* x0, int C0, const void* x1, int C1, const void* dz, int Cout, float* dw, void* ws,
+                   size_t ws_bytes, int N, int H, int W, int taps, int first_cin, int flags, void* stream) {
+  using namespace b2u;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!x1) C1 = 0;
+  const int ctot = C0 + C1;
+  if (N <= 0 || H <= 0 || W <= 0) return set_error(B2U_ERR_SHAPE, "wgrad: empty tensor");
+  if (taps != 9 && taps != 1) return set_error(B2U_ERR_SHAPE, "wgrad: taps must be 9 or 1");
+  if (C0 % 64 != 0 || C1 % 64 != 0 || ctot <= 0)
+    return set_error(B2U_ERR_SHAPE, "wgrad: input channels (%d,%d) must be multiples of 64", C0, C1);
+  if (Cout != 64 && Cout % 128 != 0) return set_error(B2U_ERR_SHAPE, "wgrad: Cout %d must be 64 or a multiple of 128", Cout);
+  if (first_cin > 0 && (taps != 1 || C0 != 64 || C1 != 0 || 9 * first_cin > 64))
+    return set_error(B2U_ERR_SHAPE, "wgrad: first-layer mode needs taps=1, C0=64, C1=0, 9*cin<=64");
+  const WgradPlan pl = plan_wgrad(N, H, W, ctot, Cout, taps);
+  if (ws == nullptr || ws_bytes < pl.ws_bytes)
+    return set_error(B2U_ERR_ARG, "wgrad: workspace %zu bytes < required %zu", ws_bytes, pl.ws_bytes);
+  int rc;
+  const int merged = (flags & 1) ? 0 : 1;
+  if (taps == 9) rc = launch_wgrad_cfg<9, 4>(x0, C0, x1, C1, dz, Cout, static_cast<float*>(ws), pl, N, H, W, merged, st);
+  else           rc = launch_wgrad_cfg<1, 4>(x0, C0, x1, C1, dz, Cout, static_cast<float*>(ws), pl, N, H, W, merged, st);
+  if (rc) return rc;
+  const int cin_real = first_cin > 0 ? first_cin : ctot;
+  const int rtaps = first_cin > 0 ? 9 : taps;
+  const int total = Cout * cin_real;
+  wgrad_reduce_kernel<<<(total + 127) / 128, 128, 0, st>>>(static_cast<const float*>(ws), dw, pl.splits, Cout, rtaps, ctot,
+                                                           cin_real, first_cin > 0 ? 1 : 0);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(B2U_ERR_CUDA, "wgrad_reduce launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+}  // extern "C"

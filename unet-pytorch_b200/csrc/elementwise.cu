@@ -1,0 +1,451 @@
+// elementwise.cu -- the HBM-bound kernels of the UNet hot path (NHWC bf16, 16-byte vectors = 8 channels).
+//
+//   im2col_first   : NCHW fp32 image -> [N,H,W,64] bf16 im2col rows of the first 3x3 conv (nets/vgg.py:53, C_in = 3)
+//   pack_weights   : OIHW fp32 -> K-major bf16 [Cout][tap*Cin] (fprop) and [Cin][tap'*Cout] flipped (dgrad)
+//   maxpool2x2     : nn.MaxPool2d(2,2) fwd / bwd (nets/vgg.py:51); bwd recomputes the arg-max (first max in
+//                    row-major window order, like ATen), adds the skip-connection gradient and applies the
+//                    ReLU mask of the pooled tensor's producer in one pass
+//   upsample2x     : nn.UpsamplingBilinear2d(scale_factor=2) = bilinear, align_corners=True (nets/unet.py:13)
+//                    fwd, and its adjoint in gather form fused with the ReLU mask of the low-res producer
+//   bias_grad      : db[c] = sum over pixels of dz
+//   nhwc<->nchw    : layout converters for the module boundary
+#include "b2u_internal.h"
+#include "b2u_ptx.cuh"
+
+namespace b2u {
+
+static inline int grid_for(long long n, int block) {
+  long long g = (n + block - 1) / block;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+#define B2U_CHECK_LAUNCH(name)                                                                           \
+  do {                                                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                                \
+    if (e__ != cudaSuccess) return b2u::set_error(B2U_ERR_CUDA, name " launch: %s", cudaGetErrorString(e__)); \
+  } while (0)
+
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 v;
+  v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+  v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// first-layer im2col: col[n,h,w,k] = x[n,c,h+r-1,w+s-1] for k = (r*3+s)*Cin + c < 9*Cin, else 0
+// ---------------------------------------------------------------------------------------------
+__global__ void im2col_first_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int Cin, int H,
+                                    int W) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // (pixel, chunk of 8 k)
+  const long long total = static_cast<long long>(N) * H * W * 8;
+  if (idx >= total) return;
+  const int chunk = static_cast<int>(idx & 7);
+  long long pix = idx >> 3;
+  const int w = static_cast<int>(pix % W); pix /= W;
+  const int h = static_cast<int>(pix % H);
+  const int n = static_cast<int>(pix / H);
+  float f[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = chunk * 8 + e;
+    float v = 0.f;
+    if (k < 9 * Cin) {
+      const int tap = k / Cin, c = k % Cin;
+      const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(x + ((static_cast<size_t>(n) * Cin + c) * H + hh) * W + ww);
+    }
+    f[e] = v;
+  }
+  reinterpret_cast<uint4*>(col)[idx] = pack8(f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing
+// ---------------------------------------------------------------------------------------------
+// wf[co][tap*Cin + ci] = w[co][ci][tap];  wd[ci][tap*Cout + co] = w[co][ci][taps-1-tap]
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                    __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int taps) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(Cout) * Cin * taps;
+  if (idx >= total) return;
+  // idx enumerates the fprop layout (coalesced writes to wf)
+  const int ci = static_cast<int>(idx % Cin);
+  const int tap = static_cast<int>((idx / Cin) % taps);
+  const int co = static_cast<int>(idx / (static_cast<long long>(Cin) * taps));
+  const float v = w[(static_cast<size_t>(co) * Cin + ci) * taps + tap];
+  const __nv_bfloat16 b = __float2bfloat16_rn(v);
+  if (wf) wf[idx] = b;
+  if (wd) wd[(static_cast<size_t>(ci) * taps + (taps - 1 - tap)) * Cout + co] = b;
+}
+// first layer: wf[co][k] for k = tap*Cin + c (k < 9*Cin), zero padded to 64 columns
+__global__ void pack_weights_first_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, int Cout, int Cin) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Cout * 64) return;
+  const int co = idx / 64, k = idx % 64;
+  float v = 0.f;
+  if (k < 9 * Cin) {
+    const int tap = k / Cin, c = k % Cin;
+    v = w[(static_cast<size_t>(co) * Cin + c) * 9 + tap];
+  }
+  wf[idx] = __float2bfloat16_rn(v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// maxpool 2x2 stride 2
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t max2_bf16(uint32_t a, uint32_t b) {
+  __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&a);
+  __nv_bfloat162 y = *reinterpret_cast<__nv_bfloat162*>(&b);
+  __nv_bfloat162 m = __hmax2(x, y);
+  return *reinterpret_cast<uint32_t*>(&m);
+}
+__global__ void maxpool2x2_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int C8) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(N) * Ho * Wo * C8;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % C8);
+  long long t = idx / C8;
+  const int wo = static_cast<int>(t % Wo); t /= Wo;
+  const int ho = static_cast<int>(t % Ho);
+  const int n = static_cast<int>(t / Ho);
+  const size_t base = ((static_cast<size_t>(n) * H + 2 * ho) * W + 2 * wo) * C8 + c;
+  const uint4 a = __ldg(x + base), b = __ldg(x + base + C8);
+  const uint4 d = __ldg(x + base + static_cast<size_t>(W) * C8), e = __ldg(x + base + static_cast<size_t>(W) * C8 + C8);
+  uint4 m;
+  m.x = max2_bf16(max2_bf16(a.x, b.x), max2_bf16(d.x, e.x));
+  m.y = max2_bf16(max2_bf16(a.y, b.y), max2_bf16(d.y, e.y));
+  m.z = max2_bf16(max2_bf16(a.z, b.z), max2_bf16(d.z, e.z));
+  m.w = max2_bf16(max2_bf16(a.w, b.w), max2_bf16(d.w, e.w));
+  y[idx] = m;
+}
+
+// dz[pos] = ((pos == argmax ? dpool : 0) + dskip[pos]) * (y[pos] > 0)   for the 4 positions of each window
+__global__ void maxpool2x2_bwd_kernel(const uint4* __restrict__ dpool, const uint4* __restrict__ dskip,
+                                      const uint4* __restrict__ y, uint4* __restrict__ dz, int N, int H, int W, int C8,
+                                      int use_mask) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(N) * Ho * Wo * C8;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % C8);
+  long long t = idx / C8;
+  const int wo = static_cast<int>(t % Wo); t /= Wo;
+  const int ho = static_cast<int>(t % Ho);
+  const int n = static_cast<int>(t / Ho);
+  const size_t base = ((static_cast<size_t>(n) * H + 2 * ho) * W + 2 * wo) * C8 + c;
+  const size_t off[4] = {base, base + C8, base + static_cast<size_t>(W) * C8, base + static_cast<size_t>(W) * C8 + C8};
+  float yv[4][8], g[8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) unpack8(__ldg(y + off[q]), yv[q]);
+  unpack8(__ldg(dpool + idx), g);
+  int amax[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    int a = 0; float m = yv[0][e];
+#pragma unroll
+    for (int q = 1; q < 4; ++q) if (yv[q][e] > m) { m = yv[q][e]; a = q; }
+    amax[e] = a;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float o[8], sk[8];
+    if (dskip) unpack8(__ldg(dskip + off[q]), sk);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = (amax[e] == q ? g[e] : 0.f) + (dskip ? sk[e] : 0.f);
+      if (use_mask && !(yv[q][e] > 0.f)) v = 0.f;
+      o[e] = v;
+    }
+    dz[off[q]] = pack8(o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bilinear 2x upsample, align_corners=True
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void src_index(int o, float scale, int in_size, int& i0, int& i1, float& lam) {
+  const float src = scale * static_cast<float>(o);   // ATen area_pixel_compute_source_index(align_corners=True)
+  i0 = static_cast<int>(src);
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  lam = src - static_cast<float>(i0);
+}
+__global__ void upsample2x_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int C8,
+                                      float sh, float sw) {
+  const int Ho = 2 * H, Wo = 2 * W;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(N) * Ho * Wo * C8;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % C8);
+  long long t = idx / C8;
+  const int wo = static_cast<int>(t % Wo); t /= Wo;
+  const int ho = static_cast<int>(t % Ho);
+  const int n = static_cast<int>(t / Ho);
+  int h0, h1, w0, w1; float lh, lw;
+  src_index(ho, sh, H, h0, h1, lh);
+  src_index(wo, sw, W, w0, w1, lw);
+  const size_t img = static_cast<size_t>(n) * H * W;
+  float a[8], b[8], d[8], e[8], o[8];
+  unpack8(__ldg(x + (img + static_cast<size_t>(h0) * W + w0) * C8 + c), a);
+  unpack8(__ldg(x + (img + static_cast<size_t>(h0) * W + w1) * C8 + c), b);
+  unpack8(__ldg(x + (img + static_cast<size_t>(h1) * W + w0) * C8 + c), d);
+  unpack8(__ldg(x + (img + static_cast<size_t>(h1) * W + w1) * C8 + c), e);
+  const float h0l = 1.f - lh, w0l = 1.f - lw;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) o[k] = h0l * (w0l * a[k] + lw * b[k]) + lh * (w0l * d[k] + lw * e[k]);
+  y[idx] = pack8(o);
+}
+
+// adjoint: dlow[h,w] = sum over output pixels (ho,wo) of weight(ho->h) * weight(wo->w) * dup[ho,wo], then ReLU mask
+__global__ void upsample2x_bwd_kernel(const uint4* __restrict__ dup, const uint4* __restrict__ ylow,
+                                      uint4* __restrict__ dlow, int N, int H, int W, int C8, float sh, float sw,
+                                      float inv_sh, float inv_sw) {
+  const int Ho = 2 * H, Wo = 2 * W;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(N) * H * W * C8;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % C8);
+  long long t = idx / C8;
+  const int w = static_cast<int>(t % W); t /= W;
+  const int h = static_cast<int>(t % H);
+  const int n = static_cast<int>(t / H);
+  // candidate outputs: src in (h-1, h+1)  ->  o in ((h-1)/s, (h+1)/s); pad by one on each side
+  int ho_lo = static_cast<int>(floorf((h - 1) * inv_sh)) - 1; if (ho_lo < 0) ho_lo = 0;
+  int ho_hi = static_cast<int>(ceilf((h + 1) * inv_sh)) + 1;  if (ho_hi > Ho - 1) ho_hi = Ho - 1;
+  int wo_lo = static_cast<int>(floorf((w - 1) * inv_sw)) - 1; if (wo_lo < 0) wo_lo = 0;
+  int wo_hi = static_cast<int>(ceilf((w + 1) * inv_sw)) + 1;  if (wo_hi > Wo - 1) wo_hi = Wo - 1;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const size_t img = static_cast<size_t>(n) * Ho * Wo;
+  for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+    int h0, h1; float lh;
+    src_index(ho, sh, H, h0, h1, lh);
+    float wh = 0.f;
+    if (h0 == h) wh += 1.f - lh;
+    if (h1 == h) wh += lh;
+    if (wh == 0.f) continue;
+    for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+      int w0, w1; float lw;
+      src_index(wo, sw, W, w0, w1, lw);
+      float ww = 0.f;
+      if (w0 == w) ww += 1.f - lw;
+      if (w1 == w) ww += lw;
+      if (ww == 0.f) continue;
+      float g[8];
+      unpack8(__ldg(dup + (img + static_cast<size_t>(ho) * Wo + wo) * C8 + c), g);
+      const float wt = wh * ww;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += wt * g[k];
+    }
+  }
+  if (ylow) {
+    float m[8];
+    unpack8(__ldg(ylow + idx), m);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if (!(m[k] > 0.f)) acc[k] = 0.f;
+  }
+  dlow[idx] = pack8(acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// bias gradient: db[c] = sum_p dz[p][c]; stage 1 -> partial[block][C], stage 2 sums the blocks
+// ---------------------------------------------------------------------------------------------
+__global__ void bias_grad_partial_kernel(const uint4* __restrict__ dz, float* __restrict__ partial, long long P, int C8) {
+  // blockDim.x = 256; thread -> (row lane, channel chunk): chunks = C8, rows per block pass = 256 / C8'
+  extern __shared__ float sred[];
+  const int tid = threadIdx.x;
+  const int cpt = C8 < 256 ? C8 : 256;           // chunk columns handled concurrently
+  const int rows = 256 / cpt;
+  const int cc = tid % cpt, rr = tid / cpt;
+  for (int c0 = 0; c0 < C8; c0 += cpt) {
+    const int c = c0 + cc;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (c < C8 && rr < rows) {
+      for (long long p = static_cast<long long>(blockIdx.x) * rows + rr; p < P; p += static_cast<long long>(gridDim.x) * rows) {
+        float f[8];
+        unpack8(__ldg(dz + p * C8 + c), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += f[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sred[tid * 8 + k] = acc[k];
+    __syncthreads();
+    if (rr == 0 && c < C8) {
+      for (int r = 1; r < rows; ++r)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += sred[(r * cpt + cc) * 8 + k];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) partial[static_cast<size_t>(blockIdx.x) * C8 * 8 + c * 8 + k] = acc[k];
+    }
+    __syncthreads();
+  }
+}
+__global__ void reduce_rows_kernel(const float* __restrict__ partial, float* __restrict__ out, int rows, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L) return;
+  float acc = 0.f;
+  for (int r = 0; r < rows; ++r) acc += partial[static_cast<size_t>(r) * L + i];
+  out[i] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout converters at the module boundary
+// ---------------------------------------------------------------------------------------------
+// NHWC bf16 [N,H,W,C] -> NCHW fp32; tile transpose through shared memory
+__global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int C,
+                                             long long HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long p0 = static_cast<long long>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long p = p0 + i; const int c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (p < HW && c < C) ? __bfloat162float(x[(static_cast<size_t>(n) * HW + p) * C + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i; const long long p = p0 + threadIdx.x;
+    if (p < HW && c < C) y[(static_cast<size_t>(n) * C + c) * HW + p] = tile[threadIdx.x][i];
+  }
+}
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int C,
+                                             long long HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long p0 = static_cast<long long>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i; const long long p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (p < HW && c < C) ? x[(static_cast<size_t>(n) * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long p = p0 + i; const int c = c0 + threadIdx.x;
+    if (p < HW && c < C) y[(static_cast<size_t>(n) * HW + p) * C + c] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+
+}  // namespace b2u
+
+extern "C" {
+using namespace b2u;
+
+int b2u_im2col_first(const float* x, void* col, int N, int Cin, int H, int W, void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || 9 * Cin > 64) return set_error(B2U_ERR_SHAPE, "im2col_first: bad shape (Cin=%d)", Cin);
+  const long long total = static_cast<long long>(N) * H * W * 8;
+  im2col_first_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__nv_bfloat16*>(col), N, Cin, H, W);
+  B2U_CHECK_LAUNCH("im2col_first");
+  return 0;
+}
+
+int b2u_pack_weights(const float* w, void* wf, void* wd, int Cout, int Cin, int taps, void* stream) {
+  if (Cout <= 0 || Cin <= 0 || (taps != 9 && taps != 1)) return set_error(B2U_ERR_SHAPE, "pack_weights: bad shape");
+  const long long total = static_cast<long long>(Cout) * Cin * taps;
+  pack_weights_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, static_cast<__nv_bfloat16*>(wf), static_cast<__nv_bfloat16*>(wd), Cout, Cin, taps);
+  B2U_CHECK_LAUNCH("pack_weights");
+  return 0;
+}
+
+int b2u_pack_weights_first(const float* w, void* wf, int Cout, int Cin, void* stream) {
+  if (Cout <= 0 || Cin <= 0 || 9 * Cin > 64) return set_error(B2U_ERR_SHAPE, "pack_weights_first: bad shape");
+  pack_weights_first_kernel<<<grid_for(Cout * 64, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, static_cast<__nv_bfloat16*>(wf), Cout, Cin);
+  B2U_CHECK_LAUNCH("pack_weights_first");
+  return 0;
+}
+
+int b2u_maxpool2x2_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || C % 8 != 0)
+    return set_error(B2U_ERR_SHAPE, "maxpool2x2_fwd: H,W must be even and C %% 8 == 0 (H=%d W=%d C=%d)", H, W, C);
+  const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
+  maxpool2x2_fwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), static_cast<uint4*>(y), N, H, W, C / 8);
+  B2U_CHECK_LAUNCH("maxpool2x2_fwd");
+  return 0;
+}
+
+// H, W: dims of the un-pooled tensor y; dpool is [N,H/2,W/2,C]; dskip (nullable) and dz are [N,H,W,C]
+int b2u_maxpool2x2_bwd(const void* dpool, const void* dskip, const void* y, void* dz, int N, int H, int W, int C,
+                       int relu_mask, void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || C % 8 != 0)
+    return set_error(B2U_ERR_SHAPE, "maxpool2x2_bwd: H,W must be even and C %% 8 == 0");
+  const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
+  maxpool2x2_bwd_kernel<<<grid_for(total, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(dpool), static_cast<const uint4*>(dskip), static_cast<const uint4*>(y),
+      static_cast<uint4*>(dz), N, H, W, C / 8, relu_mask);
+  B2U_CHECK_LAUNCH("maxpool2x2_bwd");
+  return 0;
+}
+
+// H, W: dims of the low-resolution input; output is [N,2H,2W,C]
+int b2u_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || C % 8 != 0) return set_error(B2U_ERR_SHAPE, "upsample2x_fwd: bad shape");
+  const float sh = (2 * H > 1) ? static_cast<float>(H - 1) / static_cast<float>(2 * H - 1) : 0.f;
+  const float sw = (2 * W > 1) ? static_cast<float>(W - 1) / static_cast<float>(2 * W - 1) : 0.f;
+  const long long total = static_cast<long long>(N) * 4 * H * W * (C / 8);
+  upsample2x_fwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), static_cast<uint4*>(y), N, H, W, C / 8, sh, sw);
+  B2U_CHECK_LAUNCH("upsample2x_fwd");
+  return 0;
+}
+
+// dup: [N,2H,2W,C]; ylow (nullable): ReLU output that was upsampled, dlow is zeroed where ylow <= 0
+int b2u_upsample2x_bwd(const void* dup, const void* ylow, void* dlow, int N, int H, int W, int C, void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || C % 8 != 0) return set_error(B2U_ERR_SHAPE, "upsample2x_bwd: bad shape");
+  const float sh = static_cast<float>(H - 1) / static_cast<float>(2 * H - 1);
+  const float sw = static_cast<float>(W - 1) / static_cast<float>(2 * W - 1);
+  const float ish = H > 1 ? 1.f / sh : 4.f * H;   // H == 1: every output maps to row 0
+  const float isw = W > 1 ? 1.f / sw : 4.f * W;
+  const long long total = static_cast<long long>(N) * H * W * (C / 8);
+  upsample2x_bwd_kernel<<<grid_for(total, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(dup), static_cast<const uint4*>(ylow), static_cast<uint4*>(dlow), N, H, W, C / 8, sh, sw,
+      ish, isw);
+  B2U_CHECK_LAUNCH("upsample2x_bwd");
+  return 0;
+}
+
+size_t b2u_bias_grad_workspace(int C) { return static_cast<size_t>(2 * 148) * C * sizeof(float); }
+
+int b2u_bias_grad(const void* dz, float* db, void* ws, size_t ws_bytes, long long P, int C, void* stream) {
+  if (P <= 0 || C <= 0 || C % 8 != 0) return set_error(B2U_ERR_SHAPE, "bias_grad: bad shape");
+  const int blocks = 2 * 148;
+  if (!ws || ws_bytes < static_cast<size_t>(blocks) * C * sizeof(float)) return set_error(B2U_ERR_ARG, "bias_grad: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  bias_grad_partial_kernel<<<blocks, 256, 256 * 8 * sizeof(float), st>>>(static_cast<const uint4*>(dz),
+                                                                         static_cast<float*>(ws), P, C / 8);
+  B2U_CHECK_LAUNCH("bias_grad_partial");
+  reduce_rows_kernel<<<grid_for(C, 128), 128, 0, st>>>(static_cast<const float*>(ws), db, blocks, C);
+  B2U_CHECK_LAUNCH("reduce_rows");
+  return 0;
+}
+
+int b2u_nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, int H, int W, void* stream) {
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0) return set_error(B2U_ERR_SHAPE, "nhwc->nchw: bad shape");
+  const long long HW = static_cast<long long>(H) * W;
+  dim3 grid(static_cast<unsigned>((HW + 31) / 32), (C + 31) / 32, N), block(32, 8);
+  nhwc_bf16_to_nchw_f32_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), y, C, HW);
+  B2U_CHECK_LAUNCH("nhwc_bf16_to_nchw_f32");
+  return 0;
+}
+
+int b2u_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int W, void* stream) {
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0) return set_error(B2U_ERR_SHAPE, "nchw->nhwc: bad shape");
+  const long long HW = static_cast<long long>(H) * W;
+  dim3 grid(static_cast<unsigned>((HW + 31) / 32), (C + 31) / 32, N), block(32, 8);
+  nchw_f32_to_nhwc_bf16_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__nv_bfloat16*>(y), C, HW);
+  B2U_CHECK_LAUNCH("nchw_f32_to_nhwc_bf16");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,264 @@
+"""Tensor-level wrappers over the C ABI (include/b2u.h).
+
+Activations are NHWC bf16 CUDA tensors ([N, H, W, C], contiguous); parameters and logits keep the reference's
+fp32 OIHW / NCHW layouts.  Every function launches on torch's current stream and allocates its outputs and
+workspaces with torch's caching allocator; none of them has a CPU or PyTorch fallback.
+"""
+import torch
+
+from ._lib import check, lib, ptr, stream_ptr
+
+BF16 = torch.bfloat16
+
+
+def _req(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA tensor (the hot path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous tensor")
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ---------------------------------------------------------------------------------------------- layout
+def im2col_first(x_nchw):
+    _req(x_nchw, torch.float32, "x")
+    N, C, H, W = x_nchw.shape
+    col = torch.empty((N, H, W, 64), dtype=BF16, device=x_nchw.device)
+    check(lib().b2u_im2col_first(ptr(x_nchw), ptr(col), N, C, H, W, stream_ptr()))
+    return col
+
+
+def pack_weights(w, want_dgrad=True, wf=None, wd=None):
+    """OIHW fp32 -> (wf [Cout, taps*Cin], wd [Cin, taps*Cout]) bf16."""
+    _req(w, torch.float32, "weight")
+    Cout, Cin, kh, kw = w.shape
+    taps = kh * kw
+    if wf is None:
+        wf = torch.empty((Cout, taps * Cin), dtype=BF16, device=w.device)
+    if want_dgrad and wd is None:
+        wd = torch.empty((Cin, taps * Cout), dtype=BF16, device=w.device)
+    check(lib().b2u_pack_weights(ptr(w), ptr(wf), ptr(wd) if want_dgrad else None, Cout, Cin, taps, stream_ptr()))
+    return wf, (wd if want_dgrad else None)
+
+
+def pack_weights_first(w, wf=None):
+    _req(w, torch.float32, "weight")
+    Cout, Cin, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    if wf is None:
+        wf = torch.empty((Cout, 64), dtype=BF16, device=w.device)
+    check(lib().b2u_pack_weights_first(ptr(w), ptr(wf), Cout, Cin, stream_ptr()))
+    return wf
+
+
+def nhwc_to_nchw_f32(x):
+    _req(x, BF16, "x")
+    N, H, W, C = x.shape
+    y = torch.empty((N, C, H, W), dtype=torch.float32, device=x.device)
+    check(lib().b2u_nhwc_bf16_to_nchw_f32(ptr(x), ptr(y), N, C, H, W, stream_ptr()))
+    return y
+
+
+def nchw_to_nhwc_bf16(x):
+    _req(x, torch.float32, "x")
+    N, C, H, W = x.shape
+    y = torch.empty((N, H, W, C), dtype=BF16, device=x.device)
+    check(lib().b2u_nchw_f32_to_nhwc_bf16(ptr(x), ptr(y), N, C, H, W, stream_ptr()))
+    return y
+
+
+# ---------------------------------------------------------------------------------------------- convs
+def conv_fprop(x0, wf, bias, Cout, taps=9, relu=True, x1=None, out=None, bn=0):
+    _req(x0, BF16, "x0"); _req(x1, BF16, "x1"); _req(wf, BF16, "wf"); _req(bias, torch.float32, "bias")
+    N, H, W, C0 = x0.shape
+    C1 = 0 if x1 is None else x1.shape[3]
+    if out is None:
+        out = torch.empty((N, H, W, Cout), dtype=BF16, device=x0.device)
+    check(lib().b2u_conv_fprop(ptr(x0), C0, ptr(x1), C1, ptr(wf), ptr(bias), ptr(out), N, H, W, Cout, taps,
+                               1 if relu else 0, bn, stream_ptr()))
+    return out
+
+
+def conv_dgrad(dz, wd, C0, taps=9, C1=0, mask=None, out0=None, out1=None, bn=0):
+    _req(dz, BF16, "dz"); _req(wd, BF16, "wd"); _req(mask, BF16, "mask")
+    N, H, W, Cz = dz.shape
+    if out0 is None:
+        out0 = torch.empty((N, H, W, C0), dtype=BF16, device=dz.device)
+    if C1 > 0 and out1 is None:
+        out1 = torch.empty((N, H, W, C1), dtype=BF16, device=dz.device)
+    check(lib().b2u_conv_dgrad(ptr(dz), Cz, ptr(wd), ptr(out0), C0, ptr(out1) if C1 > 0 else None, C1, ptr(mask),
+                               N, H, W, taps, bn, stream_ptr()))
+    return (out0, out1) if C1 > 0 else out0
+
+
+def conv_wgrad(x0, dz, taps=9, x1=None, first_cin=0, dw=None, ws=None, flags=0):
+    _req(x0, BF16, "x0"); _req(x1, BF16, "x1"); _req(dz, BF16, "dz")
+    N, H, W, C0 = x0.shape
+    C1 = 0 if x1 is None else x1.shape[3]
+    Cout = dz.shape[3]
+    need = lib().b2u_conv_wgrad_workspace(N, H, W, C0 + C1, Cout, taps)
+    if ws is None or ws.numel() * ws.element_size() < need:
+        ws = _ws(need, x0.device)
+    if dw is None:
+        if first_cin > 0:
+            dw = torch.empty((Cout, first_cin, 3, 3), dtype=torch.float32, device=x0.device)
+        else:
+            k = 3 if taps == 9 else 1
+            dw = torch.empty((Cout, C0 + C1, k, k), dtype=torch.float32, device=x0.device)
+    check(lib().b2u_conv_wgrad(ptr(x0), C0, ptr(x1), C1, ptr(dz), Cout, ptr(dw), ptr(ws),
+                               ws.numel() * ws.element_size(), N, H, W, taps, first_cin, flags, stream_ptr()))
+    return dw
+
+
+def bias_grad(dz, db=None, ws=None):
+    _req(dz, BF16, "dz")
+    C = dz.shape[-1]
+    P = dz.numel() // C
+    need = lib().b2u_bias_grad_workspace(C)
+    if ws is None or ws.numel() * ws.element_size() < need:
+        ws = _ws(need, dz.device)
+    if db is None:
+        db = torch.empty((C,), dtype=torch.float32, device=dz.device)
+    check(lib().b2u_bias_grad(ptr(dz), ptr(db), ptr(ws), ws.numel() * ws.element_size(), P, C, stream_ptr()))
+    return db
+
+
+# ---------------------------------------------------------------------------------------------- pool / upsample
+def maxpool2x2(x, out=None):
+    _req(x, BF16, "x")
+    N, H, W, C = x.shape
+    if out is None:
+        out = torch.empty((N, H // 2, W // 2, C), dtype=BF16, device=x.device)
+    check(lib().b2u_maxpool2x2_fwd(ptr(x), ptr(out), N, H, W, C, stream_ptr()))
+    return out
+
+
+def maxpool2x2_bwd(dpool, y, dskip=None, relu_mask=True, out=None):
+    _req(dpool, BF16, "dpool"); _req(y, BF16, "y"); _req(dskip, BF16, "dskip")
+    N, H, W, C = y.shape
+    if out is None:
+        out = torch.empty_like(y)
+    check(lib().b2u_maxpool2x2_bwd(ptr(dpool), ptr(dskip), ptr(y), ptr(out), N, H, W, C, 1 if relu_mask else 0,
+                                   stream_ptr()))
+    return out
+
+
+def upsample2x(x, out=None):
+    _req(x, BF16, "x")
+    N, H, W, C = x.shape
+    if out is None:
+        out = torch.empty((N, 2 * H, 2 * W, C), dtype=BF16, device=x.device)
+    check(lib().b2u_upsample2x_fwd(ptr(x), ptr(out), N, H, W, C, stream_ptr()))
+    return out
+
+
+def upsample2x_bwd(dup, ylow=None, out=None):
+    _req(dup, BF16, "dup"); _req(ylow, BF16, "ylow")
+    N, H2, W2, C = dup.shape
+    H, W = H2 // 2, W2 // 2
+    if out is None:
+        out = torch.empty((N, H, W, C), dtype=BF16, device=dup.device)
+    check(lib().b2u_upsample2x_bwd(ptr(dup), ptr(ylow), ptr(out), N, H, W, C, stream_ptr()))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- head
+def head_fwd(x, w, b, out=None):
+    _req(x, BF16, "x"); _req(w, torch.float32, "w"); _req(b, torch.float32, "b")
+    N, H, W, Cin = x.shape
+    ncls = w.shape[0]
+    if out is None:
+        out = torch.empty((N, ncls, H, W), dtype=torch.float32, device=x.device)
+    check(lib().b2u_head_fwd(ptr(x), ptr(w), ptr(b), ptr(out), N, H, W, Cin, ncls, stream_ptr()))
+    return out
+
+
+def head_bwd(dlogits, x, w, need_dx=True, need_dw=True, relu_mask=True, dx=None, dw=None, db=None, ws=None):
+    _req(dlogits, torch.float32, "dlogits"); _req(x, BF16, "x"); _req(w, torch.float32, "w")
+    N, H, W, Cin = x.shape
+    ncls = w.shape[0]
+    need = lib().b2u_head_bwd_workspace()
+    if need_dw and (ws is None or ws.numel() * ws.element_size() < need):
+        ws = _ws(need, x.device)
+    if need_dx and dx is None:
+        dx = torch.empty_like(x)
+    if need_dw:
+        if dw is None:
+            dw = torch.empty((ncls, Cin, 1, 1), dtype=torch.float32, device=x.device)
+        if db is None:
+            db = torch.empty((ncls,), dtype=torch.float32, device=x.device)
+    check(lib().b2u_head_bwd(ptr(dlogits), ptr(x), ptr(w), ptr(dx) if need_dx else None,
+                             ptr(dw) if need_dw else None, ptr(db) if need_dw else None, ptr(ws) if need_dw else None,
+                             0 if not need_dw else ws.numel() * ws.element_size(), N, H, W, Cin, ncls,
+                             1 if relu_mask else 0, stream_ptr()))
+    return dx, dw, db
+
+
+# ---------------------------------------------------------------------------------------------- loss / metrics
+def loss_fwd(logits, target=None, onehot=None, cls_w=None, beta=1.0, smooth=1e-5, alpha=0.5, gamma=2.0, thr=0.5,
+             ws=None):
+    """Returns the device vector [CE, Focal, Dice, f_score, backward coefficients...]."""
+    _req(logits, torch.float32, "logits"); _req(target, torch.int64, "target")
+    _req(onehot, torch.float32, "onehot"); _req(cls_w, torch.float32, "cls_weights")
+    N, C, H, W = logits.shape
+    need = lib().b2u_loss_workspace(C)
+    if ws is None or ws.numel() * ws.element_size() < need:
+        ws = _ws(need, logits.device)
+    out = torch.empty((lib().b2u_loss_out_len(C),), dtype=torch.float32, device=logits.device)
+    check(lib().b2u_loss_fwd(ptr(logits), ptr(target), ptr(onehot), ptr(cls_w), ptr(out), None, ptr(ws),
+                             ws.numel() * ws.element_size(), N, C, H, W, beta, smooth,
+                             0.0 if alpha is None else alpha, gamma, thr, stream_ptr()))
+    return out
+
+
+def loss_bwd(logits, fin, gscale, target=None, onehot=None, cls_w=None, alpha=0.5, gamma=2.0, out=None):
+    _req(logits, torch.float32, "logits"); _req(gscale, torch.float32, "gscale")
+    N, C, H, W = logits.shape
+    if out is None:
+        out = torch.empty_like(logits)
+    check(lib().b2u_loss_bwd(ptr(logits), ptr(target), ptr(onehot), ptr(cls_w), ptr(fin), ptr(gscale), ptr(out), N, C,
+                             H, W, 0.0 if alpha is None else alpha, gamma, stream_ptr()))
+    return out
+
+
+def argmax_u8(logits, out=None):
+    _req(logits, torch.float32, "logits")
+    N, C, H, W = logits.shape
+    if out is None:
+        out = torch.empty((N, H, W), dtype=torch.uint8, device=logits.device)
+    check(lib().b2u_argmax_u8(ptr(logits), ptr(out), N, C, H, W, stream_ptr()))
+    return out
+
+
+_HIST_DTYPES = {torch.uint8: 0, torch.int32: 1, torch.int64: 2}
+
+
+def fast_hist_accumulate(a, b, n, hist):
+    """hist (uint64 as int64 tensor, n*n+1) += histogram of (a, b); a, b flat CUDA tensors of one dtype."""
+    if a.dtype != b.dtype or a.dtype not in _HIST_DTYPES:
+        raise ValueError("fast_hist: a and b must both be uint8, int32 or int64")
+    _req(a, a.dtype, "a"); _req(b, b.dtype, "b"); _req(hist, torch.int64, "hist")
+    if a.numel() != b.numel():
+        raise ValueError("fast_hist: a and b must have the same number of elements")
+    check(lib().b2u_fast_hist(ptr(a), ptr(b), a.numel(), n, _HIST_DTYPES[a.dtype], ptr(hist), stream_ptr()))
+    return hist
+
+
+# ---------------------------------------------------------------------------------------------- optimizer
+def adam_step(param, grad, m, v, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+    for t, nme in ((param, "param"), (grad, "grad"), (m, "exp_avg"), (v, "exp_avg_sq")):
+        _req(t, torch.float32, nme)
+    check(lib().b2u_adam_step(ptr(param), ptr(grad), ptr(m), ptr(v), param.numel(), lr, betas[0], betas[1], eps,
+                              weight_decay, step, grad_scale, stream_ptr()))
+
+
+def sgd_step(param, grad, buf, lr, momentum=0.0, weight_decay=0.0, nesterov=False, first_step=False, grad_scale=1.0):
+    check(lib().b2u_sgd_step(ptr(param), ptr(grad), ptr(buf), param.numel(), lr, momentum, weight_decay,
+                             1 if nesterov else 0, 1 if first_step else 0, grad_scale, stream_ptr()))
