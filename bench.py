@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""Headline benchmark: 512x512 Unet-VGG16 (21 classes) training throughput, batch 16 per GPU, data parallel.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one iteration of the reference's fit_one_epoch body (utils/utils_fit.py:26-97): forward, CE + Dice
+(+ f_score), backward, gradient all-reduce (N > 1), Adam step, on one synthetic batch of 16 images per GPU.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every key.
+
+  value        img/s over all GPUs, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e          img/s through UnetTrainer.train_step with HOST (pinned) batches: H2D of images + label maps and a
+               D2H read of [loss, f_score] every step are inside the timed region
+  roofline     conv_igemm_kernel (fprop + dgrad launches): algorithmic FLOPs / per-launch CUDA-event time,
+               against MEASURED_PEAKS.json's sustained bf16 figure
+  cpu_baseline the oracle (a torch-CPU restatement of the reference path; the reference itself is Python and does
+               not travel to the GPU box) timed on this box's host cores on a bounded sample
+  --impl reference   times that same CPU path with all host threads and prints the reference-arm line
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NUM_CLASSES = 21
+BATCH_PER_GPU = 16
+HW = 512
+METRIC = "unet_vgg16_512x512_train_img_per_s"
+# fprop + dgrad + wgrad conv FLOPs per image
+TRAIN_GFLOP_PER_IMG = 1351.99
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"bf16_sustained": d.get("bf16_tflops_sustained", 1381.4), "bf16_burst": d.get("bf16_tflops", 1659.2),
+                "hbm": d.get("hbm_gbs", 6556.2), "source": "measured"}
+    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(power), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def cpu_path_img_per_s(steps, warmup, batch=2, threads=None):
+    """The reference's CPU path for this workload (oracle port), bounded sample: `batch` images per step."""
+    import torch
+    from oracle import unet_oracle as O
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    params = O.make_params(NUM_CLASSES, seed=11)
+    imgs, pngs = O.make_inputs(batch, NUM_CLASSES, HW, HW, seed=0)
+    w = torch.ones(NUM_CLASSES)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.train_step(params, imgs, pngs, w, NUM_CLASSES, dice=True)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return batch * len(times) / total, total / len(times), threads, batch
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warmup = 1 if args.warmup > 0 else 0
+    v, s_per_step, threads, batch = cpu_path_img_per_s(steps, warmup)
+    cpu_model = ""
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                cpu_model = ln.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    sample = (f"{steps} timed step(s) of batch {batch} (of the 16-image batch), 512x512, 21 classes, fp32 torch CPU, "
+              f"fwd + CE + Dice + bwd, after {warmup} warm-up; {cpu_model}")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "img/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "Unet-VGG16 21-class 512x512 training step (fwd + CE + Dice + bwd), CPU, bounded sample of batch 2",
+                       "batch_per_step": batch},
+            "cpu_baseline": {"value": v, "unit": "img/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import unet_pytorch_b200 as b2u
+    from unet_pytorch_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = _peaks()
+    K, W = args.steps, args.warmup
+    B = args.batch
+
+    params = b2u.synthetic.make_params(NUM_CLASSES, seed=11)
+    trainer = b2u.UnetTrainer(num_classes=NUM_CLASSES, device=dev, lr=1e-4, betas=(0.9, 0.999), state_dict=params,
+                              dice_loss=True)
+    # a few distinct resident batches, different per rank (DistributedSampler semantics)
+    nb = 2
+    host = [b2u.synthetic.make_inputs(B, NUM_CLASSES, HW, HW, seed=100 * rank + i) for i in range(nb)]
+    host = [(i.pin_memory(), p.pin_memory()) for i, p in host]
+    resident = [(i.to(dev), p.to(dev)) for i, p in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+        return ms
+
+    # ---------------- device-resident leg (value) + roofline timing of the conv launches
+    for i in range(W):
+        trainer.train_step(*resident[i % nb])
+    barrier()
+    lib = b2u._lib.lib()
+    lib.b2u_reset_launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        out = trainer.train_step(*resident[i % nb])
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = int(lib.b2u_launch_count())
+    clocks = sampler.stop() if rank == 0 else None
+    loss_val = out.tolist()
+
+    # per-launch timing of the tensor-core kernels (separate pass: the events add launch gaps)
+    timer = ops.KernelTimer()
+    ops.set_timer(timer)
+    tsteps = max(1, min(K, 5))
+    for i in range(tsteps):
+        trainer.train_step(*resident[i % nb])
+    kt = timer.read()
+    ops.set_timer(None)
+
+    # ---------------- end-to-end leg: host batches, H2D + D2H inside the timed region
+    h2d = host[0][0].numel() * host[0][0].element_size() + host[0][1].numel() * host[0][1].element_size()
+    for i in range(min(W, 3)):
+        trainer.stage(*host[i % nb])
+        trainer.train_step().tolist()
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    trainer.stage(*host[0])
+    for i in range(K):
+        res = trainer.train_step()                 # consumes the staged batch (waits for its copy)
+        if i + 1 < K:
+            trainer.stage(*host[(i + 1) % nb])     # next batch's H2D overlaps this step's kernels
+        res = res.tolist()                         # D2H read of [loss, f_score], per-iteration sync (utils_fit.py:96)
+    t1.record()
+    barrier()
+    ms_e2e = max_over_ranks(t0.elapsed_time(t1))
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    imgs_total = B * world * K
+    value = imgs_total / (ms_total / 1e3)
+    e2e_value = imgs_total / (ms_e2e / 1e3)
+    ig = kt.get("conv_igemm", {"launches": 0, "ms": 0.0, "flops": 0.0})
+    wg = kt.get("conv_wgrad", {"launches": 0, "ms": 0.0, "flops": 0.0})
+
+    def roof(rec, traffic=None):
+        if rec["ms"] <= 0:
+            return None
+        ach = rec["flops"] / (rec["ms"] / 1e3) / 1e12
+        return {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": ach / peaks["bf16_sustained"], "traffic": traffic, "peak_source": peaks["source"] + " (sustained)",
+                "launches_timed": rec["launches"], "avg_launch_ms": rec["ms"] / max(rec["launches"], 1),
+                "flops_per_launch": rec["flops"] / max(rec["launches"], 1)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "Unet-VGG16 21-class 512x512 bf16 training step (fwd + CE + Dice + f_score + bwd + "
+                               "grad all-reduce + Adam), BASELINE configs[1]",
+                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "l2": "inputs larger than L2 (>= 4.7 GB of activations per step), no explicit flush"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+                "ms_per_step": ms_e2e / K},
+        "gpu_launches": launches,
+        "roofline": roof(ig),
+        "roofline_wgrad": roof(wg),
+        "model_tflops": value * TRAIN_GFLOP_PER_IMG / 1e3 / world,
+        "loss": loss_val[0], "f_score": loss_val[1],
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, s_per_step, threads, batch = cpu_path_img_per_s(2, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "img/s", "cores": threads, "kind": "port",
+                                "sample": f"2 timed steps of batch {batch} (512x512, 21 classes, fp32 torch CPU oracle, "
+                                          f"fwd + CE + Dice + bwd) after 1 warm-up, {s_per_step:.2f} s/step"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="images per GPU per step (BASELINE: 16)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,9 @@ extern "C" {
 const char* b2u_last_error(void);
 int b2u_version(void);
 int b2u_num_sms(void);
+/* number of kernel launches made by this library since load / the last reset (process-wide) */
+long long b2u_launch_count(void);
+void b2u_reset_launch_count(void);
 
 /* ---- layout / packing ------------------------------------------------------------------------------------ */
 /* first conv of the encoder (nets/vgg.py:53 with in_channels=3): NCHW fp32 image -> im2col rows [N,H,W,64] bf16,

@@ -1,0 +1,119 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on seeded inputs.
+Run in the build container only (the reference does not travel to the GPU box):  python oracle/make_golden.py
+The synthetic weights/inputs come from oracle.unet_oracle.make_params / make_inputs so tests can regenerate them.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+# utils/utils_metrics.py imports matplotlib at module level (line 5); plotting is never reached on this path
+for name in ("matplotlib", "matplotlib.pyplot"):
+    sys.modules.setdefault(name, types.ModuleType(name))
+
+from nets.unet import Unet as RefUnet                                   # noqa: E402
+from nets.unet_training import CE_Loss, Dice_loss, Focal_Loss           # noqa: E402
+from utils.utils_metrics import f_score, fast_hist, per_class_iu, per_class_PA_Recall, per_class_Precision  # noqa: E402
+
+from oracle import unet_oracle as O                                     # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+torch.set_num_threads(8)
+
+
+def model_case(tag, num_classes, n, h, w, seed, medical, cls_w, dice, focal):
+    params = O.make_params(num_classes, seed=11)
+    model = RefUnet(num_classes=num_classes, pretrained=False, backbone="vgg")
+    model.load_state_dict(params)
+    model.train()
+    imgs, pngs = O.make_inputs(n, num_classes, h, w, seed=seed, medical=medical)
+    labels = torch.eye(num_classes + 1)[pngs]
+    weights = torch.tensor(cls_w, dtype=torch.float32)
+    out = model(imgs)
+    loss = Focal_Loss(out, pngs, weights, num_classes=num_classes) if focal else CE_Loss(out, pngs, weights, num_classes=num_classes)
+    parts = {"ce_or_focal": loss.item()}
+    if dice:
+        d = Dice_loss(out, labels)
+        parts["dice"] = d.item()
+        loss = loss + d
+    with torch.no_grad():
+        fs = f_score(out, labels).item()
+    loss.backward()
+    rec = {"logits": out.detach().numpy().astype(np.float32), "loss": np.float64(loss.item()), "f_score": np.float64(fs),
+           "cls_w": np.asarray(cls_w, np.float32), "meta": np.asarray([num_classes, n, h, w, seed, int(medical), int(dice), int(focal)])}
+    for k, v in parts.items():
+        rec["loss_" + k] = np.float64(v)
+    for name, p in model.named_parameters():
+        g = p.grad.detach()
+        rec["gnorm:" + name] = np.float64(g.double().norm().item())
+        flat = g.reshape(-1)
+        # evenly spaced sample of up to 4096 entries (full tensor for biases and the head)
+        if flat.numel() <= 4096:
+            rec["g:" + name] = flat.numpy().astype(np.float32)
+        else:
+            idx = torch.linspace(0, flat.numel() - 1, 4096).long()
+            rec["g:" + name] = flat[idx].numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, f"unet_vgg_{tag}.npz"), **rec)
+    print(tag, "loss", loss.item(), "f_score", fs, "logits", out.shape)
+
+
+def loss_case():
+    g = torch.Generator().manual_seed(7)
+    rec = {}
+    for C, cw in ((21, None), (4, [1, 15, 1.5, 2]), (2, [1, 1])):
+        n, h, w = 2, 24, 40
+        logits = torch.randn(n, C, h, w, generator=g) * 2
+        png = torch.randint(0, C + 1, (n, h, w), generator=g)
+        weights = torch.ones(C) if cw is None else torch.tensor(cw, dtype=torch.float32)
+        labels = torch.eye(C + 1)[png]
+        lg = logits.clone().requires_grad_(True)
+        ce = CE_Loss(lg, png, weights, num_classes=C)
+        fo = Focal_Loss(lg, png, weights, num_classes=C)
+        di = Dice_loss(lg, labels)
+        fs = f_score(lg, labels)
+        g_ce, = torch.autograd.grad(ce, lg, retain_graph=True)
+        g_fo, = torch.autograd.grad(fo, lg, retain_graph=True)
+        g_di, = torch.autograd.grad(di, lg)
+        rec[f"C{C}:logits"] = logits.numpy(); rec[f"C{C}:png"] = png.numpy(); rec[f"C{C}:w"] = weights.numpy()
+        rec[f"C{C}:vals"] = np.asarray([ce.item(), fo.item(), di.item(), fs.item()], np.float64)
+        rec[f"C{C}:g_ce"] = g_ce.numpy(); rec[f"C{C}:g_focal"] = g_fo.numpy(); rec[f"C{C}:g_dice"] = g_di.numpy()
+    np.savez_compressed(os.path.join(OUT, "losses.npz"), **rec)
+    print("losses ok")
+
+
+def hist_case():
+    rec = {}
+    for n in (2, 4, 21):
+        gt, pred = O.make_masks(3, n, h=64, w=96, seed=n)
+        hist = np.zeros((n, n))
+        for i in range(gt.shape[0]):
+            hist += fast_hist(gt[i].flatten(), pred[i].flatten(), n)     # utils_metrics.py:95
+        rec[f"n{n}:hist"] = hist.astype(np.int64)
+        rec[f"n{n}:iou"] = per_class_iu(hist); rec[f"n{n}:recall"] = per_class_PA_Recall(hist)
+        rec[f"n{n}:precision"] = per_class_Precision(hist)
+        rec[f"n{n}:miou"] = np.float64(np.nanmean(per_class_iu(hist)))
+    # adversarial: all ignored, single class, empty
+    a = np.full(1000, 255, np.uint8); b = np.zeros(1000, np.uint8)
+    rec["allignore:hist"] = fast_hist(a, b, 21).astype(np.int64)
+    a = np.full(1000, 3, np.uint8); b = np.full(1000, 3, np.uint8)
+    rec["single:hist"] = fast_hist(a, b, 21).astype(np.int64)
+    rec["empty:hist"] = fast_hist(np.zeros(0, np.uint8), np.zeros(0, np.uint8), 4).astype(np.int64)
+    np.savez_compressed(os.path.join(OUT, "fast_hist.npz"), **rec)
+    print("hist ok")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    # config 1 shape: num_classes=2, batch 2, Medical_Datasets-shaped, CE only (train_medical.py: dice_loss=False)
+    model_case("nc2_medical", 2, 2, 64, 64, 0, True, [1, 1], dice=False, focal=False)
+    # config 2 shape: 21 classes, CE + Dice, ~2 % ignore pixels
+    model_case("nc21_cedice", 21, 2, 64, 96, 1, False, [1] * 21, dice=True, focal=False)
+    # TraditionalUnet_Train-style loss settings: focal + dice, weights [1,15,1.5,2]
+    model_case("nc4_focaldice", 4, 1, 32, 32, 2, False, [1, 15, 1.5, 2], dice=True, focal=True)
+    loss_case()
+    hist_case()

@@ -1,0 +1,225 @@
+"""CPU oracle of the UNet hot path -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module;
+the product path (unet-pytorch_b200/) never does and fails loudly without its CUDA library.
+
+It restates, function by function, what clolckliang/unet-pytorch computes on this path.  The arithmetic itself
+lives in a third-party dependency of the reference that is not vendored in it -- PyTorch (requirements.txt:1,
+this image: torch 2.11.0) -- so the restatement is written directly against torch.nn.functional's published
+semantics (conv2d cross-correlation with zero padding, max_pool2d, bilinear interpolate with
+align_corners=True, cross_entropy with weight/ignore_index, softmax) on fp32 CPU tensors, plus closed forms for
+the losses and numpy for the integer histogram.
+
+Parity pin: the reference ships no tests or golden vectors for this path, so the oracle is
+pinned against outputs of the reference itself: oracle/make_golden.py imports /root/reference, runs its
+nets.unet.Unet / nets.unet_training losses / utils.utils_metrics functions on seeded inputs and commits the
+results under tests/golden/; tests/test_oracle.py checks this module against those files (<= 1e-5, integers exact).
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# nets/vgg.py:62-64 cfgs['D'] (the trailing 'M' is dropped by VGG.forward's features[23:-1], nets/vgg.py:30)
+VGG_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512]
+VGG_CONV_IDX = [0, 2, 5, 7, 10, 12, 14, 17, 19, 21, 24, 26, 28]
+# features[:4], [4:9], [9:16], [16:23], [23:-1]  (nets/vgg.py:26-30): index of the last conv of each slice
+FEAT_AFTER = {2: 0, 7: 1, 14: 2, 21: 3, 28: 4}
+
+
+def param_shapes(num_classes, in_channels=3):
+    """state_dict names/shapes of nets/unet.py::Unet(backbone='vgg') in order (44 tensors)."""
+    shapes = {}
+    cin = in_channels
+    it = iter(VGG_CONV_IDX)
+    for v in VGG_CFG:
+        if v == "M":
+            continue
+        i = next(it)
+        shapes[f"vgg.features.{i}.weight"] = (v, cin, 3, 3)
+        shapes[f"vgg.features.{i}.bias"] = (v,)
+        cin = v
+    in_filters = [192, 384, 768, 1024]      # nets/unet.py:29
+    out_filters = [64, 128, 256, 512]       # nets/unet.py:35
+    for k in (4, 3, 2, 1):
+        shapes[f"up_concat{k}.conv1.weight"] = (out_filters[k - 1], in_filters[k - 1], 3, 3)
+        shapes[f"up_concat{k}.conv1.bias"] = (out_filters[k - 1],)
+        shapes[f"up_concat{k}.conv2.weight"] = (out_filters[k - 1], out_filters[k - 1], 3, 3)
+        shapes[f"up_concat{k}.conv2.bias"] = (out_filters[k - 1],)
+    shapes["final.weight"] = (num_classes, 64, 1, 1)
+    shapes["final.bias"] = (num_classes,)
+    return shapes
+
+
+def make_params(num_classes, seed=11, in_channels=3, gain=1.0):
+    """Deterministic synthetic weights (no checkpoint is shipped for this model): tensor k of
+    the state_dict is drawn from its own generator seeded seed*1000+k; He-scaled so activations stay O(1)."""
+    params = {}
+    for k, (name, shape) in enumerate(param_shapes(num_classes, in_channels).items()):
+        g = torch.Generator().manual_seed(seed * 1000 + k)
+        if len(shape) == 4:
+            fan_in = shape[1] * shape[2] * shape[3]
+            params[name] = torch.randn(shape, generator=g) * (gain * (2.0 / fan_in) ** 0.5)
+        else:
+            params[name] = torch.randn(shape, generator=g) * 0.05
+    return params
+
+
+def make_inputs(n, num_classes, h, w, seed=0, medical=False):
+    """Structured synthetic batch: low-frequency image field, labels correlated with it, ~2 %
+    ignore pixels (= num_classes) unless `medical` (grey image replicated to RGB, binary labels, no ignore)."""
+    g = torch.Generator().manual_seed(seed)
+    if medical:
+        base = F.interpolate(torch.rand(n, 1, max(h // 64, 2), max(w // 64, 2), generator=g), size=(h, w), mode="bilinear",
+                             align_corners=True)
+        img = (base + 0.1 * torch.rand(n, 1, h, w, generator=g)).clamp(0, 1)
+        img = torch.round(img * 255) / 255
+        png = (base[:, 0] > 0.5).long()
+        return img.repeat(1, 3, 1, 1).contiguous(), png
+    fields = F.interpolate(torch.rand(n, num_classes, max(h // 32, 2), max(w // 32, 2), generator=g), size=(h, w),
+                           mode="bilinear", align_corners=True)
+    png = fields.argmax(1)
+    img = torch.stack([fields[:, k % num_classes] for k in range(3)], 1) * 0.7 + 0.3 * torch.rand(n, 3, h, w, generator=g)
+    img = torch.round(img.clamp(0, 1) * 255) / 255
+    ign = torch.rand(n, h, w, generator=g) < 0.02
+    png = torch.where(ign, torch.full_like(png, num_classes), png)
+    return img.contiguous(), png.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------- model
+def vgg_features(params, x):
+    """VGG.forward (nets/vgg.py:21-31): 13 x [conv3x3 p1 + bias + ReLU] (nets/vgg.py:53-57), MaxPool2d(2,2) (:51)."""
+    feats = [None] * 5
+    it = iter(VGG_CONV_IDX)
+    for v in VGG_CFG:
+        if v == "M":
+            x = F.max_pool2d(x, kernel_size=2, stride=2)
+            continue
+        i = next(it)
+        x = F.relu(F.conv2d(x, params[f"vgg.features.{i}.weight"], params[f"vgg.features.{i}.bias"], padding=1))
+        if i in FEAT_AFTER:
+            feats[FEAT_AFTER[i]] = x
+    return feats
+
+
+def unet_up(params, name, skip, low):
+    """unetUp.forward (nets/unet.py:16-22): cat([skip, UpsamplingBilinear2d(2)(low)], 1) -> conv+ReLU -> conv+ReLU."""
+    up = F.interpolate(low, scale_factor=2, mode="bilinear", align_corners=True)   # nets/unet.py:13
+    x = torch.cat([skip, up], 1)                                                    # nets/unet.py:17
+    x = F.relu(F.conv2d(x, params[name + ".conv1.weight"], params[name + ".conv1.bias"], padding=1))
+    x = F.relu(F.conv2d(x, params[name + ".conv2.weight"], params[name + ".conv2.bias"], padding=1))
+    return x
+
+
+def unet_forward(params, x):
+    """Unet.forward, backbone='vgg' (nets/unet.py:62-78)."""
+    f1, f2, f3, f4, f5 = vgg_features(params, x)
+    up4 = unet_up(params, "up_concat4", f4, f5)
+    up3 = unet_up(params, "up_concat3", f3, up4)
+    up2 = unet_up(params, "up_concat2", f2, up3)
+    up1 = unet_up(params, "up_concat1", f1, up2)
+    return F.conv2d(up1, params["final.weight"], params["final.bias"])             # nets/unet.py:58,76
+
+
+# ----------------------------------------------------------------------------------------------- losses
+def ce_loss(logits, target, cls_weights, num_classes):
+    """CE_Loss (nets/unet_training.py:9-19): weighted mean NLL over pixels with target != num_classes."""
+    n, c, h, w = logits.shape
+    z = logits.permute(0, 2, 3, 1).reshape(-1, c)
+    y = target.reshape(-1)
+    valid = y != num_classes
+    lsm = z - torch.logsumexp(z, dim=1, keepdim=True)
+    yy = torch.where(valid, y, torch.zeros_like(y))
+    wy = cls_weights[yy] * valid
+    return -(wy * lsm.gather(1, yy[:, None])[:, 0]).sum() / wy.sum()
+
+
+def focal_loss(logits, target, cls_weights, num_classes, alpha=0.5, gamma=2):
+    """Focal_Loss (nets/unet_training.py:21-36): logpt = -w[y] nll (0 where ignored), mean over ALL pixels."""
+    n, c, h, w = logits.shape
+    z = logits.permute(0, 2, 3, 1).reshape(-1, c)
+    y = target.reshape(-1)
+    valid = y != num_classes
+    lsm = z - torch.logsumexp(z, dim=1, keepdim=True)
+    yy = torch.where(valid, y, torch.zeros_like(y))
+    logpt = cls_weights[yy] * valid * lsm.gather(1, yy[:, None])[:, 0]
+    pt = torch.exp(logpt)
+    if alpha is not None:
+        logpt = logpt * alpha
+    return (-((1 - pt) ** gamma) * logpt).mean()
+
+
+def _tp_fp_fn(prob, onehot):
+    t = onehot[..., :-1]
+    tp = (t * prob).sum((0, 1))
+    return tp, prob.sum((0, 1)) - tp, t.sum((0, 1)) - tp
+
+
+def dice_loss(logits, onehot, beta=1, smooth=1e-5):
+    """Dice_loss (nets/unet_training.py:38-56); onehot: (N,H,W,C+1) fp32, last channel = ignore."""
+    n, c, h, w = logits.shape
+    p = torch.softmax(logits.permute(0, 2, 3, 1).reshape(n, -1, c), -1)
+    tp, fp, fn = _tp_fp_fn(p, onehot.reshape(n, -1, c + 1))
+    score = ((1 + beta ** 2) * tp + smooth) / ((1 + beta ** 2) * tp + beta ** 2 * fn + fp + smooth)
+    return 1 - score.mean()
+
+
+def f_score(logits, onehot, beta=1, smooth=1e-5, threhold=0.5):
+    """f_score (utils/utils_metrics.py:12-31)."""
+    n, c, h, w = logits.shape
+    p = torch.softmax(logits.permute(0, 2, 3, 1).reshape(n, -1, c), -1)
+    p = (p > threhold).float()
+    tp, fp, fn = _tp_fp_fn(p, onehot.reshape(n, -1, c + 1))
+    score = ((1 + beta ** 2) * tp + smooth) / ((1 + beta ** 2) * tp + beta ** 2 * fn + fp + smooth)
+    return score.mean()
+
+
+def one_hot(png, num_classes):
+    """np.eye(num_classes + 1)[png] (utils/dataloader.py:49-50)."""
+    return torch.eye(num_classes + 1)[png]
+
+
+def train_step(params, imgs, pngs, cls_weights, num_classes, dice=True, focal=False):
+    """One iteration of fit_one_epoch without the optimizer (utils/utils_fit.py:66-92): forward, CE|Focal (+Dice),
+    backward.  Returns (loss, logits, grads dict)."""
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+    logits = unet_forward(p, imgs)
+    loss = focal_loss(logits, pngs, cls_weights, num_classes) if focal else ce_loss(logits, pngs, cls_weights, num_classes)
+    if dice:
+        loss = loss + dice_loss(logits, one_hot(pngs, num_classes))
+    grads = torch.autograd.grad(loss, list(p.values()))
+    return loss.detach(), logits.detach(), dict(zip(p.keys(), grads))
+
+
+# ----------------------------------------------------------------------------------------------- metrics
+def fast_hist(a, b, n):
+    """fast_hist (utils/utils_metrics.py:34-43) on flat integer numpy arrays."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    k = (a >= 0) & (a < n)
+    return np.bincount(n * a[k].astype(int) + b[k], minlength=n ** 2).reshape(n, n)
+
+
+def per_class_iu(hist):
+    """utils/utils_metrics.py:45-46"""
+    return np.diag(hist) / np.maximum((hist.sum(1) + hist.sum(0) - np.diag(hist)), 1)
+
+
+def per_class_PA_Recall(hist):
+    """utils/utils_metrics.py:48-49"""
+    return np.diag(hist) / np.maximum(hist.sum(1), 1)
+
+
+def per_class_Precision(hist):
+    """utils/utils_metrics.py:51-52"""
+    return np.diag(hist) / np.maximum(hist.sum(0), 1)
+
+
+def make_masks(n_masks, n, h=512, w=512, seed=0):
+    """Config-5 masks: gt = randint(0,n) with 3 % = 255, pred = gt with 20 % re-drawn."""
+    rng = np.random.default_rng(seed)
+    gt = rng.integers(0, n, size=(n_masks, h, w), dtype=np.uint8)
+    pred = gt.copy()
+    redraw = rng.random((n_masks, h, w)) < 0.2
+    pred[redraw] = rng.integers(0, n, size=int(redraw.sum()), dtype=np.uint8)
+    gt[rng.random((n_masks, h, w)) < 0.03] = 255
+    return gt, pred

@@ -1,0 +1,64 @@
+"""CPU: the C-ABI library builds, loads and exports exactly what include/b2u.h declares; the product path has no
+CPU fallback."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "b2u.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2u_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(b2u):
+    names = _declared()
+    assert len(names) >= 30
+    h = ctypes.CDLL(b2u._lib.LIB_PATH)
+    for n in names:
+        assert hasattr(h, n), f"{n} declared in include/b2u.h but not exported"
+
+
+def test_ctypes_signatures_cover_the_header(b2u):
+    assert sorted(b2u._lib.SIGNATURES.keys()) == _declared()
+
+
+def test_version_and_error_channel_without_gpu(b2u):
+    lib = b2u._lib.lib()
+    assert lib.b2u_version() >= 100
+    # argument validation happens before any CUDA call: a bad shape reports through the error channel
+    rc = lib.b2u_fast_hist(None, None, 10, 0, 0, None, None)
+    assert rc == 1 and b"fast_hist" in lib.b2u_last_error()
+    rc = lib.b2u_conv_fprop(None, 60, None, 0, None, None, None, 1, 8, 8, 64, 9, 1, 0, None)
+    assert rc == 1 and b"multiples of 64" in lib.b2u_last_error()
+    assert lib.b2u_conv_wgrad_workspace(16, 512, 512, 64, 64, 9) > 0
+
+
+def test_product_path_has_no_cpu_fallback(b2u):
+    m = b2u.Unet(num_classes=2)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 32, 32))
+    with pytest.raises(ValueError):
+        b2u.ops.maxpool2x2(torch.zeros(1, 4, 4, 8, dtype=torch.bfloat16))
+    with pytest.raises(RuntimeError):
+        b2u.CE_Loss(torch.zeros(1, 2, 4, 4), torch.zeros(1, 4, 4, dtype=torch.long), torch.ones(2), num_classes=2)
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "unet-pytorch_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                assert "oracle" not in open(os.path.join(dirpath, f)).read(), f"{f} mentions the oracle"
+
+
+def test_missing_library_is_a_hard_error(b2u, monkeypatch):
+    monkeypatch.setattr(b2u._lib, "_lib", None)
+    monkeypatch.setattr(b2u._lib, "LIB_PATH", "/nonexistent/libb200unet.so")
+    with pytest.raises(b2u._lib.B2UError):
+        b2u._lib.lib()

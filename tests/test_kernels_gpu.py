@@ -1,0 +1,232 @@
+"""GPU: every CUDA kernel behind the C ABI against fp32 CPU references on the same seeded inputs.
+bf16 kernels: rel-L2 <= 6e-3 against the fp32 result of the same bf16-rounded operands (output rounding only);
+fp32 kernels (head, losses, wgrad accumulation): <= 1e-4; integer kernels: exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import unet_oracle as O
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def nhwc(x, dev):
+    return x.permute(0, 2, 3, 1).contiguous().to(BF).to(dev)
+
+
+def nchw(x):
+    return x.float().permute(0, 3, 1, 2).contiguous().cpu()
+
+
+CONV_CASES = [
+    # N, H, W, C0, C1, Cout, taps, relu
+    (1, 8, 16, 64, 0, 64, 9, True),        # exactly one tile
+    (2, 32, 48, 64, 0, 64, 9, True),
+    (2, 24, 40, 128, 0, 128, 9, True),     # ragged tiles in both directions
+    (1, 16, 16, 256, 0, 256, 9, False),
+    (1, 16, 16, 512, 0, 512, 9, True),
+    (1, 16, 32, 64, 128, 64, 9, True),     # virtual concat; dgrad N tile 192 split 64|128
+    (1, 16, 16, 512, 512, 512, 9, True),   # up_concat4.conv1 shape
+    (1, 4, 4, 512, 0, 512, 9, True),       # image smaller than the 8x16 tile
+    (2, 16, 16, 64, 0, 128, 1, False),     # 1x1
+    (1, 64, 64, 128, 256, 128, 9, True),   # dgrad 384 = 2 x 192
+]
+
+
+@pytest.mark.parametrize("N,H,W,C0,C1,Cout,taps,relu", CONV_CASES)
+def test_conv_fprop_dgrad_wgrad(b2u, cuda_device, N, H, W, C0, C1, Cout, taps, relu):
+    ops, dev = b2u.ops, cuda_device
+    g = torch.Generator().manual_seed(1)
+    k = 3 if taps == 9 else 1
+    x = torch.randn(N, C0 + C1, H, W, generator=g)
+    w = torch.randn(Cout, C0 + C1, k, k, generator=g) / ((C0 + C1) * taps) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    xb = nhwc(x, dev); xr = nchw(xb)
+    wr = w.to(BF).float()
+    wf, wd = ops.pack_weights(w.to(dev))
+    x0 = xb[..., :C0].contiguous(); x1 = xb[..., C0:].contiguous() if C1 else None
+    y = ops.conv_fprop(x0, wf, b.to(dev), Cout, taps=taps, relu=relu, x1=x1)
+    ref = F.conv2d(xr, wr, b, padding=k // 2)
+    ref = ref.relu() if relu else ref
+    assert rel(nchw(y), ref) <= 6e-3
+    dz = torch.randn(N, Cout, H, W, generator=g)
+    dzb = nhwc(dz, dev); dzr = nchw(dzb)
+    ref_dx = F.conv_transpose2d(dzr, wr, padding=k // 2)
+    if C1:
+        d0, d1 = ops.conv_dgrad(dzb, wd, C0, taps=taps, C1=C1)
+        assert rel(torch.cat([nchw(d0), nchw(d1)], 1), ref_dx) <= 6e-3
+    else:
+        mask = nhwc(torch.randn(N, C0, H, W, generator=g), dev)
+        d0 = ops.conv_dgrad(dzb, wd, C0, taps=taps, mask=mask)
+        assert rel(nchw(d0), ref_dx * (nchw(mask) > 0)) <= 6e-3
+    ref_dw = torch.nn.grad.conv2d_weight(xr, w.shape, dzr, padding=k // 2)
+    for flags in (0, 1):          # merged N=192 vertical taps and the three-instruction variant
+        dw = ops.conv_wgrad(x0, dzb, taps=taps, x1=x1, flags=flags)
+        assert rel(dw, ref_dw) <= 1e-4
+    assert rel(ops.bias_grad(dzb), dzr.sum((0, 2, 3))) <= 1e-4
+
+
+def test_first_layer_im2col_conv(b2u, cuda_device):
+    ops, dev = b2u.ops, cuda_device
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(2, 3, 32, 48, generator=g)
+    w = torch.randn(64, 3, 3, 3, generator=g) / 27 ** 0.5
+    b = torch.randn(64, generator=g)
+    col = ops.im2col_first(x.to(dev))
+    y = ops.conv_fprop(col, ops.pack_weights_first(w.to(dev)), b.to(dev), 64, taps=1, relu=True)
+    ref = F.conv2d(x.to(BF).float(), w.to(BF).float(), b, padding=1).relu()
+    assert rel(nchw(y), ref) <= 6e-3
+    dzb = nhwc(torch.randn(2, 64, 32, 48, generator=g), dev)
+    dw = ops.conv_wgrad(col, dzb, taps=1, first_cin=3)
+    ref_dw = torch.nn.grad.conv2d_weight(x.to(BF).float(), w.shape, nchw(dzb), padding=1)
+    assert rel(dw, ref_dw) <= 1e-4
+
+
+@pytest.mark.parametrize("N,H,W,C", [(2, 16, 32, 64), (1, 8, 8, 128), (1, 2, 2, 512), (3, 6, 10, 8)])
+def test_pool_and_upsample(b2u, cuda_device, N, H, W, C):
+    ops, dev = b2u.ops, cuda_device
+    g = torch.Generator().manual_seed(3)
+    xb = nhwc(torch.randn(N, C, H, W, generator=g).relu(), dev)
+    xr = nchw(xb).requires_grad_(True)
+    ref = F.max_pool2d(xr, 2, 2)
+    assert torch.equal(nchw(ops.maxpool2x2(xb)), ref.detach())
+    dp = nhwc(torch.randn(N, C, H // 2, W // 2, generator=g), dev)
+    dsk = nhwc(torch.randn(N, C, H, W, generator=g), dev)
+    ref.backward(nchw(dp))
+    want = (xr.grad + nchw(dsk)) * (xr > 0)
+    assert rel(nchw(ops.maxpool2x2_bwd(dp, xb, dskip=dsk, relu_mask=True)), want) <= 4e-3
+    xr2 = nchw(xb).requires_grad_(True)
+    refu = F.interpolate(xr2, scale_factor=2, mode="bilinear", align_corners=True)   # nets/unet.py:13
+    assert rel(nchw(ops.upsample2x(xb)), refu.detach()) <= 4e-3
+    du = nhwc(torch.randn(N, C, 2 * H, 2 * W, generator=g), dev)
+    refu.backward(nchw(du))
+    assert rel(nchw(ops.upsample2x_bwd(du, ylow=xb)), xr2.grad * (xr2 > 0)) <= 4e-3
+
+
+@pytest.mark.parametrize("C,use_onehot,cw", [(21, False, None), (4, True, [1, 15, 1.5, 2]), (2, True, [1, 1]), (4, False, [1, 15, 0, 0])])
+def test_head_and_losses_against_oracle(b2u, cuda_device, C, use_onehot, cw):
+    ops, dev = b2u.ops, cuda_device
+    g = torch.Generator().manual_seed(4)
+    N, H, W = 2, 32, 48
+    xb = nhwc(torch.randn(N, 64, H, W, generator=g).relu(), dev)
+    xr = nchw(xb).requires_grad_(True)
+    w = (torch.randn(C, 64, 1, 1, generator=g) / 8).requires_grad_(True)
+    b = torch.randn(C, generator=g).requires_grad_(True)
+    logits = ops.head_fwd(xb, w.detach().reshape(C, 64).contiguous().to(dev), b.detach().to(dev))
+    ref = F.conv2d(xr, w, b)
+    assert rel(logits, ref) <= 1e-5
+    png = torch.randint(0, C + 1, (N, H, W), generator=g)
+    oh = O.one_hot(png, C)
+    weights = torch.ones(C) if cw is None else torch.tensor(cw, dtype=torch.float32)
+    ce, fo = O.ce_loss(ref, png, weights, C), O.focal_loss(ref, png, weights, C)
+    di, fs = O.dice_loss(ref, oh), O.f_score(ref, oh)
+    fin = ops.loss_fwd(logits, target=png.to(dev), onehot=oh.to(dev) if use_onehot else None, cls_w=weights.to(dev)).cpu()
+    for got, want in zip(fin[:4], (ce, fo, di, fs)):
+        assert abs(got.item() - want.item()) <= 2e-5 * max(abs(want.item()), 1e-3)
+    for gs, loss in (([1, 0, 0], ce), ([0, 1, 0], fo), ([0, 0, 1], di), ([1, 0, 1], ce + di)):
+        gl, = torch.autograd.grad(loss, ref, retain_graph=True)
+        dl = ops.loss_bwd(logits, fin.to(dev), torch.tensor(gs, dtype=torch.float32, device=dev), target=png.to(dev),
+                          onehot=oh.to(dev) if use_onehot else None, cls_w=weights.to(dev))
+        assert rel(dl, gl) <= 2e-4
+    gl, = torch.autograd.grad(ce + di, ref, retain_graph=True)
+    (ce + di).backward()
+    dx, dw, db = ops.head_bwd(gl.contiguous().to(dev), xb, w.detach().reshape(C, 64).contiguous().to(dev))
+    assert rel(nchw(dx), xr.grad * (xr > 0)) <= 4e-3
+    assert rel(dw, w.grad) <= 1e-4 and rel(db, b.grad) <= 1e-4
+    assert torch.equal(ops.argmax_u8(logits).cpu().long(), logits.cpu().argmax(1))
+
+
+def test_losses_against_reference_golden(b2u, cuda_device, golden_dir):
+    """Drop-in CE_Loss / Focal_Loss / Dice_loss / f_score against values the reference itself produced."""
+    dev = cuda_device
+    g = np.load(os.path.join(golden_dir, "losses.npz"))
+    for C in (21, 4, 2):
+        logits = torch.from_numpy(g[f"C{C}:logits"]).to(dev).requires_grad_(True)
+        png = torch.from_numpy(g[f"C{C}:png"]).to(dev)
+        w = torch.from_numpy(g[f"C{C}:w"]).to(dev)
+        oh = O.one_hot(torch.from_numpy(g[f"C{C}:png"]), C).to(dev)
+        ce = b2u.CE_Loss(logits, png, w, num_classes=C)
+        fo = b2u.Focal_Loss(logits, png, w, num_classes=C)
+        di = b2u.Dice_loss(logits, oh)
+        fs = b2u.f_score(logits, oh)
+        for got, want in zip((ce, fo, di, fs), g[f"C{C}:vals"]):
+            assert abs(got.item() - want) <= 2e-5 * max(abs(want), 1e-3)
+        for loss, key in ((ce, "g_ce"), (fo, "g_focal"), (di, "g_dice")):
+            gr, = torch.autograd.grad(loss, logits, retain_graph=True)
+            assert rel(gr, torch.from_numpy(g[f"C{C}:{key}"])) <= 2e-4
+
+
+@pytest.mark.parametrize("n", [2, 4, 21])
+def test_fast_hist_bit_exact(b2u, cuda_device, golden_dir, n):
+    g = np.load(os.path.join(golden_dir, "fast_hist.npz"))
+    gt, pred = O.make_masks(3, n, h=64, w=96, seed=n)
+    hist = np.zeros((n, n))
+    for i in range(3):
+        hist += b2u.fast_hist(gt[i].flatten(), pred[i].flatten(), n)       # the compute_mIoU loop, utils_metrics.py:95
+    assert np.array_equal(hist.astype(np.int64), g[f"n{n}:hist"])
+    assert np.array_equal(b2u.per_class_iu(hist), g[f"n{n}:iou"])
+    assert np.nanmean(b2u.per_class_iu(hist)) == float(g[f"n{n}:miou"])
+    # other integer dtypes, ragged lengths, negative labels
+    rng = np.random.default_rng(n)
+    a = rng.integers(-2, n + 2, size=100003).astype(np.int64)
+    b = rng.integers(0, n, size=100003).astype(np.int64)
+    assert np.array_equal(b2u.fast_hist(a, b, n), O.fast_hist(a, b, n))
+    a32, b32 = a.astype(np.int32), b.astype(np.int32)
+    assert np.array_equal(b2u.fast_hist(a32, b32, n), O.fast_hist(a32, b32, n))
+
+
+def test_fast_hist_edge_cases(b2u, cuda_device, golden_dir):
+    g = np.load(os.path.join(golden_dir, "fast_hist.npz"))
+    assert np.array_equal(b2u.fast_hist(np.full(1000, 255, np.uint8), np.zeros(1000, np.uint8), 21), g["allignore:hist"])
+    assert np.array_equal(b2u.fast_hist(np.full(1000, 3, np.uint8), np.full(1000, 3, np.uint8), 21), g["single:hist"])
+    assert np.array_equal(b2u.fast_hist(np.zeros(0, np.uint8), np.zeros(0, np.uint8), 4), g["empty:hist"])
+    with pytest.raises(ValueError):
+        b2u.fast_hist(np.array([1], np.uint8), np.array([200], np.uint8), 2)
+    # unaligned device views take the scalar path
+    a = torch.randint(0, 21, (4099,), dtype=torch.uint8); b = torch.randint(0, 21, (4099,), dtype=torch.uint8)
+    got = b2u.fast_hist(a.cuda()[3:], b.cuda()[3:], 21)
+    assert np.array_equal(got, O.fast_hist(a[3:].numpy(), b[3:].numpy(), 21))
+
+
+def test_fast_hist_full_size_properties(b2u, cuda_device):
+    """BASELINE config 5 size (512x512 masks): exact against numpy on 50 masks; sum of per-mask histograms ==
+    histogram of the concatenation; total count == number of non-ignored pixels."""
+    n = 21
+    gt, pred = O.make_masks(50, n, seed=0)
+    dev_hist = None
+    for i in range(gt.shape[0]):
+        dev_hist = b2u.fast_hist_device(gt[i], pred[i], n, hist=dev_hist)
+    acc = dev_hist.cpu().numpy()
+    assert acc[-1] == 0
+    whole = b2u.fast_hist(gt.reshape(-1), pred.reshape(-1), n)
+    assert np.array_equal(acc[:-1].reshape(n, n), whole)
+    assert np.array_equal(whole, O.fast_hist(gt.reshape(-1), pred.reshape(-1), n))
+    assert whole.sum() == int((gt < n).sum())
+
+
+def test_optimizer_steps_match_torch(b2u, cuda_device):
+    ops, dev = b2u.ops, cuda_device
+    g = torch.Generator().manual_seed(6)
+    n = 4096 * 3
+    p0 = torch.randn(n, generator=g)
+    grads = [torch.randn(n, generator=g) for _ in range(3)]
+    for kind in ("adam", "sgd"):
+        p_ref = p0.clone().requires_grad_(True)
+        opt = torch.optim.Adam([p_ref], lr=1e-3) if kind == "adam" else torch.optim.SGD([p_ref], lr=1e-2, momentum=0.9, nesterov=True)
+        p = p0.clone().to(dev); m = torch.zeros_like(p); v = torch.zeros_like(p)
+        for step, gr in enumerate(grads, 1):
+            p_ref.grad = gr.clone(); opt.step()
+            if kind == "adam":
+                ops.adam_step(p, gr.to(dev), m, v, step, 1e-3)
+            else:
+                ops.sgd_step(p, gr.to(dev), m, 1e-2, momentum=0.9, nesterov=True, first_step=(step == 1))
+        assert rel(p, p_ref.detach()) <= 1e-6

@@ -1,0 +1,98 @@
+"""CPU: pins the oracle (oracle/unet_oracle.py, oracle/fast_hist.c) against golden vectors produced by the
+UNMODIFIED reference (oracle/make_golden.py -> tests/golden/)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import unet_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _sample(flat):
+    if flat.numel() <= 4096:
+        return flat
+    return flat[torch.linspace(0, flat.numel() - 1, 4096).long()]
+
+
+@pytest.mark.parametrize("tag", ["nc2_medical", "nc21_cedice", "nc4_focaldice"])
+def test_model_matches_reference_golden(tag, golden_dir):
+    torch.set_num_threads(max(torch.get_num_threads(), 4))
+    g = np.load(os.path.join(golden_dir, f"unet_vgg_{tag}.npz"))
+    C, n, h, w, seed, medical, dice, focal = [int(v) for v in g["meta"]]
+    params = O.make_params(C, seed=11)
+    imgs, pngs = O.make_inputs(n, C, h, w, seed=seed, medical=bool(medical))
+    loss, logits, grads = O.train_step(params, imgs, pngs, torch.from_numpy(g["cls_w"]), C, dice=bool(dice), focal=bool(focal))
+    ref = torch.from_numpy(g["logits"])
+    assert ((logits - ref).norm() / ref.norm()).item() <= 1e-5
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    fs = O.f_score(logits, O.one_hot(pngs, C)).item()
+    assert abs(fs - float(g["f_score"])) <= 1e-5
+    for name, gr in grads.items():
+        gn = float(g["gnorm:" + name])
+        assert abs(gr.double().norm().item() - gn) <= 2e-4 * gn + 1e-12, name
+        s = _sample(gr.reshape(-1))
+        ref_s = torch.from_numpy(g["g:" + name])
+        assert (s - ref_s).norm().item() <= 2e-4 * ref_s.norm().item() + 1e-9, name
+
+
+@pytest.mark.parametrize("C", [21, 4, 2])
+def test_losses_match_reference_golden(C, golden_dir):
+    g = np.load(os.path.join(golden_dir, "losses.npz"))
+    logits = torch.from_numpy(g[f"C{C}:logits"]).requires_grad_(True)
+    png = torch.from_numpy(g[f"C{C}:png"])
+    w = torch.from_numpy(g[f"C{C}:w"])
+    oh = O.one_hot(png, C)
+    ce = O.ce_loss(logits, png, w, C)
+    fo = O.focal_loss(logits, png, w, C)
+    di = O.dice_loss(logits, oh)
+    fs = O.f_score(logits, oh)
+    vals = g[f"C{C}:vals"]
+    for got, want in zip((ce, fo, di, fs), vals):
+        assert abs(got.item() - want) <= 1e-5 * max(abs(want), 1e-3)
+    for loss, key in ((ce, "g_ce"), (fo, "g_focal"), (di, "g_dice")):
+        gr, = torch.autograd.grad(loss, logits, retain_graph=True)
+        ref = torch.from_numpy(g[f"C{C}:{key}"])
+        assert ((gr - ref).norm() / ref.norm()).item() <= 1e-5
+
+
+def _c_oracle():
+    so = os.path.join(ROOT, "oracle", "_ref", "libfasthist.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+    lib = ctypes.CDLL(so)
+    lib.oracle_fast_hist_u8.restype = ctypes.c_longlong
+    lib.oracle_fast_hist_u8.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+    return lib
+
+
+@pytest.mark.parametrize("n", [2, 4, 21])
+def test_fast_hist_matches_reference_golden(n, golden_dir):
+    g = np.load(os.path.join(golden_dir, "fast_hist.npz"))
+    gt, pred = O.make_masks(3, n, h=64, w=96, seed=n)
+    hist = np.zeros((n, n), np.int64)
+    chist = np.zeros(n * n, np.int64)
+    lib = _c_oracle()
+    for i in range(3):
+        hist += O.fast_hist(gt[i].flatten(), pred[i].flatten(), n)
+        a = np.ascontiguousarray(gt[i].flatten()); b = np.ascontiguousarray(pred[i].flatten())
+        assert lib.oracle_fast_hist_u8(a.ctypes.data, b.ctypes.data, a.size, n, chist.ctypes.data) == 0
+    assert np.array_equal(hist, g[f"n{n}:hist"])
+    assert np.array_equal(chist.reshape(n, n), g[f"n{n}:hist"])
+    assert np.array_equal(O.per_class_iu(hist), g[f"n{n}:iou"])            # float64 of exact ints: bit-exact
+    assert np.array_equal(O.per_class_PA_Recall(hist), g[f"n{n}:recall"])
+    assert np.array_equal(O.per_class_Precision(hist), g[f"n{n}:precision"])
+    assert np.nanmean(O.per_class_iu(hist)) == float(g[f"n{n}:miou"])
+
+
+def test_fast_hist_edge_cases(golden_dir):
+    g = np.load(os.path.join(golden_dir, "fast_hist.npz"))
+    assert np.array_equal(O.fast_hist(np.full(1000, 255, np.uint8), np.zeros(1000, np.uint8), 21), g["allignore:hist"])
+    assert np.array_equal(O.fast_hist(np.full(1000, 3, np.uint8), np.full(1000, 3, np.uint8), 21), g["single:hist"])
+    assert np.array_equal(O.fast_hist(np.zeros(0, np.uint8), np.zeros(0, np.uint8), 4), g["empty:hist"])
+    with pytest.raises(ValueError):       # b >= n pushes a bin past n*n: numpy's reshape raises, like the reference
+        O.fast_hist(np.array([1], np.uint8), np.array([200], np.uint8), 2)

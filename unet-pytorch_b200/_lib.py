@@ -13,6 +13,8 @@ SIGNATURES = {
     "b2u_last_error": (c_char_p, []),
     "b2u_version": (I, []),
     "b2u_num_sms": (I, []),
+    "b2u_launch_count": (LL, []),
+    "b2u_reset_launch_count": (None, []),
     "b2u_im2col_first": (I, [P, P, I, I, I, I, P]),
     "b2u_pack_weights": (I, [P, P, P, I, I, I, P]),
     "b2u_pack_weights_first": (I, [P, P, I, I, P]),

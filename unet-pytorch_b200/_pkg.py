@@ -5,3 +5,5 @@ from .nets.unet import Unet  # noqa: F401
 from .nets.unet_training import CE_Loss, Dice_loss, Focal_Loss, ce_dice_loss  # noqa: F401
 from .utils.utils_metrics import (f_score, fast_hist, fast_hist_device, per_Accuracy, per_class_iu,  # noqa: F401
                                   per_class_PA_Recall, per_class_Precision)
+from .trainer import UnetTrainer, FlatBuckets, GradientSync  # noqa: F401,E402
+from . import synthetic  # noqa: F401,E402

@@ -17,6 +17,8 @@ namespace b2u {
 // records a thread-local message, returns `code`
 int set_error(int code, const char* fmt, ...);
 int num_sms();
+// counts kernel launches made by this library (bench.py reports them as gpu_launches)
+void note_launch(int n = 1);
 
 // NHWC bf16 tensor viewed as a rank-4 TMA tensor (C, W, H, N); `cpitch` = elements between pixels.
 int make_tmap_nhwc(CUtensorMap* out, const void* base, int N, int H, int W, int C, int boxC, int boxW, int boxH,

@@ -339,6 +339,7 @@ static int launch_cfg(const ConvLaunch& a, cudaStream_t st) {
   kern<<<grid, 192, Cfg::kSmemBytes, st>>>(tmA0, tmA1, tmB, tmC0, tmC1, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(B2U_ERR_CUDA, "conv_igemm launch: %s", cudaGetErrorString(e));
+  note_launch();
   return 0;
 }
 

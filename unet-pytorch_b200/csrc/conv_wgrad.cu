@@ -316,6 +316,7 @@ static int launch_wgrad_cfg(const void* x0, int C0, const void* x1, int C1, cons
   kern<<<grid, 192, Cfg::kSmemBytes, st>>>(tmX0, tmX1, tmDZ, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(B2U_ERR_CUDA, "conv_wgrad launch: %s", cudaGetErrorString(e));
+  note_launch();
   return 0;
 }
 
@@ -360,6 +361,7 @@ int b2u_conv_wgrad(const void* x0, int C0, const void* x1, int C1, const void* d
                                                            cin_real, first_cin > 0 ? 1 : 0);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(B2U_ERR_CUDA, "wgrad_reduce launch: %s", cudaGetErrorString(e));
+  note_launch();
   return 0;
 }
 

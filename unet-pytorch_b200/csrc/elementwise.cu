@@ -24,6 +24,7 @@ static inline int grid_for(long long n, int block) {
   do {                                                                                                   \
     cudaError_t e__ = cudaGetLastError();                                                                \
     if (e__ != cudaSuccess) return b2u::set_error(B2U_ERR_CUDA, name " launch: %s", cudaGetErrorString(e__)); \
+    b2u::note_launch();                                                                                  \
   } while (0)
 
 __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }

@@ -17,6 +17,7 @@ namespace b2u {
   do {                                                                                                   \
     cudaError_t e__ = cudaGetLastError();                                                                \
     if (e__ != cudaSuccess) return b2u::set_error(B2U_ERR_CUDA, name " launch: %s", cudaGetErrorString(e__)); \
+    b2u::note_launch();                                                                                  \
   } while (0)
 
 constexpr int kMaxCls = 32;

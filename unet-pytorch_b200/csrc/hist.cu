@@ -105,6 +105,7 @@ int b2u_fast_hist(const void* a, const void* b, long long len, int n, int dtype,
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(B2U_ERR_CUDA, "fast_hist launch: %s", cudaGetErrorString(e));
+    note_launch();
   }
   return 0;
 }

@@ -66,6 +66,7 @@ int b2u_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
       reinterpret_cast<float4*>(exp_avg_sq), n4, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(B2U_ERR_CUDA, "adam_step launch: %s", cudaGetErrorString(e));
+  note_launch();
   return 0;
 }
 
@@ -79,6 +80,7 @@ int b2u_sgd_step(float* param, const float* grad, float* momentum_buf, long long
       lr, momentum, weight_decay, nesterov, first_step, grad_scale);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(B2U_ERR_CUDA, "sgd_step launch: %s", cudaGetErrorString(e));
+  note_launch();
   return 0;
 }
 

@@ -1,6 +1,7 @@
 // runtime.cu -- error reporting, device queries and TMA tensor-map encoding for libb200unet.so
 #include <cstdarg>
 #include <cstdio>
+#include <atomic>
 #include <mutex>
 
 #include "b2u_internal.h"
@@ -17,6 +18,11 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 const char* last_error() { return g_err; }
+
+static std::atomic<long long> g_launches{0};
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+void reset_launch_count() { g_launches.store(0); }
 
 int num_sms() {
   static int cached[64] = {0};
@@ -89,9 +95,11 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t row
 
 }  // namespace b2u
 
-namespace b2u { const char* last_error(); }
+namespace b2u { const char* last_error(); long long launch_count(); void reset_launch_count(); }
 extern "C" {
 const char* b2u_last_error(void) { return b2u::last_error(); }
 int b2u_version(void) { return 100; }
 int b2u_num_sms(void) { return b2u::num_sms(); }
+long long b2u_launch_count(void) { return b2u::launch_count(); }
+void b2u_reset_launch_count(void) { b2u::reset_launch_count(); }
 }

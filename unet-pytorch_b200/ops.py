@@ -22,6 +22,49 @@ def _req(t, dtype, name):
         raise ValueError(f"{name}: expected a contiguous tensor")
 
 
+class KernelTimer:
+    """CUDA-event timer around individual launches of the tensor-core kernels (bench.py's roofline leg).
+    Events are recorded on the launching (current) stream; read() synchronises once at the end."""
+
+    def __init__(self):
+        self.records = {}       # tag -> [(start, end, flops)]
+
+    def add(self, tag, start, end, flops):
+        self.records.setdefault(tag, []).append((start, end, flops))
+
+    def read(self):
+        torch.cuda.synchronize()
+        out = {}
+        for tag, recs in self.records.items():
+            ms = sum(a.elapsed_time(b) for a, b, _ in recs)
+            out[tag] = {"launches": len(recs), "ms": ms, "flops": float(sum(f for _, _, f in recs))}
+        return out
+
+
+_TIMER = None
+
+
+def set_timer(timer):
+    global _TIMER
+    _TIMER = timer
+
+
+class _timed:
+    def __init__(self, tag, flops):
+        self.tag, self.flops = tag, flops
+
+    def __enter__(self):
+        if _TIMER is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if _TIMER is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            _TIMER.add(self.tag, self.a, b, self.flops)
+
+
 def _ws(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
@@ -81,8 +124,9 @@ def conv_fprop(x0, wf, bias, Cout, taps=9, relu=True, x1=None, out=None, bn=0):
     C1 = 0 if x1 is None else x1.shape[3]
     if out is None:
         out = torch.empty((N, H, W, Cout), dtype=BF16, device=x0.device)
-    check(lib().b2u_conv_fprop(ptr(x0), C0, ptr(x1), C1, ptr(wf), ptr(bias), ptr(out), N, H, W, Cout, taps,
-                               1 if relu else 0, bn, stream_ptr()))
+    with _timed("conv_igemm", 2.0 * N * H * W * Cout * (C0 + C1) * taps):
+        check(lib().b2u_conv_fprop(ptr(x0), C0, ptr(x1), C1, ptr(wf), ptr(bias), ptr(out), N, H, W, Cout, taps,
+                                   1 if relu else 0, bn, stream_ptr()))
     return out
 
 
@@ -93,8 +137,9 @@ def conv_dgrad(dz, wd, C0, taps=9, C1=0, mask=None, out0=None, out1=None, bn=0):
         out0 = torch.empty((N, H, W, C0), dtype=BF16, device=dz.device)
     if C1 > 0 and out1 is None:
         out1 = torch.empty((N, H, W, C1), dtype=BF16, device=dz.device)
-    check(lib().b2u_conv_dgrad(ptr(dz), Cz, ptr(wd), ptr(out0), C0, ptr(out1) if C1 > 0 else None, C1, ptr(mask),
-                               N, H, W, taps, bn, stream_ptr()))
+    with _timed("conv_igemm", 2.0 * N * H * W * Cz * (C0 + C1) * taps):
+        check(lib().b2u_conv_dgrad(ptr(dz), Cz, ptr(wd), ptr(out0), C0, ptr(out1) if C1 > 0 else None, C1, ptr(mask),
+                                   N, H, W, taps, bn, stream_ptr()))
     return (out0, out1) if C1 > 0 else out0
 
 
@@ -112,8 +157,9 @@ def conv_wgrad(x0, dz, taps=9, x1=None, first_cin=0, dw=None, ws=None, flags=0):
         else:
             k = 3 if taps == 9 else 1
             dw = torch.empty((Cout, C0 + C1, k, k), dtype=torch.float32, device=x0.device)
-    check(lib().b2u_conv_wgrad(ptr(x0), C0, ptr(x1), C1, ptr(dz), Cout, ptr(dw), ptr(ws),
-                               ws.numel() * ws.element_size(), N, H, W, taps, first_cin, flags, stream_ptr()))
+    with _timed("conv_wgrad", 2.0 * N * H * W * Cout * (C0 + C1) * taps):
+        check(lib().b2u_conv_wgrad(ptr(x0), C0, ptr(x1), C1, ptr(dz), Cout, ptr(dw), ptr(ws),
+                                   ws.numel() * ws.element_size(), N, H, W, taps, first_cin, flags, stream_ptr()))
     return dw
 
 

@@ -1,0 +1,260 @@
+"""Data-parallel training step of the VGG16-UNet hot path: what one iteration of the reference's
+`fit_one_epoch` does between the DataLoader and `loss.item()` (utils/utils_fit.py:26-97), with the model wrapped
+as train.py:335-350 wraps it (one process per GPU, gradients averaged across ranks).
+
+  train_step(imgs, pngs):  [H2D] -> forward -> CE|Focal (+Dice) (+f_score) -> backward -> bucketed all-reduce
+                           (overlapped with the remaining wgrad/dgrad kernels) -> Adam/SGD step
+
+All parameters, gradients and optimizer moments live in flat fp32 buffers laid out in *backward completion order*
+(final, up_concat1.conv2, ..., vgg.features.0) so each all-reduce bucket is one contiguous slice that becomes
+ready front to back, and one kernel launch updates every parameter.  Like DDP in the reference, every rank
+normalises its loss over its own shard and the ranks' gradients are averaged.
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .engine import VGGUnetEngine, vgg_unet_param_shapes
+
+
+def _backward_order(names):
+    """state_dict order -> order in which VGGUnetEngine.backward completes the gradients."""
+    def layer(n):
+        return n.rsplit(".", 1)[0]
+    layers = []
+    for n in names:
+        if layer(n) not in layers:
+            layers.append(layer(n))
+    enc = [l for l in layers if l.startswith("vgg.")]
+    dec = [l for l in layers if l.startswith("up_concat")]
+    # decoder executes up_concat4 .. up_concat1 (conv1, conv2); backward walks it in reverse, then the encoder in reverse
+    dec_exec = sorted(dec, key=lambda l: (-int(l[len("up_concat")]), l.endswith("conv2")))
+    order = ["final"] + dec_exec[::-1] + enc[::-1]
+    out = []
+    for l in order:
+        out += [l + ".weight", l + ".bias"]
+    assert sorted(out) == sorted(names)
+    return out
+
+
+class FlatBuckets:
+    """Flat fp32 storage for a set of named tensors + contiguous buckets for gradient all-reduce.
+    Device-agnostic (the gloo tests run it on CPU)."""
+
+    def __init__(self, shapes, order, device, bucket_bytes=16 << 20):
+        self.order = list(order)
+        self.offsets = {}
+        off = 0
+        for n in self.order:
+            numel = 1
+            for s in shapes[n]:
+                numel *= s
+            self.offsets[n] = (off, numel, tuple(shapes[n]))
+            off += (numel + 3) // 4 * 4            # 16-byte aligned slices
+        self.total = off
+        self.device = device
+        # buckets: consecutive parameters until bucket_bytes is reached
+        self.buckets = []          # (start, end, [names])
+        start, names = 0, []
+        for n in self.order:
+            o, numel, _ = self.offsets[n]
+            names.append(n)
+            end = o + (numel + 3) // 4 * 4
+            if (end - start) * 4 >= bucket_bytes:
+                self.buckets.append((start, end, names))
+                start, names = end, []
+        if names:
+            self.buckets.append((start, self.total, names))
+        self.bucket_of = {n: bi for bi, (_, _, ns) in enumerate(self.buckets) for n in ns}
+
+    def new_buffer(self):
+        return torch.zeros(self.total, dtype=torch.float32, device=self.device)
+
+    def views(self, flat):
+        return {n: flat[o:o + numel].view(shape) for n, (o, numel, shape) in self.offsets.items()}
+
+
+class GradientSync:
+    """Bucketed all-reduce (sum) of a flat gradient buffer on a side stream, fired as buckets complete."""
+
+    def __init__(self, layout, flat_grad, group=None, enabled=None):
+        self.layout = layout
+        self.flat = flat_grad
+        self.group = group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.enabled = (self.world > 1) if enabled is None else enabled
+        self.cuda = flat_grad.is_cuda
+        self.stream = torch.cuda.Stream(device=flat_grad.device) if (self.cuda and self.enabled) else None
+        self._pending = None
+        self._handles = []
+        self.reset()
+
+    def reset(self, active=None):
+        """active: names that will be reported ready this step (default: all)."""
+        names = set(self.layout.order if active is None else active)
+        self._pending = [sum(1 for n in ns if n in names) for (_, _, ns) in self.layout.buckets]
+        self._handles = []
+
+    def _fire(self, bi):
+        s, e, _ = self.layout.buckets[bi]
+        view = self.flat[s:e]
+        if self.cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self.stream.wait_event(ev)
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            self._handles.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def ready(self, names):
+        if not self.enabled:
+            return
+        for n in names:
+            bi = self.layout.bucket_of[n]
+            self._pending[bi] -= 1
+            if self._pending[bi] == 0:
+                self._fire(bi)
+
+    def finish(self):
+        """Makes the current stream wait for all fired buckets; returns the factor that turns the sum into a mean."""
+        if not self.enabled:
+            return 1.0
+        if self.cuda:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        else:
+            for h in self._handles:
+                h.wait()
+        return 1.0 / self.world
+
+
+class UnetTrainer:
+    def __init__(self, num_classes=21, device=None, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                 optimizer="adam", momentum=0.9, cls_weights=None, dice_loss=True, focal_loss=False,
+                 state_dict=None, process_group=None, bucket_mb=16, compute_f_score=True):
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("UnetTrainer needs a CUDA device (no CPU fallback)")
+        self.num_classes = num_classes
+        self.engine = VGGUnetEngine(num_classes, device=self.device)
+        shapes = vgg_unet_param_shapes(num_classes)
+        self.names = list(shapes.keys())                       # state_dict order
+        self.layout = FlatBuckets(shapes, _backward_order(self.names), self.device, bucket_bytes=bucket_mb << 20)
+        self.flat_param = self.layout.new_buffer()
+        self.flat_grad = self.layout.new_buffer()
+        self.params = self.layout.views(self.flat_param)
+        self.grads = self.layout.views(self.flat_grad)
+        self.opt_kind = optimizer
+        self.lr, self.betas, self.eps, self.weight_decay, self.momentum = lr, betas, eps, weight_decay, momentum
+        self.m = self.layout.new_buffer()
+        self.v = self.layout.new_buffer() if optimizer == "adam" else None
+        self.step_count = 0
+        self.dice, self.focal, self.compute_f_score = dice_loss, focal_loss, compute_f_score
+        cw = torch.ones(num_classes) if cls_weights is None else torch.as_tensor(cls_weights, dtype=torch.float32)
+        self.cls_w = cw.to(self.device).contiguous()
+        self.sync = GradientSync(self.layout, self.flat_grad, group=process_group)
+        self.trainable = set(self.names)
+        self._gscale = torch.tensor([0.0 if focal_loss else 1.0, 1.0 if focal_loss else 0.0, 1.0 if dice_loss else 0.0],
+                                    dtype=torch.float32, device=self.device)
+        self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._staged = None
+        self.last = None
+        if state_dict is not None:
+            self.load_state_dict(state_dict)
+        if self.sync.world > 1:
+            dist.broadcast(self.flat_param, src=0, group=process_group)      # DDP ctor semantics (train.py:346)
+
+    # ------------------------------------------------------------------ state
+    def load_state_dict(self, sd):
+        with torch.no_grad():
+            for n in self.names:
+                self.params[n].copy_(sd[n].to(self.device, dtype=torch.float32))
+
+    def state_dict(self):
+        return {n: self.params[n].detach().clone() for n in self.names}
+
+    def freeze_backbone(self):
+        self.trainable = {n for n in self.names if not n.startswith("vgg.")}
+
+    def unfreeze_backbone(self):
+        self.trainable = set(self.names)
+
+    # ------------------------------------------------------------------ input staging
+    def stage(self, imgs, pngs):
+        """Asynchronous host->device copy of the next batch on a copy stream (pinned host tensors)."""
+        with torch.cuda.stream(self._copy_stream):
+            di = imgs.to(self.device, non_blocking=True)
+            dp = pngs.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._staged = (di, dp, ev)
+
+    def _take(self, imgs, pngs):
+        if imgs is None:
+            if self._staged is None:
+                raise RuntimeError("train_step(None, None) needs a batch staged with stage()")
+            di, dp, ev = self._staged
+            self._staged = None
+            torch.cuda.current_stream().wait_event(ev)
+            di.record_stream(torch.cuda.current_stream())
+            dp.record_stream(torch.cuda.current_stream())
+            return di, dp
+        if not imgs.is_cuda:
+            imgs = imgs.to(self.device, non_blocking=True)
+        if not pngs.is_cuda:
+            pngs = pngs.to(self.device, non_blocking=True)
+        return imgs, pngs
+
+    # ------------------------------------------------------------------ the step
+    def forward_loss(self, imgs, pngs, save=True):
+        logits = self.engine.forward(imgs, self.params, save=save)
+        if pngs.dtype != torch.int64:
+            pngs = pngs.long()
+        fin = ops.loss_fwd(logits, target=pngs.contiguous(), onehot=None, cls_w=self.cls_w)
+        return logits, pngs, fin
+
+    def train_step(self, imgs=None, pngs=None):
+        """Returns a device tensor [total loss, f_score]; `.item()`/`.tolist()` on it is the per-iteration sync of
+        utils_fit.py:96-97."""
+        imgs, pngs = self._take(imgs, pngs)
+        logits, pngs, fin = self.forward_loss(imgs, pngs, save=True)
+        dlogits = ops.loss_bwd(logits, fin, self._gscale, target=pngs, onehot=None, cls_w=self.cls_w)
+        active = [n for n in self.layout.order if n in self.trainable]
+        self.sync.reset(active)
+        grads = {n: self.grads[n] for n in active}
+        self.engine.backward(dlogits, self.params, grads, trainable=self.trainable, on_grads_ready=self.sync.ready)
+        scale = self.sync.finish()
+        self.optimizer_step(scale)
+        loss = fin[0] * self._gscale[0] + fin[1] * self._gscale[1] + fin[2] * self._gscale[2]
+        self.last = torch.stack([loss, fin[3]])
+        return self.last
+
+    def optimizer_step(self, grad_scale=1.0):
+        self.step_count += 1
+        if len(self.trainable) != len(self.names):
+            # frozen tensors: zero their gradient slices so the flat update leaves them untouched (Adam with g = 0
+            # and zero moments is a no-op; weight decay is not applied to frozen tensors by the reference either)
+            for n in self.names:
+                if n not in self.trainable:
+                    self.grads[n].zero_()
+            if self.weight_decay != 0.0:
+                raise NotImplementedError("weight decay with a frozen backbone: per-slice update not built yet")
+        if self.opt_kind == "adam":
+            ops.adam_step(self.flat_param, self.flat_grad, self.m, self.v, self.step_count, self.lr, self.betas, self.eps,
+                          self.weight_decay, grad_scale)
+        else:
+            ops.sgd_step(self.flat_param, self.flat_grad, self.m, self.lr, self.momentum, self.weight_decay, True,
+                         self.step_count == 1, grad_scale)
+        # the flat update wrote every parameter behind torch's back: invalidate the engine's packed-weight cache
+        for c in self.engine.convs:
+            c.version = None
+
+    @torch.no_grad()
+    def eval_step(self, imgs, pngs):
+        """Validation iteration (utils_fit.py:111-151): forward + losses + f_score, no gradient."""
+        imgs, pngs = self._take(imgs, pngs)
+        _, _, fin = self.forward_loss(imgs, pngs, save=False)
+        loss = fin[0] * self._gscale[0] + fin[1] * self._gscale[1] + fin[2] * self._gscale[2]
+        return torch.stack([loss, fin[3]])
