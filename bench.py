@@ -240,8 +240,17 @@ def run_ours(args):
     imgs_total = B * world * K
     value = imgs_total / (ms_total / 1e3)
     e2e_value = imgs_total / (ms_e2e / 1e3)
-    ig = kt.get("conv_igemm", {"launches": 0, "ms": 0.0, "flops": 0.0})
-    wg = kt.get("conv_wgrad", {"launches": 0, "ms": 0.0, "flops": 0.0})
+    def agg(prefix):
+        recs = [v for k, v in kt.items() if k.startswith(prefix + "|")]
+        return {"launches": sum(r["launches"] for r in recs), "ms": sum(r["ms"] for r in recs),
+                "flops": sum(r["flops"] for r in recs)}
+    ig, wg = agg("conv_igemm"), agg("conv_wgrad")
+    if args.detail:
+        rows = [{"kernel": k, "launches": v["launches"], "avg_ms": v["ms"] / v["launches"],
+                 "tflops": v["flops"] / (v["ms"] / 1e3) / 1e12, "share_of_conv_ms": v["ms"] / (ig["ms"] + wg["ms"])}
+                for k, v in sorted(kt.items(), key=lambda kv: -kv[1]["ms"])]
+        with open(args.detail, "w") as f:
+            json.dump({"steps_timed": tsteps, "rows": rows}, f, indent=1)
 
     def roof(rec, traffic=None):
         if rec["ms"] <= 0:
@@ -287,6 +296,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="images per GPU per step (BASELINE: 16)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--detail", default=None, help="write the per-layer conv kernel timing table (JSON) here")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

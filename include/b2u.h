@@ -49,7 +49,8 @@ int b2u_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int 
 /* ---- tensor-core convolutions (tcgen05 implicit GEMM) ------------------------------------------------------ */
 /* y = [relu](conv(cat(x0, x1), w) + bias).  Replaces nn.Conv2d(k=3,p=1 | k=1)+ReLU (nets/vgg.py:53-57,
  * nets/unet.py:11-12,18-21) and, with x1 != NULL, torch.cat([skip, up], 1) + conv (nets/unet.py:17-18).
- * taps = 9 (3x3, pad 1) or 1.  C0, C1, Cout multiples of 64.  bn_override: 0 = choose the N tile. */
+ * taps = 9 (3x3, pad 1) or 1.  C0, C1, Cout multiples of 64.  bn_override: 0 = choose the tiling; bits 0..15 force the
+ * N tile (64/128/192/256), bit 16 forces one 8x16-pixel M tile per CTA step (tests exercise every variant). */
 int b2u_conv_fprop(const void* x0, int C0, const void* x1, int C1, const void* wf, const float* bias, void* y, int N,
                    int H, int W, int Cout, int taps, int relu, int bn_override, void* stream);
 /* dgrad of the same conv (autograd of nn.Conv2d, utils/utils_fit.py:92): dz has Cz channels; the C0+C1 input-channel
@@ -57,10 +58,11 @@ int b2u_conv_fprop(const void* x0, int C0, const void* x1, int C1, const void* w
  * ReLU backward of the tensor that fed the conv: dx0 = 0 where mask <= 0. */
 int b2u_conv_dgrad(const void* dz, int Cz, const void* wd, void* dx0, int C0, void* dx1, int C1, const void* mask,
                    int N, int H, int W, int taps, int bn_override, void* stream);
-/* wgrad: dw (OIHW fp32, overwritten) = sum over pixels of dz (x) cat(x0, x1).  first_cin > 0: x0 is the im2col tensor
- * of b2u_im2col_first and dw is [Cout][first_cin][3][3].  flags bit0: unmerged vertical taps (debug). */
+/* wgrad: dw (OIHW fp32, overwritten) = sum over pixels of dz (x) cat(x0, x1); db (nullable, [Cout]) = sum over pixels
+ * of dz, from the same pass.  first_cin > 0: x0 is the im2col tensor of b2u_im2col_first and dw is
+ * [Cout][first_cin][3][3].  flags bit0: unmerged vertical taps (debug). */
 size_t b2u_conv_wgrad_workspace(int N, int H, int W, int Cin_tot, int Cout, int taps);
-int b2u_conv_wgrad(const void* x0, int C0, const void* x1, int C1, const void* dz, int Cout, float* dw, void* ws,
+int b2u_conv_wgrad(const void* x0, int C0, const void* x1, int C1, const void* dz, int Cout, float* dw, float* db, void* ws,
                    size_t ws_bytes, int N, int H, int W, int taps, int first_cin, int flags, void* stream);
 /* db[c] = sum over pixels of dz[.,c]  (bias gradient of nn.Conv2d) */
 size_t b2u_bias_grad_workspace(int C);
@@ -93,10 +95,15 @@ int b2u_loss_out_len(int C);
 int b2u_loss_fwd(const float* logits, const long long* target, const float* onehot, const float* cls_w, float* out,
                  double* stats, void* ws, size_t ws_bytes, int N, int C, int H, int W, float beta, float smooth,
                  float focal_alpha, float focal_gamma, float thr, void* stream);
-/* dlogits = gscale[0] dCE + gscale[1] dFocal + gscale[2] dDice (gscale: 3 floats on device) */
+/* dlogits = gscale[0] dCE + gscale[1] dFocal + gscale[2] dDice (gscale: 3 floats on device).
+ * out_mode 0: fp32 NCHW (autograd of the drop-in losses); 1: bf16 NHWC [N,H,W,64] = [hi(32) | lo(32)] two-term bf16
+ * split of dlogits (classes >= C zero), the dz operand of b2u_conv_dgrad / b2u_conv_wgrad (taps = 1) for the head's
+ * backward on the tensor cores (both halves meet the same weights, see b2u_pack_head_dgrad). */
 int b2u_loss_bwd(const float* logits, const long long* target, const float* onehot, const float* cls_w, const float* fin,
-                 const float* gscale, float* dlogits, int N, int C, int H, int W, float focal_alpha, float focal_gamma,
-                 void* stream);
+                 const float* gscale, void* dlogits, int out_mode, int N, int C, int H, int W, float focal_alpha,
+                 float focal_gamma, void* stream);
+/* final.weight [C][64] fp32 -> 64x64 bf16 dgrad operand wd[ci][co], co in [0,32) and [32,64) both = class co % 32 */
+int b2u_pack_head_dgrad(const float* w, void* wd, int ncls, void* stream);
 /* per-pixel class decision of the inference loop (unet.py:246-250: argmax(softmax(z)) == argmax(z)) */
 int b2u_argmax_u8(const float* logits, unsigned char* mask, int N, int C, int H, int W, void* stream);
 /* fast_hist (utils/utils_metrics.py:34-43): hist (n*n+1 uint64, accumulated) ; dtype 0=u8 1=i32 2=i64 */

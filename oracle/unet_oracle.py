@@ -50,9 +50,11 @@ def param_shapes(num_classes, in_channels=3):
     return shapes
 
 
-def make_params(num_classes, seed=11, in_channels=3, gain=1.0):
+def make_params(num_classes, seed=11, in_channels=3, gain=0.5):
     """Deterministic synthetic weights (no checkpoint is shipped for this model): tensor k of
-    the state_dict is drawn from its own generator seeded seed*1000+k; He-scaled so activations stay O(1)."""
+    the state_dict is drawn from its own generator seeded seed*1000+k, std = gain * sqrt(2 / fan_in).  gain 0.5 is
+    the scale of torch's default Conv2d init (what the reference's decoder starts from); gain 1.0 (full He) keeps
+    activations O(1) through all 23 layers and is the harsh case for bf16."""
     params = {}
     for k, (name, shape) in enumerate(param_shapes(num_classes, in_channels).items()):
         g = torch.Generator().manual_seed(seed * 1000 + k)
@@ -175,7 +177,7 @@ def f_score(logits, onehot, beta=1, smooth=1e-5, threhold=0.5):
 
 def one_hot(png, num_classes):
     """np.eye(num_classes + 1)[png] (utils/dataloader.py:49-50)."""
-    return torch.eye(num_classes + 1)[png]
+    return torch.eye(num_classes + 1, device=png.device)[png]
 
 
 def train_step(params, imgs, pngs, cls_weights, num_classes, dice=True, focal=False):
@@ -223,3 +225,60 @@ def make_masks(n_masks, n, h=512, w=512, seed=0):
     pred[redraw] = rng.integers(0, n, size=int(redraw.sum()), dtype=np.uint8)
     gt[rng.random((n_masks, h, w)) < 0.03] = 255
     return gt, pred
+
+
+# ----------------------------------------------------------------------------------------------- bf16 storage model
+class _RoundBF16(torch.autograd.Function):
+    """y = bf16(x) in forward (if `fwd`), g = bf16(g) in backward: models a tensor that is STORED in bf16 in both
+    directions.  Used only to separate "bf16 storage noise" from "bug" when judging the CUDA path."""
+
+    @staticmethod
+    def forward(ctx, x, fwd):
+        return x.to(torch.bfloat16).to(x.dtype) if fwd else x.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype), None
+
+
+def _r(x, fwd=True):
+    return _RoundBF16.apply(x, fwd)
+
+
+def unet_forward_bf16_storage(params, x):
+    """unet_forward with every activation / activation-gradient tensor rounded to bf16 where the CUDA path stores
+    it in bf16 and weights rounded to bf16 for the convolutions (fp32 accumulation everywhere, fp32 head + loss)."""
+    def wq(name):
+        w = params[name]
+        return w + (w.to(torch.bfloat16).to(w.dtype) - w).detach()     # bf16 value, straight-through gradient
+
+    def conv(x, name):
+        return _r(F.relu(F.conv2d(_r(x, fwd=False), wq(name + ".weight"), params[name + ".bias"], padding=1)))
+
+    x = _r(x)
+    feats = [None] * 5
+    it = iter(VGG_CONV_IDX)
+    for v in VGG_CFG:
+        if v == "M":
+            x = F.max_pool2d(x, kernel_size=2, stride=2)
+            continue
+        i = next(it)
+        x = conv(x, f"vgg.features.{i}")
+        if i in FEAT_AFTER:
+            feats[FEAT_AFTER[i]] = x
+    low = feats[4]
+    for k in (4, 3, 2, 1):
+        up = _r(F.interpolate(low, scale_factor=2, mode="bilinear", align_corners=True))
+        low = conv(torch.cat([feats[k - 1], up], 1), f"up_concat{k}.conv1")
+        low = conv(low, f"up_concat{k}.conv2")
+    return F.conv2d(low, params["final.weight"], params["final.bias"])
+
+
+def train_step_bf16_storage(params, imgs, pngs, cls_weights, num_classes, dice=True, focal=False):
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+    logits = unet_forward_bf16_storage(p, imgs)
+    loss = focal_loss(logits, pngs, cls_weights, num_classes) if focal else ce_loss(logits, pngs, cls_weights, num_classes)
+    if dice:
+        loss = loss + dice_loss(logits, one_hot(pngs, num_classes))
+    grads = torch.autograd.grad(loss, list(p.values()))
+    return loss.detach(), logits.detach(), dict(zip(p.keys(), grads))

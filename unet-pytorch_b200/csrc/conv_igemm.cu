@@ -46,14 +46,16 @@ struct ConvParams {
   int mask_c;
 };
 
-template <int BN, int TAPS, int SA, int SB>
+template <int BN, int TAPS, int MT, int RB, int SA, int SB>
 struct ConvCfg {
+  // MT: M tiles (8x16 pixel patches, stacked vertically) per CTA step, sharing every B tile
+  // RB: vertical taps per B pipeline stage (3: one barrier round trip per 12*MT MMAs, for the small-N tiles)
   static constexpr int kRowBytes = KB * 2;                      // swizzle span (128 B)
-  static constexpr int kARows = (TAPS == 9 ? kHb + 2 : kHb) * kWb;
+  static constexpr int kARows = (TAPS == 9 ? kHb * MT + 2 : kHb * MT) * kWb;
   static constexpr int kABytes = kARows * kRowBytes;
-  static constexpr int kBBytes = BN * kRowBytes;
-  static constexpr int kEpiN = 64;
-  static constexpr int kStageBytes = kTileM * kEpiN * 2;
+  static constexpr int kBTap = BN * kRowBytes;                  // one tap's weight tile
+  static constexpr int kBBytes = RB * kBTap;
+  static constexpr int kStageBytes = kTileM * 64 * 2;
   static constexpr int kOffA = 0;
   static constexpr int kOffB = kOffA + SA * kABytes;
   static constexpr int kOffStage = kOffB + SB * kBBytes;
@@ -63,18 +65,21 @@ struct ConvCfg {
   static constexpr int kOffTmem = kOffBar + kNumBar * 8;
   static constexpr int kSmemBytes = kOffTmem + 16 + 1024;  // + alignment slack
   static constexpr uint32_t kSBO = 8 * kRowBytes;
-  static constexpr int kTmemCols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);
+  static constexpr int kAccCols = MT * BN;                     // accumulator columns per pipeline stage
+  static constexpr int kTmemCols = 2 * kAccCols <= 128 ? 128 : (2 * kAccCols <= 256 ? 256 : 512);
   static_assert(BN % 64 == 0 && BN <= 256, "N tile must be 64/128/192/256");
-  static_assert(kABytes % 1024 == 0 && kBBytes % 1024 == 0, "stage buffers must keep 1024B alignment");
+  static_assert(2 * kAccCols <= 512, "TMEM holds 512 columns");
+  static_assert(TAPS == 9 || RB == 1, "1x1 convs have a single tap");
+  static_assert(kABytes % 1024 == 0 && kBTap % 1024 == 0, "stage buffers must keep 1024B alignment");
   static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
 };
 
-template <int BN, int TAPS, int SA, int SB>
+template <int BN, int TAPS, int MT, int RB, int SA, int SB>
 __global__ void __launch_bounds__(192, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC0,
                   const __grid_constant__ CUtensorMap tmC1, const ConvParams p) {
-  using Cfg = ConvCfg<BN, TAPS, SA, SB>;
+  using Cfg = ConvCfg<BN, TAPS, MT, RB, SA, SB>;
   constexpr int S_TAPS = TAPS == 9 ? 3 : 1;
   constexpr int R_TAPS = TAPS == 9 ? 3 : 1;
 
@@ -135,7 +140,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const int tw = m_tile % p.tiles_w; m_tile /= p.tiles_w;
         const int th = m_tile % p.tiles_h;
         const int img = m_tile / p.tiles_h;
-        const int w0 = tw * kWb, h0 = th * kHb, n0 = n_tile * BN;
+        const int w0 = tw * kWb, h0 = th * (kHb * MT), n0 = n_tile * BN;
         for (int c = 0; c < chunks; ++c) {
           const CUtensorMap* tm = c < chunks0 ? &tmA0 : &tmA1;
           const int cc = c < chunks0 ? c * KB : c * KB - p.C0;
@@ -145,10 +150,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             if (TAPS == 9) tma_load_4d(sA + sa * Cfg::kABytes, tm, a_full(sa), cc, w0 + s - 1, h0 - 1, img);
             else           tma_load_4d(sA + sa * Cfg::kABytes, tm, a_full(sa), cc, w0, h0, img);
             if (++sa == SA) { sa = 0; pa ^= 1u; }
-            for (int r = 0; r < R_TAPS; ++r) {
+            for (int rb = 0; rb < R_TAPS / RB; ++rb) {
               mbar_wait(b_empty(sb), pb ^ 1u);
               mbar_expect_tx(b_full(sb), Cfg::kBBytes);
-              tma_load_2d(sB + sb * Cfg::kBBytes, &tmB, b_full(sb), (r * S_TAPS + s) * ctot + c * KB, n0);
+#pragma unroll
+              for (int rr = 0; rr < RB; ++rr) {
+                const int r = rb * RB + rr;
+                tma_load_2d(sB + sb * Cfg::kBBytes + rr * Cfg::kBTap, &tmB, b_full(sb), (r * S_TAPS + s) * ctot + c * KB, n0);
+              }
               if (++sb == SB) { sb = 0; pb ^= 1u; }
             }
           }
@@ -159,27 +168,37 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN, 0, 0);
+      // descriptor templates: only the 14-bit start-address field changes per MMA (smem < 256 KB, no carry)
+      const uint64_t a_desc0 = umma_smem_desc(sA, 16, Cfg::kSBO, 2u);
+      const uint64_t b_desc0 = umma_smem_desc(sB, 16, Cfg::kSBO, 2u);
       int sa = 0, sb = 0, as = 0;
       uint32_t pa = 0, pb = 0, pacc = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(t_empty(as), pacc ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * Cfg::kAccCols);
         uint32_t acc = 0;
         for (int c = 0; c < chunks; ++c) {
           for (int s = 0; s < S_TAPS; ++s) {
             mbar_wait(a_full(sa), pa);
             tc_fence_after();
-            const uint32_t a_base = sA + sa * Cfg::kABytes;
-            for (int r = 0; r < R_TAPS; ++r) {
+            const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((sa * Cfg::kABytes) >> 4);
+            for (int rb = 0; rb < R_TAPS / RB; ++rb) {
               mbar_wait(b_full(sb), pb);
               tc_fence_after();
-              const uint32_t b_base = sB + sb * Cfg::kBBytes;
+              const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((sb * Cfg::kBBytes) >> 4);
 #pragma unroll
-              for (int k = 0; k < KB / 16; ++k) {
-                const uint64_t ad = umma_smem_desc(a_base + r * (kWb * Cfg::kRowBytes) + k * 32, 16, Cfg::kSBO, 2u);
-                const uint64_t bd = umma_smem_desc(b_base + k * 32, 16, Cfg::kSBO, 2u);
-                tc_mma_bf16(d_tmem, ad, bd, idesc, acc);
+              for (int rr = 0; rr < RB; ++rr) {
+                const int r = rb * RB + rr;
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                  for (int k = 0; k < KB / 16; ++k) {
+                    const uint64_t ad = a_desc + static_cast<uint64_t>(((mt * kHb + r) * (kWb * Cfg::kRowBytes) + k * 32) >> 4);
+                    const uint64_t bd = b_desc + static_cast<uint64_t>((rr * Cfg::kBTap + k * 32) >> 4);
+                    tc_mma_bf16(d_tmem + mt * BN, ad, bd, idesc, (k == 0 ? acc : 1u));
+                  }
+                }
                 acc = 1;
               }
               tc_commit(b_empty(sb));
@@ -208,21 +227,35 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const int tw = m_tile % p.tiles_w; m_tile /= p.tiles_w;
       const int th = m_tile % p.tiles_h;
       const int img = m_tile / p.tiles_h;
-      const int w0 = tw * kWb, h0 = th * kHb, n0 = n_tile * BN;
-      const int gh = h0 + ph, gw = w0 + pw;
-      const bool inb = gh < p.H && gw < p.W;
+      const int w0 = tw * kWb, h0 = th * (kHb * MT), n0 = n_tile * BN;
+      const int gw = w0 + pw;
+
+      // ReLU-mask rows are fetched one sub-tile ahead (first one before the accumulator wait) so their latency
+      // hides behind the main loop / the previous sub-tile's staging instead of stalling the epilogue
+      uint4 mreg[8];
+      auto fetch_mask = [&](int jj_) {
+        const int mt_ = jj_ / (BN / 64), j_ = jj_ % (BN / 64);
+        const int gh_ = h0 + mt_ * kHb + ph;
+        const bool inb_ = gh_ < p.H && gw < p.W;
+        const uint4* mrow = reinterpret_cast<const uint4*>(
+            p.mask + ((static_cast<size_t>(img) * p.H + (inb_ ? gh_ : 0)) * p.W + (inb_ ? gw : 0)) * p.mask_c + n0 + j_ * 64);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) mreg[q] = inb_ ? __ldg(mrow + q) : make_uint4(0, 0, 0, 0);
+      };
+      if (p.flags & 2) fetch_mask(0);
 
       mbar_wait(t_full(as), pacc);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(as * BN);
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(as * Cfg::kAccCols);
 
 #pragma unroll 1
-      for (int j = 0; j < BN / 64; ++j) {
+      for (int jj = 0; jj < MT * (BN / 64); ++jj) {
+        const int mt = jj / (BN / 64), j = jj % (BN / 64);
         uint32_t v[64];
-        tmem_ld_32x32(t_row + j * 64, v);
-        tmem_ld_32x32(t_row + j * 64 + 32, v + 32);
+        tmem_ld_32x32(t_row + mt * BN + j * 64, v);
+        tmem_ld_32x32(t_row + mt * BN + j * 64 + 32, v + 32);
         tmem_ld_wait();
-        if (j == BN / 64 - 1) {
+        if (jj == MT * (BN / 64) - 1) {
           // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -231,12 +264,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const int cbase = n0 + j * 64;
         uint32_t packed[32];
         if (p.flags & 2) {
-          const uint4* mrow = reinterpret_cast<const uint4*>(
-              p.mask + ((static_cast<size_t>(img) * p.H + (inb ? gh : 0)) * p.W + (inb ? gw : 0)) * p.mask_c + cbase);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            uint4 m = inb ? __ldg(mrow + q) : make_uint4(0, 0, 0, 0);
-            const uint32_t mm[4] = {m.x, m.y, m.z, m.w};
+            const uint32_t mm[4] = {mreg[q].x, mreg[q].y, mreg[q].z, mreg[q].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float lo = __uint_as_float(v[q * 8 + 2 * e]) + sBias[cbase + q * 8 + 2 * e];
@@ -246,6 +276,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               packed[q * 4 + e] = pack_bf16x2(lo, hi);
             }
           }
+          if (jj + 1 < MT * (BN / 64)) fetch_mask(jj + 1);
         } else {
           const bool relu = p.flags & 1;
 #pragma unroll
@@ -270,9 +301,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (issuer) {
-          if (cbase < p.split_c) tma_store_4d(&tmC0, stage, cbase, w0, h0, img);
-          else                   tma_store_4d(&tmC1, stage, cbase - p.split_c, w0, h0, img);
-          tma_store_commit();
+          if (h0 + mt * kHb < p.H) {       // a stacked tile may hang below the image entirely
+            if (cbase < p.split_c) tma_store_4d(&tmC0, stage, cbase, w0, h0 + mt * kHb, img);
+            else                   tma_store_4d(&tmC1, stage, cbase - p.split_c, w0, h0 + mt * kHb, img);
+          }
+          tma_store_commit();              // always: the wait_group<1> bookkeeping counts one group per sub-tile
         }
         sbuf ^= 1u;
       }
@@ -292,10 +325,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 // ----------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------
-template <int BN, int TAPS, int SA, int SB>
+template <int BN, int TAPS, int MT, int RB, int SA, int SB>
 static int launch_cfg(const ConvLaunch& a, cudaStream_t st) {
-  using Cfg = ConvCfg<BN, TAPS, SA, SB>;
-  auto kern = conv_igemm_kernel<BN, TAPS, SA, SB>;
+  using Cfg = ConvCfg<BN, TAPS, MT, RB, SA, SB>;
+  auto kern = conv_igemm_kernel<BN, TAPS, MT, RB, SA, SB>;
   static bool attr_done[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -305,7 +338,7 @@ static int launch_cfg(const ConvLaunch& a, cudaStream_t st) {
     attr_done[dev] = true;
   }
   const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B;
-  const int a_box_h = TAPS == 9 ? kHb + 2 : kHb;
+  const int a_box_h = TAPS == 9 ? kHb * MT + 2 : kHb * MT;
   CUtensorMap tmA0, tmA1, tmB, tmC0, tmC1;
   int rc;
   if ((rc = make_tmap_nhwc(&tmA0, a.x0, a.N, a.H, a.W, a.C0, KB, kWb, a_box_h, swz))) return rc;
@@ -326,7 +359,7 @@ static int launch_cfg(const ConvLaunch& a, cudaStream_t st) {
   ConvParams p;
   p.N = a.N; p.H = a.H; p.W = a.W; p.C0 = a.C0; p.C1 = a.C1; p.Cout = a.Cout;
   p.tiles_w = (a.W + kWb - 1) / kWb;
-  p.tiles_h = (a.H + kHb - 1) / kHb;
+  p.tiles_h = (a.H + kHb * MT - 1) / (kHb * MT);
   p.num_m_tiles = a.N * p.tiles_h * p.tiles_w;
   p.num_n_tiles = a.Cout / BN;
   p.split_c = split;
@@ -364,19 +397,21 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st) {
   else if (a.Cout % 128 == 0) bn = 128;
   else bn = 64;
 
+  // tall = two stacked M tiles per CTA step (halves the weight traffic per pixel); pointless for tiny images
+  const bool tall = a.H > kHb && !(a.tile_flags & 1);
   if (a.taps == 9) {
     switch (bn) {
-      case 256: return launch_cfg<256, 9, 3, 4>(a, st);
-      case 192: return launch_cfg<192, 9, 3, 5>(a, st);
-      case 128: return launch_cfg<128, 9, 3, 8>(a, st);
-      case 64:  return launch_cfg<64, 9, 4, 12>(a, st);
+      case 256: return launch_cfg<256, 9, 1, 1, 3, 4>(a, st);
+      case 192: return launch_cfg<192, 9, 1, 1, 3, 5>(a, st);
+      case 128: return tall ? launch_cfg<128, 9, 2, 3, 2, 2>(a, st) : launch_cfg<128, 9, 1, 3, 3, 2>(a, st);
+      case 64:  return tall ? launch_cfg<64, 9, 2, 3, 3, 3>(a, st) : launch_cfg<64, 9, 1, 3, 4, 4>(a, st);
     }
   } else {
     switch (bn) {
-      case 256: return launch_cfg<256, 1, 3, 3>(a, st);
-      case 192: return launch_cfg<192, 1, 4, 4>(a, st);
-      case 128: return launch_cfg<128, 1, 4, 4>(a, st);
-      case 64:  return launch_cfg<64, 1, 4, 4>(a, st);
+      case 256: return launch_cfg<256, 1, 1, 1, 3, 3>(a, st);
+      case 192: return launch_cfg<192, 1, 1, 1, 4, 4>(a, st);
+      case 128: return launch_cfg<128, 1, 1, 1, 4, 4>(a, st);
+      case 64:  return launch_cfg<64, 1, 2, 1, 3, 4>(a, st);
     }
   }
   return set_error(B2U_ERR_SHAPE, "conv: unsupported N tile %d", bn);
@@ -396,7 +431,8 @@ int b2u_conv_fprop(const void* x0, int C0, const void* x1, int C1, const void* w
   a.wpacked = wf; a.bias = bias; a.y0 = y;
   a.N = N; a.H = H; a.W = W; a.Cout = Cout; a.taps = taps;
   a.flags = relu ? 1 : 0;
-  a.bn_override = bn_override;
+  a.bn_override = bn_override & 0xffff;    // bits 0..15: N tile override; bit 16: one M tile per CTA step
+  a.tile_flags = bn_override >> 16;
   return b2u::launch_conv(a, static_cast<cudaStream_t>(stream));
 }
 
@@ -414,7 +450,8 @@ int b2u_conv_dgrad(const void* dz, int Cz, const void* wd, void* dx0, int C0, vo
     if (dx1) return b2u::set_error(B2U_ERR_ARG, "dgrad: mask is only supported with a single output");
     a.flags = 2; a.mask = static_cast<const __nv_bfloat16*>(mask); a.mask_c = C0;
   }
-  a.bn_override = bn_override;
+  a.bn_override = bn_override & 0xffff;
+  a.tile_flags = bn_override >> 16;
   return b2u::launch_conv(a, static_cast<cudaStream_t>(stream));
 }
 

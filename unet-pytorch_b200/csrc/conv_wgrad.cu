@@ -32,6 +32,7 @@ struct WgradParams {
   int num_mblk, num_cblk, splits, units;
   int merged;                      // 1: N=192 merged vertical taps; 0: three N=64 instructions
   float* partial;                  // [splits][Cout][taps][C0+C1]
+  float* bias_partial;             // [splits][Cout] or null: db = column sums of dz (an extra N=16 MMA against ones)
 };
 
 template <int TAPS, int STAGES>
@@ -41,12 +42,15 @@ struct WgCfg {
   static constexpr int kDzHalf = kHb * kWb * 128;       // 64 couts x 128 px
   static constexpr int kDzBytes = 2 * kDzHalf;
   static constexpr int kStage = kDzBytes + kXBytes;
-  static constexpr int kOffBar = STAGES * kStage;
+  static constexpr int kOffOnes = STAGES * kStage;      // 16 K-rows x 128 B of bf16 1.0: B operand of the bias MMA
+  static constexpr int kOnesBytes = 2048;
+  static constexpr int kOffBar = kOffOnes + kOnesBytes;
   static constexpr int kNumBar = 2 * STAGES + 4;
   static constexpr int kOffTmem = kOffBar + kNumBar * 8;
   static constexpr int kSmemBytes = kOffTmem + 16 + 1024;
   static constexpr int kAccN = TAPS == 9 ? 192 : 64;    // accumulator columns per unit
-  static constexpr int kTmemCols = TAPS == 9 ? 512 : 128;
+  static constexpr int kBiasCol = kAccN;                // accumulator column block holding the bias sums
+  static constexpr int kTmemCols = TAPS == 9 ? 512 : 256;
   static constexpr int kAccStride = kTmemCols / 2;
   static_assert(kStage % 1024 == 0, "stage alignment");
   static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
@@ -85,6 +89,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols);
     tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < Cfg::kOnesBytes / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem_gen + Cfg::kOffOnes)[i] = 0x3F803F80u;   // two bf16 1.0
+  fence_proxy_async_smem();        // generic-proxy writes -> visible to the tensor core's async proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -139,7 +146,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
       // A = dz (M x K, MN-major), B = x (N x K, MN-major)
       constexpr uint32_t idesc_merged = umma_idesc_bf16(128, Cfg::kAccN, 1, 1);
       constexpr uint32_t idesc_single = umma_idesc_bf16(128, 64, 1, 1);
+      constexpr uint32_t idesc_bias = umma_idesc_bf16(128, 16, 1, 1);
+      const uint64_t ones_desc = umma_smem_desc(smem_base + Cfg::kOffOnes, 2048, 1024, 2u);
       const uint32_t lbo_a = two_halves ? Cfg::kDzHalf : 0u;   // Cout == 64: rows 64..127 alias rows 0..63
+      // descriptor templates: per MMA only the 14-bit start-address field moves (+128 = one 16-pixel image row)
+      const uint64_t a_desc0 = umma_smem_desc(smem_base, lbo_a, 1024, 2u);
+      const uint64_t b_desc0 = umma_smem_desc(smem_base + Cfg::kDzBytes, 2048, 1024, 2u);
+      const bool merged = TAPS == 1 || p.merged;
       int st = 0, as = 0; uint32_t ph = 0, pacc = 0;
       for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
         int split, mblk, cblk, s, k0, k1;
@@ -148,32 +161,34 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         mbar_wait(t_empty(as), pacc ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * Cfg::kAccStride);
+        const bool bias_unit = p.bias_partial != nullptr && cblk == 0 && s == 0;
         uint32_t acc = 0;
         for (int kb = k0; kb < k1; ++kb) {
           mbar_wait(full(st), ph);
           tc_fence_after();
-          const uint32_t a_base = smem_base + st * Cfg::kStage;
-          const uint32_t b_base = a_base + Cfg::kDzBytes;
+          const uint64_t a_st = a_desc0 + static_cast<uint64_t>((st * Cfg::kStage) >> 4);
+          const uint64_t b_st = b_desc0 + static_cast<uint64_t>((st * Cfg::kStage) >> 4);
+          if (merged && !bias_unit) {
 #pragma unroll
-          for (int j = 0; j < kHb; ++j) {
-            const uint64_t ad = umma_smem_desc(a_base + j * 2048, lbo_a, 1024, 2u);
-            if (TAPS == 1 || p.merged) {
-              const uint64_t bd = umma_smem_desc(b_base + j * 2048, 2048, 1024, 2u);
-              tc_mma_bf16(d_tmem, ad, bd, idesc_merged, acc);
-            } else {
+            for (int j = 0; j < kHb; ++j)
+              tc_mma_bf16(d_tmem, a_st + j * 128, b_st + j * 128, idesc_merged, j == 0 ? acc : 1u);
+          } else {
 #pragma unroll
-              for (int r = 0; r < R_TAPS; ++r) {
-                const uint64_t bd = umma_smem_desc(b_base + (j + r) * 2048, 2048, 1024, 2u);
-                tc_mma_bf16(d_tmem + r * 64, ad, bd, idesc_single, acc);
+            for (int j = 0; j < kHb; ++j) {
+              const uint32_t accj = j == 0 ? acc : 1u;
+              if (merged) {
+                tc_mma_bf16(d_tmem, a_st + j * 128, b_st + j * 128, idesc_merged, accj);
+              } else {
+#pragma unroll
+                for (int r = 0; r < R_TAPS; ++r)
+                  tc_mma_bf16(d_tmem + r * 64, a_st + j * 128, b_st + (j + r) * 128, idesc_single, accj);
               }
+              if (bias_unit) tc_mma_bf16(d_tmem + Cfg::kBiasCol, a_st + j * 128, ones_desc, idesc_bias, accj);
             }
-            acc = 1;
           }
+          acc = 1;
           tc_commit(empty(st));
           if (++st == STAGES) { st = 0; ph ^= 1u; }
-        }
-        if (k1 <= k0) {
-          // empty K range (more splits than K blocks): nothing was accumulated; the epilogue writes zeros
         }
         tc_commit(t_full(as));
         if (++as == 2) { as = 0; pacc ^= 1u; }
@@ -213,6 +228,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
             dst[q] = o;
           }
         }
+      }
+      if (p.bias_partial != nullptr && cblk == 0 && s == 0) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + Cfg::kBiasCol, v);     // only column 0 is meaningful (every column of the ones tile is 1)
+        tmem_ld_wait();
+        if (valid) p.bias_partial[static_cast<size_t>(split) * p.Cout + co] = k1 > k0 ? __uint_as_float(v[0]) : 0.f;
       }
       tc_fence_before();
       __syncwarp();
@@ -255,12 +276,65 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   }
 }
 
+// 3x3 fast path: block = (co, 64-channel block of ci); 144 threads = 9 taps x 16 float4 columns sum the splits with
+// coalesced 16-byte loads, then the 576 results leave through shared memory as one contiguous OIHW run
+// (dw[co][ci0..ci0+63][0..8]).
+__global__ void __launch_bounds__(160)
+wgrad_reduce9_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int Cout, int ctot) {
+  __shared__ float tile[9][65];
+  const int co = blockIdx.y, ci0 = blockIdx.x * 64;
+  const int tid = threadIdx.x;
+  if (tid < 144) {
+    const int tap = tid / 16, q = tid % 16;
+    const size_t split_stride = static_cast<size_t>(Cout) * 9 * ctot;
+    const float4* src = reinterpret_cast<const float4*>(partial + (static_cast<size_t>(co) * 9 + tap) * ctot + ci0 + q * 4);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int s = 0;
+    for (; s + 4 <= splits; s += 4) {
+      const float4 a = __ldg(src + (s * split_stride) / 4), b = __ldg(src + ((s + 1) * split_stride) / 4);
+      const float4 c = __ldg(src + ((s + 2) * split_stride) / 4), d = __ldg(src + ((s + 3) * split_stride) / 4);
+      acc.x += (a.x + b.x) + (c.x + d.x); acc.y += (a.y + b.y) + (c.y + d.y);
+      acc.z += (a.z + b.z) + (c.z + d.z); acc.w += (a.w + b.w) + (c.w + d.w);
+    }
+    for (; s < splits; ++s) {
+      const float4 a = __ldg(src + (s * split_stride) / 4);
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+    tile[tap][q * 4 + 0] = acc.x; tile[tap][q * 4 + 1] = acc.y; tile[tap][q * 4 + 2] = acc.z; tile[tap][q * 4 + 3] = acc.w;
+  }
+  __syncthreads();
+  float* out = dw + (static_cast<size_t>(co) * ctot + ci0) * 9;
+  for (int j = tid; j < 576; j += blockDim.x) out[j] = tile[j % 9][j / 9];
+}
+
+__global__ void wgrad_bias_reduce_kernel(const float* __restrict__ bias_partial, float* __restrict__ db, int splits, int Cout) {
+  const int co = blockIdx.x * blockDim.x + threadIdx.x;
+  if (co >= Cout) return;
+  float acc = 0.f;
+  for (int s = 0; s < splits; ++s) acc += bias_partial[static_cast<size_t>(s) * Cout + co];
+  db[co] = acc;
+}
+
+// Split-K factor: the grid is persistent (one CTA per SM, static round-robin over work units), so the kernel ends
+// when the CTA with the most units ends.  Search the split counts that give 3..8 units per SM for the one wasting
+// the fewest unit slots in the last round; keep at least 8 K blocks per unit so prologue/epilogue stay amortised.
 static int choose_splits(int base_units, int kblocks) {
   const int sms = num_sms();
-  int splits = (2 * sms + base_units - 1) / base_units;
-  if (splits > kblocks) splits = kblocks;
-  if (splits < 1) splits = 1;
-  return splits;
+  int lo = (3 * sms + base_units - 1) / base_units, hi = (8 * sms + base_units - 1) / base_units;
+  int cap = kblocks / 8;
+  if (cap < 1) cap = 1;
+  if (lo > cap) lo = cap;
+  if (hi > cap) hi = cap;
+  if (lo < 1) lo = 1;
+  int best = lo;
+  double best_waste = 1e30;
+  for (int sp = lo; sp <= hi; ++sp) {
+    const long long units = static_cast<long long>(base_units) * sp;
+    const long long rounds = (units + sms - 1) / sms;
+    const double waste = static_cast<double>(rounds * sms) / static_cast<double>(units);
+    if (waste < best_waste - 1e-9) { best_waste = waste; best = sp; }
+  }
+  return best;
 }
 
 struct WgradPlan {
@@ -278,13 +352,14 @@ static WgradPlan plan_wgrad(int N, int H, int W, int Cin_tot, int Cout, int taps
   const int base = pl.num_mblk * pl.num_cblk * pl.s_taps;
   pl.splits = choose_splits(base, pl.kblocks);
   pl.units = base * pl.splits;
-  pl.ws_bytes = static_cast<size_t>(pl.splits) * Cout * taps * Cin_tot * sizeof(float);
+  pl.ws_bytes = static_cast<size_t>(pl.splits) * Cout * taps * Cin_tot * sizeof(float)   // weight partials
+              + static_cast<size_t>(pl.splits) * Cout * sizeof(float);                // bias partials
   return pl;
 }
 
 template <int TAPS, int STAGES>
 static int launch_wgrad_cfg(const void* x0, int C0, const void* x1, int C1, const void* dz, int Cout, float* partial,
-                            const WgradPlan& pl, int N, int H, int W, int merged, cudaStream_t st) {
+                            float* bias_partial, const WgradPlan& pl, int N, int H, int W, int merged, cudaStream_t st) {
   using Cfg = WgCfg<TAPS, STAGES>;
   auto kern = conv_wgrad_kernel<TAPS, STAGES>;
   static bool attr_done[64] = {false};
@@ -312,6 +387,7 @@ static int launch_wgrad_cfg(const void* x0, int C0, const void* x1, int C1, cons
   p.num_mblk = pl.num_mblk; p.num_cblk = pl.num_cblk; p.splits = pl.splits; p.units = pl.units;
   p.merged = merged;
   p.partial = partial;
+  p.bias_partial = bias_partial;
   const int grid = pl.units < num_sms() ? pl.units : num_sms();
   kern<<<grid, 192, Cfg::kSmemBytes, st>>>(tmX0, tmX1, tmDZ, p);
   cudaError_t e = cudaGetLastError();
@@ -329,11 +405,12 @@ size_t b2u_conv_wgrad_workspace(int N, int H, int W, int Cin_tot, int Cout, int 
   return b2u::plan_wgrad(N, H, W, Cin_tot, Cout, taps).ws_bytes;
 }
 
-// dw: OIHW fp32 [Cout][cin_real][taps]  (cin_real = C0+C1 unless first_cin > 0)
+// dw: OIHW fp32 [Cout][cin_real][taps]  (cin_real = C0+C1 unless first_cin > 0); db (nullable): [Cout] bias gradient,
+// computed in the same pass as column sums of dz.
 // first_cin > 0: x0 is the first layer's im2col tensor [N,H,W,64] (taps must be 1, C0 == 64, C1 == 0);
 //                dw then is [Cout][first_cin][3][3].
 // flags bit0: use three N=64 instructions per image row instead of the merged N=192 one.
-int b2u_conv_wgrad(const void* x0, int C0, const void* x1, int C1, const void* dz, int Cout, float* dw, void* ws,
+int b2u_conv_wgrad(const void* x0, int C0, const void* x1, int C1, const void* dz, int Cout, float* dw, float* db, void* ws,
                    size_t ws_bytes, int N, int H, int W, int taps, int first_cin, int flags, void* stream) {
   using namespace b2u;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -351,14 +428,25 @@ int b2u_conv_wgrad(const void* x0, int C0, const void* x1, int C1, const void* d
     return set_error(B2U_ERR_ARG, "wgrad: workspace %zu bytes < required %zu", ws_bytes, pl.ws_bytes);
   int rc;
   const int merged = (flags & 1) ? 0 : 1;
-  if (taps == 9) rc = launch_wgrad_cfg<9, 4>(x0, C0, x1, C1, dz, Cout, static_cast<float*>(ws), pl, N, H, W, merged, st);
-  else           rc = launch_wgrad_cfg<1, 4>(x0, C0, x1, C1, dz, Cout, static_cast<float*>(ws), pl, N, H, W, merged, st);
+  float* wpart = static_cast<float*>(ws);
+  float* bpart = db ? wpart + static_cast<size_t>(pl.splits) * Cout * taps * ctot : nullptr;
+  if (taps == 9) rc = launch_wgrad_cfg<9, 4>(x0, C0, x1, C1, dz, Cout, wpart, bpart, pl, N, H, W, merged, st);
+  else           rc = launch_wgrad_cfg<1, 4>(x0, C0, x1, C1, dz, Cout, wpart, bpart, pl, N, H, W, merged, st);
   if (rc) return rc;
+  if (db) {
+    wgrad_bias_reduce_kernel<<<(Cout + 127) / 128, 128, 0, st>>>(bpart, db, pl.splits, Cout);
+    cudaError_t eb = cudaGetLastError();
+    if (eb != cudaSuccess) return set_error(B2U_ERR_CUDA, "wgrad_bias_reduce launch: %s", cudaGetErrorString(eb));
+    note_launch();
+  }
   const int cin_real = first_cin > 0 ? first_cin : ctot;
   const int rtaps = first_cin > 0 ? 9 : taps;
   const int total = Cout * cin_real;
-  wgrad_reduce_kernel<<<(total + 127) / 128, 128, 0, st>>>(static_cast<const float*>(ws), dw, pl.splits, Cout, rtaps, ctot,
-                                                           cin_real, first_cin > 0 ? 1 : 0);
+  if (taps == 9)
+    wgrad_reduce9_kernel<<<dim3(ctot / 64, Cout), 160, 0, st>>>(static_cast<const float*>(ws), dw, pl.splits, Cout, ctot);
+  else
+    wgrad_reduce_kernel<<<(total + 127) / 128, 128, 0, st>>>(static_cast<const float*>(ws), dw, pl.splits, Cout, rtaps, ctot,
+                                                             cin_real, first_cin > 0 ? 1 : 0);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(B2U_ERR_CUDA, "wgrad_reduce launch: %s", cudaGetErrorString(e));
   note_launch();

@@ -20,6 +20,12 @@ static inline int grid_for(long long n, int block) {
   return static_cast<int>(g);
 }
 
+// Row-indexed launches: blockIdx.x = image row (n * rows_per_image + row), blockIdx.y * blockDim.x + threadIdx.x = position
+// inside the row (pixel * C8 + channel chunk).  One 32-bit division per thread instead of three 64-bit ones.
+static inline dim3 row_grid(long long rows, int row_items, int block) {
+  return dim3(static_cast<unsigned>(rows), static_cast<unsigned>((row_items + block - 1) / block), 1);
+}
+
 #define B2U_CHECK_LAUNCH(name)                                                                           \
   do {                                                                                                   \
     cudaError_t e__ = cudaGetLastError();                                                                \
@@ -44,27 +50,25 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 // ---------------------------------------------------------------------------------------------
 __global__ void im2col_first_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int Cin, int H,
                                     int W) {
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // (pixel, chunk of 8 k)
-  const long long total = static_cast<long long>(N) * H * W * 8;
-  if (idx >= total) return;
-  const int chunk = static_cast<int>(idx & 7);
-  long long pix = idx >> 3;
-  const int w = static_cast<int>(pix % W); pix /= W;
-  const int h = static_cast<int>(pix % H);
-  const int n = static_cast<int>(pix / H);
+  const unsigned t = blockIdx.y * blockDim.x + threadIdx.x;    // (w, chunk of 8 k)
+  if (t >= static_cast<unsigned>(W) * 8u) return;
+  const int chunk = t & 7, w = t >> 3;
+  const int n = blockIdx.x / H, h = blockIdx.x % H;
   float f[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int k = chunk * 8 + e;
-    float v = 0.f;
-    if (k < 9 * Cin) {
-      const int tap = k / Cin, c = k % Cin;
-      const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-      if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(x + ((static_cast<size_t>(n) * Cin + c) * H + hh) * W + ww);
+  for (int e = 0; e < 8; ++e) f[e] = 0.f;
+  if (chunk * 8 < 9 * Cin) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = chunk * 8 + e;
+      if (k < 9 * Cin) {
+        const int tap = k / Cin, c = k - tap * Cin;
+        const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) f[e] = __ldg(x + ((static_cast<size_t>(n) * Cin + c) * H + hh) * W + ww);
+      }
     }
-    f[e] = v;
   }
-  reinterpret_cast<uint4*>(col)[idx] = pack8(f);
+  reinterpret_cast<uint4*>(col)[(static_cast<size_t>(blockIdx.x) * W + w) * 8 + chunk] = pack8(f);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -109,14 +113,10 @@ __device__ __forceinline__ uint32_t max2_bf16(uint32_t a, uint32_t b) {
 }
 __global__ void maxpool2x2_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int C8) {
   const int Ho = H / 2, Wo = W / 2;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(N) * Ho * Wo * C8;
-  if (idx >= total) return;
-  const int c = static_cast<int>(idx % C8);
-  long long t = idx / C8;
-  const int wo = static_cast<int>(t % Wo); t /= Wo;
-  const int ho = static_cast<int>(t % Ho);
-  const int n = static_cast<int>(t / Ho);
+  const unsigned t = blockIdx.y * blockDim.x + threadIdx.x;
+  if (t >= static_cast<unsigned>(Wo) * C8) return;
+  const int wo = t / C8, c = t - wo * C8;
+  const int n = blockIdx.x / Ho, ho = blockIdx.x - n * Ho;
   const size_t base = ((static_cast<size_t>(n) * H + 2 * ho) * W + 2 * wo) * C8 + c;
   const uint4 a = __ldg(x + base), b = __ldg(x + base + C8);
   const uint4 d = __ldg(x + base + static_cast<size_t>(W) * C8), e = __ldg(x + base + static_cast<size_t>(W) * C8 + C8);
@@ -125,7 +125,7 @@ __global__ void maxpool2x2_fwd_kernel(const uint4* __restrict__ x, uint4* __rest
   m.y = max2_bf16(max2_bf16(a.y, b.y), max2_bf16(d.y, e.y));
   m.z = max2_bf16(max2_bf16(a.z, b.z), max2_bf16(d.z, e.z));
   m.w = max2_bf16(max2_bf16(a.w, b.w), max2_bf16(d.w, e.w));
-  y[idx] = m;
+  y[static_cast<size_t>(blockIdx.x) * Wo * C8 + t] = m;
 }
 
 // dz[pos] = ((pos == argmax ? dpool : 0) + dskip[pos]) * (y[pos] > 0)   for the 4 positions of each window
@@ -133,14 +133,11 @@ __global__ void maxpool2x2_bwd_kernel(const uint4* __restrict__ dpool, const uin
                                       const uint4* __restrict__ y, uint4* __restrict__ dz, int N, int H, int W, int C8,
                                       int use_mask) {
   const int Ho = H / 2, Wo = W / 2;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(N) * Ho * Wo * C8;
-  if (idx >= total) return;
-  const int c = static_cast<int>(idx % C8);
-  long long t = idx / C8;
-  const int wo = static_cast<int>(t % Wo); t /= Wo;
-  const int ho = static_cast<int>(t % Ho);
-  const int n = static_cast<int>(t / Ho);
+  const unsigned t = blockIdx.y * blockDim.x + threadIdx.x;
+  if (t >= static_cast<unsigned>(Wo) * C8) return;
+  const int wo = t / C8, c = t - wo * C8;
+  const int n = blockIdx.x / Ho, ho = blockIdx.x - n * Ho;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * Wo * C8 + t;
   const size_t base = ((static_cast<size_t>(n) * H + 2 * ho) * W + 2 * wo) * C8 + c;
   const size_t off[4] = {base, base + C8, base + static_cast<size_t>(W) * C8, base + static_cast<size_t>(W) * C8 + C8};
   float yv[4][8], g[8];
@@ -181,14 +178,10 @@ __device__ __forceinline__ void src_index(int o, float scale, int in_size, int& 
 __global__ void upsample2x_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int C8,
                                       float sh, float sw) {
   const int Ho = 2 * H, Wo = 2 * W;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(N) * Ho * Wo * C8;
-  if (idx >= total) return;
-  const int c = static_cast<int>(idx % C8);
-  long long t = idx / C8;
-  const int wo = static_cast<int>(t % Wo); t /= Wo;
-  const int ho = static_cast<int>(t % Ho);
-  const int n = static_cast<int>(t / Ho);
+  const unsigned t = blockIdx.y * blockDim.x + threadIdx.x;
+  if (t >= static_cast<unsigned>(Wo) * C8) return;
+  const int wo = t / C8, c = t - wo * C8;
+  const int n = blockIdx.x / Ho, ho = blockIdx.x - n * Ho;
   int h0, h1, w0, w1; float lh, lw;
   src_index(ho, sh, H, h0, h1, lh);
   src_index(wo, sw, W, w0, w1, lw);
@@ -201,50 +194,60 @@ __global__ void upsample2x_fwd_kernel(const uint4* __restrict__ x, uint4* __rest
   const float h0l = 1.f - lh, w0l = 1.f - lw;
 #pragma unroll
   for (int k = 0; k < 8; ++k) o[k] = h0l * (w0l * a[k] + lw * b[k]) + lh * (w0l * d[k] + lw * e[k]);
-  y[idx] = pack8(o);
+  y[static_cast<size_t>(blockIdx.x) * Wo * C8 + t] = pack8(o);
 }
 
 // adjoint: dlow[h,w] = sum over output pixels (ho,wo) of weight(ho->h) * weight(wo->w) * dup[ho,wo], then ReLU mask
+// For scale 2 every low-res index receives contributions from at most kUpCand consecutive output indices,
+// starting at floor((i - 1) / scale); candidates with zero weight cost one multiply, not a branch.
+constexpr int kUpCand = 6;
+__device__ __forceinline__ void adjoint_weights(int i, float scale, float inv_scale, int in_size, int out_size, int& o_lo,
+                                                float* wts) {
+  o_lo = static_cast<int>(floorf((i - 1) * inv_scale));
+  if (o_lo < 0) o_lo = 0;
+#pragma unroll
+  for (int j = 0; j < kUpCand; ++j) {
+    const int o = o_lo + j;
+    int i0, i1; float lam;
+    src_index(o, scale, in_size, i0, i1, lam);
+    float wt = 0.f;
+    if (o < out_size) {
+      if (i0 == i) wt += 1.f - lam;
+      if (i1 == i) wt += lam;
+    }
+    wts[j] = wt;
+  }
+}
 __global__ void upsample2x_bwd_kernel(const uint4* __restrict__ dup, const uint4* __restrict__ ylow,
                                       uint4* __restrict__ dlow, int N, int H, int W, int C8, float sh, float sw,
                                       float inv_sh, float inv_sw) {
   const int Ho = 2 * H, Wo = 2 * W;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(N) * H * W * C8;
-  if (idx >= total) return;
-  const int c = static_cast<int>(idx % C8);
-  long long t = idx / C8;
-  const int w = static_cast<int>(t % W); t /= W;
-  const int h = static_cast<int>(t % H);
-  const int n = static_cast<int>(t / H);
-  // candidate outputs: src in (h-1, h+1)  ->  o in ((h-1)/s, (h+1)/s); pad by one on each side
-  int ho_lo = static_cast<int>(floorf((h - 1) * inv_sh)) - 1; if (ho_lo < 0) ho_lo = 0;
-  int ho_hi = static_cast<int>(ceilf((h + 1) * inv_sh)) + 1;  if (ho_hi > Ho - 1) ho_hi = Ho - 1;
-  int wo_lo = static_cast<int>(floorf((w - 1) * inv_sw)) - 1; if (wo_lo < 0) wo_lo = 0;
-  int wo_hi = static_cast<int>(ceilf((w + 1) * inv_sw)) + 1;  if (wo_hi > Wo - 1) wo_hi = Wo - 1;
+  const unsigned t = blockIdx.y * blockDim.x + threadIdx.x;
+  if (t >= static_cast<unsigned>(W) * C8) return;
+  const int w = t / C8, c = t - w * C8;
+  const int n = blockIdx.x / H, h = blockIdx.x - n * H;
+  int ho_lo, wo_lo;
+  float wh[kUpCand], ww[kUpCand];
+  adjoint_weights(h, sh, inv_sh, H, Ho, ho_lo, wh);
+  adjoint_weights(w, sw, inv_sw, W, Wo, wo_lo, ww);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const size_t img = static_cast<size_t>(n) * Ho * Wo;
-  for (int ho = ho_lo; ho <= ho_hi; ++ho) {
-    int h0, h1; float lh;
-    src_index(ho, sh, H, h0, h1, lh);
-    float wh = 0.f;
-    if (h0 == h) wh += 1.f - lh;
-    if (h1 == h) wh += lh;
-    if (wh == 0.f) continue;
-    for (int wo = wo_lo; wo <= wo_hi; ++wo) {
-      int w0, w1; float lw;
-      src_index(wo, sw, W, w0, w1, lw);
-      float ww = 0.f;
-      if (w0 == w) ww += 1.f - lw;
-      if (w1 == w) ww += lw;
-      if (ww == 0.f) continue;
-      float g[8];
-      unpack8(__ldg(dup + (img + static_cast<size_t>(ho) * Wo + wo) * C8 + c), g);
-      const float wt = wh * ww;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] += wt * g[k];
+  for (int a = 0; a < kUpCand; ++a) {
+    if (wh[a] == 0.f) continue;                       // warp-uniform in h (one image row per block row)
+    const int ho = ho_lo + a;
+    const uint4* rowp = dup + (img + static_cast<size_t>(ho) * Wo) * C8 + c;
+#pragma unroll
+    for (int b = 0; b < kUpCand; ++b) {
+      const int wo = min(wo_lo + b, Wo - 1);
+      float g[8];
+      unpack8(__ldg(rowp + static_cast<size_t>(wo) * C8), g);
+      const float wt = wh[a] * ww[b];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = fmaf(wt, g[k], acc[k]);
     }
   }
+  const size_t idx = static_cast<size_t>(blockIdx.x) * W * C8 + t;
   if (ylow) {
     float m[8];
     unpack8(__ldg(ylow + idx), m);
@@ -340,8 +343,7 @@ using namespace b2u;
 
 int b2u_im2col_first(const float* x, void* col, int N, int Cin, int H, int W, void* stream) {
   if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || 9 * Cin > 64) return set_error(B2U_ERR_SHAPE, "im2col_first: bad shape (Cin=%d)", Cin);
-  const long long total = static_cast<long long>(N) * H * W * 8;
-  im2col_first_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  im2col_first_kernel<<<row_grid(static_cast<long long>(N) * H, W * 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, static_cast<__nv_bfloat16*>(col), N, Cin, H, W);
   B2U_CHECK_LAUNCH("im2col_first");
   return 0;
@@ -367,8 +369,7 @@ int b2u_pack_weights_first(const float* w, void* wf, int Cout, int Cin, void* st
 int b2u_maxpool2x2_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream) {
   if (N <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || C % 8 != 0)
     return set_error(B2U_ERR_SHAPE, "maxpool2x2_fwd: H,W must be even and C %% 8 == 0 (H=%d W=%d C=%d)", H, W, C);
-  const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
-  maxpool2x2_fwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  maxpool2x2_fwd_kernel<<<row_grid(static_cast<long long>(N) * (H / 2), (W / 2) * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(x), static_cast<uint4*>(y), N, H, W, C / 8);
   B2U_CHECK_LAUNCH("maxpool2x2_fwd");
   return 0;
@@ -379,8 +380,7 @@ int b2u_maxpool2x2_bwd(const void* dpool, const void* dskip, const void* y, void
                        int relu_mask, void* stream) {
   if (N <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || C % 8 != 0)
     return set_error(B2U_ERR_SHAPE, "maxpool2x2_bwd: H,W must be even and C %% 8 == 0");
-  const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
-  maxpool2x2_bwd_kernel<<<grid_for(total, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  maxpool2x2_bwd_kernel<<<row_grid(static_cast<long long>(N) * (H / 2), (W / 2) * (C / 8), 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(dpool), static_cast<const uint4*>(dskip), static_cast<const uint4*>(y),
       static_cast<uint4*>(dz), N, H, W, C / 8, relu_mask);
   B2U_CHECK_LAUNCH("maxpool2x2_bwd");
@@ -392,8 +392,7 @@ int b2u_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, void*
   if (N <= 0 || H <= 0 || W <= 0 || C % 8 != 0) return set_error(B2U_ERR_SHAPE, "upsample2x_fwd: bad shape");
   const float sh = (2 * H > 1) ? static_cast<float>(H - 1) / static_cast<float>(2 * H - 1) : 0.f;
   const float sw = (2 * W > 1) ? static_cast<float>(W - 1) / static_cast<float>(2 * W - 1) : 0.f;
-  const long long total = static_cast<long long>(N) * 4 * H * W * (C / 8);
-  upsample2x_fwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  upsample2x_fwd_kernel<<<row_grid(static_cast<long long>(N) * 2 * H, 2 * W * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(x), static_cast<uint4*>(y), N, H, W, C / 8, sh, sw);
   B2U_CHECK_LAUNCH("upsample2x_fwd");
   return 0;
@@ -406,8 +405,7 @@ int b2u_upsample2x_bwd(const void* dup, const void* ylow, void* dlow, int N, int
   const float sw = static_cast<float>(W - 1) / static_cast<float>(2 * W - 1);
   const float ish = H > 1 ? 1.f / sh : 4.f * H;   // H == 1: every output maps to row 0
   const float isw = W > 1 ? 1.f / sw : 4.f * W;
-  const long long total = static_cast<long long>(N) * H * W * (C / 8);
-  upsample2x_bwd_kernel<<<grid_for(total, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  upsample2x_bwd_kernel<<<row_grid(static_cast<long long>(N) * H, W * (C / 8), 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(dup), static_cast<const uint4*>(ylow), static_cast<uint4*>(dlow), N, H, W, C / 8, sh, sw,
       ish, isw);
   B2U_CHECK_LAUNCH("upsample2x_bwd");

@@ -253,6 +253,93 @@ loss_stats_kernel(const float* __restrict__ logits, const long long* __restrict_
   }
 }
 
+// Label-map variant (the training loop's case): only P_c and Pf_c need a per-class register; the three sums that
+// involve the pixel's own class (tp, T, tpf) go to per-warp shared-memory tables.  tp is accumulated in 2^-32
+// fixed point so the result does not depend on the order in which lanes reach the table.
+__global__ void __launch_bounds__(kLossThreads)
+loss_stats_map_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
+                      const float* __restrict__ cls_w, double* __restrict__ partial, long long HW, long long P, int C,
+                      float focal_alpha, float focal_gamma, float thr) {
+  constexpr int kWarps = kLossThreads / 32;
+  __shared__ float swt[kMaxCls];
+  __shared__ unsigned long long s_tp[kWarps][kMaxCls];
+  __shared__ unsigned int s_T[kWarps][kMaxCls], s_tpf[kWarps][kMaxCls];
+  extern __shared__ double sred[];   // [2C + 4][warps]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) swt[i] = cls_w ? cls_w[i] : 1.f;
+  for (int i = threadIdx.x; i < kWarps * kMaxCls; i += blockDim.x) {
+    (&s_tp[0][0])[i] = 0ull; (&s_T[0][0])[i] = 0u; (&s_tpf[0][0])[i] = 0u;
+  }
+  __syncthreads();
+  float a_ce = 0.f, a_w = 0.f, a_focal = 0.f, a_cnt = 0.f;
+  float Ps[kMaxCls], Pf[kMaxCls];
+#pragma unroll
+  for (int c = 0; c < kMaxCls; ++c) { Ps[c] = Pf[c] = 0.f; }
+
+  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < P;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = p / HW, hw = p % HW;
+    const float* z = logits + n * C * HW + hw;
+    float v[kMaxCls];
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < kMaxCls; ++c) if (c < C) { v[c] = __ldg(z + c * HW); m = fmaxf(m, v[c]); }
+    const long long y = target[p];
+    const bool valid = y >= 0 && y < C;
+    const float zy = valid ? __ldg(z + y * HW) : 0.f;
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxCls; ++c) if (c < C) { v[c] = expf(v[c] - m); sum += v[c]; }
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int c = 0; c < kMaxCls; ++c) if (c < C) {
+      const float pc = v[c] * inv;
+      Ps[c] += pc;
+      Pf[c] += pc > thr ? 1.f : 0.f;
+    }
+    a_cnt += 1.f;
+    if (valid) {
+      const float nll = m + logf(sum) - zy;
+      const float wy = swt[y];
+      a_ce += wy * nll; a_w += wy;
+      const float logpt = -wy * nll;
+      const float pt = expf(logpt);
+      a_focal += -powf(fmaxf(1.f - pt, 0.f), focal_gamma) * (focal_alpha * logpt);
+      const float py = expf(zy - m) * inv;
+      atomicAdd(&s_tp[warp][y], static_cast<unsigned long long>(static_cast<double>(py) * 4294967296.0));
+      atomicAdd(&s_T[warp][y], 1u);
+      if (py > thr) atomicAdd(&s_tpf[warp][y], 1u);
+    }
+  }
+  const int nwarps = kWarps;
+  auto red = [&](float val, int slot) {
+    double d = static_cast<double>(val);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if (lane == 0) sred[slot * nwarps + warp] = d;
+  };
+  red(a_ce, 0); red(a_w, 1); red(a_focal, 2); red(a_cnt, 3);
+#pragma unroll
+  for (int c = 0; c < kMaxCls; ++c) if (c < C) { red(Ps[c], 4 + c); red(Pf[c], 4 + C + c); }
+  __syncthreads();
+  const int L = 5 * C + 4;
+  double* out = partial + static_cast<size_t>(blockIdx.x) * L;
+  for (int sI = threadIdx.x; sI < 2 * C + 4; sI += blockDim.x) {
+    double d = 0.0;
+    for (int w2 = 0; w2 < nwarps; ++w2) d += sred[sI * nwarps + w2];
+    if (sI < 4) out[sI] = d;
+    else if (sI < 4 + C) out[4 + C + (sI - 4)] = d;              // P_c
+    else out[4 + 4 * C + (sI - 4 - C)] = d;                      // Pf_c
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    unsigned long long tp = 0; unsigned int T = 0, tpf = 0;
+    for (int w2 = 0; w2 < nwarps; ++w2) { tp += s_tp[w2][c]; T += s_T[w2][c]; tpf += s_tpf[w2][c]; }
+    out[4 + c] = static_cast<double>(tp) / 4294967296.0;         // tp_c
+    out[4 + 2 * C + c] = static_cast<double>(T);                 // T_c
+    out[4 + 3 * C + c] = static_cast<double>(tpf);               // tpf_c
+  }
+}
+
 // out (floats): [0] CE  [1] Focal  [2] Dice loss  [3] f_score, then per class A_c (4..4+C) and B_c (4+C..4+2C)
 // (Dice backward coefficients), then [4+2C] = 1/sum_w, [4+2C+1] = 1/pixel count.
 __global__ void loss_finalize_kernel(const double* __restrict__ partial, int blocks, int C, float beta, float smooth,
@@ -288,7 +375,8 @@ __global__ void loss_finalize_kernel(const double* __restrict__ partial, int blo
 }
 
 // dlogits = g_ce * dCE/dz + g_focal * dFocal/dz + g_dice * dDice/dz   (coefficients from loss_finalize)
-template <bool ONEHOT>
+// NHWC64: dlogits leave as bf16 [pixel][64] (channels >= C zero) = the dz operand of the tensor-core 1x1 dgrad/wgrad
+template <bool ONEHOT, bool NHWC64>
 __global__ void __launch_bounds__(kLossThreads)
 loss_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ target, const float* __restrict__ onehot,
                 const float* __restrict__ cls_w, const float* __restrict__ fin, const float* __restrict__ gscale,
@@ -346,13 +434,46 @@ loss_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ 
       gdot += (sA[c] * t[c] + sB[c]) * (v[c] * inv);
     }
   }
+  float dv[kMaxCls];
 #pragma unroll
-  for (int c = 0; c < kMaxCls; ++c) if (c < C) {
-    const float pc = v[c] * inv;
-    float d = k_py * (pc - ((valid && c == y) ? 1.f : 0.f));
-    if (g_dice != 0.f) d += g_dice * pc * (sA[c] * t[c] + sB[c] - gdot);
-    dzp[c * HW] = d;
+  for (int c = 0; c < kMaxCls; ++c) {
+    float d = 0.f;
+    if (c < C) {
+      const float pc = v[c] * inv;
+      d = k_py * (pc - ((valid && c == y) ? 1.f : 0.f));
+      if (g_dice != 0.f) d += g_dice * pc * (sA[c] * t[c] + sB[c] - gdot);
+      if (!NHWC64) dzp[c * HW] = d;
+    }
+    dv[c] = d;
   }
+  if (NHWC64) {
+    // channels [0,32): bf16(d); channels [32,64): bf16(d - hi).  The two halves meet the SAME weights in the 1x1
+    // dgrad/wgrad (K resp. M is padded to 64 anyway), so the head's backward sees dlogits to ~2^-17 at no cost.
+    uint4* o = reinterpret_cast<uint4*>(dlogits) + p * 8;      // 64 bf16 = 8 x 16 B per pixel
+    float lo[kMaxCls];
+#pragma unroll
+    for (int c = 0; c < kMaxCls; ++c) lo[c] = dv[c] - __bfloat162float(__float2bfloat16_rn(dv[c]));
+#pragma unroll
+    for (int q = 0; q < kMaxCls / 8; ++q) {
+      uint4 r;
+      r.x = pack_bf16x2(dv[q * 8 + 0], dv[q * 8 + 1]); r.y = pack_bf16x2(dv[q * 8 + 2], dv[q * 8 + 3]);
+      r.z = pack_bf16x2(dv[q * 8 + 4], dv[q * 8 + 5]); r.w = pack_bf16x2(dv[q * 8 + 6], dv[q * 8 + 7]);
+      o[q] = r;
+      uint4 l;
+      l.x = pack_bf16x2(lo[q * 8 + 0], lo[q * 8 + 1]); l.y = pack_bf16x2(lo[q * 8 + 2], lo[q * 8 + 3]);
+      l.z = pack_bf16x2(lo[q * 8 + 4], lo[q * 8 + 5]); l.w = pack_bf16x2(lo[q * 8 + 6], lo[q * 8 + 7]);
+      o[kMaxCls / 8 + q] = l;
+    }
+  }
+}
+
+// final.weight [C][64] fp32 -> dgrad operand wd[ci][co] bf16, 64 x 64: columns [0,32) and [32,64) both hold W
+// (they multiply the hi and lo halves of the split dlogits), classes >= C are zero
+__global__ void pack_head_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wd, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 64) return;
+  const int ci = i / 64, co = (i % 64) % kMaxCls;
+  wd[i] = __float2bfloat16_rn(co < C ? w[co * 64 + ci] : 0.f);
 }
 
 // arg-max over classes (lowest index on ties, like numpy/torch): logits NCHW fp32 -> uint8 mask [N,H,W]
@@ -431,8 +552,8 @@ int b2u_loss_fwd(const float* logits, const long long* target, const float* oneh
     loss_stats_kernel<true><<<blocks, kLossThreads, sm, st>>>(logits, target, onehot, cls_w, static_cast<double*>(ws), HW, P, C,
                                                               focal_alpha, focal_gamma, thr);
   else
-    loss_stats_kernel<false><<<blocks, kLossThreads, sm, st>>>(logits, target, onehot, cls_w, static_cast<double*>(ws), HW, P, C,
-                                                               focal_alpha, focal_gamma, thr);
+    loss_stats_map_kernel<<<blocks, kLossThreads, static_cast<size_t>(2 * C + 4) * (kLossThreads / 32) * sizeof(double), st>>>(
+        logits, target, cls_w, static_cast<double*>(ws), HW, P, C, focal_alpha, focal_gamma, thr);
   B2U_CHECK_LAUNCH("loss_stats");
   loss_finalize_kernel<<<1, 128, L * sizeof(double), st>>>(static_cast<const double*>(ws), blocks, C, beta, smooth, out, stats);
   B2U_CHECK_LAUNCH("loss_finalize");
@@ -440,21 +561,33 @@ int b2u_loss_fwd(const float* logits, const long long* target, const float* oneh
 }
 
 // fin: the `out` vector of b2u_loss_fwd; gscale: 3 floats on device = upstream gradients of (CE, Focal, Dice)
+// out_mode 0: dlogits fp32 NCHW [N,C,H,W]; 1: bf16 NHWC [N,H,W,64] zero padded (feeds b2u_conv_dgrad/wgrad, taps=1)
 int b2u_loss_bwd(const float* logits, const long long* target, const float* onehot, const float* cls_w, const float* fin,
-                 const float* gscale, float* dlogits, int N, int C, int H, int W, float focal_alpha, float focal_gamma,
-                 void* stream) {
+                 const float* gscale, void* dlogits, int out_mode, int N, int C, int H, int W, float focal_alpha,
+                 float focal_gamma, void* stream) {
   if (C <= 0 || C > kMaxCls) return set_error(B2U_ERR_SHAPE, "loss_bwd: 1 <= classes <= 32");
   if (N <= 0 || H <= 0 || W <= 0) return set_error(B2U_ERR_SHAPE, "loss_bwd: empty tensor");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long HW = static_cast<long long>(H) * W, P = HW * N;
   const unsigned blocks = static_cast<unsigned>((P + kLossThreads - 1) / kLossThreads);
-  if (onehot)
-    loss_bwd_kernel<true><<<blocks, kLossThreads, 0, st>>>(logits, target, onehot, cls_w, fin, gscale, dlogits, HW, P, C,
-                                                           focal_alpha, focal_gamma);
-  else
-    loss_bwd_kernel<false><<<blocks, kLossThreads, 0, st>>>(logits, target, onehot, cls_w, fin, gscale, dlogits, HW, P, C,
-                                                            focal_alpha, focal_gamma);
+  float* out = static_cast<float*>(dlogits);
+  if (out_mode == 1) {
+    if (onehot) loss_bwd_kernel<true, true><<<blocks, kLossThreads, 0, st>>>(logits, target, onehot, cls_w, fin, gscale, out, HW, P, C, focal_alpha, focal_gamma);
+    else        loss_bwd_kernel<false, true><<<blocks, kLossThreads, 0, st>>>(logits, target, onehot, cls_w, fin, gscale, out, HW, P, C, focal_alpha, focal_gamma);
+  } else if (out_mode == 0) {
+    if (onehot) loss_bwd_kernel<true, false><<<blocks, kLossThreads, 0, st>>>(logits, target, onehot, cls_w, fin, gscale, out, HW, P, C, focal_alpha, focal_gamma);
+    else        loss_bwd_kernel<false, false><<<blocks, kLossThreads, 0, st>>>(logits, target, onehot, cls_w, fin, gscale, out, HW, P, C, focal_alpha, focal_gamma);
+  } else {
+    return set_error(B2U_ERR_ARG, "loss_bwd: out_mode must be 0 or 1");
+  }
   B2U_CHECK_LAUNCH("loss_bwd");
+  return 0;
+}
+
+int b2u_pack_head_dgrad(const float* w, void* wd, int ncls, void* stream) {
+  if (ncls <= 0 || ncls > kMaxCls) return set_error(B2U_ERR_SHAPE, "pack_head_dgrad: 1 <= classes <= 32");
+  pack_head_dgrad_kernel<<<16, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, static_cast<__nv_bfloat16*>(wd), ncls);
+  B2U_CHECK_LAUNCH("pack_head_dgrad");
   return 0;
 }
 

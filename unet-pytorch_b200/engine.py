@@ -79,6 +79,10 @@ class VGGUnetEngine:
         for name, cs, cu, co in DECODER_CFG:
             self.dec.append((_Conv(f"{name}.conv1", cs + cu, co, c0=cs, c1=cu), _Conv(f"{name}.conv2", co, co)))
         self.convs = [c for b in self.enc for c in b] + [c for pair in self.dec for c in pair]
+        # The wgrad kernel can produce db in the same pass (an N=16 MMA against a ones tile); measured on B200 it costs
+        # more than the separate HBM-bound column-sum kernel (work units with the extra MMAs become the stragglers of
+        # the static schedule: +40 % wgrad time vs +1.2 ms for bias_grad), so it is off by default.
+        self.fuse_bias_grad = False
         self._bufs = {}
         self._shape = None
         self.saved = None
@@ -177,7 +181,8 @@ class VGGUnetEngine:
 
     # ------------------------------------------------------------------ backward
     def backward(self, dlogits, params, grads, trainable=None, on_grads_ready=None):
-        """dlogits: NCHW fp32.  grads: name -> fp32 tensor to overwrite (missing / not in `trainable`: skipped).
+        """dlogits: NCHW fp32, or bf16 [N,H,W,64] from ops.loss_bwd(nhwc64=True).  grads: name -> fp32 tensor to
+        overwrite (missing / not in `trainable`: skipped).
         Returns nothing; the input image gets no gradient (the reference never asks for one)."""
         if self.saved is None:
             raise RuntimeError("backward() without a saved forward()")
@@ -198,25 +203,46 @@ class VGGUnetEngine:
             if not want[c.name]:
                 return
             wn, bn = c.name + ".weight", c.name + ".bias"
-            if wn in trainable and wn in grads:
+            want_w = wn in trainable and wn in grads
+            want_b = bn in trainable and bn in grads
+            fuse_b = want_w and want_b and self.fuse_bias_grad
+            if want_w:
                 need = ops.lib().b2u_conv_wgrad_workspace(dz.shape[0], dz.shape[1], dz.shape[2],
                                                           64 if c.first else c.cin, c.cout, 1 if c.first else 9)
                 ops.conv_wgrad(x0, dz, taps=1 if c.first else 9, x1=x1, first_cin=c.cin if c.first else 0,
-                               dw=grads[wn], ws=self._workspace("wgrad", need))
-            if bn in trainable and bn in grads:
+                               dw=grads[wn], db=grads[bn] if fuse_b else None, ws=self._workspace("wgrad", need))
+            if want_b and not fuse_b:
                 ops.bias_grad(dz, db=grads[bn], ws=self._workspace("bias", ops.lib().b2u_bias_grad_workspace(c.cout)))
             ready(wn, bn)
 
-        dl = dlogits.contiguous()
-        if dl.dtype != torch.float32:
-            dl = dl.float()
         last = A[self.dec[-1][1].name]
         wfin = params["final.weight"].reshape(self.num_classes, 64)
         fw, fb = "final.weight" in trainable and "final.weight" in grads, "final.bias" in trainable and "final.bias" in grads
         dz = self._buf("g:" + self.dec[-1][1].name, last.shape) if need_dx["final"] else None
-        ops.head_bwd(dl, last, wfin, need_dx=need_dx["final"], need_dw=fw or fb, relu_mask=True, dx=dz,
-                     dw=grads["final.weight"] if fw else None, db=grads["final.bias"] if fb else None,
-                     ws=self._workspace("head", ops.lib().b2u_head_bwd_workspace()))
+        if dlogits.dtype == torch.bfloat16:
+            # [N,H,W,64] = [hi | lo] split dlogits from loss_bwd(nhwc64=True): the head's backward runs on the tensor
+            # cores as a 1x1 dgrad (+ReLU mask) and a 1x1 wgrad (+bias) over 2 x 32 padded classes
+            dl = dlogits.contiguous()
+            if need_dx["final"]:
+                wd_head = ops.pack_head_dgrad(wfin, wd=self._buf("head:wd", (64, 64)))
+                ops.conv_dgrad(dl, wd_head, 64, taps=1, mask=last, out0=dz)
+            if fw or fb:
+                dw64 = self._buf("head:dw", (64, 64, 1, 1), torch.float32)
+                db64 = self._buf("head:db", (64,), torch.float32)
+                need = ops.lib().b2u_conv_wgrad_workspace(dl.shape[0], dl.shape[1], dl.shape[2], 64, 64, 1)
+                ops.conv_wgrad(last, dl, taps=1, dw=dw64, db=db64, ws=self._workspace("wgrad", need))
+                C = self.num_classes     # rows [0,32) came from the hi half of dlogits, rows [32,64) from the lo half
+                if fw:
+                    torch.add(dw64[:C], dw64[32:32 + C], out=grads["final.weight"])
+                if fb:
+                    torch.add(db64[:C], db64[32:32 + C], out=grads["final.bias"])
+        else:
+            dl = dlogits.contiguous()
+            if dl.dtype != torch.float32:
+                dl = dl.float()
+            ops.head_bwd(dl, last, wfin, need_dx=need_dx["final"], need_dw=fw or fb, relu_mask=True, dx=dz,
+                         dw=grads["final.weight"] if fw else None, db=grads["final.bias"] if fb else None,
+                         ws=self._workspace("head", ops.lib().b2u_head_bwd_workspace()))
         ready("final.weight", "final.bias")
         if dz is None:
             return

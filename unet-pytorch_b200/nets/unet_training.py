@@ -32,7 +32,9 @@ class _LossFunction(torch.autograd.Function):
                            gamma=gamma)
         ctx.save_for_backward(logits, target, onehot, cls_w, fin)
         ctx.cfg = (w_ce, w_focal, w_dice, alpha, gamma)
-        return w_ce * fin[0] + w_focal * fin[1] + w_dice * fin[2]
+        # only the requested terms: an unrequested CE is 0/0 = nan when no label map was given
+        terms = [wt * fin[i] for i, wt in enumerate((w_ce, w_focal, w_dice)) if wt != 0.0]
+        return sum(terms[1:], terms[0])
 
     @staticmethod
     def backward(ctx, gout):

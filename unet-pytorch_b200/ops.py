@@ -124,7 +124,7 @@ def conv_fprop(x0, wf, bias, Cout, taps=9, relu=True, x1=None, out=None, bn=0):
     C1 = 0 if x1 is None else x1.shape[3]
     if out is None:
         out = torch.empty((N, H, W, Cout), dtype=BF16, device=x0.device)
-    with _timed("conv_igemm", 2.0 * N * H * W * Cout * (C0 + C1) * taps):
+    with _timed(f"conv_igemm|fprop|{N}x{H}x{W}|{C0}+{C1}->{Cout}|t{taps}", 2.0 * N * H * W * Cout * (C0 + C1) * taps):
         check(lib().b2u_conv_fprop(ptr(x0), C0, ptr(x1), C1, ptr(wf), ptr(bias), ptr(out), N, H, W, Cout, taps,
                                    1 if relu else 0, bn, stream_ptr()))
     return out
@@ -137,13 +137,14 @@ def conv_dgrad(dz, wd, C0, taps=9, C1=0, mask=None, out0=None, out1=None, bn=0):
         out0 = torch.empty((N, H, W, C0), dtype=BF16, device=dz.device)
     if C1 > 0 and out1 is None:
         out1 = torch.empty((N, H, W, C1), dtype=BF16, device=dz.device)
-    with _timed("conv_igemm", 2.0 * N * H * W * Cz * (C0 + C1) * taps):
+    with _timed(f"conv_igemm|dgrad|{N}x{H}x{W}|{Cz}->{C0}+{C1}|t{taps}", 2.0 * N * H * W * Cz * (C0 + C1) * taps):
         check(lib().b2u_conv_dgrad(ptr(dz), Cz, ptr(wd), ptr(out0), C0, ptr(out1) if C1 > 0 else None, C1, ptr(mask),
                                    N, H, W, taps, bn, stream_ptr()))
     return (out0, out1) if C1 > 0 else out0
 
 
-def conv_wgrad(x0, dz, taps=9, x1=None, first_cin=0, dw=None, ws=None, flags=0):
+def conv_wgrad(x0, dz, taps=9, x1=None, first_cin=0, dw=None, ws=None, flags=0, db=None, want_db=False):
+    """Returns dw, or (dw, db) when the bias gradient is requested (db tensor given or want_db)."""
     _req(x0, BF16, "x0"); _req(x1, BF16, "x1"); _req(dz, BF16, "dz")
     N, H, W, C0 = x0.shape
     C1 = 0 if x1 is None else x1.shape[3]
@@ -157,10 +158,12 @@ def conv_wgrad(x0, dz, taps=9, x1=None, first_cin=0, dw=None, ws=None, flags=0):
         else:
             k = 3 if taps == 9 else 1
             dw = torch.empty((Cout, C0 + C1, k, k), dtype=torch.float32, device=x0.device)
-    with _timed("conv_wgrad", 2.0 * N * H * W * Cout * (C0 + C1) * taps):
-        check(lib().b2u_conv_wgrad(ptr(x0), C0, ptr(x1), C1, ptr(dz), Cout, ptr(dw), ptr(ws),
+    if want_db and db is None:
+        db = torch.empty((Cout,), dtype=torch.float32, device=x0.device)
+    with _timed(f"conv_wgrad|wgrad|{N}x{H}x{W}|{C0}+{C1}->{Cout}|t{taps}", 2.0 * N * H * W * Cout * (C0 + C1) * taps):
+        check(lib().b2u_conv_wgrad(ptr(x0), C0, ptr(x1), C1, ptr(dz), Cout, ptr(dw), ptr(db), ptr(ws),
                                    ws.numel() * ws.element_size(), N, H, W, taps, first_cin, flags, stream_ptr()))
-    return dw
+    return (dw, db) if db is not None else dw
 
 
 def bias_grad(dz, db=None, ws=None):
@@ -264,14 +267,24 @@ def loss_fwd(logits, target=None, onehot=None, cls_w=None, beta=1.0, smooth=1e-5
     return out
 
 
-def loss_bwd(logits, fin, gscale, target=None, onehot=None, cls_w=None, alpha=0.5, gamma=2.0, out=None):
+def loss_bwd(logits, fin, gscale, target=None, onehot=None, cls_w=None, alpha=0.5, gamma=2.0, out=None, nhwc64=False):
+    """dlogits as fp32 NCHW, or (nhwc64) as bf16 [N, H, W, 64] zero padded for the tensor-core head backward."""
     _req(logits, torch.float32, "logits"); _req(gscale, torch.float32, "gscale")
     N, C, H, W = logits.shape
     if out is None:
-        out = torch.empty_like(logits)
-    check(lib().b2u_loss_bwd(ptr(logits), ptr(target), ptr(onehot), ptr(cls_w), ptr(fin), ptr(gscale), ptr(out), N, C,
-                             H, W, 0.0 if alpha is None else alpha, gamma, stream_ptr()))
+        out = torch.empty((N, H, W, 64), dtype=BF16, device=logits.device) if nhwc64 else torch.empty_like(logits)
+    check(lib().b2u_loss_bwd(ptr(logits), ptr(target), ptr(onehot), ptr(cls_w), ptr(fin), ptr(gscale), ptr(out),
+                             1 if nhwc64 else 0, N, C, H, W, 0.0 if alpha is None else alpha, gamma, stream_ptr()))
     return out
+
+
+def pack_head_dgrad(w, wd=None):
+    _req(w, torch.float32, "final.weight")
+    ncls = w.shape[0]
+    if wd is None:
+        wd = torch.empty((64, 64), dtype=BF16, device=w.device)
+    check(lib().b2u_pack_head_dgrad(ptr(w), ptr(wd), ncls, stream_ptr()))
+    return wd
 
 
 def argmax_u8(logits, out=None):

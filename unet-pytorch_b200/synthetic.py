@@ -8,7 +8,7 @@ import torch.nn.functional as F
 from .engine import vgg_unet_param_shapes
 
 
-def make_params(num_classes, seed=11, in_channels=3, gain=1.0):
+def make_params(num_classes, seed=11, in_channels=3, gain=0.5):
     """He-scaled deterministic weights: tensor k of the state_dict comes from a generator seeded seed*1000+k."""
     params = {}
     for k, (name, shape) in enumerate(vgg_unet_param_shapes(num_classes, in_channels).items()):

@@ -220,16 +220,23 @@ class UnetTrainer:
         utils_fit.py:96-97."""
         imgs, pngs = self._take(imgs, pngs)
         logits, pngs, fin = self.forward_loss(imgs, pngs, save=True)
-        dlogits = ops.loss_bwd(logits, fin, self._gscale, target=pngs, onehot=None, cls_w=self.cls_w)
+        n, _, h, w = logits.shape
+        dlogits = ops.loss_bwd(logits, fin, self._gscale, target=pngs, onehot=None, cls_w=self.cls_w, nhwc64=True,
+                               out=self.engine._buf("g:logits64", (n, h, w, 64)))
         active = [n for n in self.layout.order if n in self.trainable]
         self.sync.reset(active)
         grads = {n: self.grads[n] for n in active}
         self.engine.backward(dlogits, self.params, grads, trainable=self.trainable, on_grads_ready=self.sync.ready)
         scale = self.sync.finish()
         self.optimizer_step(scale)
-        loss = fin[0] * self._gscale[0] + fin[1] * self._gscale[1] + fin[2] * self._gscale[2]
+        loss = self._total(fin)
         self.last = torch.stack([loss, fin[3]])
         return self.last
+
+    def _total(self, fin):
+        """CE | Focal (+ Dice), utils_fit.py:74-81"""
+        loss = fin[1] if self.focal else fin[0]
+        return loss + fin[2] if self.dice else loss
 
     def optimizer_step(self, grad_scale=1.0):
         self.step_count += 1
@@ -256,5 +263,4 @@ class UnetTrainer:
         """Validation iteration (utils_fit.py:111-151): forward + losses + f_score, no gradient."""
         imgs, pngs = self._take(imgs, pngs)
         _, _, fin = self.forward_loss(imgs, pngs, save=False)
-        loss = fin[0] * self._gscale[0] + fin[1] * self._gscale[1] + fin[2] * self._gscale[2]
-        return torch.stack([loss, fin[3]])
+        return torch.stack([self._total(fin), fin[3]])
