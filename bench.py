@@ -32,6 +32,8 @@ NUM_CLASSES = 21
 BATCH_PER_GPU = 16
 HW = 512
 METRIC = "unet_vgg16_512x512_train_img_per_s"
+WORKLOAD = ("Unet-VGG16 21-class 512x512 training step (fwd + CE + Dice + f_score + bwd + grad all-reduce + Adam), "
+            "batch 16 per GPU, BASELINE configs[1]")
 # fprop + dgrad + wgrad conv FLOPs per image
 TRAIN_GFLOP_PER_IMG = 1351.99
 
@@ -135,8 +137,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "img/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "Unet-VGG16 21-class 512x512 training step (fwd + CE + Dice + bwd), CPU, bounded sample of batch 2",
-                       "batch_per_step": batch},
+            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH_PER_GPU, "global_batch": BATCH_PER_GPU * args.gpus,
+                       "parallelism": f"dp{args.gpus}",
+                       "sample": f"CPU arm: each step is a bounded sample of {batch} of the {BATCH_PER_GPU} images, no optimizer step"},
             "cpu_baseline": {"value": v, "unit": "img/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -252,6 +255,11 @@ def run_ours(args):
         with open(args.detail, "w") as f:
             json.dump({"steps_timed": tsteps, "rows": rows}, f, indent=1)
 
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp))
+
     def roof(rec, traffic=None):
         if rec["ms"] <= 0:
             return None
@@ -265,16 +273,15 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": "Unet-VGG16 21-class 512x512 bf16 training step (fwd + CE + Dice + f_score + bwd + "
-                               "grad all-reduce + Adam), BASELINE configs[1]",
-                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                    "l2": "inputs larger than L2 (>= 4.7 GB of activations per step), no explicit flush"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": launches,
-        "roofline": roof(ig),
-        "roofline_wgrad": roof(wg),
+        # traffic: DRAM bytes per launch from the committed ncu capture of this same command (profiles/r1_traffic.json)
+        "roofline": roof(ig, traffic.get("conv_igemm", {}).get("dram_bytes_per_launch")),
+        "roofline_wgrad": roof(wg, traffic.get("conv_wgrad", {}).get("dram_bytes_per_launch")),
         "model_tflops": value * TRAIN_GFLOP_PER_IMG / 1e3 / world,
         "loss": loss_val[0], "f_score": loss_val[1],
     }
@@ -291,7 +298,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="images per GPU per step (BASELINE: 16)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

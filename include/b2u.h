@@ -43,6 +43,9 @@ int b2u_im2col_first(const float* x_nchw, void* col, int N, int Cin, int H, int 
  * wf[Cout][taps*Cin] for fprop, wd[Cin][taps*Cout] (taps flipped) for dgrad; either may be NULL. */
 int b2u_pack_weights(const float* w_oihw, void* wf, void* wd, int Cout, int Cin, int taps, void* stream);
 int b2u_pack_weights_first(const float* w_oihw, void* wf, int Cout, int Cin, void* stream);
+/* every conv of the model in one launch; table (DEVICE memory): n x {const float* w; void* wf; void* wd; long long start;
+ * int Cout, Cin, taps, first} (48 B each), start = prefix sum of element counts (Cout*Cin*taps; first layer Cout*64) */
+int b2u_pack_weights_multi(const void* table, int n, long long total, void* stream);
 int b2u_nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, int H, int W, void* stream);
 int b2u_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int W, void* stream);
 

@@ -18,6 +18,7 @@ SIGNATURES = {
     "b2u_im2col_first": (I, [P, P, I, I, I, I, P]),
     "b2u_pack_weights": (I, [P, P, P, I, I, I, P]),
     "b2u_pack_weights_first": (I, [P, P, I, I, P]),
+    "b2u_pack_weights_multi": (I, [P, I, LL, P]),
     "b2u_nhwc_bf16_to_nchw_f32": (I, [P, P, I, I, I, I, P]),
     "b2u_nchw_f32_to_nhwc_bf16": (I, [P, P, I, I, I, I, P]),
     "b2u_conv_fprop": (I, [P, I, P, I, P, P, P, I, I, I, I, I, I, I, P]),

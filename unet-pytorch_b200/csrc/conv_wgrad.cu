@@ -252,28 +252,26 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
 
 // out[co][ci][r][s] (OIHW fp32) = sum_split partial[split][co][tap][ci]; one thread per (co, ci).
 // cin_real < cin_pitch handles the first layer (im2col columns k = tap*cin_real + c, see layout.cu).
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int Cout,
-                                    int taps, int cin_pitch, int cin_real, int first_layer) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Cout * cin_real) return;
-  const int co = idx / cin_real, ci = idx % cin_real;
-  const size_t split_stride = static_cast<size_t>(Cout) * (first_layer ? 1 : taps) * cin_pitch;
-  if (!first_layer) {
-    for (int t = 0; t < taps; ++t) {
-      const float* src = partial + (static_cast<size_t>(co) * taps + t) * cin_pitch + ci;
-      float acc = 0.f;
-      for (int s = 0; s < splits; ++s) acc += src[s * split_stride];
-      dw[(static_cast<size_t>(co) * cin_real + ci) * taps + t] = acc;
-    }
-  } else {
-    // partial is [split][Cout][1][cin_pitch] with column k = tap*cin_real + ci
-    for (int t = 0; t < taps; ++t) {
-      const float* src = partial + static_cast<size_t>(co) * cin_pitch + t * cin_real + ci;
-      float acc = 0.f;
-      for (int s = 0; s < splits; ++s) acc += src[s * split_stride];
-      dw[(static_cast<size_t>(co) * cin_real + ci) * taps + t] = acc;
-    }
+// generic path (1x1 convs and the first layer's im2col columns): 256 threads = 64 outputs x 4 split lanes
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int Cout, int taps,
+                    int cin_pitch, int cin_real, int first_layer) {
+  __shared__ float sred[4][64];
+  const int o = blockIdx.x * 64 + (threadIdx.x & 63);      // output index in OIHW order: (co, ci, tap)
+  const int sl = threadIdx.x >> 6;
+  const int total = Cout * cin_real * taps;
+  float acc = 0.f;
+  if (o < total) {
+    const int t = o % taps, ci = (o / taps) % cin_real, co = o / (taps * cin_real);
+    // partial is [split][Cout][taps][cin_pitch], or for the first layer [split][Cout][cin_pitch] with k = tap*cin_real + ci
+    const size_t split_stride = static_cast<size_t>(Cout) * (first_layer ? 1 : taps) * cin_pitch;
+    const float* src = first_layer ? partial + static_cast<size_t>(co) * cin_pitch + t * cin_real + ci
+                                   : partial + (static_cast<size_t>(co) * taps + t) * cin_pitch + ci;
+    for (int s = sl; s < splits; s += 4) acc += __ldg(src + s * split_stride);
   }
+  sred[sl][threadIdx.x & 63] = acc;
+  __syncthreads();
+  if (sl == 0 && o < total) dw[o] = (sred[0][threadIdx.x] + sred[1][threadIdx.x]) + (sred[2][threadIdx.x] + sred[3][threadIdx.x]);
 }
 
 // 3x3 fast path: block = (co, 64-channel block of ci); 144 threads = 9 taps x 16 float4 columns sum the splits with
@@ -445,8 +443,8 @@ int b2u_conv_wgrad(const void* x0, int C0, const void* x1, int C1, const void* d
   if (taps == 9)
     wgrad_reduce9_kernel<<<dim3(ctot / 64, Cout), 160, 0, st>>>(static_cast<const float*>(ws), dw, pl.splits, Cout, ctot);
   else
-    wgrad_reduce_kernel<<<(total + 127) / 128, 128, 0, st>>>(static_cast<const float*>(ws), dw, pl.splits, Cout, rtaps, ctot,
-                                                             cin_real, first_cin > 0 ? 1 : 0);
+    wgrad_reduce_kernel<<<(total * rtaps + 63) / 64, 256, 0, st>>>(static_cast<const float*>(ws), dw, pl.splits, Cout, rtaps, ctot,
+                                                                   cin_real, first_cin > 0 ? 1 : 0);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(B2U_ERR_CUDA, "wgrad_reduce launch: %s", cudaGetErrorString(e));
   note_launch();

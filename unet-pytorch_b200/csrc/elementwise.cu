@@ -48,27 +48,35 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 // ---------------------------------------------------------------------------------------------
 // first-layer im2col: col[n,h,w,k] = x[n,c,h+r-1,w+s-1] for k = (r*3+s)*Cin + c < 9*Cin, else 0
 // ---------------------------------------------------------------------------------------------
-__global__ void im2col_first_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int Cin, int H,
-                                    int W) {
-  const unsigned t = blockIdx.y * blockDim.x + threadIdx.x;    // (w, chunk of 8 k)
-  if (t >= static_cast<unsigned>(W) * 8u) return;
-  const int chunk = t & 7, w = t >> 3;
-  const int n = blockIdx.x / H, h = blockIdx.x % H;
-  float f[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) f[e] = 0.f;
-  if (chunk * 8 < 9 * Cin) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int k = chunk * 8 + e;
-      if (k < 9 * Cin) {
-        const int tap = k / Cin, c = k - tap * Cin;
-        const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) f[e] = __ldg(x + ((static_cast<size_t>(n) * Cin + c) * H + hh) * W + ww);
-      }
+// Block = one 64-pixel row segment.  Phase 1: the 9*Cin <= 64 (tap, channel) planes are read with the pixel index
+// fastest across lanes (128-byte coalesced fp32 loads) into a [64 px][64 k] bf16 tile; phase 2: the tile leaves as
+// 64 x 128 contiguous bytes.
+constexpr int kI2cPix = 64;
+__global__ void __launch_bounds__(256)
+im2col_first_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int Cin, int H, int W) {
+  __shared__ __align__(16) __nv_bfloat16 tile[kI2cPix][64 + 8];     // +8: keeps 16-byte rows, staggers banks
+  const int segs = (W + kI2cPix - 1) / kI2cPix;
+  const int seg = blockIdx.x % segs;
+  const int row = blockIdx.x / segs;          // n * H + h
+  const int n = row / H, h = row - n * H;
+  const int w0 = seg * kI2cPix;
+  const int K = 9 * Cin;
+  for (int i = threadIdx.x; i < 64 * kI2cPix; i += blockDim.x) {
+    const int k = i / kI2cPix, pw = i - k * kI2cPix;
+    float v = 0.f;
+    if (k < K) {
+      const int tap = k / Cin, c = k - tap * Cin;
+      const int hh = h + tap / 3 - 1, ww = w0 + pw + tap % 3 - 1;
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(x + ((static_cast<size_t>(n) * Cin + c) * H + hh) * W + ww);
     }
+    tile[pw][k] = __float2bfloat16_rn(v);
   }
-  reinterpret_cast<uint4*>(col)[(static_cast<size_t>(blockIdx.x) * W + w) * 8 + chunk] = pack8(f);
+  __syncthreads();
+  uint4* out = reinterpret_cast<uint4*>(col) + (static_cast<size_t>(row) * W + w0) * 8;
+  for (int i = threadIdx.x; i < kI2cPix * 8; i += blockDim.x) {
+    const int pw = i >> 3, q = i & 7;
+    if (w0 + pw < W) out[i] = *reinterpret_cast<const uint4*>(&tile[pw][q * 8]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -100,6 +108,62 @@ __global__ void pack_weights_first_kernel(const float* __restrict__ w, __nv_bflo
     v = w[(static_cast<size_t>(co) * Cin + c) * 9 + tap];
   }
   wf[idx] = __float2bfloat16_rn(v);
+}
+
+// All layers in one launch: `table` (device memory, built once by the host because parameter and operand buffers
+// are persistent) lists every conv with the index of its first work block.  A block owns a [32 co] x [32 ci] x taps
+// tile: the OIHW rows are read as contiguous runs (32 ci x 9 taps floats per co), transposed through shared memory,
+// and leave as 64-byte runs in both operand layouts.
+struct PackEntry {
+  const float* w;          // OIHW fp32
+  __nv_bfloat16* wf;       // fprop operand (or first-layer [Cout][64])
+  __nv_bfloat16* wd;       // dgrad operand or null
+  long long start;         // first block index of this layer
+  int Cout, Cin, taps, first;
+};
+__global__ void __launch_bounds__(256)
+pack_weights_multi_kernel(const PackEntry* __restrict__ table, int n) {
+  __shared__ float tile[32][32 * 9 + 1];
+  int lo = 0, hi = n - 1;
+  const long long b = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].start <= b) lo = mid; else hi = mid - 1;
+  }
+  const PackEntry e = table[lo];
+  const int lb = static_cast<int>(b - e.start);
+  if (e.first) {
+    // one block per 32 output channels: wf[co][k], k = tap*Cin + c < 9*Cin, zero padded to 64 columns
+    for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) {
+      const int co = lb * 32 + i / 64, k = i % 64;
+      if (co >= e.Cout) continue;
+      float v = 0.f;
+      if (k < 9 * e.Cin) { const int tap = k / e.Cin, c = k % e.Cin; v = e.w[(static_cast<size_t>(co) * e.Cin + c) * 9 + tap]; }
+      e.wf[static_cast<size_t>(co) * 64 + k] = __float2bfloat16_rn(v);
+    }
+    return;
+  }
+  const int tiles_ci = e.Cin / 32;
+  const int co0 = (lb / tiles_ci) * 32, ci0 = (lb % tiles_ci) * 32;
+  const int run = 32 * e.taps;                       // contiguous floats per co row of the tile
+  for (int i = threadIdx.x; i < 32 * run; i += blockDim.x) {
+    const int r = i / run, j = i - r * run;
+    tile[r][j] = e.w[(static_cast<size_t>(co0 + r) * e.Cin + ci0) * e.taps + j];      // j = ci_local * taps + tap
+  }
+  __syncthreads();
+  const size_t kf = static_cast<size_t>(e.taps) * e.Cin, kd = static_cast<size_t>(e.taps) * e.Cout;
+  for (int i = threadIdx.x; i < 32 * run; i += blockDim.x) {
+    // fprop operand: (co, tap, ci) with ci fastest
+    const int ci = i & 31, t = (i >> 5) % e.taps, r = i / (32 * e.taps);
+    e.wf[(co0 + r) * kf + static_cast<size_t>(t) * e.Cin + ci0 + ci] = __float2bfloat16_rn(tile[r][ci * e.taps + t]);
+  }
+  if (e.wd) {
+    for (int i = threadIdx.x; i < 32 * run; i += blockDim.x) {
+      // dgrad operand: (ci, flipped tap, co) with co fastest
+      const int r = i & 31, t = (i >> 5) % e.taps, ci = i / (32 * e.taps);
+      e.wd[(ci0 + ci) * kd + static_cast<size_t>(e.taps - 1 - t) * e.Cout + co0 + r] = __float2bfloat16_rn(tile[r][ci * e.taps + t]);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -175,49 +239,76 @@ __device__ __forceinline__ void src_index(int o, float scale, int in_size, int& 
   i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
   lam = src - static_cast<float>(i0);
 }
+// Each thread owns one (output column, 8-channel chunk) and walks ROWS consecutive output rows: the column
+// interpolation weights are computed once, and the horizontally interpolated input rows are carried from one output
+// row to the next (consecutive output rows share one of their two source rows), so the kernel issues ~1/3 of the
+// instructions of a one-output-per-thread version and runs at the HBM write rate instead of the issue rate.
+template <int ROWS>
 __global__ void upsample2x_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int C8,
                                       float sh, float sw) {
   const int Ho = 2 * H, Wo = 2 * W;
   const unsigned t = blockIdx.y * blockDim.x + threadIdx.x;
   if (t >= static_cast<unsigned>(Wo) * C8) return;
   const int wo = t / C8, c = t - wo * C8;
-  const int n = blockIdx.x / Ho, ho = blockIdx.x - n * Ho;
-  int h0, h1, w0, w1; float lh, lw;
-  src_index(ho, sh, H, h0, h1, lh);
+  const int rows_per_img = Ho / ROWS;
+  const int n = blockIdx.x / rows_per_img, ho0 = (blockIdx.x - n * rows_per_img) * ROWS;
+  int w0, w1; float lw;
   src_index(wo, sw, W, w0, w1, lw);
-  const size_t img = static_cast<size_t>(n) * H * W;
-  float a[8], b[8], d[8], e[8], o[8];
-  unpack8(__ldg(x + (img + static_cast<size_t>(h0) * W + w0) * C8 + c), a);
-  unpack8(__ldg(x + (img + static_cast<size_t>(h0) * W + w1) * C8 + c), b);
-  unpack8(__ldg(x + (img + static_cast<size_t>(h1) * W + w0) * C8 + c), d);
-  unpack8(__ldg(x + (img + static_cast<size_t>(h1) * W + w1) * C8 + c), e);
-  const float h0l = 1.f - lh, w0l = 1.f - lw;
+  const float w0l = 1.f - lw;
+  const uint4* img = x + static_cast<size_t>(n) * H * W * C8 + c;
+  auto load_row = [&](int h, float* v) {
+    float a[8], b[8];
+    unpack8(__ldg(img + (static_cast<size_t>(h) * W + w0) * C8), a);
+    unpack8(__ldg(img + (static_cast<size_t>(h) * W + w1) * C8), b);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) o[k] = h0l * (w0l * a[k] + lw * b[k]) + lh * (w0l * d[k] + lw * e[k]);
-  y[static_cast<size_t>(blockIdx.x) * Wo * C8 + t] = pack8(o);
-}
-
-// adjoint: dlow[h,w] = sum over output pixels (ho,wo) of weight(ho->h) * weight(wo->w) * dup[ho,wo], then ReLU mask
-// For scale 2 every low-res index receives contributions from at most kUpCand consecutive output indices,
-// starting at floor((i - 1) / scale); candidates with zero weight cost one multiply, not a branch.
-constexpr int kUpCand = 6;
-__device__ __forceinline__ void adjoint_weights(int i, float scale, float inv_scale, int in_size, int out_size, int& o_lo,
-                                                float* wts) {
-  o_lo = static_cast<int>(floorf((i - 1) * inv_scale));
-  if (o_lo < 0) o_lo = 0;
+    for (int k = 0; k < 8; ++k) v[k] = w0l * a[k] + lw * b[k];
+  };
+  int cur0 = -1, cur1 = -1;
+  float v0[8], v1[8], o[8];
+  uint4* out = y + (static_cast<size_t>(n) * Ho + ho0) * Wo * C8 + t;
 #pragma unroll
-  for (int j = 0; j < kUpCand; ++j) {
-    const int o = o_lo + j;
-    int i0, i1; float lam;
-    src_index(o, scale, in_size, i0, i1, lam);
-    float wt = 0.f;
-    if (o < out_size) {
-      if (i0 == i) wt += 1.f - lam;
-      if (i1 == i) wt += lam;
+  for (int r = 0; r < ROWS; ++r) {
+    int h0, h1; float lh;
+    src_index(ho0 + r, sh, H, h0, h1, lh);
+    if (h0 != cur0) {
+      if (h0 == cur1) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v0[k] = v1[k];
+      } else {
+        load_row(h0, v0);
+      }
+      cur0 = h0;
     }
-    wts[j] = wt;
+    if (h1 != cur1) {
+      if (h1 == cur0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v1[k] = v0[k];
+      } else {
+        load_row(h1, v1);
+      }
+      cur1 = h1;
+    }
+    const float h0l = 1.f - lh;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = h0l * v0[k] + lh * v1[k];
+    out[static_cast<size_t>(r) * Wo * C8] = pack8(o);
   }
 }
+
+// Adjoint of the 2x bilinear upsample in gather form.  Output index o feeds low-res indices i0(o) and i1(o) with
+// weights (1 - lam, lam); for scale 2 a low-res index i receives from at most kUpCand consecutive outputs starting at
+// first_candidate(i) (checked exhaustively for every size up to 1024 against the forward index formula).
+constexpr int kUpCand = 5;
+__device__ __forceinline__ int first_candidate(int i, float inv_scale) {
+  if (i <= 0) return 0;
+  const int lo = static_cast<int>(floorf((i - 1) * inv_scale)) + 1;
+  return lo < 0 ? 0 : lo;
+}
+// Each thread owns one (low-res column, 8-channel chunk) and ROWS consecutive low-res rows.  It walks the output rows
+// that feed them once: per output row the kUpCand column candidates are combined with the column weights (shared by
+// all rows), then the row result is added to the two low-res rows it feeds -- so an output row is loaded once for the
+// whole group instead of once per low-res row.
+template <int ROWS>
 __global__ void upsample2x_bwd_kernel(const uint4* __restrict__ dup, const uint4* __restrict__ ylow,
                                       uint4* __restrict__ dlow, int N, int H, int W, int C8, float sh, float sw,
                                       float inv_sh, float inv_sw) {
@@ -225,36 +316,63 @@ __global__ void upsample2x_bwd_kernel(const uint4* __restrict__ dup, const uint4
   const unsigned t = blockIdx.y * blockDim.x + threadIdx.x;
   if (t >= static_cast<unsigned>(W) * C8) return;
   const int w = t / C8, c = t - w * C8;
-  const int n = blockIdx.x / H, h = blockIdx.x - n * H;
-  int ho_lo, wo_lo;
-  float wh[kUpCand], ww[kUpCand];
-  adjoint_weights(h, sh, inv_sh, H, Ho, ho_lo, wh);
-  adjoint_weights(w, sw, inv_sw, W, Wo, wo_lo, ww);
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const size_t img = static_cast<size_t>(n) * Ho * Wo;
+  const int groups = H / ROWS;
+  const int n = blockIdx.x / groups, hb = (blockIdx.x - n * groups) * ROWS;
+  // column weights
+  const int wo_lo = first_candidate(w, inv_sw);
+  float ww[kUpCand];
+  int wcol[kUpCand];
 #pragma unroll
-  for (int a = 0; a < kUpCand; ++a) {
-    if (wh[a] == 0.f) continue;                       // warp-uniform in h (one image row per block row)
-    const int ho = ho_lo + a;
-    const uint4* rowp = dup + (img + static_cast<size_t>(ho) * Wo) * C8 + c;
+  for (int b = 0; b < kUpCand; ++b) {
+    const int o = wo_lo + b;
+    int i0, i1; float lam;
+    src_index(o, sw, W, i0, i1, lam);
+    float wt = 0.f;
+    if (o < Wo) { if (i0 == w) wt += 1.f - lam; if (i1 == w) wt += lam; }
+    ww[b] = wt;
+    wcol[b] = o < Wo ? o : Wo - 1;
+  }
+  float acc[ROWS][8];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[r][k] = 0.f;
+  const int ho_begin = first_candidate(hb, inv_sh);
+  int ho_end = first_candidate(hb + ROWS - 1, inv_sh) + kUpCand;
+  if (ho_end > Ho) ho_end = Ho;
+  const uint4* img = dup + static_cast<size_t>(n) * Ho * Wo * C8 + c;
+  for (int ho = ho_begin; ho < ho_end; ++ho) {
+    int h0, h1; float lh;
+    src_index(ho, sh, H, h0, h1, lh);
+    const uint4* rowp = img + static_cast<size_t>(ho) * Wo * C8;
+    float trow[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int b = 0; b < kUpCand; ++b) {
-      const int wo = min(wo_lo + b, Wo - 1);
       float g[8];
-      unpack8(__ldg(rowp + static_cast<size_t>(wo) * C8), g);
-      const float wt = wh[a] * ww[b];
+      unpack8(__ldg(rowp + static_cast<size_t>(wcol[b]) * C8), g);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] = fmaf(wt, g[k], acc[k]);
+      for (int k = 0; k < 8; ++k) trow[k] = fmaf(ww[b], g[k], trow[k]);
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      float wt = 0.f;
+      if (h0 == hb + r) wt += 1.f - lh;
+      if (h1 == hb + r) wt += lh;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[r][k] = fmaf(wt, trow[k], acc[r][k]);
     }
   }
-  const size_t idx = static_cast<size_t>(blockIdx.x) * W * C8 + t;
-  if (ylow) {
-    float m[8];
-    unpack8(__ldg(ylow + idx), m);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) if (!(m[k] > 0.f)) acc[k] = 0.f;
+  for (int r = 0; r < ROWS; ++r) {
+    const size_t idx = (static_cast<size_t>(n) * H + hb + r) * W * C8 + t;
+    if (ylow) {
+      float m[8];
+      unpack8(__ldg(ylow + idx), m);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) if (!(m[k] > 0.f)) acc[r][k] = 0.f;
+    }
+    dlow[idx] = pack8(acc[r]);
   }
-  dlow[idx] = pack8(acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -291,12 +409,23 @@ __global__ void bias_grad_partial_kernel(const uint4* __restrict__ dz, float* __
     __syncthreads();
   }
 }
-__global__ void reduce_rows_kernel(const float* __restrict__ partial, float* __restrict__ out, int rows, int L) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= L) return;
+// out[i] = sum_r partial[r][i]: 256 threads = 32 columns x 8 row lanes, fixed summation order (deterministic)
+__global__ void __launch_bounds__(256)
+reduce_rows_kernel(const float* __restrict__ partial, float* __restrict__ out, int rows, int L) {
+  __shared__ float sred[8][33];
+  const int col = threadIdx.x & 31, lane_r = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + col;
   float acc = 0.f;
-  for (int r = 0; r < rows; ++r) acc += partial[static_cast<size_t>(r) * L + i];
-  out[i] = acc;
+  if (i < L)
+    for (int r = lane_r; r < rows; r += 8) acc += __ldg(partial + static_cast<size_t>(r) * L + i);
+  sred[lane_r][col] = acc;
+  __syncthreads();
+  if (lane_r == 0 && i < L) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sred[k][col];
+    out[i] = t;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -343,7 +472,7 @@ using namespace b2u;
 
 int b2u_im2col_first(const float* x, void* col, int N, int Cin, int H, int W, void* stream) {
   if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || 9 * Cin > 64) return set_error(B2U_ERR_SHAPE, "im2col_first: bad shape (Cin=%d)", Cin);
-  im2col_first_kernel<<<row_grid(static_cast<long long>(N) * H, W * 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  im2col_first_kernel<<<static_cast<unsigned>(static_cast<long long>(N) * H * ((W + kI2cPix - 1) / kI2cPix)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, static_cast<__nv_bfloat16*>(col), N, Cin, H, W);
   B2U_CHECK_LAUNCH("im2col_first");
   return 0;
@@ -355,6 +484,18 @@ int b2u_pack_weights(const float* w, void* wf, void* wd, int Cout, int Cin, int 
   pack_weights_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w, static_cast<__nv_bfloat16*>(wf), static_cast<__nv_bfloat16*>(wd), Cout, Cin, taps);
   B2U_CHECK_LAUNCH("pack_weights");
+  return 0;
+}
+
+// table: n entries of {const float* w; bf16* wf; bf16* wd; int64 start; int32 Cout, Cin, taps, first} (48 bytes each) in
+// DEVICE memory; start = index of the layer's first work block, a layer has (Cout/32)*(Cin/32) blocks (first layer:
+// ceil(Cout/32)); total_blocks = their sum.  Cout, Cin must be multiples of 32 (except the first layer's Cin).
+int b2u_pack_weights_multi(const void* table, int n, long long total_blocks, void* stream) {
+  static_assert(sizeof(b2u::PackEntry) == 48, "PackEntry layout is part of the ABI");
+  if (n <= 0 || total_blocks <= 0 || total_blocks > 0x7fffffffLL) return set_error(B2U_ERR_ARG, "pack_weights_multi: bad table");
+  pack_weights_multi_kernel<<<static_cast<unsigned>(total_blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const b2u::PackEntry*>(table), n);
+  B2U_CHECK_LAUNCH("pack_weights_multi");
   return 0;
 }
 
@@ -392,8 +533,12 @@ int b2u_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, void*
   if (N <= 0 || H <= 0 || W <= 0 || C % 8 != 0) return set_error(B2U_ERR_SHAPE, "upsample2x_fwd: bad shape");
   const float sh = (2 * H > 1) ? static_cast<float>(H - 1) / static_cast<float>(2 * H - 1) : 0.f;
   const float sw = (2 * W > 1) ? static_cast<float>(W - 1) / static_cast<float>(2 * W - 1) : 0.f;
-  upsample2x_fwd_kernel<<<row_grid(static_cast<long long>(N) * 2 * H, 2 * W * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(x), static_cast<uint4*>(y), N, H, W, C / 8, sh, sw);
+  if (H % 2 == 0)
+    upsample2x_fwd_kernel<4><<<row_grid(static_cast<long long>(N) * (2 * H / 4), 2 * W * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(x), static_cast<uint4*>(y), N, H, W, C / 8, sh, sw);
+  else
+    upsample2x_fwd_kernel<2><<<row_grid(static_cast<long long>(N) * H, 2 * W * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(x), static_cast<uint4*>(y), N, H, W, C / 8, sh, sw);
   B2U_CHECK_LAUNCH("upsample2x_fwd");
   return 0;
 }
@@ -405,24 +550,29 @@ int b2u_upsample2x_bwd(const void* dup, const void* ylow, void* dlow, int N, int
   const float sw = static_cast<float>(W - 1) / static_cast<float>(2 * W - 1);
   const float ish = H > 1 ? 1.f / sh : 4.f * H;   // H == 1: every output maps to row 0
   const float isw = W > 1 ? 1.f / sw : 4.f * W;
-  upsample2x_bwd_kernel<<<row_grid(static_cast<long long>(N) * H, W * (C / 8), 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(dup), static_cast<const uint4*>(ylow), static_cast<uint4*>(dlow), N, H, W, C / 8, sh, sw,
-      ish, isw);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint4 *pd = static_cast<const uint4*>(dup), *py = static_cast<const uint4*>(ylow);
+  uint4* po = static_cast<uint4*>(dlow);
+  if (H % 4 == 0)
+    upsample2x_bwd_kernel<4><<<row_grid(static_cast<long long>(N) * (H / 4), W * (C / 8), 128), 128, 0, st>>>(pd, py, po, N, H, W, C / 8, sh, sw, ish, isw);
+  else if (H % 2 == 0)
+    upsample2x_bwd_kernel<2><<<row_grid(static_cast<long long>(N) * (H / 2), W * (C / 8), 128), 128, 0, st>>>(pd, py, po, N, H, W, C / 8, sh, sw, ish, isw);
+  else
+    upsample2x_bwd_kernel<1><<<row_grid(static_cast<long long>(N) * H, W * (C / 8), 128), 128, 0, st>>>(pd, py, po, N, H, W, C / 8, sh, sw, ish, isw);
   B2U_CHECK_LAUNCH("upsample2x_bwd");
   return 0;
 }
 
-size_t b2u_bias_grad_workspace(int C) { return static_cast<size_t>(2 * 148) * C * sizeof(float); }
+size_t b2u_bias_grad_workspace(int C) { return static_cast<size_t>(2 * 148) * C * sizeof(float) + 256; }
 
 int b2u_bias_grad(const void* dz, float* db, void* ws, size_t ws_bytes, long long P, int C, void* stream) {
   if (P <= 0 || C <= 0 || C % 8 != 0) return set_error(B2U_ERR_SHAPE, "bias_grad: bad shape");
   const int blocks = 2 * 148;
-  if (!ws || ws_bytes < static_cast<size_t>(blocks) * C * sizeof(float)) return set_error(B2U_ERR_ARG, "bias_grad: workspace too small");
+  if (!ws || ws_bytes < b2u_bias_grad_workspace(C)) return set_error(B2U_ERR_ARG, "bias_grad: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  bias_grad_partial_kernel<<<blocks, 256, 256 * 8 * sizeof(float), st>>>(static_cast<const uint4*>(dz),
-                                                                         static_cast<float*>(ws), P, C / 8);
+  bias_grad_partial_kernel<<<blocks, 256, 256 * 8 * sizeof(float), st>>>(static_cast<const uint4*>(dz), static_cast<float*>(ws), P, C / 8);
   B2U_CHECK_LAUNCH("bias_grad_partial");
-  reduce_rows_kernel<<<grid_for(C, 128), 128, 0, st>>>(static_cast<const float*>(ws), db, blocks, C);
+  reduce_rows_kernel<<<(C + 31) / 32, 256, 0, st>>>(static_cast<const float*>(ws), db, blocks, C);
   B2U_CHECK_LAUNCH("reduce_rows");
   return 0;
 }

@@ -83,6 +83,8 @@ class VGGUnetEngine:
         # more than the separate HBM-bound column-sum kernel (work units with the extra MMAs become the stragglers of
         # the static schedule: +40 % wgrad time vs +1.2 ms for bias_grad), so it is off by default.
         self.fuse_bias_grad = False
+        self._pack_key = self._pack_versions = self._pack_table = None
+        self._pack_total = 0
         self._bufs = {}
         self._shape = None
         self.saved = None
@@ -110,19 +112,42 @@ class VGGUnetEngine:
 
     # ------------------------------------------------------------------ weights
     def pack(self, params, need_dgrad=True):
-        """(Re)packs fp32 OIHW weights to bf16 operands when their version counter changed."""
-        for c in self.convs:
-            w = params[c.name + ".weight"]
-            ver = (w.data_ptr(), w._version)
-            if c.version == ver and (c.wd is not None or not need_dgrad or c.first):
-                continue
-            if c.first:
-                c.wf = ops.pack_weights_first(w, wf=c.wf)
-            else:
-                c.wf, wd = ops.pack_weights(w, want_dgrad=need_dgrad, wf=c.wf, wd=c.wd)
-                if need_dgrad:
-                    c.wd = wd
-            c.version = ver
+        """(Re)packs fp32 OIHW weights to bf16 operands when any of them changed: one launch for the whole model,
+        driven by a device-resident table of (weight, operand) pointers that is rebuilt only if a pointer moved."""
+        key = tuple(params[c.name + ".weight"].data_ptr() for c in self.convs) + (need_dgrad,)
+        versions = tuple(params[c.name + ".weight"]._version for c in self.convs)
+        if self._pack_key == key and self._pack_versions == versions and self._pack_versions is not None:
+            return
+        dev = params[self.convs[0].name + ".weight"].device
+        if self._pack_key != key:
+            import struct
+            blob, start = b"", 0
+            for c in self.convs:
+                w = params[c.name + ".weight"]
+                if c.first:
+                    if c.wf is None:
+                        c.wf = torch.empty((c.cout, 64), dtype=torch.bfloat16, device=dev)
+                    count = (c.cout + 31) // 32                      # work blocks of this layer
+                else:
+                    if c.wf is None:
+                        c.wf = torch.empty((c.cout, 9 * c.cin), dtype=torch.bfloat16, device=dev)
+                    if need_dgrad and c.wd is None:
+                        c.wd = torch.empty((c.cin, 9 * c.cout), dtype=torch.bfloat16, device=dev)
+                    count = (c.cout // 32) * (c.cin // 32)
+                wd_ptr = c.wd.data_ptr() if (need_dgrad and not c.first) else 0
+                blob += struct.pack("<QQQqiiii", w.data_ptr(), c.wf.data_ptr(), wd_ptr, start, c.cout, c.cin,
+                                    1 if c.first else 9, 1 if c.first else 0)
+                start += count
+            self._pack_table = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+            self._pack_total = start
+            self._pack_key = key
+        ops.check(ops.lib().b2u_pack_weights_multi(self._pack_table.data_ptr(), len(self.convs), self._pack_total,
+                                                   ops.stream_ptr()))
+        self._pack_versions = versions
+
+    def invalidate_packed_weights(self):
+        """Call after writing parameters behind torch's back (raw-pointer optimizer kernels)."""
+        self._pack_versions = None
 
     # ------------------------------------------------------------------ forward
     def forward(self, x, params, save=True):

@@ -160,6 +160,8 @@ class UnetTrainer:
                                     dtype=torch.float32, device=self.device)
         self._copy_stream = torch.cuda.Stream(device=self.device)
         self._staged = None
+        self._slots = [None, None]
+        self._stage_count = 0
         self.last = None
         if state_dict is not None:
             self.load_state_dict(state_dict)
@@ -183,29 +185,45 @@ class UnetTrainer:
 
     # ------------------------------------------------------------------ input staging
     def stage(self, imgs, pngs):
-        """Asynchronous host->device copy of the next batch on a copy stream (pinned host tensors)."""
+        """Asynchronous host->device copy of the next batch (pinned host tensors) on a copy stream into one of two
+        persistent device slots, so the copy overlaps the current step's kernels and no allocation happens per step.
+        A slot is overwritten only after the step that read it has consumed it (event recorded after its last read)."""
+        slot = self._stage_count % 2
+        self._stage_count += 1
+        bufs = self._slots[slot]
+        if bufs is None or bufs[0].shape != imgs.shape or bufs[1].shape != pngs.shape or bufs[1].dtype != pngs.dtype:
+            bufs = [torch.empty(imgs.shape, dtype=torch.float32, device=self.device),
+                    torch.empty(pngs.shape, dtype=pngs.dtype, device=self.device), None]
+            self._slots[slot] = bufs
         with torch.cuda.stream(self._copy_stream):
-            di = imgs.to(self.device, non_blocking=True)
-            dp = pngs.to(self.device, non_blocking=True)
+            if bufs[2] is not None:
+                self._copy_stream.wait_event(bufs[2])          # previous reader of this slot is done
+            bufs[0].copy_(imgs, non_blocking=True)
+            bufs[1].copy_(pngs, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
-        self._staged = (di, dp, ev)
+        self._staged = (slot, ev)
 
     def _take(self, imgs, pngs):
+        """Returns (imgs, pngs, slot): device tensors for this step; slot is None for caller-owned tensors."""
         if imgs is None:
             if self._staged is None:
                 raise RuntimeError("train_step(None, None) needs a batch staged with stage()")
-            di, dp, ev = self._staged
+            slot, ev = self._staged
             self._staged = None
             torch.cuda.current_stream().wait_event(ev)
-            di.record_stream(torch.cuda.current_stream())
-            dp.record_stream(torch.cuda.current_stream())
-            return di, dp
+            return self._slots[slot][0], self._slots[slot][1], slot
         if not imgs.is_cuda:
             imgs = imgs.to(self.device, non_blocking=True)
         if not pngs.is_cuda:
             pngs = pngs.to(self.device, non_blocking=True)
-        return imgs, pngs
+        return imgs, pngs, None
+
+    def _consumed(self, slot):
+        if slot is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self._slots[slot][2] = ev
 
     # ------------------------------------------------------------------ the step
     def forward_loss(self, imgs, pngs, save=True):
@@ -218,11 +236,12 @@ class UnetTrainer:
     def train_step(self, imgs=None, pngs=None):
         """Returns a device tensor [total loss, f_score]; `.item()`/`.tolist()` on it is the per-iteration sync of
         utils_fit.py:96-97."""
-        imgs, pngs = self._take(imgs, pngs)
+        imgs, pngs, slot = self._take(imgs, pngs)
         logits, pngs, fin = self.forward_loss(imgs, pngs, save=True)
         n, _, h, w = logits.shape
         dlogits = ops.loss_bwd(logits, fin, self._gscale, target=pngs, onehot=None, cls_w=self.cls_w, nhwc64=True,
                                out=self.engine._buf("g:logits64", (n, h, w, 64)))
+        self._consumed(slot)            # image and label map are not read after this point
         active = [n for n in self.layout.order if n in self.trainable]
         self.sync.reset(active)
         grads = {n: self.grads[n] for n in active}
@@ -255,12 +274,12 @@ class UnetTrainer:
             ops.sgd_step(self.flat_param, self.flat_grad, self.m, self.lr, self.momentum, self.weight_decay, True,
                          self.step_count == 1, grad_scale)
         # the flat update wrote every parameter behind torch's back: invalidate the engine's packed-weight cache
-        for c in self.engine.convs:
-            c.version = None
+        self.engine.invalidate_packed_weights()
 
     @torch.no_grad()
     def eval_step(self, imgs, pngs):
         """Validation iteration (utils_fit.py:111-151): forward + losses + f_score, no gradient."""
-        imgs, pngs = self._take(imgs, pngs)
+        imgs, pngs, slot = self._take(imgs, pngs)
         _, _, fin = self.forward_loss(imgs, pngs, save=False)
+        self._consumed(slot)
         return torch.stack([self._total(fin), fin[3]])
