@@ -44,8 +44,9 @@ int b2u_im2col_first(const float* x_nchw, void* col, int N, int Cin, int H, int 
 int b2u_pack_weights(const float* w_oihw, void* wf, void* wd, int Cout, int Cin, int taps, void* stream);
 int b2u_pack_weights_first(const float* w_oihw, void* wf, int Cout, int Cin, void* stream);
 /* every conv of the model in one launch; table (DEVICE memory): n x {const float* w; void* wf; void* wd; long long start;
- * int Cout, Cin, taps, first} (48 B each), start = prefix sum of element counts (Cout*Cin*taps; first layer Cout*64) */
-int b2u_pack_weights_multi(const void* table, int n, long long total, void* stream);
+ * int Cout, Cin, taps, first, C0, C0_pad, Ctot_pad, Cout_pad} (64 B each); start = first work block of the layer,
+ * (Cout/32)*(Cin/32) blocks per layer (first layer: ceil(Cout/32)); operands may be channel-padded to multiples of 64 */
+int b2u_pack_weights_multi(const void* table, int n, long long total_blocks, void* stream);
 int b2u_nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, int H, int W, void* stream);
 int b2u_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int W, void* stream);
 
@@ -81,6 +82,21 @@ int b2u_maxpool2x2_bwd(const void* dpool, const void* dskip, const void* y, void
 int b2u_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream);
 /* adjoint; ylow (nullable) = the ReLU output that was upsampled: dlow = 0 where ylow <= 0 */
 int b2u_upsample2x_bwd(const void* dup, const void* ylow, void* dlow, int N, int H, int W, int C, void* stream);
+
+/* ---- batch normalisation (nn.BatchNorm2d [+ nn.ReLU], nets/TraditionalUnet.py:9-14, nets/resnet.py:65-71) ---------- */
+/* z, y, dy, dz: NHWC bf16 with C channels (C % 8 == 0), P = N*H*W pixels; gamma/beta/running/save: fp32 [C].
+ * train: batch statistics (biased variance), running stats updated with `momentum` (unbiased variance), torch semantics. */
+size_t b2u_bn_workspace(int C);
+int b2u_bn_fwd_train(const void* z, void* y, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float* save_mean, float* save_invstd, void* ws, size_t ws_bytes, long long P,
+                     int C, float eps, float momentum, int relu, void* stream);
+int b2u_bn_fwd_eval(const void* z, void* y, const float* gamma, const float* beta, const float* running_mean,
+                    const float* running_var, void* ws, size_t ws_bytes, long long P, int C, float eps, int relu,
+                    void* stream);
+/* dy = gradient wrt y = [relu](bn(z)); dz (may alias dy) = gradient wrt z; dgamma/dbeta nullable */
+int b2u_bn_bwd(const void* dy, const void* y, const void* z, const float* gamma, const float* save_mean,
+               const float* save_invstd, void* dz, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, long long P,
+               int C, int relu, void* stream);
 
 /* ---- classifier head (nn.Conv2d(64, num_classes, 1), nets/unet.py:58,76) ------------------------------------ */
 int b2u_head_fwd(const void* x, const float* w, const float* b, float* logits_nchw, int N, int H, int W, int Cin,

@@ -17,6 +17,7 @@ for name in ("matplotlib", "matplotlib.pyplot"):
     sys.modules.setdefault(name, types.ModuleType(name))
 
 from nets.unet import Unet as RefUnet                                   # noqa: E402
+from nets.TraditionalUnet import TraditionalUnet as RefTraditional      # noqa: E402
 from nets.unet_training import CE_Loss, Dice_loss, Focal_Loss           # noqa: E402
 from utils.utils_metrics import f_score, fast_hist, per_class_iu, per_class_PA_Recall, per_class_Precision  # noqa: E402
 
@@ -60,6 +61,34 @@ def model_case(tag, num_classes, n, h, w, seed, medical, cls_w, dice, focal):
             rec["g:" + name] = flat[idx].numpy().astype(np.float32)
     np.savez_compressed(os.path.join(OUT, f"unet_vgg_{tag}.npz"), **rec)
     print(tag, "loss", loss.item(), "f_score", fs, "logits", out.shape)
+
+
+def traditional_case(tag, num_classes, n, h, w, seed, cls_w, dice, focal):
+    sd = O.make_trad_params(num_classes, seed=11)
+    model = RefTraditional(in_channels=3, num_classes=num_classes)
+    model.load_state_dict(sd)
+    model.train()
+    imgs, pngs = O.make_inputs(n, num_classes, h, w, seed=seed)
+    labels = torch.eye(num_classes + 1)[pngs]
+    weights = torch.tensor(cls_w, dtype=torch.float32)
+    out = model(imgs)
+    loss = Focal_Loss(out, pngs, weights, num_classes=num_classes) if focal else CE_Loss(out, pngs, weights, num_classes=num_classes)
+    if dice:
+        loss = loss + Dice_loss(out, labels)
+    loss.backward()
+    rec = {"logits": out.detach().numpy().astype(np.float32), "loss": np.float64(loss.item()),
+           "cls_w": np.asarray(cls_w, np.float32), "meta": np.asarray([num_classes, n, h, w, seed, int(dice), int(focal)])}
+    for name, p in model.named_parameters():
+        g = p.grad.detach().reshape(-1)
+        rec["gnorm:" + name] = np.float64(g.double().norm().item())
+        rec["g:" + name] = (g if g.numel() <= 4096 else g[torch.linspace(0, g.numel() - 1, 4096).long()]).numpy().astype(np.float32)
+    for name, b in model.named_buffers():
+        rec["buf:" + name] = b.detach().numpy()
+    model.eval()
+    with torch.no_grad():
+        rec["logits_eval"] = model(imgs).numpy().astype(np.float32)       # eval mode: running statistics after one step
+    np.savez_compressed(os.path.join(OUT, f"traditional_{tag}.npz"), **rec)
+    print("traditional", tag, "loss", loss.item())
 
 
 def loss_case():
@@ -115,5 +144,8 @@ if __name__ == "__main__":
     model_case("nc21_cedice", 21, 2, 64, 96, 1, False, [1] * 21, dice=True, focal=False)
     # TraditionalUnet_Train-style loss settings: focal + dice, weights [1,15,1.5,2]
     model_case("nc4_focaldice", 4, 1, 32, 32, 2, False, [1, 15, 1.5, 2], dice=True, focal=True)
+    # TraditionalUnet_Train.py settings: focal loss, class weights [1,15,...] (lines 236, 245); and plain CE + Dice
+    traditional_case("nc4_focaldice", 4, 2, 64, 64, 3, [1, 15, 1.5, 2], dice=True, focal=True)
+    traditional_case("nc21_cedice", 21, 2, 32, 64, 4, [1] * 21, dice=True, focal=False)
     loss_case()
     hist_case()

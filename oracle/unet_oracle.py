@@ -282,3 +282,102 @@ def train_step_bf16_storage(params, imgs, pngs, cls_weights, num_classes, dice=T
         loss = loss + dice_loss(logits, one_hot(pngs, num_classes))
     grads = torch.autograd.grad(loss, list(p.values()))
     return loss.detach(), logits.detach(), dict(zip(p.keys(), grads))
+
+
+# ----------------------------------------------------------------------------------------------- TraditionalUnet
+# nets/TraditionalUnet.py:45-66: DoubleConv prefixes in execution order, with (Cin, Cout)
+TRAD_ENC = [("inc", None, 32), ("down1.maxpool_conv.1", 32, 64), ("down2.maxpool_conv.1", 64, 128),
+            ("down3.maxpool_conv.1", 128, 256)]
+TRAD_DEC = [("up1.conv", 384, 128), ("up2.conv", 192, 64), ("up3.conv", 96, 32)]
+
+
+def trad_param_shapes(num_classes, in_channels=3):
+    """Parameters (not buffers) of TraditionalUnet in state_dict order."""
+    shapes = {}
+    for prefix, cin, cout in TRAD_ENC + TRAD_DEC:
+        cin = in_channels if cin is None else cin
+        for idx, ci in ((0, cin), (3, cout)):
+            shapes[f"{prefix}.double_conv.{idx}.weight"] = (cout, ci, 3, 3)
+            shapes[f"{prefix}.double_conv.{idx}.bias"] = (cout,)
+            shapes[f"{prefix}.double_conv.{idx + 1}.weight"] = (cout,)
+            shapes[f"{prefix}.double_conv.{idx + 1}.bias"] = (cout,)
+    shapes["outc.weight"] = (num_classes, 32, 1, 1)
+    shapes["outc.bias"] = (num_classes,)
+    return shapes
+
+
+def make_trad_params(num_classes, seed=11, in_channels=3, gain=1.0):
+    """Deterministic synthetic state_dict of TraditionalUnet: convs He-scaled (BatchNorm re-normalises, so the harsh
+    full-He scale is harmless here), BN weight 1 + 0.1 N(0,1), BN bias 0.05 N(0,1), fresh running statistics."""
+    sd = {}
+    for k, (name, shape) in enumerate(trad_param_shapes(num_classes, in_channels).items()):
+        g = torch.Generator().manual_seed(seed * 1000 + 500 + k)
+        if len(shape) == 4:
+            fan_in = shape[1] * shape[2] * shape[3]
+            sd[name] = torch.randn(shape, generator=g) * (gain * (2.0 / fan_in) ** 0.5)
+        elif ".double_conv.1." in name or ".double_conv.4." in name:
+            r = torch.randn(shape, generator=g)
+            sd[name] = 1.0 + 0.1 * r if name.endswith("weight") else 0.05 * r
+        else:
+            sd[name] = torch.randn(shape, generator=g) * 0.05
+    for prefix, _, cout in TRAD_ENC + TRAD_DEC:
+        for idx in (1, 4):
+            sd[f"{prefix}.double_conv.{idx}.running_mean"] = torch.zeros(cout)
+            sd[f"{prefix}.double_conv.{idx}.running_var"] = torch.ones(cout)
+            sd[f"{prefix}.double_conv.{idx}.num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+    return sd
+
+
+def _double_conv(sd, prefix, x, training, stats, bf16):
+    """DoubleConv.forward (nets/TraditionalUnet.py:5-18); BatchNorm2d with torch defaults (eps 1e-5, momentum 0.1)."""
+    for idx in (0, 3):
+        w, b = sd[f"{prefix}.double_conv.{idx}.weight"], sd[f"{prefix}.double_conv.{idx}.bias"]
+        bn = f"{prefix}.double_conv.{idx + 1}"
+        if bf16:
+            w = w + (w.to(torch.bfloat16).to(w.dtype) - w).detach()
+            x = _r(x, fwd=False)
+        z = F.conv2d(x, w, b, padding=1)
+        if bf16:
+            z = _r(z)
+        rm, rv = stats[bn + ".running_mean"], stats[bn + ".running_var"]
+        y = F.batch_norm(z, rm, rv, sd[bn + ".weight"], sd[bn + ".bias"], training, 0.1, 1e-5)
+        if training:
+            stats[bn + ".num_batches_tracked"] = stats[bn + ".num_batches_tracked"] + 1
+        x = F.relu(y)
+        if bf16:
+            x = _r(x)
+    return x
+
+
+def trad_forward(sd, x, training=True, stats=None, bf16_storage=False):
+    """TraditionalUnet.forward (nets/TraditionalUnet.py:79-93).  stats: dict of BN buffers, updated in place when
+    training (defaults to clones of the buffers in sd)."""
+    if stats is None:
+        stats = {k: v.clone() for k, v in sd.items() if "running_" in k or "num_batches" in k}
+    if bf16_storage:
+        x = _r(x)
+    feats = []
+    for i, (prefix, _, _) in enumerate(TRAD_ENC):
+        if i > 0:
+            x = F.max_pool2d(x, 2)                                               # Down, :24-27
+        x = _double_conv(sd, prefix, x, training, stats, bf16_storage)
+        feats.append(x)
+    for i, (prefix, _, _) in enumerate(TRAD_DEC):
+        up = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)   # Up.up, :36
+        if bf16_storage:
+            up = _r(up)
+        x = _double_conv(sd, prefix, torch.cat([feats[2 - i], up], 1), training, stats, bf16_storage)   # :40-42
+    return F.conv2d(x, sd["outc.weight"], sd["outc.bias"]), stats                # :66, :92
+
+
+def trad_train_step(sd, imgs, pngs, cls_weights, num_classes, dice=True, focal=False, bf16_storage=False):
+    """One iteration of the TraditionalUnet_Train.py loop without the optimizer: returns (loss, logits, grads, stats)."""
+    p = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and "running_" not in k else v.clone())
+         for k, v in sd.items()}
+    logits, stats = trad_forward(p, imgs, training=True, bf16_storage=bf16_storage)
+    loss = focal_loss(logits, pngs, cls_weights, num_classes) if focal else ce_loss(logits, pngs, cls_weights, num_classes)
+    if dice:
+        loss = loss + dice_loss(logits, one_hot(pngs, num_classes))
+    names = [k for k, v in p.items() if v.requires_grad]
+    grads = torch.autograd.grad(loss, [p[k] for k in names])
+    return loss.detach(), logits.detach(), dict(zip(names, grads)), stats

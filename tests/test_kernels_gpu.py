@@ -245,3 +245,37 @@ def test_optimizer_steps_match_torch(b2u, cuda_device):
             else:
                 ops.sgd_step(p, gr.to(dev), m, 1e-2, momentum=0.9, nesterov=True, first_step=(step == 1))
         assert rel(p, p_ref.detach()) <= 1e-6
+
+
+@pytest.mark.parametrize("N,H,W,C,relu", [(2, 16, 24, 64, True), (1, 8, 8, 256, True), (3, 5, 7, 8, False), (2, 32, 32, 128, True)])
+def test_batchnorm_kernels(b2u, cuda_device, N, H, W, C, relu):
+    """nn.BatchNorm2d (+ReLU) train forward (batch statistics, running-stat update), eval forward and backward against
+    torch on the same bf16-rounded pre-activations."""
+    ops, dev = b2u.ops, cuda_device
+    g = torch.Generator().manual_seed(8)
+    z = torch.randn(N, C, H, W, generator=g) * 1.5 + torch.randn(1, C, 1, 1, generator=g)
+    zb = nhwc(z, dev); zr = nchw(zb).requires_grad_(True)
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).requires_grad_(True)
+    beta = (0.1 * torch.randn(C, generator=g)).requires_grad_(True)
+    rm0, rv0 = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+    rm_ref, rv_ref = rm0.clone(), rv0.clone()
+    ref = F.batch_norm(zr, rm_ref, rv_ref, gamma, beta, True, 0.1, 1e-5)
+    ref_y = ref.relu() if relu else ref
+    rm, rv = rm0.clone().to(dev), rv0.clone().to(dev)
+    y, mean, invstd = ops.bn_fwd_train(zb, gamma.detach().to(dev), beta.detach().to(dev), rm, rv, relu=relu)
+    assert rel(nchw(y), ref_y.detach()) <= 6e-3
+    assert torch.allclose(rm.cpu(), rm_ref, rtol=1e-5, atol=1e-6) and torch.allclose(rv.cpu(), rv_ref, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(mean.cpu(), zr.detach().mean((0, 2, 3)), rtol=1e-5, atol=1e-6)
+    # backward
+    dy = torch.randn(N, C, H, W, generator=g)
+    dyb = nhwc(dy, dev)
+    ref_y.backward(nchw(dyb))
+    dz, dgam, dbet = ops.bn_bwd(dyb, y, zb, gamma.detach().to(dev), mean, invstd, relu=relu)
+    # the kernel masks with its own bf16 y (> 0); where torch's fp32 y differs in sign the elements are ~0 anyway
+    assert rel(nchw(dz), zr.grad) <= 1e-2
+    assert rel(dgam, gamma.grad) <= 2e-3 and rel(dbet, beta.grad) <= 2e-3
+    # eval mode
+    ye = ops.bn_fwd_eval(zb, gamma.detach().to(dev), beta.detach().to(dev), rm, rv, relu=relu)
+    ref_e = F.batch_norm(zr.detach(), rm_ref, rv_ref, gamma.detach(), beta.detach(), False, 0.1, 1e-5)
+    ref_e = ref_e.relu() if relu else ref_e
+    assert rel(nchw(ye), ref_e) <= 6e-3

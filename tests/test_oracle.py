@@ -96,3 +96,36 @@ def test_fast_hist_edge_cases(golden_dir):
     assert np.array_equal(O.fast_hist(np.zeros(0, np.uint8), np.zeros(0, np.uint8), 4), g["empty:hist"])
     with pytest.raises(ValueError):       # b >= n pushes a bin past n*n: numpy's reshape raises, like the reference
         O.fast_hist(np.array([1], np.uint8), np.array([200], np.uint8), 2)
+
+
+@pytest.mark.parametrize("tag", ["nc4_focaldice", "nc21_cedice"])
+def test_traditional_unet_matches_reference_golden(tag, golden_dir):
+    """TraditionalUnet (conv + BatchNorm + ReLU) restatement against the reference's own module, train and eval mode."""
+    g = np.load(os.path.join(golden_dir, f"traditional_{tag}.npz"))
+    C, n, h, w, seed, dice, focal = [int(v) for v in g["meta"]]
+    sd = O.make_trad_params(C, seed=11)
+    imgs, pngs = O.make_inputs(n, C, h, w, seed=seed)
+    loss, logits, grads, stats = O.trad_train_step(sd, imgs, pngs, torch.from_numpy(g["cls_w"]), C, dice=bool(dice), focal=bool(focal))
+    ref = torch.from_numpy(g["logits"])
+    assert ((logits - ref).norm() / ref.norm()).item() <= 1e-5
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    for name, gr in grads.items():
+        gn = float(g["gnorm:" + name])
+        if name.endswith(".double_conv.0.bias") or name.endswith(".double_conv.3.bias"):
+            # a conv bias in front of a train-mode BatchNorm has an exactly-zero gradient in exact arithmetic: both
+            # sides only hold rounding noise
+            assert gr.norm().item() <= 1e-5 and gn <= 1e-5, name
+            continue
+        assert abs(gr.double().norm().item() - gn) <= 2e-4 * gn + 1e-12, name
+        s = _sample(gr.reshape(-1))
+        ref_s = torch.from_numpy(g["g:" + name])
+        assert (s - ref_s).norm().item() <= 3e-4 * ref_s.norm().item() + 2e-6, name
+    for name, b in stats.items():                       # running_mean / running_var / num_batches_tracked after one step
+        want = torch.from_numpy(np.asarray(g["buf:" + name]))
+        assert torch.allclose(b.double(), want.double(), rtol=1e-5, atol=1e-6), name
+    sd_after = dict(sd)
+    sd_after.update(stats)
+    with torch.no_grad():
+        ev, _ = O.trad_forward(sd_after, imgs, training=False)
+    ref_ev = torch.from_numpy(g["logits_eval"])
+    assert ((ev - ref_ev).norm() / ref_ev.norm()).item() <= 1e-5

@@ -31,6 +31,10 @@ SIGNATURES = {
     "b2u_maxpool2x2_bwd": (I, [P, P, P, P, I, I, I, I, I, P]),
     "b2u_upsample2x_fwd": (I, [P, P, I, I, I, I, P]),
     "b2u_upsample2x_bwd": (I, [P, P, P, I, I, I, I, P]),
+    "b2u_bn_workspace": (SZ, [I]),
+    "b2u_bn_fwd_train": (I, [P, P, P, P, P, P, P, P, P, SZ, LL, I, F, F, I, P]),
+    "b2u_bn_fwd_eval": (I, [P, P, P, P, P, P, P, SZ, LL, I, F, I, P]),
+    "b2u_bn_bwd": (I, [P, P, P, P, P, P, P, P, P, P, SZ, LL, I, I, P]),
     "b2u_head_fwd": (I, [P, P, P, P, I, I, I, I, I, P]),
     "b2u_head_bwd_workspace": (SZ, []),
     "b2u_head_bwd": (I, [P, P, P, P, P, P, P, SZ, I, I, I, I, I, I, P]),

@@ -1,0 +1,268 @@
+// bn.cu -- nn.BatchNorm2d (+ReLU) forward and backward on NHWC bf16 activations.
+//
+// Replaces nn.BatchNorm2d + nn.ReLU(inplace=True) after every conv of the reference's BN models
+// (nets/TraditionalUnet.py:9-14, nets/resnet.py:65-71,110,140, nets/LightWeightUnet.py:9-11) and their autograd.
+//
+//   train fwd : mean_c, var_c (biased) over the N*H*W pixels of z; y = [relu](gamma (z - mean) invstd + beta);
+//               running_mean = (1-m) rm + m mean, running_var = (1-m) rv + m var P/(P-1)   (torch semantics)
+//   eval fwd  : y = [relu](gamma (z - rm) / sqrt(rv + eps) + beta)
+//   bwd       : g = dy (y > 0 if relu); dbeta = sum g; dgamma = sum g xhat;
+//               dz = gamma invstd (g - dbeta/P - xhat dgamma/P)
+//
+// All HBM-bound: a column-sum pass (z read once, 2 B/element) + an elementwise pass (4 B/element) forward; a
+// column-sum pass (6 B/element) + an elementwise pass (8 B/element) backward.  Partial sums are fp32 per block,
+// combined in fp64 in block order by a one-block finalize kernel (deterministic).
+#include "b2u_internal.h"
+#include "b2u_ptx.cuh"
+
+namespace b2u {
+
+#define B2U_CHECK_LAUNCH(name)                                                                           \
+  do {                                                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                                \
+    if (e__ != cudaSuccess) return b2u::set_error(B2U_ERR_CUDA, name " launch: %s", cudaGetErrorString(e__)); \
+    b2u::note_launch();                                                                                  \
+  } while (0)
+
+constexpr int kBnBlocks = 2 * 148;
+
+__device__ __forceinline__ void bn_unpack8(const uint4& v, float* f) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 bn_pack8(const float* f) {
+  uint4 v;
+  v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+  v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+  return v;
+}
+
+// Column sums of two per-element quantities.  MODE 0: (z, z^2).  MODE 1: (g, g * xhat) with g = dy * mask.
+// partial layout: [block][2][C].  blockDim.x = 256; thread -> (row lane, 8-channel chunk).
+template <int MODE>
+__global__ void __launch_bounds__(256)
+bn_colsum_kernel(const uint4* __restrict__ a, const uint4* __restrict__ y, const uint4* __restrict__ z,
+                 const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ partial,
+                 long long P, int C8, int relu) {
+  extern __shared__ float sred[];          // [256][16]
+  const int tid = threadIdx.x;
+  const int cpt = C8 < 256 ? C8 : 256;
+  const int rows = 256 / cpt;
+  const int cc = tid % cpt, rr = tid / cpt;
+  for (int c0 = 0; c0 < C8; c0 += cpt) {
+    const int c = c0 + cc;
+    float s0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (c < C8 && rr < rows) {
+      float mu[8], is[8];
+      if (MODE == 1) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { mu[k] = mean[c * 8 + k]; is[k] = invstd[c * 8 + k]; }
+      }
+      for (long long p = static_cast<long long>(blockIdx.x) * rows + rr; p < P; p += static_cast<long long>(gridDim.x) * rows) {
+        float f[8];
+        bn_unpack8(__ldg(a + p * C8 + c), f);
+        if (MODE == 0) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { s0[k] += f[k]; s1[k] = fmaf(f[k], f[k], s1[k]); }
+        } else {
+          float yy[8], zz[8];
+          bn_unpack8(__ldg(z + p * C8 + c), zz);
+          if (relu) bn_unpack8(__ldg(y + p * C8 + c), yy);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float g = (!relu || yy[k] > 0.f) ? f[k] : 0.f;
+            s0[k] += g;
+            s1[k] = fmaf(g, (zz[k] - mu[k]) * is[k], s1[k]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sred[tid * 16 + k] = s0[k]; sred[tid * 16 + 8 + k] = s1[k]; }
+    __syncthreads();
+    if (rr == 0 && c < C8) {
+      for (int r = 1; r < rows; ++r)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s0[k] += sred[(r * cpt + cc) * 16 + k]; s1[k] += sred[(r * cpt + cc) * 16 + 8 + k]; }
+      float* out = partial + static_cast<size_t>(blockIdx.x) * 2 * C8 * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { out[c * 8 + k] = s0[k]; out[C8 * 8 + c * 8 + k] = s1[k]; }
+    }
+    __syncthreads();
+  }
+}
+
+// forward finalize: statistics -> (scale, shift) for the apply pass, saved mean/invstd, running-stat update
+__global__ void bn_fwd_finalize_kernel(const float* __restrict__ partial, int blocks, int C, long long P,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       float* __restrict__ running_mean, float* __restrict__ running_var,
+                                       float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                                       float* __restrict__ scale, float* __restrict__ shift, float eps, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, ss = 0.0;
+  for (int b = 0; b < blocks; ++b) {
+    s += partial[static_cast<size_t>(b) * 2 * C + c];
+    ss += partial[static_cast<size_t>(b) * 2 * C + C + c];
+  }
+  const double mean = s / static_cast<double>(P);
+  double var = ss / static_cast<double>(P) - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double invstd = 1.0 / sqrt(var + static_cast<double>(eps));
+  save_mean[c] = static_cast<float>(mean);
+  save_invstd[c] = static_cast<float>(invstd);
+  const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+  scale[c] = static_cast<float>(g * invstd);
+  shift[c] = static_cast<float>(bt - mean * g * invstd);
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+  if (running_var) {
+    const double unbiased = P > 1 ? var * static_cast<double>(P) / static_cast<double>(P - 1) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+  }
+}
+
+__global__ void bn_eval_coeff_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                     float* __restrict__ scale, float* __restrict__ shift, int C, float eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+  const float is = 1.f / sqrtf(running_var[c] + eps);
+  scale[c] = g * is;
+  shift[c] = bt - running_mean[c] * g * is;
+}
+
+// y = [relu](z * scale + shift); one thread per (row, 8-channel chunk) through the row-indexed grid
+__global__ void bn_apply_kernel(const uint4* __restrict__ z, uint4* __restrict__ y, const float* __restrict__ scale,
+                                const float* __restrict__ shift, long long total, int C8, int relu) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = static_cast<int>(static_cast<unsigned>(i) % static_cast<unsigned>(C8));   // host guarantees total < 2^31
+  float f[8];
+  bn_unpack8(__ldg(z + i), f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float v = fmaf(f[k], __ldg(scale + c * 8 + k), __ldg(shift + c * 8 + k));
+    f[k] = relu ? fmaxf(v, 0.f) : v;
+  }
+  y[i] = bn_pack8(f);
+}
+
+// backward finalize: dgamma, dbeta and the three per-channel coefficients of the apply pass
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int C, long long P,
+                                       const float* __restrict__ gamma, const float* __restrict__ invstd,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double sg = 0.0, sgx = 0.0;
+  for (int b = 0; b < blocks; ++b) {
+    sg += partial[static_cast<size_t>(b) * 2 * C + c];
+    sgx += partial[static_cast<size_t>(b) * 2 * C + C + c];
+  }
+  if (dbeta) dbeta[c] = static_cast<float>(sg);
+  if (dgamma) dgamma[c] = static_cast<float>(sgx);
+  const float g = gamma ? gamma[c] : 1.f;
+  coef[c] = g * invstd[c];                                   // a
+  coef[C + c] = static_cast<float>(sg / static_cast<double>(P));      // b = dbeta / P
+  coef[2 * C + c] = static_cast<float>(sgx / static_cast<double>(P)); // c = dgamma / P
+}
+
+// dz = a (g - b - xhat c)
+__global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, const uint4* __restrict__ z,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ coef, uint4* __restrict__ dz, long long total, int C8, int relu) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = static_cast<int>(static_cast<unsigned>(i) % static_cast<unsigned>(C8));
+  const int C = C8 * 8;
+  float g[8], yy[8], zz[8], o[8];
+  bn_unpack8(__ldg(dy + i), g);
+  bn_unpack8(__ldg(z + i), zz);
+  if (relu) bn_unpack8(__ldg(y + i), yy);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ch = c * 8 + k;
+    const float gg = (!relu || yy[k] > 0.f) ? g[k] : 0.f;
+    const float xhat = (zz[k] - __ldg(mean + ch)) * __ldg(invstd + ch);
+    o[k] = __ldg(coef + ch) * (gg - __ldg(coef + C + ch) - xhat * __ldg(coef + 2 * C + ch));
+  }
+  dz[i] = bn_pack8(o);
+}
+
+}  // namespace b2u
+
+extern "C" {
+using namespace b2u;
+
+// workspace: [blocks][2][C] fp32 partial sums + 3*C coefficients (scale/shift or a/b/c)
+size_t b2u_bn_workspace(int C) { return (static_cast<size_t>(kBnBlocks) * 2 * C + 3 * static_cast<size_t>(C)) * sizeof(float); }
+
+static int bn_check(long long P, int C, const void* ws, size_t ws_bytes, const char* who) {
+  if (P <= 0 || C <= 0 || C % 8 != 0) return set_error(B2U_ERR_SHAPE, "%s: needs P > 0 and C %% 8 == 0 (C=%d)", who, C);
+  if (P * (C / 8) >= (1ll << 31)) return set_error(B2U_ERR_SHAPE, "%s: tensor too large (P*C/8 must be < 2^31)", who);
+  if (!ws || ws_bytes < b2u_bn_workspace(C)) return set_error(B2U_ERR_ARG, "%s: workspace too small", who);
+  return 0;
+}
+
+int b2u_bn_fwd_train(const void* z, void* y, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float* save_mean, float* save_invstd, void* ws, size_t ws_bytes, long long P,
+                     int C, float eps, float momentum, int relu, void* stream) {
+  int rc = bn_check(P, C, ws, ws_bytes, "bn_fwd_train");
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(ws);
+  float* coef = partial + static_cast<size_t>(kBnBlocks) * 2 * C;
+  bn_colsum_kernel<0><<<kBnBlocks, 256, 256 * 16 * sizeof(float), st>>>(static_cast<const uint4*>(z), nullptr, nullptr,
+                                                                        nullptr, nullptr, partial, P, C / 8, 0);
+  B2U_CHECK_LAUNCH("bn_colsum");
+  bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, kBnBlocks, C, P, gamma, beta, running_mean, running_var,
+                                                          save_mean, save_invstd, coef, coef + C, eps, momentum);
+  B2U_CHECK_LAUNCH("bn_fwd_finalize");
+  const long long total = P * (C / 8);
+  bn_apply_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(static_cast<const uint4*>(z), static_cast<uint4*>(y),
+                                                                             coef, coef + C, total, C / 8, relu);
+  B2U_CHECK_LAUNCH("bn_apply");
+  return 0;
+}
+
+int b2u_bn_fwd_eval(const void* z, void* y, const float* gamma, const float* beta, const float* running_mean,
+                    const float* running_var, void* ws, size_t ws_bytes, long long P, int C, float eps, int relu,
+                    void* stream) {
+  int rc = bn_check(P, C, ws, ws_bytes, "bn_fwd_eval");
+  if (rc) return rc;
+  if (!running_mean || !running_var) return set_error(B2U_ERR_ARG, "bn_fwd_eval: running statistics required");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* coef = static_cast<float*>(ws);
+  bn_eval_coeff_kernel<<<(C + 127) / 128, 128, 0, st>>>(gamma, beta, running_mean, running_var, coef, coef + C, C, eps);
+  B2U_CHECK_LAUNCH("bn_eval_coeff");
+  const long long total = P * (C / 8);
+  bn_apply_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(static_cast<const uint4*>(z), static_cast<uint4*>(y),
+                                                                             coef, coef + C, total, C / 8, relu);
+  B2U_CHECK_LAUNCH("bn_apply");
+  return 0;
+}
+
+// dy: gradient wrt the BN(+ReLU) output y; dz (may alias dy) = gradient wrt the BN input z
+int b2u_bn_bwd(const void* dy, const void* y, const void* z, const float* gamma, const float* save_mean,
+               const float* save_invstd, void* dz, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, long long P,
+               int C, int relu, void* stream) {
+  int rc = bn_check(P, C, ws, ws_bytes, "bn_bwd");
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(ws);
+  float* coef = partial + static_cast<size_t>(kBnBlocks) * 2 * C;
+  bn_colsum_kernel<1><<<kBnBlocks, 256, 256 * 16 * sizeof(float), st>>>(static_cast<const uint4*>(dy), static_cast<const uint4*>(y),
+                                                                        static_cast<const uint4*>(z), save_mean, save_invstd,
+                                                                        partial, P, C / 8, relu);
+  B2U_CHECK_LAUNCH("bn_bwd_colsum");
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, kBnBlocks, C, P, gamma, save_invstd, dgamma, dbeta, coef);
+  B2U_CHECK_LAUNCH("bn_bwd_finalize");
+  const long long total = P * (C / 8);
+  bn_bwd_apply_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+      static_cast<const uint4*>(dy), static_cast<const uint4*>(y), static_cast<const uint4*>(z), save_mean, save_invstd, coef,
+      static_cast<uint4*>(dz), total, C / 8, relu);
+  B2U_CHECK_LAUNCH("bn_bwd_apply");
+  return 0;
+}
+
+}  // extern "C"

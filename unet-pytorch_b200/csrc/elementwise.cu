@@ -115,11 +115,13 @@ __global__ void pack_weights_first_kernel(const float* __restrict__ w, __nv_bflo
 // tile: the OIHW rows are read as contiguous runs (32 ci x 9 taps floats per co), transposed through shared memory,
 // and leave as 64-byte runs in both operand layouts.
 struct PackEntry {
-  const float* w;          // OIHW fp32
-  __nv_bfloat16* wf;       // fprop operand (or first-layer [Cout][64])
-  __nv_bfloat16* wd;       // dgrad operand or null
+  const float* w;          // OIHW fp32 [Cout][Cin][taps]
+  __nv_bfloat16* wf;       // fprop operand [Cout_pad][taps * Ctot_pad] (or first-layer [Cout_pad][64]); padding pre-zeroed
+  __nv_bfloat16* wd;       // dgrad operand [Ctot_pad][taps * Cout_pad] or null
   long long start;         // first block index of this layer
-  int Cout, Cin, taps, first;
+  int Cout, Cin, taps, first;   // real (unpadded) sizes
+  int C0, C0_pad;          // virtual concat: real input channels [0,C0) sit at [0,C0), channels >= C0 at C0_pad + (ci - C0)
+  int Ctot_pad, Cout_pad;  // padded channel counts of the operands (multiples of 64)
 };
 __global__ void __launch_bounds__(256)
 pack_weights_multi_kernel(const PackEntry* __restrict__ table, int n) {
@@ -151,17 +153,18 @@ pack_weights_multi_kernel(const PackEntry* __restrict__ table, int n) {
     tile[r][j] = e.w[(static_cast<size_t>(co0 + r) * e.Cin + ci0) * e.taps + j];      // j = ci_local * taps + tap
   }
   __syncthreads();
-  const size_t kf = static_cast<size_t>(e.taps) * e.Cin, kd = static_cast<size_t>(e.taps) * e.Cout;
+  const size_t kf = static_cast<size_t>(e.taps) * e.Ctot_pad, kd = static_cast<size_t>(e.taps) * e.Cout_pad;
+  const int pc0 = ci0 < e.C0 ? ci0 : ci0 - e.C0 + e.C0_pad;      // padded position of the tile's first input channel
   for (int i = threadIdx.x; i < 32 * run; i += blockDim.x) {
     // fprop operand: (co, tap, ci) with ci fastest
     const int ci = i & 31, t = (i >> 5) % e.taps, r = i / (32 * e.taps);
-    e.wf[(co0 + r) * kf + static_cast<size_t>(t) * e.Cin + ci0 + ci] = __float2bfloat16_rn(tile[r][ci * e.taps + t]);
+    e.wf[(co0 + r) * kf + static_cast<size_t>(t) * e.Ctot_pad + pc0 + ci] = __float2bfloat16_rn(tile[r][ci * e.taps + t]);
   }
   if (e.wd) {
     for (int i = threadIdx.x; i < 32 * run; i += blockDim.x) {
       // dgrad operand: (ci, flipped tap, co) with co fastest
       const int r = i & 31, t = (i >> 5) % e.taps, ci = i / (32 * e.taps);
-      e.wd[(ci0 + ci) * kd + static_cast<size_t>(e.taps - 1 - t) * e.Cout + co0 + r] = __float2bfloat16_rn(tile[r][ci * e.taps + t]);
+      e.wd[(pc0 + ci) * kd + static_cast<size_t>(e.taps - 1 - t) * e.Cout_pad + co0 + r] = __float2bfloat16_rn(tile[r][ci * e.taps + t]);
     }
   }
 }
@@ -487,11 +490,12 @@ int b2u_pack_weights(const float* w, void* wf, void* wd, int Cout, int Cin, int 
   return 0;
 }
 
-// table: n entries of {const float* w; bf16* wf; bf16* wd; int64 start; int32 Cout, Cin, taps, first} (48 bytes each) in
-// DEVICE memory; start = index of the layer's first work block, a layer has (Cout/32)*(Cin/32) blocks (first layer:
-// ceil(Cout/32)); total_blocks = their sum.  Cout, Cin must be multiples of 32 (except the first layer's Cin).
+// table: n entries of {const float* w; bf16* wf; bf16* wd; int64 start; int32 Cout, Cin, taps, first, C0, C0_pad,
+// Ctot_pad, Cout_pad} (64 bytes each) in DEVICE memory; start = index of the layer's first work block, a layer has
+// (Cout/32)*(Cin/32) blocks (first layer: ceil(Cout/32)); total_blocks = their sum.  Real Cout, Cin and C0 must be
+// multiples of 32 (except the first layer's Cin); operand padding must be zeroed by the caller once.
 int b2u_pack_weights_multi(const void* table, int n, long long total_blocks, void* stream) {
-  static_assert(sizeof(b2u::PackEntry) == 48, "PackEntry layout is part of the ABI");
+  static_assert(sizeof(b2u::PackEntry) == 64, "PackEntry layout is part of the ABI");
   if (n <= 0 || total_blocks <= 0 || total_blocks > 0x7fffffffLL) return set_error(B2U_ERR_ARG, "pack_weights_multi: bad table");
   pack_weights_multi_kernel<<<static_cast<unsigned>(total_blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const b2u::PackEntry*>(table), n);

@@ -1,17 +1,25 @@
-"""Execution engine of the VGG16-backbone UNet hot path (nets/unet.py:62-78 + nets/vgg.py:21-31 of the reference).
+"""Execution engine of the UNet hot path: one configurable encoder/decoder schedule that runs both the
+VGG16-backbone Unet (nets/unet.py:62-78 + nets/vgg.py:21-31 of the reference: conv+bias+ReLU) and the
+conv+BatchNorm+ReLU family (nets/TraditionalUnet.py:5-93).
 
 The engine owns the bf16 NHWC activation buffers and the packed bf16 weights and launches the CUDA kernels of
 libb200unet.so in the order of the reference's forward, then the hand-derived backward:
 
-  forward   im2col(first conv) -> 13 x [conv3x3+bias+ReLU] with 4 max-pools -> 4 decoder stages
-            (upsample2x -> conv over the *virtual* concat [skip, up] -> conv) -> 1x1 head -> logits (NCHW fp32)
-  backward  head bwd -> per decoder stage: wgrad/dgrad conv2, wgrad conv1, split dgrad conv1 (d skip | d up),
-            upsample adjoint (+ReLU mask) -> per encoder block: wgrad, dgrad(+ReLU mask), pool bwd (+skip grad, +mask)
+  forward   im2col(first conv) -> encoder blocks of [conv3x3 (+bias) (+BN) +ReLU] separated by 2x2 max-pools ->
+            decoder stages (upsample2x -> conv over the *virtual* concat [skip, up] -> conv) -> 1x1 head -> logits
+  backward  head bwd -> per decoder stage: (BN bwd,) wgrad/dgrad conv2, wgrad conv1, split dgrad conv1 (d skip | d up),
+            upsample adjoint -> per encoder block: wgrad, dgrad, pool bwd (+skip grad); ReLU masks are fused into the
+            dgrad / pool / upsample kernels (plain nets) or applied by the BN backward kernel (BN nets)
+
+Channel counts that are not multiples of 64 (the 32-channel layers of TraditionalUnet) are zero-padded to 64 in the
+activation buffers and operands; padded channels stay exactly zero in both directions.
 
 Gradients are written straight into caller-provided fp32 OIHW tensors (normally views of one flat buffer), and
 `on_grads_ready(names)` is called after the launches that complete each layer's gradients so a data-parallel
 trainer can start that bucket's all-reduce while the remaining dgrad/wgrad kernels still run.
 """
+import struct
+
 import torch
 
 from . import ops
@@ -23,6 +31,10 @@ VGG16_CFG = [(0, 3, 64), (2, 64, 64), "M", (5, 64, 128), (7, 128, 128), "M", (10
 # (module name, C_skip, C_up, C_out): in_filters [192, 384, 768, 1024], out_filters [64, 128, 256, 512] (nets/unet.py:28-45)
 DECODER_CFG = [("up_concat4", 512, 512, 512), ("up_concat3", 256, 512, 256), ("up_concat2", 128, 256, 128),
                ("up_concat1", 64, 128, 64)]
+
+
+def pad64(c):
+    return (c + 63) // 64 * 64
 
 
 def vgg_unet_param_shapes(num_classes, in_channels=3):
@@ -45,40 +57,77 @@ def vgg_unet_param_shapes(num_classes, in_channels=3):
     return shapes
 
 
-class _Conv:
-    __slots__ = ("name", "cin", "cout", "first", "c0", "c1", "wf", "wd", "version")
+class ConvSpec:
+    """One conv3x3 (+BN) + ReLU layer.  name/bn: parameter-name prefixes; c0/c1: real channels of the two sources
+    of a virtual concat (c1 = 0: single source)."""
+    __slots__ = ("name", "bn", "cin", "cout", "first", "c0", "c1", "wf", "wd", "cout_p", "c0_p", "c1_p")
 
-    def __init__(self, name, cin, cout, first=False, c0=None, c1=0):
-        self.name, self.cin, self.cout, self.first = name, cin, cout, first
+    def __init__(self, name, cin, cout, first=False, c0=None, c1=0, bn=None):
+        self.name, self.bn, self.cin, self.cout, self.first = name, bn, cin, cout, first
         self.c0 = cin if c0 is None else c0
         self.c1 = c1
+        self.cout_p = pad64(cout)
+        self.c0_p = 64 if first else pad64(self.c0)
+        self.c1_p = pad64(c1) if c1 else 0
         self.wf = self.wd = None
-        self.version = None
+
+    @property
+    def padded(self):
+        return self.cout_p != self.cout or (not self.first and (self.c0_p != self.c0 or self.c1_p != self.c1))
 
 
-class VGGUnetEngine:
-    def __init__(self, num_classes, in_channels=3, device=None):
-        if in_channels * 9 > 64:
+class UNetConfig:
+    """enc: list of blocks (lists of ConvSpec) separated by 2x2 max-pools; dec: list of (conv1, conv2) stages, stage i
+    consumes the output of stage i-1 (or the last encoder block) upsampled 2x plus encoder block len(enc)-2-i as skip;
+    head: (name, real input channels)."""
+
+    def __init__(self, enc, dec, head, num_classes, in_channels=3):
+        self.enc, self.dec, self.head, self.num_classes, self.in_channels = enc, dec, head, num_classes, in_channels
+        self.bn = any(c.bn for b in enc for c in b)
+
+
+def vgg_unet_config(num_classes, in_channels=3):
+    enc, block = [], []
+    for item in VGG16_CFG:
+        if item == "M":
+            enc.append(block)
+            block = []
+        else:
+            i, cin, cout = item
+            block.append(ConvSpec(f"vgg.features.{i}", in_channels if i == 0 else cin, cout, first=(i == 0)))
+    enc.append(block)
+    dec = [(ConvSpec(f"{name}.conv1", cs + cu, co, c0=cs, c1=cu), ConvSpec(f"{name}.conv2", co, co))
+           for name, cs, cu, co in DECODER_CFG]
+    return UNetConfig(enc, dec, ("final", 64), num_classes, in_channels)
+
+
+def traditional_unet_config(num_classes, in_channels=3):
+    """nets/TraditionalUnet.py:45-93: DoubleConv = (conv3x3+bias, BN, ReLU) x 2; widths 32-64-128-256; Up concatenates
+    [skip, up] (:41) like unetUp."""
+    def double(prefix, cin, cout, first=False, c0=None, c1=0):
+        return [ConvSpec(f"{prefix}.double_conv.0", cin, cout, first=first, c0=c0, c1=c1, bn=f"{prefix}.double_conv.1"),
+                ConvSpec(f"{prefix}.double_conv.3", cout, cout, bn=f"{prefix}.double_conv.4")]
+    enc = [double("inc", in_channels, 32, first=True), double("down1.maxpool_conv.1", 32, 64),
+           double("down2.maxpool_conv.1", 64, 128), double("down3.maxpool_conv.1", 128, 256)]
+    dec = [tuple(double("up1.conv", 384, 128, c0=128, c1=256)), tuple(double("up2.conv", 192, 64, c0=64, c1=128)),
+           tuple(double("up3.conv", 96, 32, c0=32, c1=64))]
+    return UNetConfig(enc, dec, ("outc", 32), num_classes, in_channels)
+
+
+class UNetEngine:
+    def __init__(self, cfg, device=None):
+        if cfg.in_channels * 9 > 64:
             raise ValueError("in_channels must be <= 7 (first-layer im2col is 64 columns wide)")
-        if not 1 <= num_classes <= 32:
+        if not 1 <= cfg.num_classes <= 32:
             raise ValueError("num_classes must be in [1, 32]")
-        self.num_classes = num_classes
-        self.in_channels = in_channels
+        self.cfg = cfg
+        self.num_classes = cfg.num_classes
+        self.in_channels = cfg.in_channels
         self.device = device
-        self.enc = []      # list of lists (blocks) of _Conv
-        block = []
-        for item in VGG16_CFG:
-            if item == "M":
-                self.enc.append(block)
-                block = []
-            else:
-                i, cin, cout = item
-                block.append(_Conv(f"vgg.features.{i}", in_channels if i == 0 else cin, cout, first=(i == 0)))
-        self.enc.append(block)
-        self.dec = []
-        for name, cs, cu, co in DECODER_CFG:
-            self.dec.append((_Conv(f"{name}.conv1", cs + cu, co, c0=cs, c1=cu), _Conv(f"{name}.conv2", co, co)))
+        self.enc, self.dec, self.bn = cfg.enc, cfg.dec, cfg.bn
+        self.head_name, self.head_cin = cfg.head
         self.convs = [c for b in self.enc for c in b] + [c for pair in self.dec for c in pair]
+        self.eps, self.momentum = 1e-5, 0.1                 # nn.BatchNorm2d defaults (the reference never changes them)
         # The wgrad kernel can produce db in the same pass (an N=16 MMA against a ones tile); measured on B200 it costs
         # more than the separate HBM-bound column-sum kernel (work units with the extra MMAs become the stragglers of
         # the static schedule: +40 % wgrad time vs +1.2 ms for bias_grad), so it is off by default.
@@ -86,15 +135,14 @@ class VGGUnetEngine:
         self._pack_key = self._pack_versions = self._pack_table = None
         self._pack_total = 0
         self._bufs = {}
-        self._shape = None
         self.saved = None
         self._ws = {}
 
     # ------------------------------------------------------------------ buffers
-    def _buf(self, key, shape, dtype=torch.bfloat16):
+    def _buf(self, key, shape, dtype=torch.bfloat16, zero=False):
         t = self._bufs.get(key)
         if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
-            t = torch.empty(shape, dtype=dtype, device=self.device)
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
             self._bufs[key] = t
         return t
 
@@ -110,6 +158,17 @@ class VGGUnetEngine:
         self._ws.clear()
         self.saved = None
 
+    def _padded_vec(self, key, vec, n, fill=0.0):
+        """fp32 per-channel vector padded to n entries (persistent buffer, real part refreshed from `vec`)."""
+        if vec.numel() == n:
+            return vec
+        t = self._bufs.get(key)
+        if t is None or t.numel() != n:
+            t = torch.full((n,), fill, dtype=torch.float32, device=self.device)
+            self._bufs[key] = t
+        t[:vec.numel()].copy_(vec)
+        return t
+
     # ------------------------------------------------------------------ weights
     def pack(self, params, need_dgrad=True):
         """(Re)packs fp32 OIHW weights to bf16 operands when any of them changed: one launch for the whole model,
@@ -120,23 +179,25 @@ class VGGUnetEngine:
             return
         dev = params[self.convs[0].name + ".weight"].device
         if self._pack_key != key:
-            import struct
             blob, start = b"", 0
             for c in self.convs:
                 w = params[c.name + ".weight"]
+                ctot_p = c.c0_p + c.c1_p
                 if c.first:
                     if c.wf is None:
-                        c.wf = torch.empty((c.cout, 64), dtype=torch.bfloat16, device=dev)
+                        c.wf = torch.zeros((c.cout_p, 64), dtype=torch.bfloat16, device=dev)
                     count = (c.cout + 31) // 32                      # work blocks of this layer
                 else:
+                    if c.cout % 32 or c.cin % 32 or c.c0 % 32:
+                        raise ValueError(f"{c.name}: channel counts must be multiples of 32")
                     if c.wf is None:
-                        c.wf = torch.empty((c.cout, 9 * c.cin), dtype=torch.bfloat16, device=dev)
+                        c.wf = torch.zeros((c.cout_p, 9 * ctot_p), dtype=torch.bfloat16, device=dev)
                     if need_dgrad and c.wd is None:
-                        c.wd = torch.empty((c.cin, 9 * c.cout), dtype=torch.bfloat16, device=dev)
+                        c.wd = torch.zeros((ctot_p, 9 * c.cout_p), dtype=torch.bfloat16, device=dev)
                     count = (c.cout // 32) * (c.cin // 32)
                 wd_ptr = c.wd.data_ptr() if (need_dgrad and not c.first) else 0
-                blob += struct.pack("<QQQqiiii", w.data_ptr(), c.wf.data_ptr(), wd_ptr, start, c.cout, c.cin,
-                                    1 if c.first else 9, 1 if c.first else 0)
+                blob += struct.pack("<QQQqiiiiiiii", w.data_ptr(), c.wf.data_ptr(), wd_ptr, start, c.cout, c.cin,
+                                    1 if c.first else 9, 1 if c.first else 0, c.c0, c.c0_p, ctot_p, c.cout_p)
                 start += count
             self._pack_table = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
             self._pack_total = start
@@ -145,28 +206,106 @@ class VGGUnetEngine:
                                                    ops.stream_ptr()))
         self._pack_versions = versions
 
+    def param_shapes(self):
+        """name -> shape of every trainable tensor, in the reference module's state_dict order."""
+        shapes = {}
+        for c in self.convs:
+            shapes[c.name + ".weight"] = (c.cout, c.cin, 3, 3)
+            shapes[c.name + ".bias"] = (c.cout,)
+            if c.bn:
+                shapes[c.bn + ".weight"] = (c.cout,)
+                shapes[c.bn + ".bias"] = (c.cout,)
+        shapes[self.head_name + ".weight"] = (self.num_classes, self.head_cin, 1, 1)
+        shapes[self.head_name + ".bias"] = (self.num_classes,)
+        return shapes
+
+    def buffer_shapes(self):
+        """BatchNorm buffers (running statistics), state_dict names."""
+        shapes = {}
+        for c in self.convs:
+            if c.bn:
+                shapes[c.bn + ".running_mean"] = (c.cout,)
+                shapes[c.bn + ".running_var"] = (c.cout,)
+                shapes[c.bn + ".num_batches_tracked"] = ()
+        return shapes
+
+    def backward_param_order(self):
+        """Parameter names in the order backward() completes their gradients (head first, first conv last)."""
+        layers = []
+        for si in range(len(self.dec) - 1, -1, -1):
+            layers += [self.dec[si][1], self.dec[si][0]]
+        for bi in range(len(self.enc) - 1, -1, -1):
+            layers += list(reversed(self.enc[bi]))
+        out = [self.head_name + ".weight", self.head_name + ".bias"]
+        for c in layers:
+            if c.bn:
+                out += [c.bn + ".weight", c.bn + ".bias"]
+            out += [c.name + ".weight", c.name + ".bias"]
+        return out
+
     def invalidate_packed_weights(self):
         """Call after writing parameters behind torch's back (raw-pointer optimizer kernels)."""
         self._pack_versions = None
 
+    # ------------------------------------------------------------------ one conv (+BN) + ReLU layer, forward
+    def _layer_fwd(self, c, x0, params, A, training, x1=None):
+        n, h, w, _ = x0.shape
+        bias = self._padded_vec("b:" + c.name, params[c.name + ".bias"], c.cout_p)
+        taps = 1 if c.first else 9
+        if not c.bn:
+            out = self._buf(c.name, (n, h, w, c.cout_p))
+            ops.conv_fprop(x0, c.wf, bias, c.cout_p, taps=taps, relu=True, x1=x1, out=out)
+            A[c.name] = out
+            return out
+        z = self._buf("z:" + c.name, (n, h, w, c.cout_p))
+        ops.conv_fprop(x0, c.wf, bias, c.cout_p, taps=taps, relu=False, x1=x1, out=z)
+        gamma = self._padded_vec("g:" + c.bn, params[c.bn + ".weight"], c.cout_p, fill=1.0)
+        beta = self._padded_vec("bt:" + c.bn, params[c.bn + ".bias"], c.cout_p)
+        out = self._buf(c.name, (n, h, w, c.cout_p))
+        ws = self._workspace("bn", ops.lib().b2u_bn_workspace(c.cout_p))
+        rm, rv = params[c.bn + ".running_mean"], params[c.bn + ".running_var"]
+        if training:
+            if c.cout_p == c.cout:
+                _, mean, invstd = ops.bn_fwd_train(z, gamma, beta, rm, rv, self.eps, self.momentum, True, out=out, ws=ws)
+            else:
+                rmp = self._padded_vec("rm:" + c.bn, rm, c.cout_p)
+                rvp = self._padded_vec("rv:" + c.bn, rv, c.cout_p, fill=1.0)
+                _, mean, invstd = ops.bn_fwd_train(z, gamma, beta, rmp, rvp, self.eps, self.momentum, True, out=out, ws=ws)
+                rm.copy_(rmp[:c.cout])
+                rv.copy_(rvp[:c.cout])
+            nbt = params.get(c.bn + ".num_batches_tracked")
+            if nbt is not None:
+                nbt.add_(1)
+            A["bn:" + c.name] = (z, mean, invstd, gamma)
+        else:
+            rmp = self._padded_vec("rm:" + c.bn, rm, c.cout_p)
+            rvp = self._padded_vec("rv:" + c.bn, rv, c.cout_p, fill=1.0)
+            ops.bn_fwd_eval(z, gamma, beta, rmp, rvp, self.eps, True, out=out, ws=ws)
+        A[c.name] = out
+        return out
+
     # ------------------------------------------------------------------ forward
-    def forward(self, x, params, save=True):
-        """x: NCHW fp32 CUDA [N, Cin, H, W] with H, W multiples of 16 -> logits NCHW fp32."""
+    def forward(self, x, params, save=True, training=None):
+        """x: NCHW fp32 CUDA [N, Cin, H, W] -> logits NCHW fp32.  training (BN nets): batch statistics + running-stat
+        update (default: same as `save`)."""
         if not x.is_cuda:
-            raise ValueError("VGGUnetEngine.forward: input must be a CUDA tensor (no CPU fallback)")
+            raise ValueError("UNetEngine.forward: input must be a CUDA tensor (no CPU fallback)")
         if x.dtype != torch.float32:
             x = x.float()
         x = x.contiguous()
         N, C, H, W = x.shape
         if C != self.in_channels:
             raise ValueError(f"expected {self.in_channels} input channels, got {C}")
-        if H % 16 or W % 16:
-            raise ValueError("input height and width must be multiples of 16")
+        div = 2 ** (len(self.enc) - 1)
+        if H % div or W % div:
+            raise ValueError(f"input height and width must be multiples of {div}")
+        if training is None:
+            training = save
         self.device = x.device
         self.pack(params, need_dgrad=save)
         A = {}
         col = self._buf("col", (N, H, W, 64))
-        ops.lib().b2u_im2col_first(x.data_ptr(), col.data_ptr(), N, C, H, W, ops.stream_ptr())
+        ops.check(ops.lib().b2u_im2col_first(x.data_ptr(), col.data_ptr(), N, C, H, W, ops.stream_ptr()))
         A["col"] = col
         cur = col
         h, w = H, W
@@ -179,30 +318,30 @@ class VGGUnetEngine:
                 cur = pooled
                 h, w = h // 2, w // 2
             for c in block:
-                out = self._buf(c.name, (N, h, w, c.cout))
-                ops.conv_fprop(cur, c.wf, params[c.name + ".bias"], c.cout, taps=1 if c.first else 9, relu=True, out=out)
-                A[c.name] = out
-                cur = out
+                cur = self._layer_fwd(c, cur, params, A, training)
             feats.append(cur)
-        low = feats[4]
+        low = feats[-1]
         for si, (c1, c2) in enumerate(self.dec):
-            skip = feats[3 - si]
-            n_, hl, wl, cl = low.shape
+            skip = feats[len(self.enc) - 2 - si]
+            _, hl, wl, cl = low.shape
             up = self._buf(f"up{si}", (N, 2 * hl, 2 * wl, cl))
             ops.upsample2x(low, out=up)
             A[f"up{si}"] = up
-            o1 = self._buf(c1.name, (N, 2 * hl, 2 * wl, c1.cout))
-            ops.conv_fprop(skip, c1.wf, params[c1.name + ".bias"], c1.cout, taps=9, relu=True, x1=up, out=o1)
-            A[c1.name] = o1
-            o2 = self._buf(c2.name, (N, 2 * hl, 2 * wl, c2.cout))
-            ops.conv_fprop(o1, c2.wf, params[c2.name + ".bias"], c2.cout, taps=9, relu=True, out=o2)
-            A[c2.name] = o2
-            low = o2
-        wfin = params["final.weight"]
-        logits = ops.head_fwd(low, wfin.reshape(self.num_classes, 64), params["final.bias"])
+            o1 = self._layer_fwd(c1, skip, params, A, training, x1=up)
+            low = self._layer_fwd(c2, o1, params, A, training)
+        wh = self._head_weight(params)
+        logits = ops.head_fwd(low, wh, params[self.head_name + ".bias"])
         if save:
             self.saved = (A, feats, (N, H, W))
         return logits
+
+    def _head_weight(self, params):
+        w = params[self.head_name + ".weight"].reshape(self.num_classes, self.head_cin)
+        if self.head_cin == 64:
+            return w
+        t = self._buf("head:w", (self.num_classes, 64), torch.float32, zero=True)
+        t[:, :self.head_cin].copy_(w)
+        return t
 
     # ------------------------------------------------------------------ backward
     def backward(self, dlogits, params, grads, trainable=None, on_grads_ready=None):
@@ -214,98 +353,152 @@ class VGGUnetEngine:
         A, feats, (N, H, W) = self.saved
         if trainable is None:
             trainable = set(grads.keys())
-        order = [c.name for c in self.convs] + ["final"]
-        want = {n: ((n + ".weight") in trainable or (n + ".bias") in trainable) for n in order}
+        bn = self.bn
+        order = [c.name for c in self.convs] + [self.head_name]
+
+        def wanted(c):
+            names = [c.name + ".weight", c.name + ".bias"] + ([c.bn + ".weight", c.bn + ".bias"] if c.bn else [])
+            return any(n in trainable for n in names)
+        want = {c.name: wanted(c) for c in self.convs}
+        want[self.head_name] = (self.head_name + ".weight") in trainable or (self.head_name + ".bias") in trainable
         # data gradients are needed down to the first (in execution order) trainable conv
         first_trainable = next((i for i, n in enumerate(order) if want[n]), len(order))
         need_dx = {n: i > first_trainable for i, n in enumerate(order)}   # does layer n have to produce dx?
+        n_enc = sum(len(b) for b in self.enc)
+        enc_trainable = first_trainable < n_enc
 
         def ready(*names):
             if on_grads_ready is not None:
                 on_grads_ready([n for n in names if n in grads])
 
-        def wgrad(c, x0, dz, x1=None):
-            if not want[c.name]:
-                return
-            wn, bn = c.name + ".weight", c.name + ".bias"
-            want_w = wn in trainable and wn in grads
-            want_b = bn in trainable and bn in grads
-            fuse_b = want_w and want_b and self.fuse_bias_grad
-            if want_w:
-                need = ops.lib().b2u_conv_wgrad_workspace(dz.shape[0], dz.shape[1], dz.shape[2],
-                                                          64 if c.first else c.cin, c.cout, 1 if c.first else 9)
-                ops.conv_wgrad(x0, dz, taps=1 if c.first else 9, x1=x1, first_cin=c.cin if c.first else 0,
-                               dw=grads[wn], db=grads[bn] if fuse_b else None, ws=self._workspace("wgrad", need))
-            if want_b and not fuse_b:
-                ops.bias_grad(dz, db=grads[bn], ws=self._workspace("bias", ops.lib().b2u_bias_grad_workspace(c.cout)))
-            ready(wn, bn)
+        def has(n):
+            return n in trainable and n in grads
 
+        def layer_bwd(c, x0, g, x1=None):
+            """g: gradient wrt the layer's output (BN nets: wrt y, unmasked; plain nets: wrt the pre-activation, already
+            masked).  Runs BN backward if any, wgrad, bias grad; returns dz (the conv's output gradient)."""
+            dz = g
+            if c.bn:
+                z, mean, invstd, gamma = A["bn:" + c.name]
+                wn, bnn = c.bn + ".weight", c.bn + ".bias"
+                dgam = self._buf("dg:" + c.bn, (c.cout_p,), torch.float32)
+                dbet = self._buf("db:" + c.bn, (c.cout_p,), torch.float32)
+                ops.bn_bwd(g, A[c.name], z, gamma, mean, invstd, relu=True, out=g, dgamma=dgam, dbeta=dbet,
+                           ws=self._workspace("bn", ops.lib().b2u_bn_workspace(c.cout_p)))
+                if has(wn):
+                    grads[wn].copy_(dgam[:c.cout])
+                if has(bnn):
+                    grads[bnn].copy_(dbet[:c.cout])
+                ready(wn, bnn)
+            if not want[c.name]:
+                return dz
+            wn, bn_ = c.name + ".weight", c.name + ".bias"
+            want_w, want_b = has(wn), has(bn_)
+            fuse_b = want_w and want_b and self.fuse_bias_grad and not c.padded
+            taps = 1 if c.first else 9
+            if want_w:
+                ctot_p = 64 if c.first else c.c0_p + c.c1_p
+                need = ops.lib().b2u_conv_wgrad_workspace(dz.shape[0], dz.shape[1], dz.shape[2], ctot_p, c.cout_p, taps)
+                ws = self._workspace("wgrad", need)
+                if not c.padded:
+                    ops.conv_wgrad(x0, dz, taps=taps, x1=x1, first_cin=c.cin if c.first else 0, dw=grads[wn],
+                                   db=grads[bn_] if fuse_b else None, ws=ws)
+                else:
+                    if c.first:
+                        tmp = self._buf("dw:" + c.name, (c.cout_p, c.cin, 3, 3), torch.float32)
+                        ops.conv_wgrad(x0, dz, taps=1, first_cin=c.cin, dw=tmp, ws=ws)
+                        grads[wn].copy_(tmp[:c.cout])
+                    else:
+                        tmp = self._buf("dw:" + c.name, (c.cout_p, ctot_p, 3, 3), torch.float32)
+                        ops.conv_wgrad(x0, dz, taps=9, x1=x1, dw=tmp, ws=ws)
+                        if c.c1:
+                            grads[wn][:, :c.c0].copy_(tmp[:c.cout, :c.c0])
+                            grads[wn][:, c.c0:].copy_(tmp[:c.cout, c.c0_p:c.c0_p + c.c1])
+                        else:
+                            grads[wn].copy_(tmp[:c.cout, :c.c0])
+            if want_b and not fuse_b:
+                if c.cout_p == c.cout:
+                    ops.bias_grad(dz, db=grads[bn_], ws=self._workspace("bias", ops.lib().b2u_bias_grad_workspace(c.cout_p)))
+                else:
+                    tmpb = self._buf("dbias:" + c.name, (c.cout_p,), torch.float32)
+                    ops.bias_grad(dz, db=tmpb, ws=self._workspace("bias", ops.lib().b2u_bias_grad_workspace(c.cout_p)))
+                    grads[bn_].copy_(tmpb[:c.cout])
+            ready(wn, bn_)
+            return dz
+
+        # ---- head
+        hn = self.head_name
         last = A[self.dec[-1][1].name]
-        wfin = params["final.weight"].reshape(self.num_classes, 64)
-        fw, fb = "final.weight" in trainable and "final.weight" in grads, "final.bias" in trainable and "final.bias" in grads
-        dz = self._buf("g:" + self.dec[-1][1].name, last.shape) if need_dx["final"] else None
+        wh = self._head_weight(params)
+        C = self.num_classes
+        fw, fb = has(hn + ".weight"), has(hn + ".bias")
+        g = self._buf("g:" + self.dec[-1][1].name, last.shape) if need_dx[hn] else None
         if dlogits.dtype == torch.bfloat16:
             # [N,H,W,64] = [hi | lo] split dlogits from loss_bwd(nhwc64=True): the head's backward runs on the tensor
             # cores as a 1x1 dgrad (+ReLU mask) and a 1x1 wgrad (+bias) over 2 x 32 padded classes
             dl = dlogits.contiguous()
-            if need_dx["final"]:
-                wd_head = ops.pack_head_dgrad(wfin, wd=self._buf("head:wd", (64, 64)))
-                ops.conv_dgrad(dl, wd_head, 64, taps=1, mask=last, out0=dz)
+            if need_dx[hn]:
+                wd_head = ops.pack_head_dgrad(wh, wd=self._buf("head:wd", (64, 64)))
+                ops.conv_dgrad(dl, wd_head, 64, taps=1, mask=None if bn else last, out0=g)
             if fw or fb:
                 dw64 = self._buf("head:dw", (64, 64, 1, 1), torch.float32)
                 db64 = self._buf("head:db", (64,), torch.float32)
                 need = ops.lib().b2u_conv_wgrad_workspace(dl.shape[0], dl.shape[1], dl.shape[2], 64, 64, 1)
                 ops.conv_wgrad(last, dl, taps=1, dw=dw64, db=db64, ws=self._workspace("wgrad", need))
-                C = self.num_classes     # rows [0,32) came from the hi half of dlogits, rows [32,64) from the lo half
-                if fw:
-                    torch.add(dw64[:C], dw64[32:32 + C], out=grads["final.weight"])
+                if fw:      # rows [0,32) came from the hi half of dlogits, rows [32,64) from the lo half
+                    torch.add(dw64[:C, :self.head_cin], dw64[32:32 + C, :self.head_cin], out=grads[hn + ".weight"])
                 if fb:
-                    torch.add(db64[:C], db64[32:32 + C], out=grads["final.bias"])
+                    torch.add(db64[:C], db64[32:32 + C], out=grads[hn + ".bias"])
         else:
             dl = dlogits.contiguous()
             if dl.dtype != torch.float32:
                 dl = dl.float()
-            ops.head_bwd(dl, last, wfin, need_dx=need_dx["final"], need_dw=fw or fb, relu_mask=True, dx=dz,
-                         dw=grads["final.weight"] if fw else None, db=grads["final.bias"] if fb else None,
+            if self.head_cin == 64:
+                dwt, dbt = (grads[hn + ".weight"] if fw else None), (grads[hn + ".bias"] if fb else None)
+            else:
+                dwt = self._buf("head:dwf", (C, 64, 1, 1), torch.float32) if fw else None
+                dbt = grads[hn + ".bias"] if fb else None
+            ops.head_bwd(dl, last, wh, need_dx=need_dx[hn], need_dw=fw or fb, relu_mask=not bn, dx=g, dw=dwt, db=dbt,
                          ws=self._workspace("head", ops.lib().b2u_head_bwd_workspace()))
-        ready("final.weight", "final.bias")
-        if dz is None:
+            if fw and self.head_cin != 64:
+                grads[hn + ".weight"].copy_(dwt[:, :self.head_cin])
+        ready(hn + ".weight", hn + ".bias")
+        if g is None:
             return
 
-        dskips = [None] * 4     # gradient wrt feat1..feat4 coming from the decoder
-        for si in range(3, -1, -1):
+        # ---- decoder, last stage first
+        n_dec = len(self.dec)
+        dskips = [None] * (len(self.enc) - 1)     # gradient wrt the encoder features coming from the decoder
+        for si in range(n_dec - 1, -1, -1):
             c1, c2 = self.dec[si]
-            skip = feats[3 - si]
+            fi = len(self.enc) - 2 - si
+            skip = feats[fi]
             up = A[f"up{si}"]
             o1 = A[c1.name]
-            low = feats[4] if si == 0 else A[self.dec[si - 1][1].name]
-            # conv2
-            wgrad(c2, o1, dz)
+            low = feats[-1] if si == 0 else A[self.dec[si - 1][1].name]
+            dz = layer_bwd(c2, o1, g)
             if not need_dx[c2.name]:
                 return
-            dz1 = self._buf("g:" + c1.name, o1.shape)
-            ops.conv_dgrad(dz, c2.wd, c2.cin, mask=o1, out0=dz1)
-            # conv1 over [skip, up]
-            wgrad(c1, skip, dz1, x1=up)
+            g1 = self._buf("g:" + c1.name, o1.shape)
+            ops.conv_dgrad(dz, c2.wd, c2.c0_p, mask=None if bn else o1, out0=g1)
+            dz1 = layer_bwd(c1, skip, g1, x1=up)
             if not need_dx[c1.name]:
                 return
-            enc_trainable = first_trainable < len([c for b in self.enc for c in b])
             dup = self._buf(f"g:up{si}", up.shape)
             if enc_trainable:
-                dsk = self._buf(f"g:skip{3 - si}", skip.shape)
-                ops.conv_dgrad(dz1, c1.wd, c1.c0, C1=c1.c1, out0=dsk, out1=dup)
-                dskips[3 - si] = dsk
+                dsk = self._buf(f"g:skip{fi}", skip.shape)
+                ops.conv_dgrad(dz1, c1.wd, c1.c0_p, C1=c1.c1_p, out0=dsk, out1=dup)
+                dskips[fi] = dsk
             else:
                 # frozen encoder: only the up-sampled half of the concat needs a gradient
-                wd_up = c1.wd[c1.c0:]
-                ops.conv_dgrad(dz1, wd_up, c1.c1, out0=dup)
+                ops.conv_dgrad(dz1, c1.wd[c1.c0_p:], c1.c1_p, out0=dup)
             if si == 0 and not enc_trainable:
                 return
-            dz = self._buf("g:low" + str(si), low.shape)
-            ops.upsample2x_bwd(dup, ylow=low, out=dz)
+            g = self._buf("g:low" + str(si), low.shape)
+            ops.upsample2x_bwd(dup, ylow=None if bn else low, out=g)
 
-        # encoder, deepest block first; dz = gradient wrt the pre-activation of the block's last conv
-        for bi in range(4, -1, -1):
+        # ---- encoder, deepest block first; g = gradient wrt the block's last conv output
+        for bi in range(len(self.enc) - 1, -1, -1):
             block = self.enc[bi]
             for ci in range(len(block) - 1, -1, -1):
                 c = block[ci]
@@ -315,17 +508,27 @@ class VGGUnetEngine:
                     xin = A[f"pool{bi}"]
                 else:
                     xin = A["col"]
-                wgrad(c, xin, dz)
+                dz = layer_bwd(c, xin, g)
                 if not need_dx[c.name]:
                     return
                 if ci > 0:
                     nxt = self._buf("g:" + block[ci - 1].name, xin.shape)
-                    ops.conv_dgrad(dz, c.wd, c.cin, mask=xin, out0=nxt)
-                    dz = nxt
+                    ops.conv_dgrad(dz, c.wd, c.c0_p, mask=None if bn else xin, out0=nxt)
+                    g = nxt
                 else:
                     dpool = self._buf(f"g:pool{bi}", xin.shape)
-                    ops.conv_dgrad(dz, c.wd, c.cin, out0=dpool)
+                    ops.conv_dgrad(dz, c.wd, c.c0_p, out0=dpool)
                     y = feats[bi - 1]
                     nxt = self._buf(f"g:feat{bi - 1}", y.shape)
-                    ops.maxpool2x2_bwd(dpool, y, dskip=dskips[bi - 1], relu_mask=True, out=nxt)
-                    dz = nxt
+                    ops.maxpool2x2_bwd(dpool, y, dskip=dskips[bi - 1], relu_mask=not bn, out=nxt)
+                    g = nxt
+
+
+class VGGUnetEngine(UNetEngine):
+    def __init__(self, num_classes, in_channels=3, device=None):
+        super().__init__(vgg_unet_config(num_classes, in_channels), device=device)
+
+
+class TraditionalUnetEngine(UNetEngine):
+    def __init__(self, num_classes, in_channels=3, device=None):
+        super().__init__(traditional_unet_config(num_classes, in_channels), device=device)

@@ -1,11 +1,9 @@
 """Drop-in for the reference's nets/unet.py::Unet (lines 24-94): same constructor, attributes, state_dict keys
 and forward contract (NCHW fp32 image in, NCHW fp32 logits out), executed by the sm_100a engine."""
-import threading
-
-import torch
 import torch.nn as nn
 
 from ..engine import VGGUnetEngine
+from ._function import EngineModuleMixin
 from .vgg import VGG16
 
 
@@ -23,34 +21,7 @@ class unetUp(nn.Module):
         raise RuntimeError("unetUp is a parameter container here; call Unet.forward (CUDA engine) instead")
 
 
-class _UnetFunction(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, module, x, *params):
-        engine = module._engine_for(x.device)
-        names = module._param_names
-        pdict = dict(zip(names, params))
-        needs = any(ctx.needs_input_grad[2:])
-        logits = engine.forward(x, pdict, save=needs)
-        if needs:
-            engine._generation = getattr(engine, "_generation", 0) + 1
-            ctx.generation = engine._generation
-            ctx.engine = engine
-            ctx.names = names
-            ctx.params = params
-        return logits
-
-    @staticmethod
-    def backward(ctx, dlogits):
-        engine = ctx.engine
-        if engine._generation != ctx.generation:
-            raise RuntimeError("Unet backward: the saved activations were overwritten by a later training forward")
-        pdict = dict(zip(ctx.names, ctx.params))
-        grads = {n: torch.empty_like(p) for n, p, need in zip(ctx.names, ctx.params, ctx.needs_input_grad[2:]) if need}
-        engine.backward(dlogits, pdict, grads)
-        return (None, None) + tuple(grads.get(n) for n in ctx.names)
-
-
-class Unet(nn.Module):
+class Unet(nn.Module, EngineModuleMixin):
     def __init__(self, num_classes=21, pretrained=False, backbone="vgg"):
         super().__init__()
         if backbone == "vgg":
@@ -69,29 +40,13 @@ class Unet(nn.Module):
         self.final = nn.Conv2d(out_filters[0], num_classes, 1)
         self.backbone = backbone
         self.num_classes = num_classes
-        self._engines = {}
-        self._engine_lock = threading.Lock()
+        self._init_engine_state()
 
-    # the engine is per device (nn.DataParallel replicas share this dict; each device thread gets its own)
-    def _engine_for(self, device):
-        key = (device.type, device.index)
-        with self._engine_lock:
-            eng = self._engines.get(key)
-            if eng is None:
-                eng = VGGUnetEngine(self.num_classes, in_channels=3, device=device)
-                self._engines[key] = eng
-            return eng
-
-    @property
-    def _param_names(self):
-        return [n for n, _ in self.named_parameters()]
+    def _make_engine(self, device):
+        return VGGUnetEngine(self.num_classes, in_channels=3, device=device)
 
     def forward(self, inputs):
-        if not inputs.is_cuda:
-            raise RuntimeError("unet_pytorch_b200.Unet runs on a B200 only: move the module and inputs to CUDA "
-                               "(there is no CPU fallback)")
-        params = [p for _, p in self.named_parameters()]
-        return _UnetFunction.apply(self, inputs, *params)
+        return self._engine_forward(inputs)
 
     def freeze_backbone(self):
         for param in self.vgg.parameters():

@@ -218,6 +218,58 @@ def upsample2x_bwd(dup, ylow=None, out=None):
     return out
 
 
+# ---------------------------------------------------------------------------------------------- batch norm
+def bn_fwd_train(z, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1, relu=True, out=None, ws=None):
+    """Returns (y, save_mean, save_invstd); running statistics are updated in place (torch semantics)."""
+    _req(z, BF16, "z")
+    C = z.shape[-1]
+    P = z.numel() // C
+    need = lib().b2u_bn_workspace(C)
+    if ws is None or ws.numel() * ws.element_size() < need:
+        ws = _ws(need, z.device)
+    if out is None:
+        out = torch.empty_like(z)
+    mean = torch.empty((C,), dtype=torch.float32, device=z.device)
+    invstd = torch.empty((C,), dtype=torch.float32, device=z.device)
+    check(lib().b2u_bn_fwd_train(ptr(z), ptr(out), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(mean),
+                                 ptr(invstd), ptr(ws), ws.numel() * ws.element_size(), P, C, eps, momentum,
+                                 1 if relu else 0, stream_ptr()))
+    return out, mean, invstd
+
+
+def bn_fwd_eval(z, gamma, beta, running_mean, running_var, eps=1e-5, relu=True, out=None, ws=None):
+    _req(z, BF16, "z")
+    C = z.shape[-1]
+    P = z.numel() // C
+    need = lib().b2u_bn_workspace(C)
+    if ws is None or ws.numel() * ws.element_size() < need:
+        ws = _ws(need, z.device)
+    if out is None:
+        out = torch.empty_like(z)
+    check(lib().b2u_bn_fwd_eval(ptr(z), ptr(out), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(ws),
+                                ws.numel() * ws.element_size(), P, C, eps, 1 if relu else 0, stream_ptr()))
+    return out
+
+
+def bn_bwd(dy, y, z, gamma, mean, invstd, relu=True, out=None, dgamma=None, dbeta=None, ws=None):
+    """Returns (dz, dgamma, dbeta)."""
+    _req(dy, BF16, "dy"); _req(y, BF16, "y"); _req(z, BF16, "z")
+    C = z.shape[-1]
+    P = z.numel() // C
+    need = lib().b2u_bn_workspace(C)
+    if ws is None or ws.numel() * ws.element_size() < need:
+        ws = _ws(need, z.device)
+    if out is None:
+        out = torch.empty_like(z)
+    if dgamma is None:
+        dgamma = torch.empty((C,), dtype=torch.float32, device=z.device)
+    if dbeta is None:
+        dbeta = torch.empty((C,), dtype=torch.float32, device=z.device)
+    check(lib().b2u_bn_bwd(ptr(dy), ptr(y), ptr(z), ptr(gamma), ptr(mean), ptr(invstd), ptr(out), ptr(dgamma), ptr(dbeta),
+                           ptr(ws), ws.numel() * ws.element_size(), P, C, 1 if relu else 0, stream_ptr()))
+    return out, dgamma, dbeta
+
+
 # ---------------------------------------------------------------------------------------------- head
 def head_fwd(x, w, b, out=None):
     _req(x, BF16, "x"); _req(w, torch.float32, "w"); _req(b, torch.float32, "b")

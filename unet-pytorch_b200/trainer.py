@@ -14,7 +14,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
-from .engine import VGGUnetEngine, vgg_unet_param_shapes
+from .engine import TraditionalUnetEngine, VGGUnetEngine, vgg_unet_param_shapes
 
 
 def _backward_order(names):
@@ -129,23 +129,40 @@ class GradientSync:
 
 
 class UnetTrainer:
+    """model: "unet_vgg" (nets/unet.py::Unet, backbone='vgg') or "traditional" (nets/TraditionalUnet.py)."""
+
+    ENGINES = {"unet_vgg": VGGUnetEngine, "traditional": TraditionalUnetEngine}
+
     def __init__(self, num_classes=21, device=None, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
                  optimizer="adam", momentum=0.9, cls_weights=None, dice_loss=True, focal_loss=False,
-                 state_dict=None, process_group=None, bucket_mb=16, compute_f_score=True):
+                 state_dict=None, process_group=None, bucket_mb=16, compute_f_score=True, model="unet_vgg"):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("UnetTrainer needs a CUDA device (no CPU fallback)")
+        if model not in self.ENGINES:
+            raise ValueError(f"unknown model {model!r}; choose from {sorted(self.ENGINES)}")
         self.num_classes = num_classes
-        self.engine = VGGUnetEngine(num_classes, device=self.device)
-        shapes = vgg_unet_param_shapes(num_classes)
-        self.names = list(shapes.keys())                       # state_dict order
-        self.layout = FlatBuckets(shapes, _backward_order(self.names), self.device, bucket_bytes=bucket_mb << 20)
+        self.engine = self.ENGINES[model](num_classes, device=self.device)
+        shapes = self.engine.param_shapes()
+        self.names = list(shapes.keys())                       # trainable tensors, state_dict order
+        self.layout = FlatBuckets(shapes, self.engine.backward_param_order(), self.device, bucket_bytes=bucket_mb << 20)
         self.flat_param = self.layout.new_buffer()
         self.flat_grad = self.layout.new_buffer()
         self.params = self.layout.views(self.flat_param)
         self.grads = self.layout.views(self.flat_grad)
+        # BatchNorm buffers: not optimised, kept beside the flat parameters (train.py's DDP broadcasts them from rank 0)
+        self.buffers = {}
+        for n, shp in self.engine.buffer_shapes().items():
+            if n.endswith("running_var"):
+                self.buffers[n] = torch.ones(shp, dtype=torch.float32, device=self.device)
+            elif n.endswith("num_batches_tracked"):
+                self.buffers[n] = torch.zeros(shp, dtype=torch.int64, device=self.device)
+            else:
+                self.buffers[n] = torch.zeros(shp, dtype=torch.float32, device=self.device)
+        self.tensors = dict(self.params)
+        self.tensors.update(self.buffers)
         self.opt_kind = optimizer
         self.lr, self.betas, self.eps, self.weight_decay, self.momentum = lr, betas, eps, weight_decay, momentum
         self.m = self.layout.new_buffer()
@@ -156,6 +173,7 @@ class UnetTrainer:
         self.cls_w = cw.to(self.device).contiguous()
         self.sync = GradientSync(self.layout, self.flat_grad, group=process_group)
         self.trainable = set(self.names)
+        self.backbone_prefixes = ("vgg.",) if model == "unet_vgg" else ("inc.", "down1.", "down2.", "down3.")
         self._gscale = torch.tensor([0.0 if focal_loss else 1.0, 1.0 if focal_loss else 0.0, 1.0 if dice_loss else 0.0],
                                     dtype=torch.float32, device=self.device)
         self._copy_stream = torch.cuda.Stream(device=self.device)
@@ -173,12 +191,19 @@ class UnetTrainer:
         with torch.no_grad():
             for n in self.names:
                 self.params[n].copy_(sd[n].to(self.device, dtype=torch.float32))
+            for n, b in self.buffers.items():
+                if n in sd:
+                    b.copy_(sd[n].to(self.device, dtype=b.dtype))
+        self.engine.invalidate_packed_weights()
 
     def state_dict(self):
-        return {n: self.params[n].detach().clone() for n in self.names}
+        sd = {n: self.params[n].detach().clone() for n in self.names}
+        sd.update({n: b.detach().clone() for n, b in self.buffers.items()})
+        return sd
 
     def freeze_backbone(self):
-        self.trainable = {n for n in self.names if not n.startswith("vgg.")}
+        """nets/unet.py:80-86 / nets/TraditionalUnet.py:95-104 (freeze_encoder)"""
+        self.trainable = {n for n in self.names if not n.startswith(self.backbone_prefixes)}
 
     def unfreeze_backbone(self):
         self.trainable = set(self.names)
@@ -227,7 +252,7 @@ class UnetTrainer:
 
     # ------------------------------------------------------------------ the step
     def forward_loss(self, imgs, pngs, save=True):
-        logits = self.engine.forward(imgs, self.params, save=save)
+        logits = self.engine.forward(imgs, self.tensors, save=save)
         if pngs.dtype != torch.int64:
             pngs = pngs.long()
         fin = ops.loss_fwd(logits, target=pngs.contiguous(), onehot=None, cls_w=self.cls_w)
@@ -245,7 +270,7 @@ class UnetTrainer:
         active = [n for n in self.layout.order if n in self.trainable]
         self.sync.reset(active)
         grads = {n: self.grads[n] for n in active}
-        self.engine.backward(dlogits, self.params, grads, trainable=self.trainable, on_grads_ready=self.sync.ready)
+        self.engine.backward(dlogits, self.tensors, grads, trainable=self.trainable, on_grads_ready=self.sync.ready)
         scale = self.sync.finish()
         self.optimizer_step(scale)
         loss = self._total(fin)
