@@ -212,6 +212,27 @@ def test_fast_hist_edge_cases(b2u, cuda_device, golden_dir):
     assert np.array_equal(got, O.fast_hist(a[3:].numpy(), b[3:].numpy(), 21))
 
 
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 6, 21, 32, 45, 64])
+def test_fast_hist_all_kernel_variants(b2u, cuda_device, n):
+    """vote kernel (n*n <= 32), lane-private byte counters (up to ~75 bins x 75), shared-atomic fallback; lengths that
+    force byte-counter folds; out-of-range predictions land in the overflow counter exactly like numpy's failure."""
+    rng = np.random.default_rng(100 + n)
+    L = 16 * 256 * 148 * 3 + 7                       # several rounds per lane + a ragged tail
+    a = rng.integers(0, n, size=L).astype(np.uint8)
+    a[rng.random(L) < 0.05] = 255
+    a[:5000] = 1 % n                                  # one lane hammers a single bin: exercises the 240-increment fold
+    b = rng.integers(0, n, size=L).astype(np.uint8)
+    b[:5000] = 0
+    assert np.array_equal(b2u.fast_hist(a, b, n), O.fast_hist(a, b, n))
+    b_bad = b.copy()
+    b_bad[L // 2] = 255                               # pushes n*a+b past n*n unless that pixel is ignored
+    a_ok = a.copy(); a_ok[L // 2] = n - 1
+    hist = b2u.fast_hist_device(a_ok, b_bad, n).cpu().numpy()
+    assert hist[-1] == 1
+    with pytest.raises(ValueError):
+        b2u.fast_hist(a_ok, b_bad, n)
+
+
 def test_fast_hist_full_size_properties(b2u, cuda_device):
     """BASELINE config 5 size (512x512 masks): exact against numpy on 50 masks; sum of per-mask histograms ==
     histogram of the concatenation; total count == number of non-ignored pixels."""
