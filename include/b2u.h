@@ -87,16 +87,34 @@ int b2u_upsample2x_bwd(const void* dup, const void* ylow, void* dlow, int N, int
 /* z, y, dy, dz: NHWC bf16 with C channels (C % 8 == 0), P = N*H*W pixels; gamma/beta/running/save: fp32 [C].
  * train: batch statistics (biased variance), running stats updated with `momentum` (unbiased variance), torch semantics. */
 size_t b2u_bn_workspace(int C);
-int b2u_bn_fwd_train(const void* z, void* y, const float* gamma, const float* beta, float* running_mean,
-                     float* running_var, float* save_mean, float* save_invstd, void* ws, size_t ws_bytes, long long P,
-                     int C, float eps, float momentum, int relu, void* stream);
-int b2u_bn_fwd_eval(const void* z, void* y, const float* gamma, const float* beta, const float* running_mean,
-                    const float* running_var, void* ws, size_t ws_bytes, long long P, int C, float eps, int relu,
-                    void* stream);
-/* dy = gradient wrt y = [relu](bn(z)); dz (may alias dy) = gradient wrt z; dgamma/dbeta nullable */
+/* residual (nullable): y = [relu](bn(z) + residual), the tail of a ResNet bottleneck (nets/resnet.py:92-95) */
+int b2u_bn_fwd_train(const void* z, const void* residual, void* y, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, float* save_mean, float* save_invstd, void* ws,
+                     size_t ws_bytes, long long P, int C, float eps, float momentum, int relu, void* stream);
+int b2u_bn_fwd_eval(const void* z, const void* residual, void* y, const float* gamma, const float* beta,
+                    const float* running_mean, const float* running_var, void* ws, size_t ws_bytes, long long P, int C,
+                    float eps, int relu, void* stream);
+/* dy = gradient wrt y; dz (may alias dy) = gradient wrt z; gout (nullable) = ReLU-masked dy = gradient wrt the residual;
+ * dgamma/dbeta nullable */
 int b2u_bn_bwd(const void* dy, const void* y, const void* z, const float* gamma, const float* save_mean,
-               const float* save_invstd, void* dz, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, long long P,
-               int C, int relu, void* stream);
+               const float* save_invstd, void* dz, void* gout, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
+               long long P, int C, int relu, void* stream);
+
+/* ---- ResNet50 encoder helpers (nets/resnet.py:100-176) ------------------------------------------------------ */
+/* 7x7 stride-2 pad-3 stem (nets/resnet.py:109): NCHW fp32 -> im2col rows [N,ceil(H/2),ceil(W/2),192] bf16 */
+int b2u_im2col_stem(const float* x_nchw, void* col, int N, int Cin, int H, int W, void* stream);
+int b2u_pack_weights_im2col(const float* w_oihw, void* wf, int Cout, int Cin, int taps, int Kpad, void* stream);
+/* wgrad of a conv that was run through an im2col tensor: x0 = im2col rows [N,H,W,Kpad], dw = [Cout][cin][taps] */
+int b2u_conv_wgrad_im2col(const void* x0, int Kpad, const void* dz, int Cout, float* dw, void* ws, size_t ws_bytes, int N,
+                          int H, int W, int cin, int taps, void* stream);
+/* stride-2 convs = stride-1 conv + keep even pixels (3x3) / keep even pixels + 1x1 conv (downsample branch) */
+int b2u_subsample2(const void* x, void* y, int N, int H, int W, int C, void* stream);
+int b2u_zero_insert2(const void* y, void* x, int N, int H, int W, int C, void* stream);
+/* nn.MaxPool2d(3, 2, padding=0, ceil_mode=True) (nets/resnet.py:113); H, W = input dims */
+int b2u_maxpool3x3s2_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream);
+int b2u_maxpool3x3s2_bwd(const void* dy, const void* x, void* dx, int N, int H, int W, int C, void* stream);
+/* out = a + b over n bf16 elements (gradient accumulation at tensors with two consumers) */
+int b2u_add_bf16(const void* a, const void* b, void* out, long long n, void* stream);
 
 /* ---- classifier head (nn.Conv2d(64, num_classes, 1), nets/unet.py:58,76) ------------------------------------ */
 int b2u_head_fwd(const void* x, const float* w, const float* b, float* logits_nchw, int N, int H, int W, int Cin,

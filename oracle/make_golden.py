@@ -91,6 +91,35 @@ def traditional_case(tag, num_classes, n, h, w, seed, cls_w, dice, focal):
     print("traditional", tag, "loss", loss.item())
 
 
+def resnet_case(tag, num_classes, n, h, w, seed, cls_w, dice):
+    sd = O.make_resnet_unet_params(num_classes, seed=11)
+    model = RefUnet(num_classes=num_classes, pretrained=False, backbone="resnet50")
+    model.load_state_dict(sd)
+    model.train()
+    imgs, pngs = O.make_inputs(n, num_classes, h, w, seed=seed)
+    labels = torch.eye(num_classes + 1)[pngs]
+    weights = torch.tensor(cls_w, dtype=torch.float32)
+    out = model(imgs)
+    loss = CE_Loss(out, pngs, weights, num_classes=num_classes)
+    if dice:
+        loss = loss + Dice_loss(out, labels)
+    loss.backward()
+    rec = {"logits": out.detach().numpy().astype(np.float32), "loss": np.float64(loss.item()),
+           "cls_w": np.asarray(cls_w, np.float32), "meta": np.asarray([num_classes, n, h, w, seed, int(dice)])}
+    for name, p in model.named_parameters():
+        g = p.grad.detach().reshape(-1)
+        rec["gnorm:" + name] = np.float64(g.double().norm().item())
+        rec["g:" + name] = (g if g.numel() <= 1024 else g[torch.linspace(0, g.numel() - 1, 1024).long()]).numpy().astype(np.float32)
+    for name, b in model.named_buffers():
+        if name.endswith("running_mean") and (".bn3" in name or name == "resnet.bn1.running_mean"):
+            rec["buf:" + name] = b.detach().numpy()
+    model.eval()
+    with torch.no_grad():
+        rec["logits_eval"] = model(imgs).numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, f"unet_resnet50_{tag}.npz"), **rec)
+    print("resnet50", tag, "loss", loss.item())
+
+
 def loss_case():
     g = torch.Generator().manual_seed(7)
     rec = {}
@@ -147,5 +176,7 @@ if __name__ == "__main__":
     # TraditionalUnet_Train.py settings: focal loss, class weights [1,15,...] (lines 236, 245); and plain CE + Dice
     traditional_case("nc4_focaldice", 4, 2, 64, 64, 3, [1, 15, 1.5, 2], dice=True, focal=True)
     traditional_case("nc21_cedice", 21, 2, 32, 64, 4, [1] * 21, dice=True, focal=False)
+    # BASELINE configs[2]: Unet-ResNet50, 21 classes, CE + Dice (batch >= 2 because of BatchNorm, train.py:139-140)
+    resnet_case("nc21_cedice", 21, 2, 64, 64, 7, [1] * 21, dice=True)
     loss_case()
     hist_case()

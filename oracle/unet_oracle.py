@@ -381,3 +381,147 @@ def trad_train_step(sd, imgs, pngs, cls_weights, num_classes, dice=True, focal=F
     names = [k for k, v in p.items() if v.requires_grad]
     grads = torch.autograd.grad(loss, [p[k] for k in names])
     return loss.detach(), logits.detach(), dict(zip(names, grads)), stats
+
+
+# ----------------------------------------------------------------------------------------------- Unet-ResNet50
+RESNET_LAYERS = [(64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)]     # planes, blocks, stride (nets/resnet.py:115-121)
+
+
+def resnet_unet_param_shapes(num_classes):
+    """Parameters of Unet(backbone='resnet50') in state_dict order (181 tensors, 43,934,101 elements at 21 classes)."""
+    sh = {"resnet.conv1.weight": (64, 3, 7, 7), "resnet.bn1.weight": (64,), "resnet.bn1.bias": (64,)}
+    inpl = 64
+    for li, (planes, blocks, stride) in enumerate(RESNET_LAYERS, start=1):
+        for b in range(blocks):
+            p = f"resnet.layer{li}.{b}"
+            sh[p + ".conv1.weight"] = (planes, inpl, 1, 1)
+            sh[p + ".bn1.weight"] = (planes,); sh[p + ".bn1.bias"] = (planes,)
+            sh[p + ".conv2.weight"] = (planes, planes, 3, 3)
+            sh[p + ".bn2.weight"] = (planes,); sh[p + ".bn2.bias"] = (planes,)
+            sh[p + ".conv3.weight"] = (planes * 4, planes, 1, 1)
+            sh[p + ".bn3.weight"] = (planes * 4,); sh[p + ".bn3.bias"] = (planes * 4,)
+            if b == 0:
+                sh[p + ".downsample.0.weight"] = (planes * 4, inpl, 1, 1)
+                sh[p + ".downsample.1.weight"] = (planes * 4,); sh[p + ".downsample.1.bias"] = (planes * 4,)
+            inpl = planes * 4
+    in_filters, out_filters = [192, 512, 1024, 3072], [64, 128, 256, 512]      # nets/unet.py:31-35
+    for k in (4, 3, 2, 1):
+        sh[f"up_concat{k}.conv1.weight"] = (out_filters[k - 1], in_filters[k - 1], 3, 3)
+        sh[f"up_concat{k}.conv1.bias"] = (out_filters[k - 1],)
+        sh[f"up_concat{k}.conv2.weight"] = (out_filters[k - 1], out_filters[k - 1], 3, 3)
+        sh[f"up_concat{k}.conv2.bias"] = (out_filters[k - 1],)
+    for i in (1, 3):
+        sh[f"up_conv.{i}.weight"] = (64, 64, 3, 3); sh[f"up_conv.{i}.bias"] = (64,)
+    sh["final.weight"] = (num_classes, 64, 1, 1); sh["final.bias"] = (num_classes,)
+    return sh
+
+
+def make_resnet_unet_params(num_classes, seed=11, gain=1.0, dec_gain=0.5):
+    """Deterministic synthetic state_dict: encoder convs He-scaled (BatchNorm follows), BN weight 1 + 0.1 N, bias 0.05 N,
+    decoder convs at the default-init scale (gain 0.5), fresh running statistics."""
+    sd = {}
+    for k, (name, shape) in enumerate(resnet_unet_param_shapes(num_classes).items()):
+        g = torch.Generator().manual_seed(seed * 1000 + 2000 + k)
+        if len(shape) == 4:
+            fan_in = shape[1] * shape[2] * shape[3]
+            gn = gain if name.startswith("resnet.") else dec_gain
+            sd[name] = torch.randn(shape, generator=g) * (gn * (2.0 / fan_in) ** 0.5)
+        elif name.startswith("resnet.") and name.endswith(".weight"):
+            sd[name] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        else:
+            sd[name] = 0.05 * torch.randn(shape, generator=g)
+    for name, shape in list(resnet_unet_param_shapes(num_classes).items()):
+        if name.startswith("resnet.") and len(shape) == 1 and name.endswith(".weight"):
+            base = name[:-len(".weight")]
+            sd[base + ".running_mean"] = torch.zeros(shape)
+            sd[base + ".running_var"] = torch.ones(shape)
+            sd[base + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+    return sd
+
+
+def _rn_bn(sd, stats, name, z, training, relu, res=None, bf16=False):
+    y = F.batch_norm(z, stats[name + ".running_mean"], stats[name + ".running_var"], sd[name + ".weight"], sd[name + ".bias"],
+                     training, 0.1, 1e-5)
+    if training:
+        stats[name + ".num_batches_tracked"] = stats[name + ".num_batches_tracked"] + 1
+    if res is not None:
+        y = y + res
+    if relu:
+        y = F.relu(y)
+    return _r(y) if bf16 else y
+
+
+def _rn_conv(sd, name, x, stride=1, padding=0, bias=None, bf16=False):
+    w = sd[name]
+    if bf16:
+        w = w + (w.to(torch.bfloat16).to(w.dtype) - w).detach()
+        x = _r(x, fwd=False)
+    z = F.conv2d(x, w, bias, stride=stride, padding=padding)
+    return _r(z) if bf16 else z
+
+
+def resnet_unet_forward(sd, x, training=True, stats=None, bf16_storage=False):
+    """Unet.forward with backbone='resnet50' (nets/unet.py:62-78, nets/resnet.py:151-176, 77-97)."""
+    b = bf16_storage
+    if stats is None:
+        stats = {k: v.clone() for k, v in sd.items() if "running_" in k or "num_batches" in k}
+    if b:
+        x = _r(x)
+    z = _rn_conv(sd, "resnet.conv1.weight", x, stride=2, padding=3, bf16=b)                         # resnet.py:166
+    feat1 = _rn_bn(sd, stats, "resnet.bn1", z, training, True, bf16=b)
+    x = F.max_pool2d(feat1, kernel_size=3, stride=2, padding=0, ceil_mode=True)                     # resnet.py:113,170
+    feats = [feat1]
+    for li, (planes, blocks, stride) in enumerate(RESNET_LAYERS, start=1):
+        for bi in range(blocks):
+            p = f"resnet.layer{li}.{bi}"
+            s = stride if bi == 0 else 1
+            out = _rn_bn(sd, stats, p + ".bn1", _rn_conv(sd, p + ".conv1.weight", x, bf16=b), training, True, bf16=b)
+            out = _rn_bn(sd, stats, p + ".bn2", _rn_conv(sd, p + ".conv2.weight", out, stride=s, padding=1, bf16=b), training, True, bf16=b)
+            z3 = _rn_conv(sd, p + ".conv3.weight", out, bf16=b)
+            idn = x
+            if bi == 0:
+                idn = _rn_bn(sd, stats, p + ".downsample.1", _rn_conv(sd, p + ".downsample.0.weight", x, stride=s, bf16=b),
+                             training, False, bf16=b)
+            x = _rn_bn(sd, stats, p + ".bn3", z3, training, True, res=idn, bf16=b)                  # resnet.py:89-95
+        feats.append(x)
+
+    def up_stage(name, skip, low):
+        up = F.interpolate(low, scale_factor=2, mode="bilinear", align_corners=True)
+        if b:
+            up = _r(up)
+        y = torch.cat([skip, up], 1)
+        for cv in ("conv1", "conv2"):
+            y = F.relu(_rn_conv(sd, f"{name}.{cv}.weight", y, padding=1, bias=sd[f"{name}.{cv}.bias"], bf16=False) if not b else
+                       F.conv2d(_r(y, fwd=False), sd[f"{name}.{cv}.weight"] + (sd[f"{name}.{cv}.weight"].to(torch.bfloat16).float() - sd[f"{name}.{cv}.weight"]).detach(),
+                                sd[f"{name}.{cv}.bias"], padding=1))
+            if b:
+                y = _r(y)
+        return y
+    up4 = up_stage("up_concat4", feats[3], feats[4])
+    up3 = up_stage("up_concat3", feats[2], up4)
+    up2 = up_stage("up_concat2", feats[1], up3)
+    up1 = up_stage("up_concat1", feats[0], up2)
+    y = F.interpolate(up1, scale_factor=2, mode="bilinear", align_corners=True)                     # up_conv, unet.py:48-54
+    if b:
+        y = _r(y)
+    for i in (1, 3):
+        w = sd[f"up_conv.{i}.weight"]
+        if b:
+            w = w + (w.to(torch.bfloat16).float() - w).detach()
+            y = _r(y, fwd=False)
+        y = F.relu(F.conv2d(y, w, sd[f"up_conv.{i}.bias"], padding=1))
+        if b:
+            y = _r(y)
+    return F.conv2d(y, sd["final.weight"], sd["final.bias"]), stats
+
+
+def resnet_unet_train_step(sd, imgs, pngs, cls_weights, num_classes, dice=True, focal=False, bf16_storage=False):
+    p = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and "running_" not in k else v.clone())
+         for k, v in sd.items()}
+    logits, stats = resnet_unet_forward(p, imgs, training=True, bf16_storage=bf16_storage)
+    loss = focal_loss(logits, pngs, cls_weights, num_classes) if focal else ce_loss(logits, pngs, cls_weights, num_classes)
+    if dice:
+        loss = loss + dice_loss(logits, one_hot(pngs, num_classes))
+    names = [k for k, v in p.items() if v.requires_grad]
+    grads = torch.autograd.grad(loss, [p[k] for k in names])
+    return loss.detach(), logits.detach(), dict(zip(names, grads)), stats

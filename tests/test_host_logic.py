@@ -23,8 +23,24 @@ def test_state_dict_contract(b2u):
 def test_backbone_errors(b2u):
     with pytest.raises(ValueError):
         b2u.Unet(num_classes=2, backbone="mobilenet")          # nets/unet.py:34
-    with pytest.raises(NotImplementedError):
-        b2u.Unet(num_classes=2, backbone="resnet50")
+
+
+def test_resnet50_and_traditional_state_dict_contract(b2u):
+    m = b2u.Unet(num_classes=21, backbone="resnet50")
+    shapes = O.resnet_unet_param_shapes(21)
+    assert [n for n, _ in m.named_parameters()] == list(shapes.keys())
+    assert all(tuple(p.shape) == shapes[n] for n, p in m.named_parameters())
+    assert sum(p.numel() for p in m.parameters()) == 43_934_101
+    assert m.up_conv is not None and hasattr(m, "resnet")
+    m.load_state_dict(O.make_resnet_unet_params(21))
+    m.freeze_backbone()
+    assert all(not p.requires_grad for p in m.resnet.parameters()) and m.final.weight.requires_grad
+    t = b2u.TraditionalUnet(in_channels=3, num_classes=21)
+    assert [n for n, _ in t.named_parameters()] == list(O.trad_param_shapes(21).keys())
+    assert sum(p.numel() for p in t.parameters()) == 1_950_357        # Submit_result figure quoted in BASELINE.md
+    t.load_state_dict(O.make_trad_params(21))
+    t.freeze_encoder()
+    assert not t.inc.double_conv[0].weight.requires_grad and t.outc.weight.requires_grad
 
 
 def test_freeze_unfreeze(b2u):

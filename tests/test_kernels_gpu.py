@@ -300,3 +300,89 @@ def test_batchnorm_kernels(b2u, cuda_device, N, H, W, C, relu):
     ref_e = F.batch_norm(zr.detach(), rm_ref, rv_ref, gamma.detach(), beta.detach(), False, 0.1, 1e-5)
     ref_e = ref_e.relu() if relu else ref_e
     assert rel(nchw(ye), ref_e) <= 6e-3
+
+
+def test_resnet_helper_kernels(b2u, cuda_device):
+    """7x7 stride-2 stem as im2col GEMM (+ its wgrad), stride-2 helpers, ceil-mode 3x3 max-pool fwd/bwd, residual
+    BatchNorm tail, bf16 add -- nets/resnet.py:109-113, 77-97."""
+    ops, dev = b2u.ops, cuda_device
+    g = torch.Generator().manual_seed(9)
+    # stem
+    x = torch.rand(2, 3, 64, 96, generator=g)
+    w = torch.randn(64, 3, 7, 7, generator=g) / 147 ** 0.5
+    col = ops.im2col_stem(x.to(dev))
+    wf = ops.pack_weights_im2col(w.to(dev), 192)
+    z = ops.conv_fprop(col, wf, None, 64, taps=1, relu=False)
+    ref = F.conv2d(x.to(BF).float(), w.to(BF).float(), None, stride=2, padding=3)
+    assert rel(nchw(z), ref) <= 6e-3
+    dz = nhwc(torch.randn(2, 64, 32, 48, generator=g), dev)
+    dw = ops.conv_wgrad_im2col(col, dz, 3, 49)
+    ref_dw = torch.nn.grad.conv2d_weight(x.to(BF).float(), w.shape, nchw(dz), stride=2, padding=3)
+    assert rel(dw, ref_dw) <= 1e-4
+    # stride-2 3x3 conv = stride-1 conv + subsample; its backward through zero_insert
+    xb = nhwc(torch.randn(2, 64, 16, 24, generator=g), dev)
+    full = nchw(xb)
+    sub = ops.subsample2(xb)
+    assert torch.equal(nchw(sub), full[:, :, ::2, ::2])
+    back = ops.zero_insert2(sub, 16, 24)
+    want = torch.zeros_like(full); want[:, :, ::2, ::2] = full[:, :, ::2, ::2]
+    assert torch.equal(nchw(back), want)
+    w3 = torch.randn(128, 64, 3, 3, generator=g) / 24
+    wf3, wd3 = ops.pack_weights(w3.to(dev))
+    y2 = ops.subsample2(ops.conv_fprop(xb, wf3, None, 128, taps=9, relu=False))
+    assert rel(nchw(y2), F.conv2d(full, w3.to(BF).float(), None, stride=2, padding=1)) <= 6e-3
+    # ceil-mode pool, odd and even sizes
+    for (H, W) in ((16, 24), (15, 9), (3, 3)):
+        xp = nhwc(torch.randn(2, 16, H, W, generator=g), dev)
+        xr = nchw(xp).requires_grad_(True)
+        refp = F.max_pool2d(xr, 3, 2, 0, ceil_mode=True)
+        yp = ops.maxpool3x3s2(xp)
+        assert torch.equal(nchw(yp), refp.detach())
+        dyp = nhwc(torch.randn(refp.shape, generator=g), dev)
+        refp.backward(nchw(dyp))
+        assert rel(nchw(ops.maxpool3x3s2_bwd(dyp, xp)), xr.grad) <= 4e-3
+    # add
+    a, b_ = nhwc(torch.randn(2, 64, 8, 8, generator=g), dev), nhwc(torch.randn(2, 64, 8, 8, generator=g), dev)
+    assert rel(ops.add_bf16(a, b_), a.float() + b_.float()) <= 4e-3
+    # residual BatchNorm tail: y = relu(bn(z) + identity)
+    C = 64
+    zt = torch.randn(2, C, 8, 12, generator=g); idn = torch.randn(2, C, 8, 12, generator=g)
+    zb, ib = nhwc(zt, dev), nhwc(idn, dev)
+    zr, ir = nchw(zb).requires_grad_(True), nchw(ib).requires_grad_(True)
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).requires_grad_(True); beta = (0.1 * torch.randn(C, generator=g)).requires_grad_(True)
+    refy = (F.batch_norm(zr, None, None, gamma, beta, True, 0.1, 1e-5) + ir).relu()
+    rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+    y, mean, invstd = ops.bn_fwd_train(zb, gamma.detach().to(dev), beta.detach().to(dev), rm, rv, relu=True, residual=ib)
+    assert rel(nchw(y), refy.detach()) <= 6e-3
+    dy = nhwc(torch.randn(2, C, 8, 12, generator=g), dev)
+    refy.backward(nchw(dy))
+    gout = torch.empty_like(zb)
+    dzb, dgam, dbet = ops.bn_bwd(dy, y, zb, gamma.detach().to(dev), mean, invstd, relu=True, gout=gout)
+    assert rel(nchw(dzb), zr.grad) <= 1e-2 and rel(nchw(gout), ir.grad) <= 6e-3
+    assert rel(dgam, gamma.grad) <= 3e-3 and rel(dbet, beta.grad) <= 3e-3
+
+
+def test_conv_large_channel_counts(b2u, cuda_device):
+    """ResNet50 decoder shapes: 3072 -> 512 over a virtual concat (1024 | 2048), 1x1 2048-wide GEMMs."""
+    ops, dev = b2u.ops, cuda_device
+    g = torch.Generator().manual_seed(10)
+    x0 = nhwc(torch.randn(1, 1024, 8, 8, generator=g), dev); x1 = nhwc(torch.randn(1, 2048, 8, 8, generator=g), dev)
+    w = torch.randn(512, 3072, 3, 3, generator=g) / (3072 * 9) ** 0.5
+    b = torch.randn(512, generator=g)
+    wf, wd = ops.pack_weights(w.to(dev))
+    y = ops.conv_fprop(x0, wf, b.to(dev), 512, taps=9, relu=True, x1=x1)
+    xr = torch.cat([nchw(x0), nchw(x1)], 1)
+    assert rel(nchw(y), F.conv2d(xr, w.to(BF).float(), b, padding=1).relu()) <= 6e-3
+    dz = nhwc(torch.randn(1, 512, 8, 8, generator=g), dev)
+    d0, d1 = ops.conv_dgrad(dz, wd, 1024, taps=9, C1=2048)
+    ref_dx = F.conv_transpose2d(nchw(dz), w.to(BF).float(), padding=1)
+    assert rel(torch.cat([nchw(d0), nchw(d1)], 1), ref_dx) <= 6e-3
+    assert rel(ops.conv_wgrad(x0, dz, taps=9, x1=x1), torch.nn.grad.conv2d_weight(xr, w.shape, nchw(dz), padding=1)) <= 1e-4
+    w1 = torch.randn(2048, 512, 1, 1, generator=g) / 512 ** 0.5
+    wf1, wd1 = ops.pack_weights(w1.to(dev))
+    xs = nhwc(torch.randn(2, 512, 8, 8, generator=g), dev)
+    y1 = ops.conv_fprop(xs, wf1, None, 2048, taps=1, relu=False)
+    assert rel(nchw(y1), F.conv2d(nchw(xs), w1.to(BF).float())) <= 6e-3
+    dz1 = nhwc(torch.randn(2, 2048, 8, 8, generator=g), dev)
+    assert rel(nchw(ops.conv_dgrad(dz1, wd1, 512, taps=1)), F.conv_transpose2d(nchw(dz1), w1.to(BF).float())) <= 6e-3
+    assert rel(ops.conv_wgrad(xs, dz1, taps=1), torch.nn.grad.conv2d_weight(nchw(xs), w1.shape, nchw(dz1))) <= 1e-4

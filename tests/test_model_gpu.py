@@ -288,3 +288,74 @@ def test_traditional_trainer_step(b2u, cuda_device):
     tr3 = b2u.UnetTrainer(num_classes=C, device=dev, state_dict=sd, lr=1e-3, model="traditional")
     losses = [tr3.train_step(imgs.to(dev), pngs.to(dev))[0].item() for _ in range(8)]
     assert losses[-1] < losses[0]
+
+
+# ------------------------------------------------------------------------------------------------ Unet-ResNet50
+def test_resnet50_unet_dropin(b2u, cuda_device, golden_dir):
+    """BASELINE configs[2]: Unet(backbone='resnet50'), train-mode BatchNorm, CE + Dice.  Same yardstick policy as
+    TraditionalUnet (BatchNorm nets amplify bf16 storage rounding in the gradients); forward quantities are tight."""
+    dev = cuda_device
+    C, n, h, w, seed = 21, 2, 64, 64, 7
+    sd = O.make_resnet_unet_params(C, seed=11)
+    imgs, pngs = O.make_inputs(n, C, h, w, seed=seed)
+    weights = torch.ones(C)
+    l32, z32, g32, s32 = O.resnet_unet_train_step(sd, imgs, pngs, weights, C, dice=True)
+    lbf, zbf, gbf, sbf = O.resnet_unet_train_step(sd, imgs, pngs, weights, C, dice=True, bf16_storage=True)
+    model = b2u.Unet(num_classes=C, pretrained=False, backbone="resnet50")
+    model.load_state_dict(sd)
+    model = model.train().to(dev)
+    outputs = model(imgs.to(dev))
+    loss = b2u.CE_Loss(outputs, pngs.to(dev), weights.to(dev), num_classes=C) + b2u.Dice_loss(outputs, O.one_hot(pngs, C).to(dev))
+    loss.backward()
+    noise_z, noise_g = rel(zbf, z32), _global_rel(gbf, g32)
+    assert outputs.shape == z32.shape
+    assert rel(outputs, z32) <= max(1.5 * noise_z, 1e-2)
+    assert abs(loss.item() - l32.item()) <= 1e-2 * abs(l32.item())
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    assert all(v is not None and torch.isfinite(v).all() for v in grads.values())
+    assert _global_rel(grads, g32) <= 1.5 * noise_g and _global_rel(grads, gbf) <= 1.2 * noise_g
+    # decoder-side tensors are not behind a BatchNorm backward: plain bf16 accuracy
+    for k in ("final.weight", "final.bias", "up_conv.3.weight", "up_conv.1.weight", "up_concat1.conv2.weight"):
+        assert rel(grads[k], g32[k]) <= 2e-2, k
+    for name, b in model.named_buffers():
+        # statistics of bf16 activations ~50 layers deep: the per-channel means are small against the activations' spread
+        if name.endswith("running_mean"):
+            assert rel(b, s32[name]) <= 6e-2, name
+        elif name.endswith("running_var"):
+            assert rel(b, s32[name]) <= 1e-2, name
+    g = np.load(os.path.join(golden_dir, "unet_resnet50_nc21_cedice.npz"))
+    assert rel(outputs, torch.from_numpy(g["logits"])) <= max(1.5 * noise_z, 1e-2)
+    assert abs(loss.item() - float(g["loss"])) <= 1e-2 * abs(float(g["loss"]))
+    model.eval()
+    with torch.no_grad():
+        ev = model(imgs.to(dev))
+    sd_after = dict(sd); sd_after.update({k: v.cpu() for k, v in model.named_buffers()})
+    with torch.no_grad():
+        ev_ref, _ = O.resnet_unet_forward(sd_after, imgs, training=False)
+    assert rel(ev, ev_ref) <= 2e-2
+
+
+def test_resnet50_frozen_backbone_and_trainer(b2u, cuda_device):
+    dev = cuda_device
+    C = 4
+    sd = O.make_resnet_unet_params(C, seed=11)
+    imgs, pngs = O.make_inputs(2, C, 64, 64, seed=8)
+    l32, z32, g32, _ = O.resnet_unet_train_step(sd, imgs, pngs, torch.ones(C), C, dice=True)
+    lbf, zbf, gbf, _ = O.resnet_unet_train_step(sd, imgs, pngs, torch.ones(C), C, dice=True, bf16_storage=True)
+    model = b2u.Unet(num_classes=C, backbone="resnet50")
+    model.load_state_dict(sd)
+    model = model.to(dev).train()
+    model.freeze_backbone()
+    out = model(imgs.to(dev))
+    loss = b2u.CE_Loss(out, pngs.to(dev), torch.ones(C, device=dev), num_classes=C) + b2u.Dice_loss(out, O.one_hot(pngs, C).to(dev))
+    loss.backward()
+    dec = {k: p.grad for k, p in model.named_parameters() if not k.startswith("resnet.")}
+    assert all(p.grad is None for k, p in model.named_parameters() if k.startswith("resnet."))
+    assert _global_rel(dec, {k: g32[k] for k in dec}) <= 2e-2          # decoder gradients do not cross a BatchNorm backward
+    tr = b2u.UnetTrainer(num_classes=C, device=dev, state_dict=sd, lr=0.0, model="unet_resnet50")
+    o = tr.train_step(imgs.to(dev), pngs.to(dev)).cpu()
+    assert abs(o[0].item() - l32.item()) <= 1e-2 * abs(l32.item())
+    assert _global_rel(tr.grads, g32) <= 1.5 * _global_rel(gbf, g32)
+    tr3 = b2u.UnetTrainer(num_classes=C, device=dev, state_dict=sd, lr=1e-3, model="unet_resnet50")
+    losses = [tr3.train_step(imgs.to(dev), pngs.to(dev))[0].item() for _ in range(6)]
+    assert losses[-1] < losses[0]

@@ -129,3 +129,27 @@ def test_traditional_unet_matches_reference_golden(tag, golden_dir):
         ev, _ = O.trad_forward(sd_after, imgs, training=False)
     ref_ev = torch.from_numpy(g["logits_eval"])
     assert ((ev - ref_ev).norm() / ref_ev.norm()).item() <= 1e-5
+
+
+def test_resnet50_unet_matches_reference_golden(golden_dir):
+    """Unet(backbone='resnet50') restatement (bottlenecks, BatchNorm, ceil-mode pool, up_conv) against the reference."""
+    g = np.load(os.path.join(golden_dir, "unet_resnet50_nc21_cedice.npz"))
+    C, n, h, w, seed, dice = [int(v) for v in g["meta"]]
+    sd = O.make_resnet_unet_params(C, seed=11)
+    assert sum(v.numel() for k, v in O.resnet_unet_param_shapes(21).items() for v in [torch.empty(v)]) == 43_934_101
+    imgs, pngs = O.make_inputs(n, C, h, w, seed=seed)
+    loss, logits, grads, stats = O.resnet_unet_train_step(sd, imgs, pngs, torch.from_numpy(g["cls_w"]), C, dice=bool(dice))
+    ref = torch.from_numpy(g["logits"])
+    assert ((logits - ref).norm() / ref.norm()).item() <= 1e-5
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    for name, gr in grads.items():
+        gn = float(g["gnorm:" + name])
+        assert abs(gr.double().norm().item() - gn) <= 5e-4 * gn + 1e-9, name
+    for key in g.files:
+        if key.startswith("buf:"):
+            assert torch.allclose(stats[key[4:]], torch.from_numpy(g[key]), rtol=1e-5, atol=1e-6), key
+    sd_after = dict(sd); sd_after.update(stats)
+    with torch.no_grad():
+        ev, _ = O.resnet_unet_forward(sd_after, imgs, training=False)
+    ref_ev = torch.from_numpy(g["logits_eval"])
+    assert ((ev - ref_ev).norm() / ref_ev.norm()).item() <= 1e-5

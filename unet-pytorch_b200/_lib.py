@@ -32,9 +32,17 @@ SIGNATURES = {
     "b2u_upsample2x_fwd": (I, [P, P, I, I, I, I, P]),
     "b2u_upsample2x_bwd": (I, [P, P, P, I, I, I, I, P]),
     "b2u_bn_workspace": (SZ, [I]),
-    "b2u_bn_fwd_train": (I, [P, P, P, P, P, P, P, P, P, SZ, LL, I, F, F, I, P]),
-    "b2u_bn_fwd_eval": (I, [P, P, P, P, P, P, P, SZ, LL, I, F, I, P]),
-    "b2u_bn_bwd": (I, [P, P, P, P, P, P, P, P, P, P, SZ, LL, I, I, P]),
+    "b2u_bn_fwd_train": (I, [P, P, P, P, P, P, P, P, P, P, SZ, LL, I, F, F, I, P]),
+    "b2u_bn_fwd_eval": (I, [P, P, P, P, P, P, P, P, SZ, LL, I, F, I, P]),
+    "b2u_bn_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, SZ, LL, I, I, P]),
+    "b2u_im2col_stem": (I, [P, P, I, I, I, I, P]),
+    "b2u_pack_weights_im2col": (I, [P, P, I, I, I, I, P]),
+    "b2u_conv_wgrad_im2col": (I, [P, I, P, I, P, P, SZ, I, I, I, I, I, P]),
+    "b2u_subsample2": (I, [P, P, I, I, I, I, P]),
+    "b2u_zero_insert2": (I, [P, P, I, I, I, I, P]),
+    "b2u_maxpool3x3s2_fwd": (I, [P, P, I, I, I, I, P]),
+    "b2u_maxpool3x3s2_bwd": (I, [P, P, P, I, I, I, I, P]),
+    "b2u_add_bf16": (I, [P, P, P, LL, P]),
     "b2u_head_fwd": (I, [P, P, P, P, I, I, I, I, I, P]),
     "b2u_head_bwd_workspace": (SZ, []),
     "b2u_head_bwd": (I, [P, P, P, P, P, P, P, SZ, I, I, I, I, I, I, P]),

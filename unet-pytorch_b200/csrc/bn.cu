@@ -133,16 +133,18 @@ __global__ void bn_eval_coeff_kernel(const float* __restrict__ gamma, const floa
 }
 
 // y = [relu](z * scale + shift); one thread per (row, 8-channel chunk) through the row-indexed grid
-__global__ void bn_apply_kernel(const uint4* __restrict__ z, uint4* __restrict__ y, const float* __restrict__ scale,
-                                const float* __restrict__ shift, long long total, int C8, int relu) {
+__global__ void bn_apply_kernel(const uint4* __restrict__ z, const uint4* __restrict__ res, uint4* __restrict__ y,
+                                const float* __restrict__ scale, const float* __restrict__ shift, long long total, int C8,
+                                int relu) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c = static_cast<int>(static_cast<unsigned>(i) % static_cast<unsigned>(C8));   // host guarantees total < 2^31
-  float f[8];
+  float f[8], rs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   bn_unpack8(__ldg(z + i), f);
+  if (res) bn_unpack8(__ldg(res + i), rs);          // residual branch of a bottleneck: y = relu(bn(z) + identity)
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    float v = fmaf(f[k], __ldg(scale + c * 8 + k), __ldg(shift + c * 8 + k));
+    float v = fmaf(f[k], __ldg(scale + c * 8 + k), __ldg(shift + c * 8 + k)) + rs[k];
     f[k] = relu ? fmaxf(v, 0.f) : v;
   }
   y[i] = bn_pack8(f);
@@ -170,12 +172,13 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int bl
 // dz = a (g - b - xhat c)
 __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, const uint4* __restrict__ z,
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
-                                    const float* __restrict__ coef, uint4* __restrict__ dz, long long total, int C8, int relu) {
+                                    const float* __restrict__ coef, uint4* __restrict__ dz, uint4* __restrict__ gout,
+                                    long long total, int C8, int relu) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c = static_cast<int>(static_cast<unsigned>(i) % static_cast<unsigned>(C8));
   const int C = C8 * 8;
-  float g[8], yy[8], zz[8], o[8];
+  float g[8], yy[8], zz[8], o[8], gm[8];
   bn_unpack8(__ldg(dy + i), g);
   bn_unpack8(__ldg(z + i), zz);
   if (relu) bn_unpack8(__ldg(y + i), yy);
@@ -185,7 +188,9 @@ __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* _
     const float gg = (!relu || yy[k] > 0.f) ? g[k] : 0.f;
     const float xhat = (zz[k] - __ldg(mean + ch)) * __ldg(invstd + ch);
     o[k] = __ldg(coef + ch) * (gg - __ldg(coef + C + ch) - xhat * __ldg(coef + 2 * C + ch));
+    gm[k] = gg;
   }
+  if (gout) gout[i] = bn_pack8(gm);      // ReLU-masked dy: the gradient of the residual (identity) branch
   dz[i] = bn_pack8(o);
 }
 
@@ -204,7 +209,7 @@ static int bn_check(long long P, int C, const void* ws, size_t ws_bytes, const c
   return 0;
 }
 
-int b2u_bn_fwd_train(const void* z, void* y, const float* gamma, const float* beta, float* running_mean,
+int b2u_bn_fwd_train(const void* z, const void* residual, void* y, const float* gamma, const float* beta, float* running_mean,
                      float* running_var, float* save_mean, float* save_invstd, void* ws, size_t ws_bytes, long long P,
                      int C, float eps, float momentum, int relu, void* stream) {
   int rc = bn_check(P, C, ws, ws_bytes, "bn_fwd_train");
@@ -219,13 +224,13 @@ int b2u_bn_fwd_train(const void* z, void* y, const float* gamma, const float* be
                                                           save_mean, save_invstd, coef, coef + C, eps, momentum);
   B2U_CHECK_LAUNCH("bn_fwd_finalize");
   const long long total = P * (C / 8);
-  bn_apply_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(static_cast<const uint4*>(z), static_cast<uint4*>(y),
-                                                                             coef, coef + C, total, C / 8, relu);
+  bn_apply_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(static_cast<const uint4*>(z), static_cast<const uint4*>(residual),
+                                                                             static_cast<uint4*>(y), coef, coef + C, total, C / 8, relu);
   B2U_CHECK_LAUNCH("bn_apply");
   return 0;
 }
 
-int b2u_bn_fwd_eval(const void* z, void* y, const float* gamma, const float* beta, const float* running_mean,
+int b2u_bn_fwd_eval(const void* z, const void* residual, void* y, const float* gamma, const float* beta, const float* running_mean,
                     const float* running_var, void* ws, size_t ws_bytes, long long P, int C, float eps, int relu,
                     void* stream) {
   int rc = bn_check(P, C, ws, ws_bytes, "bn_fwd_eval");
@@ -236,16 +241,17 @@ int b2u_bn_fwd_eval(const void* z, void* y, const float* gamma, const float* bet
   bn_eval_coeff_kernel<<<(C + 127) / 128, 128, 0, st>>>(gamma, beta, running_mean, running_var, coef, coef + C, C, eps);
   B2U_CHECK_LAUNCH("bn_eval_coeff");
   const long long total = P * (C / 8);
-  bn_apply_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(static_cast<const uint4*>(z), static_cast<uint4*>(y),
-                                                                             coef, coef + C, total, C / 8, relu);
+  bn_apply_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(static_cast<const uint4*>(z), static_cast<const uint4*>(residual),
+                                                                             static_cast<uint4*>(y), coef, coef + C, total, C / 8, relu);
   B2U_CHECK_LAUNCH("bn_apply");
   return 0;
 }
 
-// dy: gradient wrt the BN(+ReLU) output y; dz (may alias dy) = gradient wrt the BN input z
+// dy: gradient wrt y = [relu](bn(z) [+ residual]); dz (may alias dy) = gradient wrt the BN input z; gout (nullable,
+// must not alias dy/dz) = dy masked by the ReLU = gradient wrt the residual input
 int b2u_bn_bwd(const void* dy, const void* y, const void* z, const float* gamma, const float* save_mean,
-               const float* save_invstd, void* dz, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, long long P,
-               int C, int relu, void* stream) {
+               const float* save_invstd, void* dz, void* gout, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
+               long long P, int C, int relu, void* stream) {
   int rc = bn_check(P, C, ws, ws_bytes, "bn_bwd");
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -260,7 +266,7 @@ int b2u_bn_bwd(const void* dy, const void* y, const void* z, const float* gamma,
   const long long total = P * (C / 8);
   bn_bwd_apply_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
       static_cast<const uint4*>(dy), static_cast<const uint4*>(y), static_cast<const uint4*>(z), save_mean, save_invstd, coef,
-      static_cast<uint4*>(dz), total, C / 8, relu);
+      static_cast<uint4*>(dz), static_cast<uint4*>(gout), total, C / 8, relu);
   B2U_CHECK_LAUNCH("bn_bwd_apply");
   return 0;
 }

@@ -30,7 +30,6 @@ namespace b2u {
 constexpr int kWb = 16;   // patch width  (pixels)
 constexpr int kHb = 8;    // patch height (pixels)
 constexpr int kTileM = kWb * kHb;
-constexpr int kMaxCout = 1024;
 constexpr int KB = 64;    // channels per K block = one 128-byte swizzle row
 
 struct ConvParams {
@@ -60,7 +59,7 @@ struct ConvCfg {
   static constexpr int kOffB = kOffA + SA * kABytes;
   static constexpr int kOffStage = kOffB + SB * kBBytes;
   static constexpr int kOffBias = kOffStage + 2 * kStageBytes;
-  static constexpr int kOffBar = kOffBias + kMaxCout * 4;
+  static constexpr int kOffBar = kOffBias + 2 * 256 * 4;     // bias of the current N tile, double buffered by tile parity
   static constexpr int kNumBar = 2 * SA + 2 * SB + 4;
   static constexpr int kOffTmem = kOffBar + kNumBar * 8;
   static constexpr int kSmemBytes = kOffTmem + 16 + 1024;  // + alignment slack
@@ -118,7 +117,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) sBias[i] = p.bias ? p.bias[i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -221,6 +219,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     int as = 0;
     uint32_t pacc = 0;
     uint32_t sbuf = 0;
+    uint32_t bpar = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.num_n_tiles;
       int m_tile = tile / p.num_n_tiles;
@@ -243,6 +242,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         for (int q = 0; q < 8; ++q) mreg[q] = inb_ ? __ldg(mrow + q) : make_uint4(0, 0, 0, 0);
       };
       if (p.flags & 2) fetch_mask(0);
+      // this tile's bias slice; the parity double buffer + the barrier keep a fast warp from overwriting values a
+      // slow warp of the previous tile still reads
+      float* sB = sBias + bpar * 256;
+      for (int c = threadIdx.x - 64; c < BN; c += 128) sB[c] = p.bias ? __ldg(p.bias + n0 + c) : 0.f;
+      named_bar_sync(2, 128);
+      bpar ^= 1u;
 
       mbar_wait(t_full(as), pacc);
       tc_fence_after();
@@ -269,8 +274,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             const uint32_t mm[4] = {mreg[q].x, mreg[q].y, mreg[q].z, mreg[q].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float lo = __uint_as_float(v[q * 8 + 2 * e]) + sBias[cbase + q * 8 + 2 * e];
-              float hi = __uint_as_float(v[q * 8 + 2 * e + 1]) + sBias[cbase + q * 8 + 2 * e + 1];
+              float lo = __uint_as_float(v[q * 8 + 2 * e]) + sB[j * 64 + q * 8 + 2 * e];
+              float hi = __uint_as_float(v[q * 8 + 2 * e + 1]) + sB[j * 64 + q * 8 + 2 * e + 1];
               lo = bf16_lo(mm[e]) > 0.f ? lo : 0.f;
               hi = bf16_hi(mm[e]) > 0.f ? hi : 0.f;
               packed[q * 4 + e] = pack_bf16x2(lo, hi);
@@ -281,8 +286,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           const bool relu = p.flags & 1;
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
-            float lo = __uint_as_float(v[2 * e]) + sBias[cbase + 2 * e];
-            float hi = __uint_as_float(v[2 * e + 1]) + sBias[cbase + 2 * e + 1];
+            float lo = __uint_as_float(v[2 * e]) + sB[j * 64 + 2 * e];
+            float hi = __uint_as_float(v[2 * e + 1]) + sB[j * 64 + 2 * e + 1];
             if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
             packed[e] = pack_bf16x2(lo, hi);
           }
@@ -380,7 +385,7 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st) {
   const int ctot = a.C0 + a.C1;
   if (a.N <= 0 || a.H <= 0 || a.W <= 0) return set_error(B2U_ERR_SHAPE, "conv: empty tensor");
   if (a.taps != 9 && a.taps != 1) return set_error(B2U_ERR_SHAPE, "conv: taps must be 9 or 1");
-  if (a.Cout > kMaxCout || a.Cout <= 0) return set_error(B2U_ERR_SHAPE, "conv: Cout %d outside (0,%d]", a.Cout, kMaxCout);
+  if (a.Cout <= 0) return set_error(B2U_ERR_SHAPE, "conv: Cout %d must be positive", a.Cout);
   if (a.Cout % 64 != 0) return set_error(B2U_ERR_SHAPE, "conv: Cout %d must be a multiple of 64", a.Cout);
   if ((a.flags & 2) && (a.mask == nullptr || a.mask_c % 8 != 0 || a.mask_c < a.Cout))
     return set_error(B2U_ERR_SHAPE, "conv: mask flag needs a mask tensor with >= Cout channels, %% 8 == 0");

@@ -451,4 +451,25 @@ int b2u_conv_wgrad(const void* x0, int C0, const void* x1, int C1, const void* d
   return 0;
 }
 
+// wgrad of a conv that ran as a 1x1 GEMM over im2col rows (first VGG layer: Kpad 64, 3x3; ResNet stem: Kpad 192, 7x7):
+// dw[co][c][tap] = partial column tap*cin + c
+int b2u_conv_wgrad_im2col(const void* x0, int Kpad, const void* dz, int Cout, float* dw, void* ws, size_t ws_bytes, int N,
+                          int H, int W, int cin, int taps, void* stream) {
+  using namespace b2u;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (N <= 0 || H <= 0 || W <= 0) return set_error(B2U_ERR_SHAPE, "wgrad_im2col: empty tensor");
+  if (Kpad % 64 != 0 || cin <= 0 || taps <= 0 || cin * taps > Kpad) return set_error(B2U_ERR_SHAPE, "wgrad_im2col: bad K layout");
+  if (Cout != 64 && Cout % 128 != 0) return set_error(B2U_ERR_SHAPE, "wgrad_im2col: Cout %d must be 64 or a multiple of 128", Cout);
+  const WgradPlan pl = plan_wgrad(N, H, W, Kpad, Cout, 1);
+  if (ws == nullptr || ws_bytes < pl.ws_bytes) return set_error(B2U_ERR_ARG, "wgrad_im2col: workspace too small");
+  int rc = launch_wgrad_cfg<1, 4>(x0, Kpad, nullptr, 0, dz, Cout, static_cast<float*>(ws), nullptr, pl, N, H, W, 1, st);
+  if (rc) return rc;
+  const int total = Cout * cin * taps;
+  wgrad_reduce_kernel<<<(total + 63) / 64, 256, 0, st>>>(static_cast<const float*>(ws), dw, pl.splits, Cout, taps, Kpad, cin, 1);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(B2U_ERR_CUDA, "wgrad_reduce launch: %s", cudaGetErrorString(e));
+  note_launch();
+  return 0;
+}
+
 }  // extern "C"

@@ -285,9 +285,10 @@ class UNetEngine:
         return out
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x, params, save=True, training=None):
+    def forward(self, x, params, save=True, training=None, trainable=None):
         """x: NCHW fp32 CUDA [N, Cin, H, W] -> logits NCHW fp32.  training (BN nets): batch statistics + running-stat
-        update (default: same as `save`)."""
+        update (default: same as `save`).  trainable is accepted for interface parity with GraphEngine (backward decides
+        what to skip from the gradient names it is given)."""
         if not x.is_cuda:
             raise ValueError("UNetEngine.forward: input must be a CUDA tensor (no CPU fallback)")
         if x.dtype != torch.float32:

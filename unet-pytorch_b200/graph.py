@@ -1,0 +1,427 @@
+"""Static-program executor for the networks that are not a plain conv chain: the ResNet50-backbone Unet
+(nets/unet.py:24-78 with backbone='resnet50' + nets/resnet.py:55-176 of the reference).
+
+A network is a list of instructions over named tensors (NHWC bf16, channels multiples of 64).  forward() interprets
+the list and keeps what backward needs; backward() walks it in reverse, accumulating gradients at tensors that have
+several consumers (residual identities, skip connections) with the add kernel.  Every instruction maps to kernels
+of libb200unet.so:
+
+  stem      7x7 stride-2 conv as im2col rows (K = 147 -> 192) + 1x1 tensor-core GEMM           nets/resnet.py:109
+  conv      1x1 / 3x3, stride 1 or 2 (3x3 s2 = stride-1 conv -> keep even pixels; 1x1 s2 = keep even pixels -> conv),
+            bias-free (encoder) or bias + fused ReLU (decoder), optional second source (virtual concat)
+  bn        BatchNorm (+ residual add) (+ ReLU), train or eval                                  nets/resnet.py:77-97
+  pool3     MaxPool2d(3, 2, 0, ceil_mode=True)                                                  nets/resnet.py:113
+  up        UpsamplingBilinear2d(2)                                                             nets/unet.py:13,49
+  head      final 1x1 conv -> logits NCHW fp32                                                  nets/unet.py:58,76
+
+ReLU handling: a tensor produced by a conv with fused ReLU is marked `fused_relu`; whoever sends a gradient to it
+applies the mask (y > 0) on the way (dgrad epilogue / upsample adjoint / head dgrad), so its gradient is always wrt
+the pre-activation.  BatchNorm outputs are plain: the bn instruction's own backward applies its ReLU mask.
+"""
+import struct
+
+import torch
+
+from . import ops
+
+
+class _T:
+    __slots__ = ("data", "grad", "fused_relu", "needs_grad", "aux")
+
+    def __init__(self, data, fused_relu=False, needs_grad=False):
+        self.data, self.grad, self.fused_relu, self.needs_grad, self.aux = data, None, fused_relu, needs_grad, None
+
+
+def resnet50_unet_program(num_classes):
+    """Instruction list + conv table of Unet(backbone='resnet50')."""
+    P = []
+    convs = {}       # weight name -> (cout, cin, taps)
+
+    def conv(out, x, w, cin, cout, taps, stride=1, bias=None, relu=False, x1=None, c1=0):
+        convs[w] = (cout, cin + c1, taps)
+        P.append(dict(op="conv", out=out, x=x, x1=x1, w=w, bias=bias, cin=cin, c1=c1, cout=cout, taps=taps, stride=stride,
+                      relu=relu))
+
+    def bn(out, z, name, c, relu=True, res=None):
+        P.append(dict(op="bn", out=out, z=z, bn=name, c=c, relu=relu, res=res))
+
+    P.append(dict(op="stem", out="stem.z", w="resnet.conv1.weight", cout=64))
+    bn("feat1", "stem.z", "resnet.bn1", 64)
+    P.append(dict(op="pool3", out="pool", x="feat1"))
+    x, inplanes = "pool", 64
+    feats = ["feat1"]
+    for li, (planes, blocks, stride) in enumerate([(64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)], start=1):
+        for b in range(blocks):
+            pre = f"resnet.layer{li}.{b}"
+            s = stride if b == 0 else 1
+            conv(pre + ".z1", x, pre + ".conv1.weight", inplanes, planes, 1)
+            bn(pre + ".y1", pre + ".z1", pre + ".bn1", planes)
+            conv(pre + ".z2", pre + ".y1", pre + ".conv2.weight", planes, planes, 9, stride=s)
+            bn(pre + ".y2", pre + ".z2", pre + ".bn2", planes)
+            conv(pre + ".z3", pre + ".y2", pre + ".conv3.weight", planes, planes * 4, 1)
+            idn = x
+            if b == 0:      # downsample branch (nets/resnet.py:134-141): 1x1 conv (stride s) + BN, no ReLU
+                conv(pre + ".zd", x, pre + ".downsample.0.weight", inplanes, planes * 4, 1, stride=s)
+                bn(pre + ".yd", pre + ".zd", pre + ".downsample.1", planes * 4, relu=False)
+                idn = pre + ".yd"
+            bn(pre + ".out", pre + ".z3", pre + ".bn3", planes * 4, relu=True, res=idn)
+            x, inplanes = pre + ".out", planes * 4
+        feats.append(x)
+    # decoder: in_filters [192, 512, 1024, 3072], out_filters [64, 128, 256, 512] (nets/unet.py:31-45)
+    chans = {"feat1": 64, feats[1]: 256, feats[2]: 512, feats[3]: 1024, feats[4]: 2048}
+    low, clow = feats[4], 2048
+    for k, co in ((4, 512), (3, 256), (2, 128), (1, 64)):
+        skip = feats[k - 1]
+        P.append(dict(op="up", out=f"up{k}", x=low))
+        conv(f"d{k}a", skip, f"up_concat{k}.conv1.weight", chans[skip], co, 9, bias=f"up_concat{k}.conv1.bias", relu=True,
+             x1=f"up{k}", c1=clow)
+        conv(f"d{k}b", f"d{k}a", f"up_concat{k}.conv2.weight", co, co, 9, bias=f"up_concat{k}.conv2.bias", relu=True)
+        low, clow = f"d{k}b", co
+    # up_conv (nets/unet.py:47-54): upsample, conv+ReLU, conv+ReLU at full resolution
+    P.append(dict(op="up", out="upc", x=low))
+    conv("uc1", "upc", "up_conv.1.weight", 64, 64, 9, bias="up_conv.1.bias", relu=True)
+    conv("uc2", "uc1", "up_conv.3.weight", 64, 64, 9, bias="up_conv.3.bias", relu=True)
+    P.append(dict(op="head", out="logits", x="uc2", w="final.weight", bias="final.bias"))
+    return P, convs
+
+
+class GraphEngine:
+    def __init__(self, program, convs, num_classes, device=None):
+        self.program, self.convs, self.num_classes, self.device = program, convs, num_classes, device
+        self.eps, self.momentum = 1e-5, 0.1
+        self._bufs, self._ws = {}, {}
+        self._packed = {}            # weight name -> (wf, wd)
+        self._pack_key = self._pack_versions = self._pack_table = None
+        self._pack_total = 0
+        self.saved = None
+
+    # ------------------------------------------------------------------ static description
+    def param_shapes(self):
+        shapes = {}
+        for ins in self.program:
+            if ins["op"] == "stem":
+                shapes[ins["w"]] = (ins["cout"], 3, 7, 7)
+            elif ins["op"] == "conv":
+                k = 3 if ins["taps"] == 9 else 1
+                shapes[ins["w"]] = (ins["cout"], ins["cin"] + ins["c1"], k, k)
+                if ins["bias"]:
+                    shapes[ins["bias"]] = (ins["cout"],)
+            elif ins["op"] == "bn":
+                shapes[ins["bn"] + ".weight"] = (ins["c"],)
+                shapes[ins["bn"] + ".bias"] = (ins["c"],)
+            elif ins["op"] == "head":
+                shapes[ins["w"]] = (self.num_classes, 64, 1, 1)
+                shapes[ins["bias"]] = (self.num_classes,)
+        return shapes
+
+    def buffer_shapes(self):
+        shapes = {}
+        for ins in self.program:
+            if ins["op"] == "bn":
+                shapes[ins["bn"] + ".running_mean"] = (ins["c"],)
+                shapes[ins["bn"] + ".running_var"] = (ins["c"],)
+                shapes[ins["bn"] + ".num_batches_tracked"] = ()
+        return shapes
+
+    def backward_param_order(self):
+        out = []
+        for ins in reversed(self.program):
+            if ins["op"] == "head":
+                out += [ins["w"], ins["bias"]]
+            elif ins["op"] == "conv":
+                out += [ins["w"]] + ([ins["bias"]] if ins["bias"] else [])
+            elif ins["op"] == "bn":
+                out += [ins["bn"] + ".weight", ins["bn"] + ".bias"]
+            elif ins["op"] == "stem":
+                out += [ins["w"]]
+        return out
+
+    # ------------------------------------------------------------------ buffers
+    def _buf(self, key, shape, dtype=torch.bfloat16):
+        t = self._bufs.get(key)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self._bufs[key] = t
+        return t
+
+    def _workspace(self, key, nbytes):
+        t = self._ws.get(key)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=self.device)
+            self._ws[key] = t
+        return t
+
+    def release(self):
+        self._bufs.clear(); self._ws.clear(); self.saved = None
+
+    # ------------------------------------------------------------------ weights
+    def pack(self, params, need_dgrad=True):
+        names = list(self.convs.keys())
+        key = tuple(params[n].data_ptr() for n in names) + (need_dgrad,)
+        versions = tuple(params[n]._version for n in names) + (params["resnet.conv1.weight"]._version,)
+        if self._pack_key == key and self._pack_versions == versions:
+            return
+        dev = params[names[0]].device
+        if self._pack_key != key:
+            blob, start = b"", 0
+            for n in names:
+                cout, cin, taps = self.convs[n]
+                wf, wd = self._packed.get(n, (None, None))
+                if wf is None:
+                    wf = torch.zeros((cout, taps * cin), dtype=torch.bfloat16, device=dev)
+                if need_dgrad and wd is None:
+                    wd = torch.zeros((cin, taps * cout), dtype=torch.bfloat16, device=dev)
+                self._packed[n] = (wf, wd)
+                blob += struct.pack("<QQQqiiiiiiii", params[n].data_ptr(), wf.data_ptr(), wd.data_ptr() if need_dgrad else 0,
+                                    start, cout, cin, taps, 0, cin, cin, cin, cout)
+                start += (cout // 32) * (cin // 32)
+            self._pack_table = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+            self._pack_total, self._pack_key = start, key
+        ops.check(ops.lib().b2u_pack_weights_multi(self._pack_table.data_ptr(), len(names), self._pack_total, ops.stream_ptr()))
+        self._stem_wf = ops.pack_weights_im2col(params["resnet.conv1.weight"], 192, wf=getattr(self, "_stem_wf", None))
+        self._pack_versions = versions
+
+    def invalidate_packed_weights(self):
+        self._pack_versions = None
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, params, save=True, training=None, trainable=None):
+        if not x.is_cuda:
+            raise ValueError("GraphEngine.forward: input must be a CUDA tensor (no CPU fallback)")
+        x = x.float().contiguous() if x.dtype != torch.float32 else x.contiguous()
+        N, C, H, W = x.shape
+        if C != 3 or H % 32 or W % 32:
+            raise ValueError("expected a 3-channel image with height and width multiples of 32")
+        if training is None:
+            training = save
+        if trainable is None:
+            trainable = set(self.param_shapes().keys())
+        self.device = x.device
+        self.pack(params, need_dgrad=save)
+        zero_bias = {}
+        T = {}
+        logits = None
+        for ins in self.program:
+            op = ins["op"]
+            if op == "stem":
+                col = ops.im2col_stem(x, out=self._buf("stem.col", (N, H // 2, W // 2, 192)))
+                z = self._buf(ins["out"], (N, H // 2, W // 2, 64))
+                ops.conv_fprop(col, self._stem_wf, None, 64, taps=1, relu=False, out=z)
+                t = _T(z, needs_grad=ins["w"] in trainable)
+                t.aux = col
+                T[ins["out"]] = t
+            elif op == "conv":
+                xin = T[ins["x"]]
+                x1 = T[ins["x1"]] if ins["x1"] else None
+                wf, _ = self._packed[ins["w"]]
+                n, h, w, _ = xin.data.shape
+                bias = params[ins["bias"]] if ins["bias"] else None
+                aux = None
+                if ins["stride"] == 1:
+                    z = self._buf(ins["out"], (n, h, w, ins["cout"]))
+                    ops.conv_fprop(xin.data, wf, bias, ins["cout"], taps=ins["taps"], relu=ins["relu"],
+                                   x1=x1.data if x1 else None, out=z)
+                elif ins["taps"] == 9:      # 3x3 stride 2 = stride-1 conv, keep even pixels
+                    full = self._buf(ins["out"] + ":full", (n, h, w, ins["cout"]))
+                    ops.conv_fprop(xin.data, wf, bias, ins["cout"], taps=9, relu=ins["relu"], out=full)
+                    z = ops.subsample2(full, out=self._buf(ins["out"], (n, h // 2, w // 2, ins["cout"])))
+                else:                        # 1x1 stride 2 = keep even pixels, then conv
+                    aux = ops.subsample2(xin.data, out=self._buf(ins["out"] + ":xs", (n, h // 2, w // 2, xin.data.shape[3])))
+                    z = self._buf(ins["out"], (n, h // 2, w // 2, ins["cout"]))
+                    ops.conv_fprop(aux, wf, bias, ins["cout"], taps=1, relu=ins["relu"], out=z)
+                ng = xin.needs_grad or (x1 is not None and x1.needs_grad) or ins["w"] in trainable or (ins["bias"] in trainable)
+                t = _T(z, fused_relu=ins["relu"], needs_grad=ng)
+                t.aux = aux
+                T[ins["out"]] = t
+            elif op == "bn":
+                zt = T[ins["z"]]
+                res = T[ins["res"]] if ins["res"] else None
+                bnn = ins["bn"]
+                y = self._buf(ins["out"], zt.data.shape)
+                ws = self._workspace("bn", ops.lib().b2u_bn_workspace(ins["c"]))
+                if training:
+                    _, mean, invstd = ops.bn_fwd_train(zt.data, params[bnn + ".weight"], params[bnn + ".bias"],
+                                                       params[bnn + ".running_mean"], params[bnn + ".running_var"], self.eps,
+                                                       self.momentum, ins["relu"], out=y, ws=ws,
+                                                       residual=res.data if res else None)
+                    nbt = params.get(bnn + ".num_batches_tracked")
+                    if nbt is not None:
+                        nbt.add_(1)
+                else:
+                    ops.bn_fwd_eval(zt.data, params[bnn + ".weight"], params[bnn + ".bias"], params[bnn + ".running_mean"],
+                                    params[bnn + ".running_var"], self.eps, ins["relu"], out=y, ws=ws,
+                                    residual=res.data if res else None)
+                    mean = invstd = None
+                ng = zt.needs_grad or (res is not None and res.needs_grad) or (bnn + ".weight") in trainable or (bnn + ".bias") in trainable
+                t = _T(y, needs_grad=ng)
+                t.aux = (mean, invstd)
+                T[ins["out"]] = t
+            elif op == "pool3":
+                xin = T[ins["x"]]
+                n, h, w, c = xin.data.shape
+                y = ops.maxpool3x3s2(xin.data, out=self._buf(ins["out"], (n, (h - 2) // 2 + 1, (w - 2) // 2 + 1, c)))
+                T[ins["out"]] = _T(y, needs_grad=xin.needs_grad)
+            elif op == "up":
+                xin = T[ins["x"]]
+                n, h, w, c = xin.data.shape
+                y = ops.upsample2x(xin.data, out=self._buf(ins["out"], (n, 2 * h, 2 * w, c)))
+                T[ins["out"]] = _T(y, needs_grad=xin.needs_grad)
+            elif op == "head":
+                xin = T[ins["x"]]
+                logits = ops.head_fwd(xin.data, params[ins["w"]].reshape(self.num_classes, 64), params[ins["bias"]])
+        if save:
+            self.saved = (T, (N, H, W), set(trainable))
+        return logits
+
+    # ------------------------------------------------------------------ backward
+    def _acc(self, t, g):
+        if t.grad is None:
+            t.grad = g
+        else:
+            ops.add_bf16(t.grad, g, out=t.grad)
+
+    def backward(self, dlogits, params, grads, trainable=None, on_grads_ready=None):
+        if self.saved is None:
+            raise RuntimeError("backward() without a saved forward()")
+        T, (N, H, W), fwd_trainable = self.saved
+        if trainable is None:
+            trainable = set(grads.keys())
+        for t in T.values():
+            t.grad = None
+
+        def has(n):
+            return n is not None and n in trainable and n in grads
+
+        def ready(*names):
+            if on_grads_ready is not None:
+                on_grads_ready([n for n in names if n in grads])
+
+        for ins in reversed(self.program):
+            op = ins["op"]
+            if op == "head":
+                xin = T[ins["x"]]
+                wh = params[ins["w"]].reshape(self.num_classes, 64)
+                C = self.num_classes
+                fw, fb = has(ins["w"]), has(ins["bias"])
+                g = self._buf("g:" + ins["x"], xin.data.shape) if xin.needs_grad else None
+                if dlogits.dtype == torch.bfloat16:
+                    dl = dlogits.contiguous()
+                    if g is not None:
+                        wd_head = ops.pack_head_dgrad(wh, wd=self._buf("head:wd", (64, 64)))
+                        ops.conv_dgrad(dl, wd_head, 64, taps=1, mask=xin.data if xin.fused_relu else None, out0=g)
+                    if fw or fb:
+                        dw64 = self._buf("head:dw", (64, 64, 1, 1), torch.float32)
+                        db64 = self._buf("head:db", (64,), torch.float32)
+                        need = ops.lib().b2u_conv_wgrad_workspace(dl.shape[0], dl.shape[1], dl.shape[2], 64, 64, 1)
+                        ops.conv_wgrad(xin.data, dl, taps=1, dw=dw64, db=db64, ws=self._workspace("wgrad", need))
+                        if fw:
+                            torch.add(dw64[:C], dw64[32:32 + C], out=grads[ins["w"]])
+                        if fb:
+                            torch.add(db64[:C], db64[32:32 + C], out=grads[ins["bias"]])
+                else:
+                    dl = dlogits.float().contiguous() if dlogits.dtype != torch.float32 else dlogits.contiguous()
+                    ops.head_bwd(dl, xin.data, wh, need_dx=g is not None, need_dw=fw or fb, relu_mask=xin.fused_relu, dx=g,
+                                 dw=grads[ins["w"]] if fw else None, db=grads[ins["bias"]] if fb else None,
+                                 ws=self._workspace("head", ops.lib().b2u_head_bwd_workspace()))
+                if g is not None:
+                    self._acc(xin, g)
+                ready(ins["w"], ins["bias"])
+            elif op == "up":
+                t, xin = T[ins["out"]], T[ins["x"]]
+                if t.grad is None or not xin.needs_grad:
+                    continue
+                g = self._buf("g:" + ins["out"] + ">", xin.data.shape)
+                ops.upsample2x_bwd(t.grad, ylow=xin.data if xin.fused_relu else None, out=g)
+                self._acc(xin, g)
+            elif op == "pool3":
+                t, xin = T[ins["out"]], T[ins["x"]]
+                if t.grad is None or not xin.needs_grad:
+                    continue
+                g = ops.maxpool3x3s2_bwd(t.grad, xin.data, out=self._buf("g:" + ins["out"] + ">", xin.data.shape))
+                self._acc(xin, g)
+            elif op == "bn":
+                t, zt = T[ins["out"]], T[ins["z"]]
+                res = T[ins["res"]] if ins["res"] else None
+                if t.grad is None:
+                    continue
+                bnn = ins["bn"]
+                mean, invstd = t.aux
+                need_res = res is not None and res.needs_grad
+                gout = self._buf("g:" + ins["out"] + ">res", t.data.shape) if need_res else None
+                dz = self._buf("g:" + ins["z"], zt.data.shape)
+                dgam = self._buf("dg:" + bnn, (ins["c"],), torch.float32)
+                dbet = self._buf("db:" + bnn, (ins["c"],), torch.float32)
+                ops.bn_bwd(t.grad, t.data, zt.data, params[bnn + ".weight"], mean, invstd, relu=ins["relu"], out=dz,
+                           dgamma=grads[bnn + ".weight"] if has(bnn + ".weight") else dgam,
+                           dbeta=grads[bnn + ".bias"] if has(bnn + ".bias") else dbet,
+                           ws=self._workspace("bn", ops.lib().b2u_bn_workspace(ins["c"])), gout=gout)
+                ready(bnn + ".weight", bnn + ".bias")
+                if zt.needs_grad:
+                    self._acc(zt, dz)
+                if need_res:
+                    self._acc(res, gout)
+            elif op == "conv":
+                t, xin = T[ins["out"]], T[ins["x"]]
+                x1 = T[ins["x1"]] if ins["x1"] else None
+                if t.grad is None:
+                    continue
+                dz = t.grad
+                wf, wd = self._packed[ins["w"]]
+                n, h, w, _ = xin.data.shape
+                taps, cout = ins["taps"], ins["cout"]
+                if ins["stride"] == 2 and taps == 9:
+                    dz = ops.zero_insert2(dz, h, w, out=self._buf("g:" + ins["out"] + ":full", (n, h, w, cout)))
+                xw = t.aux if (ins["stride"] == 2 and taps == 1) else xin.data          # wgrad's activation operand
+                if has(ins["w"]):
+                    ctot = xw.shape[3] + (x1.data.shape[3] if x1 else 0)
+                    need = ops.lib().b2u_conv_wgrad_workspace(dz.shape[0], dz.shape[1], dz.shape[2], ctot, cout, taps)
+                    ops.conv_wgrad(xw, dz, taps=taps, x1=x1.data if x1 else None, dw=grads[ins["w"]],
+                                   ws=self._workspace("wgrad", need))
+                if has(ins["bias"]):
+                    ops.bias_grad(dz, db=grads[ins["bias"]], ws=self._workspace("bias", ops.lib().b2u_bias_grad_workspace(cout)))
+                ready(ins["w"], ins["bias"])
+                need0, need1 = xin.needs_grad, (x1 is not None and x1.needs_grad)
+                if not (need0 or need1):
+                    continue
+                c0 = xw.shape[3]
+                if x1 is not None:
+                    c1 = x1.data.shape[3]
+                    if need0:
+                        d0 = self._buf("g:" + ins["out"] + ">0", xin.data.shape)
+                        d1 = self._buf("g:" + ins["out"] + ">1", x1.data.shape)
+                        ops.conv_dgrad(dz, wd, c0, taps=taps, C1=c1, out0=d0, out1=d1)
+                        self._acc_masked(xin, d0)
+                        if need1:
+                            self._acc_masked(x1, d1)
+                    else:       # frozen skip source: only the second (up-sampled) half needs a gradient
+                        d1 = self._buf("g:" + ins["out"] + ">1", x1.data.shape)
+                        ops.conv_dgrad(dz, wd[c0:], c1, taps=taps, mask=x1.data if x1.fused_relu else None, out0=d1)
+                        self._acc(x1, d1)
+                else:
+                    d0 = self._buf("g:" + ins["out"] + ">0", xw.shape)
+                    ops.conv_dgrad(dz, wd, c0, taps=taps, mask=xin.data if (xin.fused_relu and xw is xin.data) else None, out0=d0)
+                    if ins["stride"] == 2 and taps == 1:
+                        d0 = ops.zero_insert2(d0, h, w, out=self._buf("g:" + ins["out"] + ">0:full", xin.data.shape))
+                    self._acc(xin, d0)
+            elif op == "stem":
+                t = T[ins["out"]]
+                if t.grad is None or not has(ins["w"]):
+                    continue
+                col = t.aux
+                need = ops.lib().b2u_conv_wgrad_workspace(col.shape[0], col.shape[1], col.shape[2], 192, 64, 1)
+                ops.conv_wgrad_im2col(col, t.grad, 3, 49, dw=grads[ins["w"]], ws=self._workspace("wgrad", need))
+                ready(ins["w"])
+
+    def _acc_masked(self, t, g):
+        """Gradient from a split (two-output) dgrad, which cannot mask in its epilogue."""
+        if t.fused_relu:
+            raise NotImplementedError("split dgrad into a fused-ReLU tensor needs a mask pass")   # not needed by ResNet50-Unet's encoder features
+        self._acc(t, g)
+
+
+class ResNet50UnetEngine(GraphEngine):
+    def __init__(self, num_classes, device=None):
+        if not 1 <= num_classes <= 32:
+            raise ValueError("num_classes must be in [1, 32]")
+        program, convs = resnet50_unet_program(num_classes)
+        super().__init__(program, convs, num_classes, device=device)

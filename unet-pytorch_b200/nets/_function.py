@@ -12,7 +12,8 @@ class EngineFunction(torch.autograd.Function):
         tensors = dict(zip(names, params))
         tensors.update(dict(module.named_buffers()))          # BatchNorm running statistics (updated in place)
         needs = any(ctx.needs_input_grad[2:])
-        logits = engine.forward(x, tensors, save=needs, training=module.training)
+        trainable = {n for n, need in zip(names, ctx.needs_input_grad[2:]) if need}
+        logits = engine.forward(x, tensors, save=needs, training=module.training, trainable=trainable)
         if needs:
             engine._generation = getattr(engine, "_generation", 0) + 1
             ctx.generation = engine._generation

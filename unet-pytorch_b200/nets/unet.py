@@ -3,7 +3,9 @@ and forward contract (NCHW fp32 image in, NCHW fp32 logits out), executed by the
 import torch.nn as nn
 
 from ..engine import VGGUnetEngine
+from ..graph import ResNet50UnetEngine
 from ._function import EngineModuleMixin
+from .resnet import resnet50
 from .vgg import VGG16
 
 
@@ -28,7 +30,8 @@ class Unet(nn.Module, EngineModuleMixin):
             self.vgg = VGG16(pretrained=pretrained)
             in_filters = [192, 384, 768, 1024]
         elif backbone == "resnet50":
-            raise NotImplementedError("backbone='resnet50' is not built yet in the B200 engine (SURVEY.md 8(a) row a4)")
+            self.resnet = resnet50(pretrained=pretrained)
+            in_filters = [192, 512, 1024, 3072]
         else:
             raise ValueError("Unsupported backbone - `{}`, Use vgg, resnet50.".format(backbone))
         out_filters = [64, 128, 256, 512]
@@ -36,22 +39,33 @@ class Unet(nn.Module, EngineModuleMixin):
         self.up_concat3 = unetUp(in_filters[2], out_filters[2])
         self.up_concat2 = unetUp(in_filters[1], out_filters[1])
         self.up_concat1 = unetUp(in_filters[0], out_filters[0])
-        self.up_conv = None
+        if backbone == "resnet50":
+            self.up_conv = nn.Sequential(                   # nets/unet.py:47-54
+                nn.UpsamplingBilinear2d(scale_factor=2),
+                nn.Conv2d(out_filters[0], out_filters[0], kernel_size=3, padding=1), nn.ReLU(),
+                nn.Conv2d(out_filters[0], out_filters[0], kernel_size=3, padding=1), nn.ReLU())
+        else:
+            self.up_conv = None
         self.final = nn.Conv2d(out_filters[0], num_classes, 1)
         self.backbone = backbone
         self.num_classes = num_classes
         self._init_engine_state()
 
     def _make_engine(self, device):
+        if self.backbone == "resnet50":
+            return ResNet50UnetEngine(self.num_classes, device=device)
         return VGGUnetEngine(self.num_classes, in_channels=3, device=device)
 
     def forward(self, inputs):
         return self._engine_forward(inputs)
 
+    def _backbone(self):
+        return self.vgg if self.backbone == "vgg" else self.resnet
+
     def freeze_backbone(self):
-        for param in self.vgg.parameters():
+        for param in self._backbone().parameters():
             param.requires_grad = False
 
     def unfreeze_backbone(self):
-        for param in self.vgg.parameters():
+        for param in self._backbone().parameters():
             param.requires_grad = True

@@ -219,7 +219,8 @@ def upsample2x_bwd(dup, ylow=None, out=None):
 
 
 # ---------------------------------------------------------------------------------------------- batch norm
-def bn_fwd_train(z, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1, relu=True, out=None, ws=None):
+def bn_fwd_train(z, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1, relu=True, out=None, ws=None,
+                 residual=None):
     """Returns (y, save_mean, save_invstd); running statistics are updated in place (torch semantics)."""
     _req(z, BF16, "z")
     C = z.shape[-1]
@@ -231,13 +232,13 @@ def bn_fwd_train(z, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0
         out = torch.empty_like(z)
     mean = torch.empty((C,), dtype=torch.float32, device=z.device)
     invstd = torch.empty((C,), dtype=torch.float32, device=z.device)
-    check(lib().b2u_bn_fwd_train(ptr(z), ptr(out), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(mean),
+    check(lib().b2u_bn_fwd_train(ptr(z), ptr(residual), ptr(out), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(mean),
                                  ptr(invstd), ptr(ws), ws.numel() * ws.element_size(), P, C, eps, momentum,
                                  1 if relu else 0, stream_ptr()))
     return out, mean, invstd
 
 
-def bn_fwd_eval(z, gamma, beta, running_mean, running_var, eps=1e-5, relu=True, out=None, ws=None):
+def bn_fwd_eval(z, gamma, beta, running_mean, running_var, eps=1e-5, relu=True, out=None, ws=None, residual=None):
     _req(z, BF16, "z")
     C = z.shape[-1]
     P = z.numel() // C
@@ -246,13 +247,13 @@ def bn_fwd_eval(z, gamma, beta, running_mean, running_var, eps=1e-5, relu=True, 
         ws = _ws(need, z.device)
     if out is None:
         out = torch.empty_like(z)
-    check(lib().b2u_bn_fwd_eval(ptr(z), ptr(out), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(ws),
+    check(lib().b2u_bn_fwd_eval(ptr(z), ptr(residual), ptr(out), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(ws),
                                 ws.numel() * ws.element_size(), P, C, eps, 1 if relu else 0, stream_ptr()))
     return out
 
 
-def bn_bwd(dy, y, z, gamma, mean, invstd, relu=True, out=None, dgamma=None, dbeta=None, ws=None):
-    """Returns (dz, dgamma, dbeta)."""
+def bn_bwd(dy, y, z, gamma, mean, invstd, relu=True, out=None, dgamma=None, dbeta=None, ws=None, gout=None):
+    """Returns (dz, dgamma, dbeta); gout (optional tensor) receives the ReLU-masked dy (residual-branch gradient)."""
     _req(dy, BF16, "dy"); _req(y, BF16, "y"); _req(z, BF16, "z")
     C = z.shape[-1]
     P = z.numel() // C
@@ -265,9 +266,91 @@ def bn_bwd(dy, y, z, gamma, mean, invstd, relu=True, out=None, dgamma=None, dbet
         dgamma = torch.empty((C,), dtype=torch.float32, device=z.device)
     if dbeta is None:
         dbeta = torch.empty((C,), dtype=torch.float32, device=z.device)
-    check(lib().b2u_bn_bwd(ptr(dy), ptr(y), ptr(z), ptr(gamma), ptr(mean), ptr(invstd), ptr(out), ptr(dgamma), ptr(dbeta),
+    check(lib().b2u_bn_bwd(ptr(dy), ptr(y), ptr(z), ptr(gamma), ptr(mean), ptr(invstd), ptr(out), ptr(gout), ptr(dgamma), ptr(dbeta),
                            ptr(ws), ws.numel() * ws.element_size(), P, C, 1 if relu else 0, stream_ptr()))
     return out, dgamma, dbeta
+
+
+# ---------------------------------------------------------------------------------------------- ResNet helpers
+def im2col_stem(x_nchw, out=None):
+    _req(x_nchw, torch.float32, "x")
+    N, C, H, W = x_nchw.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    if out is None:
+        out = torch.empty((N, Ho, Wo, 192), dtype=BF16, device=x_nchw.device)
+    check(lib().b2u_im2col_stem(ptr(x_nchw), ptr(out), N, C, H, W, stream_ptr()))
+    return out
+
+
+def pack_weights_im2col(w, kpad, wf=None):
+    _req(w, torch.float32, "weight")
+    Cout, Cin, kh, kw = w.shape
+    if wf is None:
+        wf = torch.empty((Cout, kpad), dtype=BF16, device=w.device)
+    check(lib().b2u_pack_weights_im2col(ptr(w), ptr(wf), Cout, Cin, kh * kw, kpad, stream_ptr()))
+    return wf
+
+
+def conv_wgrad_im2col(col, dz, cin, taps, dw=None, ws=None):
+    """wgrad of a conv executed as a 1x1 GEMM over im2col rows; dw: [Cout, cin, k, k] with k*k = taps."""
+    _req(col, BF16, "col"); _req(dz, BF16, "dz")
+    N, H, W, Kpad = col.shape
+    Cout = dz.shape[3]
+    need = lib().b2u_conv_wgrad_workspace(N, H, W, Kpad, Cout, 1)
+    if ws is None or ws.numel() * ws.element_size() < need:
+        ws = _ws(need, col.device)
+    if dw is None:
+        k = int(round(taps ** 0.5))
+        dw = torch.empty((Cout, cin, k, k), dtype=torch.float32, device=col.device)
+    with _timed(f"conv_wgrad|wgrad|{N}x{H}x{W}|{Kpad}+0->{Cout}|t1", 2.0 * N * H * W * Cout * Kpad):
+        check(lib().b2u_conv_wgrad_im2col(ptr(col), Kpad, ptr(dz), Cout, ptr(dw), ptr(ws), ws.numel() * ws.element_size(),
+                                          N, H, W, cin, taps, stream_ptr()))
+    return dw
+
+
+def subsample2(x, out=None):
+    _req(x, BF16, "x")
+    N, H, W, C = x.shape
+    if out is None:
+        out = torch.empty((N, (H + 1) // 2, (W + 1) // 2, C), dtype=BF16, device=x.device)
+    check(lib().b2u_subsample2(ptr(x), ptr(out), N, H, W, C, stream_ptr()))
+    return out
+
+
+def zero_insert2(y, H, W, out=None):
+    _req(y, BF16, "y")
+    N, _, _, C = y.shape
+    if out is None:
+        out = torch.empty((N, H, W, C), dtype=BF16, device=y.device)
+    check(lib().b2u_zero_insert2(ptr(y), ptr(out), N, H, W, C, stream_ptr()))
+    return out
+
+
+def maxpool3x3s2(x, out=None):
+    _req(x, BF16, "x")
+    N, H, W, C = x.shape
+    Ho, Wo = (H - 2) // 2 + 1, (W - 2) // 2 + 1
+    if out is None:
+        out = torch.empty((N, Ho, Wo, C), dtype=BF16, device=x.device)
+    check(lib().b2u_maxpool3x3s2_fwd(ptr(x), ptr(out), N, H, W, C, stream_ptr()))
+    return out
+
+
+def maxpool3x3s2_bwd(dy, x, out=None):
+    _req(dy, BF16, "dy"); _req(x, BF16, "x")
+    N, H, W, C = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib().b2u_maxpool3x3s2_bwd(ptr(dy), ptr(x), ptr(out), N, H, W, C, stream_ptr()))
+    return out
+
+
+def add_bf16(a, b, out=None):
+    _req(a, BF16, "a"); _req(b, BF16, "b")
+    if out is None:
+        out = torch.empty_like(a)
+    check(lib().b2u_add_bf16(ptr(a), ptr(b), ptr(out), a.numel(), stream_ptr()))
+    return out
 
 
 # ---------------------------------------------------------------------------------------------- head

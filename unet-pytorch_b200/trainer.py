@@ -15,6 +15,7 @@ import torch.distributed as dist
 
 from . import ops
 from .engine import TraditionalUnetEngine, VGGUnetEngine, vgg_unet_param_shapes
+from .graph import ResNet50UnetEngine
 
 
 def _backward_order(names):
@@ -129,9 +130,10 @@ class GradientSync:
 
 
 class UnetTrainer:
-    """model: "unet_vgg" (nets/unet.py::Unet, backbone='vgg') or "traditional" (nets/TraditionalUnet.py)."""
+    """model: "unet_vgg" / "unet_resnet50" (nets/unet.py::Unet with backbone 'vgg' / 'resnet50') or "traditional"
+    (nets/TraditionalUnet.py)."""
 
-    ENGINES = {"unet_vgg": VGGUnetEngine, "traditional": TraditionalUnetEngine}
+    ENGINES = {"unet_vgg": VGGUnetEngine, "traditional": TraditionalUnetEngine, "unet_resnet50": ResNet50UnetEngine}
 
     def __init__(self, num_classes=21, device=None, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
                  optimizer="adam", momentum=0.9, cls_weights=None, dice_loss=True, focal_loss=False,
@@ -173,7 +175,7 @@ class UnetTrainer:
         self.cls_w = cw.to(self.device).contiguous()
         self.sync = GradientSync(self.layout, self.flat_grad, group=process_group)
         self.trainable = set(self.names)
-        self.backbone_prefixes = ("vgg.",) if model == "unet_vgg" else ("inc.", "down1.", "down2.", "down3.")
+        self.backbone_prefixes = {"unet_vgg": ("vgg.",), "unet_resnet50": ("resnet.",)}.get(model, ("inc.", "down1.", "down2.", "down3."))
         self._gscale = torch.tensor([0.0 if focal_loss else 1.0, 1.0 if focal_loss else 0.0, 1.0 if dice_loss else 0.0],
                                     dtype=torch.float32, device=self.device)
         self._copy_stream = torch.cuda.Stream(device=self.device)
