@@ -49,6 +49,8 @@ int b2u_pack_weights_first(const float* w_oihw, void* wf, int Cout, int Cin, voi
 int b2u_pack_weights_multi(const void* table, int n, long long total_blocks, void* stream);
 int b2u_nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, int H, int W, void* stream);
 int b2u_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int W, void* stream);
+/* same with the channel dimension zero-padded to Cpad (the 3-channel image feeding a 1x1 first conv) */
+int b2u_nchw_f32_to_nhwc_bf16_padded(const float* x, void* y, int N, int C, int H, int W, int Cpad, void* stream);
 
 /* ---- tensor-core convolutions (tcgen05 implicit GEMM) ------------------------------------------------------ */
 /* y = [relu](conv(cat(x0, x1), w) + bias).  Replaces nn.Conv2d(k=3,p=1 | k=1)+ReLU (nets/vgg.py:53-57,
@@ -115,6 +117,27 @@ int b2u_maxpool3x3s2_fwd(const void* x, void* y, int N, int H, int W, int C, voi
 int b2u_maxpool3x3s2_bwd(const void* dy, const void* x, void* dx, int N, int H, int W, int C, void* stream);
 /* out = a + b over n bf16 elements (gradient accumulation at tensors with two consumers) */
 int b2u_add_bf16(const void* a, const void* b, void* out, long long n, void* stream);
+
+/* ---- depthwise conv, squeeze-excite, per-(image,channel) scaling (Lightweight / UltraLightweight UNets) ---------- */
+/* nn.Conv2d(C, C, 3, padding=1, groups=C) (nets/UltraLightweightUnet_large.py:9-10): w fp32 [C][9]; flip=1 uses the
+ * taps reversed and is the data gradient */
+int b2u_dwconv3x3_fwd(const void* x, const float* w, const float* bias, void* y, int N, int H, int W, int C, int flip,
+                      void* stream);
+size_t b2u_dwconv3x3_wgrad_workspace(int C);
+int b2u_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, float* db, void* ws, size_t ws_bytes, int N, int H, int W,
+                        int C, void* stream);
+/* out[n][c] = scale * sum over image n's pixels of a (b NULL: AdaptiveAvgPool2d(1) with scale 1/HW) or of a*b */
+int b2u_spatial_reduce_workspace_floats(int N, int C);
+int b2u_spatial_reduce(const void* a, const void* b, float* out, void* ws, size_t ws_bytes, int N, long long HW, int C,
+                       float scale, void* stream);
+/* y = x * s[n][c] + a[n][c] (a nullable): SE excitation `x * y` (:52), its backward, nn.Dropout2d masks */
+int b2u_scale_nc(const void* x, const float* s, const float* a, void* y, int N, long long HW, int C, void* stream);
+/* SE block's Linear-ReLU-Linear-Sigmoid (nets/UltraLightweightUnet_large.py:41-46) and its gradients */
+int b2u_se_fc_fwd(const float* pooled, const float* w1, const float* b1, const float* w2, const float* b2, float* hidden,
+                  float* scale, int N, int C, int Cp, int R, void* stream);
+int b2u_se_fc_bwd(const float* dscale, const float* pooled, const float* hidden, const float* scale, const float* w1,
+                  const float* w2, float* dpooled, float* dw1, float* db1, float* dw2, float* db2, float* scratch, int N,
+                  int C, int Cp, int R, float dp_scale, void* stream);
 
 /* ---- classifier head (nn.Conv2d(64, num_classes, 1), nets/unet.py:58,76) ------------------------------------ */
 int b2u_head_fwd(const void* x, const float* w, const float* b, float* logits_nchw, int N, int H, int W, int Cin,

@@ -18,6 +18,9 @@ for name in ("matplotlib", "matplotlib.pyplot"):
 
 from nets.unet import Unet as RefUnet                                   # noqa: E402
 from nets.TraditionalUnet import TraditionalUnet as RefTraditional      # noqa: E402
+from nets.UltraLightweightUnet import UltraLightweightUnet as RefULU                           # noqa: E402
+from nets.UltraLightweightUnet_large import UltraLightweightUnet_large as RefULULarge         # noqa: E402
+from nets.UltraLightweightUnet_large_optimized import UltraLightweightUnet_large_optimized as RefULUOpt   # noqa: E402
 from nets.unet_training import CE_Loss, Dice_loss, Focal_Loss           # noqa: E402
 from utils.utils_metrics import f_score, fast_hist, per_class_iu, per_class_PA_Recall, per_class_Precision  # noqa: E402
 
@@ -120,6 +123,58 @@ def resnet_case(tag, num_classes, n, h, w, seed, cls_w, dice):
     print("resnet50", tag, "loss", loss.item())
 
 
+ULU_REF = {"ultralight": RefULU, "ultralight_large": RefULULarge, "ultralight_large_optimized": RefULUOpt}
+
+
+def ulu_case(variant, tag, num_classes, n, h, w, seed, cls_w, dice, focal):
+    """UltraLightweightUnet family in train mode.  The bridge Dropout2d draws from torch's RNG, so a forward hook records
+    the multiplier the reference applied (output / input per (sample, channel)); the CUDA path replays that mask."""
+    sd = O.make_ulu_params(num_classes, variant, seed=11)
+    model = ULU_REF[variant](num_classes=num_classes)
+    model.load_state_dict(sd)
+    model.train()
+    imgs, pngs = O.make_inputs(n, num_classes, h, w, seed=seed)
+    labels = torch.eye(num_classes + 1)[pngs]
+    weights = torch.tensor(cls_w, dtype=torch.float32)
+    rec = {}
+    captured = {}
+
+    def hook(mod, inp, out):
+        x = inp[0].detach()
+        amax = x.abs().amax(dim=(2, 3))
+        ratio = (out.detach().abs().amax(dim=(2, 3)) / amax.clamp_min(1e-30))
+        keep = 1.0 - mod.p
+        captured["mask"] = torch.where(amax > 0, (ratio > 0.5).float() / keep, torch.full_like(ratio, 1.0 / keep))
+        captured["dead"] = int((amax == 0).sum())
+    torch.manual_seed(seed)
+    hnd = model.dropout.register_forward_hook(hook)
+    out = model(imgs)
+    hnd.remove()
+    if "mask" in captured:
+        rec["drop_mask"] = captured["mask"].numpy().astype(np.float32)
+        assert captured["dead"] == 0, "a bridge channel is identically zero: its dropout decision cannot be recovered"
+    loss = Focal_Loss(out, pngs, weights, num_classes=num_classes) if focal else CE_Loss(out, pngs, weights, num_classes=num_classes)
+    if dice:
+        loss = loss + Dice_loss(out, labels)
+    with torch.no_grad():
+        fs = f_score(out, labels).item()
+    loss.backward()
+    rec.update({"logits": out.detach().numpy().astype(np.float32), "loss": np.float64(loss.item()), "f_score": np.float64(fs),
+                "cls_w": np.asarray(cls_w, np.float32), "meta": np.asarray([num_classes, n, h, w, seed, int(dice), int(focal)])})
+    for name, p in model.named_parameters():
+        g = p.grad.detach().reshape(-1)
+        rec["gnorm:" + name] = np.float64(g.double().norm().item())
+        rec["g:" + name] = (g if g.numel() <= 1024 else g[torch.linspace(0, g.numel() - 1, 1024).long()]).numpy().astype(np.float32)
+    for name, b in model.named_buffers():
+        if name.endswith("conv.4.running_mean") or name.endswith("conv.4.running_var"):
+            rec["buf:" + name] = b.detach().numpy()
+    model.eval()
+    with torch.no_grad():
+        rec["logits_eval"] = model(imgs).numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, f"{variant}_{tag}.npz"), **rec)
+    print(variant, tag, "loss", loss.item(), "dropmask" if "drop_mask" in rec else "")
+
+
 def loss_case():
     g = torch.Generator().manual_seed(7)
     rec = {}
@@ -178,5 +233,9 @@ if __name__ == "__main__":
     traditional_case("nc21_cedice", 21, 2, 32, 64, 4, [1] * 21, dice=True, focal=False)
     # BASELINE configs[2]: Unet-ResNet50, 21 classes, CE + Dice (batch >= 2 because of BatchNorm, train.py:139-140)
     resnet_case("nc21_cedice", 21, 2, 64, 64, 7, [1] * 21, dice=True)
+    # UltraLightweightUnet family (UltraLightweightUnet*_Train.py): focal+dice with class weights, and CE+dice
+    ulu_case("ultralight", "nc21_cedice", 21, 2, 64, 64, 8, [1] * 21, dice=True, focal=False)
+    ulu_case("ultralight_large", "nc4_focaldice", 4, 2, 64, 64, 9, [1, 15, 1.5, 2], dice=True, focal=True)
+    ulu_case("ultralight_large_optimized", "nc21_cedice", 21, 2, 32, 64, 10, [1] * 21, dice=True, focal=False)
     loss_case()
     hist_case()

@@ -525,3 +525,133 @@ def resnet_unet_train_step(sd, imgs, pngs, cls_weights, num_classes, dice=True, 
     names = [k for k, v in p.items() if v.requires_grad]
     grads = torch.autograd.grad(loss, [p[k] for k in names])
     return loss.detach(), logits.detach(), dict(zip(names, grads)), stats
+
+
+# ----------------------------------------------------------------------------------------------- UltraLightweightUnet family
+# name: (stage widths, minimum mid channels, SE reduced-channel rule or None, bridge Dropout2d p)
+ULU_VARIANTS = {
+    "ultralight": ((32, 64, 128, 256, 512), 8, None, 0.0),                                   # nets/UltraLightweightUnet.py:57-108
+    "ultralight_large": ((64, 128, 256, 512, 1024), 16, lambda c: max(8, c // 4), 0.2),      # nets/UltraLightweightUnet_large.py:55-113
+    "ultralight_large_optimized": ((44, 88, 176, 352, 704), 16, lambda c: max(8, c // 4), 0.15),   # ..._large_optimized.py:51-109
+}
+
+
+def ulu_param_shapes(num_classes, variant):
+    """state_dict-ordered trainable tensors (module registration order: enc1-4, bridge, dec4-1, final, se1-4)."""
+    widths, mid_min, se_rule, _ = ULU_VARIANTS[variant]
+    sh = {}
+
+    def block(p, cin, cout):            # LightConvBlock, nets/UltraLightweightUnet_large.py:19-33
+        mid = max(mid_min, cout // 2)
+        sh[p + ".conv.0.weight"] = (mid, cin, 1, 1); sh[p + ".conv.0.bias"] = (mid,)
+        sh[p + ".conv.1.weight"] = (mid,); sh[p + ".conv.1.bias"] = (mid,)
+        sh[p + ".conv.3.depthwise.weight"] = (mid, 1, 3, 3); sh[p + ".conv.3.depthwise.bias"] = (mid,)
+        sh[p + ".conv.3.pointwise.weight"] = (cout, mid, 1, 1); sh[p + ".conv.3.pointwise.bias"] = (cout,)
+        sh[p + ".conv.4.weight"] = (cout,); sh[p + ".conv.4.bias"] = (cout,)
+
+    cin = 3
+    for i in range(4):
+        block(f"enc{i + 1}", cin, widths[i]); cin = widths[i]
+    block("bridge", widths[3], widths[4])
+    for k in (4, 3, 2, 1):
+        block(f"dec{k}", widths[k] + widths[k - 1], widths[k - 1])
+    sh["final.weight"] = (num_classes, widths[0], 1, 1); sh["final.bias"] = (num_classes,)
+    if se_rule is not None:
+        for i in range(4):
+            c, r = widths[i], se_rule(widths[i])
+            sh[f"se{i + 1}.fc.0.weight"] = (r, c); sh[f"se{i + 1}.fc.0.bias"] = (r,)
+            sh[f"se{i + 1}.fc.2.weight"] = (c, r); sh[f"se{i + 1}.fc.2.bias"] = (c,)
+    return sh
+
+
+def make_ulu_params(num_classes, variant, seed=11):
+    """Deterministic synthetic state_dict: He-scaled convs (BatchNorm follows each), BN weight 1 + 0.1 N, biases 0.05 N,
+    SE linears at 1/sqrt(fan_in), fresh running statistics."""
+    sd = {}
+    shapes = ulu_param_shapes(num_classes, variant)
+    for k, (name, shape) in enumerate(shapes.items()):
+        g = torch.Generator().manual_seed(seed * 1000 + 5000 + k)
+        is_bn = (".conv.1." in name or ".conv.4." in name)
+        if len(shape) == 4:
+            fan_in = shape[1] * shape[2] * shape[3]
+            gn = 0.5 if name == "final.weight" else 1.0
+            sd[name] = torch.randn(shape, generator=g) * (gn * (2.0 / fan_in) ** 0.5)
+        elif len(shape) == 2:
+            sd[name] = torch.randn(shape, generator=g) * (1.0 / shape[1]) ** 0.5
+        elif is_bn and name.endswith(".weight"):
+            sd[name] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        else:
+            sd[name] = 0.05 * torch.randn(shape, generator=g)
+        if is_bn and name.endswith(".bias"):
+            base = name[:-len(".bias")]
+            sd[base + ".running_mean"] = torch.zeros(shape)
+            sd[base + ".running_var"] = torch.ones(shape)
+            sd[base + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+    return sd
+
+
+def _ulu_block(sd, stats, p, x, training, b):
+    """LightConvBlock: 1x1 conv, BN, ReLU, depthwise 3x3 (+bias), 1x1 conv, BN, ReLU.  bf16 storage model: the CUDA path
+    stores conv outputs, BN outputs and the depthwise output in bf16, weights of the tensor-core 1x1 convs in bf16; the
+    depthwise weights stay fp32."""
+    z = _rn_conv(sd, p + ".conv.0.weight", x, bias=sd[p + ".conv.0.bias"], bf16=b)
+    y = _rn_bn(sd, stats, p + ".conv.1", z, training, True, bf16=b)
+    wdw = sd[p + ".conv.3.depthwise.weight"]
+    d = F.conv2d(_r(y, fwd=False) if b else y, wdw, sd[p + ".conv.3.depthwise.bias"], padding=1, groups=wdw.shape[0])
+    if b:
+        d = _r(d)
+    z = _rn_conv(sd, p + ".conv.3.pointwise.weight", d, bias=sd[p + ".conv.3.pointwise.bias"], bf16=b)
+    return _rn_bn(sd, stats, p + ".conv.4", z, training, True, bf16=b)
+
+
+def _ulu_se(sd, name, x, b):
+    """LightSEBlock (nets/UltraLightweightUnet_large.py:36-52): x * sigmoid(fc2(relu(fc1(avgpool(x)))))."""
+    y = x.mean(dim=(2, 3))
+    y = F.relu(F.linear(y, sd[name + ".fc.0.weight"], sd[name + ".fc.0.bias"]))
+    y = torch.sigmoid(F.linear(y, sd[name + ".fc.2.weight"], sd[name + ".fc.2.bias"]))
+    out = x * y[:, :, None, None]
+    return _r(out) if b else out
+
+
+def ulu_forward(sd, x, variant, training=True, stats=None, bf16_storage=False, drop_mask=None):
+    """forward() of the three UltraLightweightUnet modules.  drop_mask: the [N, C_bridge] Dropout2d multiplier (already
+    divided by 1-p) to apply in training; None = no dropout (eval, or the base variant, whose forward never calls it)."""
+    widths, _, se_rule, p_drop = ULU_VARIANTS[variant]
+    b = bf16_storage
+    if stats is None:
+        stats = {k: v.clone() for k, v in sd.items() if "running_" in k or "num_batches" in k}
+    if b:
+        x = _r(x)
+    skips = []
+    for i in range(1, 5):
+        if i > 1:
+            x = F.max_pool2d(x, 2, 2)
+        x = _ulu_block(sd, stats, f"enc{i}", x, training, b)
+        if se_rule is not None:
+            x = _ulu_se(sd, f"se{i}", x, b)
+        skips.append(x)
+    x = _ulu_block(sd, stats, "bridge", F.max_pool2d(x, 2, 2), training, b)
+    if training and p_drop > 0 and drop_mask is not None:
+        x = x * drop_mask[:, :, None, None]
+        if b:
+            x = _r(x)
+    for k in (4, 3, 2, 1):
+        skip = skips[k - 1]
+        up = F.interpolate(x, size=skip.shape[2:], mode="bilinear", align_corners=True)
+        if b:
+            up = _r(up)
+        x = _ulu_block(sd, stats, f"dec{k}", torch.cat([up, skip], 1), training, b)
+    logits = F.conv2d(x, sd["final.weight"], sd["final.bias"])
+    return logits, stats        # the trailing interpolate to the input size is the identity (same size, align_corners)
+
+
+def ulu_train_step(sd, imgs, pngs, cls_weights, num_classes, variant, dice=True, focal=False, bf16_storage=False, drop_mask=None):
+    p = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and "running_" not in k else v.clone())
+         for k, v in sd.items()}
+    logits, stats = ulu_forward(p, imgs, variant, training=True, bf16_storage=bf16_storage, drop_mask=drop_mask)
+    loss = focal_loss(logits, pngs, cls_weights, num_classes) if focal else ce_loss(logits, pngs, cls_weights, num_classes)
+    if dice:
+        loss = loss + dice_loss(logits, one_hot(pngs, num_classes))
+    names = [k for k, v in p.items() if v.requires_grad]
+    grads = torch.autograd.grad(loss, [p[k] for k in names])
+    return loss.detach(), logits.detach(), dict(zip(names, grads)), stats

@@ -386,3 +386,114 @@ def test_conv_large_channel_counts(b2u, cuda_device):
     dz1 = nhwc(torch.randn(2, 2048, 8, 8, generator=g), dev)
     assert rel(nchw(ops.conv_dgrad(dz1, wd1, 512, taps=1)), F.conv_transpose2d(nchw(dz1), w1.to(BF).float())) <= 6e-3
     assert rel(ops.conv_wgrad(xs, dz1, taps=1), torch.nn.grad.conv2d_weight(nchw(xs), w1.shape, nchw(dz1))) <= 1e-4
+
+
+# ------------------------------------------------------------------------------ depthwise conv / squeeze-excite / padding
+@pytest.mark.parametrize("N,H,W,C", [(2, 16, 24, 64), (1, 7, 9, 128), (3, 32, 32, 64), (1, 2, 2, 512)])
+def test_depthwise_conv_kernels(b2u, cuda_device, N, H, W, C):
+    from unet_pytorch_b200 import ops
+    dev = cuda_device
+    g = torch.Generator().manual_seed(N * 100 + C)
+    x = torch.randn(N, C, H, W, generator=g).to(BF).float()
+    w = torch.randn(C, 1, 3, 3, generator=g) * 0.3
+    b = torch.randn(C, generator=g) * 0.1
+    dy = torch.randn(N, C, H, W, generator=g).to(BF).float()
+    xr = x.clone().requires_grad_(True); wr = w.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
+    y_ref = F.conv2d(xr, wr, br, padding=1, groups=C)
+    y_ref.backward(dy)
+    xd, dyd, wd = nhwc(x, dev), nhwc(dy, dev), w.reshape(C, 9).contiguous().to(dev)
+    y = ops.dwconv3x3(xd, wd, b.to(dev))
+    assert rel(nchw(y), y_ref.detach()) <= 6e-3
+    dx = ops.dwconv3x3(dyd, wd, None, flip=True)
+    assert rel(nchw(dx), xr.grad) <= 6e-3
+    dw, db = ops.dwconv3x3_wgrad(xd, dyd)
+    assert rel(dw.reshape(C, 1, 3, 3), wr.grad) <= 1e-4
+    assert rel(db, br.grad) <= 1e-4
+
+
+@pytest.mark.parametrize("N,H,W,C,Cp,R", [(2, 16, 16, 64, 64, 16), (3, 8, 8, 44, 64, 11), (2, 4, 4, 512, 512, 128), (1, 32, 32, 176, 192, 44)])
+def test_squeeze_excite_kernels(b2u, cuda_device, N, H, W, C, Cp, R):
+    """spatial_reduce -> se_fc_fwd -> scale_nc and the matching backward against autograd of the module's math
+    (nets/UltraLightweightUnet_large.py:36-52); channels C..Cp are zero padding and must stay zero."""
+    from unet_pytorch_b200 import ops
+    dev = cuda_device
+    g = torch.Generator().manual_seed(C + R)
+    x = torch.zeros(N, Cp, H, W); x[:, :C] = torch.randn(N, C, H, W, generator=g).to(BF).float()
+    dy = torch.zeros(N, Cp, H, W); dy[:, :C] = torch.randn(N, C, H, W, generator=g).to(BF).float()
+    w1 = (torch.randn(R, C, generator=g) / C ** 0.5); b1 = torch.randn(R, generator=g) * 0.1
+    w2 = (torch.randn(C, R, generator=g) / R ** 0.5); b2 = torch.randn(C, generator=g) * 0.1
+    xr = x[:, :C].clone().requires_grad_(True)
+    ps = [t.clone().requires_grad_(True) for t in (w1, b1, w2, b2)]
+    s_ref = torch.sigmoid(F.linear(F.relu(F.linear(xr.mean(dim=(2, 3)), ps[0], ps[1])), ps[2], ps[3]))
+    y_ref = xr * s_ref[:, :, None, None]
+    y_ref.backward(dy[:, :C])
+    xd, dyd = nhwc(x, dev), nhwc(dy, dev)
+    pooled = ops.spatial_reduce(xd, scale=1.0 / (H * W))
+    assert rel(pooled[:, :C], x[:, :C].mean(dim=(2, 3))) <= 1e-5
+    hidden, sc = ops.se_fc_fwd(pooled, w1.to(dev), b1.to(dev), w2.to(dev), b2.to(dev), C)
+    assert rel(sc[:, :C], s_ref.detach()) <= 1e-5
+    y = ops.scale_nc(xd, sc)
+    assert rel(nchw(y)[:, :C], y_ref.detach()) <= 6e-3
+    assert nchw(y)[:, C:].abs().max().item() == 0 if Cp > C else True
+    dscale = ops.spatial_reduce(dyd, xd)
+    grads = [torch.empty_like(t, device=dev) for t in (w1, b1, w2, b2)]
+    dpooled = ops.se_fc_bwd(dscale, pooled, hidden, sc, w1.to(dev), w2.to(dev), C, 1.0 / (H * W), dw1=grads[0], db1=grads[1],
+                            dw2=grads[2], db2=grads[3])
+    for got, p in zip(grads, ps):
+        assert rel(got, p.grad) <= 1e-4
+    dx = ops.scale_nc(dyd, sc, add=dpooled)
+    assert rel(nchw(dx)[:, :C], xr.grad) <= 6e-3
+    if Cp > C:
+        assert nchw(dx)[:, C:].abs().max().item() == 0
+
+
+def test_padded_channel_convs(b2u, cuda_device):
+    """Channel counts that are not multiples of 64 (UltraLightweightUnet_large_optimized: 44/88/176/352/704, mids 22..352)
+    run on the tensor-core kernels with zero-padded operands: pack_weights_multi pads, the conv sees pad64 channels."""
+    import struct
+    from unet_pytorch_b200 import ops
+    from unet_pytorch_b200.graph import pad64
+    dev = cuda_device
+    g = torch.Generator().manual_seed(5)
+    for (cout, c0, c1, taps) in ((22, 3, 0, 1), (44, 22, 0, 1), (176, 352, 176, 1), (88, 44, 0, 9), (352, 704, 352, 1)):
+        k = 3 if taps == 9 else 1
+        w = (torch.randn(cout, c0 + c1, k, k, generator=g) / ((c0 + c1) * k * k) ** 0.5).to(dev)
+        c0p, c1p, coutp = pad64(c0), (pad64(c1) if c1 else 0), pad64(cout)
+        wf = torch.zeros((coutp, taps * (c0p + c1p)), dtype=BF, device=dev)
+        wd = torch.zeros((c0p + c1p, taps * coutp), dtype=BF, device=dev)
+        blob = struct.pack("<QQQqiiiiiiii", w.data_ptr(), wf.data_ptr(), wd.data_ptr(), 0, cout, c0 + c1, taps, 0, c0, c0p, c0p + c1p, coutp)
+        count = ((cout + 31) // 32) * ((c0 + c1 + 31) // 32)
+        table = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+        ops.check(ops.lib().b2u_pack_weights_multi(table.data_ptr(), 1, count, ops.stream_ptr()))
+        N, H, W = 2, 16, 16
+        x0 = torch.zeros(N, c0p, H, W); x0[:, :c0] = torch.randn(N, c0, H, W, generator=g).to(BF).float()
+        x1 = None
+        if c1:
+            x1 = torch.zeros(N, c1p, H, W); x1[:, :c1] = torch.randn(N, c1, H, W, generator=g).to(BF).float()
+        bias = torch.zeros(coutp); bias[:cout] = torch.randn(cout, generator=g) * 0.1
+        xin = x0[:, :c0] if x1 is None else torch.cat([x0[:, :c0], x1[:, :c1]], 1)
+        wr = w.cpu().to(BF).float()
+        y_ref = F.conv2d(xin, wr, bias[:cout], padding=k // 2)
+        y = ops.conv_fprop(nhwc(x0, dev), wf, bias.to(dev), coutp, taps=taps, relu=False, x1=nhwc(x1, dev) if c1 else None)
+        yh = nchw(y)
+        assert rel(yh[:, :cout], y_ref) <= 6e-3, (cout, c0, c1)
+        if coutp > cout:
+            assert yh[:, cout:].abs().max().item() == 0
+        dz = torch.zeros(N, coutp, H, W); dz[:, :cout] = torch.randn(N, cout, H, W, generator=g).to(BF).float()
+        dx_ref = F.conv_transpose2d(dz[:, :cout], wr, padding=k // 2)
+        if c1:
+            d0, d1 = ops.conv_dgrad(nhwc(dz, dev), wd, c0p, taps=taps, C1=c1p)
+            assert rel(nchw(d0)[:, :c0], dx_ref[:, :c0]) <= 6e-3 and rel(nchw(d1)[:, :c1], dx_ref[:, c0:]) <= 6e-3
+            assert nchw(d0)[:, c0:].abs().max().item() == 0 if c0p > c0 else True
+        else:
+            d0 = ops.conv_dgrad(nhwc(dz, dev), wd, c0p, taps=taps)
+            d0 = d0[0] if isinstance(d0, tuple) else d0
+            assert rel(nchw(d0)[:, :c0], dx_ref) <= 6e-3
+
+
+def test_padded_input_conversion(b2u, cuda_device):
+    from unet_pytorch_b200 import ops
+    x = torch.randn(2, 3, 16, 32)
+    y = ops.nchw_to_nhwc_bf16_padded(x.to(cuda_device), 64)
+    assert tuple(y.shape) == (2, 16, 32, 64)
+    assert torch.equal(y[..., :3].cpu(), x.permute(0, 2, 3, 1).to(BF)) and y[..., 3:].abs().max().item() == 0

@@ -359,3 +359,87 @@ def test_resnet50_frozen_backbone_and_trainer(b2u, cuda_device):
     tr3 = b2u.UnetTrainer(num_classes=C, device=dev, state_dict=sd, lr=1e-3, model="unet_resnet50")
     losses = [tr3.train_step(imgs.to(dev), pngs.to(dev))[0].item() for _ in range(6)]
     assert losses[-1] < losses[0]
+
+
+# ------------------------------------------------------------------------------------------------ UltraLightweightUnet family
+ULU_CASES = [("ultralight", "UltraLightweightUnet", "nc21_cedice"), ("ultralight_large", "UltraLightweightUnet_large", "nc4_focaldice"),
+             ("ultralight_large_optimized", "UltraLightweightUnet_large_optimized", "nc21_cedice")]
+
+
+@pytest.mark.parametrize("variant,cls,tag", ULU_CASES)
+def test_ultralight_unet_dropin(b2u, cuda_device, golden_dir, variant, cls, tag):
+    """nets/UltraLightweightUnet*.py drop-ins against the reference's golden forward/backward (train-mode BatchNorm,
+    depthwise-separable blocks, SE, the reference's own Dropout2d mask replayed).  Every conv sits in front of a BatchNorm,
+    so gradients are judged against the bf16-storage model's own distance from fp32 (same policy as TraditionalUnet)."""
+    import importlib
+    dev = cuda_device
+    g = np.load(os.path.join(golden_dir, f"{variant}_{tag}.npz"))
+    C, n, h, w, seed, dice, focal = [int(v) for v in g["meta"]]
+    sd = O.make_ulu_params(C, variant, seed=11)
+    imgs, pngs = O.make_inputs(n, C, h, w, seed=seed)
+    weights = torch.from_numpy(g["cls_w"])
+    mask = torch.from_numpy(g["drop_mask"]) if "drop_mask" in g.files else None
+    l32, z32, g32, s32 = O.ulu_train_step(sd, imgs, pngs, weights, C, variant, dice=bool(dice), focal=bool(focal), drop_mask=mask)
+    lbf, zbf, gbf, sbf = O.ulu_train_step(sd, imgs, pngs, weights, C, variant, dice=bool(dice), focal=bool(focal), drop_mask=mask,
+                                          bf16_storage=True)
+    Net = getattr(importlib.import_module(f"unet_pytorch_b200.nets.{cls}"), cls)
+    model = Net(num_classes=C)
+    assert list(model.state_dict().keys()) == list(sd.keys())
+    model.load_state_dict(sd)
+    model = model.train().to(dev)
+    model._engine_for(dev).dropout_override = mask
+    outputs = model(imgs.to(dev))
+    lossf = b2u.Focal_Loss if focal else b2u.CE_Loss
+    loss = lossf(outputs, pngs.to(dev), weights.to(dev), num_classes=C)
+    if dice:
+        loss = loss + b2u.Dice_loss(outputs, O.one_hot(pngs, C).to(dev))
+    loss.backward()
+    noise_z, noise_g = rel(zbf, z32), _global_rel(gbf, g32)
+    ref = torch.from_numpy(g["logits"])
+    assert outputs.shape == ref.shape
+    assert rel(outputs, ref) <= max(1.5 * noise_z, 1e-2)
+    assert rel(outputs, zbf) <= max(0.75 * noise_z, 5e-3)
+    assert abs(loss.item() - float(g["loss"])) <= 1e-2 * abs(float(g["loss"]))
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    assert all(v is not None and torch.isfinite(v).all() for v in grads.values())
+    live = {k: v for k, v in grads.items() if not (k.endswith(".conv.0.bias") or k.endswith("wise.bias"))}    # zero-gradient biases
+    assert _global_rel(live, {k: g32[k] for k in live}) <= 1.5 * noise_g
+    assert _global_rel(live, {k: gbf[k] for k in live}) <= 1.2 * noise_g
+    for k in ("final.weight", "final.bias"):
+        assert rel(grads[k], g32[k]) <= 2e-2, k
+    for name, b in model.named_buffers():
+        if name.endswith("running_mean"):
+            assert rel(b, s32[name]) <= 6e-2, name
+        elif name.endswith("running_var"):
+            assert rel(b, s32[name]) <= 2e-2, name
+        elif name.endswith("num_batches_tracked"):
+            assert int(b) == 1
+    model.eval()
+    with torch.no_grad():
+        ev = model(imgs.to(dev))
+    sd_after = dict(sd); sd_after.update({k: v.cpu() for k, v in model.named_buffers()})
+    with torch.no_grad():
+        ev_ref, _ = O.ulu_forward(sd_after, imgs, variant, training=False)
+    assert rel(ev, ev_ref) <= 3e-2
+
+
+def test_ultralight_trainer_and_dropout(b2u, cuda_device):
+    dev = cuda_device
+    C, variant = 4, "ultralight_large_optimized"
+    sd = O.make_ulu_params(C, variant, seed=11)
+    imgs, pngs = O.make_inputs(2, C, 64, 64, seed=12)
+    tr = b2u.UnetTrainer(num_classes=C, device=dev, state_dict=sd, lr=1e-3, model=variant)
+    losses = [tr.train_step(imgs.to(dev), pngs.to(dev))[0].item() for _ in range(8)]
+    assert all(np.isfinite(losses)) and min(losses[-3:]) < losses[0]
+    # Dropout2d: training draws a fresh per-(sample, channel) mask, eval is deterministic
+    from unet_pytorch_b200.nets.UltraLightweightUnet_large import UltraLightweightUnet_large
+    model = UltraLightweightUnet_large(num_classes=C)
+    model.load_state_dict(O.make_ulu_params(C, "ultralight_large", seed=11))
+    model = model.to(dev).train()
+    with torch.no_grad():
+        a, b = model(imgs.to(dev)), model(imgs.to(dev))
+    assert not torch.equal(a, b)
+    model.eval()
+    with torch.no_grad():
+        a, b = model(imgs.to(dev)), model(imgs.to(dev))
+    assert torch.equal(a, b)

@@ -153,3 +153,41 @@ def test_resnet50_unet_matches_reference_golden(golden_dir):
         ev, _ = O.resnet_unet_forward(sd_after, imgs, training=False)
     ref_ev = torch.from_numpy(g["logits_eval"])
     assert ((ev - ref_ev).norm() / ref_ev.norm()).item() <= 1e-5
+
+
+ULU_FIXTURES = [("ultralight", "nc21_cedice"), ("ultralight_large", "nc4_focaldice"), ("ultralight_large_optimized", "nc21_cedice")]
+
+
+@pytest.mark.parametrize("variant,tag", ULU_FIXTURES)
+def test_ultralight_unet_matches_reference_golden(golden_dir, variant, tag):
+    """UltraLightweightUnet / _large / _large_optimized restatement (depthwise-separable blocks, SE, Dropout2d replayed from
+    the mask the reference drew) against the reference's own forward/backward."""
+    g = np.load(os.path.join(golden_dir, f"{variant}_{tag}.npz"))
+    C, n, h, w, seed, dice, focal = [int(v) for v in g["meta"]]
+    sd = O.make_ulu_params(C, variant, seed=11)
+    imgs, pngs = O.make_inputs(n, C, h, w, seed=seed)
+    mask = torch.from_numpy(g["drop_mask"]) if "drop_mask" in g.files else None
+    loss, logits, grads, stats = O.ulu_train_step(sd, imgs, pngs, torch.from_numpy(g["cls_w"]), C, variant, dice=bool(dice),
+                                                  focal=bool(focal), drop_mask=mask)
+    ref = torch.from_numpy(g["logits"])
+    assert ((logits - ref).norm() / ref.norm()).item() <= 1e-5
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    for name, gr in grads.items():
+        gn = float(g["gnorm:" + name])
+        if ".conv.0.bias" in name or "pointwise.bias" in name or "depthwise.bias" in name:
+            # a constant per channel ahead of BatchNorm (directly, or through the linear pointwise conv): true gradient is zero
+            assert gr.abs().max().item() <= 1e-4 and gn <= 1e-3, name      # fp32 cancellation residue
+            continue
+        assert abs(gr.double().norm().item() - gn) <= 5e-4 * gn + 1e-9, name
+        flat = gr.reshape(-1)
+        samp = flat if flat.numel() <= 1024 else flat[torch.linspace(0, flat.numel() - 1, 1024).long()]
+        r = torch.from_numpy(g["g:" + name])
+        assert ((samp - r).norm() / r.norm().clamp_min(1e-12)).item() <= 2e-3, name
+    for key in g.files:
+        if key.startswith("buf:"):
+            assert torch.allclose(stats[key[4:]], torch.from_numpy(g[key]), rtol=1e-5, atol=1e-6), key
+    sd_after = dict(sd); sd_after.update(stats)
+    with torch.no_grad():
+        ev, _ = O.ulu_forward(sd_after, imgs, variant, training=False)
+    ref_ev = torch.from_numpy(g["logits_eval"])
+    assert ((ev - ref_ev).norm() / ref_ev.norm()).item() <= 1e-5

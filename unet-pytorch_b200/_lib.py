@@ -21,6 +21,7 @@ SIGNATURES = {
     "b2u_pack_weights_multi": (I, [P, I, LL, P]),
     "b2u_nhwc_bf16_to_nchw_f32": (I, [P, P, I, I, I, I, P]),
     "b2u_nchw_f32_to_nhwc_bf16": (I, [P, P, I, I, I, I, P]),
+    "b2u_nchw_f32_to_nhwc_bf16_padded": (I, [P, P, I, I, I, I, I, P]),
     "b2u_conv_fprop": (I, [P, I, P, I, P, P, P, I, I, I, I, I, I, I, P]),
     "b2u_conv_dgrad": (I, [P, I, P, P, I, P, I, P, I, I, I, I, I, P]),
     "b2u_conv_wgrad_workspace": (SZ, [I, I, I, I, I, I]),
@@ -43,6 +44,14 @@ SIGNATURES = {
     "b2u_maxpool3x3s2_fwd": (I, [P, P, I, I, I, I, P]),
     "b2u_maxpool3x3s2_bwd": (I, [P, P, P, I, I, I, I, P]),
     "b2u_add_bf16": (I, [P, P, P, LL, P]),
+    "b2u_dwconv3x3_fwd": (I, [P, P, P, P, I, I, I, I, I, P]),
+    "b2u_dwconv3x3_wgrad_workspace": (SZ, [I]),
+    "b2u_dwconv3x3_wgrad": (I, [P, P, P, P, P, SZ, I, I, I, I, P]),
+    "b2u_spatial_reduce_workspace_floats": (I, [I, I]),
+    "b2u_spatial_reduce": (I, [P, P, P, P, SZ, I, LL, I, F, P]),
+    "b2u_scale_nc": (I, [P, P, P, P, I, LL, I, P]),
+    "b2u_se_fc_fwd": (I, [P, P, P, P, P, P, P, I, I, I, I, P]),
+    "b2u_se_fc_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, F, P]),
     "b2u_head_fwd": (I, [P, P, P, P, I, I, I, I, I, P]),
     "b2u_head_bwd_workspace": (SZ, []),
     "b2u_head_bwd": (I, [P, P, P, P, P, P, P, SZ, I, I, I, I, I, I, P]),

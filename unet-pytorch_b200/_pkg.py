@@ -1,7 +1,7 @@
 """Public surface of the package (see unet_pytorch_b200/__init__.py for why this is not __init__)."""
 from . import _lib, ops  # noqa: F401
 from .engine import TraditionalUnetEngine, UNetEngine, VGGUnetEngine, vgg_unet_param_shapes  # noqa: F401
-from .graph import GraphEngine, ResNet50UnetEngine  # noqa: F401
+from .graph import GraphEngine, ResNet50UnetEngine, UltraLightUnetEngine  # noqa: F401
 from .nets.unet import Unet  # noqa: F401
 from .nets.TraditionalUnet import TraditionalUnet  # noqa: F401
 from .nets.unet_training import CE_Loss, Dice_loss, Focal_Loss, ce_dice_loss  # noqa: F401

@@ -145,26 +145,32 @@ pack_weights_multi_kernel(const PackEntry* __restrict__ table, int n) {
     }
     return;
   }
-  const int tiles_ci = e.Cin / 32;
+  const int tiles_ci = (e.Cin + 31) / 32;
   const int co0 = (lb / tiles_ci) * 32, ci0 = (lb % tiles_ci) * 32;
-  const int run = 32 * e.taps;                       // contiguous floats per co row of the tile
-  for (int i = threadIdx.x; i < 32 * run; i += blockDim.x) {
+  const int nco = min(32, e.Cout - co0), nci = min(32, e.Cin - ci0);   // ragged last tiles
+  const int run = nci * e.taps;                      // contiguous floats per co row of the tile
+  for (int i = threadIdx.x; i < nco * run; i += blockDim.x) {
     const int r = i / run, j = i - r * run;
     tile[r][j] = e.w[(static_cast<size_t>(co0 + r) * e.Cin + ci0) * e.taps + j];      // j = ci_local * taps + tap
   }
   __syncthreads();
   const size_t kf = static_cast<size_t>(e.taps) * e.Ctot_pad, kd = static_cast<size_t>(e.taps) * e.Cout_pad;
-  const int pc0 = ci0 < e.C0 ? ci0 : ci0 - e.C0 + e.C0_pad;      // padded position of the tile's first input channel
-  for (int i = threadIdx.x; i < 32 * run; i += blockDim.x) {
+  for (int i = threadIdx.x; i < 32 * 32 * e.taps; i += blockDim.x) {
     // fprop operand: (co, tap, ci) with ci fastest
     const int ci = i & 31, t = (i >> 5) % e.taps, r = i / (32 * e.taps);
-    e.wf[(co0 + r) * kf + static_cast<size_t>(t) * e.Ctot_pad + pc0 + ci] = __float2bfloat16_rn(tile[r][ci * e.taps + t]);
+    if (r >= nco || ci >= nci) continue;
+    const int gci = ci0 + ci;
+    const int pc = gci < e.C0 ? gci : gci - e.C0 + e.C0_pad;       // padded position of this input channel
+    e.wf[(co0 + r) * kf + static_cast<size_t>(t) * e.Ctot_pad + pc] = __float2bfloat16_rn(tile[r][ci * e.taps + t]);
   }
   if (e.wd) {
-    for (int i = threadIdx.x; i < 32 * run; i += blockDim.x) {
+    for (int i = threadIdx.x; i < 32 * 32 * e.taps; i += blockDim.x) {
       // dgrad operand: (ci, flipped tap, co) with co fastest
       const int r = i & 31, t = (i >> 5) % e.taps, ci = i / (32 * e.taps);
-      e.wd[(pc0 + ci) * kd + static_cast<size_t>(e.taps - 1 - t) * e.Cout_pad + co0 + r] = __float2bfloat16_rn(tile[r][ci * e.taps + t]);
+      if (r >= nco || ci >= nci) continue;
+      const int gci = ci0 + ci;
+      const int pc = gci < e.C0 ? gci : gci - e.C0 + e.C0_pad;
+      e.wd[pc * kd + static_cast<size_t>(e.taps - 1 - t) * e.Cout_pad + co0 + r] = __float2bfloat16_rn(tile[r][ci * e.taps + t]);
     }
   }
 }
@@ -468,10 +474,35 @@ __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_b
   }
 }
 
+// NCHW fp32 -> NHWC bf16 with the channel dimension zero-padded to Cpad (multiple of 8): one thread = one pixel x 8
+// output channels; plane reads are coalesced across the pixels of a warp
+__global__ void nchw_f32_to_nhwc_bf16_padded_kernel(const float* __restrict__ x, uint4* __restrict__ y, int C, long long HW,
+                                                    int Cpad8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // pixel index within the image
+  const int n = blockIdx.z, q = blockIdx.y;
+  if (i >= HW) return;
+  float f[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = q * 8 + k;
+    f[k] = c < C ? __ldg(x + (static_cast<size_t>(n) * C + c) * HW + i) : 0.f;
+  }
+  y[(static_cast<size_t>(n) * HW + i) * Cpad8 + q] = pack8(f);
+}
+
 }  // namespace b2u
 
 extern "C" {
 using namespace b2u;
+
+int b2u_nchw_f32_to_nhwc_bf16_padded(const float* x, void* y, int N, int C, int H, int W, int Cpad, void* stream) {
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || Cpad < C || Cpad % 8 != 0) return set_error(B2U_ERR_SHAPE, "nchw->nhwc padded: bad shape");
+  const long long HW = static_cast<long long>(H) * W;
+  dim3 grid(static_cast<unsigned>((HW + 255) / 256), Cpad / 8, N);
+  nchw_f32_to_nhwc_bf16_padded_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<uint4*>(y), C, HW, Cpad / 8);
+  B2U_CHECK_LAUNCH("nchw_f32_to_nhwc_bf16_padded");
+  return 0;
+}
 
 int b2u_im2col_first(const float* x, void* col, int N, int Cin, int H, int W, void* stream) {
   if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || 9 * Cin > 64) return set_error(B2U_ERR_SHAPE, "im2col_first: bad shape (Cin=%d)", Cin);
@@ -492,8 +523,8 @@ int b2u_pack_weights(const float* w, void* wf, void* wd, int Cout, int Cin, int 
 
 // table: n entries of {const float* w; bf16* wf; bf16* wd; int64 start; int32 Cout, Cin, taps, first, C0, C0_pad,
 // Ctot_pad, Cout_pad} (64 bytes each) in DEVICE memory; start = index of the layer's first work block, a layer has
-// (Cout/32)*(Cin/32) blocks (first layer: ceil(Cout/32)); total_blocks = their sum.  Real Cout, Cin and C0 must be
-// multiples of 32 (except the first layer's Cin); operand padding must be zeroed by the caller once.
+// ceil(Cout/32)*ceil(Cin/32) blocks (first layer: ceil(Cout/32)); total_blocks = their sum.  Any real channel counts;
+// operand padding must be zeroed by the caller once.
 int b2u_pack_weights_multi(const void* table, int n, long long total_blocks, void* stream) {
   static_assert(sizeof(b2u::PackEntry) == 64, "PackEntry layout is part of the ABI");
   if (n <= 0 || total_blocks <= 0 || total_blocks > 0x7fffffffLL) return set_error(B2U_ERR_ARG, "pack_weights_multi: bad table");

@@ -188,13 +188,11 @@ class UNetEngine:
                         c.wf = torch.zeros((c.cout_p, 64), dtype=torch.bfloat16, device=dev)
                     count = (c.cout + 31) // 32                      # work blocks of this layer
                 else:
-                    if c.cout % 32 or c.cin % 32 or c.c0 % 32:
-                        raise ValueError(f"{c.name}: channel counts must be multiples of 32")
                     if c.wf is None:
                         c.wf = torch.zeros((c.cout_p, 9 * ctot_p), dtype=torch.bfloat16, device=dev)
                     if need_dgrad and c.wd is None:
                         c.wd = torch.zeros((ctot_p, 9 * c.cout_p), dtype=torch.bfloat16, device=dev)
-                    count = (c.cout // 32) * (c.cin // 32)
+                    count = ((c.cout + 31) // 32) * ((c.cin + 31) // 32)
                 wd_ptr = c.wd.data_ptr() if (need_dgrad and not c.first) else 0
                 blob += struct.pack("<QQQqiiiiiiii", w.data_ptr(), c.wf.data_ptr(), wd_ptr, start, c.cout, c.cin,
                                     1 if c.first else 9, 1 if c.first else 0, c.c0, c.c0_p, ctot_p, c.cout_p)

@@ -13,6 +13,14 @@ of libb200unet.so:
   pool3     MaxPool2d(3, 2, 0, ceil_mode=True)                                                  nets/resnet.py:113
   up        UpsamplingBilinear2d(2)                                                             nets/unet.py:13,49
   head      final 1x1 conv -> logits NCHW fp32                                                  nets/unet.py:58,76
+  input     NCHW fp32 image -> NHWC bf16, channels zero-padded to 64 (nets that start with a 1x1 conv)
+  dw        depthwise 3x3 conv + bias                                         nets/UltraLightweightUnet_large.py:9-10
+  se        squeeze-excite: global mean, Linear-ReLU-Linear-Sigmoid, channel scaling              ...:36-52
+  drop      nn.Dropout2d (per-(image, channel) mask)                                              ...:78,97
+  pool2     MaxPool2d(2, 2)
+
+Channel counts that are not multiples of 64 are zero-padded in the activation buffers and operands (padded channels
+stay exactly zero in both directions); parameters and their gradients keep the reference's unpadded shapes.
 
 ReLU handling: a tensor produced by a conv with fused ReLU is marked `fused_relu`; whoever sends a gradient to it
 applies the mask (y > 0) on the way (dgrad epilogue / upsample adjoint / head dgrad), so its gradient is always wrt
@@ -23,6 +31,10 @@ import struct
 import torch
 
 from . import ops
+
+
+def pad64(c):
+    return (c + 63) // 64 * 64
 
 
 class _T:
@@ -38,7 +50,7 @@ def resnet50_unet_program(num_classes):
     convs = {}       # weight name -> (cout, cin, taps)
 
     def conv(out, x, w, cin, cout, taps, stride=1, bias=None, relu=False, x1=None, c1=0):
-        convs[w] = (cout, cin + c1, taps)
+        convs[w] = (cout, cin, c1, taps)
         P.append(dict(op="conv", out=out, x=x, x1=x1, w=w, bias=bias, cin=cin, c1=c1, cout=cout, taps=taps, stride=stride,
                       relu=relu))
 
@@ -85,8 +97,63 @@ def resnet50_unet_program(num_classes):
     return P, convs
 
 
+def ultralight_unet_program(num_classes, widths, mid_min, se_rule=None, dropout_p=0.0):
+    """UltraLightweightUnet / _large / _large_optimized (nets/UltraLightweightUnet*.py): LightConvBlock = 1x1 conv, BN,
+    ReLU, depthwise 3x3, 1x1 conv, BN, ReLU; optional SE after each encoder block; Dropout2d on the bridge; decoder
+    input = cat[upsampled, skip] (upsampled FIRST); 1x1 head.  se_rule: channels -> reduced channels, or None."""
+    P, convs = [], {}
+
+    def conv(out, x, w, cin, cout, bias, x1=None, c1=0):
+        convs[w] = (cout, cin, c1, 1)
+        P.append(dict(op="conv", out=out, x=x, x1=x1, w=w, bias=bias, cin=cin, c1=c1, cout=cout, taps=1, stride=1, relu=False))
+
+    def block(prefix, x, cin, cout, x1=None, c1=0):
+        mid = max(mid_min, cout // 2)
+        conv(prefix + ".z1", x, prefix + ".conv.0.weight", cin, mid, prefix + ".conv.0.bias", x1=x1, c1=c1)
+        P.append(dict(op="bn", out=prefix + ".y1", z=prefix + ".z1", bn=prefix + ".conv.1", c=mid, relu=True, res=None))
+        P.append(dict(op="dw", out=prefix + ".d", x=prefix + ".y1", w=prefix + ".conv.3.depthwise.weight",
+                      bias=prefix + ".conv.3.depthwise.bias", c=mid))
+        conv(prefix + ".z2", prefix + ".d", prefix + ".conv.3.pointwise.weight", mid, cout, prefix + ".conv.3.pointwise.bias")
+        P.append(dict(op="bn", out=prefix + ".out", z=prefix + ".z2", bn=prefix + ".conv.4", c=cout, relu=True, res=None))
+        return prefix + ".out"
+
+    P.append(dict(op="input", out="x", c=3))
+    x, cin, skips = "x", 3, []
+    for i, w_ in enumerate(widths[:4], start=1):
+        if i > 1:
+            P.append(dict(op="pool2", out=f"p{i}", x=x))
+            x = f"p{i}"
+        x = block(f"enc{i}", x, cin, w_)
+        if se_rule is not None:
+            P.append(dict(op="se", out=f"se{i}.out", x=x, se=f"se{i}", c=w_, r=se_rule(w_)))
+            x = f"se{i}.out"
+        skips.append((x, w_))
+        cin = w_
+    P.append(dict(op="pool2", out="p5", x=x))
+    x = block("bridge", "p5", cin, widths[4])
+    if dropout_p > 0:
+        P.append(dict(op="drop", out="bridge.drop", x=x, p=dropout_p))
+        x = "bridge.drop"
+    clow = widths[4]
+    for k in (4, 3, 2, 1):
+        skip, cs = skips[k - 1]
+        P.append(dict(op="up", out=f"up{k}", x=x))
+        x = block(f"dec{k}", f"up{k}", clow, cs, x1=skip, c1=cs)      # cat([up, skip]): nets/UltraLightweightUnet_large.py:100-107
+        clow = cs
+    P.append(dict(op="head", out="logits", x=x, w="final.weight", bias="final.bias", cin=widths[0]))
+    return P, convs
+
+
+ULU_VARIANTS = {
+    # name: (widths, minimum mid channels, SE reduction rule, bridge dropout)
+    "ultralight": ((32, 64, 128, 256, 512), 8, None, 0.0),                                     # UltraLightweightUnet.py
+    "ultralight_large": ((64, 128, 256, 512, 1024), 16, lambda c: max(8, c // 4), 0.2),        # ..._large.py
+    "ultralight_large_optimized": ((44, 88, 176, 352, 704), 16, lambda c: max(8, c // 4), 0.15),   # ..._large_optimized.py
+}
+
+
 class GraphEngine:
-    def __init__(self, program, convs, num_classes, device=None):
+    def __init__(self, program, convs, num_classes, device=None, first_trainable_prefix=None):
         self.program, self.convs, self.num_classes, self.device = program, convs, num_classes, device
         self.eps, self.momentum = 1e-5, 0.1
         self._bufs, self._ws = {}, {}
@@ -94,23 +161,34 @@ class GraphEngine:
         self._pack_key = self._pack_versions = self._pack_table = None
         self._pack_total = 0
         self.saved = None
+        self.has_stem = any(i["op"] == "stem" for i in program)
+        self.dropout_override = None
 
     # ------------------------------------------------------------------ static description
     def param_shapes(self):
         shapes = {}
         for ins in self.program:
-            if ins["op"] == "stem":
+            op = ins["op"]
+            if op == "stem":
                 shapes[ins["w"]] = (ins["cout"], 3, 7, 7)
-            elif ins["op"] == "conv":
+            elif op == "conv":
                 k = 3 if ins["taps"] == 9 else 1
                 shapes[ins["w"]] = (ins["cout"], ins["cin"] + ins["c1"], k, k)
                 if ins["bias"]:
                     shapes[ins["bias"]] = (ins["cout"],)
-            elif ins["op"] == "bn":
+            elif op == "bn":
                 shapes[ins["bn"] + ".weight"] = (ins["c"],)
                 shapes[ins["bn"] + ".bias"] = (ins["c"],)
-            elif ins["op"] == "head":
-                shapes[ins["w"]] = (self.num_classes, 64, 1, 1)
+            elif op == "dw":
+                shapes[ins["w"]] = (ins["c"], 1, 3, 3)
+                shapes[ins["bias"]] = (ins["c"],)
+            elif op == "se":
+                shapes[ins["se"] + ".fc.0.weight"] = (ins["r"], ins["c"])
+                shapes[ins["se"] + ".fc.0.bias"] = (ins["r"],)
+                shapes[ins["se"] + ".fc.2.weight"] = (ins["c"], ins["r"])
+                shapes[ins["se"] + ".fc.2.bias"] = (ins["c"],)
+            elif op == "head":
+                shapes[ins["w"]] = (self.num_classes, ins.get("cin", 64), 1, 1)
                 shapes[ins["bias"]] = (self.num_classes,)
         return shapes
 
@@ -126,13 +204,18 @@ class GraphEngine:
     def backward_param_order(self):
         out = []
         for ins in reversed(self.program):
-            if ins["op"] == "head":
+            op = ins["op"]
+            if op == "head":
                 out += [ins["w"], ins["bias"]]
-            elif ins["op"] == "conv":
+            elif op == "conv":
                 out += [ins["w"]] + ([ins["bias"]] if ins["bias"] else [])
-            elif ins["op"] == "bn":
+            elif op == "bn":
                 out += [ins["bn"] + ".weight", ins["bn"] + ".bias"]
-            elif ins["op"] == "stem":
+            elif op == "dw":
+                out += [ins["w"], ins["bias"]]
+            elif op == "se":
+                out += [ins["se"] + ".fc.0.weight", ins["se"] + ".fc.0.bias", ins["se"] + ".fc.2.weight", ins["se"] + ".fc.2.bias"]
+            elif op == "stem":
                 out += [ins["w"]]
         return out
 
@@ -151,6 +234,17 @@ class GraphEngine:
             self._ws[key] = t
         return t
 
+    def _padded(self, key, t, shape, fill=0.0):
+        """fp32 parameter padded with `fill` to `shape` (persistent buffer; the real part is refreshed every call)."""
+        if tuple(t.shape) == tuple(shape):
+            return t
+        b = self._bufs.get(key)
+        if b is None or tuple(b.shape) != tuple(shape):
+            b = torch.full(shape, fill, dtype=torch.float32, device=self.device)
+            self._bufs[key] = b
+        b[tuple(slice(0, d) for d in t.shape)].copy_(t)
+        return b
+
     def release(self):
         self._bufs.clear(); self._ws.clear(); self.saved = None
 
@@ -158,27 +252,31 @@ class GraphEngine:
     def pack(self, params, need_dgrad=True):
         names = list(self.convs.keys())
         key = tuple(params[n].data_ptr() for n in names) + (need_dgrad,)
-        versions = tuple(params[n]._version for n in names) + (params["resnet.conv1.weight"]._version,)
+        versions = tuple(params[n]._version for n in names)
+        if self.has_stem:
+            versions += (params["resnet.conv1.weight"]._version,)
         if self._pack_key == key and self._pack_versions == versions:
             return
         dev = params[names[0]].device
         if self._pack_key != key:
             blob, start = b"", 0
             for n in names:
-                cout, cin, taps = self.convs[n]
+                cout, c0, c1, taps = self.convs[n]
+                c0p, c1p, coutp = pad64(c0), (pad64(c1) if c1 else 0), pad64(cout)
                 wf, wd = self._packed.get(n, (None, None))
                 if wf is None:
-                    wf = torch.zeros((cout, taps * cin), dtype=torch.bfloat16, device=dev)
+                    wf = torch.zeros((coutp, taps * (c0p + c1p)), dtype=torch.bfloat16, device=dev)
                 if need_dgrad and wd is None:
-                    wd = torch.zeros((cin, taps * cout), dtype=torch.bfloat16, device=dev)
+                    wd = torch.zeros((c0p + c1p, taps * coutp), dtype=torch.bfloat16, device=dev)
                 self._packed[n] = (wf, wd)
                 blob += struct.pack("<QQQqiiiiiiii", params[n].data_ptr(), wf.data_ptr(), wd.data_ptr() if need_dgrad else 0,
-                                    start, cout, cin, taps, 0, cin, cin, cin, cout)
-                start += (cout // 32) * (cin // 32)
+                                    start, cout, c0 + c1, taps, 0, c0, c0p, c0p + c1p, coutp)
+                start += ((cout + 31) // 32) * ((c0 + c1 + 31) // 32)
             self._pack_table = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
             self._pack_total, self._pack_key = start, key
         ops.check(ops.lib().b2u_pack_weights_multi(self._pack_table.data_ptr(), len(names), self._pack_total, ops.stream_ptr()))
-        self._stem_wf = ops.pack_weights_im2col(params["resnet.conv1.weight"], 192, wf=getattr(self, "_stem_wf", None))
+        if self.has_stem:
+            self._stem_wf = ops.pack_weights_im2col(params["resnet.conv1.weight"], 192, wf=getattr(self, "_stem_wf", None))
         self._pack_versions = versions
 
     def invalidate_packed_weights(self):
@@ -198,7 +296,6 @@ class GraphEngine:
             trainable = set(self.param_shapes().keys())
         self.device = x.device
         self.pack(params, need_dgrad=save)
-        zero_bias = {}
         T = {}
         logits = None
         for ins in self.program:
@@ -210,25 +307,28 @@ class GraphEngine:
                 t = _T(z, needs_grad=ins["w"] in trainable)
                 t.aux = col
                 T[ins["out"]] = t
+            elif op == "input":
+                T[ins["out"]] = _T(ops.nchw_to_nhwc_bf16_padded(x, 64, out=self._buf("x", (N, H, W, 64))))
             elif op == "conv":
                 xin = T[ins["x"]]
                 x1 = T[ins["x1"]] if ins["x1"] else None
                 wf, _ = self._packed[ins["w"]]
                 n, h, w, _ = xin.data.shape
-                bias = params[ins["bias"]] if ins["bias"] else None
+                coutp = pad64(ins["cout"])
+                bias = self._padded("b:" + ins["w"], params[ins["bias"]], (coutp,)) if ins["bias"] else None
                 aux = None
                 if ins["stride"] == 1:
-                    z = self._buf(ins["out"], (n, h, w, ins["cout"]))
-                    ops.conv_fprop(xin.data, wf, bias, ins["cout"], taps=ins["taps"], relu=ins["relu"],
+                    z = self._buf(ins["out"], (n, h, w, coutp))
+                    ops.conv_fprop(xin.data, wf, bias, coutp, taps=ins["taps"], relu=ins["relu"],
                                    x1=x1.data if x1 else None, out=z)
                 elif ins["taps"] == 9:      # 3x3 stride 2 = stride-1 conv, keep even pixels
-                    full = self._buf(ins["out"] + ":full", (n, h, w, ins["cout"]))
-                    ops.conv_fprop(xin.data, wf, bias, ins["cout"], taps=9, relu=ins["relu"], out=full)
-                    z = ops.subsample2(full, out=self._buf(ins["out"], (n, h // 2, w // 2, ins["cout"])))
+                    full = self._buf(ins["out"] + ":full", (n, h, w, coutp))
+                    ops.conv_fprop(xin.data, wf, bias, coutp, taps=9, relu=ins["relu"], out=full)
+                    z = ops.subsample2(full, out=self._buf(ins["out"], (n, h // 2, w // 2, coutp)))
                 else:                        # 1x1 stride 2 = keep even pixels, then conv
                     aux = ops.subsample2(xin.data, out=self._buf(ins["out"] + ":xs", (n, h // 2, w // 2, xin.data.shape[3])))
-                    z = self._buf(ins["out"], (n, h // 2, w // 2, ins["cout"]))
-                    ops.conv_fprop(aux, wf, bias, ins["cout"], taps=1, relu=ins["relu"], out=z)
+                    z = self._buf(ins["out"], (n, h // 2, w // 2, coutp))
+                    ops.conv_fprop(aux, wf, bias, coutp, taps=1, relu=ins["relu"], out=z)
                 ng = xin.needs_grad or (x1 is not None and x1.needs_grad) or ins["w"] in trainable or (ins["bias"] in trainable)
                 t = _T(z, fused_relu=ins["relu"], needs_grad=ng)
                 t.aux = aux
@@ -236,30 +336,77 @@ class GraphEngine:
             elif op == "bn":
                 zt = T[ins["z"]]
                 res = T[ins["res"]] if ins["res"] else None
-                bnn = ins["bn"]
+                bnn, c = ins["bn"], ins["c"]
+                cp = zt.data.shape[3]
                 y = self._buf(ins["out"], zt.data.shape)
-                ws = self._workspace("bn", ops.lib().b2u_bn_workspace(ins["c"]))
+                ws = self._workspace("bn", ops.lib().b2u_bn_workspace(cp))
+                gamma = self._padded("g:" + bnn, params[bnn + ".weight"], (cp,), 1.0)
+                beta = self._padded("bt:" + bnn, params[bnn + ".bias"], (cp,))
+                rm, rv = params[bnn + ".running_mean"], params[bnn + ".running_var"]
+                rmp, rvp = self._padded("rm:" + bnn, rm, (cp,)), self._padded("rv:" + bnn, rv, (cp,), 1.0)
                 if training:
-                    _, mean, invstd = ops.bn_fwd_train(zt.data, params[bnn + ".weight"], params[bnn + ".bias"],
-                                                       params[bnn + ".running_mean"], params[bnn + ".running_var"], self.eps,
-                                                       self.momentum, ins["relu"], out=y, ws=ws,
-                                                       residual=res.data if res else None)
+                    _, mean, invstd = ops.bn_fwd_train(zt.data, gamma, beta, rmp, rvp, self.eps, self.momentum, ins["relu"],
+                                                       out=y, ws=ws, residual=res.data if res else None)
+                    if cp != c:
+                        rm.copy_(rmp[:c]); rv.copy_(rvp[:c])
                     nbt = params.get(bnn + ".num_batches_tracked")
                     if nbt is not None:
                         nbt.add_(1)
                 else:
-                    ops.bn_fwd_eval(zt.data, params[bnn + ".weight"], params[bnn + ".bias"], params[bnn + ".running_mean"],
-                                    params[bnn + ".running_var"], self.eps, ins["relu"], out=y, ws=ws,
+                    ops.bn_fwd_eval(zt.data, gamma, beta, rmp, rvp, self.eps, ins["relu"], out=y, ws=ws,
                                     residual=res.data if res else None)
                     mean = invstd = None
                 ng = zt.needs_grad or (res is not None and res.needs_grad) or (bnn + ".weight") in trainable or (bnn + ".bias") in trainable
                 t = _T(y, needs_grad=ng)
-                t.aux = (mean, invstd)
+                t.aux = (mean, invstd, gamma)
+                T[ins["out"]] = t
+            elif op == "dw":
+                xin = T[ins["x"]]
+                c, cp = ins["c"], xin.data.shape[3]
+                wdw = self._padded("dw:" + ins["w"], params[ins["w"]].reshape(c, 9), (cp, 9))
+                bdw = self._padded("dwb:" + ins["w"], params[ins["bias"]], (cp,))
+                y = ops.dwconv3x3(xin.data, wdw, bdw, out=self._buf(ins["out"], xin.data.shape))
+                t = _T(y, needs_grad=xin.needs_grad or ins["w"] in trainable or ins["bias"] in trainable)
+                t.aux = wdw
+                T[ins["out"]] = t
+            elif op == "se":
+                xin = T[ins["x"]]
+                n, h, w, cp = xin.data.shape
+                se, c = ins["se"], ins["c"]
+                ws = self._workspace("spatial", ops.lib().b2u_spatial_reduce_workspace_floats(n, cp) * 4)
+                pooled = ops.spatial_reduce(xin.data, scale=1.0 / (h * w), ws=ws)
+                hidden, sc = ops.se_fc_fwd(pooled, params[se + ".fc.0.weight"], params[se + ".fc.0.bias"],
+                                           params[se + ".fc.2.weight"], params[se + ".fc.2.bias"], c)
+                y = ops.scale_nc(xin.data, sc, out=self._buf(ins["out"], xin.data.shape))
+                t = _T(y, needs_grad=xin.needs_grad or any((se + s_) in trainable for s_ in (".fc.0.weight", ".fc.0.bias", ".fc.2.weight", ".fc.2.bias")))
+                t.aux = (pooled, hidden, sc)
+                T[ins["out"]] = t
+            elif op == "drop":
+                xin = T[ins["x"]]
+                if training and ins["p"] > 0:
+                    n, h, w, cp = xin.data.shape
+                    keep = 1.0 - ins["p"]
+                    if self.dropout_override is not None:       # tests replay the multiplier the reference drew ([N, C])
+                        mask = torch.zeros((n, cp), dtype=torch.float32, device=self.device)
+                        mask[:, :self.dropout_override.shape[1]] = self.dropout_override.to(self.device)
+                    else:
+                        mask = torch.bernoulli(torch.full((n, cp), keep, dtype=torch.float32, device=self.device)) / keep
+                    y = ops.scale_nc(xin.data, mask, out=self._buf(ins["out"], xin.data.shape))
+                    t = _T(y, needs_grad=xin.needs_grad)
+                    t.aux = mask
+                else:
+                    t = _T(xin.data, needs_grad=xin.needs_grad)
+                    t.aux = None
                 T[ins["out"]] = t
             elif op == "pool3":
                 xin = T[ins["x"]]
                 n, h, w, c = xin.data.shape
                 y = ops.maxpool3x3s2(xin.data, out=self._buf(ins["out"], (n, (h - 2) // 2 + 1, (w - 2) // 2 + 1, c)))
+                T[ins["out"]] = _T(y, needs_grad=xin.needs_grad)
+            elif op == "pool2":
+                xin = T[ins["x"]]
+                n, h, w, c = xin.data.shape
+                y = ops.maxpool2x2(xin.data, out=self._buf(ins["out"], (n, h // 2, w // 2, c)))
                 T[ins["out"]] = _T(y, needs_grad=xin.needs_grad)
             elif op == "up":
                 xin = T[ins["x"]]
@@ -268,10 +415,15 @@ class GraphEngine:
                 T[ins["out"]] = _T(y, needs_grad=xin.needs_grad)
             elif op == "head":
                 xin = T[ins["x"]]
-                logits = ops.head_fwd(xin.data, params[ins["w"]].reshape(self.num_classes, 64), params[ins["bias"]])
+                logits = ops.head_fwd(xin.data, self._head_weight(params, ins), params[ins["bias"]])
         if save:
             self.saved = (T, (N, H, W), set(trainable))
         return logits
+
+    def _head_weight(self, params, ins):
+        cin = ins.get("cin", 64)
+        w = params[ins["w"]].reshape(self.num_classes, cin)
+        return w if cin == 64 else self._padded("head:w", w, (self.num_classes, 64))
 
     # ------------------------------------------------------------------ backward
     def _acc(self, t, g):
@@ -300,7 +452,8 @@ class GraphEngine:
             op = ins["op"]
             if op == "head":
                 xin = T[ins["x"]]
-                wh = params[ins["w"]].reshape(self.num_classes, 64)
+                cin = ins.get("cin", 64)
+                wh = self._head_weight(params, ins)
                 C = self.num_classes
                 fw, fb = has(ins["w"]), has(ins["bias"])
                 g = self._buf("g:" + ins["x"], xin.data.shape) if xin.needs_grad else None
@@ -315,14 +468,19 @@ class GraphEngine:
                         need = ops.lib().b2u_conv_wgrad_workspace(dl.shape[0], dl.shape[1], dl.shape[2], 64, 64, 1)
                         ops.conv_wgrad(xin.data, dl, taps=1, dw=dw64, db=db64, ws=self._workspace("wgrad", need))
                         if fw:
-                            torch.add(dw64[:C], dw64[32:32 + C], out=grads[ins["w"]])
+                            torch.add(dw64[:C, :cin], dw64[32:32 + C, :cin], out=grads[ins["w"]])
                         if fb:
                             torch.add(db64[:C], db64[32:32 + C], out=grads[ins["bias"]])
                 else:
                     dl = dlogits.float().contiguous() if dlogits.dtype != torch.float32 else dlogits.contiguous()
+                    dwt = None
+                    if fw:
+                        dwt = grads[ins["w"]] if cin == 64 else self._buf("head:dwf", (C, 64, 1, 1), torch.float32)
                     ops.head_bwd(dl, xin.data, wh, need_dx=g is not None, need_dw=fw or fb, relu_mask=xin.fused_relu, dx=g,
-                                 dw=grads[ins["w"]] if fw else None, db=grads[ins["bias"]] if fb else None,
+                                 dw=dwt, db=grads[ins["bias"]] if fb else None,
                                  ws=self._workspace("head", ops.lib().b2u_head_bwd_workspace()))
+                    if fw and cin != 64:
+                        grads[ins["w"]].copy_(dwt[:, :cin])
                 if g is not None:
                     self._acc(xin, g)
                 ready(ins["w"], ins["bias"])
@@ -339,22 +497,76 @@ class GraphEngine:
                     continue
                 g = ops.maxpool3x3s2_bwd(t.grad, xin.data, out=self._buf("g:" + ins["out"] + ">", xin.data.shape))
                 self._acc(xin, g)
+            elif op == "pool2":
+                t, xin = T[ins["out"]], T[ins["x"]]
+                if t.grad is None or not xin.needs_grad:
+                    continue
+                g = ops.maxpool2x2_bwd(t.grad, xin.data, dskip=None, relu_mask=xin.fused_relu,
+                                       out=self._buf("g:" + ins["out"] + ">", xin.data.shape))
+                self._acc(xin, g)
+            elif op == "drop":
+                t, xin = T[ins["out"]], T[ins["x"]]
+                if t.grad is None or not xin.needs_grad:
+                    continue
+                if t.aux is None:
+                    self._acc(xin, t.grad)
+                else:
+                    self._acc(xin, ops.scale_nc(t.grad, t.aux, out=self._buf("g:" + ins["out"] + ">", xin.data.shape)))
+            elif op == "se":
+                t, xin = T[ins["out"]], T[ins["x"]]
+                if t.grad is None:
+                    continue
+                se, c = ins["se"], ins["c"]
+                pooled, hidden, sc = t.aux
+                n, h, w, cp = xin.data.shape
+                ws = self._workspace("spatial", ops.lib().b2u_spatial_reduce_workspace_floats(n, cp) * 4)
+                dscale = ops.spatial_reduce(t.grad, xin.data, ws=ws)
+                names = [se + ".fc.0.weight", se + ".fc.0.bias", se + ".fc.2.weight", se + ".fc.2.bias"]
+                dpooled = ops.se_fc_bwd(dscale, pooled, hidden, sc, params[names[0]], params[names[2]], c, 1.0 / (h * w),
+                                        dw1=grads[names[0]] if has(names[0]) else None, db1=grads[names[1]] if has(names[1]) else None,
+                                        dw2=grads[names[2]] if has(names[2]) else None, db2=grads[names[3]] if has(names[3]) else None)
+                ready(*names)
+                if xin.needs_grad:
+                    self._acc(xin, ops.scale_nc(t.grad, sc, add=dpooled, out=self._buf("g:" + ins["out"] + ">", xin.data.shape)))
+            elif op == "dw":
+                t, xin = T[ins["out"]], T[ins["x"]]
+                if t.grad is None:
+                    continue
+                c, cp = ins["c"], xin.data.shape[3]
+                if has(ins["w"]) or has(ins["bias"]):
+                    dwp = self._buf("dwg:" + ins["w"], (cp, 9), torch.float32)
+                    dbp = self._buf("dwgb:" + ins["w"], (cp,), torch.float32)
+                    ops.dwconv3x3_wgrad(xin.data, t.grad, dw=dwp, db=dbp,
+                                        ws=self._workspace("dwgrad", ops.lib().b2u_dwconv3x3_wgrad_workspace(cp)))
+                    if has(ins["w"]):
+                        grads[ins["w"]].copy_(dwp[:c].reshape(c, 1, 3, 3))
+                    if has(ins["bias"]):
+                        grads[ins["bias"]].copy_(dbp[:c])
+                ready(ins["w"], ins["bias"])
+                if xin.needs_grad:
+                    g = ops.dwconv3x3(t.grad, t.aux, None, flip=True, out=self._buf("g:" + ins["out"] + ">", xin.data.shape))
+                    self._acc(xin, g)
             elif op == "bn":
                 t, zt = T[ins["out"]], T[ins["z"]]
                 res = T[ins["res"]] if ins["res"] else None
                 if t.grad is None:
                     continue
-                bnn = ins["bn"]
-                mean, invstd = t.aux
+                bnn, c = ins["bn"], ins["c"]
+                cp = zt.data.shape[3]
+                mean, invstd, gamma = t.aux
                 need_res = res is not None and res.needs_grad
                 gout = self._buf("g:" + ins["out"] + ">res", t.data.shape) if need_res else None
                 dz = self._buf("g:" + ins["z"], zt.data.shape)
-                dgam = self._buf("dg:" + bnn, (ins["c"],), torch.float32)
-                dbet = self._buf("db:" + bnn, (ins["c"],), torch.float32)
-                ops.bn_bwd(t.grad, t.data, zt.data, params[bnn + ".weight"], mean, invstd, relu=ins["relu"], out=dz,
-                           dgamma=grads[bnn + ".weight"] if has(bnn + ".weight") else dgam,
-                           dbeta=grads[bnn + ".bias"] if has(bnn + ".bias") else dbet,
-                           ws=self._workspace("bn", ops.lib().b2u_bn_workspace(ins["c"])), gout=gout)
+                direct = cp == c
+                dgam = grads[bnn + ".weight"] if (direct and has(bnn + ".weight")) else self._buf("dg:" + bnn, (cp,), torch.float32)
+                dbet = grads[bnn + ".bias"] if (direct and has(bnn + ".bias")) else self._buf("db:" + bnn, (cp,), torch.float32)
+                ops.bn_bwd(t.grad, t.data, zt.data, gamma, mean, invstd, relu=ins["relu"], out=dz, dgamma=dgam, dbeta=dbet,
+                           ws=self._workspace("bn", ops.lib().b2u_bn_workspace(cp)), gout=gout)
+                if not direct:
+                    if has(bnn + ".weight"):
+                        grads[bnn + ".weight"].copy_(dgam[:c])
+                    if has(bnn + ".bias"):
+                        grads[bnn + ".bias"].copy_(dbet[:c])
                 ready(bnn + ".weight", bnn + ".bias")
                 if zt.needs_grad:
                     self._acc(zt, dz)
@@ -368,38 +580,52 @@ class GraphEngine:
                 dz = t.grad
                 wf, wd = self._packed[ins["w"]]
                 n, h, w, _ = xin.data.shape
-                taps, cout = ins["taps"], ins["cout"]
+                taps, cout, c0r, c1r = ins["taps"], ins["cout"], ins["cin"], ins["c1"]
+                coutp = pad64(cout)
                 if ins["stride"] == 2 and taps == 9:
-                    dz = ops.zero_insert2(dz, h, w, out=self._buf("g:" + ins["out"] + ":full", (n, h, w, cout)))
+                    dz = ops.zero_insert2(dz, h, w, out=self._buf("g:" + ins["out"] + ":full", (n, h, w, coutp)))
                 xw = t.aux if (ins["stride"] == 2 and taps == 1) else xin.data          # wgrad's activation operand
+                c0p = xw.shape[3]
+                c1p = x1.data.shape[3] if x1 else 0
                 if has(ins["w"]):
-                    ctot = xw.shape[3] + (x1.data.shape[3] if x1 else 0)
-                    need = ops.lib().b2u_conv_wgrad_workspace(dz.shape[0], dz.shape[1], dz.shape[2], ctot, cout, taps)
-                    ops.conv_wgrad(xw, dz, taps=taps, x1=x1.data if x1 else None, dw=grads[ins["w"]],
-                                   ws=self._workspace("wgrad", need))
+                    need = ops.lib().b2u_conv_wgrad_workspace(dz.shape[0], dz.shape[1], dz.shape[2], c0p + c1p, coutp, taps)
+                    ws = self._workspace("wgrad", need)
+                    if coutp == cout and c0p == c0r and c1p == c1r:
+                        ops.conv_wgrad(xw, dz, taps=taps, x1=x1.data if x1 else None, dw=grads[ins["w"]], ws=ws)
+                    else:       # padded operands: gradient of the padded weight, then keep the real rows/columns
+                        k = 3 if taps == 9 else 1
+                        tmp = self._buf("dw:" + ins["w"], (coutp, c0p + c1p, k, k), torch.float32)
+                        ops.conv_wgrad(xw, dz, taps=taps, x1=x1.data if x1 else None, dw=tmp, ws=ws)
+                        gw = grads[ins["w"]]
+                        gw[:, :c0r].copy_(tmp[:cout, :c0r])
+                        if c1r:
+                            gw[:, c0r:].copy_(tmp[:cout, c0p:c0p + c1r])
                 if has(ins["bias"]):
-                    ops.bias_grad(dz, db=grads[ins["bias"]], ws=self._workspace("bias", ops.lib().b2u_bias_grad_workspace(cout)))
+                    wsb = self._workspace("bias", ops.lib().b2u_bias_grad_workspace(coutp))
+                    if coutp == cout:
+                        ops.bias_grad(dz, db=grads[ins["bias"]], ws=wsb)
+                    else:
+                        tb = ops.bias_grad(dz, db=self._buf("dbias:" + ins["w"], (coutp,), torch.float32), ws=wsb)
+                        grads[ins["bias"]].copy_(tb[:cout])
                 ready(ins["w"], ins["bias"])
                 need0, need1 = xin.needs_grad, (x1 is not None and x1.needs_grad)
                 if not (need0 or need1):
                     continue
-                c0 = xw.shape[3]
                 if x1 is not None:
-                    c1 = x1.data.shape[3]
                     if need0:
                         d0 = self._buf("g:" + ins["out"] + ">0", xin.data.shape)
                         d1 = self._buf("g:" + ins["out"] + ">1", x1.data.shape)
-                        ops.conv_dgrad(dz, wd, c0, taps=taps, C1=c1, out0=d0, out1=d1)
+                        ops.conv_dgrad(dz, wd, c0p, taps=taps, C1=c1p, out0=d0, out1=d1)
                         self._acc_masked(xin, d0)
                         if need1:
                             self._acc_masked(x1, d1)
-                    else:       # frozen skip source: only the second (up-sampled) half needs a gradient
+                    else:       # frozen first source: only the second half needs a gradient
                         d1 = self._buf("g:" + ins["out"] + ">1", x1.data.shape)
-                        ops.conv_dgrad(dz, wd[c0:], c1, taps=taps, mask=x1.data if x1.fused_relu else None, out0=d1)
+                        ops.conv_dgrad(dz, wd[c0p:], c1p, taps=taps, mask=x1.data if x1.fused_relu else None, out0=d1)
                         self._acc(x1, d1)
                 else:
                     d0 = self._buf("g:" + ins["out"] + ">0", xw.shape)
-                    ops.conv_dgrad(dz, wd, c0, taps=taps, mask=xin.data if (xin.fused_relu and xw is xin.data) else None, out0=d0)
+                    ops.conv_dgrad(dz, wd, c0p, taps=taps, mask=xin.data if (xin.fused_relu and xw is xin.data) else None, out0=d0)
                     if ins["stride"] == 2 and taps == 1:
                         d0 = ops.zero_insert2(d0, h, w, out=self._buf("g:" + ins["out"] + ">0:full", xin.data.shape))
                     self._acc(xin, d0)
@@ -415,7 +641,7 @@ class GraphEngine:
     def _acc_masked(self, t, g):
         """Gradient from a split (two-output) dgrad, which cannot mask in its epilogue."""
         if t.fused_relu:
-            raise NotImplementedError("split dgrad into a fused-ReLU tensor needs a mask pass")   # not needed by ResNet50-Unet's encoder features
+            raise NotImplementedError("split dgrad into a fused-ReLU tensor needs a mask pass")
         self._acc(t, g)
 
 
@@ -425,3 +651,13 @@ class ResNet50UnetEngine(GraphEngine):
             raise ValueError("num_classes must be in [1, 32]")
         program, convs = resnet50_unet_program(num_classes)
         super().__init__(program, convs, num_classes, device=device)
+
+
+class UltraLightUnetEngine(GraphEngine):
+    def __init__(self, num_classes, variant="ultralight_large", device=None):
+        if not 1 <= num_classes <= 32:
+            raise ValueError("num_classes must be in [1, 32]")
+        widths, mid_min, se_rule, p = ULU_VARIANTS[variant]
+        program, convs = ultralight_unet_program(num_classes, widths, mid_min, se_rule, p)
+        super().__init__(program, convs, num_classes, device=device)
+        self.variant = variant

@@ -117,6 +117,15 @@ def nchw_to_nhwc_bf16(x):
     return y
 
 
+def nchw_to_nhwc_bf16_padded(x, cpad, out=None):
+    _req(x, torch.float32, "x")
+    N, C, H, W = x.shape
+    if out is None:
+        out = torch.empty((N, H, W, cpad), dtype=BF16, device=x.device)
+    check(lib().b2u_nchw_f32_to_nhwc_bf16_padded(ptr(x), ptr(out), N, C, H, W, cpad, stream_ptr()))
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- convs
 def conv_fprop(x0, wf, bias, Cout, taps=9, relu=True, x1=None, out=None, bn=0):
     _req(x0, BF16, "x0"); _req(x1, BF16, "x1"); _req(wf, BF16, "wf"); _req(bias, torch.float32, "bias")
@@ -351,6 +360,74 @@ def add_bf16(a, b, out=None):
         out = torch.empty_like(a)
     check(lib().b2u_add_bf16(ptr(a), ptr(b), ptr(out), a.numel(), stream_ptr()))
     return out
+
+
+# ---------------------------------------------------------------------------------------------- depthwise / SE
+def dwconv3x3(x, w, bias=None, flip=False, out=None):
+    """w: fp32 [C, 9] (or [C,1,3,3]); flip=True is the data gradient."""
+    _req(x, BF16, "x"); _req(w, torch.float32, "w")
+    N, H, W, C = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib().b2u_dwconv3x3_fwd(ptr(x), ptr(w), ptr(bias), ptr(out), N, H, W, C, 1 if flip else 0, stream_ptr()))
+    return out
+
+
+def dwconv3x3_wgrad(x, dy, dw=None, db=None, ws=None):
+    _req(x, BF16, "x"); _req(dy, BF16, "dy")
+    N, H, W, C = x.shape
+    need = lib().b2u_dwconv3x3_wgrad_workspace(C)
+    if ws is None or ws.numel() * ws.element_size() < need:
+        ws = _ws(need, x.device)
+    if dw is None:
+        dw = torch.empty((C, 9), dtype=torch.float32, device=x.device)
+    if db is None:
+        db = torch.empty((C,), dtype=torch.float32, device=x.device)
+    check(lib().b2u_dwconv3x3_wgrad(ptr(x), ptr(dy), ptr(dw), ptr(db), ptr(ws), ws.numel() * ws.element_size(), N, H, W, C,
+                                    stream_ptr()))
+    return dw, db
+
+
+def spatial_reduce(a, b=None, scale=1.0, out=None, ws=None):
+    """[N, C] fp32: scale * sum over H*W of a (or a*b)."""
+    _req(a, BF16, "a"); _req(b, BF16, "b")
+    N, H, W, C = a.shape
+    need = lib().b2u_spatial_reduce_workspace_floats(N, C) * 4
+    if ws is None or ws.numel() * ws.element_size() < need:
+        ws = _ws(need, a.device)
+    if out is None:
+        out = torch.empty((N, C), dtype=torch.float32, device=a.device)
+    check(lib().b2u_spatial_reduce(ptr(a), ptr(b), ptr(out), ptr(ws), ws.numel() * ws.element_size(), N, H * W, C, scale,
+                                   stream_ptr()))
+    return out
+
+
+def scale_nc(x, s, add=None, out=None):
+    _req(x, BF16, "x"); _req(s, torch.float32, "s"); _req(add, torch.float32, "add")
+    N, H, W, C = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib().b2u_scale_nc(ptr(x), ptr(s), ptr(add), ptr(out), N, H * W, C, stream_ptr()))
+    return out
+
+
+def se_fc_fwd(pooled, w1, b1, w2, b2, C):
+    N, Cp = pooled.shape
+    R = w1.shape[0]
+    hidden = torch.empty((N, R), dtype=torch.float32, device=pooled.device)
+    scale = torch.empty((N, Cp), dtype=torch.float32, device=pooled.device)
+    check(lib().b2u_se_fc_fwd(ptr(pooled), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(hidden), ptr(scale), N, C, Cp, R, stream_ptr()))
+    return hidden, scale
+
+
+def se_fc_bwd(dscale, pooled, hidden, scale, w1, w2, C, dp_scale, dw1=None, db1=None, dw2=None, db2=None):
+    N, Cp = pooled.shape
+    R = w1.shape[0]
+    dpooled = torch.empty((N, Cp), dtype=torch.float32, device=pooled.device)
+    scratch = torch.empty((N * (C + R),), dtype=torch.float32, device=pooled.device)
+    check(lib().b2u_se_fc_bwd(ptr(dscale), ptr(pooled), ptr(hidden), ptr(scale), ptr(w1), ptr(w2), ptr(dpooled), ptr(dw1),
+                              ptr(db1), ptr(dw2), ptr(db2), ptr(scratch), N, C, Cp, R, dp_scale, stream_ptr()))
+    return dpooled
 
 
 # ---------------------------------------------------------------------------------------------- head

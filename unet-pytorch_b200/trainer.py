@@ -10,12 +10,14 @@ All parameters, gradients and optimizer moments live in flat fp32 buffers laid o
 ready front to back, and one kernel launch updates every parameter.  Like DDP in the reference, every rank
 normalises its loss over its own shard and the ranks' gradients are averaged.
 """
+import functools
+
 import torch
 import torch.distributed as dist
 
 from . import ops
 from .engine import TraditionalUnetEngine, VGGUnetEngine, vgg_unet_param_shapes
-from .graph import ResNet50UnetEngine
+from .graph import ResNet50UnetEngine, UltraLightUnetEngine
 
 
 def _backward_order(names):
@@ -130,10 +132,14 @@ class GradientSync:
 
 
 class UnetTrainer:
-    """model: "unet_vgg" / "unet_resnet50" (nets/unet.py::Unet with backbone 'vgg' / 'resnet50') or "traditional"
-    (nets/TraditionalUnet.py)."""
+    """model: "unet_vgg" / "unet_resnet50" (nets/unet.py::Unet with backbone 'vgg' / 'resnet50'), "traditional"
+    (nets/TraditionalUnet.py) or "ultralight" / "ultralight_large" / "ultralight_large_optimized"
+    (nets/UltraLightweightUnet*.py)."""
 
-    ENGINES = {"unet_vgg": VGGUnetEngine, "traditional": TraditionalUnetEngine, "unet_resnet50": ResNet50UnetEngine}
+    ENGINES = {"unet_vgg": VGGUnetEngine, "traditional": TraditionalUnetEngine, "unet_resnet50": ResNet50UnetEngine,
+               "ultralight": functools.partial(UltraLightUnetEngine, variant="ultralight"),
+               "ultralight_large": functools.partial(UltraLightUnetEngine, variant="ultralight_large"),
+               "ultralight_large_optimized": functools.partial(UltraLightUnetEngine, variant="ultralight_large_optimized")}
 
     def __init__(self, num_classes=21, device=None, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
                  optimizer="adam", momentum=0.9, cls_weights=None, dice_loss=True, focal_loss=False,
@@ -175,7 +181,8 @@ class UnetTrainer:
         self.cls_w = cw.to(self.device).contiguous()
         self.sync = GradientSync(self.layout, self.flat_grad, group=process_group)
         self.trainable = set(self.names)
-        self.backbone_prefixes = {"unet_vgg": ("vgg.",), "unet_resnet50": ("resnet.",)}.get(model, ("inc.", "down1.", "down2.", "down3."))
+        self.backbone_prefixes = {"unet_vgg": ("vgg.",), "unet_resnet50": ("resnet.",)}.get(
+            model, ("enc", "se") if model.startswith("ultralight") else ("inc.", "down1.", "down2.", "down3."))
         self._gscale = torch.tensor([0.0 if focal_loss else 1.0, 1.0 if focal_loss else 0.0, 1.0 if dice_loss else 0.0],
                                     dtype=torch.float32, device=self.device)
         self._copy_stream = torch.cuda.Stream(device=self.device)
