@@ -565,14 +565,18 @@ def ulu_param_shapes(num_classes, variant):
 
 
 def make_ulu_params(num_classes, variant, seed=11):
-    """Deterministic synthetic state_dict: He-scaled convs (BatchNorm follows each), BN weight 1 + 0.1 N, biases 0.05 N,
-    SE linears at 1/sqrt(fan_in), fresh running statistics."""
+    """Deterministic synthetic state_dict: He-scaled 1x1 convs (BatchNorm follows each), depthwise taps 1/3 (1 + 0.5 N),
+    BN weight 1 + 0.1 N and bias 0.5 + 0.05 N, other biases 0.05 N, SE linears at 1/sqrt(fan_in), fresh running statistics."""
     sd = {}
     shapes = ulu_param_shapes(num_classes, variant)
     for k, (name, shape) in enumerate(shapes.items()):
         g = torch.Generator().manual_seed(seed * 1000 + 5000 + k)
         is_bn = (".conv.1." in name or ".conv.4." in name)
-        if len(shape) == 4:
+        if name.endswith("depthwise.weight"):
+            # smoothing-like filters (positive mean): random-sign 3x3 taps act as high-pass filters on the smooth feature
+            # maps and amplify bf16 storage rounding ~4x, which would only loosen the parity tolerances
+            sd[name] = (1.0 / 3.0) * (1.0 + 0.5 * torch.randn(shape, generator=g))
+        elif len(shape) == 4:
             fan_in = shape[1] * shape[2] * shape[3]
             gn = 0.5 if name == "final.weight" else 1.0
             sd[name] = torch.randn(shape, generator=g) * (gn * (2.0 / fan_in) ** 0.5)
@@ -580,6 +584,8 @@ def make_ulu_params(num_classes, variant, seed=11):
             sd[name] = torch.randn(shape, generator=g) * (1.0 / shape[1]) ** 0.5
         elif is_bn and name.endswith(".weight"):
             sd[name] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif is_bn:
+            sd[name] = 0.5 + 0.05 * torch.randn(shape, generator=g)      # beta > 0: most units stay alive after the ReLU
         else:
             sd[name] = 0.05 * torch.randn(shape, generator=g)
         if is_bn and name.endswith(".bias"):

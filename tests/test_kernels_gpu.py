@@ -489,6 +489,15 @@ def test_padded_channel_convs(b2u, cuda_device):
             d0 = ops.conv_dgrad(nhwc(dz, dev), wd, c0p, taps=taps)
             d0 = d0[0] if isinstance(d0, tuple) else d0
             assert rel(nchw(d0)[:, :c0], dx_ref) <= 6e-3
+        # weight gradient of the padded problem: real rows/columns match, padding rows/columns are exactly zero
+        dwp = ops.conv_wgrad(nhwc(x0, dev), nhwc(dz, dev), taps=taps, x1=nhwc(x1, dev) if c1 else None)
+        dwp = (dwp[0] if isinstance(dwp, tuple) else dwp).cpu()
+        xr = xin.clone().requires_grad_(True)
+        wr_ = wr.clone().requires_grad_(True)
+        F.conv2d(xr, wr_, None, padding=k // 2).backward(dz[:, :cout])
+        got = dwp[:cout, :c0] if not c1 else torch.cat([dwp[:cout, :c0], dwp[:cout, c0p:c0p + c1]], 1)
+        assert rel(got, wr_.grad) <= 1e-4, (cout, c0, c1)
+        assert dwp[cout:].abs().max().item() == 0 if coutp > cout else True
 
 
 def test_padded_input_conversion(b2u, cuda_device):

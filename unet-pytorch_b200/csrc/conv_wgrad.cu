@@ -418,7 +418,7 @@ int b2u_conv_wgrad(const void* x0, int C0, const void* x1, int C1, const void* d
   if (taps != 9 && taps != 1) return set_error(B2U_ERR_SHAPE, "wgrad: taps must be 9 or 1");
   if (C0 % 64 != 0 || C1 % 64 != 0 || ctot <= 0)
     return set_error(B2U_ERR_SHAPE, "wgrad: input channels (%d,%d) must be multiples of 64", C0, C1);
-  if (Cout != 64 && Cout % 128 != 0) return set_error(B2U_ERR_SHAPE, "wgrad: Cout %d must be 64 or a multiple of 128", Cout);
+  if (Cout % 64 != 0) return set_error(B2U_ERR_SHAPE, "wgrad: Cout %d must be a multiple of 64", Cout);   // a ragged last 128-block reads zero-filled (out-of-bounds) dz channels
   if (first_cin > 0 && (taps != 1 || C0 != 64 || C1 != 0 || 9 * first_cin > 64))
     return set_error(B2U_ERR_SHAPE, "wgrad: first-layer mode needs taps=1, C0=64, C1=0, 9*cin<=64");
   const WgradPlan pl = plan_wgrad(N, H, W, ctot, Cout, taps);
@@ -459,7 +459,7 @@ int b2u_conv_wgrad_im2col(const void* x0, int Kpad, const void* dz, int Cout, fl
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (N <= 0 || H <= 0 || W <= 0) return set_error(B2U_ERR_SHAPE, "wgrad_im2col: empty tensor");
   if (Kpad % 64 != 0 || cin <= 0 || taps <= 0 || cin * taps > Kpad) return set_error(B2U_ERR_SHAPE, "wgrad_im2col: bad K layout");
-  if (Cout != 64 && Cout % 128 != 0) return set_error(B2U_ERR_SHAPE, "wgrad_im2col: Cout %d must be 64 or a multiple of 128", Cout);
+  if (Cout % 64 != 0) return set_error(B2U_ERR_SHAPE, "wgrad_im2col: Cout %d must be a multiple of 64", Cout);
   const WgradPlan pl = plan_wgrad(N, H, W, Kpad, Cout, 1);
   if (ws == nullptr || ws_bytes < pl.ws_bytes) return set_error(B2U_ERR_ARG, "wgrad_im2col: workspace too small");
   int rc = launch_wgrad_cfg<1, 4>(x0, Kpad, nullptr, 0, dz, Cout, static_cast<float*>(ws), nullptr, pl, N, H, W, 1, st);

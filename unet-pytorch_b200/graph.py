@@ -97,25 +97,30 @@ def resnet50_unet_program(num_classes):
     return P, convs
 
 
+def light_conv_block_ops(P, convs, prefix, x, cin, cout, mid_min, x1=None, c1=0):
+    """Appends one LightConvBlock (1x1 conv, BN, ReLU, depthwise 3x3, 1x1 conv, BN, ReLU) reading x (and x1: virtual concat)."""
+    def conv(out, xin, w, ci, co, bias, x1=None, c1=0):
+        convs[w] = (co, ci, c1, 1)
+        P.append(dict(op="conv", out=out, x=xin, x1=x1, w=w, bias=bias, cin=ci, c1=c1, cout=co, taps=1, stride=1, relu=False))
+
+    mid = max(mid_min, cout // 2)
+    conv(prefix + ".z1", x, prefix + ".conv.0.weight", cin, mid, prefix + ".conv.0.bias", x1=x1, c1=c1)
+    P.append(dict(op="bn", out=prefix + ".y1", z=prefix + ".z1", bn=prefix + ".conv.1", c=mid, relu=True, res=None))
+    P.append(dict(op="dw", out=prefix + ".d", x=prefix + ".y1", w=prefix + ".conv.3.depthwise.weight",
+                  bias=prefix + ".conv.3.depthwise.bias", c=mid))
+    conv(prefix + ".z2", prefix + ".d", prefix + ".conv.3.pointwise.weight", mid, cout, prefix + ".conv.3.pointwise.bias")
+    P.append(dict(op="bn", out=prefix + ".out", z=prefix + ".z2", bn=prefix + ".conv.4", c=cout, relu=True, res=None))
+    return prefix + ".out"
+
+
 def ultralight_unet_program(num_classes, widths, mid_min, se_rule=None, dropout_p=0.0):
-    """UltraLightweightUnet / _large / _large_optimized (nets/UltraLightweightUnet*.py): LightConvBlock = 1x1 conv, BN,
-    ReLU, depthwise 3x3, 1x1 conv, BN, ReLU; optional SE after each encoder block; Dropout2d on the bridge; decoder
-    input = cat[upsampled, skip] (upsampled FIRST); 1x1 head.  se_rule: channels -> reduced channels, or None."""
+    """UltraLightweightUnet / _large / _large_optimized (nets/UltraLightweightUnet*.py): LightConvBlock stages; optional SE
+    after each encoder block; Dropout2d on the bridge; decoder input = cat[upsampled, skip] (upsampled FIRST); 1x1 head.
+    se_rule: channels -> reduced channels, or None."""
     P, convs = [], {}
 
-    def conv(out, x, w, cin, cout, bias, x1=None, c1=0):
-        convs[w] = (cout, cin, c1, 1)
-        P.append(dict(op="conv", out=out, x=x, x1=x1, w=w, bias=bias, cin=cin, c1=c1, cout=cout, taps=1, stride=1, relu=False))
-
     def block(prefix, x, cin, cout, x1=None, c1=0):
-        mid = max(mid_min, cout // 2)
-        conv(prefix + ".z1", x, prefix + ".conv.0.weight", cin, mid, prefix + ".conv.0.bias", x1=x1, c1=c1)
-        P.append(dict(op="bn", out=prefix + ".y1", z=prefix + ".z1", bn=prefix + ".conv.1", c=mid, relu=True, res=None))
-        P.append(dict(op="dw", out=prefix + ".d", x=prefix + ".y1", w=prefix + ".conv.3.depthwise.weight",
-                      bias=prefix + ".conv.3.depthwise.bias", c=mid))
-        conv(prefix + ".z2", prefix + ".d", prefix + ".conv.3.pointwise.weight", mid, cout, prefix + ".conv.3.pointwise.bias")
-        P.append(dict(op="bn", out=prefix + ".out", z=prefix + ".z2", bn=prefix + ".conv.4", c=cout, relu=True, res=None))
-        return prefix + ".out"
+        return light_conv_block_ops(P, convs, prefix, x, cin, cout, mid_min, x1=x1, c1=c1)
 
     P.append(dict(op="input", out="x", c=3))
     x, cin, skips = "x", 3, []
