@@ -97,8 +97,10 @@ int b2u_bn_fwd_eval(const void* z, const void* residual, void* y, const float* g
                     const float* running_mean, const float* running_var, void* ws, size_t ws_bytes, long long P, int C,
                     float eps, int relu, void* stream);
 /* dy = gradient wrt y; dz (may alias dy) = gradient wrt z; gout (nullable) = ReLU-masked dy = gradient wrt the residual;
- * dgamma/dbeta nullable */
-int b2u_bn_bwd(const void* dy, const void* y, const void* z, const float* gamma, const float* save_mean,
+ * dgamma/dbeta nullable.  y = the forward output, required only when a residual was added before the ReLU; with
+ * y == NULL the ReLU mask is recomputed from z, gamma, beta and the saved statistics exactly as the forward evaluated
+ * it (one tensor read less per pass) */
+int b2u_bn_bwd(const void* dy, const void* y, const void* z, const float* gamma, const float* beta, const float* save_mean,
                const float* save_invstd, void* dz, void* gout, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
                long long P, int C, int relu, void* stream);
 

@@ -292,6 +292,9 @@ def test_batchnorm_kernels(b2u, cuda_device, N, H, W, C, relu):
     dyb = nhwc(dy, dev)
     ref_y.backward(nchw(dyb))
     dz, dgam, dbet = ops.bn_bwd(dyb, y, zb, gamma.detach().to(dev), mean, invstd, relu=relu)
+    # same gradients with the ReLU mask recomputed from z instead of read from y (bit-identical by construction)
+    dz2, dgam2, dbet2 = ops.bn_bwd(dyb, None, zb, gamma.detach().to(dev), mean, invstd, relu=relu, beta=beta.detach().to(dev))
+    assert torch.equal(dz2, dz) and torch.equal(dgam2, dgam) and torch.equal(dbet2, dbet)
     # the kernel masks with its own bf16 y (> 0); where torch's fp32 y differs in sign the elements are ~0 anyway
     assert rel(nchw(dz), zr.grad) <= 1e-2
     assert rel(dgam, gamma.grad) <= 2e-3 and rel(dbet, beta.grad) <= 2e-3

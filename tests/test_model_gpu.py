@@ -323,7 +323,7 @@ def test_resnet50_unet_dropin(b2u, cuda_device, golden_dir):
         if name.endswith("running_mean"):
             assert rel(b, s32[name]) <= 6e-2, name
         elif name.endswith("running_var"):
-            assert rel(b, s32[name]) <= 1e-2, name
+            assert rel(b, s32[name]) <= 2e-2, name
     g = np.load(os.path.join(golden_dir, "unet_resnet50_nc21_cedice.npz"))
     assert rel(outputs, torch.from_numpy(g["logits"])) <= max(1.5 * noise_z, 1e-2)
     assert abs(loss.item() - float(g["loss"])) <= 1e-2 * abs(float(g["loss"]))

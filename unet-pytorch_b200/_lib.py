@@ -35,7 +35,7 @@ SIGNATURES = {
     "b2u_bn_workspace": (SZ, [I]),
     "b2u_bn_fwd_train": (I, [P, P, P, P, P, P, P, P, P, P, SZ, LL, I, F, F, I, P]),
     "b2u_bn_fwd_eval": (I, [P, P, P, P, P, P, P, P, SZ, LL, I, F, I, P]),
-    "b2u_bn_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, SZ, LL, I, I, P]),
+    "b2u_bn_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, P, SZ, LL, I, I, P]),
     "b2u_im2col_stem": (I, [P, P, I, I, I, I, P]),
     "b2u_pack_weights_im2col": (I, [P, P, I, I, I, I, P]),
     "b2u_conv_wgrad_im2col": (I, [P, I, P, I, P, P, SZ, I, I, I, I, I, P]),
@@ -88,6 +88,46 @@ def lib():
             fn.argtypes = args
         _lib = h
     return _lib
+
+
+class CallProfile:
+    """Measurement aid (scripts/variants_bench.py): while active, every C-ABI call made through lib() is bracketed with CUDA
+    events on the current stream.  read() -> {entry point: {"launches", "ms"}}.  Not used on the product path."""
+
+    def __init__(self, by_shape=False):
+        self.records = {}
+        self.by_shape = by_shape
+
+    def __enter__(self):
+        import torch
+        real, rec, by_shape = lib(), self.records, self.by_shape
+
+        class _Proxy:
+            def __getattr__(self, name):
+                fn = getattr(real, name)
+                if not name.startswith("b2u_") or not SIGNATURES.get(name, (None, []))[1] or SIGNATURES[name][1][-1] is not ctypes.c_void_p:
+                    return fn
+
+                def timed(*a):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); rc = fn(*a); e1.record()
+                    key = name if not by_shape else name + str(tuple(x for x in a if isinstance(x, int) and 0 <= x < (1 << 24)))
+                    rec.setdefault(key, []).append((e0, e1))
+                    return rc
+                return timed
+        global _lib
+        self._real = real
+        _lib = _Proxy()
+        return self
+
+    def __exit__(self, *exc):
+        global _lib
+        _lib = self._real
+
+    def read(self):
+        import torch
+        torch.cuda.synchronize()
+        return {k: {"launches": len(v), "ms": sum(a.elapsed_time(b) for a, b in v)} for k, v in self.records.items()}
 
 
 def check(rc):

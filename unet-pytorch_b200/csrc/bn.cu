@@ -10,7 +10,7 @@
 //               dz = gamma invstd (g - dbeta/P - xhat dgamma/P)
 //
 // All HBM-bound: a column-sum pass (z read once, 2 B/element) + an elementwise pass (4 B/element) forward; a
-// column-sum pass (6 B/element) + an elementwise pass (8 B/element) backward.  Partial sums are fp32 per block,
+// column-sum pass (4 B/element; 6 with a residual) + an elementwise pass (6 B/element; 8 / 10 with a residual) backward.  Partial sums are fp32 per block,
 // combined in fp64 in block order by a one-block finalize kernel (deterministic).
 #include "b2u_internal.h"
 #include "b2u_ptx.cuh"
@@ -24,7 +24,7 @@ namespace b2u {
     b2u::note_launch();                                                                                  \
   } while (0)
 
-constexpr int kBnBlocks = 2 * 148;
+constexpr int kBnBlocks = 2 * 148;      // column-sum grid: 2 resident blocks of 256 threads per SM
 
 __device__ __forceinline__ void bn_unpack8(const uint4& v, float* f) {
   f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
@@ -36,43 +36,80 @@ __device__ __forceinline__ uint4 bn_pack8(const float* f) {
   v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
   return v;
 }
+// 8 consecutive per-channel fp32 coefficients as two 16-byte loads
+__device__ __forceinline__ void bn_load8(const float* __restrict__ p, float* f) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+// The forward's affine form, reproducible bit for bit from (gamma, beta, save_mean, save_invstd): the backward
+// recomputes the ReLU mask as fmaf(z, scale, shift) > 0 instead of re-reading y.
+__device__ __forceinline__ void bn_affine(float g, float bt, float mean, float invstd, float* scale, float* shift) {
+  const double sc = static_cast<double>(g) * static_cast<double>(invstd);
+  *scale = static_cast<float>(sc);
+  *shift = static_cast<float>(static_cast<double>(bt) - static_cast<double>(mean) * sc);
+}
 
-// Column sums of two per-element quantities.  MODE 0: (z, z^2).  MODE 1: (g, g * xhat) with g = dy * mask.
-// partial layout: [block][2][C].  blockDim.x = 256; thread -> (row lane, 8-channel chunk).
+// Column sums of two per-element quantities.  MODE 0: (z, z^2).  MODE 1: (g, g * xhat) with g = dy * mask, where the
+// mask is y > 0 (y given: residual blocks) or recomputed from z (y null).  partial layout: [block][2][C].
+// blockDim.x = 256; thread -> (row lane, 8-channel chunk); kBnUnroll rows (independent 16-byte loads per operand) are
+// requested before any is consumed: ~64 KB in flight per SM.
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_colsum_kernel(const uint4* __restrict__ a, const uint4* __restrict__ y, const uint4* __restrict__ z,
+                 const float* __restrict__ gamma, const float* __restrict__ beta,
                  const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ partial,
                  long long P, int C8, int relu) {
+  constexpr int kBnUnroll = MODE == 0 ? 8 : 4;
   extern __shared__ float sred[];          // [256][16]
   const int tid = threadIdx.x;
   const int cpt = C8 < 256 ? C8 : 256;
   const int rows = 256 / cpt;
   const int cc = tid % cpt, rr = tid / cpt;
+  const long long stride = static_cast<long long>(gridDim.x) * rows;
   for (int c0 = 0; c0 < C8; c0 += cpt) {
     const int c = c0 + cc;
     float s0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (c < C8 && rr < rows) {
-      float mu[8], is[8];
+      float mu[8], is[8], sc[8], sh[8];
       if (MODE == 1) {
+        bn_load8(mean + c * 8, mu); bn_load8(invstd + c * 8, is);
+        if (relu && !y) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { mu[k] = mean[c * 8 + k]; is[k] = invstd[c * 8 + k]; }
+          for (int k = 0; k < 8; ++k)
+            bn_affine(gamma ? gamma[c * 8 + k] : 1.f, beta ? beta[c * 8 + k] : 0.f, mu[k], is[k], &sc[k], &sh[k]);
+        }
       }
-      for (long long p = static_cast<long long>(blockIdx.x) * rows + rr; p < P; p += static_cast<long long>(gridDim.x) * rows) {
-        float f[8];
-        bn_unpack8(__ldg(a + p * C8 + c), f);
-        if (MODE == 0) {
+      const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+      for (long long p = static_cast<long long>(blockIdx.x) * rows + rr; p < P; p += kBnUnroll * stride) {
+        uint4 va[kBnUnroll], vz[kBnUnroll], vy[kBnUnroll];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) { s0[k] += f[k]; s1[k] = fmaf(f[k], f[k], s1[k]); }
-        } else {
-          float yy[8], zz[8];
-          bn_unpack8(__ldg(z + p * C8 + c), zz);
-          if (relu) bn_unpack8(__ldg(y + p * C8 + c), yy);
+        for (int u = 0; u < kBnUnroll; ++u) {
+          const long long q = p + u * stride;
+          const bool ok = q < P;
+          va[u] = ok ? __ldg(a + q * C8 + c) : zero;
+          if (MODE == 1) {
+            vz[u] = ok ? __ldg(z + q * C8 + c) : zero;
+            if (relu && y) vy[u] = ok ? __ldg(y + q * C8 + c) : zero;
+          }
+        }
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float g = (!relu || yy[k] > 0.f) ? f[k] : 0.f;
-            s0[k] += g;
-            s1[k] = fmaf(g, (zz[k] - mu[k]) * is[k], s1[k]);
+        for (int u = 0; u < kBnUnroll; ++u) {
+          float f[8];
+          bn_unpack8(va[u], f);
+          if (MODE == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { s0[k] += f[k]; s1[k] = fmaf(f[k], f[k], s1[k]); }
+          } else {
+            float zz[8], yy[8];
+            bn_unpack8(vz[u], zz);
+            if (relu && y) bn_unpack8(vy[u], yy);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const bool on = !relu || (y ? yy[k] > 0.f : fmaf(zz[k], sc[k], sh[k]) > 0.f);
+              const float g = on ? f[k] : 0.f;      // rows past the end carry dy = 0
+              s0[k] += g;
+              s1[k] = fmaf(g, (zz[k] - mu[k]) * is[k], s1[k]);
+            }
           }
         }
       }
@@ -109,11 +146,10 @@ __global__ void bn_fwd_finalize_kernel(const float* __restrict__ partial, int bl
   double var = ss / static_cast<double>(P) - mean * mean;
   if (var < 0.0) var = 0.0;
   const double invstd = 1.0 / sqrt(var + static_cast<double>(eps));
-  save_mean[c] = static_cast<float>(mean);
-  save_invstd[c] = static_cast<float>(invstd);
-  const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
-  scale[c] = static_cast<float>(g * invstd);
-  shift[c] = static_cast<float>(bt - mean * g * invstd);
+  const float mean_f = static_cast<float>(mean), invstd_f = static_cast<float>(invstd);
+  save_mean[c] = mean_f;
+  save_invstd[c] = invstd_f;
+  bn_affine(gamma ? gamma[c] : 1.f, beta ? beta[c] : 0.f, mean_f, invstd_f, scale + c, shift + c);
   if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
   if (running_var) {
     const double unbiased = P > 1 ? var * static_cast<double>(P) / static_cast<double>(P - 1) : var;
@@ -132,27 +168,51 @@ __global__ void bn_eval_coeff_kernel(const float* __restrict__ gamma, const floa
   shift[c] = bt - running_mean[c] * g * is;
 }
 
-// y = [relu](z * scale + shift); one thread per (row, 8-channel chunk) through the row-indexed grid
-__global__ void bn_apply_kernel(const uint4* __restrict__ z, const uint4* __restrict__ res, uint4* __restrict__ y,
-                                const float* __restrict__ scale, const float* __restrict__ shift, long long total, int C8,
-                                int relu) {
+// y = [relu](z * scale + shift).  One thread = one 8-channel chunk of kBnApplyRows rows spaced G rows apart (so a warp's
+// loads stay contiguous): the per-channel coefficients are loaded once and all the rows' 16-byte loads are in flight
+// together.
+constexpr int kBnApplyRows = 4;
+
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const uint4* __restrict__ z, const uint4* __restrict__ res, uint4* __restrict__ y,
+                const float* __restrict__ scale, const float* __restrict__ shift, long long P, long long G, int C8, int relu) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c = static_cast<int>(static_cast<unsigned>(i) % static_cast<unsigned>(C8));   // host guarantees total < 2^31
-  float f[8], rs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  bn_unpack8(__ldg(z + i), f);
-  if (res) bn_unpack8(__ldg(res + i), rs);          // residual branch of a bottleneck: y = relu(bn(z) + identity)
+  if (i >= G * C8) return;
+  const long long g = i / C8;
+  const int c = static_cast<int>(i - g * C8);
+  uint4 vz[kBnApplyRows], vr[kBnApplyRows];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    float v = fmaf(f[k], __ldg(scale + c * 8 + k), __ldg(shift + c * 8 + k)) + rs[k];
-    f[k] = relu ? fmaxf(v, 0.f) : v;
+  for (int u = 0; u < kBnApplyRows; ++u) {
+    const long long row = g + u * G;
+    if (row < P) {
+      vz[u] = __ldg(z + row * C8 + c);
+      if (res) vr[u] = __ldg(res + row * C8 + c);      // residual branch of a bottleneck: y = relu(bn(z) + identity)
+    }
   }
-  y[i] = bn_pack8(f);
+  float sc[8], sh[8];
+  bn_load8(scale + c * 8, sc); bn_load8(shift + c * 8, sh);
+#pragma unroll
+  for (int u = 0; u < kBnApplyRows; ++u) {
+    const long long row = g + u * G;
+    if (row >= P) break;
+    float f[8], rs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bn_unpack8(vz[u], f);
+    if (res) bn_unpack8(vr[u], rs);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float v = fmaf(f[k], sc[k], sh[k]) + rs[k];
+      f[k] = relu ? fmaxf(v, 0.f) : v;
+    }
+    y[row * C8 + c] = bn_pack8(f);
+  }
 }
 
-// backward finalize: dgamma, dbeta and the three per-channel coefficients of the apply pass
+// backward finalize: dgamma, dbeta and the per-channel coefficients of the apply pass.
+// dz = a (g - b - xhat c) with a = gamma invstd, b = dbeta / P, c = dgamma / P, written as dz = a g + kz z + k0.
+// coef: [5][C] = a, kz, k0, scale, shift (the last two reproduce the forward's ReLU mask).
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int C, long long P,
-                                       const float* __restrict__ gamma, const float* __restrict__ invstd,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       const float* __restrict__ mean, const float* __restrict__ invstd,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -164,34 +224,55 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int bl
   if (dbeta) dbeta[c] = static_cast<float>(sg);
   if (dgamma) dgamma[c] = static_cast<float>(sgx);
   const float g = gamma ? gamma[c] : 1.f;
-  coef[c] = g * invstd[c];                                   // a
-  coef[C + c] = static_cast<float>(sg / static_cast<double>(P));      // b = dbeta / P
-  coef[2 * C + c] = static_cast<float>(sgx / static_cast<double>(P)); // c = dgamma / P
+  const double a = static_cast<double>(g) * invstd[c];
+  const double kz = -a * (sgx / static_cast<double>(P)) * invstd[c];
+  coef[c] = static_cast<float>(a);
+  coef[C + c] = static_cast<float>(kz);
+  coef[2 * C + c] = static_cast<float>(-a * (sg / static_cast<double>(P)) - kz * mean[c]);
+  bn_affine(g, beta ? beta[c] : 0.f, mean[c], invstd[c], coef + 3 * C + c, coef + 4 * C + c);
 }
 
-// dz = a (g - b - xhat c)
-__global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, const uint4* __restrict__ z,
-                                    const float* __restrict__ mean, const float* __restrict__ invstd,
-                                    const float* __restrict__ coef, uint4* __restrict__ dz, uint4* __restrict__ gout,
-                                    long long total, int C8, int relu) {
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, const uint4* __restrict__ z,
+                    const float* __restrict__ coef, uint4* __restrict__ dz, uint4* __restrict__ gout, long long P,
+                    long long G, int C8, int relu) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c = static_cast<int>(static_cast<unsigned>(i) % static_cast<unsigned>(C8));
+  if (i >= G * C8) return;
+  const long long gr = i / C8;
+  const int c = static_cast<int>(i - gr * C8);
   const int C = C8 * 8;
-  float g[8], yy[8], zz[8], o[8], gm[8];
-  bn_unpack8(__ldg(dy + i), g);
-  bn_unpack8(__ldg(z + i), zz);
-  if (relu) bn_unpack8(__ldg(y + i), yy);
+  const bool from_y = relu && y;
+  uint4 vg[kBnApplyRows], vz[kBnApplyRows], vy[kBnApplyRows];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int ch = c * 8 + k;
-    const float gg = (!relu || yy[k] > 0.f) ? g[k] : 0.f;
-    const float xhat = (zz[k] - __ldg(mean + ch)) * __ldg(invstd + ch);
-    o[k] = __ldg(coef + ch) * (gg - __ldg(coef + C + ch) - xhat * __ldg(coef + 2 * C + ch));
-    gm[k] = gg;
+  for (int u = 0; u < kBnApplyRows; ++u) {
+    const long long row = gr + u * G;
+    if (row < P) {
+      vg[u] = __ldg(dy + row * C8 + c);
+      vz[u] = __ldg(z + row * C8 + c);
+      if (from_y) vy[u] = __ldg(y + row * C8 + c);
+    }
   }
-  if (gout) gout[i] = bn_pack8(gm);      // ReLU-masked dy: the gradient of the residual (identity) branch
-  dz[i] = bn_pack8(o);
+  float ca[8], kz[8], k0[8], sc[8], sh[8];
+  bn_load8(coef + c * 8, ca); bn_load8(coef + C + c * 8, kz); bn_load8(coef + 2 * C + c * 8, k0);
+  if (relu && !y) { bn_load8(coef + 3 * C + c * 8, sc); bn_load8(coef + 4 * C + c * 8, sh); }
+#pragma unroll
+  for (int u = 0; u < kBnApplyRows; ++u) {
+    const long long row = gr + u * G;
+    if (row >= P) break;
+    float g[8], yy[8], zz[8], o[8], gm[8];
+    bn_unpack8(vg[u], g);
+    bn_unpack8(vz[u], zz);
+    if (from_y) bn_unpack8(vy[u], yy);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const bool on = !relu || (from_y ? yy[k] > 0.f : fmaf(zz[k], sc[k], sh[k]) > 0.f);
+      const float gg = on ? g[k] : 0.f;
+      o[k] = fmaf(ca[k], gg, fmaf(kz[k], zz[k], k0[k]));
+      gm[k] = gg;
+    }
+    if (gout) gout[row * C8 + c] = bn_pack8(gm);      // ReLU-masked dy: the gradient of the residual (identity) branch
+    dz[row * C8 + c] = bn_pack8(o);
+  }
 }
 
 }  // namespace b2u
@@ -199,8 +280,8 @@ __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* _
 extern "C" {
 using namespace b2u;
 
-// workspace: [blocks][2][C] fp32 partial sums + 3*C coefficients (scale/shift or a/b/c)
-size_t b2u_bn_workspace(int C) { return (static_cast<size_t>(kBnBlocks) * 2 * C + 3 * static_cast<size_t>(C)) * sizeof(float); }
+// workspace: [blocks][2][C] fp32 partial sums + 5*C coefficients
+size_t b2u_bn_workspace(int C) { return (static_cast<size_t>(kBnBlocks) * 2 * C + 5 * static_cast<size_t>(C)) * sizeof(float); }
 
 static int bn_check(long long P, int C, const void* ws, size_t ws_bytes, const char* who) {
   if (P <= 0 || C <= 0 || C % 8 != 0) return set_error(B2U_ERR_SHAPE, "%s: needs P > 0 and C %% 8 == 0 (C=%d)", who, C);
@@ -217,15 +298,15 @@ int b2u_bn_fwd_train(const void* z, const void* residual, void* y, const float* 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* partial = static_cast<float*>(ws);
   float* coef = partial + static_cast<size_t>(kBnBlocks) * 2 * C;
-  bn_colsum_kernel<0><<<kBnBlocks, 256, 256 * 16 * sizeof(float), st>>>(static_cast<const uint4*>(z), nullptr, nullptr,
-                                                                        nullptr, nullptr, partial, P, C / 8, 0);
+  bn_colsum_kernel<0><<<kBnBlocks, 256, 256 * 16 * sizeof(float), st>>>(static_cast<const uint4*>(z), nullptr, nullptr, nullptr,
+                                                                        nullptr, nullptr, nullptr, partial, P, C / 8, 0);
   B2U_CHECK_LAUNCH("bn_colsum");
   bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, kBnBlocks, C, P, gamma, beta, running_mean, running_var,
                                                           save_mean, save_invstd, coef, coef + C, eps, momentum);
   B2U_CHECK_LAUNCH("bn_fwd_finalize");
-  const long long total = P * (C / 8);
-  bn_apply_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(static_cast<const uint4*>(z), static_cast<const uint4*>(residual),
-                                                                             static_cast<uint4*>(y), coef, coef + C, total, C / 8, relu);
+  const long long G = (P + kBnApplyRows - 1) / kBnApplyRows;
+  bn_apply_kernel<<<static_cast<unsigned>((G * (C / 8) + 255) / 256), 256, 0, st>>>(static_cast<const uint4*>(z), static_cast<const uint4*>(residual),
+                                                                                   static_cast<uint4*>(y), coef, coef + C, P, G, C / 8, relu);
   B2U_CHECK_LAUNCH("bn_apply");
   return 0;
 }
@@ -240,16 +321,19 @@ int b2u_bn_fwd_eval(const void* z, const void* residual, void* y, const float* g
   float* coef = static_cast<float*>(ws);
   bn_eval_coeff_kernel<<<(C + 127) / 128, 128, 0, st>>>(gamma, beta, running_mean, running_var, coef, coef + C, C, eps);
   B2U_CHECK_LAUNCH("bn_eval_coeff");
-  const long long total = P * (C / 8);
-  bn_apply_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(static_cast<const uint4*>(z), static_cast<const uint4*>(residual),
-                                                                             static_cast<uint4*>(y), coef, coef + C, total, C / 8, relu);
+  const long long G = (P + kBnApplyRows - 1) / kBnApplyRows;
+  bn_apply_kernel<<<static_cast<unsigned>((G * (C / 8) + 255) / 256), 256, 0, st>>>(static_cast<const uint4*>(z), static_cast<const uint4*>(residual),
+                                                                                   static_cast<uint4*>(y), coef, coef + C, P, G, C / 8, relu);
   B2U_CHECK_LAUNCH("bn_apply");
   return 0;
 }
 
 // dy: gradient wrt y = [relu](bn(z) [+ residual]); dz (may alias dy) = gradient wrt the BN input z; gout (nullable,
-// must not alias dy/dz) = dy masked by the ReLU = gradient wrt the residual input
-int b2u_bn_bwd(const void* dy, const void* y, const void* z, const float* gamma, const float* save_mean,
+// must not alias dy/dz) = dy masked by the ReLU = gradient wrt the residual input.
+// y: the forward output, needed only when a residual was added before the ReLU; y == NULL (no residual) recomputes the
+// ReLU mask from z, gamma, beta and the saved statistics exactly as the forward evaluated it, saving one tensor read
+// in each of the two passes.
+int b2u_bn_bwd(const void* dy, const void* y, const void* z, const float* gamma, const float* beta, const float* save_mean,
                const float* save_invstd, void* dz, void* gout, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
                long long P, int C, int relu, void* stream) {
   int rc = bn_check(P, C, ws, ws_bytes, "bn_bwd");
@@ -258,15 +342,16 @@ int b2u_bn_bwd(const void* dy, const void* y, const void* z, const float* gamma,
   float* partial = static_cast<float*>(ws);
   float* coef = partial + static_cast<size_t>(kBnBlocks) * 2 * C;
   bn_colsum_kernel<1><<<kBnBlocks, 256, 256 * 16 * sizeof(float), st>>>(static_cast<const uint4*>(dy), static_cast<const uint4*>(y),
-                                                                        static_cast<const uint4*>(z), save_mean, save_invstd,
-                                                                        partial, P, C / 8, relu);
+                                                                        static_cast<const uint4*>(z), gamma, beta, save_mean,
+                                                                        save_invstd, partial, P, C / 8, relu);
   B2U_CHECK_LAUNCH("bn_bwd_colsum");
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, kBnBlocks, C, P, gamma, save_invstd, dgamma, dbeta, coef);
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, kBnBlocks, C, P, gamma, beta, save_mean, save_invstd, dgamma,
+                                                          dbeta, coef);
   B2U_CHECK_LAUNCH("bn_bwd_finalize");
-  const long long total = P * (C / 8);
-  bn_bwd_apply_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
-      static_cast<const uint4*>(dy), static_cast<const uint4*>(y), static_cast<const uint4*>(z), save_mean, save_invstd, coef,
-      static_cast<uint4*>(dz), static_cast<uint4*>(gout), total, C / 8, relu);
+  const long long G = (P + kBnApplyRows - 1) / kBnApplyRows;
+  bn_bwd_apply_kernel<<<static_cast<unsigned>((G * (C / 8) + 255) / 256), 256, 0, st>>>(
+      static_cast<const uint4*>(dy), static_cast<const uint4*>(y), static_cast<const uint4*>(z), coef,
+      static_cast<uint4*>(dz), static_cast<uint4*>(gout), P, G, C / 8, relu);
   B2U_CHECK_LAUNCH("bn_bwd_apply");
   return 0;
 }

@@ -32,45 +32,111 @@ __device__ __forceinline__ uint4 d_pack8(const float* f) {
 }
 
 // ------------------------------------------------------------------------------------------ depthwise 3x3
-// one thread = one pixel x 8 channels; w: fp32 [C][9]; flip: use w[8 - tap] (dgrad)
-__global__ void dwconv3x3_kernel(const uint4* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                                 uint4* __restrict__ y, int N, int H, int W, int C8, int flip) {
-  const unsigned t = blockIdx.y * blockDim.x + threadIdx.x;
-  if (t >= static_cast<unsigned>(W) * C8) return;
+// One thread = one image column x 8 channels, marching down a strip of R output rows: every input row is fetched once
+// (three 16-byte pieces: columns x-1, x, x+1; the horizontal neighbours are other lanes' lines in L1) and feeds the three
+// output rows it overlaps, held in a rolling register window; the chunk's 72 weights stay in registers.
+// The fetches are cp.async copies into thread-private shared-memory slots, kDwStages rows deep, so the bytes in flight
+// (what an HBM-bound kernel needs) cost no registers and no block-level synchronisation; out-of-image pieces are
+// zero-filled by the copy itself (src-size 0).
+// Traffic: (R+2)/R reads + 1 write per element.  w: fp32 [C][9]; FLIP uses w[8 - tap] (the data gradient).
+constexpr int kDwRows = 8;
+constexpr int kDwStages = 4;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool FLIP>
+__global__ void __launch_bounds__(128, 3)
+dwconv3x3_strip_kernel(const uint4* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                       uint4* __restrict__ y, int H, int W, int C8) {
+  __shared__ uint4 slots[kDwStages][3][128];      // [stage][column piece][thread]
+  const unsigned t = blockIdx.x * 128u + threadIdx.x;
+  if (t >= static_cast<unsigned>(W) * C8) return;   // no block-level barrier below: early exit is safe
   const int wx = t / C8, c = t - wx * C8;
-  const int n = blockIdx.x / H, h = blockIdx.x - n * H;
-  float acc[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) acc[k] = bias ? __ldg(bias + c * 8 + k) : 0.f;
+  const int h0 = blockIdx.y * kDwRows, n = blockIdx.z;
   const uint4* img = x + static_cast<size_t>(n) * H * W * C8 + c;
+  const bool left = wx > 0, right = wx + 1 < W;
+  auto fetch_row = [&](int i) {        // strip-relative input row i -> stage i % kDwStages
+    const int r = h0 - 1 + i;
+    const bool ok = r >= 0 && r < H;
+    const uint4* row = img + (static_cast<size_t>(ok ? r : 0) * W + wx) * C8;
+    const int st = i % kDwStages;
+    cp_async16(smem_u32(&slots[st][0][threadIdx.x]), left ? row - C8 : row, ok && left);
+    cp_async16(smem_u32(&slots[st][1][threadIdx.x]), row, ok);
+    cp_async16(smem_u32(&slots[st][2][threadIdx.x]), right ? row + C8 : row, ok && right);
+  };
 #pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const int hh = h + r - 1;
-    if (hh < 0 || hh >= H) continue;
+  for (int i = 0; i < kDwStages - 1; ++i) { fetch_row(i); cp_async_commit(); }
+  float wt[9][8];                       // [tap as applied][channel]
+  {
+    float wf[72];
+    const float4* wp = reinterpret_cast<const float4*>(w + static_cast<size_t>(c) * 72);
 #pragma unroll
-    for (int s = 0; s < 3; ++s) {
-      const int ww = wx + s - 1;
-      if (ww < 0 || ww >= W) continue;
-      float f[8];
-      d_unpack8(__ldg(img + (static_cast<size_t>(hh) * W + ww) * C8), f);
-      const int tap = flip ? 8 - (r * 3 + s) : r * 3 + s;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] = fmaf(f[k], __ldg(w + (c * 8 + k) * 9 + tap), acc[k]);
+    for (int i = 0; i < 18; ++i) {
+      const float4 v = __ldg(wp + i);
+      wf[4 * i] = v.x; wf[4 * i + 1] = v.y; wf[4 * i + 2] = v.z; wf[4 * i + 3] = v.w;
     }
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) wt[tap][k] = wf[k * 9 + (FLIP ? 8 - tap : tap)];
   }
-  y[static_cast<size_t>(blockIdx.x) * W * C8 + t] = d_pack8(acc);
+  float b8[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) b8[k] = bias ? __ldg(bias + c * 8 + k) : 0.f;
+  uint4* out = y + static_cast<size_t>(n) * H * W * C8 + t;
+  float a0[8], a1[8], a2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { a0[k] = b8[k]; a1[k] = b8[k]; }
+#pragma unroll
+  for (int i = 0; i < kDwRows + 2; ++i) {
+    const int r = h0 - 1 + i;           // input row; feeds output rows r-1 (kernel row 2), r (1), r+1 (0)
+    if (i + kDwStages - 1 < kDwRows + 2) fetch_row(i + kDwStages - 1);
+    cp_async_commit();                  // one group per iteration (possibly empty) keeps the wait count uniform
+    cp_async_wait<kDwStages - 1>();     // row i has landed
+    const int st = i % kDwStages;
+    float f[3][8];
+    d_unpack8(slots[st][0][threadIdx.x], f[0]);
+    d_unpack8(slots[st][1][threadIdx.x], f[1]);
+    d_unpack8(slots[st][2][threadIdx.x], f[2]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a2[k] = b8[k];
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {     // rows/columns outside the image arrive as zeros
+        a0[k] = fmaf(f[s][k], wt[6 + s][k], a0[k]);
+        a1[k] = fmaf(f[s][k], wt[3 + s][k], a1[k]);
+        a2[k] = fmaf(f[s][k], wt[s][k], a2[k]);
+      }
+    const int o = r - 1;                // output row completed by this input row
+    if (i >= 2 && o < H) out[static_cast<size_t>(o) * W * C8] = d_pack8(a0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a0[k] = a1[k]; a1[k] = a2[k]; }
+  }
 }
 
-// partial[block][C][10]: 9 weight-gradient taps + bias gradient per channel, over the block's pixel rows
-__global__ void __launch_bounds__(256)
-dwconv3x3_wgrad_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, float* __restrict__ partial, int N, int H,
-                       int W, int C8) {
-  extern __shared__ float sred[];          // [256][10]
+// Weight + bias gradient: same marching scheme and cp.async pipeline (four pieces per row: dy and three columns of x);
+// thread = (column, 8-channel chunk) keeps the 9 tap sums and the bias sum of its chunk in registers over all its work
+// items (image, strip of R rows, column tile), then the block folds its column lanes in shared memory and writes one
+// partial [C][10] (9 taps + bias).  Traffic: (R+2)/R x + 1 dy reads.
+constexpr int kDwgStages = 3;
+
+__global__ void __launch_bounds__(128, 3)
+dwconv3x3_wgrad_strip_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, float* __restrict__ partial, int N,
+                             int H, int W, int C8) {
+  __shared__ uint4 slots[kDwgStages][4][128];      // [stage][dy, x-1, x, x+1][thread]; reused by the final fold
+  float* sred = reinterpret_cast<float*>(slots);   // [128][10]
   const int tid = threadIdx.x;
-  const int cpt = C8 < 256 ? C8 : 256;
-  const int lanes = 256 / cpt;
-  const int cc = tid % cpt, rr = tid / cpt;
-  const long long P = static_cast<long long>(N) * H * W;
+  const int cpt = C8 < 128 ? C8 : 128;     // chunks handled per pass
+  const int xs = 128 / cpt;                // columns per block
+  const int cc = tid % cpt, xi = tid / cpt;
+  const int strips = (H + kDwRows - 1) / kDwRows, xtiles = (W + xs - 1) / xs;
+  const long long items = static_cast<long long>(N) * strips * xtiles;
   for (int c0 = 0; c0 < C8; c0 += cpt) {
     const int c = c0 + cc;
     float acc[10][8];
@@ -78,43 +144,70 @@ dwconv3x3_wgrad_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy
     for (int a = 0; a < 10; ++a)
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[a][k] = 0.f;
-    if (c < C8 && rr < lanes) {
-      for (long long p = static_cast<long long>(blockIdx.x) * lanes + rr; p < P; p += static_cast<long long>(gridDim.x) * lanes) {
-        const int wx = static_cast<int>(p % W);
-        const long long q = p / W;
-        const int h = static_cast<int>(q % H);
-        const long long n = q / H;
-        float g[8];
-        d_unpack8(__ldg(dy + p * C8 + c), g);
+    if (c < C8 && xi < xs) {
+      for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+        const int xt = static_cast<int>(it % xtiles);
+        const long long q = it / xtiles;
+        const int h0 = static_cast<int>(q % strips) * kDwRows;
+        const long long n = q / strips;
+        const int wx = xt * xs + xi;
+        if (wx >= W) continue;
+        const bool left = wx > 0, right = wx + 1 < W;
+        const uint4* xi_ = x + (n * H * W + wx) * C8 + c;
+        const uint4* di_ = dy + (n * H * W + wx) * C8 + c;
+        auto fetch_row = [&](int i) {
+          const int r = h0 - 1 + i, o = r + 1;      // x row r pairs with dy rows r-1 (tap row 2), r (1), r+1 (0)
+          const bool dok = i < kDwRows && o < H, xok = r >= 0 && r < H;
+          const uint4* drow = di_ + static_cast<size_t>(dok ? o : 0) * W * C8;
+          const uint4* row = xi_ + static_cast<size_t>(xok ? r : 0) * W * C8;
+          const int st = i % kDwgStages;
+          cp_async16(smem_u32(&slots[st][0][tid]), drow, dok);
+          cp_async16(smem_u32(&slots[st][1][tid]), left ? row - C8 : row, xok && left);
+          cp_async16(smem_u32(&slots[st][2][tid]), row, xok);
+          cp_async16(smem_u32(&slots[st][3][tid]), right ? row + C8 : row, xok && right);
+        };
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[9][k] += g[k];
+        for (int i = 0; i < kDwgStages - 1; ++i) { fetch_row(i); cp_async_commit(); }
+        float d0[8], d1[8], d2[8];          // dy rows r-1, r, r+1 (zero outside the strip / image)
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const int hh = h + r - 1;
-          if (hh < 0 || hh >= H) continue;
+        for (int k = 0; k < 8; ++k) { d0[k] = 0.f; d1[k] = 0.f; }
 #pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            const int ww = wx + s - 1;
-            if (ww < 0 || ww >= W) continue;
-            float f[8];
-            d_unpack8(__ldg(x + ((n * H + hh) * W + ww) * C8 + c), f);
+        for (int i = 0; i < kDwRows + 2; ++i) {
+          if (i + kDwgStages - 1 < kDwRows + 2) fetch_row(i + kDwgStages - 1);
+          cp_async_commit();
+          cp_async_wait<kDwgStages - 1>();
+          const int st = i % kDwgStages;
+          d_unpack8(slots[st][0][tid], d2);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[r * 3 + s][k] = fmaf(g[k], f[k], acc[r * 3 + s][k]);
-          }
+          for (int k = 0; k < 8; ++k) acc[9][k] += d2[k];
+          float f[3][8];
+          d_unpack8(slots[st][1][tid], f[0]); d_unpack8(slots[st][2][tid], f[1]); d_unpack8(slots[st][3][tid], f[2]);
+#pragma unroll
+          for (int s = 0; s < 3; ++s)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              acc[6 + s][k] = fmaf(d0[k], f[s][k], acc[6 + s][k]);
+              acc[3 + s][k] = fmaf(d1[k], f[s][k], acc[3 + s][k]);
+              acc[s][k] = fmaf(d2[k], f[s][k], acc[s][k]);
+            }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { d0[k] = d1[k]; d1[k] = d2[k]; }
         }
       }
     }
-    // reduce the row lanes, one channel element at a time (keeps shared memory at 10 KB)
+    cp_async_wait<0>();
+    __syncthreads();                       // the slots become the fold buffer
+    // fold the column lanes, one channel element at a time
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
 #pragma unroll
       for (int a = 0; a < 10; ++a) sred[tid * 10 + a] = acc[a][k];
       __syncthreads();
-      if (rr == 0 && c < C8) {
+      if (xi == 0 && c < C8) {
         float* out = partial + (static_cast<size_t>(blockIdx.x) * C8 * 8 + c * 8 + k) * 10;
         for (int a = 0; a < 10; ++a) {
           float t = sred[tid * 10 + a];
-          for (int r = 1; r < lanes; ++r) t += sred[(r * cpt + cc) * 10 + a];
+          for (int r = 1; r < xs; ++r) t += sred[(r * cpt + cc) * 10 + a];
           out[a] = t;
         }
       }
@@ -123,9 +216,9 @@ dwconv3x3_wgrad_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy
   }
 }
 
-// out[i] = sum_r partial[r][i]  (same shape of reduction as reduce_rows in elementwise.cu)
+// dw[c][a] / db[c] = sum_r partial[r][c][10]  (fixed order: deterministic)
 __global__ void __launch_bounds__(256)
-dw_reduce_rows_kernel(const float* __restrict__ partial, float* __restrict__ out, int rows, int L) {
+dw_reduce_split_kernel(const float* __restrict__ partial, float* __restrict__ dw, float* __restrict__ db, int rows, int L) {
   __shared__ float sred[8][33];
   const int col = threadIdx.x & 31, lane_r = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + col;
@@ -138,7 +231,9 @@ dw_reduce_rows_kernel(const float* __restrict__ partial, float* __restrict__ out
     float t = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) t += sred[k][col];
-    out[i] = t;
+    const int c = i / 10, a = i - c * 10;
+    if (a < 9) { if (dw) dw[c * 9 + a] = t; }
+    else if (db) db[c] = t;
   }
 }
 
@@ -303,13 +398,17 @@ using namespace b2u;
 int b2u_dwconv3x3_fwd(const void* x, const float* w, const float* bias, void* y, int N, int H, int W, int C, int flip,
                       void* stream) {
   if (N <= 0 || H <= 0 || W <= 0 || C % 8 != 0) return set_error(B2U_ERR_SHAPE, "dwconv3x3: bad shape");
-  dwconv3x3_kernel<<<rgrid(static_cast<long long>(N) * H, W * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(x), w, bias, static_cast<uint4*>(y), N, H, W, C / 8, flip);
+  if (N > 65535 || (H + kDwRows - 1) / kDwRows > 65535) return set_error(B2U_ERR_SHAPE, "dwconv3x3: N or H too large");
+  const dim3 grid((static_cast<unsigned>(W) * (C / 8) + 127) / 128, (H + kDwRows - 1) / kDwRows, N);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (reinterpret_cast<uintptr_t>(w) % 16 != 0) return set_error(B2U_ERR_ARG, "dwconv3x3: weights must be 16-byte aligned");
+  if (flip) dwconv3x3_strip_kernel<true><<<grid, 128, 0, st>>>(static_cast<const uint4*>(x), w, bias, static_cast<uint4*>(y), H, W, C / 8);
+  else      dwconv3x3_strip_kernel<false><<<grid, 128, 0, st>>>(static_cast<const uint4*>(x), w, bias, static_cast<uint4*>(y), H, W, C / 8);
   B2U_CHECK_LAUNCH("dwconv3x3");
   return 0;
 }
 
-static const int kDwBlocks = 2 * 148;
+static const int kDwBlocks = 3 * 148;
 size_t b2u_dwconv3x3_wgrad_workspace(int C) { return (static_cast<size_t>(kDwBlocks) + 1) * C * 10 * sizeof(float); }
 
 // dw: [C][9] fp32, db: [C] (either may be NULL)
@@ -373,16 +472,14 @@ int b2u_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, float* db, voi
   if (!ws || ws_bytes < b2u_dwconv3x3_wgrad_workspace(C)) return set_error(B2U_ERR_ARG, "dwconv3x3_wgrad: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* partial = static_cast<float*>(ws);
-  float* total = partial + static_cast<size_t>(kDwBlocks) * C * 10;      // [C][10]
-  dwconv3x3_wgrad_kernel<<<kDwBlocks, 256, 256 * 10 * sizeof(float), st>>>(static_cast<const uint4*>(x), static_cast<const uint4*>(dy), partial, N, H, W, C / 8);
+  const int C8 = C / 8, cpt = C8 < 128 ? C8 : 128, xs = 128 / cpt;
+  const long long items = static_cast<long long>(N) * ((H + kDwRows - 1) / kDwRows) * ((W + xs - 1) / xs);
+  const int blocks = static_cast<int>(items < kDwBlocks ? items : kDwBlocks);
+  dwconv3x3_wgrad_strip_kernel<<<blocks, 128, 0, st>>>(static_cast<const uint4*>(x), static_cast<const uint4*>(dy),
+                                                                              partial, N, H, W, C8);
   B2U_CHECK_LAUNCH("dwconv3x3_wgrad");
-  dw_reduce_rows_kernel<<<(C * 10 + 31) / 32, 256, 0, st>>>(partial, total, kDwBlocks, C * 10);
-  B2U_CHECK_LAUNCH("dw_reduce_rows");
-  // split [C][10] into dw [C][9] and db [C]
-  if (dw) { cudaError_t e = cudaMemcpy2DAsync(dw, 9 * sizeof(float), total, 10 * sizeof(float), 9 * sizeof(float), C, cudaMemcpyDeviceToDevice, st);
-            if (e != cudaSuccess) return set_error(B2U_ERR_CUDA, "dwconv3x3_wgrad copy: %s", cudaGetErrorString(e)); }
-  if (db) { cudaError_t e = cudaMemcpy2DAsync(db, sizeof(float), total + 9, 10 * sizeof(float), sizeof(float), C, cudaMemcpyDeviceToDevice, st);
-            if (e != cudaSuccess) return set_error(B2U_ERR_CUDA, "dwconv3x3_wgrad copy: %s", cudaGetErrorString(e)); }
+  dw_reduce_split_kernel<<<(C * 10 + 31) / 32, 256, 0, st>>>(partial, dw, db, blocks, C * 10);
+  B2U_CHECK_LAUNCH("dw_reduce_split");
   return 0;
 }
 

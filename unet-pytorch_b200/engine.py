@@ -274,7 +274,7 @@ class UNetEngine:
             nbt = params.get(c.bn + ".num_batches_tracked")
             if nbt is not None:
                 nbt.add_(1)
-            A["bn:" + c.name] = (z, mean, invstd, gamma)
+            A["bn:" + c.name] = (z, mean, invstd, gamma, beta)
         else:
             rmp = self._padded_vec("rm:" + c.bn, rm, c.cout_p)
             rvp = self._padded_vec("rv:" + c.bn, rv, c.cout_p, fill=1.0)
@@ -378,11 +378,11 @@ class UNetEngine:
             masked).  Runs BN backward if any, wgrad, bias grad; returns dz (the conv's output gradient)."""
             dz = g
             if c.bn:
-                z, mean, invstd, gamma = A["bn:" + c.name]
+                z, mean, invstd, gamma, beta = A["bn:" + c.name]
                 wn, bnn = c.bn + ".weight", c.bn + ".bias"
                 dgam = self._buf("dg:" + c.bn, (c.cout_p,), torch.float32)
                 dbet = self._buf("db:" + c.bn, (c.cout_p,), torch.float32)
-                ops.bn_bwd(g, A[c.name], z, gamma, mean, invstd, relu=True, out=g, dgamma=dgam, dbeta=dbet,
+                ops.bn_bwd(g, None, z, gamma, mean, invstd, relu=True, out=g, dgamma=dgam, dbeta=dbet, beta=beta,   # mask from z
                            ws=self._workspace("bn", ops.lib().b2u_bn_workspace(c.cout_p)))
                 if has(wn):
                     grads[wn].copy_(dgam[:c.cout])

@@ -363,7 +363,7 @@ class GraphEngine:
                     mean = invstd = None
                 ng = zt.needs_grad or (res is not None and res.needs_grad) or (bnn + ".weight") in trainable or (bnn + ".bias") in trainable
                 t = _T(y, needs_grad=ng)
-                t.aux = (mean, invstd, gamma)
+                t.aux = (mean, invstd, gamma, beta)
                 T[ins["out"]] = t
             elif op == "dw":
                 xin = T[ins["x"]]
@@ -558,14 +558,16 @@ class GraphEngine:
                     continue
                 bnn, c = ins["bn"], ins["c"]
                 cp = zt.data.shape[3]
-                mean, invstd, gamma = t.aux
+                mean, invstd, gamma, beta = t.aux
                 need_res = res is not None and res.needs_grad
                 gout = self._buf("g:" + ins["out"] + ">res", t.data.shape) if need_res else None
                 dz = self._buf("g:" + ins["z"], zt.data.shape)
                 direct = cp == c
                 dgam = grads[bnn + ".weight"] if (direct and has(bnn + ".weight")) else self._buf("dg:" + bnn, (cp,), torch.float32)
                 dbet = grads[bnn + ".bias"] if (direct and has(bnn + ".bias")) else self._buf("db:" + bnn, (cp,), torch.float32)
-                ops.bn_bwd(t.grad, t.data, zt.data, gamma, mean, invstd, relu=ins["relu"], out=dz, dgamma=dgam, dbeta=dbet,
+                # y is read only where a residual was added before the ReLU; otherwise the mask is recomputed from z
+                ops.bn_bwd(t.grad, t.data if res is not None else None, zt.data, gamma, mean, invstd, relu=ins["relu"], out=dz,
+                           dgamma=dgam, dbeta=dbet, beta=beta,
                            ws=self._workspace("bn", ops.lib().b2u_bn_workspace(cp)), gout=gout)
                 if not direct:
                     if has(bnn + ".weight"):

@@ -261,9 +261,12 @@ def bn_fwd_eval(z, gamma, beta, running_mean, running_var, eps=1e-5, relu=True, 
     return out
 
 
-def bn_bwd(dy, y, z, gamma, mean, invstd, relu=True, out=None, dgamma=None, dbeta=None, ws=None, gout=None):
-    """Returns (dz, dgamma, dbeta); gout (optional tensor) receives the ReLU-masked dy (residual-branch gradient)."""
+def bn_bwd(dy, y, z, gamma, mean, invstd, relu=True, out=None, dgamma=None, dbeta=None, ws=None, gout=None, beta=None):
+    """Returns (dz, dgamma, dbeta); gout (optional tensor) receives the ReLU-masked dy (residual-branch gradient).
+    y=None (allowed when no residual was added before the ReLU; needs beta) recomputes the ReLU mask from z."""
     _req(dy, BF16, "dy"); _req(y, BF16, "y"); _req(z, BF16, "z")
+    if y is None and relu and beta is None:
+        raise ValueError("bn_bwd: y=None needs beta to recompute the ReLU mask")
     C = z.shape[-1]
     P = z.numel() // C
     need = lib().b2u_bn_workspace(C)
@@ -275,8 +278,8 @@ def bn_bwd(dy, y, z, gamma, mean, invstd, relu=True, out=None, dgamma=None, dbet
         dgamma = torch.empty((C,), dtype=torch.float32, device=z.device)
     if dbeta is None:
         dbeta = torch.empty((C,), dtype=torch.float32, device=z.device)
-    check(lib().b2u_bn_bwd(ptr(dy), ptr(y), ptr(z), ptr(gamma), ptr(mean), ptr(invstd), ptr(out), ptr(gout), ptr(dgamma), ptr(dbeta),
-                           ptr(ws), ws.numel() * ws.element_size(), P, C, 1 if relu else 0, stream_ptr()))
+    check(lib().b2u_bn_bwd(ptr(dy), ptr(y), ptr(z), ptr(gamma), ptr(beta), ptr(mean), ptr(invstd), ptr(out), ptr(gout), ptr(dgamma),
+                           ptr(dbeta), ptr(ws), ws.numel() * ws.element_size(), P, C, 1 if relu else 0, stream_ptr()))
     return out, dgamma, dbeta
 
 

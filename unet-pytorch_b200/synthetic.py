@@ -38,3 +38,32 @@ def make_inputs(n, num_classes, h, w, seed=0, medical=False):
     ign = torch.rand(n, h, w, generator=g) < 0.02
     png = torch.where(ign, torch.full_like(png, num_classes), png)
     return img.contiguous(), png.contiguous()
+
+
+def random_state_dict(param_shapes, buffer_shapes, seed=0):
+    """Random-init state_dict for any engine (the benches' stand-in for nets/unet_training.py::weights_init, lines 60-80,
+    and the modules' own _initialize_weights): He-normal dense convs, depthwise taps around 1/3, Linear 1/sqrt(fan_in),
+    BatchNorm weight 1 / bias 0, biases 0, fresh running statistics."""
+    g = torch.Generator().manual_seed(seed)
+    bn = {n[:-len(".running_mean")] for n in buffer_shapes if n.endswith(".running_mean")}
+    sd = {}
+    for name, shape in param_shapes.items():
+        base = name.rsplit(".", 1)[0]
+        if base in bn:
+            sd[name] = torch.ones(shape) if name.endswith(".weight") else torch.zeros(shape)
+        elif len(shape) == 4 and shape[1] == 1 and shape[2] == 3:
+            sd[name] = (1.0 / 3.0) * (1.0 + 0.5 * torch.randn(shape, generator=g))
+        elif len(shape) == 4:
+            sd[name] = torch.randn(shape, generator=g) * (2.0 / (shape[1] * shape[2] * shape[3])) ** 0.5
+        elif len(shape) == 2:
+            sd[name] = torch.randn(shape, generator=g) * (1.0 / shape[1]) ** 0.5
+        else:
+            sd[name] = torch.zeros(shape)
+    for name, shape in buffer_shapes.items():
+        if name.endswith("running_var"):
+            sd[name] = torch.ones(shape)
+        elif name.endswith("num_batches_tracked"):
+            sd[name] = torch.tensor(0, dtype=torch.long)
+        else:
+            sd[name] = torch.zeros(shape)
+    return sd

@@ -190,8 +190,10 @@ class UnetTrainer:
         self._slots = [None, None]
         self._stage_count = 0
         self.last = None
-        if state_dict is not None:
-            self.load_state_dict(state_dict)
+        if state_dict is None:       # random init (the reference's weights_init / _initialize_weights role)
+            from .synthetic import random_state_dict
+            state_dict = random_state_dict(shapes, self.engine.buffer_shapes(), seed=0)
+        self.load_state_dict(state_dict)
         if self.sync.world > 1:
             dist.broadcast(self.flat_param, src=0, group=process_group)      # DDP ctor semantics (train.py:346)
 
