@@ -320,10 +320,12 @@ def test_resnet50_unet_dropin(b2u, cuda_device, golden_dir):
         assert rel(grads[k], g32[k]) <= 2e-2, k
     for name, b in model.named_buffers():
         # statistics of bf16 activations ~50 layers deep: the per-channel means are small against the activations' spread
+        # (layer4 sees 2x2 maps: 8 samples per channel); each buffer is judged against the bf16-storage model's own
+        # distance from fp32 for that buffer
         if name.endswith("running_mean"):
-            assert rel(b, s32[name]) <= 6e-2, name
+            assert rel(b, s32[name]) <= max(6e-2, 1.5 * rel(sbf[name], s32[name])), name
         elif name.endswith("running_var"):
-            assert rel(b, s32[name]) <= 2e-2, name
+            assert rel(b, s32[name]) <= max(2e-2, 1.5 * rel(sbf[name], s32[name])), name
     g = np.load(os.path.join(golden_dir, "unet_resnet50_nc21_cedice.npz"))
     assert rel(outputs, torch.from_numpy(g["logits"])) <= max(1.5 * noise_z, 1e-2)
     assert abs(loss.item() - float(g["loss"])) <= 1e-2 * abs(float(g["loss"]))

@@ -248,137 +248,155 @@ __device__ __forceinline__ void src_index(int o, float scale, int in_size, int& 
   i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
   lam = src - static_cast<float>(i0);
 }
-// Each thread owns one (output column, 8-channel chunk) and walks ROWS consecutive output rows: the column
-// interpolation weights are computed once, and the horizontally interpolated input rows are carried from one output
-// row to the next (consecutive output rows share one of their two source rows), so the kernel issues ~1/3 of the
-// instructions of a one-output-per-thread version and runs at the HBM write rate instead of the issue rate.
-template <int ROWS>
-__global__ void upsample2x_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int C8,
-                                      float sh, float sw) {
+// For scale 2 with align_corners=True, output index o reads low-res indices i0(o), i1(o) that always lie in
+// {j, j + 1} with j = floor((o - 1) / 2) (checked exhaustively in float arithmetic for every size up to 1024), so
+// output rows 2i+1 and 2i+2 interpolate between the same two source rows i and i+1.  weight_of(o, i) is the weight of
+// low-res index i in output o under ATen's formula.
+__device__ __forceinline__ float weight_of(int o, int i, float scale, int in_size, int out_size) {
+  if (o < 0 || o >= out_size) return 0.f;
+  int i0, i1; float lam;
+  src_index(o, scale, in_size, i0, i1, lam);
+  return (i0 == i ? 1.f - lam : 0.f) + (i1 == i ? lam : 0.f);
+}
+
+constexpr int kUpRows = 8;      // low-res rows per strip
+
+// Forward: thread = (output column, 8-channel chunk), strip of kUpRows source intervals = 2 kUpRows output rows.
+// Each source row is loaded once per strip (two 16-byte loads, the next row requested before the current one is used),
+// interpolated horizontally once, and used by the four output rows around it.
+__global__ void __launch_bounds__(128)
+upsample2x_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W, int C8, float sh, float sw) {
   const int Ho = 2 * H, Wo = 2 * W;
-  const unsigned t = blockIdx.y * blockDim.x + threadIdx.x;
+  const unsigned t = blockIdx.x * 128u + threadIdx.x;
   if (t >= static_cast<unsigned>(Wo) * C8) return;
   const int wo = t / C8, c = t - wo * C8;
-  const int rows_per_img = Ho / ROWS;
-  const int n = blockIdx.x / rows_per_img, ho0 = (blockIdx.x - n * rows_per_img) * ROWS;
+  const int i_begin = blockIdx.y * kUpRows, n = blockIdx.z;     // source intervals [i_begin, i_begin + kUpRows)
   int w0, w1; float lw;
   src_index(wo, sw, W, w0, w1, lw);
   const float w0l = 1.f - lw;
   const uint4* img = x + static_cast<size_t>(n) * H * W * C8 + c;
-  auto load_row = [&](int h, float* v) {
-    float a[8], b[8];
-    unpack8(__ldg(img + (static_cast<size_t>(h) * W + w0) * C8), a);
-    unpack8(__ldg(img + (static_cast<size_t>(h) * W + w1) * C8), b);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = w0l * a[k] + lw * b[k];
+  uint4* out = y + static_cast<size_t>(n) * Ho * Wo * C8 + t;
+  auto fetch = [&](int h, uint4& a, uint4& b) {
+    const int hc = h < H ? h : H - 1;        // rows past the end carry zero weight
+    a = __ldg(img + (static_cast<size_t>(hc) * W + w0) * C8);
+    b = __ldg(img + (static_cast<size_t>(hc) * W + w1) * C8);
   };
-  int cur0 = -1, cur1 = -1;
-  float v0[8], v1[8], o[8];
-  uint4* out = y + (static_cast<size_t>(n) * Ho + ho0) * Wo * C8 + t;
+  auto hlerp = [&](const uint4& a, const uint4& b, float* v) {
+    float fa[8], fb[8];
+    unpack8(a, fa); unpack8(b, fb);
 #pragma unroll
-  for (int r = 0; r < ROWS; ++r) {
-    int h0, h1; float lh;
-    src_index(ho0 + r, sh, H, h0, h1, lh);
-    if (h0 != cur0) {
-      if (h0 == cur1) {
+    for (int k = 0; k < 8; ++k) v[k] = w0l * fa[k] + lw * fb[k];
+  };
+  auto emit = [&](int o, int i, const float* va, const float* vb) {     // output row o from source rows i, i+1
+    if (o >= Ho) return;
+    const float wa = weight_of(o, i, sh, H, Ho), wb = weight_of(o, i + 1, sh, H, Ho);
+    float v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v0[k] = v1[k];
-      } else {
-        load_row(h0, v0);
-      }
-      cur0 = h0;
-    }
-    if (h1 != cur1) {
-      if (h1 == cur0) {
+    for (int k = 0; k < 8; ++k) v[k] = fmaf(wb, vb[k], wa * va[k]);
+    out[static_cast<size_t>(o) * Wo * C8] = pack8(v);
+  };
+  uint4 na, nb;
+  fetch(i_begin, na, nb);
+  float va[8], vb[8];
+  hlerp(na, nb, va);
+  if (i_begin == 0) emit(0, -1, va, va);       // output row 0 reads source row 0 only (weight_of(0, -1) = 0)
+  fetch(i_begin + 1, na, nb);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v1[k] = v0[k];
-      } else {
-        load_row(h1, v1);
-      }
-      cur1 = h1;
-    }
-    const float h0l = 1.f - lh;
+  for (int r = 0; r < kUpRows; ++r) {
+    const int i = i_begin + r;
+    if (i >= H) break;
+    const uint4 ca = na, cb = nb;
+    if (r + 1 < kUpRows) fetch(i + 2, na, nb);
+    hlerp(ca, cb, vb);
+    emit(2 * i + 1, i, va, vb);
+    emit(2 * i + 2, i, va, vb);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = h0l * v0[k] + lh * v1[k];
-    out[static_cast<size_t>(r) * Wo * C8] = pack8(o);
+    for (int k = 0; k < 8; ++k) va[k] = vb[k];
   }
 }
 
-// Adjoint of the 2x bilinear upsample in gather form.  Output index o feeds low-res indices i0(o) and i1(o) with
-// weights (1 - lam, lam); for scale 2 a low-res index i receives from at most kUpCand consecutive outputs starting at
-// first_candidate(i) (checked exhaustively for every size up to 1024 against the forward index formula).
-constexpr int kUpCand = 5;
-__device__ __forceinline__ int first_candidate(int i, float inv_scale) {
-  if (i <= 0) return 0;
-  const int lo = static_cast<int>(floorf((i - 1) * inv_scale)) + 1;
-  return lo < 0 ? 0 : lo;
+// Backward (adjoint, gather form): thread = (low-res column, 8-channel chunk), strip of kUpRows low-res rows.  The
+// 2 kUpRows + 2 output rows feeding the strip are streamed once through a cp.async pipeline (four column candidates
+// 2w-1 .. 2w+2 per row into thread-private shared-memory slots, kUpStages rows deep, zero-filled outside the image);
+// each row is combined with the four column weights and added to the two low-res rows it feeds.
+constexpr int kUpStages = 4;
+
+__device__ __forceinline__ void up_cp_async16(uint32_t dst, const void* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
 }
-// Each thread owns one (low-res column, 8-channel chunk) and ROWS consecutive low-res rows.  It walks the output rows
-// that feed them once: per output row the kUpCand column candidates are combined with the column weights (shared by
-// all rows), then the row result is added to the two low-res rows it feeds -- so an output row is loaded once for the
-// whole group instead of once per low-res row.
-template <int ROWS>
-__global__ void upsample2x_bwd_kernel(const uint4* __restrict__ dup, const uint4* __restrict__ ylow,
-                                      uint4* __restrict__ dlow, int N, int H, int W, int C8, float sh, float sw,
-                                      float inv_sh, float inv_sw) {
+
+__global__ void __launch_bounds__(128, 3)
+upsample2x_bwd_kernel(const uint4* __restrict__ dup, const uint4* __restrict__ ylow, uint4* __restrict__ dlow, int H, int W,
+                      int C8, float sh, float sw) {
+  __shared__ uint4 slots[kUpStages][4][128];
   const int Ho = 2 * H, Wo = 2 * W;
-  const unsigned t = blockIdx.y * blockDim.x + threadIdx.x;
-  if (t >= static_cast<unsigned>(W) * C8) return;
+  const unsigned t = blockIdx.x * 128u + threadIdx.x;
+  if (t >= static_cast<unsigned>(W) * C8) return;     // no block-level barrier below
   const int w = t / C8, c = t - w * C8;
-  const int groups = H / ROWS;
-  const int n = blockIdx.x / groups, hb = (blockIdx.x - n * groups) * ROWS;
-  // column weights
-  const int wo_lo = first_candidate(w, inv_sw);
-  float ww[kUpCand];
-  int wcol[kUpCand];
+  const int hb = blockIdx.y * kUpRows, n = blockIdx.z;
+  float cw[4];
 #pragma unroll
-  for (int b = 0; b < kUpCand; ++b) {
-    const int o = wo_lo + b;
-    int i0, i1; float lam;
-    src_index(o, sw, W, i0, i1, lam);
-    float wt = 0.f;
-    if (o < Wo) { if (i0 == w) wt += 1.f - lam; if (i1 == w) wt += lam; }
-    ww[b] = wt;
-    wcol[b] = o < Wo ? o : Wo - 1;
+  for (int b = 0; b < 4; ++b) cw[b] = weight_of(2 * w - 1 + b, w, sw, W, Wo);
+  const uint4* img = dup + static_cast<size_t>(n) * Ho * Wo * C8 + c;
+  constexpr int kRowsIn = 2 * kUpRows + 2;
+  auto fetch_row = [&](int k) {          // strip-relative output row k -> o = 2 hb - 1 + k
+    const int o = 2 * hb - 1 + k;
+    const bool rok = o >= 0 && o < Ho;
+    const uint4* row = img + static_cast<size_t>(rok ? o : 0) * Wo * C8;
+    const int st = k % kUpStages;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int p = 2 * w - 1 + b;
+      const bool ok = rok && p >= 0 && p < Wo;
+      up_cp_async16(smem_u32(&slots[st][b][threadIdx.x]), row + static_cast<size_t>(ok ? p : 0) * C8, ok);
+    }
+  };
+#pragma unroll
+  for (int k = 0; k < kUpStages - 1; ++k) {
+    fetch_row(k);
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  float acc[ROWS][8];
+  float acc[kUpRows][8];
 #pragma unroll
-  for (int r = 0; r < ROWS; ++r)
+  for (int r = 0; r < kUpRows; ++r)
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[r][k] = 0.f;
-  const int ho_begin = first_candidate(hb, inv_sh);
-  int ho_end = first_candidate(hb + ROWS - 1, inv_sh) + kUpCand;
-  if (ho_end > Ho) ho_end = Ho;
-  const uint4* img = dup + static_cast<size_t>(n) * Ho * Wo * C8 + c;
-  for (int ho = ho_begin; ho < ho_end; ++ho) {
-    int h0, h1; float lh;
-    src_index(ho, sh, H, h0, h1, lh);
-    const uint4* rowp = img + static_cast<size_t>(ho) * Wo * C8;
+#pragma unroll
+  for (int k = 0; k < kRowsIn; ++k) {
+    if (k + kUpStages - 1 < kRowsIn) fetch_row(k + kUpStages - 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group %0;" ::"n"(kUpStages - 1) : "memory");
+    const int st = k % kUpStages;
     float trow[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-    for (int b = 0; b < kUpCand; ++b) {
+    for (int b = 0; b < 4; ++b) {
       float g[8];
-      unpack8(__ldg(rowp + static_cast<size_t>(wcol[b]) * C8), g);
+      unpack8(slots[st][b][threadIdx.x], g);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) trow[k] = fmaf(ww[b], g[k], trow[k]);
+      for (int e = 0; e < 8; ++e) trow[e] = fmaf(cw[b], g[e], trow[e]);
     }
+    const int o = 2 * hb - 1 + k;          // feeds low-res rows hb - 1 + k/2 and hb + k/2
+    const int ra = k / 2 - 1, rb = k / 2;  // strip-relative accumulator indices (compile-time after unrolling)
+    if (ra >= 0) {
+      const float wa = weight_of(o, hb + ra, sh, H, Ho);
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-      float wt = 0.f;
-      if (h0 == hb + r) wt += 1.f - lh;
-      if (h1 == hb + r) wt += lh;
+      for (int e = 0; e < 8; ++e) acc[ra < 0 ? 0 : ra][e] = fmaf(wa, trow[e], acc[ra < 0 ? 0 : ra][e]);
+    }
+    if (rb < kUpRows) {
+      const float wb = weight_of(o, hb + rb, sh, H, Ho);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[r][k] = fmaf(wt, trow[k], acc[r][k]);
+      for (int e = 0; e < 8; ++e) acc[rb < kUpRows ? rb : 0][e] = fmaf(wb, trow[e], acc[rb < kUpRows ? rb : 0][e]);
     }
   }
 #pragma unroll
-  for (int r = 0; r < ROWS; ++r) {
+  for (int r = 0; r < kUpRows; ++r) {
+    if (hb + r >= H) break;
     const size_t idx = (static_cast<size_t>(n) * H + hb + r) * W * C8 + t;
     if (ylow) {
       float m[8];
       unpack8(__ldg(ylow + idx), m);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) if (!(m[k] > 0.f)) acc[r][k] = 0.f;
+      for (int e = 0; e < 8; ++e) if (!(m[e] > 0.f)) acc[r][e] = 0.f;
     }
     dlow[idx] = pack8(acc[r]);
   }
@@ -566,14 +584,12 @@ int b2u_maxpool2x2_bwd(const void* dpool, const void* dskip, const void* y, void
 // H, W: dims of the low-resolution input; output is [N,2H,2W,C]
 int b2u_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream) {
   if (N <= 0 || H <= 0 || W <= 0 || C % 8 != 0) return set_error(B2U_ERR_SHAPE, "upsample2x_fwd: bad shape");
+  if (N > 65535 || (H + kUpRows - 1) / kUpRows > 65535) return set_error(B2U_ERR_SHAPE, "upsample2x_fwd: N or H too large");
   const float sh = (2 * H > 1) ? static_cast<float>(H - 1) / static_cast<float>(2 * H - 1) : 0.f;
   const float sw = (2 * W > 1) ? static_cast<float>(W - 1) / static_cast<float>(2 * W - 1) : 0.f;
-  if (H % 2 == 0)
-    upsample2x_fwd_kernel<4><<<row_grid(static_cast<long long>(N) * (2 * H / 4), 2 * W * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const uint4*>(x), static_cast<uint4*>(y), N, H, W, C / 8, sh, sw);
-  else
-    upsample2x_fwd_kernel<2><<<row_grid(static_cast<long long>(N) * H, 2 * W * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const uint4*>(x), static_cast<uint4*>(y), N, H, W, C / 8, sh, sw);
+  const dim3 grid((2u * W * (C / 8) + 127) / 128, (H + kUpRows - 1) / kUpRows, N);
+  upsample2x_fwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y),
+                                                                             H, W, C / 8, sh, sw);
   B2U_CHECK_LAUNCH("upsample2x_fwd");
   return 0;
 }
@@ -581,19 +597,12 @@ int b2u_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, void*
 // dup: [N,2H,2W,C]; ylow (nullable): ReLU output that was upsampled, dlow is zeroed where ylow <= 0
 int b2u_upsample2x_bwd(const void* dup, const void* ylow, void* dlow, int N, int H, int W, int C, void* stream) {
   if (N <= 0 || H <= 0 || W <= 0 || C % 8 != 0) return set_error(B2U_ERR_SHAPE, "upsample2x_bwd: bad shape");
+  if (N > 65535 || (H + kUpRows - 1) / kUpRows > 65535) return set_error(B2U_ERR_SHAPE, "upsample2x_bwd: N or H too large");
   const float sh = static_cast<float>(H - 1) / static_cast<float>(2 * H - 1);
   const float sw = static_cast<float>(W - 1) / static_cast<float>(2 * W - 1);
-  const float ish = H > 1 ? 1.f / sh : 4.f * H;   // H == 1: every output maps to row 0
-  const float isw = W > 1 ? 1.f / sw : 4.f * W;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const uint4 *pd = static_cast<const uint4*>(dup), *py = static_cast<const uint4*>(ylow);
-  uint4* po = static_cast<uint4*>(dlow);
-  if (H % 4 == 0)
-    upsample2x_bwd_kernel<4><<<row_grid(static_cast<long long>(N) * (H / 4), W * (C / 8), 128), 128, 0, st>>>(pd, py, po, N, H, W, C / 8, sh, sw, ish, isw);
-  else if (H % 2 == 0)
-    upsample2x_bwd_kernel<2><<<row_grid(static_cast<long long>(N) * (H / 2), W * (C / 8), 128), 128, 0, st>>>(pd, py, po, N, H, W, C / 8, sh, sw, ish, isw);
-  else
-    upsample2x_bwd_kernel<1><<<row_grid(static_cast<long long>(N) * H, W * (C / 8), 128), 128, 0, st>>>(pd, py, po, N, H, W, C / 8, sh, sw, ish, isw);
+  const dim3 grid((static_cast<unsigned>(W) * (C / 8) + 127) / 128, (H + kUpRows - 1) / kUpRows, N);
+  upsample2x_bwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(dup), static_cast<const uint4*>(ylow), static_cast<uint4*>(dlow), H, W, C / 8, sh, sw);
   B2U_CHECK_LAUNCH("upsample2x_bwd");
   return 0;
 }

@@ -393,7 +393,7 @@ class UNetEngine:
                 return dz
             wn, bn_ = c.name + ".weight", c.name + ".bias"
             want_w, want_b = has(wn), has(bn_)
-            fuse_b = want_w and want_b and self.fuse_bias_grad and not c.padded
+            fuse_b = want_w and want_b and self.fuse_bias_grad and not c.padded and not c.bn
             taps = 1 if c.first else 9
             if want_w:
                 ctot_p = 64 if c.first else c.c0_p + c.c1_p
@@ -415,7 +415,11 @@ class UNetEngine:
                             grads[wn][:, c.c0:].copy_(tmp[:c.cout, c.c0_p:c.c0_p + c.c1])
                         else:
                             grads[wn].copy_(tmp[:c.cout, :c.c0])
-            if want_b and not fuse_b:
+            if want_b and c.bn:
+                # a bias in front of BatchNorm: dz = a (g - mean(g) - xhat mean(g xhat)) sums to zero over the batch
+                # exactly, so the gradient is 0 (the reference's autograd returns fp32 cancellation residue ~1e-8)
+                grads[bn_].zero_()
+            elif want_b and not fuse_b:
                 if c.cout_p == c.cout:
                     ops.bias_grad(dz, db=grads[bn_], ws=self._workspace("bias", ops.lib().b2u_bias_grad_workspace(c.cout_p)))
                 else:

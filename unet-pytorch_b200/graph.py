@@ -168,6 +168,12 @@ class GraphEngine:
         self.saved = None
         self.has_stem = any(i["op"] == "stem" for i in program)
         self.dropout_override = None
+        readers = {}
+        for i in program:
+            for key in ("x", "x1", "z", "res"):
+                if i.get(key):
+                    readers.setdefault(i[key], []).append(i["op"] if key == "z" else "other")
+        self._pre_bn = {name for name, ops_ in readers.items() if ops_ == ["bn"]}      # tensors read only as a BN input
 
     # ------------------------------------------------------------------ static description
     def param_shapes(self):
@@ -506,9 +512,10 @@ class GraphEngine:
                 t, xin = T[ins["out"]], T[ins["x"]]
                 if t.grad is None or not xin.needs_grad:
                     continue
-                g = ops.maxpool2x2_bwd(t.grad, xin.data, dskip=None, relu_mask=xin.fused_relu,
+                # the gradient already accumulated at the pooled tensor (its skip consumer) is added in the same pass
+                g = ops.maxpool2x2_bwd(t.grad, xin.data, dskip=xin.grad, relu_mask=xin.fused_relu,
                                        out=self._buf("g:" + ins["out"] + ">", xin.data.shape))
-                self._acc(xin, g)
+                xin.grad = g
             elif op == "drop":
                 t, xin = T[ins["out"]], T[ins["x"]]
                 if t.grad is None or not xin.needs_grad:
@@ -607,7 +614,11 @@ class GraphEngine:
                         gw[:, :c0r].copy_(tmp[:cout, :c0r])
                         if c1r:
                             gw[:, c0r:].copy_(tmp[:cout, c0p:c0p + c1r])
-                if has(ins["bias"]):
+                if has(ins["bias"]) and ins["out"] in self._pre_bn:
+                    # a bias in front of BatchNorm: the BN backward's dz sums to zero over the batch exactly, so the
+                    # gradient is 0 (the reference's autograd returns fp32 cancellation residue ~1e-8)
+                    grads[ins["bias"]].zero_()
+                elif has(ins["bias"]):
                     wsb = self._workspace("bias", ops.lib().b2u_bias_grad_workspace(coutp))
                     if coutp == cout:
                         ops.bias_grad(dz, db=grads[ins["bias"]], ws=wsb)
