@@ -119,6 +119,15 @@ int b2u_maxpool3x3s2_fwd(const void* x, void* y, int N, int H, int W, int C, voi
 int b2u_maxpool3x3s2_bwd(const void* dy, const void* x, void* dx, int N, int H, int W, int C, void* stream);
 /* out = a + b over n bf16 elements (gradient accumulation at tensors with two consumers) */
 int b2u_add_bf16(const void* a, const void* b, void* out, long long n, void* stream);
+/* out = relu(a + b): the residual join `x += residual; relu(x)` of ResidualBlock (nets/LightWeightUnet.py:52-53);
+ * dx = dy * (y > 0): its gradient towards both inputs */
+int b2u_add_relu_bf16(const void* a, const void* b, void* out, long long n, void* stream);
+int b2u_relu_bwd_bf16(const void* dy, const void* y, void* dx, long long n, void* stream);
+/* F.interpolate(x, size=(Ho, Wo), mode="bilinear", align_corners=True) on fp32 NCHW maps and its adjoint: the resize the
+ * losses / f_score apply to logits smaller than the labels (nets/unet_training.py:12-13, 24-25, 41-42;
+ * utils/utils_metrics.py:15-16).  x: [NC][Hi][Wi], y: [NC][Ho][Wo] */
+int b2u_resize_bilinear_f32_fwd(const float* x, float* y, long long NC, int Hi, int Wi, int Ho, int Wo, void* stream);
+int b2u_resize_bilinear_f32_bwd(const float* dy, float* dx, long long NC, int Hi, int Wi, int Ho, int Wo, void* stream);
 
 /* ---- depthwise conv, squeeze-excite, per-(image,channel) scaling (Lightweight / UltraLightweight UNets) ---------- */
 /* nn.Conv2d(C, C, 3, padding=1, groups=C) (nets/UltraLightweightUnet_large.py:9-10): w fp32 [C][9]; flip=1 uses the

@@ -21,6 +21,7 @@ from nets.TraditionalUnet import TraditionalUnet as RefTraditional      # noqa: 
 from nets.UltraLightweightUnet import UltraLightweightUnet as RefULU                           # noqa: E402
 from nets.UltraLightweightUnet_large import UltraLightweightUnet_large as RefULULarge         # noqa: E402
 from nets.UltraLightweightUnet_large_optimized import UltraLightweightUnet_large_optimized as RefULUOpt   # noqa: E402
+from nets.LightWeightUnet import LightweightUnet as RefLightweight                            # noqa: E402
 from nets.unet_training import CE_Loss, Dice_loss, Focal_Loss           # noqa: E402
 from utils.utils_metrics import f_score, fast_hist, per_class_iu, per_class_PA_Recall, per_class_Precision  # noqa: E402
 
@@ -176,6 +177,82 @@ def ulu_case(variant, tag, num_classes, n, h, w, seed, cls_w, dice, focal):
     print(variant, tag, "loss", loss.item(), "dropmask" if "drop_mask" in rec else "")
 
 
+def lightweight_case(tag, num_classes, n, h, w, seed, cls_w, dice, focal):
+    """LightweightUnet in train mode: logits at H/2 x W/2 (the reference's losses resize them); the ten Dropout2d draws
+    are recorded by forward hooks in call order and replayed by the CUDA path."""
+    sd = O.make_lw_params(num_classes, seed=11)
+    model = RefLightweight(num_classes=num_classes)
+    model.load_state_dict(sd)
+    model.train()
+    imgs, pngs = O.make_inputs(n, num_classes, h, w, seed=seed)
+    labels = torch.eye(num_classes + 1)[pngs]
+    weights = torch.tensor(cls_w, dtype=torch.float32)
+    masks = {}
+    counters = {"backbone": 0}
+
+    def make_hook(site_fn):
+        def hook(mod, inp, out):
+            x = inp[0].detach()
+            amax = x.abs().amax(dim=(2, 3))
+            ratio = out.detach().abs().amax(dim=(2, 3)) / amax.clamp_min(1e-30)
+            keep = 1.0 - mod.p
+            masks[site_fn()] = torch.where(amax > 0, (ratio > 0.5).float() / keep, torch.full_like(ratio, 1.0 / keep))
+        return hook
+
+    def backbone_site():
+        counters["backbone"] += 1
+        return f"feat{counters['backbone']}"
+    hooks = [model.backbone.dropout.register_forward_hook(make_hook(backbone_site)),
+             model.final_conv[1].register_forward_hook(make_hook(lambda: "final_conv.1"))]
+    for k in (4, 3, 2, 1):
+        hooks.append(getattr(model, f"up_concat{k}").dropout.register_forward_hook(make_hook(lambda k=k: f"up_concat{k}.drop")))
+    torch.manual_seed(seed)
+    out = model(imgs)
+    for hnd in hooks:
+        hnd.remove()
+    assert len(masks) == 10
+    loss = Focal_Loss(out, pngs, weights, num_classes=num_classes) if focal else CE_Loss(out, pngs, weights, num_classes=num_classes)
+    if dice:
+        loss = loss + Dice_loss(out, labels)
+    with torch.no_grad():
+        fs = f_score(out, labels).item()
+    loss.backward()
+    rec = {"logits": out.detach().numpy().astype(np.float32), "loss": np.float64(loss.item()), "f_score": np.float64(fs),
+           "cls_w": np.asarray(cls_w, np.float32), "meta": np.asarray([num_classes, n, h, w, seed, int(dice), int(focal)])}
+    for site, m in masks.items():
+        rec["drop:" + site] = m.numpy().astype(np.float32)
+    for name, p in model.named_parameters():
+        g = p.grad.detach().reshape(-1)
+        rec["gnorm:" + name] = np.float64(g.double().norm().item())
+        rec["g:" + name] = (g if g.numel() <= 1024 else g[torch.linspace(0, g.numel() - 1, 1024).long()]).numpy().astype(np.float32)
+    for name, b in model.named_buffers():
+        if name.endswith("bn2.running_mean") or name.endswith("bn2.running_var"):
+            rec["buf:" + name] = b.detach().numpy()
+    model.eval()
+    with torch.no_grad():
+        rec["logits_eval"] = model(imgs).numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, f"lightweight_{tag}.npz"), **rec)
+    print("lightweight", tag, "loss", loss.item(), "f_score", fs)
+
+
+def checkpoint_case():
+    """The reference's own trained checkpoint (Submit_result/model.pth = UltraLightweightUnet_large_optimized, 4 classes,
+    all keys match) in eval mode on a seeded input: trained BatchNorm statistics make this a well-conditioned fixture
+    (the bf16-storage model sits at 1.1e-2 of fp32).  The weights travel with the fixture (3.7 MB fp32)."""
+    sd = torch.load("/root/reference/Submit_result/model.pth", map_location="cpu")
+    model = RefULUOpt(num_classes=4)
+    model.load_state_dict(sd)
+    model.eval()
+    imgs, _ = O.make_inputs(2, 4, 128, 128, seed=5)
+    with torch.no_grad():
+        out = model(imgs)
+    rec = {"logits": out.numpy().astype(np.float32), "meta": np.asarray([4, 2, 128, 128, 5])}
+    for k, v in sd.items():
+        rec["sd:" + k] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, "ultralight_large_optimized_checkpoint_eval.npz"), **rec)
+    print("checkpoint eval fixture ok", out.abs().max().item())
+
+
 def loss_case():
     g = torch.Generator().manual_seed(7)
     rec = {}
@@ -238,5 +315,9 @@ if __name__ == "__main__":
     ulu_case("ultralight", "nc21_cedice", 21, 2, 64, 64, 8, [1] * 21, dice=True, focal=False)
     ulu_case("ultralight_large", "nc4_focaldice", 4, 2, 64, 64, 9, [1, 15, 1.5, 2], dice=True, focal=True)
     ulu_case("ultralight_large_optimized", "nc21_cedice", 21, 2, 32, 64, 10, [1] * 21, dice=True, focal=False)
+    # LightweightUnet_Train.py-style settings (focal + dice with class weights) and plain CE + Dice
+    lightweight_case("nc4_focaldice", 4, 2, 64, 64, 12, [1, 15, 1.5, 2], dice=True, focal=True)
+    lightweight_case("nc21_cedice", 21, 2, 64, 96, 13, [1] * 21, dice=True, focal=False)
+    checkpoint_case()
     loss_case()
     hist_case()

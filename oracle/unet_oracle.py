@@ -661,3 +661,152 @@ def ulu_train_step(sd, imgs, pngs, cls_weights, num_classes, variant, dice=True,
     names = [k for k, v in p.items() if v.requires_grad]
     grads = torch.autograd.grad(loss, [p[k] for k in names])
     return loss.detach(), logits.detach(), dict(zip(names, grads)), stats
+
+
+# ----------------------------------------------------------------------------------------------- LightweightUnet
+LW_WIDTHS = (24, 48, 96, 192, 384)                     # nets/LightWeightUnet.py:62-90
+
+
+def resize_logits(logits, ht, wt):
+    """The losses' `if h != ht and w != wt: F.interpolate(..., align_corners=True)` (nets/unet_training.py:12-13, 24-25, 41-42)."""
+    if logits.shape[2] != ht and logits.shape[3] != wt:
+        return F.interpolate(logits, size=(ht, wt), mode="bilinear", align_corners=True)
+    return logits
+
+
+def lw_param_shapes(num_classes, in_channels=3):
+    sh = {}
+
+    def conv_block(p, cin, cout):
+        sh[p + ".conv.0.weight"] = (cout, cin, 3, 3); sh[p + ".conv.0.bias"] = (cout,)
+        sh[p + ".conv.1.weight"] = (cout,); sh[p + ".conv.1.bias"] = (cout,)
+
+    def res_block(p, c):
+        for i in ("1", "2"):
+            sh[f"{p}.conv{i}.weight"] = (c, c, 3, 3); sh[f"{p}.conv{i}.bias"] = (c,)
+            sh[f"{p}.bn{i}.weight"] = (c,); sh[f"{p}.bn{i}.bias"] = (c,)
+        # registration order in the reference: conv1, bn1, conv2, bn2, se
+        sh[p + ".se.fc.0.weight"] = (c // 4, c); sh[p + ".se.fc.0.bias"] = (c // 4,)
+        sh[p + ".se.fc.2.weight"] = (c, c // 4); sh[p + ".se.fc.2.bias"] = (c,)
+
+    cin = in_channels
+    for k, w in enumerate(LW_WIDTHS, start=1):
+        conv_block(f"backbone.stage{k}.0", cin, w); res_block(f"backbone.stage{k}.1", w); cin = w
+    for k, (cin, cout) in zip((4, 3, 2, 1), ((576, 192), (288, 96), (144, 48), (72, 24))):
+        conv_block(f"up_concat{k}.conv.0", cin, cout); res_block(f"up_concat{k}.conv.1", cout)
+    conv_block("final_conv.0", 24, 24); res_block("final_conv.2", 24)
+    sh["final_conv.3.weight"] = (num_classes, 24, 1, 1); sh["final_conv.3.bias"] = (num_classes,)
+    # state_dict order inside a ResidualBlock is conv1, bn1, conv2, bn2 (weights and biases interleaved per module)
+    ordered = {}
+    for name in sh:
+        ordered[name] = sh[name]
+    return _lw_reorder(ordered)
+
+
+def _lw_reorder(sh):
+    """conv1.{w,b}, bn1.{w,b}, conv2.{w,b}, bn2.{w,b}, se.* -- the per-module order nn.Module.state_dict() yields."""
+    out, done = {}, set()
+    names = list(sh)
+    for n in names:
+        if n in done:
+            continue
+        if ".conv1.weight" in n:
+            p = n[:-len(".conv1.weight")]
+            for k in ("conv1.weight", "conv1.bias", "bn1.weight", "bn1.bias", "conv2.weight", "conv2.bias", "bn2.weight", "bn2.bias",
+                      "se.fc.0.weight", "se.fc.0.bias", "se.fc.2.weight", "se.fc.2.bias"):
+                out[p + "." + k] = sh[p + "." + k]; done.add(p + "." + k)
+        else:
+            out[n] = sh[n]; done.add(n)
+    return out
+
+
+def make_lw_params(num_classes, seed=11):
+    """Deterministic synthetic state_dict: He-scaled 3x3 convs (a BatchNorm follows each), BN weight 1 + 0.1 N and bias
+    0.5 + 0.05 N (0.05 N for bn2, whose output feeds the residual sum), conv biases 0.05 N, SE linears at 1/sqrt(fan_in),
+    head at half the He scale, fresh running statistics."""
+    sd = {}
+    for k, (name, shape) in enumerate(lw_param_shapes(num_classes).items()):
+        g = torch.Generator().manual_seed(seed * 1000 + 7000 + k)
+        base_ = name.rsplit(".", 1)[0]
+        is_bn = base_.endswith(".conv.1") or base_.endswith(".bn1") or base_.endswith(".bn2")
+        if len(shape) == 4:
+            fan_in = shape[1] * shape[2] * shape[3]
+            sd[name] = torch.randn(shape, generator=g) * ((0.5 if name.startswith("final_conv.3") else 1.0) * (2.0 / fan_in) ** 0.5)
+        elif len(shape) == 2:
+            sd[name] = torch.randn(shape, generator=g) * (1.0 / shape[1]) ** 0.5
+        elif is_bn and name.endswith(".weight"):
+            sd[name] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif is_bn:
+            sd[name] = (0.0 if ".bn2." in name else 0.5) + 0.05 * torch.randn(shape, generator=g)
+        else:
+            sd[name] = 0.05 * torch.randn(shape, generator=g)
+        if is_bn and name.endswith(".bias"):
+            base = name[:-len(".bias")]
+            sd[base + ".running_mean"] = torch.zeros(shape)
+            sd[base + ".running_var"] = torch.ones(shape)
+            sd[base + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+    return sd
+
+
+def _lw_conv_block(sd, stats, p, x, training, b):
+    z = _rn_conv(sd, p + ".conv.0.weight", x, padding=1, bias=sd[p + ".conv.0.bias"], bf16=b)
+    return _rn_bn(sd, stats, p + ".conv.1", z, training, True, bf16=b)
+
+
+def _lw_res_block(sd, stats, p, x, training, b):
+    """ResidualBlock.forward (nets/LightWeightUnet.py:45-55)."""
+    y = _rn_bn(sd, stats, p + ".bn1", _rn_conv(sd, p + ".conv1.weight", x, padding=1, bias=sd[p + ".conv1.bias"], bf16=b), training, True, bf16=b)
+    y = _rn_bn(sd, stats, p + ".bn2", _rn_conv(sd, p + ".conv2.weight", y, padding=1, bias=sd[p + ".conv2.bias"], bf16=b), training, False, bf16=b)
+    y = _ulu_se(sd, p + ".se", y, b)
+    y = F.relu(y + x)
+    return _r(y) if b else y
+
+
+def lw_forward(sd, x, training=True, stats=None, bf16_storage=False, drop_masks=None):
+    """LightweightUnet.forward (nets/LightWeightUnet.py:160-169, 92-110, 117-122).  drop_masks: {site: [N, C] multiplier} for
+    the ten Dropout2d sites (feat1..5, up_concat4..1.drop, final_conv.1) in training; missing sites = no dropout."""
+    b = bf16_storage
+    drop_masks = drop_masks or {}
+    if stats is None:
+        stats = {k: v.clone() for k, v in sd.items() if "running_" in k or "num_batches" in k}
+
+    def drop(site, t):
+        m = drop_masks.get(site) if training else None
+        if m is None:
+            return t
+        t = t * m[:, :, None, None]
+        return _r(t) if b else t
+
+    if b:
+        x = _r(x)
+    feats = []
+    for k in range(1, 6):
+        x = _lw_conv_block(sd, stats, f"backbone.stage{k}.0", x, training, b)
+        x = _lw_res_block(sd, stats, f"backbone.stage{k}.1", x, training, b)
+        x = drop(f"feat{k}", F.max_pool2d(x, 2, 2))
+        feats.append(x)
+    low = feats[4]
+    for k in (4, 3, 2, 1):
+        up = F.interpolate(low, scale_factor=2, mode="bilinear", align_corners=True)
+        if b:
+            up = _r(up)
+        y = _lw_conv_block(sd, stats, f"up_concat{k}.conv.0", torch.cat([feats[k - 1], up], 1), training, b)
+        y = _lw_res_block(sd, stats, f"up_concat{k}.conv.1", y, training, b)
+        low = drop(f"up_concat{k}.drop", y)
+    y = _lw_conv_block(sd, stats, "final_conv.0", low, training, b)
+    y = drop("final_conv.1", y)
+    y = _lw_res_block(sd, stats, "final_conv.2", y, training, b)
+    return F.conv2d(y, sd["final_conv.3.weight"], sd["final_conv.3.bias"]), stats
+
+
+def lw_train_step(sd, imgs, pngs, cls_weights, num_classes, dice=True, focal=False, bf16_storage=False, drop_masks=None):
+    p = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and "running_" not in k else v.clone())
+         for k, v in sd.items()}
+    logits, stats = lw_forward(p, imgs, training=True, bf16_storage=bf16_storage, drop_masks=drop_masks)
+    full = resize_logits(logits, pngs.shape[1], pngs.shape[2])
+    loss = focal_loss(full, pngs, cls_weights, num_classes) if focal else ce_loss(full, pngs, cls_weights, num_classes)
+    if dice:
+        loss = loss + dice_loss(full, one_hot(pngs, num_classes))
+    names = [k for k, v in p.items() if v.requires_grad]
+    grads = torch.autograd.grad(loss, [p[k] for k in names])
+    return loss.detach(), logits.detach(), dict(zip(names, grads)), stats

@@ -509,3 +509,41 @@ def test_padded_input_conversion(b2u, cuda_device):
     y = ops.nchw_to_nhwc_bf16_padded(x.to(cuda_device), 64)
     assert tuple(y.shape) == (2, 16, 32, 64)
     assert torch.equal(y[..., :3].cpu(), x.permute(0, 2, 3, 1).to(BF)) and y[..., 3:].abs().max().item() == 0
+
+
+def test_residual_join_and_resize_kernels(b2u, cuda_device, golden_dir):
+    """relu(a + b) and its gradient mask; F.interpolate(bilinear, align_corners=True) of fp32 NCHW logits and its adjoint
+    (the losses' resize for half-resolution logits) against torch, including non-2x sizes."""
+    from unet_pytorch_b200 import ops
+    dev = cuda_device
+    g = torch.Generator().manual_seed(31)
+    a = torch.randn(2, 12, 20, 64, generator=g).to(BF); b = torch.randn(2, 12, 20, 64, generator=g).to(BF)
+    y = ops.add_relu(a.to(dev), b.to(dev))
+    assert torch.equal(y.cpu(), (a.float() + b.float()).relu().to(BF))
+    dy = torch.randn(2, 12, 20, 64, generator=g).to(BF)
+    dx = ops.relu_bwd(dy.to(dev), y)
+    assert torch.equal(dx.cpu(), torch.where(y.cpu().float() > 0, dy.float(), torch.zeros(())).to(BF))
+    for (hi, wi, ho, wo) in ((16, 24, 32, 48), (7, 5, 20, 11), (1, 1, 4, 4), (32, 32, 64, 64), (9, 9, 9, 17)):
+        x = torch.randn(2, 5, hi, wi, generator=g)
+        xr = x.clone().requires_grad_(True)
+        ref = F.interpolate(xr, size=(ho, wo), mode="bilinear", align_corners=True)
+        out = ops.resize_bilinear(x.to(dev), (ho, wo))
+        assert torch.allclose(out.cpu(), ref.detach(), rtol=1e-5, atol=1e-6), (hi, wi, ho, wo)
+        gy = torch.randn(2, 5, ho, wo, generator=g)
+        ref.backward(gy)
+        gx = ops.resize_bilinear_bwd(gy.to(dev), (hi, wi))
+        assert torch.allclose(gx.cpu(), xr.grad, rtol=1e-4, atol=1e-5), (hi, wi, ho, wo)
+    # the loss wrappers resize exactly like the reference's (golden values of CE/Dice/f_score on half-resolution logits)
+    gl = np.load(os.path.join(golden_dir, "lightweight_nc4_focaldice.npz"))
+    C, n, h, w, seed, dice, focal = [int(v) for v in gl["meta"]]
+    _, pngs = O.make_inputs(n, C, h, w, seed=seed)
+    lg = torch.from_numpy(gl["logits"]).to(dev).requires_grad_(True)
+    cw = torch.from_numpy(gl["cls_w"]).to(dev)
+    loss = b2u.Focal_Loss(lg, pngs.to(dev), cw, num_classes=C) + b2u.Dice_loss(lg, O.one_hot(pngs, C).to(dev))
+    assert abs(loss.item() - float(gl["loss"])) <= 1e-5 * abs(float(gl["loss"]))
+    assert abs(b2u.f_score(lg.detach(), O.one_hot(pngs, C).to(dev)).item() - float(gl["f_score"])) <= 1e-5
+    loss.backward()
+    lref = torch.from_numpy(gl["logits"]).requires_grad_(True)
+    full = O.resize_logits(lref, h, w)
+    (O.focal_loss(full, pngs, cw.cpu(), C) + O.dice_loss(full, O.one_hot(pngs, C))).backward()
+    assert rel(lg.grad, lref.grad) <= 1e-4

@@ -191,3 +191,61 @@ def test_ultralight_unet_matches_reference_golden(golden_dir, variant, tag):
         ev, _ = O.ulu_forward(sd_after, imgs, variant, training=False)
     ref_ev = torch.from_numpy(g["logits_eval"])
     assert ((ev - ref_ev).norm() / ref_ev.norm()).item() <= 1e-5
+
+
+def _load_checkpoint_fixture(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ultralight_large_optimized_checkpoint_eval.npz"))
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd:")}
+    C, n, h, w, seed = [int(v) for v in g["meta"]]
+    imgs, _ = O.make_inputs(n, C, h, w, seed=seed)
+    return sd, imgs, torch.from_numpy(g["logits"]), C
+
+
+def test_ultralight_trained_checkpoint_eval(golden_dir):
+    """The reference's shipped checkpoint (Submit_result/model.pth) through the restatement in eval mode."""
+    sd, imgs, ref, C = _load_checkpoint_fixture(golden_dir)
+    assert list(sd.keys()) == list(O.make_ulu_params(C, "ultralight_large_optimized").keys())
+    with torch.no_grad():
+        out, _ = O.ulu_forward(sd, imgs, "ultralight_large_optimized", training=False)
+    assert ((out - ref).norm() / ref.norm()).item() <= 1e-5
+
+
+def _lw_masks(g):
+    return {k[5:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("drop:")}
+
+
+@pytest.mark.parametrize("tag", ["nc4_focaldice", "nc21_cedice"])
+def test_lightweight_unet_matches_reference_golden(golden_dir, tag):
+    """LightweightUnet restatement (ConvBlock, SE ResidualBlock, ten Dropout2d sites replayed from the reference's own draws,
+    half-resolution logits resized inside the losses) against the reference's forward/backward."""
+    g = np.load(os.path.join(golden_dir, f"lightweight_{tag}.npz"))
+    C, n, h, w, seed, dice, focal = [int(v) for v in g["meta"]]
+    sd = O.make_lw_params(C, seed=11)
+    imgs, pngs = O.make_inputs(n, C, h, w, seed=seed)
+    loss, logits, grads, stats = O.lw_train_step(sd, imgs, pngs, torch.from_numpy(g["cls_w"]), C, dice=bool(dice), focal=bool(focal),
+                                                 drop_masks=_lw_masks(g))
+    ref = torch.from_numpy(g["logits"])
+    assert tuple(logits.shape) == (n, C, h // 2, w // 2)
+    assert ((logits - ref).norm() / ref.norm()).item() <= 1e-5
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    full = O.resize_logits(logits, h, w)
+    assert abs(O.f_score(full, O.one_hot(pngs, C)).item() - float(g["f_score"])) <= 1e-5
+    for name, gr in grads.items():
+        gn = float(g["gnorm:" + name])
+        base = name.rsplit(".", 1)[0]
+        if name.endswith(".bias") and (base.endswith(".conv.0") or base.endswith(".conv1") or base.endswith(".conv2")):
+            assert gr.abs().max().item() <= 1e-4 and gn <= 1e-3, name      # conv bias ahead of BatchNorm: zero gradient
+            continue
+        assert abs(gr.double().norm().item() - gn) <= 5e-4 * gn + 1e-9, name
+        flat = gr.reshape(-1)
+        samp = flat if flat.numel() <= 1024 else flat[torch.linspace(0, flat.numel() - 1, 1024).long()]
+        r = torch.from_numpy(g["g:" + name])
+        assert ((samp - r).norm() / r.norm().clamp_min(1e-12)).item() <= 2e-3, name
+    for key in g.files:
+        if key.startswith("buf:"):
+            assert torch.allclose(stats[key[4:]], torch.from_numpy(g[key]), rtol=1e-5, atol=1e-6), key
+    sd_after = dict(sd); sd_after.update(stats)
+    with torch.no_grad():
+        ev, _ = O.lw_forward(sd_after, imgs, training=False)
+    ref_ev = torch.from_numpy(g["logits_eval"])
+    assert ((ev - ref_ev).norm() / ref_ev.norm()).item() <= 1e-5

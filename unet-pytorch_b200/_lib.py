@@ -44,6 +44,10 @@ SIGNATURES = {
     "b2u_maxpool3x3s2_fwd": (I, [P, P, I, I, I, I, P]),
     "b2u_maxpool3x3s2_bwd": (I, [P, P, P, I, I, I, I, P]),
     "b2u_add_bf16": (I, [P, P, P, LL, P]),
+    "b2u_add_relu_bf16": (I, [P, P, P, LL, P]),
+    "b2u_relu_bwd_bf16": (I, [P, P, P, LL, P]),
+    "b2u_resize_bilinear_f32_fwd": (I, [P, P, LL, I, I, I, I, P]),
+    "b2u_resize_bilinear_f32_bwd": (I, [P, P, LL, I, I, I, I, P]),
     "b2u_dwconv3x3_fwd": (I, [P, P, P, P, I, I, I, I, I, P]),
     "b2u_dwconv3x3_wgrad_workspace": (SZ, [I]),
     "b2u_dwconv3x3_wgrad": (I, [P, P, P, P, P, SZ, I, I, I, I, P]),

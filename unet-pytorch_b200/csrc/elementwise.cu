@@ -403,6 +403,64 @@ upsample2x_bwd_kernel(const uint4* __restrict__ dup, const uint4* __restrict__ y
 }
 
 // ---------------------------------------------------------------------------------------------
+// General bilinear resize of fp32 NCHW maps, align_corners=True: the `F.interpolate(inputs, size=(ht, wt), ...)` the
+// reference's losses apply when the logits are smaller than the labels (nets/unet_training.py:12-13, 24-25, 41-42;
+// LightweightUnet emits logits at H/2 x W/2).  Forward: one thread per output element.  Backward: gather form, one
+// thread per input element over the (superset) range of outputs whose two source indices can include it; weights come
+// from weight_of(), i.e. the forward formula itself, so any range slack only adds zero terms.  Deterministic.
+// ---------------------------------------------------------------------------------------------
+__global__ void resize_bilinear_f32_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int Hi, int Wi, int Ho,
+                                               int Wo, float sh, float sw, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int wo = static_cast<int>(i % Wo);
+  const long long q = i / Wo;
+  const int ho = static_cast<int>(q % Ho);
+  const long long nc = q / Ho;
+  int h0, h1, w0, w1; float lh, lw;
+  src_index(ho, sh, Hi, h0, h1, lh);
+  src_index(wo, sw, Wi, w0, w1, lw);
+  const float* p = x + nc * Hi * Wi;
+  const float top = (1.f - lw) * __ldg(p + static_cast<size_t>(h0) * Wi + w0) + lw * __ldg(p + static_cast<size_t>(h0) * Wi + w1);
+  const float bot = (1.f - lw) * __ldg(p + static_cast<size_t>(h1) * Wi + w0) + lw * __ldg(p + static_cast<size_t>(h1) * Wi + w1);
+  y[i] = (1.f - lh) * top + lh * bot;
+}
+
+__device__ __forceinline__ void adjoint_range(int i, float inv_scale, int out_size, int& lo, int& hi) {
+  // outputs o with floor(scale * o) in {i - 1, i}: (i - 1) / scale <= o < (i + 1) / scale, widened by one on each side
+  lo = static_cast<int>(floorf((i - 1) * inv_scale)) - 1;
+  hi = static_cast<int>(ceilf((i + 1) * inv_scale)) + 1;
+  if (lo < 0) lo = 0;
+  if (hi > out_size - 1) hi = out_size - 1;
+}
+
+__global__ void resize_bilinear_f32_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int Hi, int Wi, int Ho,
+                                               int Wo, float sh, float sw, float ish, float isw, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int wi = static_cast<int>(i % Wi);
+  const long long q = i / Wi;
+  const int hi = static_cast<int>(q % Hi);
+  const long long nc = q / Hi;
+  int rlo, rhi, clo, chi;
+  if (Hi > 1) adjoint_range(hi, ish, Ho, rlo, rhi); else { rlo = 0; rhi = Ho - 1; }
+  if (Wi > 1) adjoint_range(wi, isw, Wo, clo, chi); else { clo = 0; chi = Wo - 1; }
+  const float* p = dy + nc * Ho * Wo;
+  float acc = 0.f;
+  for (int o = rlo; o <= rhi; ++o) {
+    const float wr = weight_of(o, hi, sh, Hi, Ho);
+    if (wr == 0.f) continue;
+    float row = 0.f;
+    for (int c = clo; c <= chi; ++c) {
+      const float wc = weight_of(c, wi, sw, Wi, Wo);
+      if (wc != 0.f) row = fmaf(wc, __ldg(p + static_cast<size_t>(o) * Wo + c), row);
+    }
+    acc = fmaf(wr, row, acc);
+  }
+  dx[i] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
 // bias gradient: db[c] = sum_p dz[p][c]; stage 1 -> partial[block][C], stage 2 sums the blocks
 // ---------------------------------------------------------------------------------------------
 __global__ void bias_grad_partial_kernel(const uint4* __restrict__ dz, float* __restrict__ partial, long long P, int C8) {
@@ -604,6 +662,31 @@ int b2u_upsample2x_bwd(const void* dup, const void* ylow, void* dlow, int N, int
   upsample2x_bwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(dup), static_cast<const uint4*>(ylow), static_cast<uint4*>(dlow), H, W, C / 8, sh, sw);
   B2U_CHECK_LAUNCH("upsample2x_bwd");
+  return 0;
+}
+
+// x: [NC][Hi][Wi] fp32 -> y: [NC][Ho][Wo] fp32, bilinear, align_corners=True
+int b2u_resize_bilinear_f32_fwd(const float* x, float* y, long long NC, int Hi, int Wi, int Ho, int Wo, void* stream) {
+  if (NC <= 0 || Hi <= 0 || Wi <= 0 || Ho <= 0 || Wo <= 0) return set_error(B2U_ERR_SHAPE, "resize_bilinear: bad shape");
+  const float sh = Ho > 1 ? static_cast<float>(Hi - 1) / static_cast<float>(Ho - 1) : 0.f;
+  const float sw = Wo > 1 ? static_cast<float>(Wi - 1) / static_cast<float>(Wo - 1) : 0.f;
+  const long long total = NC * Ho * Wo;
+  resize_bilinear_f32_fwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, y, Hi, Wi, Ho, Wo, sh, sw, total);
+  B2U_CHECK_LAUNCH("resize_bilinear_fwd");
+  return 0;
+}
+
+// dy: [NC][Ho][Wo] -> dx: [NC][Hi][Wi] (adjoint of the forward)
+int b2u_resize_bilinear_f32_bwd(const float* dy, float* dx, long long NC, int Hi, int Wi, int Ho, int Wo, void* stream) {
+  if (NC <= 0 || Hi <= 0 || Wi <= 0 || Ho <= 0 || Wo <= 0) return set_error(B2U_ERR_SHAPE, "resize_bilinear_bwd: bad shape");
+  const float sh = Ho > 1 ? static_cast<float>(Hi - 1) / static_cast<float>(Ho - 1) : 0.f;
+  const float sw = Wo > 1 ? static_cast<float>(Wi - 1) / static_cast<float>(Wo - 1) : 0.f;
+  const float ish = sh > 0.f ? 1.f / sh : 0.f, isw = sw > 0.f ? 1.f / sw : 0.f;
+  const long long total = NC * Hi * Wi;
+  resize_bilinear_f32_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dy, dx, Hi, Wi, Ho, Wo, sh, sw, ish, isw, total);
+  B2U_CHECK_LAUNCH("resize_bilinear_bwd");
   return 0;
 }
 

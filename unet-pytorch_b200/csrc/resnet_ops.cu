@@ -174,6 +174,29 @@ __global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __rest
   out[i] = r_pack8(fa);
 }
 
+// y = relu(a + b): the residual join `x += residual; x = relu(x)` (nets/LightWeightUnet.py:52-53)
+__global__ void add_relu_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out, long long n8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  float fa[8], fb[8];
+  r_unpack8(__ldg(a + i), fa);
+  r_unpack8(__ldg(b + i), fb);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) fa[k] = fmaxf(fa[k] + fb[k], 0.f);
+  out[i] = r_pack8(fa);
+}
+// dx = dy where y > 0, else 0 (gradient of the join for both of its inputs)
+__global__ void relu_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, uint4* __restrict__ dx, long long n8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  float g[8], v[8];
+  r_unpack8(__ldg(dy + i), g);
+  r_unpack8(__ldg(y + i), v);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) g[k] = v[k] > 0.f ? g[k] : 0.f;
+  dx[i] = r_pack8(g);
+}
+
 static inline dim3 rgrid(long long rows, int row_items, int block) {
   return dim3(static_cast<unsigned>(rows), static_cast<unsigned>((row_items + block - 1) / block), 1);
 }
@@ -245,6 +268,26 @@ int b2u_add_bf16(const void* a, const void* b, void* out, long long n, void* str
   add_bf16_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(a), static_cast<const uint4*>(b), static_cast<uint4*>(out), n8);
   B2U_CHECK_LAUNCH("add_bf16");
+  return 0;
+}
+
+// out = relu(a + b); out may alias a or b
+int b2u_add_relu_bf16(const void* a, const void* b, void* out, long long n, void* stream) {
+  if (n <= 0 || n % 8 != 0) return set_error(B2U_ERR_SHAPE, "add_relu_bf16: n must be a positive multiple of 8");
+  const long long n8 = n / 8;
+  add_relu_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(a), static_cast<const uint4*>(b), static_cast<uint4*>(out), n8);
+  B2U_CHECK_LAUNCH("add_relu_bf16");
+  return 0;
+}
+
+// dx = dy * (y > 0); dx may alias dy
+int b2u_relu_bwd_bf16(const void* dy, const void* y, void* dx, long long n, void* stream) {
+  if (n <= 0 || n % 8 != 0) return set_error(B2U_ERR_SHAPE, "relu_bwd_bf16: n must be a positive multiple of 8");
+  const long long n8 = n / 8;
+  relu_bwd_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(dy), static_cast<const uint4*>(y), static_cast<uint4*>(dx), n8);
+  B2U_CHECK_LAUNCH("relu_bwd_bf16");
   return 0;
 }
 

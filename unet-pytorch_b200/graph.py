@@ -149,6 +149,59 @@ def ultralight_unet_program(num_classes, widths, mid_min, se_rule=None, dropout_
     return P, convs
 
 
+def lightweight_unet_program(num_classes, in_channels=3):
+    """LightweightUnet (nets/LightWeightUnet.py:125-177): five stages of ConvBlock (conv3x3+bias, BN, ReLU) + ResidualBlock
+    (conv-BN-ReLU-conv-BN-SE, + input, ReLU) + maxpool + Dropout2d(0.1); four decoder stages cat[skip, up2x(low)] ->
+    ConvBlock -> ResidualBlock -> Dropout2d; final_conv = ConvBlock, Dropout2d, ResidualBlock, 1x1 conv.  The logits are at
+    H/2 x W/2 (every stage, including the first, ends in a maxpool)."""
+    P, convs = [], {}
+    p_drop = 0.1
+
+    def conv3(out, x, w, cin, cout, bias, x1=None, c1=0):
+        convs[w] = (cout, cin, c1, 9)
+        P.append(dict(op="conv", out=out, x=x, x1=x1, w=w, bias=bias, cin=cin, c1=c1, cout=cout, taps=9, stride=1, relu=False))
+
+    def conv_block(prefix, x, cin, cout, x1=None, c1=0):
+        conv3(prefix + ".z", x, prefix + ".conv.0.weight", cin, cout, prefix + ".conv.0.bias", x1=x1, c1=c1)
+        P.append(dict(op="bn", out=prefix + ".y", z=prefix + ".z", bn=prefix + ".conv.1", c=cout, relu=True, res=None))
+        return prefix + ".y"
+
+    def res_block(prefix, x, c):
+        conv3(prefix + ".z1", x, prefix + ".conv1.weight", c, c, prefix + ".conv1.bias")
+        P.append(dict(op="bn", out=prefix + ".y1", z=prefix + ".z1", bn=prefix + ".bn1", c=c, relu=True, res=None))
+        conv3(prefix + ".z2", prefix + ".y1", prefix + ".conv2.weight", c, c, prefix + ".conv2.bias")
+        P.append(dict(op="bn", out=prefix + ".y2", z=prefix + ".z2", bn=prefix + ".bn2", c=c, relu=False, res=None))
+        P.append(dict(op="se", out=prefix + ".s", x=prefix + ".y2", se=prefix + ".se", c=c, r=c // 4))
+        P.append(dict(op="addrelu", out=prefix + ".out", a=prefix + ".s", b=x))
+        return prefix + ".out"
+
+    def drop(name, x):
+        P.append(dict(op="drop", out=name, x=x, p=p_drop))
+        return name
+
+    P.append(dict(op="input", out="x", c=in_channels))
+    x, cin, feats = "x", in_channels, []
+    for k, w_ in enumerate((24, 48, 96, 192, 384), start=1):
+        x = conv_block(f"backbone.stage{k}.0", x, cin, w_)
+        x = res_block(f"backbone.stage{k}.1", x, w_)
+        P.append(dict(op="pool2", out=f"pool{k}", x=x))
+        x = drop(f"feat{k}", f"pool{k}")
+        feats.append((x, w_))
+        cin = w_
+    low, clow = feats[4]
+    for k in (4, 3, 2, 1):
+        skip, cs = feats[k - 1]
+        P.append(dict(op="up", out=f"up{k}", x=low))
+        x = conv_block(f"up_concat{k}.conv.0", skip, cs, cs, x1=f"up{k}", c1=clow)      # cat([skip, up]): LightWeightUnet.py:120
+        x = res_block(f"up_concat{k}.conv.1", x, cs)
+        low, clow = drop(f"up_concat{k}.drop", x), cs
+    x = conv_block("final_conv.0", low, 24, 24)
+    x = drop("final_conv.1", x)
+    x = res_block("final_conv.2", x, 24)
+    P.append(dict(op="head", out="logits", x=x, w="final_conv.3.weight", bias="final_conv.3.bias", cin=24))
+    return P, convs
+
+
 ULU_VARIANTS = {
     # name: (widths, minimum mid channels, SE reduction rule, bridge dropout)
     "ultralight": ((32, 64, 128, 256, 512), 8, None, 0.0),                                     # UltraLightweightUnet.py
@@ -170,7 +223,7 @@ class GraphEngine:
         self.dropout_override = None
         readers = {}
         for i in program:
-            for key in ("x", "x1", "z", "res"):
+            for key in ("x", "x1", "z", "res", "a", "b"):
                 if i.get(key):
                     readers.setdefault(i[key], []).append(i["op"] if key == "z" else "other")
         self._pre_bn = {name for name, ops_ in readers.items() if ops_ == ["bn"]}      # tensors read only as a BN input
@@ -397,9 +450,12 @@ class GraphEngine:
                 if training and ins["p"] > 0:
                     n, h, w, cp = xin.data.shape
                     keep = 1.0 - ins["p"]
-                    if self.dropout_override is not None:       # tests replay the multiplier the reference drew ([N, C])
+                    ov = self.dropout_override
+                    if isinstance(ov, dict):
+                        ov = ov.get(ins["out"])
+                    if ov is not None:       # tests replay the multiplier the reference drew ([N, C])
                         mask = torch.zeros((n, cp), dtype=torch.float32, device=self.device)
-                        mask[:, :self.dropout_override.shape[1]] = self.dropout_override.to(self.device)
+                        mask[:, :ov.shape[1]] = ov.to(self.device)
                     else:
                         mask = torch.bernoulli(torch.full((n, cp), keep, dtype=torch.float32, device=self.device)) / keep
                     y = ops.scale_nc(xin.data, mask, out=self._buf(ins["out"], xin.data.shape))
@@ -409,6 +465,10 @@ class GraphEngine:
                     t = _T(xin.data, needs_grad=xin.needs_grad)
                     t.aux = None
                 T[ins["out"]] = t
+            elif op == "addrelu":
+                a, b = T[ins["a"]], T[ins["b"]]
+                y = ops.add_relu(a.data, b.data, out=self._buf(ins["out"], a.data.shape))
+                T[ins["out"]] = _T(y, needs_grad=a.needs_grad or b.needs_grad)
             elif op == "pool3":
                 xin = T[ins["x"]]
                 n, h, w, c = xin.data.shape
@@ -502,6 +562,17 @@ class GraphEngine:
                 g = self._buf("g:" + ins["out"] + ">", xin.data.shape)
                 ops.upsample2x_bwd(t.grad, ylow=xin.data if xin.fused_relu else None, out=g)
                 self._acc(xin, g)
+            elif op == "addrelu":
+                t, a, b = T[ins["out"]], T[ins["a"]], T[ins["b"]]
+                if t.grad is None:
+                    continue
+                # both inputs receive dy * (y > 0).  They may share this buffer: `a` (the SE output) is consumed by the
+                # next backward instruction, before anything accumulates into `b` (the block input) in place.
+                g = ops.relu_bwd(t.grad, t.data, out=self._buf("g:" + ins["out"] + ">", t.data.shape))
+                if a.needs_grad:
+                    self._acc(a, g)
+                if b.needs_grad:
+                    self._acc(b, g)
             elif op == "pool3":
                 t, xin = T[ins["out"]], T[ins["x"]]
                 if t.grad is None or not xin.needs_grad:
@@ -679,3 +750,14 @@ class UltraLightUnetEngine(GraphEngine):
         program, convs = ultralight_unet_program(num_classes, widths, mid_min, se_rule, p)
         super().__init__(program, convs, num_classes, device=device)
         self.variant = variant
+
+
+class LightweightUnetEngine(GraphEngine):
+    def __init__(self, num_classes, in_channels=3, device=None):
+        if not 1 <= num_classes <= 32:
+            raise ValueError("num_classes must be in [1, 32]")
+        if in_channels != 3:
+            raise NotImplementedError("the CUDA input conversion takes 3-channel images")
+        program, convs = lightweight_unet_program(num_classes, in_channels)
+        super().__init__(program, convs, num_classes, device=device)
+        self.logit_stride = 2       # logits are H/2 x W/2; the losses resize them (nets/unet_training.py:12-13)

@@ -11,16 +11,32 @@ import torch
 from .. import ops
 
 
+class _ResizeBilinear(torch.autograd.Function):
+    """F.interpolate(x, size=(ht, wt), mode="bilinear", align_corners=True) on the CUDA resize kernels."""
+
+    @staticmethod
+    def forward(ctx, x, ht, wt):
+        ctx.size_in = tuple(x.shape[2:])
+        return ops.resize_bilinear(x, (ht, wt))
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.resize_bilinear_bwd(g.contiguous(), ctx.size_in), None, None
+
+
 def _prep_logits(inputs, ht, wt):
     n, c, h, w = inputs.shape
-    if h != ht and w != wt:   # same (and-) condition as the reference, nets/unet_training.py:12
-        raise NotImplementedError("logits/label size mismatch: the B200 loss kernels expect logits at label resolution")
     if not inputs.is_cuda:
         raise RuntimeError("B200 loss kernels need CUDA tensors (no CPU fallback)")
     x = inputs
     if x.dtype != torch.float32:
         x = x.float()
-    return x.contiguous()
+    x = x.contiguous()
+    if h != ht and w != wt:   # same (and-) condition as the reference, nets/unet_training.py:12 (LightweightUnet: H/2 logits)
+        x = _ResizeBilinear.apply(x, ht, wt)
+    elif h != ht or w != wt:
+        raise ValueError("logits and labels differ in exactly one spatial dimension (the reference would fail in view())")
+    return x
 
 
 class _LossFunction(torch.autograd.Function):

@@ -365,6 +365,44 @@ def add_bf16(a, b, out=None):
     return out
 
 
+def add_relu(a, b, out=None):
+    """relu(a + b), bf16 (the residual join of nets/LightWeightUnet.py:52-53)."""
+    _req(a, BF16, "a"); _req(b, BF16, "b")
+    if out is None:
+        out = torch.empty_like(a)
+    check(lib().b2u_add_relu_bf16(ptr(a), ptr(b), ptr(out), a.numel(), stream_ptr()))
+    return out
+
+
+def relu_bwd(dy, y, out=None):
+    _req(dy, BF16, "dy"); _req(y, BF16, "y")
+    if out is None:
+        out = torch.empty_like(dy)
+    check(lib().b2u_relu_bwd_bf16(ptr(dy), ptr(y), ptr(out), dy.numel(), stream_ptr()))
+    return out
+
+
+def resize_bilinear(x, size, out=None):
+    """F.interpolate(x, size, mode='bilinear', align_corners=True) for fp32 NCHW."""
+    _req(x, torch.float32, "x")
+    N, C, Hi, Wi = x.shape
+    Ho, Wo = size
+    if out is None:
+        out = torch.empty((N, C, Ho, Wo), dtype=torch.float32, device=x.device)
+    check(lib().b2u_resize_bilinear_f32_fwd(ptr(x), ptr(out), N * C, Hi, Wi, Ho, Wo, stream_ptr()))
+    return out
+
+
+def resize_bilinear_bwd(dy, size_in, out=None):
+    _req(dy, torch.float32, "dy")
+    N, C, Ho, Wo = dy.shape
+    Hi, Wi = size_in
+    if out is None:
+        out = torch.empty((N, C, Hi, Wi), dtype=torch.float32, device=dy.device)
+    check(lib().b2u_resize_bilinear_f32_bwd(ptr(dy), ptr(out), N * C, Hi, Wi, Ho, Wo, stream_ptr()))
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- depthwise / SE
 def dwconv3x3(x, w, bias=None, flip=False, out=None):
     """w: fp32 [C, 9] (or [C,1,3,3]); flip=True is the data gradient."""

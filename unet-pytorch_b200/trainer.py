@@ -17,7 +17,7 @@ import torch.distributed as dist
 
 from . import ops
 from .engine import TraditionalUnetEngine, VGGUnetEngine, vgg_unet_param_shapes
-from .graph import ResNet50UnetEngine, UltraLightUnetEngine
+from .graph import LightweightUnetEngine, ResNet50UnetEngine, UltraLightUnetEngine
 
 
 def _backward_order(names):
@@ -134,9 +134,10 @@ class GradientSync:
 class UnetTrainer:
     """model: "unet_vgg" / "unet_resnet50" (nets/unet.py::Unet with backbone 'vgg' / 'resnet50'), "traditional"
     (nets/TraditionalUnet.py) or "ultralight" / "ultralight_large" / "ultralight_large_optimized"
-    (nets/UltraLightweightUnet*.py)."""
+    (nets/UltraLightweightUnet*.py) or "lightweight" (nets/LightWeightUnet.py; logits at H/2, resized inside the loss)."""
 
     ENGINES = {"unet_vgg": VGGUnetEngine, "traditional": TraditionalUnetEngine, "unet_resnet50": ResNet50UnetEngine,
+               "lightweight": LightweightUnetEngine,
                "ultralight": functools.partial(UltraLightUnetEngine, variant="ultralight"),
                "ultralight_large": functools.partial(UltraLightUnetEngine, variant="ultralight_large"),
                "ultralight_large_optimized": functools.partial(UltraLightUnetEngine, variant="ultralight_large_optimized")}
@@ -182,7 +183,7 @@ class UnetTrainer:
         self.sync = GradientSync(self.layout, self.flat_grad, group=process_group)
         self.trainable = set(self.names)
         self.backbone_prefixes = {"unet_vgg": ("vgg.",), "unet_resnet50": ("resnet.",)}.get(
-            model, ("enc", "se") if model.startswith("ultralight") else ("inc.", "down1.", "down2.", "down3."))
+            model, ("backbone.",) if model == "lightweight" else ("enc", "se") if model.startswith("ultralight") else ("inc.", "down1.", "down2.", "down3."))
         self._gscale = torch.tensor([0.0 if focal_loss else 1.0, 1.0 if focal_loss else 0.0, 1.0 if dice_loss else 0.0],
                                     dtype=torch.float32, device=self.device)
         self._copy_stream = torch.cuda.Stream(device=self.device)
@@ -266,6 +267,9 @@ class UnetTrainer:
         logits = self.engine.forward(imgs, self.tensors, save=save)
         if pngs.dtype != torch.int64:
             pngs = pngs.long()
+        if logits.shape[2] != pngs.shape[1] and logits.shape[3] != pngs.shape[2]:
+            # LightweightUnet: logits at H/2 x W/2 are resized to the label size inside the loss (unet_training.py:12-13)
+            logits = ops.resize_bilinear(logits, tuple(pngs.shape[1:]))
         fin = ops.loss_fwd(logits, target=pngs.contiguous(), onehot=None, cls_w=self.cls_w)
         return logits, pngs, fin
 
@@ -275,8 +279,13 @@ class UnetTrainer:
         imgs, pngs, slot = self._take(imgs, pngs)
         logits, pngs, fin = self.forward_loss(imgs, pngs, save=True)
         n, _, h, w = logits.shape
-        dlogits = ops.loss_bwd(logits, fin, self._gscale, target=pngs, onehot=None, cls_w=self.cls_w, nhwc64=True,
-                               out=self.engine._buf("g:logits64", (n, h, w, 64)))
+        stride = getattr(self.engine, "logit_stride", 1)
+        if stride == 1:
+            dlogits = ops.loss_bwd(logits, fin, self._gscale, target=pngs, onehot=None, cls_w=self.cls_w, nhwc64=True,
+                                   out=self.engine._buf("g:logits64", (n, h, w, 64)))
+        else:       # gradient at label resolution (fp32), then the adjoint of the resize back to the logits' own size
+            dfull = ops.loss_bwd(logits, fin, self._gscale, target=pngs, onehot=None, cls_w=self.cls_w)
+            dlogits = ops.resize_bilinear_bwd(dfull, (h // stride, w // stride))
         self._consumed(slot)            # image and label map are not read after this point
         active = [n for n in self.layout.order if n in self.trainable]
         self.sync.reset(active)

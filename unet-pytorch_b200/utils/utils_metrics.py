@@ -10,12 +10,12 @@ from .. import ops
 def f_score(inputs, target, beta=1, smooth=1e-5, threhold=0.5):
     n, c, h, w = inputs.size()
     nt, ht, wt, ct = target.size()
-    if h != ht and w != wt:
-        raise NotImplementedError("f_score: logits/label size mismatch is not supported by the B200 kernels")
     if not inputs.is_cuda:
         raise RuntimeError("f_score: CUDA tensors required (no CPU fallback)")
     x = inputs.detach()
     x = (x if x.dtype == torch.float32 else x.float()).contiguous()
+    if h != ht and w != wt:       # utils/utils_metrics.py:15-16
+        x = ops.resize_bilinear(x, (ht, wt))
     oh = target.to(device=x.device, dtype=torch.float32).contiguous()
     fin = ops.loss_fwd(x, target=None, onehot=oh, cls_w=None, beta=float(beta), smooth=float(smooth), thr=float(threhold))
     return fin[3]
