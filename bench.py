@@ -97,6 +97,39 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def variant_cpu_img_per_s(model, num_classes, batch=2, hw=HW, steps=1, warmup=1, threads=None):
+    """cpu_baseline leg of the side measurements (scripts/variants_bench.py): the oracle port of another model family's
+    forward + CE + Dice + backward on this box's host cores, `batch` images per step -> img/s."""
+    import torch
+    from oracle import unet_oracle as O
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    imgs, pngs = O.make_inputs(batch, num_classes, hw, hw, seed=0)
+    w = torch.ones(num_classes)
+    if model == "unet_resnet50":
+        sd = O.make_resnet_unet_params(num_classes)
+        step = lambda: O.resnet_unet_train_step(sd, imgs, pngs, w, num_classes)
+    elif model == "traditional":
+        sd = O.make_trad_params(num_classes)
+        step = lambda: O.trad_train_step(sd, imgs, pngs, w, num_classes)
+    elif model == "lightweight":
+        sd = O.make_lw_params(num_classes)
+        step = lambda: O.lw_train_step(sd, imgs, pngs, w, num_classes)
+    elif model.startswith("ultralight"):
+        sd = O.make_ulu_params(num_classes, model)
+        step = lambda: O.ulu_train_step(sd, imgs, pngs, w, num_classes, model)
+    else:
+        raise ValueError(model)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return {"value": batch / (sum(times) / len(times)), "unit": "img/s", "cores": threads, "kind": "port",
+            "sample": f"{steps} step(s) of batch {batch} at {hw}x{hw}, fwd + CE + Dice + bwd (no optimizer), after {warmup} warm-up"}
+
+
 def cpu_path_img_per_s(steps, warmup, batch=2, threads=None):
     """The reference's CPU path for this workload (oracle port), bounded sample: `batch` images per step.
     One step = forward, CE + Dice, f_score (no grad), backward, Adam -- the same work the GPU arm times."""

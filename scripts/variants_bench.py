@@ -11,11 +11,12 @@ from unet_pytorch_b200 import _lib
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--models", default="ultralight_large,ultralight,ultralight_large_optimized,traditional,unet_resnet50")
+    ap.add_argument("--models", default="lightweight,ultralight_large,ultralight,ultralight_large_optimized,traditional,unet_resnet50")
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--classes", type=int, default=2)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--by-shape", action="store_true")
+    ap.add_argument("--cpu-baseline", action="store_true", help="also time the CPU port (bench.py's cpu_baseline leg) per model")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -43,6 +44,10 @@ def main():
                       "params": int(sum(p.numel() for p in tr.params.values())),
                       "profiled_step_ms_sum": tot,
                       "by_entry_point": {k: {"launches": v["launches"], "ms": round(v["ms"], 4)} for k, v in top}}
+        if args.cpu_baseline:
+            import bench
+            res[model]["cpu_baseline"] = bench.variant_cpu_img_per_s(model, C)
+            res[model]["speedup_vs_cpu_port"] = res[model]["img_per_s"] / res[model]["cpu_baseline"]["value"]
         loss = float(tr.last[0]) if tr.last is not None else None
         res[model]["loss_finite"] = loss is None or loss == loss
         del tr
