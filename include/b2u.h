@@ -175,6 +175,11 @@ int b2u_loss_bwd(const float* logits, const long long* target, const float* oneh
                  float focal_gamma, void* stream);
 /* final.weight [C][64] fp32 -> 64x64 bf16 dgrad operand wd[ci][co], co in [0,32) and [32,64) both = class co % 32 */
 int b2u_pack_head_dgrad(const float* w, void* wd, int ncls, void* stream);
+/* the same 1x1 classifier forward on the tensor cores: wf = bf16 [64][64] from b2u_pack_head_fprop (rows [0,32) =
+ * bf16(W), rows [32,64) = bf16(W - bf16(W)); the epilogue adds the halves), fp32 NCHW logits written directly */
+int b2u_pack_head_fprop(const float* w, void* wf, int ncls, void* stream);
+int b2u_head_fwd_tc(const void* x, const void* wf, const float* bias, float* logits, int N, int H, int W, int ncls,
+                    void* stream);
 /* per-pixel class decision of the inference loop (unet.py:246-250: argmax(softmax(z)) == argmax(z)) */
 int b2u_argmax_u8(const float* logits, unsigned char* mask, int N, int C, int H, int W, void* stream);
 /* fast_hist (utils/utils_metrics.py:34-43): hist (n*n+1 uint64, accumulated) ; dtype 0=u8 1=i32 2=i64 */

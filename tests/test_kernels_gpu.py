@@ -547,3 +547,22 @@ def test_residual_join_and_resize_kernels(b2u, cuda_device, golden_dir):
     full = O.resize_logits(lref, h, w)
     (O.focal_loss(full, pngs, cw.cpu(), C) + O.dice_loss(full, O.one_hot(pngs, C))).backward()
     assert rel(lg.grad, lref.grad) <= 1e-4
+
+
+@pytest.mark.parametrize("N,H,W,C", [(2, 16, 32, 21), (1, 24, 40, 2), (3, 8, 16, 32), (1, 5, 7, 4)])
+def test_head_forward_on_tensor_cores(b2u, cuda_device, N, H, W, C):
+    """The 1x1 classifier through the conv kernel's head epilogue ([hi | lo] bf16 split of the fp32 weights, fp32 NCHW
+    logits) against fp32 torch on the same bf16 activations and against the SIMT head."""
+    from unet_pytorch_b200 import ops
+    dev = cuda_device
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(N, 64, H, W, generator=g).to(BF).float()
+    w = torch.randn(C, 64, generator=g) * 0.2
+    b = torch.randn(C, generator=g)
+    ref = F.conv2d(x, w[:, :, None, None], b)
+    xd = nhwc(x, dev)
+    out = ops.head_fwd_tc(xd, ops.pack_head_fprop(w.to(dev)), b.to(dev), C)
+    assert tuple(out.shape) == (N, C, H, W)
+    assert rel(out, ref) <= 2e-5          # fp32 accumulation of bf16 x (exact products) and ~2^-17 weights
+    simt = ops.head_fwd(xd, w.to(dev), b.to(dev))
+    assert rel(out, simt) <= 2e-5

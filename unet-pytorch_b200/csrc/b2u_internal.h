@@ -36,7 +36,8 @@ struct ConvLaunch {
   int split_c = 0;
   const __nv_bfloat16* mask = nullptr; int mask_c = 0;
   int N = 0, H = 0, W = 0, Cout = 0, taps = 9;
-  int flags = 0;                            // bit0 relu, bit1 mask
+  int flags = 0;                            // bit0 relu, bit1 mask, bit2 classifier head (fp32 NCHW logits)
+  float* head_out = nullptr; int head_cls = 0;   // bit2: logits [N][head_cls][H][W]; Cout must be 64 = [hi(32) | lo(32)] weights
   int bn_override = 0;
   int tile_flags = 0;                       // bit0: force one M tile per CTA step (debug / tests)
 };

@@ -39,8 +39,10 @@ struct ConvParams {
   int tiles_w, tiles_h;
   int num_m_tiles, num_n_tiles;
   int split_c;       // output channels >= split_c go to the second output tensor map
-  int flags;         // bit0 relu, bit1 mask
-  const float* bias; // [Cout] or null
+  int flags;         // bit0 relu, bit1 mask, bit2 classifier head
+  float* head_out;   // bit2: fp32 NCHW logits [N][head_cls][H][W]
+  int head_cls;
+  const float* bias; // [Cout] or null (head: [head_cls])
   const __nv_bfloat16* mask;  // NHWC [N,H,W,mask_c] or null; keeps y where mask > 0
   int mask_c;
 };
@@ -245,7 +247,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       // this tile's bias slice; the parity double buffer + the barrier keep a fast warp from overwriting values a
       // slow warp of the previous tile still reads
       float* sB = sBias + bpar * 256;
-      for (int c = threadIdx.x - 64; c < BN; c += 128) sB[c] = p.bias ? __ldg(p.bias + n0 + c) : 0.f;
+      for (int c = threadIdx.x - 64; c < BN; c += 128)
+        sB[c] = (p.bias && (!(p.flags & 4) || c < p.head_cls)) ? __ldg(p.bias + n0 + c) : 0.f;
       named_bar_sync(2, 128);
       bpar ^= 1u;
 
@@ -265,6 +268,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(t_empty(as));
+        }
+        if (p.flags & 4) {
+          // classifier head (nets/unet.py:58,76): the 64 accumulator columns are [hi(32) | lo(32)] of the two-term bf16
+          // split of the fp32 weights, so logits[c] = acc[c] + acc[32 + c] + bias[c] carries them to ~2^-17; written
+          // straight to the fp32 NCHW tensor the losses read (a warp covers two 64-byte runs per class)
+          const int gh = h0 + mt * kHb + ph;
+          if (gh < p.H && gw < p.W) {
+            const size_t plane = static_cast<size_t>(p.H) * p.W;
+            float* o = p.head_out + static_cast<size_t>(img) * p.head_cls * plane + static_cast<size_t>(gh) * p.W + gw;
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (c < p.head_cls) o[c * plane] = __uint_as_float(v[c]) + __uint_as_float(v[32 + c]) + sB[c];
+          }
+          continue;
         }
         const int cbase = n0 + j * 64;
         uint32_t packed[32];
@@ -369,6 +386,8 @@ static int launch_cfg(const ConvLaunch& a, cudaStream_t st) {
   p.num_n_tiles = a.Cout / BN;
   p.split_c = split;
   p.flags = a.flags;
+  p.head_out = a.head_out;
+  p.head_cls = a.head_cls;
   p.bias = a.bias;
   p.mask = a.mask;
   p.mask_c = a.mask_c;
@@ -393,6 +412,8 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st) {
     return set_error(B2U_ERR_SHAPE, "conv: input channels (%d,%d) must be multiples of 64", a.C0, a.C1);
   if (a.y1 != nullptr && (a.split_c <= 0 || a.split_c >= a.Cout || a.split_c % 64 != 0))
     return set_error(B2U_ERR_SHAPE, "conv: split_c %d must be a multiple of 64 inside (0,Cout)", a.split_c);
+  if ((a.flags & 4) && (a.Cout != 64 || a.head_out == nullptr || a.head_cls < 1 || a.head_cls > 32 || a.y1 != nullptr))
+    return set_error(B2U_ERR_SHAPE, "conv: head mode needs Cout == 64, 1..32 classes and an fp32 output");
   int bn = 0;
   if (a.bn_override) {
     if (a.Cout % a.bn_override != 0) return set_error(B2U_ERR_SHAPE, "conv: bn_override does not divide Cout");
@@ -457,6 +478,19 @@ int b2u_conv_dgrad(const void* dz, int Cz, const void* wd, void* dx0, int C0, vo
   }
   a.bn_override = bn_override & 0xffff;
   a.tile_flags = bn_override >> 16;
+  return b2u::launch_conv(a, static_cast<cudaStream_t>(stream));
+}
+
+// Classifier head on the tensor cores: logits[n][c][h][w] = sum_k x[n][h][w][k] W[c][k] + b[c], fp32 NCHW.
+// wf: bf16 [64][64] from b2u_pack_head_fprop (rows [0,32) = bf16(W), rows [32,64) = bf16(W - bf16(W))).
+int b2u_head_fwd_tc(const void* x, const void* wf, const float* bias, float* logits, int N, int H, int W, int ncls,
+                    void* stream) {
+  b2u::ConvLaunch a;
+  a.x0 = x; a.C0 = 64;
+  a.wpacked = wf; a.bias = bias;
+  a.y0 = const_cast<void*>(x);          // never written: the head epilogue bypasses the NHWC store path
+  a.N = N; a.H = H; a.W = W; a.Cout = 64; a.taps = 1;
+  a.flags = 4; a.head_out = logits; a.head_cls = ncls;
   return b2u::launch_conv(a, static_cast<cudaStream_t>(stream));
 }
 

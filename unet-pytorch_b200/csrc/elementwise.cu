@@ -49,33 +49,45 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 // first-layer im2col: col[n,h,w,k] = x[n,c,h+r-1,w+s-1] for k = (r*3+s)*Cin + c < 9*Cin, else 0
 // ---------------------------------------------------------------------------------------------
 // Block = one 64-pixel row segment.  Phase 1: the 9*Cin <= 64 (tap, channel) planes are read with the pixel index
-// fastest across lanes (128-byte coalesced fp32 loads) into a [64 px][64 k] bf16 tile; phase 2: the tile leaves as
-// 64 x 128 contiguous bytes.
+// fastest across lanes (128-byte coalesced fp32 loads), two k per thread, into a [64 px][33 words] tile of bf16 pairs
+// (stride 33: conflict-free for both phases); phase 2: the tile leaves as 64 x 128 contiguous bytes, the k >= 9*Cin
+// padding synthesised as zeros without touching shared memory.
 constexpr int kI2cPix = 64;
+template <int CIN>
 __global__ void __launch_bounds__(256)
-im2col_first_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int Cin, int H, int W) {
-  __shared__ __align__(16) __nv_bfloat16 tile[kI2cPix][64 + 8];     // +8: keeps 16-byte rows, staggers banks
+im2col_first_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int cin_rt, int H, int W) {
+  __shared__ uint32_t tile[kI2cPix][33];
+  const int Cin = CIN > 0 ? CIN : cin_rt;
   const int segs = (W + kI2cPix - 1) / kI2cPix;
   const int seg = blockIdx.x % segs;
   const int row = blockIdx.x / segs;          // n * H + h
   const int n = row / H, h = row - n * H;
   const int w0 = seg * kI2cPix;
-  const int K = 9 * Cin;
-  for (int i = threadIdx.x; i < 64 * kI2cPix; i += blockDim.x) {
-    const int k = i / kI2cPix, pw = i - k * kI2cPix;
-    float v = 0.f;
-    if (k < K) {
-      const int tap = k / Cin, c = k - tap * Cin;
-      const int hh = h + tap / 3 - 1, ww = w0 + pw + tap % 3 - 1;
-      if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(x + ((static_cast<size_t>(n) * Cin + c) * H + hh) * W + ww);
-    }
-    tile[pw][k] = __float2bfloat16_rn(v);
+  const int K = 9 * Cin, KP = (K + 1) / 2;    // k pairs that hold data
+  const float* img = x + static_cast<size_t>(n) * Cin * H * W;
+  auto fetch = [&](int k, int pw) -> float {
+    if (k >= K) return 0.f;
+    const int tap = k / Cin, c = k - tap * Cin;
+    const int hh = h + tap / 3 - 1, ww = w0 + pw + tap % 3 - 1;
+    return (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(img + (static_cast<size_t>(c) * H + hh) * W + ww) : 0.f;
+  };
+  for (int i = threadIdx.x; i < KP * kI2cPix; i += 256) {
+    const int kp = i / kI2cPix, pw = i - kp * kI2cPix;
+    tile[pw][kp] = pack_bf16x2(fetch(2 * kp, pw), fetch(2 * kp + 1, pw));
   }
   __syncthreads();
   uint4* out = reinterpret_cast<uint4*>(col) + (static_cast<size_t>(row) * W + w0) * 8;
-  for (int i = threadIdx.x; i < kI2cPix * 8; i += blockDim.x) {
+  for (int i = threadIdx.x; i < kI2cPix * 8; i += 256) {
     const int pw = i >> 3, q = i & 7;
-    if (w0 + pw < W) out[i] = *reinterpret_cast<const uint4*>(&tile[pw][q * 8]);
+    if (w0 + pw >= W) continue;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (4 * q < KP) {
+      v.x = tile[pw][4 * q];
+      if (4 * q + 1 < KP) v.y = tile[pw][4 * q + 1];
+      if (4 * q + 2 < KP) v.z = tile[pw][4 * q + 2];
+      if (4 * q + 3 < KP) v.w = tile[pw][4 * q + 3];
+    }
+    out[i] = v;
   }
 }
 
@@ -582,8 +594,9 @@ int b2u_nchw_f32_to_nhwc_bf16_padded(const float* x, void* y, int N, int C, int 
 
 int b2u_im2col_first(const float* x, void* col, int N, int Cin, int H, int W, void* stream) {
   if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || 9 * Cin > 64) return set_error(B2U_ERR_SHAPE, "im2col_first: bad shape (Cin=%d)", Cin);
-  im2col_first_kernel<<<static_cast<unsigned>(static_cast<long long>(N) * H * ((W + kI2cPix - 1) / kI2cPix)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, static_cast<__nv_bfloat16*>(col), N, Cin, H, W);
+  const unsigned blocks = static_cast<unsigned>(static_cast<long long>(N) * H * ((W + kI2cPix - 1) / kI2cPix));
+  if (Cin == 3) im2col_first_kernel<3><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16*>(col), N, Cin, H, W);
+  else          im2col_first_kernel<0><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16*>(col), N, Cin, H, W);
   B2U_CHECK_LAUNCH("im2col_first");
   return 0;
 }

@@ -276,28 +276,36 @@ loss_stats_map_kernel(const float* __restrict__ logits, const long long* __restr
 #pragma unroll
   for (int c = 0; c < kMaxCls; ++c) { Ps[c] = Pf[c] = 0.f; }
 
-  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < P;
-       p += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long n = p / HW, hw = p % HW;
+  // warp-uniform loop (every lane stays in it, `inb` guards the tail) so the class-wise aggregation below can use
+  // full-warp collectives
+  for (long long p0 = static_cast<long long>(blockIdx.x) * blockDim.x + warp * 32; p0 < P;
+       p0 += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = p0 + lane;
+    const bool inb = p < P;
+    const long long pc_ = inb ? p : P - 1;
+    const long long n = pc_ / HW, hw = pc_ % HW;
     const float* z = logits + n * C * HW + hw;
     float v[kMaxCls];
     float m = -INFINITY;
 #pragma unroll
     for (int c = 0; c < kMaxCls; ++c) if (c < C) { v[c] = __ldg(z + c * HW); m = fmaxf(m, v[c]); }
-    const long long y = target[p];
-    const bool valid = y >= 0 && y < C;
+    const long long y = target[pc_];
+    const bool valid = inb && y >= 0 && y < C;
     const float zy = valid ? __ldg(z + y * HW) : 0.f;
     float sum = 0.f;
 #pragma unroll
     for (int c = 0; c < kMaxCls; ++c) if (c < C) { v[c] = expf(v[c] - m); sum += v[c]; }
     const float inv = 1.f / sum;
+    if (inb) {
 #pragma unroll
-    for (int c = 0; c < kMaxCls; ++c) if (c < C) {
-      const float pc = v[c] * inv;
-      Ps[c] += pc;
-      Pf[c] += pc > thr ? 1.f : 0.f;
+      for (int c = 0; c < kMaxCls; ++c) if (c < C) {
+        const float pc = v[c] * inv;
+        Ps[c] += pc;
+        Pf[c] += pc > thr ? 1.f : 0.f;
+      }
+      a_cnt += 1.f;
     }
-    a_cnt += 1.f;
+    float py = 0.f;
     if (valid) {
       const float nll = m + logf(sum) - zy;
       const float wy = swt[y];
@@ -305,10 +313,19 @@ loss_stats_map_kernel(const float* __restrict__ logits, const long long* __restr
       const float logpt = -wy * nll;
       const float pt = expf(logpt);
       a_focal += -powf(fmaxf(1.f - pt, 0.f), focal_gamma) * (focal_alpha * logpt);
-      const float py = expf(zy - m) * inv;
-      atomicAdd(&s_tp[warp][y], static_cast<unsigned long long>(static_cast<double>(py) * 4294967296.0));
-      atomicAdd(&s_T[warp][y], 1u);
-      if (py > thr) atomicAdd(&s_tpf[warp][y], 1u);
+      py = expf(zy - m) * inv;
+    }
+    // own-class sums: lanes holding the same class are grouped (label maps are blob-structured, so a warp usually holds
+    // one or two classes) and one lane per group updates the warp's table -- integer arithmetic, order-independent
+    const unsigned gm = __match_any_sync(0xffffffffu, valid ? static_cast<int>(y) : -1);
+    if (valid) {
+      const unsigned fx = __reduce_add_sync(gm, __float2uint_rn(py * 16777216.f));      // 2^-24 fixed point, <= 2^29
+      const unsigned hard = __popc(__ballot_sync(gm, py > thr));
+      if (lane == __ffs(gm) - 1) {
+        atomicAdd(&s_tp[warp][y], static_cast<unsigned long long>(fx) << 8);            // table is 2^-32 fixed point
+        atomicAdd(&s_T[warp][y], static_cast<unsigned>(__popc(gm)));
+        if (hard) atomicAdd(&s_tpf[warp][y], hard);
+      }
     }
   }
   const int nwarps = kWarps;
@@ -389,8 +406,10 @@ loss_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ 
   const float g_ce = gscale[0] * fin[4 + 2 * C];       // upstream grad / sum_w
   const float g_focal = gscale[1] * fin[4 + 2 * C + 1];  // upstream grad / pixel count
   const float g_dice = gscale[2];
-  const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (p >= P) return;
+  const long long p_raw = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (!NHWC64 && p_raw >= P) return;
+  const bool inb = p_raw < P;                  // NHWC64: every lane stays for the warp's cooperative store
+  const long long p = inb ? p_raw : P - 1;
   const long long n = p / HW, hw = p % HW;
   const float* z = logits + n * C * HW + hw;
   float* dzp = dlogits + n * C * HW + hw;
@@ -449,7 +468,10 @@ loss_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ 
   if (NHWC64) {
     // channels [0,32): bf16(d); channels [32,64): bf16(d - hi).  The two halves meet the SAME weights in the 1x1
     // dgrad/wgrad (K resp. M is padded to 64 anyway), so the head's backward sees dlogits to ~2^-17 at no cost.
-    uint4* o = reinterpret_cast<uint4*>(dlogits) + p * 8;      // 64 bf16 = 8 x 16 B per pixel
+    // Each lane owns one pixel row of 128 B; the warp's 32 rows are contiguous (4 KB), so they go through a
+    // warp-private shared-memory tile and leave as fully coalesced 512-byte stores.
+    __shared__ uint4 tile[kLossThreads / 32][32][9];          // [warp][pixel][8 + 1 pad]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float lo[kMaxCls];
 #pragma unroll
     for (int c = 0; c < kMaxCls; ++c) lo[c] = dv[c] - __bfloat162float(__float2bfloat16_rn(dv[c]));
@@ -458,11 +480,19 @@ loss_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ 
       uint4 r;
       r.x = pack_bf16x2(dv[q * 8 + 0], dv[q * 8 + 1]); r.y = pack_bf16x2(dv[q * 8 + 2], dv[q * 8 + 3]);
       r.z = pack_bf16x2(dv[q * 8 + 4], dv[q * 8 + 5]); r.w = pack_bf16x2(dv[q * 8 + 6], dv[q * 8 + 7]);
-      o[q] = r;
+      tile[warp][lane][q] = r;
       uint4 l;
       l.x = pack_bf16x2(lo[q * 8 + 0], lo[q * 8 + 1]); l.y = pack_bf16x2(lo[q * 8 + 2], lo[q * 8 + 3]);
       l.z = pack_bf16x2(lo[q * 8 + 4], lo[q * 8 + 5]); l.w = pack_bf16x2(lo[q * 8 + 6], lo[q * 8 + 7]);
-      o[kMaxCls / 8 + q] = l;
+      tile[warp][lane][kMaxCls / 8 + q] = l;
+    }
+    __syncwarp();
+    const long long p_warp = p_raw - lane;                     // first pixel of this warp
+    uint4* o = reinterpret_cast<uint4*>(dlogits) + p_warp * 8;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int idx = it * 32 + lane, px = idx >> 3, q = idx & 7;
+      if (p_warp + px < P) o[idx] = tile[warp][px][q];
     }
   }
 }
@@ -474,6 +504,21 @@ __global__ void pack_head_dgrad_kernel(const float* __restrict__ w, __nv_bfloat1
   if (i >= 64 * 64) return;
   const int ci = i / 64, co = (i % 64) % kMaxCls;
   wd[i] = __float2bfloat16_rn(co < C ? w[co * 64 + ci] : 0.f);
+}
+
+// final.weight [C][64] fp32 -> fprop operand wf[co'][k] bf16, 64 x 64: rows [0,32) = bf16(W), rows [32,64) = the bf16
+// remainder W - bf16(W); the head epilogue adds the two halves (classes >= C are zero rows)
+__global__ void pack_head_fprop_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 64) return;
+  const int co = i / 64, k = i % 64, c = co % kMaxCls;
+  float v = 0.f;
+  if (c < C) {
+    const float full = w[c * 64 + k];
+    const float hi = __bfloat162float(__float2bfloat16_rn(full));
+    v = co < kMaxCls ? hi : full - hi;
+  }
+  wf[i] = __float2bfloat16_rn(v);
 }
 
 // arg-max over classes (lowest index on ties, like numpy/torch): logits NCHW fp32 -> uint8 mask [N,H,W]
@@ -588,6 +633,13 @@ int b2u_pack_head_dgrad(const float* w, void* wd, int ncls, void* stream) {
   if (ncls <= 0 || ncls > kMaxCls) return set_error(B2U_ERR_SHAPE, "pack_head_dgrad: 1 <= classes <= 32");
   pack_head_dgrad_kernel<<<16, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, static_cast<__nv_bfloat16*>(wd), ncls);
   B2U_CHECK_LAUNCH("pack_head_dgrad");
+  return 0;
+}
+
+int b2u_pack_head_fprop(const float* w, void* wf, int ncls, void* stream) {
+  if (ncls <= 0 || ncls > kMaxCls) return set_error(B2U_ERR_SHAPE, "pack_head_fprop: 1 <= classes <= 32");
+  pack_head_fprop_kernel<<<16, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, static_cast<__nv_bfloat16*>(wf), ncls);
+  B2U_CHECK_LAUNCH("pack_head_fprop");
   return 0;
 }
 

@@ -329,7 +329,9 @@ class UNetEngine:
             o1 = self._layer_fwd(c1, skip, params, A, training, x1=up)
             low = self._layer_fwd(c2, o1, params, A, training)
         wh = self._head_weight(params)
-        logits = ops.head_fwd(low, wh, params[self.head_name + ".bias"])
+        # 1x1 classifier on the tensor cores: [hi | lo] bf16 split of the fp32 weights, fp32 NCHW logits from the epilogue
+        wf_head = ops.pack_head_fprop(wh, wf=self._buf("head:wf", (64, 64)))
+        logits = ops.head_fwd_tc(low, wf_head, params[self.head_name + ".bias"], self.num_classes)
         if save:
             self.saved = (A, feats, (N, H, W))
         return logits

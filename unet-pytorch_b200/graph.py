@@ -486,7 +486,8 @@ class GraphEngine:
                 T[ins["out"]] = _T(y, needs_grad=xin.needs_grad)
             elif op == "head":
                 xin = T[ins["x"]]
-                logits = ops.head_fwd(xin.data, self._head_weight(params, ins), params[ins["bias"]])
+                wf_head = ops.pack_head_fprop(self._head_weight(params, ins), wf=self._buf("head:wf", (64, 64)))
+                logits = ops.head_fwd_tc(xin.data, wf_head, params[ins["bias"]], self.num_classes)
         if save:
             self.saved = (T, (N, H, W), set(trainable))
         return logits

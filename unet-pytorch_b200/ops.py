@@ -540,6 +540,27 @@ def pack_head_dgrad(w, wd=None):
     return wd
 
 
+def pack_head_fprop(w, wf=None):
+    _req(w, torch.float32, "final.weight")
+    ncls = w.shape[0]
+    if wf is None:
+        wf = torch.empty((64, 64), dtype=BF16, device=w.device)
+    check(lib().b2u_pack_head_fprop(ptr(w), ptr(wf), ncls, stream_ptr()))
+    return wf
+
+
+def head_fwd_tc(x, wf, b, ncls, out=None):
+    """The 1x1 classifier on the tensor cores (wf from pack_head_fprop): fp32 NCHW logits."""
+    _req(x, BF16, "x"); _req(wf, BF16, "wf"); _req(b, torch.float32, "b")
+    N, H, W, Cin = x.shape
+    if Cin != 64:
+        raise ValueError("head_fwd_tc: the head input must have 64 (padded) channels")
+    if out is None:
+        out = torch.empty((N, ncls, H, W), dtype=torch.float32, device=x.device)
+    check(lib().b2u_head_fwd_tc(ptr(x), ptr(wf), ptr(b), ptr(out), N, H, W, ncls, stream_ptr()))
+    return out
+
+
 def argmax_u8(logits, out=None):
     _req(logits, torch.float32, "logits")
     N, C, H, W = logits.shape
