@@ -17,7 +17,8 @@
 //   * The horizontal taps s are separate work units (separate TMA boxes shifted by s-1).
 //   * Work unit = (cout block, cin block, s, K split); fp32 partial sums go to a workspace
 //     [split][Cout][taps][Cin]; wgrad_reduce sums the splits and writes OIHW fp32 (deterministic).
-//   * Warp roles: warp0 TMA producer, warp1 MMA issuer, warps 2..5 epilogue (TMEM -> global).
+//   * Warp roles: warp0 TMA producer, warp1 MMA issuer, warps 2..5 epilogue (TMEM -> global), warps 6-7 bias sums
+//     (db = column sums of dz, read from the dz tiles while they sit in shared memory for the MMA).
 #include "b2u_internal.h"
 #include "b2u_ptx.cuh"
 
@@ -32,7 +33,7 @@ struct WgradParams {
   int num_mblk, num_cblk, splits, units;
   int merged;                      // 1: N=192 merged vertical taps; 0: three N=64 instructions
   float* partial;                  // [splits][Cout][taps][C0+C1]
-  float* bias_partial;             // [splits][Cout] or null: db = column sums of dz (an extra N=16 MMA against ones)
+  float* bias_partial;             // [splits][Cout] or null: db = column sums of dz (warp 6 sums the staged dz tiles)
 };
 
 template <int TAPS, int STAGES>
@@ -42,14 +43,11 @@ struct WgCfg {
   static constexpr int kDzHalf = kHb * kWb * 128;       // 64 couts x 128 px
   static constexpr int kDzBytes = 2 * kDzHalf;
   static constexpr int kStage = kDzBytes + kXBytes;
-  static constexpr int kOffOnes = STAGES * kStage;      // 16 K-rows x 128 B of bf16 1.0: B operand of the bias MMA
-  static constexpr int kOnesBytes = 2048;
-  static constexpr int kOffBar = kOffOnes + kOnesBytes;
+  static constexpr int kOffBar = STAGES * kStage;
   static constexpr int kNumBar = 2 * STAGES + 4;
   static constexpr int kOffTmem = kOffBar + kNumBar * 8;
   static constexpr int kSmemBytes = kOffTmem + 16 + 1024;
   static constexpr int kAccN = TAPS == 9 ? 192 : 64;    // accumulator columns per unit
-  static constexpr int kBiasCol = kAccN;                // accumulator column block holding the bias sums
   static constexpr int kTmemCols = TAPS == 9 ? 512 : 256;
   static constexpr int kAccStride = kTmemCols / 2;
   static_assert(kStage % 1024 == 0, "stage alignment");
@@ -57,7 +55,7 @@ struct WgCfg {
 };
 
 template <int TAPS, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(256, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
                   const __grid_constant__ CUtensorMap tmDZ, const WgradParams p) {
   using Cfg = WgCfg<TAPS, STAGES>;
@@ -81,7 +79,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
     tma_prefetch_desc(&tmX0);
     tma_prefetch_desc(&tmX1);
     tma_prefetch_desc(&tmDZ);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
+    // a stage is free again after the MMAs that read it committed AND (bias wanted) warps 6 and 7 have summed / skipped it
+    for (int i = 0; i < STAGES; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), p.bias_partial ? 3 : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(t_full(i), 1); mbar_init(t_empty(i), 4); }
     fence_mbar_init();
   }
@@ -89,9 +88,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < Cfg::kOnesBytes / 4; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(smem_gen + Cfg::kOffOnes)[i] = 0x3F803F80u;   // two bf16 1.0
-  fence_proxy_async_smem();        // generic-proxy writes -> visible to the tensor core's async proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -146,8 +142,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
       // A = dz (M x K, MN-major), B = x (N x K, MN-major)
       constexpr uint32_t idesc_merged = umma_idesc_bf16(128, Cfg::kAccN, 1, 1);
       constexpr uint32_t idesc_single = umma_idesc_bf16(128, 64, 1, 1);
-      constexpr uint32_t idesc_bias = umma_idesc_bf16(128, 16, 1, 1);
-      const uint64_t ones_desc = umma_smem_desc(smem_base + Cfg::kOffOnes, 2048, 1024, 2u);
       const uint32_t lbo_a = two_halves ? Cfg::kDzHalf : 0u;   // Cout == 64: rows 64..127 alias rows 0..63
       // descriptor templates: per MMA only the 14-bit start-address field moves (+128 = one 16-pixel image row)
       const uint64_t a_desc0 = umma_smem_desc(smem_base, lbo_a, 1024, 2u);
@@ -161,14 +155,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         mbar_wait(t_empty(as), pacc ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * Cfg::kAccStride);
-        const bool bias_unit = p.bias_partial != nullptr && cblk == 0 && s == 0;
         uint32_t acc = 0;
         for (int kb = k0; kb < k1; ++kb) {
           mbar_wait(full(st), ph);
           tc_fence_after();
           const uint64_t a_st = a_desc0 + static_cast<uint64_t>((st * Cfg::kStage) >> 4);
           const uint64_t b_st = b_desc0 + static_cast<uint64_t>((st * Cfg::kStage) >> 4);
-          if (merged && !bias_unit) {
+          if (merged) {
 #pragma unroll
             for (int j = 0; j < kHb; ++j)
               tc_mma_bf16(d_tmem, a_st + j * 128, b_st + j * 128, idesc_merged, j == 0 ? acc : 1u);
@@ -176,14 +169,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
 #pragma unroll
             for (int j = 0; j < kHb; ++j) {
               const uint32_t accj = j == 0 ? acc : 1u;
-              if (merged) {
-                tc_mma_bf16(d_tmem, a_st + j * 128, b_st + j * 128, idesc_merged, accj);
-              } else {
 #pragma unroll
-                for (int r = 0; r < R_TAPS; ++r)
-                  tc_mma_bf16(d_tmem + r * 64, a_st + j * 128, b_st + (j + r) * 128, idesc_single, accj);
-              }
-              if (bias_unit) tc_mma_bf16(d_tmem + Cfg::kBiasCol, a_st + j * 128, ones_desc, idesc_bias, accj);
+              for (int r = 0; r < R_TAPS; ++r)
+                tc_mma_bf16(d_tmem + r * 64, a_st + j * 128, b_st + (j + r) * 128, idesc_single, accj);
             }
           }
           acc = 1;
@@ -192,6 +180,53 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         }
         tc_commit(t_full(as));
         if (++as == 2) { as = 0; pacc ^= 1u; }
+      }
+    }
+  } else if (warp >= 6) {
+    // ===================== bias warps (6: couts 0..63 of the block, 7: couts 64..127): db[co] = sum over pixels of dz[., co]
+    // Mirrors the MMA warp's walk over the stages.  In the one unit per (split, cout block) that owns the bias
+    // (cblk == 0, s == 0) it sums the dz tile of every stage from shared memory: lane = (16-byte chunk c of 8
+    // channels, row group g), rows g, g+4, ...; the 128-byte swizzle puts logical chunk c of row r at chunk c ^ (r & 7),
+    // and the 8 lanes of a quarter warp read one full 128-byte row, so the loads are conflict-free.
+    if (p.bias_partial != nullptr) {
+      const int c = lane & 7, g = lane >> 3;
+      int st = 0; uint32_t ph = 0;
+      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+        int split, mblk, cblk, s, k0, k1;
+        decode(unit, split, mblk, cblk, s);
+        krange(split, k0, k1);
+        const bool bias_unit = cblk == 0 && s == 0;
+        const int h = warp - 6;                         // which 64-channel half of the dz tile this warp sums
+        const bool mine = bias_unit && (h == 0 || two_halves);
+        float sum[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum[k] = 0.f;
+        for (int kb = k0; kb < k1; ++kb) {
+          mbar_wait(full(st), ph);
+          if (mine) {
+            const uint8_t* tile = smem_gen + st * Cfg::kStage + h * Cfg::kDzHalf;
+#pragma unroll 8
+            for (int it = 0; it < (kHb * kWb) / 4; ++it) {
+              const int row = it * 4 + g;
+              const uint4 v = *reinterpret_cast<const uint4*>(tile + row * 128 + ((c ^ (row & 7)) << 4));
+              sum[0] += bf16_lo(v.x); sum[1] += bf16_hi(v.x); sum[2] += bf16_lo(v.y); sum[3] += bf16_hi(v.y);
+              sum[4] += bf16_lo(v.z); sum[5] += bf16_hi(v.z); sum[6] += bf16_lo(v.w); sum[7] += bf16_hi(v.w);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty(st));
+          if (++st == STAGES) { st = 0; ph ^= 1u; }
+        }
+        if (mine) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float t = sum[k];
+            t += __shfl_xor_sync(0xffffffffu, t, 8);
+            t += __shfl_xor_sync(0xffffffffu, t, 16);
+            const int co = mblk * 128 + h * 64 + c * 8 + k;
+            if (g == 0 && co < p.Cout) p.bias_partial[static_cast<size_t>(split) * p.Cout + co] = t;   // zero for an empty split
+          }
+        }
       }
     }
   } else {
@@ -228,12 +263,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
             dst[q] = o;
           }
         }
-      }
-      if (p.bias_partial != nullptr && cblk == 0 && s == 0) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + Cfg::kBiasCol, v);     // only column 0 is meaningful (every column of the ones tile is 1)
-        tmem_ld_wait();
-        if (valid) p.bias_partial[static_cast<size_t>(split) * p.Cout + co] = k1 > k0 ? __uint_as_float(v[0]) : 0.f;
       }
       tc_fence_before();
       __syncwarp();
@@ -387,7 +416,7 @@ static int launch_wgrad_cfg(const void* x0, int C0, const void* x1, int C1, cons
   p.partial = partial;
   p.bias_partial = bias_partial;
   const int grid = pl.units < num_sms() ? pl.units : num_sms();
-  kern<<<grid, 192, Cfg::kSmemBytes, st>>>(tmX0, tmX1, tmDZ, p);
+  kern<<<grid, 256, Cfg::kSmemBytes, st>>>(tmX0, tmX1, tmDZ, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(B2U_ERR_CUDA, "conv_wgrad launch: %s", cudaGetErrorString(e));
   note_launch();

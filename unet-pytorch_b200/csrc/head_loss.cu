@@ -256,7 +256,8 @@ loss_stats_kernel(const float* __restrict__ logits, const long long* __restrict_
 // Label-map variant (the training loop's case): only P_c and Pf_c need a per-class register; the three sums that
 // involve the pixel's own class (tp, T, tpf) go to per-warp shared-memory tables.  tp is accumulated in 2^-32
 // fixed point so the result does not depend on the order in which lanes reach the table.
-__global__ void __launch_bounds__(kLossThreads)
+template <int CM>
+__global__ void __launch_bounds__(kLossThreads, 2)
 loss_stats_map_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
                       const float* __restrict__ cls_w, double* __restrict__ partial, long long HW, long long P, int C,
                       float focal_alpha, float focal_gamma, float thr) {
@@ -272,9 +273,9 @@ loss_stats_map_kernel(const float* __restrict__ logits, const long long* __restr
   }
   __syncthreads();
   float a_ce = 0.f, a_w = 0.f, a_focal = 0.f, a_cnt = 0.f;
-  float Ps[kMaxCls], Pf[kMaxCls];
+  float Ps[CM], Pf[CM];
 #pragma unroll
-  for (int c = 0; c < kMaxCls; ++c) { Ps[c] = Pf[c] = 0.f; }
+  for (int c = 0; c < CM; ++c) { Ps[c] = Pf[c] = 0.f; }
 
   // warp-uniform loop (every lane stays in it, `inb` guards the tail) so the class-wise aggregation below can use
   // full-warp collectives
@@ -285,20 +286,20 @@ loss_stats_map_kernel(const float* __restrict__ logits, const long long* __restr
     const long long pc_ = inb ? p : P - 1;
     const long long n = pc_ / HW, hw = pc_ % HW;
     const float* z = logits + n * C * HW + hw;
-    float v[kMaxCls];
+    float v[CM];
     float m = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < kMaxCls; ++c) if (c < C) { v[c] = __ldg(z + c * HW); m = fmaxf(m, v[c]); }
+    for (int c = 0; c < CM; ++c) if (c < C) { v[c] = __ldg(z + c * HW); m = fmaxf(m, v[c]); }
     const long long y = target[pc_];
     const bool valid = inb && y >= 0 && y < C;
     const float zy = valid ? __ldg(z + y * HW) : 0.f;
     float sum = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxCls; ++c) if (c < C) { v[c] = expf(v[c] - m); sum += v[c]; }
+    for (int c = 0; c < CM; ++c) if (c < C) { v[c] = expf(v[c] - m); sum += v[c]; }
     const float inv = 1.f / sum;
     if (inb) {
 #pragma unroll
-      for (int c = 0; c < kMaxCls; ++c) if (c < C) {
+      for (int c = 0; c < CM; ++c) if (c < C) {
         const float pc = v[c] * inv;
         Ps[c] += pc;
         Pf[c] += pc > thr ? 1.f : 0.f;
@@ -337,7 +338,7 @@ loss_stats_map_kernel(const float* __restrict__ logits, const long long* __restr
   };
   red(a_ce, 0); red(a_w, 1); red(a_focal, 2); red(a_cnt, 3);
 #pragma unroll
-  for (int c = 0; c < kMaxCls; ++c) if (c < C) { red(Ps[c], 4 + c); red(Pf[c], 4 + C + c); }
+  for (int c = 0; c < CM; ++c) if (c < C) { red(Ps[c], 4 + c); red(Pf[c], 4 + C + c); }
   __syncthreads();
   const int L = 5 * C + 4;
   double* out = partial + static_cast<size_t>(blockIdx.x) * L;
@@ -393,7 +394,7 @@ __global__ void loss_finalize_kernel(const double* __restrict__ partial, int blo
 
 // dlogits = g_ce * dCE/dz + g_focal * dFocal/dz + g_dice * dDice/dz   (coefficients from loss_finalize)
 // NHWC64: dlogits leave as bf16 [pixel][64] (channels >= C zero) = the dz operand of the tensor-core 1x1 dgrad/wgrad
-template <bool ONEHOT, bool NHWC64>
+template <bool ONEHOT, bool NHWC64, int CM>
 __global__ void __launch_bounds__(kLossThreads)
 loss_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ target, const float* __restrict__ onehot,
                 const float* __restrict__ cls_w, const float* __restrict__ fin, const float* __restrict__ gscale,
@@ -413,18 +414,18 @@ loss_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ 
   const long long n = p / HW, hw = p % HW;
   const float* z = logits + n * C * HW + hw;
   float* dzp = dlogits + n * C * HW + hw;
-  float v[kMaxCls];
+  float v[CM];
   float m = -INFINITY;
 #pragma unroll
-  for (int c = 0; c < kMaxCls; ++c) if (c < C) { v[c] = __ldg(z + c * HW); m = fmaxf(m, v[c]); }
+  for (int c = 0; c < CM; ++c) if (c < C) { v[c] = __ldg(z + c * HW); m = fmaxf(m, v[c]); }
   const long long y = target ? target[p] : -1;
   const bool valid = target && y >= 0 && y < C;
   float zy = 0.f;
 #pragma unroll
-  for (int c = 0; c < kMaxCls; ++c) if (c < C) { if (valid && c == y) zy = v[c]; }
+  for (int c = 0; c < CM; ++c) if (c < C) { if (valid && c == y) zy = v[c]; }
   float sum = 0.f;
 #pragma unroll
-  for (int c = 0; c < kMaxCls; ++c) if (c < C) { v[c] = expf(v[c] - m); sum += v[c]; }
+  for (int c = 0; c < CM; ++c) if (c < C) { v[c] = expf(v[c] - m); sum += v[c]; }
   const float inv = 1.f / sum;
   // per-pixel scalar multiplying (p - onehot_y): CE and focal share the direction
   float k_py = 0.f;
@@ -444,18 +445,18 @@ loss_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ 
   }
   // dice: g_c = A_c t_c + B_c ; ddice/dz_k = p_k (g_k - sum_c g_c p_c)
   float gdot = 0.f;
-  float t[kMaxCls];
+  float t[CM];
   if (g_dice != 0.f) {
 #pragma unroll
-    for (int c = 0; c < kMaxCls; ++c) if (c < C) {
+    for (int c = 0; c < CM; ++c) if (c < C) {
       if (ONEHOT) t[c] = __ldg(onehot + p * (C + 1) + c);
       else t[c] = (y == c) ? 1.f : 0.f;
       gdot += (sA[c] * t[c] + sB[c]) * (v[c] * inv);
     }
   }
-  float dv[kMaxCls];
+  float dv[CM];
 #pragma unroll
-  for (int c = 0; c < kMaxCls; ++c) {
+  for (int c = 0; c < CM; ++c) {
     float d = 0.f;
     if (c < C) {
       const float pc = v[c] * inv;
@@ -472,18 +473,19 @@ loss_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ 
     // warp-private shared-memory tile and leave as fully coalesced 512-byte stores.
     __shared__ uint4 tile[kLossThreads / 32][32][9];          // [warp][pixel][8 + 1 pad]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float lo[kMaxCls];
+    float lo[CM];
 #pragma unroll
-    for (int c = 0; c < kMaxCls; ++c) lo[c] = dv[c] - __bfloat162float(__float2bfloat16_rn(dv[c]));
+    for (int c = 0; c < CM; ++c) lo[c] = dv[c] - __bfloat162float(__float2bfloat16_rn(dv[c]));
 #pragma unroll
     for (int q = 0; q < kMaxCls / 8; ++q) {
-      uint4 r;
-      r.x = pack_bf16x2(dv[q * 8 + 0], dv[q * 8 + 1]); r.y = pack_bf16x2(dv[q * 8 + 2], dv[q * 8 + 3]);
-      r.z = pack_bf16x2(dv[q * 8 + 4], dv[q * 8 + 5]); r.w = pack_bf16x2(dv[q * 8 + 6], dv[q * 8 + 7]);
+      uint4 r = make_uint4(0u, 0u, 0u, 0u), l = make_uint4(0u, 0u, 0u, 0u);
+      if (q * 8 < CM) {       // classes >= CM (>= C) are zero columns
+        r.x = pack_bf16x2(dv[q * 8 + 0], dv[q * 8 + 1]); r.y = pack_bf16x2(dv[q * 8 + 2], dv[q * 8 + 3]);
+        r.z = pack_bf16x2(dv[q * 8 + 4], dv[q * 8 + 5]); r.w = pack_bf16x2(dv[q * 8 + 6], dv[q * 8 + 7]);
+        l.x = pack_bf16x2(lo[q * 8 + 0], lo[q * 8 + 1]); l.y = pack_bf16x2(lo[q * 8 + 2], lo[q * 8 + 3]);
+        l.z = pack_bf16x2(lo[q * 8 + 4], lo[q * 8 + 5]); l.w = pack_bf16x2(lo[q * 8 + 6], lo[q * 8 + 7]);
+      }
       tile[warp][lane][q] = r;
-      uint4 l;
-      l.x = pack_bf16x2(lo[q * 8 + 0], lo[q * 8 + 1]); l.y = pack_bf16x2(lo[q * 8 + 2], lo[q * 8 + 3]);
-      l.z = pack_bf16x2(lo[q * 8 + 4], lo[q * 8 + 5]); l.w = pack_bf16x2(lo[q * 8 + 6], lo[q * 8 + 7]);
       tile[warp][lane][kMaxCls / 8 + q] = l;
     }
     __syncwarp();
@@ -593,12 +595,17 @@ int b2u_loss_fwd(const float* logits, const long long* target, const float* oneh
   long long want = (P + kLossThreads - 1) / kLossThreads;
   const int blocks = static_cast<int>(want < kLossBlocks ? want : kLossBlocks);
   const size_t sm = static_cast<size_t>(L) * (kLossThreads / 32) * sizeof(double);
-  if (onehot)
+  if (onehot) {
     loss_stats_kernel<true><<<blocks, kLossThreads, sm, st>>>(logits, target, onehot, cls_w, static_cast<double*>(ws), HW, P, C,
                                                               focal_alpha, focal_gamma, thr);
-  else
-    loss_stats_map_kernel<<<blocks, kLossThreads, static_cast<size_t>(2 * C + 4) * (kLossThreads / 32) * sizeof(double), st>>>(
-        logits, target, cls_w, static_cast<double*>(ws), HW, P, C, focal_alpha, focal_gamma, thr);
+  } else {
+    // class loops are unrolled to the smallest bucket >= C (a runtime bound would run all 32 predicated iterations)
+    const size_t smm = static_cast<size_t>(2 * C + 4) * (kLossThreads / 32) * sizeof(double);
+#define B2U_STATS(CM_) loss_stats_map_kernel<CM_><<<blocks, kLossThreads, smm, st>>>( \
+        logits, target, cls_w, static_cast<double*>(ws), HW, P, C, focal_alpha, focal_gamma, thr)
+    if (C <= 8) B2U_STATS(8); else if (C <= 16) B2U_STATS(16); else if (C <= 24) B2U_STATS(24); else B2U_STATS(32);
+#undef B2U_STATS
+  }
   B2U_CHECK_LAUNCH("loss_stats");
   loss_finalize_kernel<<<1, 128, L * sizeof(double), st>>>(static_cast<const double*>(ws), blocks, C, beta, smooth, out, stats);
   B2U_CHECK_LAUNCH("loss_finalize");
@@ -616,15 +623,19 @@ int b2u_loss_bwd(const float* logits, const long long* target, const float* oneh
   const long long HW = static_cast<long long>(H) * W, P = HW * N;
   const unsigned blocks = static_cast<unsigned>((P + kLossThreads - 1) / kLossThreads);
   float* out = static_cast<float*>(dlogits);
+#define B2U_LBWD(OH_, NH_, CM_) loss_bwd_kernel<OH_, NH_, CM_><<<blocks, kLossThreads, 0, st>>>( \
+      logits, target, onehot, cls_w, fin, gscale, out, HW, P, C, focal_alpha, focal_gamma)
+#define B2U_LBWD_C(OH_, NH_) do { if (C <= 8) B2U_LBWD(OH_, NH_, 8); else if (C <= 16) B2U_LBWD(OH_, NH_, 16); \
+                                  else if (C <= 24) B2U_LBWD(OH_, NH_, 24); else B2U_LBWD(OH_, NH_, 32); } while (0)
   if (out_mode == 1) {
-    if (onehot) loss_bwd_kernel<true, true><<<blocks, kLossThreads, 0, st>>>(logits, target, onehot, cls_w, fin, gscale, out, HW, P, C, focal_alpha, focal_gamma);
-    else        loss_bwd_kernel<false, true><<<blocks, kLossThreads, 0, st>>>(logits, target, onehot, cls_w, fin, gscale, out, HW, P, C, focal_alpha, focal_gamma);
+    if (onehot) B2U_LBWD_C(true, true); else B2U_LBWD_C(false, true);
   } else if (out_mode == 0) {
-    if (onehot) loss_bwd_kernel<true, false><<<blocks, kLossThreads, 0, st>>>(logits, target, onehot, cls_w, fin, gscale, out, HW, P, C, focal_alpha, focal_gamma);
-    else        loss_bwd_kernel<false, false><<<blocks, kLossThreads, 0, st>>>(logits, target, onehot, cls_w, fin, gscale, out, HW, P, C, focal_alpha, focal_gamma);
+    if (onehot) B2U_LBWD_C(true, false); else B2U_LBWD_C(false, false);
   } else {
     return set_error(B2U_ERR_ARG, "loss_bwd: out_mode must be 0 or 1");
   }
+#undef B2U_LBWD_C
+#undef B2U_LBWD
   B2U_CHECK_LAUNCH("loss_bwd");
   return 0;
 }

@@ -131,6 +131,8 @@ class UNetEngine:
         # The wgrad kernel can produce db in the same pass (an N=16 MMA against a ones tile); measured on B200 it costs
         # more than the separate HBM-bound column-sum kernel (work units with the extra MMAs become the stragglers of
         # the static schedule: +40 % wgrad time vs +1.2 ms for bias_grad), so it is off by default.
+        # db from the wgrad kernel's bias warps (3x3 layers) instead of a separate pass over dz: an A/B on one box
+        # (scripts/ab_fuse_bias.py: 23.2-23.9 vs 23.4-23.5 ms/step) shows no gain, so the separate pass stays the default
         self.fuse_bias_grad = False
         self._pack_key = self._pack_versions = self._pack_table = None
         self._pack_total = 0
@@ -395,7 +397,7 @@ class UNetEngine:
                 return dz
             wn, bn_ = c.name + ".weight", c.name + ".bias"
             want_w, want_b = has(wn), has(bn_)
-            fuse_b = want_w and want_b and self.fuse_bias_grad and not c.padded and not c.bn
+            fuse_b = want_w and want_b and self.fuse_bias_grad and not c.padded and not c.bn and not c.first
             taps = 1 if c.first else 9
             if want_w:
                 ctot_p = 64 if c.first else c.c0_p + c.c1_p

@@ -221,6 +221,9 @@ class GraphEngine:
         self.saved = None
         self.has_stem = any(i["op"] == "stem" for i in program)
         self.dropout_override = None
+        # db from the wgrad kernel's bias warps instead of a separate pass over dz: measured on one box (scripts/ab_fuse_bias.py)
+        # it does not change the step time (the extra smem reads slow the bias-owning work units), so it stays off
+        self.fuse_bias_grad = False
         readers = {}
         for i in program:
             for key in ("x", "x1", "z", "res", "a", "b"):
@@ -673,11 +676,15 @@ class GraphEngine:
                 xw = t.aux if (ins["stride"] == 2 and taps == 1) else xin.data          # wgrad's activation operand
                 c0p = xw.shape[3]
                 c1p = x1.data.shape[3] if x1 else 0
+                # 3x3 layers with a live bias: db comes out of the wgrad kernel (its bias warp sums the staged dz tiles)
+                fused_db = (self.fuse_bias_grad and has(ins["w"]) and has(ins["bias"]) and taps == 9 and ins["out"] not in self._pre_bn
+                            and coutp == cout and c0p == c0r and c1p == c1r)
                 if has(ins["w"]):
                     need = ops.lib().b2u_conv_wgrad_workspace(dz.shape[0], dz.shape[1], dz.shape[2], c0p + c1p, coutp, taps)
                     ws = self._workspace("wgrad", need)
                     if coutp == cout and c0p == c0r and c1p == c1r:
-                        ops.conv_wgrad(xw, dz, taps=taps, x1=x1.data if x1 else None, dw=grads[ins["w"]], ws=ws)
+                        ops.conv_wgrad(xw, dz, taps=taps, x1=x1.data if x1 else None, dw=grads[ins["w"]], ws=ws,
+                                       db=grads[ins["bias"]] if fused_db else None)
                     else:       # padded operands: gradient of the padded weight, then keep the real rows/columns
                         k = 3 if taps == 9 else 1
                         tmp = self._buf("dw:" + ins["w"], (coutp, c0p + c1p, k, k), torch.float32)
@@ -690,7 +697,7 @@ class GraphEngine:
                     # a bias in front of BatchNorm: the BN backward's dz sums to zero over the batch exactly, so the
                     # gradient is 0 (the reference's autograd returns fp32 cancellation residue ~1e-8)
                     grads[ins["bias"]].zero_()
-                elif has(ins["bias"]):
+                elif has(ins["bias"]) and not fused_db:
                     wsb = self._workspace("bias", ops.lib().b2u_bias_grad_workspace(coutp))
                     if coutp == cout:
                         ops.bias_grad(dz, db=grads[ins["bias"]], ws=wsb)
