@@ -182,6 +182,10 @@ int b2u_head_fwd_tc(const void* x, const void* wf, const float* bias, float* log
                     void* stream);
 /* per-pixel class decision of the inference loop (unet.py:246-250: argmax(softmax(z)) == argmax(z)) */
 int b2u_argmax_u8(const float* logits, unsigned char* mask, int N, int C, int H, int W, void* stream);
+/* the predictor's tail (unet.py:135-148, 324-340): softmax, crop of the letterbox bars (cy, cx, ch, cw), cv2.resize(...,
+ * INTER_LINEAR) of the probabilities to oh x ow, argmax -> uint8 mask [N][oh][ow]; nothing but the mask leaves the GPU */
+int b2u_softmax_resize_argmax_u8(const float* logits, unsigned char* mask, int N, int C, int H, int W, int cy, int cx,
+                                 int ch, int cw, int oh, int ow, void* stream);
 /* fast_hist (utils/utils_metrics.py:34-43): hist (n*n+1 uint64, accumulated) ; dtype 0=u8 1=i32 2=i64 */
 int b2u_fast_hist(const void* a, const void* b, long long len, int n, int dtype, unsigned long long* hist, void* stream);
 

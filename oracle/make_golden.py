@@ -235,6 +235,41 @@ def lightweight_case(tag, num_classes, n, h, w, seed, cls_w, dice, focal):
     print("lightweight", tag, "loss", loss.item(), "f_score", fs)
 
 
+def predictor_case():
+    """The reference's predictor class (unet.py::Unet, CPU) on a seeded non-square RGB image: get_miou_png's class map at
+    the original size (letterbox -> net -> softmax -> crop -> cv2.resize INTER_LINEAR -> argmax) and the top-2 probability
+    margin per pixel (random-init logits are near-tied in places; the GPU test scores confident pixels)."""
+    import contextlib, io, tempfile
+    import cv2
+    from PIL import Image
+    import unet as ref_unet_module
+    C = 21
+    sd = O.make_predictor_params(C, seed=11)
+    g = torch.Generator().manual_seed(41)
+    low = torch.rand(1, 3, 10, 14, generator=g)
+    img = (torch.nn.functional.interpolate(low, size=(300, 420), mode="bilinear", align_corners=False)[0] * 255).round().byte()
+    img = img.permute(1, 2, 0).contiguous().numpy()                    # H x W x 3 uint8
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "w.pth")
+        torch.save(sd, path)
+        with contextlib.redirect_stdout(io.StringIO()):
+            pred = ref_unet_module.Unet(model_path=path, num_classes=C, backbone="vgg", input_shape=[256, 256], mix_type=1, cuda=False)
+            mask = np.array(pred.get_miou_png(Image.fromarray(img)))
+            seg = np.array(pred.detect_image(Image.fromarray(img)))
+        # the probabilities the reference arg-maxes, for the margin map (same steps as unet.py:324-336)
+        boxed, nw, nh = ref_unet_module.resize_image(Image.fromarray(img), (256, 256))
+        data = np.expand_dims(np.transpose(np.array(boxed, np.float32) / 255.0, (2, 0, 1)), 0)
+        with torch.no_grad():
+            pr = torch.softmax(pred.net(torch.from_numpy(data))[0].permute(1, 2, 0), dim=-1).numpy()
+        pr = pr[(256 - nh) // 2:(256 - nh) // 2 + nh, (256 - nw) // 2:(256 - nw) // 2 + nw]
+        pr = cv2.resize(pr, (420, 300), interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(pr.argmax(-1), mask)
+        top2 = np.sort(pr, axis=-1)[..., -2:]
+    np.savez_compressed(os.path.join(OUT, "predictor_vgg_nc21.npz"), image=img, mask=mask.astype(np.uint8), seg=seg.astype(np.uint8),
+                        margin=(top2[..., 1] - top2[..., 0]).astype(np.float16), meta=np.asarray([C, 256, 256]))
+    print("predictor ok", mask.shape, np.bincount(mask.reshape(-1), minlength=C)[:8])
+
+
 def checkpoint_case():
     """The reference's own trained checkpoint (Submit_result/model.pth = UltraLightweightUnet_large_optimized, 4 classes,
     all keys match) in eval mode on a seeded input: trained BatchNorm statistics make this a well-conditioned fixture
@@ -319,5 +354,6 @@ if __name__ == "__main__":
     lightweight_case("nc4_focaldice", 4, 2, 64, 64, 12, [1, 15, 1.5, 2], dice=True, focal=True)
     lightweight_case("nc21_cedice", 21, 2, 64, 96, 13, [1] * 21, dice=True, focal=False)
     checkpoint_case()
+    predictor_case()
     loss_case()
     hist_case()

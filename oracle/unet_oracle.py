@@ -810,3 +810,62 @@ def lw_train_step(sd, imgs, pngs, cls_weights, num_classes, dice=True, focal=Fal
     names = [k for k, v in p.items() if v.requires_grad]
     grads = torch.autograd.grad(loss, [p[k] for k in names])
     return loss.detach(), logits.detach(), dict(zip(names, grads)), stats
+
+
+# ----------------------------------------------------------------------------------------------- predictor (unet.py)
+def make_predictor_params(num_classes, seed=11):
+    """make_params with the classifier scaled x150: random-init logits are all ~0 (every class at 1/C), which would make the
+    predictor's argmax a coin flip; the scaled head yields confident, multi-class maps (77 % of pixels with a top-2
+    probability margin > 0.02 on the fixture image)."""
+    p = make_params(num_classes, seed=seed)
+    p["final.weight"] = p["final.weight"] * 150.0
+    return p
+
+
+def letterbox(img_u8, input_shape):
+    """cvtColor + resize_image (utils/utils.py:12-34): BICUBIC resize that keeps the aspect ratio, pasted on a grey canvas.
+    img_u8: H x W x 3 uint8.  Returns (float32 1x3xHxW in [0,1], nw, nh)."""
+    from PIL import Image
+    image = Image.fromarray(img_u8)
+    iw, ih = image.size
+    h, w = input_shape
+    scale = min(w / iw, h / ih)
+    nw, nh = int(iw * scale), int(ih * scale)
+    canvas = Image.new("RGB", (w, h), (128, 128, 128))
+    canvas.paste(image.resize((nw, nh), Image.BICUBIC), ((w - nw) // 2, (h - nh) // 2))
+    data = np.transpose(np.array(canvas, np.float32) / 255.0, (2, 0, 1))[None]
+    return torch.from_numpy(data), nw, nh
+
+
+def resize_linear_cv2(pr, out_h, out_w):
+    """cv2.resize(pr, (out_w, out_h), interpolation=cv2.INTER_LINEAR) for float32 H x W x C (unet.py:144, 336):
+    f = (d + 0.5) * in / out - 0.5, s = floor(f), f -= s; s < 0 -> (0, 0); s >= in - 1 -> (in - 1, 0)."""
+    pr = np.asarray(pr, np.float32)
+    ih, iw = pr.shape[:2]
+
+    def taps(n_out, n_in):
+        f = (np.arange(n_out, dtype=np.float32) + np.float32(0.5)) * np.float32(n_in / n_out) - np.float32(0.5)
+        s = np.floor(f).astype(np.int64)
+        f = (f - s).astype(np.float32)
+        lo = s < 0
+        s[lo] = 0; f[lo] = 0
+        hi = s >= n_in - 1
+        s[hi] = n_in - 1; f[hi] = 0
+        return s, np.minimum(s + 1, n_in - 1), f
+    y0, y1, fy = taps(out_h, ih)
+    x0, x1, fx = taps(out_w, iw)
+    fy = fy[:, None, None]; fx = fx[None, :, None]
+    top = pr[y0][:, x0] * (1 - fx) + pr[y0][:, x1] * fx
+    bot = pr[y1][:, x0] * (1 - fx) + pr[y1][:, x1] * fx
+    return top * (1 - fy) + bot * fy
+
+
+def predictor_mask(params, img_u8, input_shape):
+    """Unet.get_miou_png (unet.py:298-344): the class map at the original image size."""
+    oh, ow = img_u8.shape[:2]
+    data, nw, nh = letterbox(img_u8, input_shape)
+    with torch.no_grad():
+        pr = torch.softmax(unet_forward(params, data)[0].permute(1, 2, 0), dim=-1).numpy()
+    top, left = (input_shape[0] - nh) // 2, (input_shape[1] - nw) // 2
+    pr = resize_linear_cv2(pr[top:top + nh, left:left + nw], oh, ow)
+    return pr.argmax(-1).astype(np.uint8), pr

@@ -566,3 +566,22 @@ def test_head_forward_on_tensor_cores(b2u, cuda_device, N, H, W, C):
     assert rel(out, ref) <= 2e-5          # fp32 accumulation of bf16 x (exact products) and ~2^-17 weights
     simt = ops.head_fwd(xd, w.to(dev), b.to(dev))
     assert rel(out, simt) <= 2e-5
+
+
+@pytest.mark.parametrize("C,H,W,crop,out", [(21, 64, 64, (8, 0, 48, 64), (90, 120)), (2, 32, 48, (0, 6, 32, 36), (17, 19)),
+                                            (4, 16, 16, (0, 0, 16, 16), (16, 16)), (32, 24, 24, (2, 3, 20, 18), (61, 47))])
+def test_softmax_resize_argmax_kernel(b2u, cuda_device, C, H, W, crop, out):
+    """softmax -> crop -> cv2-style INTER_LINEAR resize -> argmax in one kernel against the oracle's numpy restatement
+    (itself pinned to cv2 through the reference predictor's golden mask)."""
+    from unet_pytorch_b200 import ops
+    g = torch.Generator().manual_seed(C + H)
+    logits = torch.randn(2, C, H, W, generator=g) * 3
+    cy, cx, ch, cw = crop
+    got = ops.softmax_resize_argmax_u8(logits.to(cuda_device), crop, out).cpu().numpy()
+    for n in range(2):
+        pr = torch.softmax(logits[n].permute(1, 2, 0), dim=-1).numpy()[cy:cy + ch, cx:cx + cw]
+        ref = O.resize_linear_cv2(pr, out[0], out[1])
+        top2 = np.sort(ref, axis=-1)[..., -2:]
+        confident = (top2[..., 1] - top2[..., 0]) > 1e-4
+        assert (got[n] == ref.argmax(-1))[confident].all()
+        assert (got[n] == ref.argmax(-1)).mean() >= 0.999

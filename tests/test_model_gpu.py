@@ -607,3 +607,29 @@ def test_lightweight_trainer_and_freeze(b2u, cuda_device):
     assert all(p.grad is not None for k, p in model.named_parameters() if not k.startswith("backbone."))
     with pytest.raises(ValueError):
         b2u.LightweightUnet(num_classes=C, backbone="vgg")
+
+
+def test_predictor_class_against_reference(b2u, cuda_device, golden_dir):
+    """unet.py::Unet drop-in (detect_image / get_miou_png / get_FPS) against the mask the reference's own predictor class
+    produced for the same image and weights.  Agreement is scored on pixels whose reference top-2 probability margin
+    exceeds 0.02 (77 % of the image; >= 99.9 % must match) and overall (>= 97 %)."""
+    from PIL import Image
+    from unet_pytorch_b200.unet import Unet as Predictor
+    g = np.load(os.path.join(golden_dir, "predictor_vgg_nc21.npz"))
+    C, ih, iw = [int(v) for v in g["meta"]]
+    pred = Predictor(state_dict=O.make_predictor_params(C, seed=11), num_classes=C, backbone="vgg", input_shape=[ih, iw], mix_type=1)
+    image = Image.fromarray(g["image"])
+    mask = np.array(pred.get_miou_png(image))
+    assert mask.shape == g["mask"].shape and mask.dtype == np.uint8
+    agree = mask == g["mask"]
+    margin = g["margin"].astype(np.float32)
+    assert agree[margin > 0.02].mean() >= 0.999
+    assert agree.mean() >= 0.97
+    seg = np.array(pred.detect_image(image))
+    assert seg.shape == g["seg"].shape
+    assert (seg == g["seg"]).all(axis=-1)[margin > 0.02].mean() >= 0.999
+    pred.mix_type = 0
+    assert pred.detect_image(image).size == image.size
+    assert pred.get_FPS(image, 3) > 0
+    with pytest.raises(RuntimeError):
+        Predictor(state_dict=O.make_params(C, seed=11), num_classes=C, cuda=False)

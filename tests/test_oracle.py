@@ -249,3 +249,16 @@ def test_lightweight_unet_matches_reference_golden(golden_dir, tag):
         ev, _ = O.lw_forward(sd_after, imgs, training=False)
     ref_ev = torch.from_numpy(g["logits_eval"])
     assert ((ev - ref_ev).norm() / ref_ev.norm()).item() <= 1e-5
+
+
+def test_predictor_tail_matches_reference(golden_dir):
+    """unet.py::Unet.get_miou_png (letterbox, forward, softmax, crop, cv2 INTER_LINEAR resize, argmax) restated without cv2."""
+    g = np.load(os.path.join(golden_dir, "predictor_vgg_nc21.npz"))
+    C, ih, iw = [int(v) for v in g["meta"]]
+    mask, pr = O.predictor_mask(O.make_predictor_params(C, seed=11), g["image"], (ih, iw))
+    assert mask.shape == g["mask"].shape
+    agree = (mask == g["mask"])
+    confident = g["margin"].astype(np.float32) > 1e-3
+    assert agree[confident].all() and agree.mean() >= 0.9999
+    top2 = np.sort(pr, axis=-1)[..., -2:]
+    assert np.abs((top2[..., 1] - top2[..., 0]) - g["margin"].astype(np.float32)).max() <= 2e-3      # fp16-stored margins

@@ -534,6 +534,52 @@ __global__ void argmax_u8_kernel(const float* __restrict__ logits, uint8_t* __re
   mask[p] = static_cast<uint8_t>(arg);
 }
 
+// Inference tail of the reference's predictor (unet.py:135-148, 324-340): softmax over classes, crop of the letterbox
+// bars, cv2.resize(pr, (w, h), INTER_LINEAR) of the probabilities back to the original image size, argmax -- fused:
+// one thread per output pixel interpolates the softmax of its 4 source pixels and keeps the best class, so only a
+// uint8 mask ever leaves the GPU.  cv2's float INTER_LINEAR: f = (d + 0.5) * in/out - 0.5, s = floor(f), f -= s;
+// s < 0 -> (s, f) = (0, 0); s >= in - 1 -> (s, f) = (in - 1, 0) (second tap clamped).
+template <int CM>
+__global__ void __launch_bounds__(128)
+softmax_resize_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask, int C, int H, int W, int cy,
+                             int cx, int ch, int cw, int oh, int ow, float sy, float sx) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, n = blockIdx.z;
+  if (x >= ow) return;
+  float fy = (y + 0.5f) * sy - 0.5f, fx = (x + 0.5f) * sx - 0.5f;
+  int y0 = static_cast<int>(floorf(fy)), x0 = static_cast<int>(floorf(fx));
+  fy -= y0; fx -= x0;
+  if (y0 < 0) { y0 = 0; fy = 0.f; }
+  if (y0 >= ch - 1) { y0 = ch - 1; fy = 0.f; }
+  if (x0 < 0) { x0 = 0; fx = 0.f; }
+  if (x0 >= cw - 1) { x0 = cw - 1; fx = 0.f; }
+  const int y1 = y0 + 1 < ch ? y0 + 1 : ch - 1, x1 = x0 + 1 < cw ? x0 + 1 : cw - 1;
+  const size_t plane = static_cast<size_t>(H) * W;
+  const float* base = logits + static_cast<size_t>(n) * C * plane;
+  const size_t o[4] = {static_cast<size_t>(cy + y0) * W + cx + x0, static_cast<size_t>(cy + y0) * W + cx + x1,
+                       static_cast<size_t>(cy + y1) * W + cx + x0, static_cast<size_t>(cy + y1) * W + cx + x1};
+  const float wgt[4] = {(1.f - fy) * (1.f - fx), (1.f - fy) * fx, fy * (1.f - fx), fy * fx};
+  float acc[CM];
+#pragma unroll
+  for (int c = 0; c < CM; ++c) acc[c] = 0.f;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    float v[CM];
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < CM; ++c) if (c < C) { v[c] = __ldg(base + c * plane + o[t]); m = fmaxf(m, v[c]); }
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < CM; ++c) if (c < C) { v[c] = expf(v[c] - m); sum += v[c]; }
+    const float k = wgt[t] / sum;
+#pragma unroll
+    for (int c = 0; c < CM; ++c) if (c < C) acc[c] = fmaf(k, v[c], acc[c]);
+  }
+  float best = acc[0]; int arg = 0;
+#pragma unroll
+  for (int c = 1; c < CM; ++c) if (c < C && acc[c] > best) { best = acc[c]; arg = c; }
+  mask[(static_cast<size_t>(n) * oh + y) * ow + x] = static_cast<uint8_t>(arg);
+}
+
 }  // namespace b2u
 
 extern "C" {
@@ -659,6 +705,23 @@ int b2u_argmax_u8(const float* logits, unsigned char* mask, int N, int C, int H,
   const long long HW = static_cast<long long>(H) * W, P = HW * N;
   argmax_u8_kernel<<<static_cast<unsigned>((P + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, mask, HW, P, C);
   B2U_CHECK_LAUNCH("argmax_u8");
+  return 0;
+}
+
+// logits [N][C][H][W] fp32; crop (cy, cx, ch, cw) inside H x W; mask [N][oh][ow] uint8 (class index, lowest on ties)
+int b2u_softmax_resize_argmax_u8(const float* logits, unsigned char* mask, int N, int C, int H, int W, int cy, int cx,
+                                 int ch, int cw, int oh, int ow, void* stream) {
+  if (N <= 0 || C <= 0 || C > kMaxCls || H <= 0 || W <= 0 || oh <= 0 || ow <= 0 || N > 65535 || oh > 65535)
+    return set_error(B2U_ERR_SHAPE, "softmax_resize_argmax: bad shape");
+  if (cy < 0 || cx < 0 || ch <= 0 || cw <= 0 || cy + ch > H || cx + cw > W)
+    return set_error(B2U_ERR_SHAPE, "softmax_resize_argmax: crop outside the logits");
+  const float sy = static_cast<float>(static_cast<double>(ch) / oh), sx = static_cast<float>(static_cast<double>(cw) / ow);
+  const dim3 grid((ow + 127) / 128, oh, N);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define B2U_SRA(CM_) softmax_resize_argmax_kernel<CM_><<<grid, 128, 0, st>>>(logits, mask, C, H, W, cy, cx, ch, cw, oh, ow, sy, sx)
+  if (C <= 8) B2U_SRA(8); else if (C <= 16) B2U_SRA(16); else if (C <= 24) B2U_SRA(24); else B2U_SRA(32);
+#undef B2U_SRA
+  B2U_CHECK_LAUNCH("softmax_resize_argmax");
   return 0;
 }
 

@@ -570,6 +570,18 @@ def argmax_u8(logits, out=None):
     return out
 
 
+def softmax_resize_argmax_u8(logits, crop, out_size, out=None):
+    """argmax(cv2.resize(softmax(logits)[crop], out_size, INTER_LINEAR)) as a uint8 mask; crop = (y, x, h, w)."""
+    _req(logits, torch.float32, "logits")
+    N, C, H, W = logits.shape
+    cy, cx, ch, cw = crop
+    oh, ow = out_size
+    if out is None:
+        out = torch.empty((N, oh, ow), dtype=torch.uint8, device=logits.device)
+    check(lib().b2u_softmax_resize_argmax_u8(ptr(logits), ptr(out), N, C, H, W, cy, cx, ch, cw, oh, ow, stream_ptr()))
+    return out
+
+
 _HIST_DTYPES = {torch.uint8: 0, torch.int32: 1, torch.int64: 2}
 
 

@@ -1,0 +1,141 @@
+"""Drop-in for the reference's predictor class `unet.py::Unet` (lines 19-357): same keyword configuration
+(`model_path`, `num_classes`, `backbone`, `input_shape`, `mix_type`, `cuda`), same `detect_image`, `get_FPS`,
+`get_miou_png` results -- with the per-frame tail moved onto the GPU.
+
+Reference per frame: logits -> softmax -> .cpu().numpy() (H x W x C fp32, 22 MB at C = 21, 512^2) -> crop of the letterbox
+bars -> cv2.resize of the probabilities to the original size -> argmax (unet.py:131-148).  Here: logits stay on the device,
+one kernel (`b2u_softmax_resize_argmax_u8`) does softmax + crop + INTER_LINEAR resize + argmax, and a uint8 mask (1 byte
+per pixel) is the only thing copied back.  Host-side image handling (RGB conversion, BICUBIC letterbox with grey bars,
+colour blending) follows utils/utils.py:12-34 and unet.py:150-203 with PIL/numpy, as in the reference."""
+import colorsys
+import copy
+import time
+
+import numpy as np
+import torch
+from PIL import Image
+
+from . import ops
+from .nets.unet import Unet as unet
+
+_VOC_COLORS = [(0, 0, 0), (128, 0, 0), (0, 128, 0), (128, 128, 0), (0, 0, 128), (128, 0, 128), (0, 128, 128),
+               (128, 128, 128), (64, 0, 0), (192, 0, 0), (64, 128, 0), (192, 128, 0), (64, 0, 128), (192, 0, 128),
+               (64, 128, 128), (192, 128, 128), (0, 64, 0), (128, 64, 0), (0, 192, 0), (128, 192, 0), (0, 64, 128),
+               (128, 64, 12)]
+
+
+def cvtColor(image):                                   # utils/utils.py:12-17
+    if len(np.shape(image)) == 3 and np.shape(image)[2] == 3:
+        return image
+    return image.convert("RGB")
+
+
+def resize_image(image, size):                         # utils/utils.py:22-34: undistorted resize onto a grey canvas
+    iw, ih = image.size
+    w, h = size
+    scale = min(w / iw, h / ih)
+    nw, nh = int(iw * scale), int(ih * scale)
+    canvas = Image.new("RGB", size, (128, 128, 128))
+    canvas.paste(image.resize((nw, nh), Image.BICUBIC), ((w - nw) // 2, (h - nh) // 2))
+    return canvas, nw, nh
+
+
+class Unet(object):
+    _defaults = {
+        "model_path": "model_data/unet_vgg_voc.pth",
+        "num_classes": 21,
+        "backbone": "vgg",
+        "input_shape": [512, 512],
+        "mix_type": 0,
+        "cuda": True,
+    }
+
+    def __init__(self, **kwargs):
+        self.__dict__.update(self._defaults)
+        self.state_dict = None                         # optional: weights passed in memory instead of model_path
+        for name, value in kwargs.items():
+            setattr(self, name, value)
+        if self.num_classes <= 21:
+            self.colors = list(_VOC_COLORS)
+        else:
+            hsv = [(x / self.num_classes, 1.0, 1.0) for x in range(self.num_classes)]
+            self.colors = [tuple(int(v * 255) for v in colorsys.hsv_to_rgb(*t)) for t in hsv]
+        self.generate()
+
+    def generate(self, onnx=False):                    # unet.py:86-98
+        if not self.cuda or not torch.cuda.is_available():
+            raise RuntimeError("the B200 predictor needs CUDA (cuda=True and a visible GPU); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.net = unet(num_classes=self.num_classes, backbone=self.backbone)
+        sd = self.state_dict if self.state_dict is not None else torch.load(self.model_path, map_location="cpu")
+        self.net.load_state_dict(sd)
+        self.net = self.net.eval().to(self.device)
+
+    # ------------------------------------------------------------------ shared pieces
+    def _letterbox(self, image):
+        image = cvtColor(image)
+        oh, ow = np.array(image).shape[:2]
+        boxed, nw, nh = resize_image(image, (self.input_shape[1], self.input_shape[0]))
+        data = np.expand_dims(np.transpose(np.array(boxed, np.float32) / 255.0, (2, 0, 1)), 0)     # preprocess_input
+        return image, torch.from_numpy(data), nw, nh, oh, ow
+
+    def _crop(self, nw, nh):
+        return (int((self.input_shape[0] - nh) // 2), int((self.input_shape[1] - nw) // 2), nh, nw)
+
+    def predict_mask(self, image):
+        """uint8 class map at the original image size (the `pr` of unet.py:148 / 340)."""
+        image, data, nw, nh, oh, ow = self._letterbox(image)
+        with torch.no_grad():
+            logits = self.net(data.to(self.device, non_blocking=True))
+            mask = ops.softmax_resize_argmax_u8(logits, self._crop(nw, nh), (oh, ow))
+        return image, mask[0].cpu().numpy()
+
+    # ------------------------------------------------------------------ reference API
+    def detect_image(self, image, count=False, name_classes=None):
+        old_img, pr = self.predict_mask(image)
+        old_img = copy.deepcopy(old_img)
+        oh, ow = pr.shape
+        if count:
+            classes_nums = np.zeros([self.num_classes])
+            total = oh * ow
+            print("-" * 63)
+            print("|%25s | %15s | %15s|" % ("Key", "Value", "Ratio"))
+            print("-" * 63)
+            for i in range(self.num_classes):
+                num = np.sum(pr == i)
+                if num > 0:
+                    print("|%25s | %15s | %14.2f%%|" % (str(name_classes[i]), str(num), num / total * 100))
+                    print("-" * 63)
+                classes_nums[i] = num
+            print("classes_nums:", classes_nums)
+        if self.mix_type == 0:
+            seg = np.reshape(np.array(self.colors, np.uint8)[np.reshape(pr, [-1])], [oh, ow, -1])
+            return Image.blend(old_img, Image.fromarray(np.uint8(seg)), 0.7)
+        if self.mix_type == 1:
+            seg = np.reshape(np.array(self.colors, np.uint8)[np.reshape(pr, [-1])], [oh, ow, -1])
+            return Image.fromarray(np.uint8(seg))
+        if self.mix_type == 2:
+            seg = (np.expand_dims(pr != 0, -1) * np.array(old_img, np.float32)).astype("uint8")
+            return Image.fromarray(np.uint8(seg))
+        return old_img
+
+    def get_FPS(self, image, test_interval):           # unet.py:205-258: forward + per-pixel class + crop, result on the host
+        _, data, nw, nh, _, _ = self._letterbox(image)
+        cy, cx, ch, cw = self._crop(nw, nh)
+        pinned = data.pin_memory()
+        host = torch.empty((1, ch, cw), dtype=torch.uint8).pin_memory()
+
+        def frame():
+            with torch.no_grad():
+                logits = self.net(pinned.to(self.device, non_blocking=True))
+                host.copy_(ops.argmax_u8(logits)[:, cy:cy + ch, cx:cx + cw], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        frame()
+        t1 = time.time()
+        for _ in range(test_interval):
+            frame()
+        return (time.time() - t1) / test_interval
+
+    def get_miou_png(self, image):                     # unet.py:298-344
+        _, pr = self.predict_mask(image)
+        return Image.fromarray(np.uint8(pr))
