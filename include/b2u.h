@@ -51,6 +51,10 @@ int b2u_nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, int H, int 
 int b2u_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int W, void* stream);
 /* same with the channel dimension zero-padded to Cpad (the 3-channel image feeding a 1x1 first conv) */
 int b2u_nchw_f32_to_nhwc_bf16_padded(const float* x, void* y, int N, int C, int H, int W, int Cpad, void* stream);
+/* device-side input pipeline: raw uint8 HWC image -> `preprocess_input` (/255) + CHW fp32 (utils/dataloader.py:41,
+ * utils/utils.py:64-66), uint8 label map -> int64 (dataloader.py:43); 4 B/pixel over PCIe instead of 20 */
+int b2u_u8hwc_to_nchw_f32(const unsigned char* x, float* y, int N, int H, int W, int C, float scale, void* stream);
+int b2u_u8_to_i64(const unsigned char* x, long long* y, long long n, void* stream);
 
 /* ---- tensor-core convolutions (tcgen05 implicit GEMM) ------------------------------------------------------ */
 /* y = [relu](conv(cat(x0, x1), w) + bias).  Replaces nn.Conv2d(k=3,p=1 | k=1)+ReLU (nets/vgg.py:53-57,

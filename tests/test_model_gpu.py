@@ -633,3 +633,26 @@ def test_predictor_class_against_reference(b2u, cuda_device, golden_dir):
     assert pred.get_FPS(image, 3) > 0
     with pytest.raises(RuntimeError):
         Predictor(state_dict=O.make_params(C, seed=11), num_classes=C, cuda=False)
+
+
+def test_device_input_pipeline_uint8(b2u, cuda_device):
+    """Raw uint8 NHWC images + uint8 label maps staged from pinned host memory give the same step as the fp32 NCHW / int64
+    batches the reference's dataloader would have produced from them on the host (utils/dataloader.py:41-43)."""
+    from unet_pytorch_b200 import ops
+    dev = cuda_device
+    C = 4
+    sd = O.make_params(C, seed=11)
+    g = torch.Generator().manual_seed(3)
+    raw = torch.randint(0, 256, (2, 64, 96, 3), generator=g, dtype=torch.uint8)
+    lab = torch.randint(0, C + 1, (2, 64, 96), generator=g).to(torch.uint8)
+    imgs = (raw.float() / 255.0).permute(0, 3, 1, 2).contiguous()           # preprocess_input + transpose on the host
+    conv = ops.u8hwc_to_nchw_f32(raw.to(dev))
+    assert torch.allclose(conv.cpu(), imgs, rtol=0, atol=1e-7)
+    assert torch.equal(ops.u8_to_i64(lab.to(dev)).cpu(), lab.long())
+    a = b2u.UnetTrainer(num_classes=C, device=dev, state_dict=sd, lr=0.0)
+    b = b2u.UnetTrainer(num_classes=C, device=dev, state_dict=sd, lr=0.0)
+    ra = a.train_step(imgs.to(dev), lab.long().to(dev)).cpu()
+    b.stage(raw.pin_memory(), lab.pin_memory())
+    rb = b.train_step().cpu()
+    assert torch.allclose(ra, rb, rtol=2e-3, atol=1e-5)
+    assert _global_rel(b.grads, {k: v.cpu() for k, v in a.grads.items()}) <= 5e-3

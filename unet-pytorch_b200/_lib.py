@@ -22,6 +22,8 @@ SIGNATURES = {
     "b2u_nhwc_bf16_to_nchw_f32": (I, [P, P, I, I, I, I, P]),
     "b2u_nchw_f32_to_nhwc_bf16": (I, [P, P, I, I, I, I, P]),
     "b2u_nchw_f32_to_nhwc_bf16_padded": (I, [P, P, I, I, I, I, I, P]),
+    "b2u_u8hwc_to_nchw_f32": (I, [P, P, I, I, I, I, F, P]),
+    "b2u_u8_to_i64": (I, [P, P, LL, P]),
     "b2u_conv_fprop": (I, [P, I, P, I, P, P, P, I, I, I, I, I, I, I, P]),
     "b2u_conv_dgrad": (I, [P, I, P, P, I, P, I, P, I, I, I, I, I, P]),
     "b2u_conv_wgrad_workspace": (SZ, [I, I, I, I, I, I]),

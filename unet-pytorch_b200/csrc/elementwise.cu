@@ -473,6 +473,27 @@ __global__ void resize_bilinear_f32_bwd_kernel(const float* __restrict__ dy, flo
 }
 
 // ---------------------------------------------------------------------------------------------
+// Device-side input pipeline: what the reference's dataloader does on the host before the H2D
+// copy -- `preprocess_input` (/255) + HWC->CHW transpose of the image (utils/dataloader.py:41, utils/utils.py:64-66) and
+// the int64 label map (dataloader.py:43) -- from the raw uint8 image / uint8 label map, so a step moves 4 B/pixel over
+// PCIe instead of 20 B/pixel.
+// ---------------------------------------------------------------------------------------------
+__global__ void u8hwc_to_nchw_f32_kernel(const uint8_t* __restrict__ x, float* __restrict__ y, long long HW, int C, float scale,
+                                         long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;     // over N*C*HW (output order)
+  if (i >= total) return;
+  const long long hw = i % HW;
+  const long long nc = i / HW;
+  const int c = static_cast<int>(nc % C);
+  const long long n = nc / C;
+  y[i] = static_cast<float>(x[(n * HW + hw) * C + c]) * scale;
+}
+__global__ void u8_to_i64_kernel(const uint8_t* __restrict__ x, long long* __restrict__ y, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = x[i];
+}
+
+// ---------------------------------------------------------------------------------------------
 // bias gradient: db[c] = sum_p dz[p][c]; stage 1 -> partial[block][C], stage 2 sums the blocks
 // ---------------------------------------------------------------------------------------------
 __global__ void bias_grad_partial_kernel(const uint4* __restrict__ dz, float* __restrict__ partial, long long P, int C8) {
@@ -700,6 +721,23 @@ int b2u_resize_bilinear_f32_bwd(const float* dy, float* dx, long long NC, int Hi
   resize_bilinear_f32_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       dy, dx, Hi, Wi, Ho, Wo, sh, sw, ish, isw, total);
   B2U_CHECK_LAUNCH("resize_bilinear_bwd");
+  return 0;
+}
+
+// x: [N][H][W][C] uint8 -> y: [N][C][H][W] fp32 = x * scale (scale = 1/255: preprocess_input)
+int b2u_u8hwc_to_nchw_f32(const unsigned char* x, float* y, int N, int H, int W, int C, float scale, void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0) return set_error(B2U_ERR_SHAPE, "u8hwc_to_nchw_f32: bad shape");
+  const long long HW = static_cast<long long>(H) * W, total = HW * N * C;
+  u8hwc_to_nchw_f32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, HW, C, scale, total);
+  B2U_CHECK_LAUNCH("u8hwc_to_nchw_f32");
+  return 0;
+}
+
+// uint8 label map -> the int64 map the loss kernels read
+int b2u_u8_to_i64(const unsigned char* x, long long* y, long long n, void* stream) {
+  if (n <= 0) return set_error(B2U_ERR_SHAPE, "u8_to_i64: empty");
+  u8_to_i64_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n);
+  B2U_CHECK_LAUNCH("u8_to_i64");
   return 0;
 }
 

@@ -117,6 +117,24 @@ def nchw_to_nhwc_bf16(x):
     return y
 
 
+def u8hwc_to_nchw_f32(x, scale=1.0 / 255.0, out=None):
+    """uint8 [N, H, W, C] image batch -> fp32 [N, C, H, W] * scale (the dataloader's preprocess_input + transpose)."""
+    _req(x, torch.uint8, "x")
+    N, H, W, C = x.shape
+    if out is None:
+        out = torch.empty((N, C, H, W), dtype=torch.float32, device=x.device)
+    check(lib().b2u_u8hwc_to_nchw_f32(ptr(x), ptr(out), N, H, W, C, scale, stream_ptr()))
+    return out
+
+
+def u8_to_i64(x, out=None):
+    _req(x, torch.uint8, "x")
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.int64, device=x.device)
+    check(lib().b2u_u8_to_i64(ptr(x), ptr(out), x.numel(), stream_ptr()))
+    return out
+
+
 def nchw_to_nhwc_bf16_padded(x, cpad, out=None):
     _req(x, torch.float32, "x")
     N, C, H, W = x.shape

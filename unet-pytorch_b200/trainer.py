@@ -228,8 +228,10 @@ class UnetTrainer:
         slot = self._stage_count % 2
         self._stage_count += 1
         bufs = self._slots[slot]
-        if bufs is None or bufs[0].shape != imgs.shape or bufs[1].shape != pngs.shape or bufs[1].dtype != pngs.dtype:
-            bufs = [torch.empty(imgs.shape, dtype=torch.float32, device=self.device),
+        if (bufs is None or bufs[0].shape != imgs.shape or bufs[0].dtype != imgs.dtype or bufs[1].shape != pngs.shape
+                or bufs[1].dtype != pngs.dtype):
+            # fp32 NCHW images (what the reference's dataloader yields) or raw uint8 NHWC images (device input pipeline)
+            bufs = [torch.empty(imgs.shape, dtype=torch.uint8 if imgs.dtype == torch.uint8 else torch.float32, device=self.device),
                     torch.empty(pngs.shape, dtype=pngs.dtype, device=self.device), None]
             self._slots[slot] = bufs
         with torch.cuda.stream(self._copy_stream):
@@ -249,12 +251,24 @@ class UnetTrainer:
             slot, ev = self._staged
             self._staged = None
             torch.cuda.current_stream().wait_event(ev)
-            return self._slots[slot][0], self._slots[slot][1], slot
+            imgs, pngs = self._device_preprocess(self._slots[slot][0], self._slots[slot][1])
+            return imgs, pngs, slot
         if not imgs.is_cuda:
             imgs = imgs.to(self.device, non_blocking=True)
         if not pngs.is_cuda:
             pngs = pngs.to(self.device, non_blocking=True)
+        imgs, pngs = self._device_preprocess(imgs, pngs)
         return imgs, pngs, None
+
+    def _device_preprocess(self, imgs, pngs):
+        """Raw uint8 inputs (NHWC image batch, uint8 label map) -> what the dataloader would have produced on the host
+        (utils/dataloader.py:41-43): fp32 NCHW image / 255 and an int64 label map, on the device."""
+        if imgs.dtype == torch.uint8:
+            n, h, w, c = imgs.shape
+            imgs = ops.u8hwc_to_nchw_f32(imgs.contiguous(), out=self.engine._buf("in:f32", (n, c, h, w), torch.float32))
+        if pngs.dtype == torch.uint8:
+            pngs = ops.u8_to_i64(pngs.contiguous(), out=self.engine._buf("in:i64", tuple(pngs.shape), torch.int64))
+        return imgs, pngs
 
     def _consumed(self, slot):
         if slot is not None:
