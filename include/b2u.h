@@ -63,6 +63,14 @@ int b2u_u8_to_i64(const unsigned char* x, long long* y, long long n, void* strea
  * N tile (64/128/192/256), bit 16 forces one 8x16-pixel M tile per CTA step (tests exercise every variant). */
 int b2u_conv_fprop(const void* x0, int C0, const void* x1, int C1, const void* wf, const float* bias, void* y, int N,
                    int H, int W, int Cout, int taps, int relu, int bn_override, void* stream);
+/* b2u_conv_fprop that also emits the BatchNorm statistics of its output (conv -> nn.BatchNorm2d chains,
+ * nets/TraditionalUnet.py:9-14, nets/resnet.py:77-95, nets/LightWeightUnet.py:8-11, nets/UltraLightweightUnet*.py):
+ * stat_partial [b2u_conv_stat_rows(...)][2][Cout] fp32 = per M tile, the sums of z and z^2 over its in-image pixels, taken
+ * from the bf16 values as stored; b2u_bn_fwd_train_stats consumes them instead of re-reading z */
+int b2u_conv_stat_rows(int N, int H, int W, int Cout, int taps, int bn_override);
+int b2u_conv_fprop_stats(const void* x0, int C0, const void* x1, int C1, const void* wf, const float* bias, void* y, int N,
+                         int H, int W, int Cout, int taps, int relu, int bn_override, float* stat_partial, int stat_rows,
+                         void* stream);
 /* dgrad of the same conv (autograd of nn.Conv2d, utils/utils_fit.py:92): dz has Cz channels; the C0+C1 input-channel
  * gradients go to dx0 / dx1 (dx1 NULL: single input).  mask (NHWC bf16, C0 channels, single output only) applies the
  * ReLU backward of the tensor that fed the conv: dx0 = 0 where mask <= 0. */
@@ -97,6 +105,10 @@ size_t b2u_bn_workspace(int C);
 int b2u_bn_fwd_train(const void* z, const void* residual, void* y, const float* gamma, const float* beta,
                      float* running_mean, float* running_var, float* save_mean, float* save_invstd, void* ws,
                      size_t ws_bytes, long long P, int C, float eps, float momentum, int relu, void* stream);
+int b2u_bn_fwd_train_stats(const void* z, const void* residual, void* y, const float* gamma, const float* beta,
+                           float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                           const float* stat_partial, int stat_rows, void* ws, size_t ws_bytes, long long P, int C, float eps,
+                           float momentum, int relu, void* stream);
 int b2u_bn_fwd_eval(const void* z, const void* residual, void* y, const float* gamma, const float* beta,
                     const float* running_mean, const float* running_var, void* ws, size_t ws_bytes, long long P, int C,
                     float eps, int relu, void* stream);

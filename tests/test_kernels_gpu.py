@@ -585,3 +585,38 @@ def test_softmax_resize_argmax_kernel(b2u, cuda_device, C, H, W, crop, out):
         confident = (top2[..., 1] - top2[..., 0]) > 1e-4
         assert (got[n] == ref.argmax(-1))[confident].all()
         assert (got[n] == ref.argmax(-1)).mean() >= 0.999
+
+
+@pytest.mark.parametrize("N,H,W,C0,C1,Cout,taps", [(2, 24, 40, 64, 0, 64, 9), (1, 16, 16, 128, 0, 256, 9), (2, 32, 32, 64, 64, 128, 9),
+                                                    (2, 16, 48, 64, 0, 64, 1), (1, 8, 8, 256, 0, 512, 1), (3, 5, 7, 64, 0, 192, 1),
+                                                    (1, 40, 24, 64, 0, 128, 1)])
+def test_conv_epilogue_batchnorm_statistics(b2u, cuda_device, N, H, W, C0, C1, Cout, taps):
+    """conv_fprop(stats=...) emits per-tile sums of z and z^2 of the stored bf16 output; BatchNorm driven by them must equal
+    BatchNorm driven by its own statistics pass over the same z (ragged tiles, stacked tiles, virtual concat, 1x1)."""
+    from unet_pytorch_b200 import ops
+    dev = cuda_device
+    g = torch.Generator().manual_seed(Cout + H)
+    k = 3 if taps == 9 else 1
+    x0 = nhwc(torch.randn(N, C0, H, W, generator=g), dev)
+    x1 = nhwc(torch.randn(N, C1, H, W, generator=g), dev) if C1 else None
+    w = torch.randn(Cout, C0 + C1, k, k, generator=g) / ((C0 + C1) * k * k) ** 0.5
+    wf, _ = ops.pack_weights(w.to(dev))
+    bias = (torch.randn(Cout, generator=g) * 0.5).to(dev)
+    rows = ops.conv_stat_rows(N, H, W, Cout, taps)
+    stats = torch.full((rows, 2, Cout), float("nan"), dtype=torch.float32, device=dev)
+    z = ops.conv_fprop(x0, wf, bias, Cout, taps=taps, relu=False, x1=x1, stats=stats)
+    z_plain = ops.conv_fprop(x0, wf, bias, Cout, taps=taps, relu=False, x1=x1)
+    assert torch.equal(z, z_plain)
+    assert torch.isfinite(stats).all()
+    zf = z.float().reshape(-1, Cout)
+    tot = stats.double().sum(0).cpu()
+    assert torch.allclose(tot[0], zf.double().sum(0).cpu(), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(tot[1], (zf.double() ** 2).sum(0).cpu(), rtol=1e-5, atol=1e-3)
+    gamma = (1 + 0.1 * torch.randn(Cout, generator=g)).to(dev); beta = (0.1 * torch.randn(Cout, generator=g)).to(dev)
+    rm_a, rv_a = torch.zeros(Cout, device=dev), torch.ones(Cout, device=dev)
+    rm_b, rv_b = torch.zeros(Cout, device=dev), torch.ones(Cout, device=dev)
+    ya, ma, ia = ops.bn_fwd_train(z, gamma, beta, rm_a, rv_a)
+    yb, mb, ib = ops.bn_fwd_train(z, gamma, beta, rm_b, rv_b, stats=stats, stat_rows=rows)
+    assert torch.allclose(ma, mb, rtol=1e-5, atol=1e-6) and torch.allclose(ia, ib, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(rm_a, rm_b, rtol=1e-5, atol=1e-6) and torch.allclose(rv_a, rv_b, rtol=1e-4, atol=1e-6)
+    assert rel(yb, ya) <= 1e-3

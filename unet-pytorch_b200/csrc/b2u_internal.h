@@ -37,11 +37,13 @@ struct ConvLaunch {
   const __nv_bfloat16* mask = nullptr; int mask_c = 0;
   int N = 0, H = 0, W = 0, Cout = 0, taps = 9;
   int flags = 0;                            // bit0 relu, bit1 mask, bit2 classifier head (fp32 NCHW logits)
+  float* stat_partial = nullptr;            // optional [m tiles][2][Cout] fp32: per-tile column sums (z, z^2) of the stored output
   float* head_out = nullptr; int head_cls = 0;   // bit2: logits [N][head_cls][H][W]; Cout must be 64 = [hi(32) | lo(32)] weights
   int bn_override = 0;
   int tile_flags = 0;                       // bit0: force one M tile per CTA step (debug / tests)
 };
 int launch_conv(const ConvLaunch& a, cudaStream_t st);
+int conv_m_tiles(int N, int H, int W, int Cout, int taps, int bn_override);   // rows of ConvLaunch::stat_partial
 
 struct WgradLaunch {
   const void* x0 = nullptr; int C0 = 0;

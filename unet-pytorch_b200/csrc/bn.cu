@@ -129,6 +129,25 @@ bn_colsum_kernel(const uint4* __restrict__ a, const uint4* __restrict__ y, const
   }
 }
 
+// rows [R][L] fp32 -> out[L] (fp64 accumulation, fixed order): folds the per-tile statistics a conv epilogue wrote
+__global__ void __launch_bounds__(256)
+bn_rows_reduce_kernel(const float* __restrict__ rows, float* __restrict__ out, int R, int L) {
+  __shared__ double sred[8][33];
+  const int col = threadIdx.x & 31, lane_r = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + col;
+  double acc = 0.0;
+  if (i < L)
+    for (int r = lane_r; r < R; r += 8) acc += static_cast<double>(__ldg(rows + static_cast<size_t>(r) * L + i));
+  sred[lane_r][col] = acc;
+  __syncthreads();
+  if (lane_r == 0 && i < L) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sred[k][col];
+    out[i] = static_cast<float>(t);
+  }
+}
+
 // forward finalize: statistics -> (scale, shift) for the apply pass, saved mean/invstd, running-stat update
 __global__ void bn_fwd_finalize_kernel(const float* __restrict__ partial, int blocks, int C, long long P,
                                        const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -302,6 +321,30 @@ int b2u_bn_fwd_train(const void* z, const void* residual, void* y, const float* 
                                                                         nullptr, nullptr, nullptr, partial, P, C / 8, 0);
   B2U_CHECK_LAUNCH("bn_colsum");
   bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, kBnBlocks, C, P, gamma, beta, running_mean, running_var,
+                                                          save_mean, save_invstd, coef, coef + C, eps, momentum);
+  B2U_CHECK_LAUNCH("bn_fwd_finalize");
+  const long long G = (P + kBnApplyRows - 1) / kBnApplyRows;
+  bn_apply_kernel<<<static_cast<unsigned>((G * (C / 8) + 255) / 256), 256, 0, st>>>(static_cast<const uint4*>(z), static_cast<const uint4*>(residual),
+                                                                                   static_cast<uint4*>(y), coef, coef + C, P, G, C / 8, relu);
+  B2U_CHECK_LAUNCH("bn_apply");
+  return 0;
+}
+
+// b2u_bn_fwd_train with the column sums supplied by the producing conv (b2u_conv_fprop_stats): stat_rows rows of
+// [2][C] fp32 per-tile sums of z and z^2 replace the statistics pass over z (one tensor read less).
+int b2u_bn_fwd_train_stats(const void* z, const void* residual, void* y, const float* gamma, const float* beta,
+                           float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                           const float* stat_partial, int stat_rows, void* ws, size_t ws_bytes, long long P, int C, float eps,
+                           float momentum, int relu, void* stream) {
+  int rc = bn_check(P, C, ws, ws_bytes, "bn_fwd_train_stats");
+  if (rc) return rc;
+  if (!stat_partial || stat_rows <= 0) return set_error(B2U_ERR_ARG, "bn_fwd_train_stats: statistics missing");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(ws);
+  float* coef = partial + static_cast<size_t>(kBnBlocks) * 2 * C;
+  bn_rows_reduce_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(stat_partial, partial, stat_rows, 2 * C);
+  B2U_CHECK_LAUNCH("bn_rows_reduce");
+  bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, 1, C, P, gamma, beta, running_mean, running_var,
                                                           save_mean, save_invstd, coef, coef + C, eps, momentum);
   B2U_CHECK_LAUNCH("bn_fwd_finalize");
   const long long G = (P + kBnApplyRows - 1) / kBnApplyRows;

@@ -40,6 +40,7 @@ struct ConvParams {
   int num_m_tiles, num_n_tiles;
   int split_c;       // output channels >= split_c go to the second output tensor map
   int flags;         // bit0 relu, bit1 mask, bit2 classifier head
+  float* stat_partial;  // [m tiles][2][Cout] or null: per-tile sums of z and z^2 over the tile's in-image pixels (BatchNorm statistics)
   float* head_out;   // bit2: fp32 NCHW logits [N][head_cls][H][W]
   int head_cls;
   const float* bias; // [Cout] or null (head: [head_cls])
@@ -61,7 +62,8 @@ struct ConvCfg {
   static constexpr int kOffB = kOffA + SA * kABytes;
   static constexpr int kOffStage = kOffB + SB * kBBytes;
   static constexpr int kOffBias = kOffStage + 2 * kStageBytes;
-  static constexpr int kOffBar = kOffBias + 2 * 256 * 4;     // bias of the current N tile, double buffered by tile parity
+  static constexpr int kOffStat = kOffBias + 2 * 256 * 4;    // [4 row quarters][64 channels][2] fp32 scratch of the BatchNorm-statistics pass
+  static constexpr int kOffBar = kOffStat + 4 * 64 * 2 * 4;  // (bias of the current N tile is double buffered by tile parity)
   static constexpr int kNumBar = 2 * SA + 2 * SB + 4;
   static constexpr int kOffTmem = kOffBar + kNumBar * 8;
   static constexpr int kSmemBytes = kOffTmem + 16 + 1024;  // + alignment slack
@@ -92,6 +94,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const uint32_t sB = smem_base + Cfg::kOffB;
   const uint32_t sStage = smem_base + Cfg::kOffStage;
   float* sBias = reinterpret_cast<float*>(smem_gen + Cfg::kOffBias);
+  float* sStat = reinterpret_cast<float*>(smem_gen + Cfg::kOffStat);
   const uint32_t bars = smem_base + Cfg::kOffBar;
   auto a_full = [&](int i) { return bars + 8u * i; };
   auto a_empty = [&](int i) { return bars + 8u * (SA + i); };
@@ -255,6 +258,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       mbar_wait(t_full(as), pacc);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(as * Cfg::kAccCols);
+      float stat_acc[BN / 64];       // thread (c = row & 63, quantity = row >> 6) owns one column sum per 64-channel block
+#pragma unroll
+      for (int j = 0; j < BN / 64; ++j) stat_acc[j] = 0.f;
 
 #pragma unroll 1
       for (int jj = 0; jj < MT * (BN / 64); ++jj) {
@@ -329,7 +335,39 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           }
           tma_store_commit();              // always: the wait_group<1> bookkeeping counts one group per sub-tile
         }
+        if (p.stat_partial != nullptr) {
+          // BatchNorm statistics of this conv's output, taken from the bf16 tile exactly as it is stored (so they equal a
+          // separate pass over z): thread = (channel pair cp, row quarter q) sums its 32 rows of the staged tile (a warp
+          // reads one permuted 128-byte row per step: conflict-free), the four quarters meet in a 2 KB scratch, and
+          // thread (c, quantity) keeps the running sum of the tile's stacked sub-tiles in a register.
+          const int cp = row & 31, q4 = row >> 5;
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            const int r = q4 * 32 + rr;
+            const bool inimg = (h0 + mt * kHb + r / kWb) < p.H && (w0 + r % kWb) < p.W;
+            uint32_t wv;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv) : "r"(stage + r * 128 + (((cp >> 2) ^ (r & 7)) << 4) + ((cp & 3) << 2)));
+            const float lo = inimg ? bf16_lo(wv) : 0.f, hi = inimg ? bf16_hi(wv) : 0.f;
+            s0 += lo; s1 += hi; q0 = fmaf(lo, lo, q0); q1 = fmaf(hi, hi, q1);
+          }
+          float* sq = sStat + q4 * 128;            // [channel 0..63][2]
+          sq[(2 * cp) * 2] = s0; sq[(2 * cp) * 2 + 1] = q0;
+          sq[(2 * cp + 1) * 2] = s1; sq[(2 * cp + 1) * 2 + 1] = q1;
+          named_bar_sync(3, 128);
+          const int c = row & 63, qty = row >> 6;
+          const float tsum = sStat[c * 2 + qty] + sStat[128 + c * 2 + qty] + sStat[256 + c * 2 + qty] + sStat[384 + c * 2 + qty];
+#pragma unroll
+          for (int j2 = 0; j2 < BN / 64; ++j2) if (j2 == j) stat_acc[j2] += tsum;      // static indices keep it in registers
+          // the scratch is rewritten only after the two named barriers at the top of the next sub-tile
+        }
         sbuf ^= 1u;
+      }
+      if (p.stat_partial != nullptr) {
+        const int c = row & 63, qty = row >> 6;
+        float* dst = p.stat_partial + (static_cast<size_t>(tile / p.num_n_tiles) * 2 + qty) * p.Cout + n0 + c;
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j) dst[j * 64] = stat_acc[j];
       }
       if (++as == 2) { as = 0; pacc ^= 1u; }
     }
@@ -386,6 +424,7 @@ static int launch_cfg(const ConvLaunch& a, cudaStream_t st) {
   p.num_n_tiles = a.Cout / BN;
   p.split_c = split;
   p.flags = a.flags;
+  p.stat_partial = a.stat_partial;
   p.head_out = a.head_out;
   p.head_cls = a.head_cls;
   p.bias = a.bias;
@@ -398,6 +437,17 @@ static int launch_cfg(const ConvLaunch& a, cudaStream_t st) {
   if (e != cudaSuccess) return set_error(B2U_ERR_CUDA, "conv_igemm launch: %s", cudaGetErrorString(e));
   note_launch();
   return 0;
+}
+
+// number of M tiles launch_conv will use for this problem = rows of ConvLaunch::stat_partial
+int conv_m_tiles(int N, int H, int W, int Cout, int taps, int bn_override) {
+  int bn = bn_override & 0xffff;
+  if (!bn) bn = Cout % 256 == 0 ? 256 : (Cout % 192 == 0 ? 192 : (Cout % 128 == 0 ? 128 : 64));
+  const bool tall = H > kHb && !((bn_override >> 16) & 1);
+  int mt = 1;
+  if (taps == 9) mt = (bn == 128 || bn == 64) && tall ? 2 : 1;
+  else           mt = bn == 64 ? 2 : 1;
+  return N * ((H + kHb * mt - 1) / (kHb * mt)) * ((W + kWb - 1) / kWb);
 }
 
 int launch_conv(const ConvLaunch& a, cudaStream_t st) {
@@ -459,6 +509,29 @@ int b2u_conv_fprop(const void* x0, int C0, const void* x1, int C1, const void* w
   a.flags = relu ? 1 : 0;
   a.bn_override = bn_override & 0xffff;    // bits 0..15: N tile override; bit 16: one M tile per CTA step
   a.tile_flags = bn_override >> 16;
+  return b2u::launch_conv(a, static_cast<cudaStream_t>(stream));
+}
+
+// b2u_conv_fprop that also emits the BatchNorm statistics of its output: stat_partial [b2u_conv_stat_rows(...)][2][Cout]
+// fp32 receives, per M tile, the sums of z and z^2 over the tile's in-image pixels, taken from the bf16 values as stored.
+int b2u_conv_stat_rows(int N, int H, int W, int Cout, int taps, int bn_override) {
+  if (N <= 0 || H <= 0 || W <= 0 || Cout <= 0) return 0;
+  return b2u::conv_m_tiles(N, H, W, Cout, taps, bn_override);
+}
+
+int b2u_conv_fprop_stats(const void* x0, int C0, const void* x1, int C1, const void* wf, const float* bias, void* y, int N,
+                         int H, int W, int Cout, int taps, int relu, int bn_override, float* stat_partial, int stat_rows,
+                         void* stream) {
+  if (stat_partial == nullptr || stat_rows < b2u::conv_m_tiles(N, H, W, Cout, taps, bn_override))
+    return b2u::set_error(B2U_ERR_ARG, "conv_fprop_stats: statistics buffer too small");
+  b2u::ConvLaunch a;
+  a.x0 = x0; a.C0 = C0; a.x1 = x1; a.C1 = x1 ? C1 : 0;
+  a.wpacked = wf; a.bias = bias; a.y0 = y;
+  a.N = N; a.H = H; a.W = W; a.Cout = Cout; a.taps = taps;
+  a.flags = relu ? 1 : 0;
+  a.bn_override = bn_override & 0xffff;
+  a.tile_flags = bn_override >> 16;
+  a.stat_partial = stat_partial;
   return b2u::launch_conv(a, static_cast<cudaStream_t>(stream));
 }
 

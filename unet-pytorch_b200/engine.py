@@ -131,6 +131,11 @@ class UNetEngine:
         # The wgrad kernel can produce db in the same pass (an N=16 MMA against a ones tile); measured on B200 it costs
         # more than the separate HBM-bound column-sum kernel (work units with the extra MMAs become the stragglers of
         # the static schedule: +40 % wgrad time vs +1.2 ms for bias_grad), so it is off by default.
+        # BatchNorm statistics from the conv epilogue (one pass over z less); only where the reduction is long enough for the
+        # extra epilogue work to hide behind the main loop (scripts/ab_fuse_bnstats.py)
+        self.fuse_bn_stats = True
+        self.bn_stats_min_k = 1024
+        self.bn_stats_min_cout = 256
         # db from the wgrad kernel's bias warps (3x3 layers) instead of a separate pass over dz: an A/B on one box
         # (scripts/ab_fuse_bias.py: 23.2-23.9 vs 23.4-23.5 ms/step) shows no gain, so the separate pass stays the default
         self.fuse_bias_grad = False
@@ -258,7 +263,14 @@ class UNetEngine:
             A[c.name] = out
             return out
         z = self._buf("z:" + c.name, (n, h, w, c.cout_p))
-        ops.conv_fprop(x0, c.wf, bias, c.cout_p, taps=taps, relu=False, x1=x1, out=z)
+        # training: the conv epilogue also emits the BatchNorm statistics of z (per-tile sums), so BatchNorm skips its
+        # statistics pass over z
+        stats, rows = None, 0
+        kdim = taps * (x0.shape[3] + (x1.shape[3] if x1 is not None else 0))
+        if training and self.fuse_bn_stats and (kdim >= self.bn_stats_min_k or c.cout_p >= self.bn_stats_min_cout):
+            rows = ops.conv_stat_rows(n, h, w, c.cout_p, taps)
+            stats = self._workspace("bnstat", rows * 2 * c.cout_p * 4)[:rows * 2 * c.cout_p * 4].view(torch.float32)
+        ops.conv_fprop(x0, c.wf, bias, c.cout_p, taps=taps, relu=False, x1=x1, out=z, stats=stats)
         gamma = self._padded_vec("g:" + c.bn, params[c.bn + ".weight"], c.cout_p, fill=1.0)
         beta = self._padded_vec("bt:" + c.bn, params[c.bn + ".bias"], c.cout_p)
         out = self._buf(c.name, (n, h, w, c.cout_p))
@@ -266,11 +278,13 @@ class UNetEngine:
         rm, rv = params[c.bn + ".running_mean"], params[c.bn + ".running_var"]
         if training:
             if c.cout_p == c.cout:
-                _, mean, invstd = ops.bn_fwd_train(z, gamma, beta, rm, rv, self.eps, self.momentum, True, out=out, ws=ws)
+                _, mean, invstd = ops.bn_fwd_train(z, gamma, beta, rm, rv, self.eps, self.momentum, True, out=out, ws=ws,
+                                                   stats=stats, stat_rows=rows)
             else:
                 rmp = self._padded_vec("rm:" + c.bn, rm, c.cout_p)
                 rvp = self._padded_vec("rv:" + c.bn, rv, c.cout_p, fill=1.0)
-                _, mean, invstd = ops.bn_fwd_train(z, gamma, beta, rmp, rvp, self.eps, self.momentum, True, out=out, ws=ws)
+                _, mean, invstd = ops.bn_fwd_train(z, gamma, beta, rmp, rvp, self.eps, self.momentum, True, out=out, ws=ws,
+                                                   stats=stats, stat_rows=rows)
                 rm.copy_(rmp[:c.cout])
                 rv.copy_(rvp[:c.cout])
             nbt = params.get(c.bn + ".num_batches_tracked")

@@ -38,10 +38,11 @@ def pad64(c):
 
 
 class _T:
-    __slots__ = ("data", "grad", "fused_relu", "needs_grad", "aux")
+    __slots__ = ("data", "grad", "fused_relu", "needs_grad", "aux", "stats")
 
     def __init__(self, data, fused_relu=False, needs_grad=False):
         self.data, self.grad, self.fused_relu, self.needs_grad, self.aux = data, None, fused_relu, needs_grad, None
+        self.stats = None      # (fp32 per-tile column sums, rows) when the producing conv emitted BatchNorm statistics
 
 
 def resnet50_unet_program(num_classes):
@@ -224,6 +225,12 @@ class GraphEngine:
         # db from the wgrad kernel's bias warps instead of a separate pass over dz: measured on one box (scripts/ab_fuse_bias.py)
         # it does not change the step time (the extra smem reads slow the bias-owning work units), so it stays off
         self.fuse_bias_grad = False
+        # BatchNorm statistics from the producing conv's epilogue (one pass over z less).  The extra epilogue work only hides
+        # behind the main loop when the reduction is long enough: measured (scripts/ab_fuse_bnstats.py) it gains 0.8 ms on
+        # Unet-ResNet50 but loses 0.7-1.3 ms on the full-resolution, short-K layers of the other BatchNorm nets
+        self.fuse_bn_stats = True
+        self.bn_stats_min_k = 1024
+        self.bn_stats_min_cout = 256
         readers = {}
         for i in program:
             for key in ("x", "x1", "z", "res", "a", "b"):
@@ -384,10 +391,17 @@ class GraphEngine:
                 coutp = pad64(ins["cout"])
                 bias = self._padded("b:" + ins["w"], params[ins["bias"]], (coutp,)) if ins["bias"] else None
                 aux = None
+                stats = None
                 if ins["stride"] == 1:
                     z = self._buf(ins["out"], (n, h, w, coutp))
+                    kdim = ins["taps"] * (xin.data.shape[3] + (x1.data.shape[3] if x1 else 0))
+                    if training and self.fuse_bn_stats and ins["out"] in self._pre_bn and (kdim >= self.bn_stats_min_k or coutp >= self.bn_stats_min_cout):
+                        # the BatchNorm that reads this output takes its statistics from this conv's epilogue (no pass over
+                        # z); one buffer per conv output: another conv may run before that BatchNorm (downsample branches)
+                        rows = ops.conv_stat_rows(n, h, w, coutp, ins["taps"])
+                        stats = (self._workspace("bnstat:" + ins["out"], rows * 2 * coutp * 4)[:rows * 2 * coutp * 4].view(torch.float32), rows)
                     ops.conv_fprop(xin.data, wf, bias, coutp, taps=ins["taps"], relu=ins["relu"],
-                                   x1=x1.data if x1 else None, out=z)
+                                   x1=x1.data if x1 else None, out=z, stats=stats[0] if stats else None)
                 elif ins["taps"] == 9:      # 3x3 stride 2 = stride-1 conv, keep even pixels
                     full = self._buf(ins["out"] + ":full", (n, h, w, coutp))
                     ops.conv_fprop(xin.data, wf, bias, coutp, taps=9, relu=ins["relu"], out=full)
@@ -399,6 +413,7 @@ class GraphEngine:
                 ng = xin.needs_grad or (x1 is not None and x1.needs_grad) or ins["w"] in trainable or (ins["bias"] in trainable)
                 t = _T(z, fused_relu=ins["relu"], needs_grad=ng)
                 t.aux = aux
+                t.stats = stats
                 T[ins["out"]] = t
             elif op == "bn":
                 zt = T[ins["z"]]
@@ -413,7 +428,8 @@ class GraphEngine:
                 rmp, rvp = self._padded("rm:" + bnn, rm, (cp,)), self._padded("rv:" + bnn, rv, (cp,), 1.0)
                 if training:
                     _, mean, invstd = ops.bn_fwd_train(zt.data, gamma, beta, rmp, rvp, self.eps, self.momentum, ins["relu"],
-                                                       out=y, ws=ws, residual=res.data if res else None)
+                                                       out=y, ws=ws, residual=res.data if res else None,
+                                                       stats=zt.stats[0] if zt.stats else None, stat_rows=zt.stats[1] if zt.stats else 0)
                     if cp != c:
                         rm.copy_(rmp[:c]); rv.copy_(rvp[:c])
                     nbt = params.get(bnn + ".num_batches_tracked")

@@ -145,16 +145,27 @@ def nchw_to_nhwc_bf16_padded(x, cpad, out=None):
 
 
 # ---------------------------------------------------------------------------------------------- convs
-def conv_fprop(x0, wf, bias, Cout, taps=9, relu=True, x1=None, out=None, bn=0):
+def conv_fprop(x0, wf, bias, Cout, taps=9, relu=True, x1=None, out=None, bn=0, stats=None):
+    """stats: optional fp32 buffer [>= conv_stat_rows(...)][2][Cout]; the conv then also writes the per-tile sums of z and
+    z^2 of its output (BatchNorm statistics, consumed by bn_fwd_train(stats=...))."""
     _req(x0, BF16, "x0"); _req(x1, BF16, "x1"); _req(wf, BF16, "wf"); _req(bias, torch.float32, "bias")
     N, H, W, C0 = x0.shape
     C1 = 0 if x1 is None else x1.shape[3]
     if out is None:
         out = torch.empty((N, H, W, Cout), dtype=BF16, device=x0.device)
     with _timed(f"conv_igemm|fprop|{N}x{H}x{W}|{C0}+{C1}->{Cout}|t{taps}", 2.0 * N * H * W * Cout * (C0 + C1) * taps):
-        check(lib().b2u_conv_fprop(ptr(x0), C0, ptr(x1), C1, ptr(wf), ptr(bias), ptr(out), N, H, W, Cout, taps,
-                                   1 if relu else 0, bn, stream_ptr()))
+        if stats is None:
+            check(lib().b2u_conv_fprop(ptr(x0), C0, ptr(x1), C1, ptr(wf), ptr(bias), ptr(out), N, H, W, Cout, taps,
+                                       1 if relu else 0, bn, stream_ptr()))
+        else:
+            _req(stats, torch.float32, "stats")
+            check(lib().b2u_conv_fprop_stats(ptr(x0), C0, ptr(x1), C1, ptr(wf), ptr(bias), ptr(out), N, H, W, Cout, taps,
+                                             1 if relu else 0, bn, ptr(stats), stats.numel() // (2 * Cout), stream_ptr()))
     return out
+
+
+def conv_stat_rows(N, H, W, Cout, taps=9, bn=0):
+    return lib().b2u_conv_stat_rows(N, H, W, Cout, taps, bn)
 
 
 def conv_dgrad(dz, wd, C0, taps=9, C1=0, mask=None, out0=None, out1=None, bn=0):
@@ -247,8 +258,9 @@ def upsample2x_bwd(dup, ylow=None, out=None):
 
 # ---------------------------------------------------------------------------------------------- batch norm
 def bn_fwd_train(z, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1, relu=True, out=None, ws=None,
-                 residual=None):
-    """Returns (y, save_mean, save_invstd); running statistics are updated in place (torch semantics)."""
+                 residual=None, stats=None, stat_rows=0):
+    """Returns (y, save_mean, save_invstd); running statistics are updated in place (torch semantics).
+    stats/stat_rows: per-tile column sums written by conv_fprop(stats=...) -- skips the statistics pass over z."""
     _req(z, BF16, "z")
     C = z.shape[-1]
     P = z.numel() // C
@@ -259,9 +271,14 @@ def bn_fwd_train(z, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0
         out = torch.empty_like(z)
     mean = torch.empty((C,), dtype=torch.float32, device=z.device)
     invstd = torch.empty((C,), dtype=torch.float32, device=z.device)
-    check(lib().b2u_bn_fwd_train(ptr(z), ptr(residual), ptr(out), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(mean),
-                                 ptr(invstd), ptr(ws), ws.numel() * ws.element_size(), P, C, eps, momentum,
-                                 1 if relu else 0, stream_ptr()))
+    if stats is None:
+        check(lib().b2u_bn_fwd_train(ptr(z), ptr(residual), ptr(out), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(mean),
+                                     ptr(invstd), ptr(ws), ws.numel() * ws.element_size(), P, C, eps, momentum, 1 if relu else 0,
+                                     stream_ptr()))
+    else:
+        check(lib().b2u_bn_fwd_train_stats(ptr(z), ptr(residual), ptr(out), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
+                                           ptr(mean), ptr(invstd), ptr(stats), stat_rows, ptr(ws), ws.numel() * ws.element_size(), P, C,
+                                           eps, momentum, 1 if relu else 0, stream_ptr()))
     return out, mean, invstd
 
 
