@@ -30,6 +30,8 @@ def nchw(x):
 CONV_CASES = [
     # N, H, W, C0, C1, Cout, taps, relu
     (1, 8, 16, 64, 0, 64, 9, True),        # exactly one tile
+    (2, 24, 40, 64, 0, 64, 9, True),       # Cout = 64 with ragged tiles in both directions (swapped-role wgrad)
+    (3, 5, 7, 128, 64, 64, 9, False),      # Cout = 64, image smaller than a tile, two sources, three cin blocks
     (2, 32, 48, 64, 0, 64, 9, True),
     (2, 24, 40, 128, 0, 128, 9, True),     # ragged tiles in both directions
     (1, 16, 16, 256, 0, 256, 9, False),
@@ -76,7 +78,10 @@ def test_conv_fprop_dgrad_wgrad(b2u, cuda_device, N, H, W, C0, C1, Cout, taps, r
         dw, db = ops.conv_wgrad(x0, dzb, taps=taps, x1=x1, flags=flags, want_db=True)
         assert rel(dw, ref_dw) <= 1e-4
         assert rel(db, dzr.sum((0, 2, 3))) <= 1e-4      # bias gradient fused into the wgrad kernel
+    # without db: Cout = 64 3x3 layers take the swapped-role kernel (x as the M operand, three shifted dz boxes as N);
+    # flags bit 1 forces the generic kernel
     assert rel(ops.conv_wgrad(x0, dzb, taps=taps, x1=x1), ref_dw) <= 1e-4
+    assert rel(ops.conv_wgrad(x0, dzb, taps=taps, x1=x1, flags=2), ref_dw) <= 1e-4
     assert rel(ops.bias_grad(dzb), dzr.sum((0, 2, 3))) <= 1e-4
 
 

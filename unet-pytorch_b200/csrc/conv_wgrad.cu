@@ -279,6 +279,183 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
   }
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// Cout == 64, 3x3: operand roles swapped so that no half of the 128-row datapath carries duplicates.
+//   A (M x K) = x: the halo box [10 rows][16 px][64 ci]; the two M atoms of one MMA are vertical taps r and r+1 (atom stride
+//               = one image row of the box, 2048 B), so M = 128 = 2 taps x 64 input channels.  A second MMA starting
+//               at tap 2 supplies r = 2 (its second atom reads past the halo and is discarded).
+//   B (N x K) = dz: three boxes [8 rows][16 px][64 co] shifted horizontally by +1, 0, -1 pixels (TMA zero-fills outside
+//               the image); sum_c dz[c - (s-1)] x[c] is the tap with x offset s-1, so ONE x box (offset 0) serves all
+//               three horizontal taps and N = 192 = 3 taps x 64 output channels.
+//   D1[(r in {0,1}, ci)][(s, co)], D2[(r = 2, ci)][(s, co)]: 2 MMAs of N = 192 per image row deliver all 9 taps, where
+//   the generic kernel needs 3 (one per horizontal tap, each with its M rows duplicated).
+// Work unit = (K split, cin block); accumulators are single-buffered (a unit spans hundreds of K blocks).
+// ----------------------------------------------------------------------------------------------------------------
+struct Wg64Params {
+  int N, H, W, C0, C1;
+  int tiles_w, tiles_h, kblocks;
+  int num_cblk, splits, units;
+  float* partial;                  // [splits][64][9][C0+C1]
+};
+
+struct Wg64Cfg {
+  static constexpr int kStages = 3;
+  static constexpr int kXBytes = (kHb + 2) * kWb * 128;     // 20480
+  static constexpr int kDzBox = kHb * kWb * 128;            // 16384
+  static constexpr int kStage = kXBytes + 3 * kDzBox;       // 69632
+  static constexpr int kOffBar = kStages * kStage;
+  static constexpr int kNumBar = 2 * kStages + 2;
+  static constexpr int kOffTmem = kOffBar + kNumBar * 8;
+  static constexpr int kSmemBytes = kOffTmem + 16 + 1024;
+  static constexpr int kTmemCols = 512;                     // D1 at column 0, D2 at column 256 (192 columns each)
+  static_assert(kStage % 1024 == 0 && kXBytes % 1024 == 0, "stage alignment");
+  static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
+};
+
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad64_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
+                    const __grid_constant__ CUtensorMap tmDZ, const Wg64Params p) {
+  using Cfg = Wg64Cfg;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bars = smem_base + Cfg::kOffBar;
+  auto full = [&](int i) { return bars + 8u * i; };
+  auto empty = [&](int i) { return bars + 8u * (STAGES + i); };
+  const uint32_t t_full = bars + 8u * (2 * STAGES), t_empty = bars + 8u * (2 * STAGES + 1);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kOffTmem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX0); tma_prefetch_desc(&tmX1); tma_prefetch_desc(&tmDZ);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
+    mbar_init(t_full, 1); mbar_init(t_empty, 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int ctot = p.C0 + p.C1;
+
+  auto decode = [&](int unit, int& split, int& cblk) { cblk = unit % p.num_cblk; split = unit / p.num_cblk; };
+  auto krange = [&](int split, int& k0, int& k1) {
+    const long long kb = p.kblocks;
+    k0 = static_cast<int>(kb * split / p.splits);
+    k1 = static_cast<int>(kb * (split + 1) / p.splits);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0;
+      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+        int split, cblk, k0, k1;
+        decode(unit, split, cblk);
+        krange(split, k0, k1);
+        const int cin0 = cblk * 64;
+        const CUtensorMap* tmx = cin0 < p.C0 ? &tmX0 : &tmX1;
+        const int cx = cin0 < p.C0 ? cin0 : cin0 - p.C0;
+        for (int kb = k0; kb < k1; ++kb) {
+          int t = kb;
+          const int tw = t % p.tiles_w; t /= p.tiles_w;
+          const int th = t % p.tiles_h;
+          const int img = t / p.tiles_h;
+          const int w0 = tw * kWb, h0 = th * kHb;
+          mbar_wait(empty(st), ph ^ 1u);
+          const uint32_t base = smem_base + st * Cfg::kStage;
+          mbar_expect_tx(full(st), Cfg::kStage);
+          tma_load_4d(base, tmx, full(st), cx, w0, h0 - 1, img);
+          // N atom s holds dz shifted so that it meets x with offset s - 1: columns w0 - (s - 1) ...
+          tma_load_4d(base + Cfg::kXBytes, &tmDZ, full(st), 0, w0 + 1, h0, img);
+          tma_load_4d(base + Cfg::kXBytes + Cfg::kDzBox, &tmDZ, full(st), 0, w0, h0, img);
+          tma_load_4d(base + Cfg::kXBytes + 2 * Cfg::kDzBox, &tmDZ, full(st), 0, w0 - 1, h0, img);
+          if (++st == STAGES) { st = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 192, 1, 1);
+      const uint64_t a_desc0 = umma_smem_desc(smem_base, 2048, 1024, 2u);                         // M atoms: taps r, r+1
+      const uint64_t b_desc0 = umma_smem_desc(smem_base + Cfg::kXBytes, Cfg::kDzBox, 1024, 2u);    // N atoms: 3 shifted dz boxes
+      int st = 0; uint32_t ph = 0, pacc = 0;
+      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+        int split, cblk, k0, k1;
+        decode(unit, split, cblk);
+        krange(split, k0, k1);
+        mbar_wait(t_empty, pacc ^ 1u);
+        tc_fence_after();
+        uint32_t acc = 0;
+        for (int kb = k0; kb < k1; ++kb) {
+          mbar_wait(full(st), ph);
+          tc_fence_after();
+          const uint64_t a_st = a_desc0 + static_cast<uint64_t>((st * Cfg::kStage) >> 4);
+          const uint64_t b_st = b_desc0 + static_cast<uint64_t>((st * Cfg::kStage) >> 4);
+#pragma unroll
+          for (int j = 0; j < kHb; ++j) {
+            const uint32_t accj = j == 0 ? acc : 1u;
+            tc_mma_bf16(tmem_base, a_st + j * 128, b_st + j * 128, idesc, accj);                  // taps r = 0, 1
+            tc_mma_bf16(tmem_base + 256, a_st + (j + 2) * 128, b_st + j * 128, idesc, accj);      // tap r = 2 (+ discarded rows)
+          }
+          acc = 1;
+          tc_commit(empty(st));
+          if (++st == STAGES) { st = 0; ph ^= 1u; }
+        }
+        tc_commit(t_full);
+        pacc ^= 1u;
+      }
+    }
+  } else {
+    const int ew = warp & 3;
+    uint32_t pacc = 0;
+    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+      int split, cblk, k0, k1;
+      decode(unit, split, cblk);
+      krange(split, k0, k1);
+      mbar_wait(t_full, pacc);
+      tc_fence_after();
+      const bool nz = k1 > k0;
+      const int m = ew * 32 + lane;                  // accumulator row = (tap r index, input channel)
+      const int ci = cblk * 64 + (m & 63);
+#pragma unroll 1
+      for (int part = 0; part < 2; ++part) {         // part 0: D1 (r = m / 64), part 1: D2 (r = 2, rows 0..63 only)
+        const int r = part == 0 ? (m >> 6) : 2;
+        const bool valid = part == 0 || m < 64;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(part * 256);
+#pragma unroll 1
+        for (int c32 = 0; c32 < 6; ++c32) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + c32 * 32, v);
+          tmem_ld_wait();
+          if (valid) {
+            const int s = (c32 * 32) / 64, co0 = (c32 * 32) % 64;
+            float* dst = p.partial + ((static_cast<size_t>(split) * 64 + co0) * 9 + r * 3 + s) * ctot + ci;
+#pragma unroll
+            for (int q = 0; q < 32; ++q)             // consecutive lanes = consecutive ci: 128-byte stores
+              dst[static_cast<size_t>(q) * 9 * ctot] = nz ? __uint_as_float(v[q]) : 0.f;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty);
+      pacc ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
 // out[co][ci][r][s] (OIHW fp32) = sum_split partial[split][co][tap][ci]; one thread per (co, ci).
 // cin_real < cin_pitch handles the first layer (im2col columns k = tap*cin_real + c, see layout.cu).
 // generic path (1x1 convs and the first layer's im2col columns): 256 threads = 64 outputs x 4 split lanes
@@ -423,20 +600,72 @@ static int launch_wgrad_cfg(const void* x0, int C0, const void* x1, int C1, cons
   return 0;
 }
 
+struct Wgrad64Plan { int num_cblk, splits, units, kblocks; size_t ws_bytes; };
+
+static Wgrad64Plan plan_wgrad64(int N, int H, int W, int Cin_tot) {
+  Wgrad64Plan pl;
+  pl.num_cblk = Cin_tot / 64;
+  pl.kblocks = N * ((H + kHb - 1) / kHb) * ((W + kWb - 1) / kWb);
+  pl.splits = choose_splits(pl.num_cblk, pl.kblocks);
+  pl.units = pl.num_cblk * pl.splits;
+  pl.ws_bytes = static_cast<size_t>(pl.splits) * 64 * 9 * Cin_tot * sizeof(float);
+  return pl;
+}
+
+static int launch_wgrad64(const void* x0, int C0, const void* x1, int C1, const void* dz, float* partial, const Wgrad64Plan& pl,
+                          int N, int H, int W, cudaStream_t st) {
+  using Cfg = Wg64Cfg;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return set_error(B2U_ERR_CUDA, "cudaFuncSetAttribute(wgrad64): %s", cudaGetErrorString(e));
+    attr_done[dev] = true;
+  }
+  const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B;
+  CUtensorMap tmX0, tmX1, tmDZ;
+  int rc;
+  if ((rc = make_tmap_nhwc(&tmX0, x0, N, H, W, C0, 64, kWb, kHb + 2, swz))) return rc;
+  if (C1 > 0) {
+    if ((rc = make_tmap_nhwc(&tmX1, x1, N, H, W, C1, 64, kWb, kHb + 2, swz))) return rc;
+  } else {
+    tmX1 = tmX0;
+  }
+  if ((rc = make_tmap_nhwc(&tmDZ, dz, N, H, W, 64, 64, kWb, kHb, swz))) return rc;
+  Wg64Params p;
+  p.N = N; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1;
+  p.tiles_w = (W + kWb - 1) / kWb; p.tiles_h = (H + kHb - 1) / kHb; p.kblocks = pl.kblocks;
+  p.num_cblk = pl.num_cblk; p.splits = pl.splits; p.units = pl.units;
+  p.partial = partial;
+  const int grid = pl.units < num_sms() ? pl.units : num_sms();
+  conv_wgrad64_kernel<<<grid, 192, Cfg::kSmemBytes, st>>>(tmX0, tmX1, tmDZ, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(B2U_ERR_CUDA, "conv_wgrad64 launch: %s", cudaGetErrorString(e));
+  note_launch();
+  return 0;
+}
+
 }  // namespace b2u
 
 extern "C" {
 
 size_t b2u_conv_wgrad_workspace(int N, int H, int W, int Cin_tot, int Cout, int taps) {
   if (N <= 0 || H <= 0 || W <= 0 || Cin_tot <= 0 || Cout <= 0) return 0;
-  return b2u::plan_wgrad(N, H, W, Cin_tot, Cout, taps).ws_bytes;
+  size_t need = b2u::plan_wgrad(N, H, W, Cin_tot, Cout, taps).ws_bytes;
+  if (Cout == 64 && taps == 9) {          // the swapped-role kernel may use a different split count
+    const size_t n64 = b2u::plan_wgrad64(N, H, W, Cin_tot).ws_bytes;
+    if (n64 > need) need = n64;
+  }
+  return need;
 }
 
 // dw: OIHW fp32 [Cout][cin_real][taps]  (cin_real = C0+C1 unless first_cin > 0); db (nullable): [Cout] bias gradient,
 // computed in the same pass as column sums of dz.
 // first_cin > 0: x0 is the first layer's im2col tensor [N,H,W,64] (taps must be 1, C0 == 64, C1 == 0);
 //                dw then is [Cout][first_cin][3][3].
-// flags bit0: use three N=64 instructions per image row instead of the merged N=192 one.
+// flags bit0: use three N=64 instructions per image row instead of the merged N=192 one; bit1: never use the
+// swapped-role Cout = 64 kernel.
 int b2u_conv_wgrad(const void* x0, int C0, const void* x1, int C1, const void* dz, int Cout, float* dw, float* db, void* ws,
                    size_t ws_bytes, int N, int H, int W, int taps, int first_cin, int flags, void* stream) {
   using namespace b2u;
@@ -450,6 +679,19 @@ int b2u_conv_wgrad(const void* x0, int C0, const void* x1, int C1, const void* d
   if (Cout % 64 != 0) return set_error(B2U_ERR_SHAPE, "wgrad: Cout %d must be a multiple of 64", Cout);   // a ragged last 128-block reads zero-filled (out-of-bounds) dz channels
   if (first_cin > 0 && (taps != 1 || C0 != 64 || C1 != 0 || 9 * first_cin > 64))
     return set_error(B2U_ERR_SHAPE, "wgrad: first-layer mode needs taps=1, C0=64, C1=0, 9*cin<=64");
+  if (Cout == 64 && taps == 9 && db == nullptr && !(flags & 2)) {
+    // flags bit1 forces the generic kernel (tests); otherwise Cout = 64 runs with swapped operand roles
+    const Wgrad64Plan p64 = plan_wgrad64(N, H, W, ctot);
+    if (ws == nullptr || ws_bytes < p64.ws_bytes)
+      return set_error(B2U_ERR_ARG, "wgrad: workspace %zu bytes < required %zu", ws_bytes, p64.ws_bytes);
+    int rc64 = launch_wgrad64(x0, C0, x1, C1, dz, static_cast<float*>(ws), p64, N, H, W, st);
+    if (rc64) return rc64;
+    wgrad_reduce9_kernel<<<dim3(ctot / 64, 64), 160, 0, st>>>(static_cast<const float*>(ws), dw, p64.splits, 64, ctot);
+    cudaError_t e64 = cudaGetLastError();
+    if (e64 != cudaSuccess) return set_error(B2U_ERR_CUDA, "wgrad_reduce launch: %s", cudaGetErrorString(e64));
+    note_launch();
+    return 0;
+  }
   const WgradPlan pl = plan_wgrad(N, H, W, ctot, Cout, taps);
   if (ws == nullptr || ws_bytes < pl.ws_bytes)
     return set_error(B2U_ERR_ARG, "wgrad: workspace %zu bytes < required %zu", ws_bytes, pl.ws_bytes);
