@@ -289,6 +289,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
 //               three horizontal taps and N = 192 = 3 taps x 64 output channels.
 //   D1[(r in {0,1}, ci)][(s, co)], D2[(r = 2, ci)][(s, co)]: 2 MMAs of N = 192 per image row deliver all 9 taps, where
 //   the generic kernel needs 3 (one per horizontal tap, each with its M rows duplicated).
+//   The second M atom of D2 would be waste; it is pointed (per-row descriptor, LBO = distance to the tile) at a tile of
+//   ones, so rows 64..127 of D2 hold sum_p dz[p][co] -- the bias gradient -- at no extra MMA.
 // Work unit = (K split, cin block); accumulators are single-buffered (a unit spans hundreds of K blocks).
 // ----------------------------------------------------------------------------------------------------------------
 struct Wg64Params {
@@ -296,6 +298,7 @@ struct Wg64Params {
   int tiles_w, tiles_h, kblocks;
   int num_cblk, splits, units;
   float* partial;                  // [splits][64][9][C0+C1]
+  float* bias_partial;             // [splits][64] or null
 };
 
 struct Wg64Cfg {
@@ -303,7 +306,8 @@ struct Wg64Cfg {
   static constexpr int kXBytes = (kHb + 2) * kWb * 128;     // 20480
   static constexpr int kDzBox = kHb * kWb * 128;            // 16384
   static constexpr int kStage = kXBytes + 3 * kDzBox;       // 69632
-  static constexpr int kOffBar = kStages * kStage;
+  static constexpr int kOffOnes = kStages * kStage;         // one M atom (16 K rows x 128 B) of bf16 1.0
+  static constexpr int kOffBar = kOffOnes + 2048;
   static constexpr int kNumBar = 2 * kStages + 2;
   static constexpr int kOffTmem = kOffBar + kNumBar * 8;
   static constexpr int kSmemBytes = kOffTmem + 16 + 1024;
@@ -337,6 +341,9 @@ conv_wgrad64_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_const
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols);
     tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < 2048 / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem_gen + Cfg::kOffOnes)[i] = 0x3F803F80u;   // two bf16 1.0
+  fence_proxy_async_smem();        // generic-proxy writes -> visible to the tensor core's async proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -383,6 +390,15 @@ conv_wgrad64_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_const
       constexpr uint32_t idesc = umma_idesc_bf16(128, 192, 1, 1);
       const uint64_t a_desc0 = umma_smem_desc(smem_base, 2048, 1024, 2u);                         // M atoms: taps r, r+1
       const uint64_t b_desc0 = umma_smem_desc(smem_base + Cfg::kXBytes, Cfg::kDzBox, 1024, 2u);    // N atoms: 3 shifted dz boxes
+      // D2's operand: atom 0 = tap r = 2 of image row j, atom 1 = the ones tile (LBO = its distance from atom 0)
+      uint64_t a2_desc[STAGES][kHb];
+#pragma unroll
+      for (int s_ = 0; s_ < STAGES; ++s_)
+#pragma unroll
+        for (int j = 0; j < kHb; ++j) {
+          const uint32_t a0 = smem_base + s_ * Cfg::kStage + (j + 2) * 2048;
+          a2_desc[s_][j] = umma_smem_desc(a0, smem_base + Cfg::kOffOnes - a0, 1024, 2u);
+        }
       int st = 0; uint32_t ph = 0, pacc = 0;
       for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
         int split, cblk, k0, k1;
@@ -400,7 +416,10 @@ conv_wgrad64_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_const
           for (int j = 0; j < kHb; ++j) {
             const uint32_t accj = j == 0 ? acc : 1u;
             tc_mma_bf16(tmem_base, a_st + j * 128, b_st + j * 128, idesc, accj);                  // taps r = 0, 1
-            tc_mma_bf16(tmem_base + 256, a_st + (j + 2) * 128, b_st + j * 128, idesc, accj);      // tap r = 2 (+ discarded rows)
+            uint64_t a2 = a2_desc[0][j];                                                          // tap r = 2 | ones
+#pragma unroll
+            for (int s_ = 1; s_ < STAGES; ++s_) if (s_ == st) a2 = a2_desc[s_][j];
+            tc_mma_bf16(tmem_base + 256, a2, b_st + j * 128, idesc, accj);
           }
           acc = 1;
           tc_commit(empty(st));
@@ -438,6 +457,20 @@ conv_wgrad64_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_const
 #pragma unroll
             for (int q = 0; q < 32; ++q)             // consecutive lanes = consecutive ci: 128-byte stores
               dst[static_cast<size_t>(q) * 9 * ctot] = nz ? __uint_as_float(v[q]) : 0.f;
+          }
+        }
+      }
+      if (p.bias_partial != nullptr && cblk == 0 && ew == 2) {
+        // rows 64..127 of D2 all hold the column sums of dz; columns 64..127 belong to the unshifted box: db[co]
+        uint32_t v[32];
+#pragma unroll 1
+        for (int c32 = 2; c32 < 4; ++c32) {
+          tmem_ld_32x32(tmem_base + (64u << 16) + 256u + c32 * 32, v);
+          tmem_ld_wait();
+          if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+              p.bias_partial[static_cast<size_t>(split) * 64 + (c32 - 2) * 32 + q] = nz ? __uint_as_float(v[q]) : 0.f;
           }
         }
       }
@@ -608,12 +641,12 @@ static Wgrad64Plan plan_wgrad64(int N, int H, int W, int Cin_tot) {
   pl.kblocks = N * ((H + kHb - 1) / kHb) * ((W + kWb - 1) / kWb);
   pl.splits = choose_splits(pl.num_cblk, pl.kblocks);
   pl.units = pl.num_cblk * pl.splits;
-  pl.ws_bytes = static_cast<size_t>(pl.splits) * 64 * 9 * Cin_tot * sizeof(float);
+  pl.ws_bytes = static_cast<size_t>(pl.splits) * 64 * 9 * Cin_tot * sizeof(float) + static_cast<size_t>(pl.splits) * 64 * sizeof(float);
   return pl;
 }
 
-static int launch_wgrad64(const void* x0, int C0, const void* x1, int C1, const void* dz, float* partial, const Wgrad64Plan& pl,
-                          int N, int H, int W, cudaStream_t st) {
+static int launch_wgrad64(const void* x0, int C0, const void* x1, int C1, const void* dz, float* partial, float* bias_partial,
+                          const Wgrad64Plan& pl, int N, int H, int W, cudaStream_t st) {
   using Cfg = Wg64Cfg;
   static bool attr_done[64] = {false};
   int dev = 0;
@@ -638,6 +671,7 @@ static int launch_wgrad64(const void* x0, int C0, const void* x1, int C1, const 
   p.tiles_w = (W + kWb - 1) / kWb; p.tiles_h = (H + kHb - 1) / kHb; p.kblocks = pl.kblocks;
   p.num_cblk = pl.num_cblk; p.splits = pl.splits; p.units = pl.units;
   p.partial = partial;
+  p.bias_partial = bias_partial;
   const int grid = pl.units < num_sms() ? pl.units : num_sms();
   conv_wgrad64_kernel<<<grid, 192, Cfg::kSmemBytes, st>>>(tmX0, tmX1, tmDZ, p);
   cudaError_t e = cudaGetLastError();
@@ -679,13 +713,21 @@ int b2u_conv_wgrad(const void* x0, int C0, const void* x1, int C1, const void* d
   if (Cout % 64 != 0) return set_error(B2U_ERR_SHAPE, "wgrad: Cout %d must be a multiple of 64", Cout);   // a ragged last 128-block reads zero-filled (out-of-bounds) dz channels
   if (first_cin > 0 && (taps != 1 || C0 != 64 || C1 != 0 || 9 * first_cin > 64))
     return set_error(B2U_ERR_SHAPE, "wgrad: first-layer mode needs taps=1, C0=64, C1=0, 9*cin<=64");
-  if (Cout == 64 && taps == 9 && db == nullptr && !(flags & 2)) {
+  if (Cout == 64 && taps == 9 && !(flags & 2)) {
     // flags bit1 forces the generic kernel (tests); otherwise Cout = 64 runs with swapped operand roles
     const Wgrad64Plan p64 = plan_wgrad64(N, H, W, ctot);
     if (ws == nullptr || ws_bytes < p64.ws_bytes)
       return set_error(B2U_ERR_ARG, "wgrad: workspace %zu bytes < required %zu", ws_bytes, p64.ws_bytes);
-    int rc64 = launch_wgrad64(x0, C0, x1, C1, dz, static_cast<float*>(ws), p64, N, H, W, st);
+    float* wp64 = static_cast<float*>(ws);
+    float* bp64 = db ? wp64 + static_cast<size_t>(p64.splits) * 64 * 9 * ctot : nullptr;
+    int rc64 = launch_wgrad64(x0, C0, x1, C1, dz, wp64, bp64, p64, N, H, W, st);
     if (rc64) return rc64;
+    if (db) {
+      wgrad_bias_reduce_kernel<<<1, 128, 0, st>>>(bp64, db, p64.splits, 64);
+      cudaError_t eb = cudaGetLastError();
+      if (eb != cudaSuccess) return set_error(B2U_ERR_CUDA, "wgrad_bias_reduce launch: %s", cudaGetErrorString(eb));
+      note_launch();
+    }
     wgrad_reduce9_kernel<<<dim3(ctot / 64, 64), 160, 0, st>>>(static_cast<const float*>(ws), dw, p64.splits, 64, ctot);
     cudaError_t e64 = cudaGetLastError();
     if (e64 != cudaSuccess) return set_error(B2U_ERR_CUDA, "wgrad_reduce launch: %s", cudaGetErrorString(e64));

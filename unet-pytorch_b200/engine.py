@@ -411,7 +411,8 @@ class UNetEngine:
                 return dz
             wn, bn_ = c.name + ".weight", c.name + ".bias"
             want_w, want_b = has(wn), has(bn_)
-            fuse_b = want_w and want_b and self.fuse_bias_grad and not c.padded and not c.bn and not c.first
+            fuse_b = (want_w and want_b and not c.padded and not c.bn and not c.first
+                      and (self.fuse_bias_grad or c.cout_p == 64))     # Cout = 64: db is free in the swapped-role wgrad kernel
             taps = 1 if c.first else 9
             if want_w:
                 ctot_p = 64 if c.first else c.c0_p + c.c1_p

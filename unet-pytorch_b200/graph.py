@@ -693,7 +693,7 @@ class GraphEngine:
                 c0p = xw.shape[3]
                 c1p = x1.data.shape[3] if x1 else 0
                 # 3x3 layers with a live bias: db comes out of the wgrad kernel (its bias warp sums the staged dz tiles)
-                fused_db = (self.fuse_bias_grad and has(ins["w"]) and has(ins["bias"]) and taps == 9 and ins["out"] not in self._pre_bn
+                fused_db = ((self.fuse_bias_grad or coutp == 64) and has(ins["w"]) and has(ins["bias"]) and taps == 9 and ins["out"] not in self._pre_bn
                             and coutp == cout and c0p == c0r and c1p == c1r)
                 if has(ins["w"]):
                     need = ops.lib().b2u_conv_wgrad_workspace(dz.shape[0], dz.shape[1], dz.shape[2], c0p + c1p, coutp, taps)
