@@ -656,3 +656,45 @@ def test_device_input_pipeline_uint8(b2u, cuda_device):
     rb = b.train_step().cpu()
     assert torch.allclose(ra, rb, rtol=2e-3, atol=1e-5)
     assert _global_rel(b.grads, {k: v.cpu() for k, v in a.grads.items()}) <= 5e-3
+
+
+def test_reference_training_wrappers(b2u, cuda_device):
+    """The wrappers the reference's train.py puts around the model keep working with the drop-in: autocast + GradScaler
+    (utils_fit.py:65-94), DistributedDataParallel(find_unused_parameters=True) (train.py:346) -- one rank here -- and a
+    torch optimizer over model.parameters() (train.py:402-405)."""
+    import torch.distributed as dist
+    dev = cuda_device
+    C = 4
+    sd = O.make_params(C, seed=11)
+    imgs, pngs = O.make_inputs(2, C, 64, 64, seed=5)
+    l32, _, g32 = O.train_step(sd, imgs, pngs, torch.ones(C), C, dice=True)
+    model = b2u.Unet(num_classes=C, backbone="vgg")
+    model.load_state_dict(sd)
+    model = model.to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    scaler = torch.amp.GradScaler("cuda")
+    with torch.autocast("cuda", dtype=torch.float16):
+        out = model(imgs.to(dev))
+        loss = b2u.CE_Loss(out, pngs.to(dev), torch.ones(C, device=dev), num_classes=C) + b2u.Dice_loss(out, O.one_hot(pngs, C).to(dev))
+    scaler.scale(loss).backward()
+    scaler.unscale_(opt)
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    assert abs(loss.item() - l32.item()) <= 1e-2 * abs(l32.item())
+    assert _global_rel(grads, g32) <= 1e-2
+    scaler.step(opt); scaler.update()
+    created = False
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29577")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+        created = True
+    try:
+        m2 = b2u.Unet(num_classes=C, backbone="vgg")
+        m2.load_state_dict(sd)
+        ddp = torch.nn.parallel.DistributedDataParallel(m2.to(dev).train(), device_ids=[dev.index or 0], find_unused_parameters=True)
+        out = ddp(imgs.to(dev))
+        loss = b2u.CE_Loss(out, pngs.to(dev), torch.ones(C, device=dev), num_classes=C) + b2u.Dice_loss(out, O.one_hot(pngs, C).to(dev))
+        loss.backward()
+        assert _global_rel({k: p.grad for k, p in m2.named_parameters()}, g32) <= 1e-2
+    finally:
+        if created:
+            dist.destroy_process_group()
