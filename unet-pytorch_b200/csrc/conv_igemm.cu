@@ -48,8 +48,9 @@ struct ConvParams {
   int mask_c;
 };
 
-template <int BN, int TAPS, int MT, int RB, int SA, int SB>
+template <int BN, int TAPS, int MT, int RB, int SA, int SB, int MD = 0>
 struct ConvCfg {
+  // MD: depth of the cp.async ReLU-mask pipeline (0: mask rows are prefetched into registers one sub-tile ahead)
   // MT: M tiles (8x16 pixel patches, stacked vertically) per CTA step, sharing every B tile
   // RB: vertical taps per B pipeline stage (3: one barrier round trip per 12*MT MMAs, for the small-N tiles)
   static constexpr int kRowBytes = KB * 2;                      // swizzle span (128 B)
@@ -63,7 +64,8 @@ struct ConvCfg {
   static constexpr int kOffStage = kOffB + SB * kBBytes;
   static constexpr int kOffBias = kOffStage + 2 * kStageBytes;
   static constexpr int kOffStat = kOffBias + 2 * 256 * 4;    // [4 row quarters][64 channels][2] fp32 scratch of the BatchNorm-statistics pass
-  static constexpr int kOffBar = kOffStat + 4 * 64 * 2 * 4;  // (bias of the current N tile is double buffered by tile parity)
+  static constexpr int kOffMask = kOffStat + 4 * 64 * 2 * 4; // MD thread-private mask tiles [128 rows][128 B]
+  static constexpr int kOffBar = kOffMask + MD * kTileM * 128;  // (bias of the current N tile is double buffered by tile parity)
   static constexpr int kNumBar = 2 * SA + 2 * SB + 4;
   static constexpr int kOffTmem = kOffBar + kNumBar * 8;
   static constexpr int kSmemBytes = kOffTmem + 16 + 1024;  // + alignment slack
@@ -77,12 +79,12 @@ struct ConvCfg {
   static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
 };
 
-template <int BN, int TAPS, int MT, int RB, int SA, int SB>
+template <int BN, int TAPS, int MT, int RB, int SA, int SB, int MD = 0>
 __global__ void __launch_bounds__(192, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC0,
                   const __grid_constant__ CUtensorMap tmC1, const ConvParams p) {
-  using Cfg = ConvCfg<BN, TAPS, MT, RB, SA, SB>;
+  using Cfg = ConvCfg<BN, TAPS, MT, RB, SA, SB, MD>;
   constexpr int S_TAPS = TAPS == 9 ? 3 : 1;
   constexpr int R_TAPS = TAPS == 9 ? 3 : 1;
 
@@ -225,6 +227,39 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     uint32_t pacc = 0;
     uint32_t sbuf = 0;
     uint32_t bpar = 0;
+    // ReLU-mask stream for the memory-bound small-N tiles (MD > 0): every thread copies the 128-byte mask row of its
+    // pixel with cp.async into a thread-private slot, MD sub-tiles ahead of its use (across tile boundaries), so 16 KB x MD
+    // of mask bytes are in flight per SM instead of one register-held row per thread.
+    const uint32_t sMask = smem_base + Cfg::kOffMask;
+    int pf_tile = blockIdx.x, pf_jj = 0, pf_slot = 0, use_slot = 0;
+    auto mask_issue = [&]() {
+      if (MD > 0) {
+        if (pf_tile < total_tiles) {
+          const int n_tile_ = pf_tile % p.num_n_tiles;
+          int m_ = pf_tile / p.num_n_tiles;
+          const int tw_ = m_ % p.tiles_w; m_ /= p.tiles_w;
+          const int th_ = m_ % p.tiles_h;
+          const int img_ = m_ / p.tiles_h;
+          const int mt_ = pf_jj / (BN / 64), j_ = pf_jj % (BN / 64);
+          const int gh_ = th_ * (kHb * MT) + mt_ * kHb + ph, gw_ = tw_ * kWb + pw;
+          const bool inb_ = gh_ < p.H && gw_ < p.W;
+          const uint4* mrow = reinterpret_cast<const uint4*>(
+              p.mask + ((static_cast<size_t>(img_) * p.H + (inb_ ? gh_ : 0)) * p.W + (inb_ ? gw_ : 0)) * p.mask_c + n_tile_ * BN + j_ * 64);
+          const uint32_t dst = sMask + pf_slot * (kTileM * 128) + row * 128;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + ((q ^ (row & 7)) << 4)), "l"(mrow + q),
+                         "r"(inb_ ? 16 : 0) : "memory");
+          if (++pf_jj == MT * (BN / 64)) { pf_jj = 0; pf_tile += gridDim.x; }
+          if (++pf_slot == MD) pf_slot = 0;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");       // always: keeps the wait count uniform at the tail
+      }
+    };
+    if (MD > 0 && (p.flags & 2)) {
+#pragma unroll
+      for (int i = 0; i < (MD > 0 ? MD : 1); ++i) mask_issue();
+    }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.num_n_tiles;
       int m_tile = tile / p.num_n_tiles;
@@ -246,7 +281,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll
         for (int q = 0; q < 8; ++q) mreg[q] = inb_ ? __ldg(mrow + q) : make_uint4(0, 0, 0, 0);
       };
-      if (p.flags & 2) fetch_mask(0);
+      if (MD == 0 && (p.flags & 2)) fetch_mask(0);
       // this tile's bias slice; the parity double buffer + the barrier keep a fast warp from overwriting values a
       // slow warp of the previous tile still reads
       float* sB = sBias + bpar * 256;
@@ -292,6 +327,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const int cbase = n0 + j * 64;
         uint32_t packed[32];
         if (p.flags & 2) {
+          if (MD > 0) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(MD > 0 ? MD - 1 : 0) : "memory");
+            const uint32_t src = sMask + use_slot * (kTileM * 128) + row * 128;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(mreg[q].x), "=r"(mreg[q].y), "=r"(mreg[q].z), "=r"(mreg[q].w) : "r"(src + ((q ^ (row & 7)) << 4)));
+            if (++use_slot == MD) use_slot = 0;
+          }
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const uint32_t mm[4] = {mreg[q].x, mreg[q].y, mreg[q].z, mreg[q].w};
@@ -304,7 +348,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               packed[q * 4 + e] = pack_bf16x2(lo, hi);
             }
           }
-          if (jj + 1 < MT * (BN / 64)) fetch_mask(jj + 1);
+          if (MD > 0) mask_issue();             // refill the slot just consumed (its values now sit in `packed`)
+          else if (jj + 1 < MT * (BN / 64)) fetch_mask(jj + 1);
         } else {
           const bool relu = p.flags & 1;
 #pragma unroll
@@ -385,10 +430,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 // ----------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------
-template <int BN, int TAPS, int MT, int RB, int SA, int SB>
+template <int BN, int TAPS, int MT, int RB, int SA, int SB, int MD = 0>
 static int launch_cfg(const ConvLaunch& a, cudaStream_t st) {
-  using Cfg = ConvCfg<BN, TAPS, MT, RB, SA, SB>;
-  auto kern = conv_igemm_kernel<BN, TAPS, MT, RB, SA, SB>;
+  using Cfg = ConvCfg<BN, TAPS, MT, RB, SA, SB, MD>;
+  auto kern = conv_igemm_kernel<BN, TAPS, MT, RB, SA, SB, MD>;
   static bool attr_done[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -480,14 +525,17 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st) {
       case 256: return launch_cfg<256, 9, 1, 1, 3, 4>(a, st);
       case 192: return launch_cfg<192, 9, 1, 1, 3, 5>(a, st);
       case 128: return tall ? launch_cfg<128, 9, 2, 3, 2, 2>(a, st) : launch_cfg<128, 9, 1, 3, 3, 2>(a, st);
-      case 64:  return tall ? launch_cfg<64, 9, 2, 3, 3, 3>(a, st) : launch_cfg<64, 9, 1, 3, 4, 4>(a, st);
+      case 64:
+        // masked (dgrad + ReLU) Cin-side-64 layers are HBM-bound: the mask rows go through the cp.async stream
+        if (tall && (a.flags & 2)) return launch_cfg<64, 9, 2, 3, 3, 2, 2>(a, st);
+        return tall ? launch_cfg<64, 9, 2, 3, 3, 3>(a, st) : launch_cfg<64, 9, 1, 3, 4, 4>(a, st);
     }
   } else {
     switch (bn) {
       case 256: return launch_cfg<256, 1, 1, 1, 3, 3>(a, st);
       case 192: return launch_cfg<192, 1, 1, 1, 4, 4>(a, st);
       case 128: return launch_cfg<128, 1, 1, 1, 4, 4>(a, st);
-      case 64:  return launch_cfg<64, 1, 2, 1, 3, 4>(a, st);
+      case 64:  return (a.flags & 2) ? launch_cfg<64, 1, 2, 1, 3, 4, 3>(a, st) : launch_cfg<64, 1, 2, 1, 3, 4>(a, st);
     }
   }
   return set_error(B2U_ERR_SHAPE, "conv: unsupported N tile %d", bn);
