@@ -98,13 +98,29 @@ def resnet50_unet_program(num_classes):
     return P, convs
 
 
-def light_conv_block_ops(P, convs, prefix, x, cin, cout, mid_min, x1=None, c1=0):
-    """Appends one LightConvBlock (1x1 conv, BN, ReLU, depthwise 3x3, 1x1 conv, BN, ReLU) reading x (and x1: virtual concat)."""
-    def conv(out, xin, w, ci, co, bias, x1=None, c1=0):
+def light_conv_block_ops(P, convs, prefix, x, cin, cout, mid_min, x1=None, c1=0, pack_mid=True):
+    """Appends one LightConvBlock (1x1 conv, BN, ReLU, depthwise 3x3, 1x1 conv, BN, ReLU) reading x (and x1: virtual concat).
+
+    pack_mid: a mid width of 16 or 32 channels is stored DENSE ([N,H,W,mid], not zero-padded to 64) and the two 1x1 convs
+    around it see it as [N,H,W/f,64] with f = 64/mid pixels per row and block-diagonal weights (kron(I_f, W)): the GEMM does
+    f x the multiply-adds on zeros, but these layers are HBM-bound and every pass over the mid tensors (conv out, BN
+    statistics/apply, depthwise, and all their gradients) moves 1/f of the bytes."""
+    def conv(out, xin, w, ci, co, bias, x1=None, c1=0, pk=None, pix=1):
         convs[w] = (co, ci, c1, 1)
-        P.append(dict(op="conv", out=out, x=xin, x1=x1, w=w, bias=bias, cin=ci, c1=c1, cout=co, taps=1, stride=1, relu=False))
+        P.append(dict(op="conv", out=out, x=xin, x1=x1, w=w, bias=bias, cin=ci, c1=c1, cout=co, taps=1, stride=1, relu=False,
+                      pk=pk, pix=pix))
 
     mid = max(mid_min, cout // 2)
+    if pack_mid and mid in (16, 32):
+        f = 64 // mid
+        conv(prefix + ".z1", x, prefix + ".conv.0.weight", cin, mid, prefix + ".conv.0.bias", x1=x1, c1=c1, pk="to", pix=f)
+        P.append(dict(op="bn", out=prefix + ".y1", z=prefix + ".z1", bn=prefix + ".conv.1", c=mid, relu=True, res=None))
+        P.append(dict(op="dw", out=prefix + ".d", x=prefix + ".y1", w=prefix + ".conv.3.depthwise.weight",
+                      bias=prefix + ".conv.3.depthwise.bias", c=mid))
+        conv(prefix + ".z2", prefix + ".d", prefix + ".conv.3.pointwise.weight", mid, cout, prefix + ".conv.3.pointwise.bias",
+             pk="from", pix=f)
+        P.append(dict(op="bn", out=prefix + ".out", z=prefix + ".z2", bn=prefix + ".conv.4", c=cout, relu=True, res=None))
+        return prefix + ".out"
     conv(prefix + ".z1", x, prefix + ".conv.0.weight", cin, mid, prefix + ".conv.0.bias", x1=x1, c1=c1)
     P.append(dict(op="bn", out=prefix + ".y1", z=prefix + ".z1", bn=prefix + ".conv.1", c=mid, relu=True, res=None))
     P.append(dict(op="dw", out=prefix + ".d", x=prefix + ".y1", w=prefix + ".conv.3.depthwise.weight",
@@ -221,6 +237,7 @@ class GraphEngine:
         self._pack_total = 0
         self.saved = None
         self.has_stem = any(i["op"] == "stem" for i in program)
+        self.pk = {i["w"]: i for i in program if i["op"] == "conv" and i.get("pk")}     # pixel-packed 1x1 convs
         self.dropout_override = None
         # db from the wgrad kernel's bias warps instead of a separate pass over dz: measured on one box (scripts/ab_fuse_bias.py)
         # it does not change the step time (the extra smem reads slow the bias-owning work units), so it stays off
@@ -319,6 +336,15 @@ class GraphEngine:
         b[tuple(slice(0, d) for d in t.shape)].copy_(t)
         return b
 
+    def _tiled(self, key, t, width, f):
+        """fp32 vector zero-padded to `width` and repeated f times (bias of a pixel-packed conv)."""
+        b = self._bufs.get(key)
+        if b is None or b.numel() != width * f:
+            b = torch.zeros((f, width), dtype=torch.float32, device=self.device)
+            self._bufs[key] = b
+        b[:, :t.numel()].copy_(t.reshape(1, -1).expand(f, -1))
+        return b.view(-1)
+
     def release(self):
         self._bufs.clear(); self._ws.clear(); self.saved = None
 
@@ -337,17 +363,42 @@ class GraphEngine:
             for n in names:
                 cout, c0, c1, taps = self.convs[n]
                 c0p, c1p, coutp = pad64(c0), (pad64(c1) if c1 else 0), pad64(cout)
+                src = params[n]
+                if n in self.pk:            # the view problem: block-diagonal weights over f pixels (built below)
+                    f, kind = self.pk[n]["pix"], self.pk[n]["pk"]
+                    if kind == "to":        # dense 64-padded inputs -> packed `cout` (= mid) channels
+                        cout, c0, c1 = 64, f * c0p, f * c1p
+                    else:                   # packed `c0` (= mid) channels -> dense 64-padded outputs
+                        cout, c0, c1 = f * coutp, 64, 0
+                    c0p, c1p, coutp = c0, c1, cout
+                    src = self._bufs.get("w2:" + n)
+                    if src is None or tuple(src.shape) != (cout, c0 + c1, 1, 1):
+                        src = torch.zeros((cout, c0 + c1, 1, 1), dtype=torch.float32, device=dev)
+                        self._bufs["w2:" + n] = src
                 wf, wd = self._packed.get(n, (None, None))
                 if wf is None:
                     wf = torch.zeros((coutp, taps * (c0p + c1p)), dtype=torch.bfloat16, device=dev)
                 if need_dgrad and wd is None:
                     wd = torch.zeros((c0p + c1p, taps * coutp), dtype=torch.bfloat16, device=dev)
                 self._packed[n] = (wf, wd)
-                blob += struct.pack("<QQQqiiiiiiii", params[n].data_ptr(), wf.data_ptr(), wd.data_ptr() if need_dgrad else 0,
+                blob += struct.pack("<QQQqiiiiiiii", src.data_ptr(), wf.data_ptr(), wd.data_ptr() if need_dgrad else 0,
                                     start, cout, c0 + c1, taps, 0, c0, c0p, c0p + c1p, coutp)
                 start += ((cout + 31) // 32) * ((c0 + c1 + 31) // 32)
             self._pack_table = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
             self._pack_total, self._pack_key = start, key
+        for n, ins in self.pk.items():          # refresh the block-diagonal fp32 weights kron(I_f, W) of the packed convs
+            f, w2, w = ins["pix"], self._bufs["w2:" + n], params[n]
+            if ins["pk"] == "to":
+                mid, c0r, c1r = ins["cout"], ins["cin"], ins["c1"]
+                c0p, c1p = pad64(c0r), (pad64(c1r) if c1r else 0)
+                for k in range(f):
+                    w2[k * mid:(k + 1) * mid, k * c0p:k * c0p + c0r].copy_(w[:, :c0r])
+                    if c1r:
+                        w2[k * mid:(k + 1) * mid, f * c0p + k * c1p:f * c0p + k * c1p + c1r].copy_(w[:, c0r:])
+            else:
+                mid, co, cop = ins["cin"], ins["cout"], pad64(ins["cout"])
+                for k in range(f):
+                    w2[k * cop:k * cop + co, k * mid:(k + 1) * mid].copy_(w)
         ops.check(ops.lib().b2u_pack_weights_multi(self._pack_table.data_ptr(), len(names), self._pack_total, ops.stream_ptr()))
         if self.has_stem:
             self._stem_wf = ops.pack_weights_im2col(params["resnet.conv1.weight"], 192, wf=getattr(self, "_stem_wf", None))
@@ -388,6 +439,19 @@ class GraphEngine:
                 x1 = T[ins["x1"]] if ins["x1"] else None
                 wf, _ = self._packed[ins["w"]]
                 n, h, w, _ = xin.data.shape
+                if ins.get("pk"):           # pixel-packed 1x1 conv: every tensor is viewed with f pixels per row
+                    f = ins["pix"]
+                    if ins["pk"] == "to":
+                        z = self._buf(ins["out"], (n, h, w, ins["cout"]))           # dense, `mid` channels
+                        bias = self._tiled("b2:" + ins["w"], params[ins["bias"]], ins["cout"], f)
+                    else:
+                        z = self._buf(ins["out"], (n, h, w, pad64(ins["cout"])))
+                        bias = self._tiled("b2:" + ins["w"], params[ins["bias"]], pad64(ins["cout"]), f)
+                    ops.conv_fprop(xin.data.view(n, h, w // f, -1), wf, bias, z.shape[3] * f, taps=1, relu=False,
+                                   x1=x1.data.view(n, h, w // f, -1) if x1 else None, out=z.view(n, h, w // f, -1))
+                    ng = xin.needs_grad or (x1 is not None and x1.needs_grad) or ins["w"] in trainable or (ins["bias"] in trainable)
+                    T[ins["out"]] = _T(z, needs_grad=ng)
+                    continue
                 coutp = pad64(ins["cout"])
                 bias = self._padded("b:" + ins["w"], params[ins["bias"]], (coutp,)) if ins["bias"] else None
                 aux = None
@@ -686,6 +750,59 @@ class GraphEngine:
                 wf, wd = self._packed[ins["w"]]
                 n, h, w, _ = xin.data.shape
                 taps, cout, c0r, c1r = ins["taps"], ins["cout"], ins["cin"], ins["c1"]
+                if ins.get("pk"):
+                    # pixel-packed 1x1 conv: wgrad / dgrad of the view problem (f pixels per row, block-diagonal weights);
+                    # the real weight gradient is the sum of the f diagonal blocks
+                    f = ins["pix"]
+                    xv = xin.data.view(n, h, w // f, -1)
+                    x1v = x1.data.view(n, h, w // f, -1) if x1 else None
+                    dzv = dz.view(n, h, w // f, -1)
+                    cin_v = xv.shape[3] + (x1v.shape[3] if x1 else 0)
+                    if has(ins["w"]):
+                        need = ops.lib().b2u_conv_wgrad_workspace(n, h, w // f, cin_v, dzv.shape[3], 1)
+                        tmp = self._buf("dw:" + ins["w"], (dzv.shape[3], cin_v, 1, 1), torch.float32)
+                        ops.conv_wgrad(xv, dzv, taps=1, x1=x1v, dw=tmp, ws=self._workspace("wgrad", need))
+                        gw = grads[ins["w"]]
+                        if ins["pk"] == "to":
+                            mid, c0p = cout, xin.data.shape[3]
+                            c1p = x1.data.shape[3] if x1 else 0
+                            for k in range(f):
+                                blk = tmp[k * mid:(k + 1) * mid]
+                                if k == 0:
+                                    gw[:, :c0r].copy_(blk[:, k * c0p:k * c0p + c0r])
+                                else:
+                                    gw[:, :c0r].add_(blk[:, k * c0p:k * c0p + c0r])
+                                if c1r:
+                                    src = blk[:, f * c0p + k * c1p:f * c0p + k * c1p + c1r]
+                                    if k == 0:
+                                        gw[:, c0r:].copy_(src)
+                                    else:
+                                        gw[:, c0r:].add_(src)
+                        else:
+                            mid, cop = c0r, dz.shape[3]
+                            for k in range(f):
+                                src = tmp[k * cop:k * cop + cout, k * mid:(k + 1) * mid]
+                                if k == 0:
+                                    gw.copy_(src)
+                                else:
+                                    gw.add_(src)
+                    if has(ins["bias"]):
+                        grads[ins["bias"]].zero_()          # both packed convs of a LightConvBlock sit in front of a BatchNorm
+                    ready(ins["w"], ins["bias"])
+                    need0, need1 = xin.needs_grad, (x1 is not None and x1.needs_grad)
+                    if need0 or need1:
+                        d0 = self._buf("g:" + ins["out"] + ">0", xin.data.shape)
+                        if x1 is not None:
+                            d1 = self._buf("g:" + ins["out"] + ">1", x1.data.shape)
+                            ops.conv_dgrad(dzv, wd, xv.shape[3], taps=1, C1=x1v.shape[3], out0=d0.view(xv.shape), out1=d1.view(x1v.shape))
+                            if need0:
+                                self._acc_masked(xin, d0)
+                            if need1:
+                                self._acc_masked(x1, d1)
+                        else:
+                            ops.conv_dgrad(dzv, wd, xv.shape[3], taps=1, out0=d0.view(xv.shape))
+                            self._acc(xin, d0)
+                    continue
                 coutp = pad64(cout)
                 if ins["stride"] == 2 and taps == 9:
                     dz = ops.zero_insert2(dz, h, w, out=self._buf("g:" + ins["out"] + ":full", (n, h, w, coutp)))
