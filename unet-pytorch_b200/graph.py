@@ -101,7 +101,7 @@ def resnet50_unet_program(num_classes):
 def light_conv_block_ops(P, convs, prefix, x, cin, cout, mid_min, x1=None, c1=0, pack_mid=True):
     """Appends one LightConvBlock (1x1 conv, BN, ReLU, depthwise 3x3, 1x1 conv, BN, ReLU) reading x (and x1: virtual concat).
 
-    pack_mid: a mid width of 16 or 32 channels is stored DENSE ([N,H,W,mid], not zero-padded to 64) and the two 1x1 convs
+    pack_mid: a mid width of at most 32 channels is stored at 16 or 32 channels ([N,H,W,64/f], not zero-padded to 64) and the two 1x1 convs
     around it see it as [N,H,W/f,64] with f = 64/mid pixels per row and block-diagonal weights (kron(I_f, W)): the GEMM does
     f x the multiply-adds on zeros, but these layers are HBM-bound and every pass over the mid tensors (conv out, BN
     statistics/apply, depthwise, and all their gradients) moves 1/f of the bytes."""
@@ -111,8 +111,8 @@ def light_conv_block_ops(P, convs, prefix, x, cin, cout, mid_min, x1=None, c1=0,
                       pk=pk, pix=pix))
 
     mid = max(mid_min, cout // 2)
-    if pack_mid and mid in (16, 32):
-        f = 64 // mid
+    if pack_mid and mid <= 32:
+        f = 4 if mid <= 16 else 2        # stored width 64 / f (16 or 32 channels; e.g. 22 real channels are padded to 32)
         conv(prefix + ".z1", x, prefix + ".conv.0.weight", cin, mid, prefix + ".conv.0.bias", x1=x1, c1=c1, pk="to", pix=f)
         P.append(dict(op="bn", out=prefix + ".y1", z=prefix + ".z1", bn=prefix + ".conv.1", c=mid, relu=True, res=None))
         P.append(dict(op="dw", out=prefix + ".d", x=prefix + ".y1", w=prefix + ".conv.3.depthwise.weight",
@@ -388,17 +388,18 @@ class GraphEngine:
             self._pack_total, self._pack_key = start, key
         for n, ins in self.pk.items():          # refresh the block-diagonal fp32 weights kron(I_f, W) of the packed convs
             f, w2, w = ins["pix"], self._bufs["w2:" + n], params[n]
+            midp = 64 // f
             if ins["pk"] == "to":
                 mid, c0r, c1r = ins["cout"], ins["cin"], ins["c1"]
                 c0p, c1p = pad64(c0r), (pad64(c1r) if c1r else 0)
                 for k in range(f):
-                    w2[k * mid:(k + 1) * mid, k * c0p:k * c0p + c0r].copy_(w[:, :c0r])
+                    w2[k * midp:k * midp + mid, k * c0p:k * c0p + c0r].copy_(w[:, :c0r])
                     if c1r:
-                        w2[k * mid:(k + 1) * mid, f * c0p + k * c1p:f * c0p + k * c1p + c1r].copy_(w[:, c0r:])
+                        w2[k * midp:k * midp + mid, f * c0p + k * c1p:f * c0p + k * c1p + c1r].copy_(w[:, c0r:])
             else:
                 mid, co, cop = ins["cin"], ins["cout"], pad64(ins["cout"])
                 for k in range(f):
-                    w2[k * cop:k * cop + co, k * mid:(k + 1) * mid].copy_(w)
+                    w2[k * cop:k * cop + co, k * midp:k * midp + mid].copy_(w)
         ops.check(ops.lib().b2u_pack_weights_multi(self._pack_table.data_ptr(), len(names), self._pack_total, ops.stream_ptr()))
         if self.has_stem:
             self._stem_wf = ops.pack_weights_im2col(params["resnet.conv1.weight"], 192, wf=getattr(self, "_stem_wf", None))
@@ -442,8 +443,8 @@ class GraphEngine:
                 if ins.get("pk"):           # pixel-packed 1x1 conv: every tensor is viewed with f pixels per row
                     f = ins["pix"]
                     if ins["pk"] == "to":
-                        z = self._buf(ins["out"], (n, h, w, ins["cout"]))           # dense, `mid` channels
-                        bias = self._tiled("b2:" + ins["w"], params[ins["bias"]], ins["cout"], f)
+                        z = self._buf(ins["out"], (n, h, w, 64 // f))               # 16 or 32 stored channels
+                        bias = self._tiled("b2:" + ins["w"], params[ins["bias"]], 64 // f, f)
                     else:
                         z = self._buf(ins["out"], (n, h, w, pad64(ins["cout"])))
                         bias = self._tiled("b2:" + ins["w"], params[ins["bias"]], pad64(ins["cout"]), f)
@@ -763,11 +764,12 @@ class GraphEngine:
                         tmp = self._buf("dw:" + ins["w"], (dzv.shape[3], cin_v, 1, 1), torch.float32)
                         ops.conv_wgrad(xv, dzv, taps=1, x1=x1v, dw=tmp, ws=self._workspace("wgrad", need))
                         gw = grads[ins["w"]]
+                        midp = 64 // f
                         if ins["pk"] == "to":
                             mid, c0p = cout, xin.data.shape[3]
                             c1p = x1.data.shape[3] if x1 else 0
                             for k in range(f):
-                                blk = tmp[k * mid:(k + 1) * mid]
+                                blk = tmp[k * midp:k * midp + mid]
                                 if k == 0:
                                     gw[:, :c0r].copy_(blk[:, k * c0p:k * c0p + c0r])
                                 else:
@@ -781,7 +783,7 @@ class GraphEngine:
                         else:
                             mid, cop = c0r, dz.shape[3]
                             for k in range(f):
-                                src = tmp[k * cop:k * cop + cout, k * mid:(k + 1) * mid]
+                                src = tmp[k * cop:k * cop + cout, k * midp:k * midp + mid]
                                 if k == 0:
                                     gw.copy_(src)
                                 else:
