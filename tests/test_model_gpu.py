@@ -698,3 +698,25 @@ def test_reference_training_wrappers(b2u, cuda_device):
     finally:
         if created:
             dist.destroy_process_group()
+
+
+def test_dataparallel_two_gpus(b2u, cuda_device):
+    """train.py:348 wraps the model in nn.DataParallel when it is not running distributed: replicas on two GPUs (one engine
+    per device, shared through the module's engine table) must give the single-GPU result on the concatenated batch."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    dev = cuda_device
+    C = 4
+    sd = O.make_params(C, seed=11)
+    imgs, pngs = O.make_inputs(4, C, 64, 64, seed=6)
+    l32, z32, g32 = O.train_step(sd, imgs, pngs, torch.ones(C), C, dice=True)
+    model = b2u.Unet(num_classes=C, backbone="vgg")
+    model.load_state_dict(sd)
+    dp = torch.nn.DataParallel(model.to(dev).train(), device_ids=[0, 1])
+    out = dp(imgs.to(dev))
+    assert out.shape == z32.shape and rel(out, z32) <= 1e-2
+    loss = b2u.CE_Loss(out, pngs.to(dev), torch.ones(C, device=dev), num_classes=C) + b2u.Dice_loss(out, O.one_hot(pngs, C).to(dev))
+    loss.backward()
+    assert abs(loss.item() - l32.item()) <= 1e-2 * abs(l32.item())
+    assert _global_rel({k: p.grad for k, p in model.named_parameters()}, g32) <= 1e-2
+    assert len(model._engines) == 2

@@ -10,7 +10,7 @@ class EngineFunction(torch.autograd.Function):
         engine = module._engine_for(x.device)
         names = module._param_names
         tensors = dict(zip(names, params))
-        tensors.update(dict(module.named_buffers()))          # BatchNorm running statistics (updated in place)
+        tensors.update(module._named_buffer_tensors())        # BatchNorm running statistics (updated in place)
         needs = any(ctx.needs_input_grad[2:])
         trainable = {n for n, need in zip(names, ctx.needs_input_grad[2:]) if need}
         logits = engine.forward(x, tensors, save=needs, training=module.training, trainable=trainable)
@@ -37,10 +37,6 @@ class EngineModuleMixin:
     """Gives an nn.Module (a pure parameter container) a forward() that runs on the CUDA engine.  One engine per
     device: nn.DataParallel replicas share this object's dict, each device thread gets its own engine."""
 
-    def _init_engine_state(self):
-        self._engines = {}
-        self._engine_lock = threading.Lock()
-
     def _make_engine(self, device):
         raise NotImplementedError
 
@@ -53,13 +49,30 @@ class EngineModuleMixin:
                 self._engines[key] = eng
             return eng
 
+    def _init_engine_state(self):
+        self._engines = {}
+        self._engine_lock = threading.Lock()
+        # names are fixed at construction: nn.DataParallel replicas carry their parameters as plain tensor attributes
+        # (named_parameters() is empty there), so tensors are always fetched by walking the module tree by name
+        self._pnames = [n for n, _ in self.named_parameters()]
+        self._bnames = [n for n, _ in self.named_buffers()]
+
     @property
     def _param_names(self):
-        return [n for n, _ in self.named_parameters()]
+        return self._pnames
+
+    def _by_name(self, name):
+        obj = self
+        for part in name.split("."):
+            obj = getattr(obj, part)
+        return obj
+
+    def _named_buffer_tensors(self):
+        return {n: self._by_name(n) for n in self._bnames}
 
     def _engine_forward(self, inputs):
         if not inputs.is_cuda:
             raise RuntimeError(f"unet_pytorch_b200.{type(self).__name__} runs on a B200 only: move the module and inputs "
                                "to CUDA (there is no CPU fallback)")
-        params = [p for _, p in self.named_parameters()]
+        params = [self._by_name(n) for n in self._pnames]
         return EngineFunction.apply(self, inputs, *params)
