@@ -208,7 +208,7 @@ loss_stats_kernel(const float* __restrict__ logits, const long long* __restrict_
     for (int c = 0; c < kMaxCls; ++c) if (c < C) { v[c] = __ldg(z + c * HW); m = fmaxf(m, v[c]); }
     float sum = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxCls; ++c) if (c < C) { v[c] = expf(v[c] - m); sum += v[c]; }
+    for (int c = 0; c < kMaxCls; ++c) if (c < C) { v[c] = __expf(v[c] - m); sum += v[c]; }
     const float inv = 1.f / sum;
     const float lse = m + logf(sum);
     long long y = target ? target[p] : -1;
@@ -295,7 +295,7 @@ loss_stats_map_kernel(const float* __restrict__ logits, const long long* __restr
     const float zy = valid ? __ldg(z + y * HW) : 0.f;
     float sum = 0.f;
 #pragma unroll
-    for (int c = 0; c < CM; ++c) if (c < C) { v[c] = expf(v[c] - m); sum += v[c]; }
+    for (int c = 0; c < CM; ++c) if (c < C) { v[c] = __expf(v[c] - m); sum += v[c]; }   // arguments <= 0: ex2.approx, <= 2 ulp near the max class
     const float inv = 1.f / sum;
     if (inb) {
 #pragma unroll
@@ -360,13 +360,23 @@ loss_stats_map_kernel(const float* __restrict__ logits, const long long* __restr
 
 // out (floats): [0] CE  [1] Focal  [2] Dice loss  [3] f_score, then per class A_c (4..4+C) and B_c (4+C..4+2C)
 // (Dice backward coefficients), then [4+2C] = 1/sum_w, [4+2C+1] = 1/pixel count.
-__global__ void loss_finalize_kernel(const double* __restrict__ partial, int blocks, int C, float beta, float smooth,
-                                     float* __restrict__ out, double* __restrict__ stats_out) {
-  extern __shared__ double tot[];
+__global__ void __launch_bounds__(1024)
+loss_finalize_kernel(const double* __restrict__ partial, int blocks, int C, float beta, float smooth,
+                     float* __restrict__ out, double* __restrict__ stats_out) {
+  extern __shared__ double tot[];            // [L] totals, then [4][L] staging
   const int L = 5 * C + 4;
-  for (int s = threadIdx.x; s < L; s += blockDim.x) {
+  double* part = tot + L;
+  // 4 lanes per slot walk the block partials with stride 4 (fixed order -> deterministic), then fold
+  const int lanes = 4;
+  for (int i = threadIdx.x; i < L * lanes; i += blockDim.x) {
+    const int s = i % L, q = i / L;
     double d = 0.0;
-    for (int b = 0; b < blocks; ++b) d += partial[static_cast<size_t>(b) * L + s];
+    for (int b = q; b < blocks; b += lanes) d += partial[static_cast<size_t>(b) * L + s];
+    part[q * L + s] = d;
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < L; s += blockDim.x) {
+    const double d = (part[s] + part[L + s]) + (part[2 * L + s] + part[3 * L + s]);
     tot[s] = d;
     if (stats_out) stats_out[s] = d;
   }
@@ -425,7 +435,7 @@ loss_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ 
   for (int c = 0; c < CM; ++c) if (c < C) { if (valid && c == y) zy = v[c]; }
   float sum = 0.f;
 #pragma unroll
-  for (int c = 0; c < CM; ++c) if (c < C) { v[c] = expf(v[c] - m); sum += v[c]; }
+  for (int c = 0; c < CM; ++c) if (c < C) { v[c] = __expf(v[c] - m); sum += v[c]; }   // arguments <= 0: ex2.approx, <= 2 ulp near the max class
   const float inv = 1.f / sum;
   // per-pixel scalar multiplying (p - onehot_y): CE and focal share the direction
   float k_py = 0.f;
@@ -569,7 +579,7 @@ softmax_resize_argmax_kernel(const float* __restrict__ logits, uint8_t* __restri
     for (int c = 0; c < CM; ++c) if (c < C) { v[c] = __ldg(base + c * plane + o[t]); m = fmaxf(m, v[c]); }
     float sum = 0.f;
 #pragma unroll
-    for (int c = 0; c < CM; ++c) if (c < C) { v[c] = expf(v[c] - m); sum += v[c]; }
+    for (int c = 0; c < CM; ++c) if (c < C) { v[c] = __expf(v[c] - m); sum += v[c]; }   // arguments <= 0: ex2.approx, <= 2 ulp near the max class
     const float k = wgt[t] / sum;
 #pragma unroll
     for (int c = 0; c < CM; ++c) if (c < C) acc[c] = fmaf(k, v[c], acc[c]);
@@ -653,7 +663,7 @@ int b2u_loss_fwd(const float* logits, const long long* target, const float* oneh
 #undef B2U_STATS
   }
   B2U_CHECK_LAUNCH("loss_stats");
-  loss_finalize_kernel<<<1, 128, L * sizeof(double), st>>>(static_cast<const double*>(ws), blocks, C, beta, smooth, out, stats);
+  loss_finalize_kernel<<<1, 1024, 5 * L * sizeof(double), st>>>(static_cast<const double*>(ws), blocks, C, beta, smooth, out, stats);
   B2U_CHECK_LAUNCH("loss_finalize");
   return 0;
 }
