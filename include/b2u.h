@@ -112,6 +112,13 @@ int b2u_bn_fwd_train_stats(const void* z, const void* residual, void* y, const f
 int b2u_bn_fwd_eval(const void* z, const void* residual, void* y, const float* gamma, const float* beta,
                     const float* running_mean, const float* running_var, void* ws, size_t ws_bytes, long long P, int C,
                     float eps, int relu, void* stream);
+/* eval-mode conv -> nn.BatchNorm2d (-> ReLU) as ONE kernel: b2u_bn_fold gives scale = gamma / sqrt(rv + eps) and
+ * bias = (conv_bias - rm) * scale + beta; b2u_conv_fprop_scaled applies y = [relu](acc * scale + bias) in the conv epilogue
+ * (model.eval() inference of the BatchNorm nets: no z tensor, no BatchNorm pass) */
+int b2u_bn_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                const float* conv_bias, float* scale, float* bias, int C, float eps, void* stream);
+int b2u_conv_fprop_scaled(const void* x0, int C0, const void* x1, int C1, const void* wf, const float* scale, const float* bias,
+                          void* y, int N, int H, int W, int Cout, int taps, int relu, int bn_override, void* stream);
 /* dy = gradient wrt y; dz (may alias dy) = gradient wrt z; gout (nullable) = ReLU-masked dy = gradient wrt the residual;
  * dgamma/dbeta nullable.  y = the forward output, required only when a residual was added before the ReLU; with
  * y == NULL the ReLU mask is recomputed from z, gamma, beta and the saved statistics exactly as the forward evaluated

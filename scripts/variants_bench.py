@@ -35,6 +35,15 @@ def main():
             tr.train_step(imgs, pngs)
         b.record(); torch.cuda.synchronize()
         ms = a.elapsed_time(b) / args.steps
+        # inference forward (model.eval(): BatchNorm folded into the conv epilogues), logits only
+        for _ in range(2):
+            tr.engine.forward(imgs, tr.tensors, save=False, training=False)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(args.steps):
+            tr.engine.forward(imgs, tr.tensors, save=False, training=False)
+        b.record(); torch.cuda.synchronize()
+        ms_inf = a.elapsed_time(b) / args.steps
         with _lib.CallProfile(by_shape=args.by_shape) as prof:
             tr.train_step(imgs, pngs)
         calls = prof.read()
@@ -42,6 +51,7 @@ def main():
         top = sorted(calls.items(), key=lambda kv: -kv[1]["ms"])[:40 if args.by_shape else 25]
         res[model] = {"classes": C, "ms_per_step": ms, "img_per_s": args.batch * 1e3 / ms,
                       "params": int(sum(p.numel() for p in tr.params.values())),
+                      "eval_forward_ms": ms_inf, "eval_forward_img_per_s": args.batch * 1e3 / ms_inf,
                       "profiled_step_ms_sum": tot,
                       "by_entry_point": {k: {"launches": v["launches"], "ms": round(v["ms"], 4)} for k, v in top}}
         if args.cpu_baseline:

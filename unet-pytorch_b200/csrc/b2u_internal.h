@@ -32,6 +32,7 @@ struct ConvLaunch {
   const void* x1 = nullptr; int C1 = 0;     // optional source 1 (virtual concat), same N,H,W
   const void* wpacked = nullptr;            // bf16 [Cout][taps*(C0+C1)]
   const float* bias = nullptr;              // fp32 [Cout] or null
+  const float* scale = nullptr;             // fp32 [Cout] or null: y = acc * scale + bias (eval-mode BatchNorm folded into the conv)
   void* y0 = nullptr; void* y1 = nullptr;   // outputs (NHWC bf16); y1 receives channels >= split_c
   int split_c = 0;
   const __nv_bfloat16* mask = nullptr; int mask_c = 0;

@@ -187,6 +187,18 @@ __global__ void bn_eval_coeff_kernel(const float* __restrict__ gamma, const floa
   shift[c] = bt - running_mean[c] * g * is;
 }
 
+// eval-mode BatchNorm folded into the preceding conv: y = acc * scale + bias with scale = gamma / sqrt(rv + eps),
+// bias = (conv_bias - rm) * scale + beta
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ rm,
+                               const float* __restrict__ rv, const float* __restrict__ conv_bias, float* __restrict__ scale,
+                               float* __restrict__ bias, int C, float eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float s = (gamma ? gamma[c] : 1.f) / sqrtf(rv[c] + eps);
+  scale[c] = s;
+  bias[c] = ((conv_bias ? conv_bias[c] : 0.f) - rm[c]) * s + (beta ? beta[c] : 0.f);
+}
+
 // y = [relu](z * scale + shift).  One thread = one 8-channel chunk of kBnApplyRows rows spaced G rows apart (so a warp's
 // loads stay contiguous): the per-channel coefficients are loaded once and all the rows' 16-byte loads are in flight
 // together.
@@ -351,6 +363,15 @@ int b2u_bn_fwd_train_stats(const void* z, const void* residual, void* y, const f
   bn_apply_kernel<<<static_cast<unsigned>((G * (C / 8) + 255) / 256), 256, 0, st>>>(static_cast<const uint4*>(z), static_cast<const uint4*>(residual),
                                                                                    static_cast<uint4*>(y), coef, coef + C, P, G, C / 8, relu);
   B2U_CHECK_LAUNCH("bn_apply");
+  return 0;
+}
+
+int b2u_bn_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                const float* conv_bias, float* scale, float* bias, int C, float eps, void* stream) {
+  if (C <= 0 || !running_mean || !running_var || !scale || !bias) return set_error(B2U_ERR_ARG, "bn_fold: bad arguments");
+  bn_fold_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(gamma, beta, running_mean, running_var, conv_bias,
+                                                                                scale, bias, C, eps);
+  B2U_CHECK_LAUNCH("bn_fold");
   return 0;
 }
 

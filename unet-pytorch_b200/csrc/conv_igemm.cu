@@ -44,6 +44,7 @@ struct ConvParams {
   float* head_out;   // bit2: fp32 NCHW logits [N][head_cls][H][W]
   int head_cls;
   const float* bias; // [Cout] or null (head: [head_cls])
+  const float* scale;   // [Cout] or null: per-channel multiplier of the accumulator (folded eval-mode BatchNorm)
   const __nv_bfloat16* mask;  // NHWC [N,H,W,mask_c] or null; keeps y where mask > 0
   int mask_c;
 };
@@ -285,8 +286,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       // this tile's bias slice; the parity double buffer + the barrier keep a fast warp from overwriting values a
       // slow warp of the previous tile still reads
       float* sB = sBias + bpar * 256;
-      for (int c = threadIdx.x - 64; c < BN; c += 128)
+      float* sS = sStat + bpar * 256;      // the statistics scratch doubles as the scale buffer (training vs eval: never both)
+      for (int c = threadIdx.x - 64; c < BN; c += 128) {
         sB[c] = (p.bias && (!(p.flags & 4) || c < p.head_cls)) ? __ldg(p.bias + n0 + c) : 0.f;
+        if (p.scale) sS[c] = __ldg(p.scale + n0 + c);
+      }
       named_bar_sync(2, 128);
       bpar ^= 1u;
 
@@ -352,12 +356,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           else if (jj + 1 < MT * (BN / 64)) fetch_mask(jj + 1);
         } else {
           const bool relu = p.flags & 1;
+          if (p.scale) {          // y = [relu](acc * s + b'): conv + eval-mode BatchNorm (+ ReLU) in one epilogue
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            float lo = __uint_as_float(v[2 * e]) + sB[j * 64 + 2 * e];
-            float hi = __uint_as_float(v[2 * e + 1]) + sB[j * 64 + 2 * e + 1];
-            if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
-            packed[e] = pack_bf16x2(lo, hi);
+            for (int e = 0; e < 32; ++e) {
+              float lo = fmaf(__uint_as_float(v[2 * e]), sS[j * 64 + 2 * e], sB[j * 64 + 2 * e]);
+              float hi = fmaf(__uint_as_float(v[2 * e + 1]), sS[j * 64 + 2 * e + 1], sB[j * 64 + 2 * e + 1]);
+              if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+              packed[e] = pack_bf16x2(lo, hi);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              float lo = __uint_as_float(v[2 * e]) + sB[j * 64 + 2 * e];
+              float hi = __uint_as_float(v[2 * e + 1]) + sB[j * 64 + 2 * e + 1];
+              if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+              packed[e] = pack_bf16x2(lo, hi);
+            }
           }
         }
         // staging buffer `sbuf` was last read by the TMA store issued two sub-tiles ago
@@ -473,6 +487,7 @@ static int launch_cfg(const ConvLaunch& a, cudaStream_t st) {
   p.head_out = a.head_out;
   p.head_cls = a.head_cls;
   p.bias = a.bias;
+  p.scale = a.scale;
   p.mask = a.mask;
   p.mask_c = a.mask_c;
   const int total = p.num_m_tiles * p.num_n_tiles;
@@ -507,6 +522,8 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st) {
     return set_error(B2U_ERR_SHAPE, "conv: input channels (%d,%d) must be multiples of 64", a.C0, a.C1);
   if (a.y1 != nullptr && (a.split_c <= 0 || a.split_c >= a.Cout || a.split_c % 64 != 0))
     return set_error(B2U_ERR_SHAPE, "conv: split_c %d must be a multiple of 64 inside (0,Cout)", a.split_c);
+  if (a.scale && (a.stat_partial || (a.flags & 6)))
+    return set_error(B2U_ERR_ARG, "conv: a per-channel scale excludes the statistics, mask and head epilogues");
   if ((a.flags & 4) && (a.Cout != 64 || a.head_out == nullptr || a.head_cls < 1 || a.head_cls > 32 || a.y1 != nullptr))
     return set_error(B2U_ERR_SHAPE, "conv: head mode needs Cout == 64, 1..32 classes and an fp32 output");
   int bn = 0;
@@ -580,6 +597,21 @@ int b2u_conv_fprop_stats(const void* x0, int C0, const void* x1, int C1, const v
   a.bn_override = bn_override & 0xffff;
   a.tile_flags = bn_override >> 16;
   a.stat_partial = stat_partial;
+  return b2u::launch_conv(a, static_cast<cudaStream_t>(stream));
+}
+
+// y = [relu](conv(x) * scale[c] + bias[c]): a conv followed by eval-mode nn.BatchNorm2d (+ReLU) in one kernel; scale/bias
+// come from b2u_bn_fold (scale = gamma / sqrt(rv + eps), bias = (conv_bias - rm) * scale + beta).
+int b2u_conv_fprop_scaled(const void* x0, int C0, const void* x1, int C1, const void* wf, const float* scale, const float* bias,
+                          void* y, int N, int H, int W, int Cout, int taps, int relu, int bn_override, void* stream) {
+  if (!scale) return b2u::set_error(B2U_ERR_ARG, "conv_fprop_scaled: scale vector missing");
+  b2u::ConvLaunch a;
+  a.x0 = x0; a.C0 = C0; a.x1 = x1; a.C1 = x1 ? C1 : 0;
+  a.wpacked = wf; a.bias = bias; a.scale = scale; a.y0 = y;
+  a.N = N; a.H = H; a.W = W; a.Cout = Cout; a.taps = taps;
+  a.flags = relu ? 1 : 0;
+  a.bn_override = bn_override & 0xffff;
+  a.tile_flags = bn_override >> 16;
   return b2u::launch_conv(a, static_cast<cudaStream_t>(stream));
 }
 

@@ -262,6 +262,19 @@ class UNetEngine:
             ops.conv_fprop(x0, c.wf, bias, c.cout_p, taps=taps, relu=True, x1=x1, out=out)
             A[c.name] = out
             return out
+        if not training:
+            # eval mode: BatchNorm is an affine map with fixed statistics, folded into the conv epilogue
+            # (y = relu(acc * s + b')): no z tensor, no BatchNorm pass
+            gamma = self._padded_vec("g:" + c.bn, params[c.bn + ".weight"], c.cout_p, fill=1.0)
+            beta = self._padded_vec("bt:" + c.bn, params[c.bn + ".bias"], c.cout_p)
+            rmp = self._padded_vec("rm:" + c.bn, params[c.bn + ".running_mean"], c.cout_p)
+            rvp = self._padded_vec("rv:" + c.bn, params[c.bn + ".running_var"], c.cout_p, fill=1.0)
+            sc, bs = ops.bn_fold(gamma, beta, rmp, rvp, bias, self.eps, scale=self._buf("fs:" + c.bn, (c.cout_p,), torch.float32),
+                                 bias=self._buf("fb:" + c.bn, (c.cout_p,), torch.float32))
+            out = self._buf(c.name, (n, h, w, c.cout_p))
+            ops.conv_fprop_scaled(x0, c.wf, sc, bs, c.cout_p, taps=taps, relu=True, x1=x1, out=out)
+            A[c.name] = out
+            return out
         z = self._buf("z:" + c.name, (n, h, w, c.cout_p))
         # training: the conv epilogue also emits the BatchNorm statistics of z (per-tile sums), so BatchNorm skips its
         # statistics pass over z

@@ -38,11 +38,12 @@ def pad64(c):
 
 
 class _T:
-    __slots__ = ("data", "grad", "fused_relu", "needs_grad", "aux", "stats")
+    __slots__ = ("data", "grad", "fused_relu", "needs_grad", "aux", "stats", "folded")
 
     def __init__(self, data, fused_relu=False, needs_grad=False):
         self.data, self.grad, self.fused_relu, self.needs_grad, self.aux = data, None, fused_relu, needs_grad, None
         self.stats = None      # (fp32 per-tile column sums, rows) when the producing conv emitted BatchNorm statistics
+        self.folded = False    # eval mode: this conv output already is the BatchNorm (+ReLU) output
 
 
 def resnet50_unet_program(num_classes):
@@ -254,6 +255,8 @@ class GraphEngine:
                 if i.get(key):
                     readers.setdefault(i[key], []).append(i["op"] if key == "z" else "other")
         self._pre_bn = {name for name, ops_ in readers.items() if ops_ == ["bn"]}      # tensors read only as a BN input
+        # eval-mode folding: conv output -> the BatchNorm (without residual) that is its only reader
+        self._fold_bn = {i["z"]: i for i in program if i["op"] == "bn" and i["z"] in self._pre_bn and not i["res"]}
 
     # ------------------------------------------------------------------ static description
     def param_shapes(self):
@@ -335,6 +338,17 @@ class GraphEngine:
             self._bufs[key] = b
         b[tuple(slice(0, d) for d in t.shape)].copy_(t)
         return b
+
+    def _folded_bn(self, bn_ins, params, conv_bias, cp):
+        """(scale, bias) of `conv -> eval BatchNorm` as one affine map, padded to cp channels."""
+        bnn = bn_ins["bn"]
+        gamma = self._padded("g:" + bnn, params[bnn + ".weight"], (cp,), 1.0)
+        beta = self._padded("bt:" + bnn, params[bnn + ".bias"], (cp,))
+        rmp = self._padded("rm:" + bnn, params[bnn + ".running_mean"], (cp,))
+        rvp = self._padded("rv:" + bnn, params[bnn + ".running_var"], (cp,), 1.0)
+        cb = self._padded("b:" + bnn, conv_bias, (cp,)) if conv_bias is not None else None
+        return ops.bn_fold(gamma, beta, rmp, rvp, cb, self.eps, scale=self._buf("fs:" + bnn, (cp,), torch.float32),
+                           bias=self._buf("fb:" + bnn, (cp,), torch.float32))
 
     def _tiled(self, key, t, width, f):
         """fp32 vector zero-padded to `width` and repeated f times (bias of a pixel-packed conv)."""
@@ -448,15 +462,45 @@ class GraphEngine:
                     else:
                         z = self._buf(ins["out"], (n, h, w, pad64(ins["cout"])))
                         bias = self._tiled("b2:" + ins["w"], params[ins["bias"]], pad64(ins["cout"]), f)
-                    ops.conv_fprop(xin.data.view(n, h, w // f, -1), wf, bias, z.shape[3] * f, taps=1, relu=False,
-                                   x1=x1.data.view(n, h, w // f, -1) if x1 else None, out=z.view(n, h, w // f, -1))
+                    fold = self._fold_bn.get(ins["out"]) if not training else None
+                    if fold is not None:        # eval: BatchNorm (+ReLU) folded into the epilogue, vectors tiled like the bias
+                        sc, bs = self._folded_bn(fold, params, params[ins["bias"]], z.shape[3])
+                        sc = self._tiled("fs2:" + ins["w"], sc, z.shape[3], f)
+                        bs = self._tiled("fb2:" + ins["w"], bs, z.shape[3], f)
+                        ops.conv_fprop_scaled(xin.data.view(n, h, w // f, -1), wf, sc, bs, z.shape[3] * f, taps=1, relu=fold["relu"],
+                                              x1=x1.data.view(n, h, w // f, -1) if x1 else None, out=z.view(n, h, w // f, -1))
+                    else:
+                        ops.conv_fprop(xin.data.view(n, h, w // f, -1), wf, bias, z.shape[3] * f, taps=1, relu=False,
+                                       x1=x1.data.view(n, h, w // f, -1) if x1 else None, out=z.view(n, h, w // f, -1))
                     ng = xin.needs_grad or (x1 is not None and x1.needs_grad) or ins["w"] in trainable or (ins["bias"] in trainable)
-                    T[ins["out"]] = _T(z, needs_grad=ng)
+                    t = _T(z, needs_grad=ng)
+                    t.folded = fold is not None
+                    T[ins["out"]] = t
                     continue
                 coutp = pad64(ins["cout"])
                 bias = self._padded("b:" + ins["w"], params[ins["bias"]], (coutp,)) if ins["bias"] else None
                 aux = None
                 stats = None
+                fold = self._fold_bn.get(ins["out"]) if not training else None
+                if fold is not None:
+                    # eval mode: y = [relu](acc * s + b') straight from the conv epilogue; the BatchNorm instruction passes it on
+                    sc, bs = self._folded_bn(fold, params, params[ins["bias"]] if ins["bias"] else None, coutp)
+                    if ins["stride"] == 1:
+                        z = self._buf(ins["out"], (n, h, w, coutp))
+                        ops.conv_fprop_scaled(xin.data, wf, sc, bs, coutp, taps=ins["taps"], relu=fold["relu"],
+                                              x1=x1.data if x1 else None, out=z)
+                    elif ins["taps"] == 9:
+                        full = self._buf(ins["out"] + ":full", (n, h, w, coutp))
+                        ops.conv_fprop_scaled(xin.data, wf, sc, bs, coutp, taps=9, relu=fold["relu"], out=full)
+                        z = ops.subsample2(full, out=self._buf(ins["out"], (n, h // 2, w // 2, coutp)))
+                    else:
+                        xs = ops.subsample2(xin.data, out=self._buf(ins["out"] + ":xs", (n, h // 2, w // 2, xin.data.shape[3])))
+                        z = self._buf(ins["out"], (n, h // 2, w // 2, coutp))
+                        ops.conv_fprop_scaled(xs, wf, sc, bs, coutp, taps=1, relu=fold["relu"], out=z)
+                    t = _T(z)
+                    t.folded = True
+                    T[ins["out"]] = t
+                    continue
                 if ins["stride"] == 1:
                     z = self._buf(ins["out"], (n, h, w, coutp))
                     kdim = ins["taps"] * (xin.data.shape[3] + (x1.data.shape[3] if x1 else 0))
@@ -482,6 +526,9 @@ class GraphEngine:
                 T[ins["out"]] = t
             elif op == "bn":
                 zt = T[ins["z"]]
+                if zt.folded:            # eval mode: the producing conv already applied this BatchNorm (+ReLU)
+                    T[ins["out"]] = _T(zt.data)
+                    continue
                 res = T[ins["res"]] if ins["res"] else None
                 bnn, c = ins["bn"], ins["c"]
                 cp = zt.data.shape[3]

@@ -164,6 +164,29 @@ def conv_fprop(x0, wf, bias, Cout, taps=9, relu=True, x1=None, out=None, bn=0, s
     return out
 
 
+def conv_fprop_scaled(x0, wf, scale, bias, Cout, taps=9, relu=True, x1=None, out=None, bn=0):
+    """y = [relu](conv(x) * scale[c] + bias[c]): conv + eval-mode BatchNorm (+ReLU) in one kernel (scale/bias from bn_fold)."""
+    _req(x0, BF16, "x0"); _req(x1, BF16, "x1"); _req(wf, BF16, "wf"); _req(bias, torch.float32, "bias"); _req(scale, torch.float32, "scale")
+    N, H, W, C0 = x0.shape
+    C1 = 0 if x1 is None else x1.shape[3]
+    if out is None:
+        out = torch.empty((N, H, W, Cout), dtype=BF16, device=x0.device)
+    check(lib().b2u_conv_fprop_scaled(ptr(x0), C0, ptr(x1), C1, ptr(wf), ptr(scale), ptr(bias), ptr(out), N, H, W, Cout, taps,
+                                      1 if relu else 0, bn, stream_ptr()))
+    return out
+
+
+def bn_fold(gamma, beta, running_mean, running_var, conv_bias, eps=1e-5, scale=None, bias=None):
+    C = running_mean.numel()
+    if scale is None:
+        scale = torch.empty((C,), dtype=torch.float32, device=running_mean.device)
+    if bias is None:
+        bias = torch.empty((C,), dtype=torch.float32, device=running_mean.device)
+    check(lib().b2u_bn_fold(ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(conv_bias), ptr(scale), ptr(bias), C, eps,
+                            stream_ptr()))
+    return scale, bias
+
+
 def conv_stat_rows(N, H, W, Cout, taps=9, bn=0):
     return lib().b2u_conv_stat_rows(N, H, W, Cout, taps, bn)
 
