@@ -106,7 +106,10 @@ def variant_cpu_img_per_s(model, num_classes, batch=2, hw=HW, steps=1, warmup=1,
     torch.set_num_threads(threads)
     imgs, pngs = O.make_inputs(batch, num_classes, hw, hw, seed=0)
     w = torch.ones(num_classes)
-    if model == "unet_resnet50":
+    if model == "unet_vgg":
+        sd = O.make_params(num_classes)
+        step = lambda: O.train_step(sd, imgs, pngs, w, num_classes)
+    elif model == "unet_resnet50":
         sd = O.make_resnet_unet_params(num_classes)
         step = lambda: O.resnet_unet_train_step(sd, imgs, pngs, w, num_classes)
     elif model == "traditional":
