@@ -213,6 +213,7 @@ def run_ours(args):
 
     params = b2u.synthetic.make_params(NUM_CLASSES, seed=11)
     trainer = b2u.UnetTrainer(num_classes=NUM_CLASSES, device=dev, lr=1e-4, betas=(0.9, 0.999), state_dict=params,
+                              bucket_mb=int(os.environ.get("B2U_BUCKET_MB", "16")),      # experiment knob (all-reduce bucket size)
                               dice_loss=True)
     # a few distinct resident batches, different per rank (DistributedSampler semantics)
     nb = 2
@@ -227,6 +228,8 @@ def run_ours(args):
 
     def max_over_ranks(ms):
         if world > 1:
+            if os.environ.get("B2U_RANK_TIMES"):          # diagnostic: every rank's own time on stderr
+                print(f"[rank {rank}] {ms:.3f} ms", file=sys.stderr, flush=True)
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return t.item()
