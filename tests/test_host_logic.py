@@ -101,3 +101,79 @@ def test_per_class_metrics_match_oracle(b2u):
     assert np.array_equal(b2u.per_class_iu(hist), O.per_class_iu(hist))
     assert np.array_equal(b2u.per_class_PA_Recall(hist), O.per_class_PA_Recall(hist))
     assert np.array_equal(b2u.per_class_Precision(hist), O.per_class_Precision(hist))
+
+
+ULU = [("ultralight", "UltraLightweightUnet", 449_810), ("ultralight_large", "UltraLightweightUnet_large", 1_946_322),
+       ("ultralight_large_optimized", "UltraLightweightUnet_large_optimized", 926_257)]
+
+
+@pytest.mark.parametrize("variant,cls,nparams", ULU)
+def test_ultralight_state_dict_and_program_contract(b2u, variant, cls, nparams):
+    """Module tree, state_dict order and parameter counts of the three UltraLightweightUnet files (2 classes), and the
+    static program behind them: every parameter appears exactly once in the backward order, narrow mids are pixel-packed."""
+    import importlib
+    from unet_pytorch_b200.graph import UltraLightUnetEngine
+    Net = getattr(importlib.import_module(f"unet_pytorch_b200.nets.{cls}"), cls)
+    m = Net(num_classes=2)
+    sd = O.make_ulu_params(2, variant)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    assert all(tuple(m.state_dict()[k].shape) == tuple(sd[k].shape) for k in sd)
+    assert sum(p.numel() for p in m.parameters()) == nparams
+    m.load_state_dict(sd)
+    eng = UltraLightUnetEngine(2, variant)
+    shapes = eng.param_shapes()
+    assert set(shapes) == set(n for n, _ in m.named_parameters())
+    assert all(tuple(shapes[n]) == tuple(p.shape) for n, p in m.named_parameters())
+    order = eng.backward_param_order()
+    assert sorted(order) == sorted(shapes) and len(set(order)) == len(order)
+    assert set(eng.buffer_shapes()) == set(n for n, _ in m.named_buffers())
+    packed = {i["w"]: i["pix"] for i in eng.pk.values()}
+    mids = {"ultralight": {"enc1": 4, "enc2": 2, "dec1": 4, "dec2": 2}, "ultralight_large": {"enc1": 2, "dec1": 2},
+            "ultralight_large_optimized": {"enc1": 2, "dec1": 2}}[variant]
+    assert packed == {f"{blk}.conv.{sfx}.weight": f for blk, f in mids.items() for sfx in ("0", "3.pointwise")}
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 64, 64))          # CPU tensors: no fallback
+
+
+def test_lightweight_state_dict_and_program_contract(b2u):
+    from unet_pytorch_b200.graph import LightweightUnetEngine
+    m = b2u.LightweightUnet(num_classes=21)
+    sd = O.make_lw_params(21)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    assert sum(p.numel() for p in m.parameters()) == 6_770_756 + (21 - 2) * 25     # SURVEY.md 8(a) a6 counts the 2-class model
+    m.load_state_dict(sd)
+    m.freeze_backbone()
+    assert all(not p.requires_grad for p in m.backbone.parameters()) and m.final_conv[3].weight.requires_grad
+    m.unfreeze_backbone()
+    assert all(p.requires_grad for p in m.parameters())
+    eng = LightweightUnetEngine(21)
+    assert sorted(eng.backward_param_order()) == sorted(eng.param_shapes())
+    assert sum(1 for i in eng.program if i["op"] == "drop") == 10 and eng.logit_stride == 2
+    assert sum(1 for i in eng.program if i["op"] == "se") == 5 + 4 + 1
+    with pytest.raises(ValueError):
+        b2u.LightweightUnet(num_classes=2, backbone="resnet50")
+
+
+def test_conv_tile_count_helper(b2u):
+    """b2u_conv_stat_rows (host-only arithmetic): M tiles of 8x16 pixels, two stacked tiles per step for the small-N configs."""
+    lib = b2u._lib.lib()
+    assert lib.b2u_conv_stat_rows(2, 24, 40, 256, 9, 0) == 2 * 3 * 3
+    assert lib.b2u_conv_stat_rows(2, 24, 40, 64, 9, 0) == 2 * 2 * 3            # tall: 16-row steps
+    assert lib.b2u_conv_stat_rows(1, 8, 16, 64, 9, 0) == 1                     # H <= 8: one tile per step
+    assert lib.b2u_conv_stat_rows(3, 5, 7, 64, 1, 0) == 3                      # 1x1, N tile 64: always two stacked tiles
+    assert lib.b2u_conv_stat_rows(3, 5, 7, 192, 1, 0) == 3
+    assert lib.b2u_conv_stat_rows(0, 5, 7, 192, 1, 0) == 0
+
+
+def test_predictor_host_helpers(b2u):
+    """Letterbox geometry of the predictor (utils/utils.py:22-34) and its refusal to run without CUDA."""
+    from PIL import Image
+    from unet_pytorch_b200.unet import Unet as Predictor, resize_image, cvtColor
+    img = Image.fromarray(np.zeros((300, 420, 3), np.uint8))
+    boxed, nw, nh = resize_image(img, (256, 256))
+    assert boxed.size == (256, 256) and (nw, nh) == (256, 182)
+    assert np.array(boxed)[0, 0].tolist() == [128, 128, 128]                  # grey bars above/below
+    assert cvtColor(Image.fromarray(np.zeros((8, 8), np.uint8))).mode == "RGB"
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            Predictor(state_dict={}, num_classes=2)
