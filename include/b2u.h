@@ -112,6 +112,20 @@ int b2u_bn_fwd_train_stats(const void* z, const void* residual, void* y, const f
 int b2u_bn_fwd_eval(const void* z, const void* residual, void* y, const float* gamma, const float* beta,
                     const float* running_mean, const float* running_var, void* ws, size_t ws_bytes, long long P, int C,
                     float eps, int relu, void* stream);
+/* SyncBatchNorm building blocks (nn.SyncBatchNorm.convert_sync_batchnorm, train.py:335-336): the statistics and apply
+ * passes as separate calls so the caller can all-reduce the [2][C] fp32 sums across ranks in between.  P_stat = rows over
+ * all ranks.  b2u_bn_bwd_sums returns this rank's (dbeta, dgamma), which stay local (DDP averages them), like torch */
+int b2u_bn_sums(const void* z, float* sums, void* ws, size_t ws_bytes, long long P, int C, void* stream);
+int b2u_bn_fwd_train_sums(const void* z, const void* residual, void* y, const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, float* save_mean, float* save_invstd, const float* sums,
+                          long long P_stat, void* ws, size_t ws_bytes, long long P, int C, float eps, float momentum, int relu,
+                          void* stream);
+int b2u_bn_bwd_sums(const void* dy, const void* y, const void* z, const float* gamma, const float* beta, const float* save_mean,
+                    const float* save_invstd, float* sums, void* ws, size_t ws_bytes, long long P, int C, int relu,
+                    void* stream);
+int b2u_bn_bwd_apply_sums(const void* dy, const void* y, const void* z, const float* gamma, const float* beta,
+                          const float* save_mean, const float* save_invstd, void* dz, void* gout, const float* sums,
+                          long long P_stat, void* ws, size_t ws_bytes, long long P, int C, int relu, void* stream);
 /* eval-mode conv -> nn.BatchNorm2d (-> ReLU) as ONE kernel: b2u_bn_fold gives scale = gamma / sqrt(rv + eps) and
  * bias = (conv_bias - rm) * scale + beta; b2u_conv_fprop_scaled applies y = [relu](acc * scale + bias) in the conv epilogue
  * (model.eval() inference of the BatchNorm nets: no z tensor, no BatchNorm pass) */

@@ -25,6 +25,10 @@ SIGNATURES = {
     "b2u_u8hwc_to_nchw_f32": (I, [P, P, I, I, I, I, F, P]),
     "b2u_u8_to_i64": (I, [P, P, LL, P]),
     "b2u_conv_fprop": (I, [P, I, P, I, P, P, P, I, I, I, I, I, I, I, P]),
+    "b2u_bn_sums": (I, [P, P, P, SZ, LL, I, P]),
+    "b2u_bn_fwd_train_sums": (I, [P, P, P, P, P, P, P, P, P, P, LL, P, SZ, LL, I, F, F, I, P]),
+    "b2u_bn_bwd_sums": (I, [P, P, P, P, P, P, P, P, P, SZ, LL, I, I, P]),
+    "b2u_bn_bwd_apply_sums": (I, [P, P, P, P, P, P, P, P, P, P, LL, P, SZ, LL, I, I, P]),
     "b2u_bn_fold": (I, [P, P, P, P, P, P, P, I, F, P]),
     "b2u_conv_fprop_scaled": (I, [P, I, P, I, P, P, P, P, I, I, I, I, I, I, I, P]),
     "b2u_conv_stat_rows": (I, [I, I, I, I, I, I]),

@@ -366,6 +366,80 @@ int b2u_bn_fwd_train_stats(const void* z, const void* residual, void* y, const f
   return 0;
 }
 
+// ---- SyncBatchNorm building blocks (nn.SyncBatchNorm.convert_sync_batchnorm, train.py:335-336): the statistics pass and the
+// apply pass as separate calls, so the caller can all-reduce the 2C per-layer sums across ranks in between.
+// sums [2][C] fp32 = (sum z, sum z^2) over this rank's P rows
+int b2u_bn_sums(const void* z, float* sums, void* ws, size_t ws_bytes, long long P, int C, void* stream) {
+  int rc = bn_check(P, C, ws, ws_bytes, "bn_sums");
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(ws);
+  bn_colsum_kernel<0><<<kBnBlocks, 256, 256 * 16 * sizeof(float), st>>>(static_cast<const uint4*>(z), nullptr, nullptr, nullptr,
+                                                                        nullptr, nullptr, nullptr, partial, P, C / 8, 0);
+  B2U_CHECK_LAUNCH("bn_colsum");
+  bn_rows_reduce_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(partial, sums, kBnBlocks, 2 * C);
+  B2U_CHECK_LAUNCH("bn_rows_reduce");
+  return 0;
+}
+
+// forward from given sums over P_stat rows (all ranks); running statistics and saved mean / invstd are the global ones
+int b2u_bn_fwd_train_sums(const void* z, const void* residual, void* y, const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, float* save_mean, float* save_invstd, const float* sums,
+                          long long P_stat, void* ws, size_t ws_bytes, long long P, int C, float eps, float momentum, int relu,
+                          void* stream) {
+  int rc = bn_check(P, C, ws, ws_bytes, "bn_fwd_train_sums");
+  if (rc) return rc;
+  if (!sums || P_stat < P) return set_error(B2U_ERR_ARG, "bn_fwd_train_sums: sums missing or P_stat < P");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* coef = static_cast<float*>(ws) + static_cast<size_t>(kBnBlocks) * 2 * C;
+  bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, 1, C, P_stat, gamma, beta, running_mean, running_var,
+                                                          save_mean, save_invstd, coef, coef + C, eps, momentum);
+  B2U_CHECK_LAUNCH("bn_fwd_finalize");
+  const long long G = (P + kBnApplyRows - 1) / kBnApplyRows;
+  bn_apply_kernel<<<static_cast<unsigned>((G * (C / 8) + 255) / 256), 256, 0, st>>>(static_cast<const uint4*>(z), static_cast<const uint4*>(residual),
+                                                                                   static_cast<uint4*>(y), coef, coef + C, P, G, C / 8, relu);
+  B2U_CHECK_LAUNCH("bn_apply");
+  return 0;
+}
+
+// backward statistics of this rank: sums [2][C] = (sum g, sum g xhat) with g = dy masked by the ReLU (= dbeta, dgamma of
+// this rank: torch's SyncBatchNorm keeps the affine gradients local and lets DDP average them)
+int b2u_bn_bwd_sums(const void* dy, const void* y, const void* z, const float* gamma, const float* beta, const float* save_mean,
+                    const float* save_invstd, float* sums, void* ws, size_t ws_bytes, long long P, int C, int relu,
+                    void* stream) {
+  int rc = bn_check(P, C, ws, ws_bytes, "bn_bwd_sums");
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(ws);
+  bn_colsum_kernel<1><<<kBnBlocks, 256, 256 * 16 * sizeof(float), st>>>(static_cast<const uint4*>(dy), static_cast<const uint4*>(y),
+                                                                        static_cast<const uint4*>(z), gamma, beta, save_mean,
+                                                                        save_invstd, partial, P, C / 8, relu);
+  B2U_CHECK_LAUNCH("bn_bwd_colsum");
+  bn_rows_reduce_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(partial, sums, kBnBlocks, 2 * C);
+  B2U_CHECK_LAUNCH("bn_rows_reduce");
+  return 0;
+}
+
+// dz from given (all-reduced) sums over P_stat rows
+int b2u_bn_bwd_apply_sums(const void* dy, const void* y, const void* z, const float* gamma, const float* beta,
+                          const float* save_mean, const float* save_invstd, void* dz, void* gout, const float* sums,
+                          long long P_stat, void* ws, size_t ws_bytes, long long P, int C, int relu, void* stream) {
+  int rc = bn_check(P, C, ws, ws_bytes, "bn_bwd_apply_sums");
+  if (rc) return rc;
+  if (!sums || P_stat < P) return set_error(B2U_ERR_ARG, "bn_bwd_apply_sums: sums missing or P_stat < P");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* coef = static_cast<float*>(ws) + static_cast<size_t>(kBnBlocks) * 2 * C;
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, 1, C, P_stat, gamma, beta, save_mean, save_invstd, nullptr,
+                                                          nullptr, coef);
+  B2U_CHECK_LAUNCH("bn_bwd_finalize");
+  const long long G = (P + kBnApplyRows - 1) / kBnApplyRows;
+  bn_bwd_apply_kernel<<<static_cast<unsigned>((G * (C / 8) + 255) / 256), 256, 0, st>>>(
+      static_cast<const uint4*>(dy), static_cast<const uint4*>(y), static_cast<const uint4*>(z), coef,
+      static_cast<uint4*>(dz), static_cast<uint4*>(gout), P, G, C / 8, relu);
+  B2U_CHECK_LAUNCH("bn_bwd_apply");
+  return 0;
+}
+
 int b2u_bn_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                 const float* conv_bias, float* scale, float* bias, int C, float eps, void* stream) {
   if (C <= 0 || !running_mean || !running_var || !scale || !bias) return set_error(B2U_ERR_ARG, "bn_fold: bad arguments");

@@ -20,6 +20,8 @@ trainer can start that bucket's all-reduce while the remaining dgrad/wgrad kerne
 """
 import struct
 
+import functools
+
 import torch
 
 from . import ops
@@ -134,6 +136,7 @@ class UNetEngine:
         # BatchNorm statistics from the conv epilogue (one pass over z less); only where the reduction is long enough for the
         # extra epilogue work to hide behind the main loop (scripts/ab_fuse_bnstats.py)
         self.fuse_bn_stats = True
+        self.sync_bn_group = None        # torch.distributed group: BatchNorm statistics over all ranks (SyncBatchNorm)
         self.bn_stats_min_k = 1024
         self.bn_stats_min_cout = 256
         # db from the wgrad kernel's bias warps (3x3 layers) instead of a separate pass over dz: an A/B on one box
@@ -280,7 +283,7 @@ class UNetEngine:
         # statistics pass over z
         stats, rows = None, 0
         kdim = taps * (x0.shape[3] + (x1.shape[3] if x1 is not None else 0))
-        if training and self.fuse_bn_stats and (kdim >= self.bn_stats_min_k or c.cout_p >= self.bn_stats_min_cout):
+        if training and self.fuse_bn_stats and self.sync_bn_group is None and (kdim >= self.bn_stats_min_k or c.cout_p >= self.bn_stats_min_cout):
             rows = ops.conv_stat_rows(n, h, w, c.cout_p, taps)
             stats = self._workspace("bnstat", rows * 2 * c.cout_p * 4)[:rows * 2 * c.cout_p * 4].view(torch.float32)
         ops.conv_fprop(x0, c.wf, bias, c.cout_p, taps=taps, relu=False, x1=x1, out=z, stats=stats)
@@ -289,7 +292,18 @@ class UNetEngine:
         out = self._buf(c.name, (n, h, w, c.cout_p))
         ws = self._workspace("bn", ops.lib().b2u_bn_workspace(c.cout_p))
         rm, rv = params[c.bn + ".running_mean"], params[c.bn + ".running_var"]
-        if training:
+        if training and self.sync_bn_group is not None:
+            rmp = self._padded_vec("rm:" + c.bn, rm, c.cout_p)
+            rvp = self._padded_vec("rv:" + c.bn, rv, c.cout_p, fill=1.0)
+            _, mean, invstd = ops.bn_fwd_train_sync(z, gamma, beta, rmp, rvp, self.sync_bn_group, self.eps, self.momentum, True,
+                                                    out=out, ws=ws)
+            if c.cout_p != c.cout or rmp is not rm:
+                rm.copy_(rmp[:c.cout]); rv.copy_(rvp[:c.cout])
+            nbt = params.get(c.bn + ".num_batches_tracked")
+            if nbt is not None:
+                nbt.add_(1)
+            A["bn:" + c.name] = (z, mean, invstd, gamma, beta)
+        elif training:
             if c.cout_p == c.cout:
                 _, mean, invstd = ops.bn_fwd_train(z, gamma, beta, rm, rv, self.eps, self.momentum, True, out=out, ws=ws,
                                                    stats=stats, stat_rows=rows)
@@ -413,7 +427,8 @@ class UNetEngine:
                 wn, bnn = c.bn + ".weight", c.bn + ".bias"
                 dgam = self._buf("dg:" + c.bn, (c.cout_p,), torch.float32)
                 dbet = self._buf("db:" + c.bn, (c.cout_p,), torch.float32)
-                ops.bn_bwd(g, None, z, gamma, mean, invstd, relu=True, out=g, dgamma=dgam, dbeta=dbet, beta=beta,   # mask from z
+                bwd = ops.bn_bwd if self.sync_bn_group is None else functools.partial(ops.bn_bwd_sync, group=self.sync_bn_group)
+                bwd(g, None, z, gamma, mean, invstd, relu=True, out=g, dgamma=dgam, dbeta=dbet, beta=beta,   # mask from z
                            ws=self._workspace("bn", ops.lib().b2u_bn_workspace(c.cout_p)))
                 if has(wn):
                     grads[wn].copy_(dgam[:c.cout])

@@ -28,6 +28,8 @@ the pre-activation.  BatchNorm outputs are plain: the bn instruction's own backw
 """
 import struct
 
+import functools
+
 import torch
 
 from . import ops
@@ -247,6 +249,7 @@ class GraphEngine:
         # behind the main loop when the reduction is long enough: measured (scripts/ab_fuse_bnstats.py) it gains 0.8 ms on
         # Unet-ResNet50 but loses 0.7-1.3 ms on the full-resolution, short-K layers of the other BatchNorm nets
         self.fuse_bn_stats = True
+        self.sync_bn_group = None       # torch.distributed group: BatchNorm statistics over all ranks (SyncBatchNorm)
         self.bn_stats_min_k = 1024
         self.bn_stats_min_cout = 256
         readers = {}
@@ -504,7 +507,8 @@ class GraphEngine:
                 if ins["stride"] == 1:
                     z = self._buf(ins["out"], (n, h, w, coutp))
                     kdim = ins["taps"] * (xin.data.shape[3] + (x1.data.shape[3] if x1 else 0))
-                    if training and self.fuse_bn_stats and ins["out"] in self._pre_bn and (kdim >= self.bn_stats_min_k or coutp >= self.bn_stats_min_cout):
+                    if (training and self.fuse_bn_stats and self.sync_bn_group is None and ins["out"] in self._pre_bn
+                            and (kdim >= self.bn_stats_min_k or coutp >= self.bn_stats_min_cout)):
                         # the BatchNorm that reads this output takes its statistics from this conv's epilogue (no pass over
                         # z); one buffer per conv output: another conv may run before that BatchNorm (downsample branches)
                         rows = ops.conv_stat_rows(n, h, w, coutp, ins["taps"])
@@ -539,9 +543,14 @@ class GraphEngine:
                 rm, rv = params[bnn + ".running_mean"], params[bnn + ".running_var"]
                 rmp, rvp = self._padded("rm:" + bnn, rm, (cp,)), self._padded("rv:" + bnn, rv, (cp,), 1.0)
                 if training:
-                    _, mean, invstd = ops.bn_fwd_train(zt.data, gamma, beta, rmp, rvp, self.eps, self.momentum, ins["relu"],
-                                                       out=y, ws=ws, residual=res.data if res else None,
-                                                       stats=zt.stats[0] if zt.stats else None, stat_rows=zt.stats[1] if zt.stats else 0)
+                    if self.sync_bn_group is not None:
+                        _, mean, invstd = ops.bn_fwd_train_sync(zt.data, gamma, beta, rmp, rvp, self.sync_bn_group, self.eps,
+                                                                self.momentum, ins["relu"], out=y, ws=ws,
+                                                                residual=res.data if res else None)
+                    else:
+                        _, mean, invstd = ops.bn_fwd_train(zt.data, gamma, beta, rmp, rvp, self.eps, self.momentum, ins["relu"],
+                                                           out=y, ws=ws, residual=res.data if res else None,
+                                                           stats=zt.stats[0] if zt.stats else None, stat_rows=zt.stats[1] if zt.stats else 0)
                     if cp != c:
                         rm.copy_(rmp[:c]); rv.copy_(rvp[:c])
                     nbt = params.get(bnn + ".num_batches_tracked")
@@ -776,7 +785,8 @@ class GraphEngine:
                 dgam = grads[bnn + ".weight"] if (direct and has(bnn + ".weight")) else self._buf("dg:" + bnn, (cp,), torch.float32)
                 dbet = grads[bnn + ".bias"] if (direct and has(bnn + ".bias")) else self._buf("db:" + bnn, (cp,), torch.float32)
                 # y is read only where a residual was added before the ReLU; otherwise the mask is recomputed from z
-                ops.bn_bwd(t.grad, t.data if res is not None else None, zt.data, gamma, mean, invstd, relu=ins["relu"], out=dz,
+                bwd = ops.bn_bwd if self.sync_bn_group is None else functools.partial(ops.bn_bwd_sync, group=self.sync_bn_group)
+                bwd(t.grad, t.data if res is not None else None, zt.data, gamma, mean, invstd, relu=ins["relu"], out=dz,
                            dgamma=dgam, dbeta=dbet, beta=beta,
                            ws=self._workspace("bn", ops.lib().b2u_bn_workspace(cp)), gout=gout)
                 if not direct:

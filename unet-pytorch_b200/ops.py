@@ -305,6 +305,60 @@ def bn_fwd_train(z, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0
     return out, mean, invstd
 
 
+def bn_fwd_train_sync(z, gamma, beta, running_mean, running_var, group, eps=1e-5, momentum=0.1, relu=True, out=None, ws=None,
+                      residual=None):
+    """SyncBatchNorm forward (train.py:335-336): this rank's column sums, one all-reduce of 2C floats over `group`, apply
+    with the global statistics.  Every rank is assumed to hold the same number of rows (DistributedSampler batches)."""
+    import torch.distributed as dist
+    _req(z, BF16, "z")
+    C = z.shape[-1]
+    P = z.numel() // C
+    need = lib().b2u_bn_workspace(C)
+    if ws is None or ws.numel() * ws.element_size() < need:
+        ws = _ws(need, z.device)
+    if out is None:
+        out = torch.empty_like(z)
+    sums = torch.empty((2, C), dtype=torch.float32, device=z.device)
+    check(lib().b2u_bn_sums(ptr(z), ptr(sums), ptr(ws), ws.numel() * ws.element_size(), P, C, stream_ptr()))
+    dist.all_reduce(sums, group=group)
+    world = dist.get_world_size(group)
+    mean = torch.empty((C,), dtype=torch.float32, device=z.device)
+    invstd = torch.empty((C,), dtype=torch.float32, device=z.device)
+    check(lib().b2u_bn_fwd_train_sums(ptr(z), ptr(residual), ptr(out), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
+                                      ptr(mean), ptr(invstd), ptr(sums), P * world, ptr(ws), ws.numel() * ws.element_size(), P, C, eps,
+                                      momentum, 1 if relu else 0, stream_ptr()))
+    return out, mean, invstd
+
+
+def bn_bwd_sync(dy, y, z, gamma, mean, invstd, group, relu=True, out=None, dgamma=None, dbeta=None, ws=None, gout=None, beta=None):
+    """SyncBatchNorm backward: local (sum g, sum g xhat) = this rank's (dbeta, dgamma), all-reduced only for dz."""
+    import torch.distributed as dist
+    _req(dy, BF16, "dy"); _req(y, BF16, "y"); _req(z, BF16, "z")
+    if y is None and relu and beta is None:
+        raise ValueError("bn_bwd_sync: y=None needs beta to recompute the ReLU mask")
+    C = z.shape[-1]
+    P = z.numel() // C
+    need = lib().b2u_bn_workspace(C)
+    if ws is None or ws.numel() * ws.element_size() < need:
+        ws = _ws(need, z.device)
+    if out is None:
+        out = torch.empty_like(z)
+    sums = torch.empty((2, C), dtype=torch.float32, device=z.device)
+    check(lib().b2u_bn_bwd_sums(ptr(dy), ptr(y), ptr(z), ptr(gamma), ptr(beta), ptr(mean), ptr(invstd), ptr(sums), ptr(ws),
+                                ws.numel() * ws.element_size(), P, C, 1 if relu else 0, stream_ptr()))
+    if dbeta is not None:
+        dbeta.copy_(sums[0])
+    if dgamma is not None:
+        dgamma.copy_(sums[1])
+    local = sums.clone()
+    dist.all_reduce(sums, group=group)
+    world = dist.get_world_size(group)
+    check(lib().b2u_bn_bwd_apply_sums(ptr(dy), ptr(y), ptr(z), ptr(gamma), ptr(beta), ptr(mean), ptr(invstd), ptr(out), ptr(gout),
+                                      ptr(sums), P * world, ptr(ws), ws.numel() * ws.element_size(), P, C, 1 if relu else 0,
+                                      stream_ptr()))
+    return out, local[1], local[0]
+
+
 def bn_fwd_eval(z, gamma, beta, running_mean, running_var, eps=1e-5, relu=True, out=None, ws=None, residual=None):
     _req(z, BF16, "z")
     C = z.shape[-1]

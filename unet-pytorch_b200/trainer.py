@@ -144,7 +144,7 @@ class UnetTrainer:
 
     def __init__(self, num_classes=21, device=None, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
                  optimizer="adam", momentum=0.9, cls_weights=None, dice_loss=True, focal_loss=False,
-                 state_dict=None, process_group=None, bucket_mb=16, compute_f_score=True, model="unet_vgg"):
+                 state_dict=None, process_group=None, bucket_mb=16, compute_f_score=True, model="unet_vgg", sync_bn=False):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         self.device = torch.device(device)
@@ -181,6 +181,8 @@ class UnetTrainer:
         cw = torch.ones(num_classes) if cls_weights is None else torch.as_tensor(cls_weights, dtype=torch.float32)
         self.cls_w = cw.to(self.device).contiguous()
         self.sync = GradientSync(self.layout, self.flat_grad, group=process_group)
+        if sync_bn and self.sync.world > 1:       # train.py:66, 335-336: BatchNorm statistics over all ranks
+            self.engine.sync_bn_group = process_group if process_group is not None else dist.group.WORLD
         self.trainable = set(self.names)
         self.backbone_prefixes = {"unet_vgg": ("vgg.",), "unet_resnet50": ("resnet.",)}.get(
             model, ("backbone.",) if model == "lightweight" else ("enc", "se") if model.startswith("ultralight") else ("inc.", "down1.", "down2.", "down3."))
