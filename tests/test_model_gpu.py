@@ -628,6 +628,12 @@ def test_predictor_class_against_reference(b2u, cuda_device, golden_dir):
     seg = np.array(pred.detect_image(image))
     assert seg.shape == g["seg"].shape
     assert (seg == g["seg"]).all(axis=-1)[margin > 0.02].mean() >= 0.999
+    # batched evaluation without the PNG round trip: device-resident masks folded into one confusion matrix
+    gt = g["mask"].copy(); gt[:10] = 255                               # some ignored pixels
+    hist, ious, recall, precision = pred.get_miou([image, image], [gt, Image.fromarray(gt)])
+    ref_hist = 2 * O.fast_hist(gt.reshape(-1), mask.reshape(-1), C)
+    assert np.array_equal(hist, ref_hist) and hist.sum() == 2 * (gt != 255).sum()
+    assert np.allclose(ious, O.per_class_iu(ref_hist))
     pred.mix_type = 0
     assert pred.detect_image(image).size == image.size
     assert pred.get_FPS(image, 3) > 0

@@ -90,6 +90,33 @@ class Unet(object):
             mask = ops.softmax_resize_argmax_u8(logits, self._crop(nw, nh), (oh, ow))
         return image, mask[0].cpu().numpy()
 
+    def predict_mask_device(self, image):
+        """The same class map, left on the device (uint8 [H, W] CUDA tensor)."""
+        _, data, nw, nh, oh, ow = self._letterbox(image)
+        with torch.no_grad():
+            logits = self.net(data.to(self.device, non_blocking=True))
+            return ops.softmax_resize_argmax_u8(logits, self._crop(nw, nh), (oh, ow))[0]
+
+    def get_miou(self, images, gts):
+        """get_miou.py:45-65 + utils_metrics.compute_mIoU (:58-126) without the PNG round trip: every prediction stays on
+        the GPU and is folded into one device-resident confusion matrix (`fast_hist`), read back once at the end.
+        images: iterable of PIL images; gts: iterable of label maps (PIL 'L'/'P' images or uint8 arrays, 255 = ignore).
+        Returns (hist int64 [n, n], IoUs, PA_Recall, Precision) like compute_mIoU."""
+        from .utils.utils_metrics import fast_hist_device, per_class_iu, per_class_PA_Recall, per_class_Precision
+        n = self.num_classes
+        hist = torch.zeros(n * n + 1, dtype=torch.int64, device=self.device)
+        for image, gt in zip(images, gts):
+            pred = self.predict_mask_device(image)
+            g = torch.from_numpy(np.ascontiguousarray(np.array(gt, dtype=np.uint8))).to(self.device, non_blocking=True)
+            if g.numel() != pred.numel():          # utils_metrics.py:88-93: mismatching pairs are skipped
+                continue
+            fast_hist_device(g.reshape(-1), pred.reshape(-1), n, hist=hist)
+        h = hist.cpu().numpy()
+        if h[-1] != 0:
+            raise ValueError("predictions outside [0, num_classes)")
+        h = h[:-1].reshape(n, n)
+        return h, per_class_iu(h), per_class_PA_Recall(h), per_class_Precision(h)
+
     # ------------------------------------------------------------------ reference API
     def detect_image(self, image, count=False, name_classes=None):
         old_img, pr = self.predict_mask(image)
