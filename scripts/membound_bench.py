@@ -22,11 +22,12 @@ def ev(fn, reps=10, warm=3):
 
 
 def main():
-    ap = argparse.ArgumentParser(); ap.add_argument("--out", default=None); ap.add_argument("--only", default=None)
+    ap = argparse.ArgumentParser(); ap.add_argument("--out", default=None); ap.add_argument("--only", default=None); ap.add_argument("--shapes", default=None, help="e.g. 16x512x512x32,8x256x256x16")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     res = {}
-    for (N, H, W, C) in ((16, 512, 512, 64), (16, 128, 128, 256)):
+    shapes = ((16, 512, 512, 64), (16, 128, 128, 256), (16, 512, 512, 32)) if not args.shapes else [tuple(int(v) for v in t.split('x')) for t in args.shapes.split(',')]
+    for (N, H, W, C) in shapes:
         shp = (N, H, W, C)
         T = N * H * W * C * 2          # bytes of one bf16 tensor
         x = torch.randn(shp, device=dev).to(BF); dy = torch.randn(shp, device=dev).to(BF)

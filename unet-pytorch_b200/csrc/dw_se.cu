@@ -197,18 +197,37 @@ dwconv3x3_wgrad_strip_kernel(const uint4* __restrict__ x, const uint4* __restric
     }
     cp_async_wait<0>();
     __syncthreads();                       // the slots become the fold buffer
-    // fold the column lanes, one channel element at a time
+    // fold the column lanes, one channel element at a time.  Narrow tensors have up to 64 column lanes per chunk and only
+    // cpt * 10 outputs, so each output is first summed by `lpo` lanes in parallel and then by one thread.
+    const int nout = cpt * 10;
+    const int lpo = nout >= 128 ? 1 : 128 / nout;           // lanes per output (block-uniform)
+    float* sfold = sred + 128 * 10;                         // [128], inside the 24 KB slot area
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
 #pragma unroll
       for (int a = 0; a < 10; ++a) sred[tid * 10 + a] = acc[a][k];
       __syncthreads();
-      if (xi == 0 && c < C8) {
-        float* out = partial + (static_cast<size_t>(blockIdx.x) * C8 * 8 + c * 8 + k) * 10;
-        for (int a = 0; a < 10; ++a) {
-          float t = sred[tid * 10 + a];
-          for (int r = 1; r < xs; ++r) t += sred[(r * cpt + cc) * 10 + a];
-          out[a] = t;
+      if (lpo == 1) {
+        for (int o = tid; o < nout; o += 128) {
+          const int oc = o / 10, oa = o - oc * 10;
+          float t = 0.f;
+          for (int r = 0; r < xs; ++r) t += sred[(r * cpt + oc) * 10 + oa];
+          if (c0 + oc < C8) partial[(static_cast<size_t>(blockIdx.x) * C8 * 8 + (c0 + oc) * 8 + k) * 10 + oa] = t;
+        }
+      } else {
+        float t = 0.f;
+        if (tid < nout * lpo) {
+          const int o = tid / lpo, part = tid - o * lpo;
+          const int oc = o / 10, oa = o - oc * 10;
+          for (int r = part; r < xs; r += lpo) t += sred[(r * cpt + oc) * 10 + oa];
+        }
+        sfold[tid] = t;
+        __syncthreads();
+        if (tid < nout) {
+          const int oc = tid / 10, oa = tid - oc * 10;
+          float u = 0.f;
+          for (int q = 0; q < lpo; ++q) u += sfold[tid * lpo + q];
+          if (c0 + oc < C8) partial[(static_cast<size_t>(blockIdx.x) * C8 * 8 + (c0 + oc) * 8 + k) * 10 + oa] = u;
         }
       }
       __syncthreads();
