@@ -334,7 +334,7 @@ upsample2x_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H,
 constexpr int kUpStages = 4;
 
 __device__ __forceinline__ void up_cp_async16(uint32_t dst, const void* src, bool valid) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
 }
 
 __global__ void __launch_bounds__(128, 3)
