@@ -328,8 +328,11 @@ def make_trad_params(num_classes, seed=11, in_channels=3, gain=1.0):
     return sd
 
 
-def _double_conv(sd, prefix, x, training, stats, bf16):
-    """DoubleConv.forward (nets/TraditionalUnet.py:5-18); BatchNorm2d with torch defaults (eps 1e-5, momentum 0.1)."""
+def _double_conv(sd, prefix, x, training, stats, bf16, relu_masks=None, record=None):
+    """DoubleConv.forward (nets/TraditionalUnet.py:5-18); BatchNorm2d with torch defaults (eps 1e-5, momentum 0.1).
+    relu_masks (test aid): {BatchNorm name: bool NCHW}; the ReLU after that BatchNorm keeps exactly these elements, which pins
+    the piecewise-linear branch when two precisions disagree about the sign of a pre-activation that is ~0.
+    record (test aid): dict that receives this run's own ReLU masks."""
     for idx in (0, 3):
         w, b = sd[f"{prefix}.double_conv.{idx}.weight"], sd[f"{prefix}.double_conv.{idx}.bias"]
         bn = f"{prefix}.double_conv.{idx + 1}"
@@ -343,13 +346,28 @@ def _double_conv(sd, prefix, x, training, stats, bf16):
         y = F.batch_norm(z, rm, rv, sd[bn + ".weight"], sd[bn + ".bias"], training, 0.1, 1e-5)
         if training:
             stats[bn + ".num_batches_tracked"] = stats[bn + ".num_batches_tracked"] + 1
-        x = F.relu(y)
+        if record is not None:
+            record[bn] = (y > 0).detach()
+        x = F.relu(y) if relu_masks is None else y * relu_masks[bn].to(y.dtype)
         if bf16:
             x = _r(x)
     return x
 
 
-def trad_forward(sd, x, training=True, stats=None, bf16_storage=False):
+def _pinned_max_pool(x, key, pool_indices, record):
+    """F.max_pool2d(x, 2); pool_indices (test aid, like relu_masks): {key: flat arg-max indices from return_indices=True} pins
+    which element of each window passes (two precisions may order a near-tie differently)."""
+    if pool_indices is None:
+        y, idx = F.max_pool2d(x, 2, return_indices=True)
+    else:
+        idx = pool_indices[key]
+        y = x.flatten(2).gather(2, idx.flatten(2)).view(idx.shape)
+    if record is not None:
+        record[key] = idx.detach()
+    return y
+
+
+def trad_forward(sd, x, training=True, stats=None, bf16_storage=False, relu_masks=None, record=None, pool_indices=None):
     """TraditionalUnet.forward (nets/TraditionalUnet.py:79-93).  stats: dict of BN buffers, updated in place when
     training (defaults to clones of the buffers in sd)."""
     if stats is None:
@@ -359,22 +377,24 @@ def trad_forward(sd, x, training=True, stats=None, bf16_storage=False):
     feats = []
     for i, (prefix, _, _) in enumerate(TRAD_ENC):
         if i > 0:
-            x = F.max_pool2d(x, 2)                                               # Down, :24-27
-        x = _double_conv(sd, prefix, x, training, stats, bf16_storage)
+            x = _pinned_max_pool(x, f"pool{i}", pool_indices, record)           # Down, :24-27
+        x = _double_conv(sd, prefix, x, training, stats, bf16_storage, relu_masks, record)
         feats.append(x)
     for i, (prefix, _, _) in enumerate(TRAD_DEC):
         up = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)   # Up.up, :36
         if bf16_storage:
             up = _r(up)
-        x = _double_conv(sd, prefix, torch.cat([feats[2 - i], up], 1), training, stats, bf16_storage)   # :40-42
+        x = _double_conv(sd, prefix, torch.cat([feats[2 - i], up], 1), training, stats, bf16_storage, relu_masks, record)   # :40-42
     return F.conv2d(x, sd["outc.weight"], sd["outc.bias"]), stats                # :66, :92
 
 
-def trad_train_step(sd, imgs, pngs, cls_weights, num_classes, dice=True, focal=False, bf16_storage=False):
+def trad_train_step(sd, imgs, pngs, cls_weights, num_classes, dice=True, focal=False, bf16_storage=False, relu_masks=None,
+                    record=None, pool_indices=None):
     """One iteration of the TraditionalUnet_Train.py loop without the optimizer: returns (loss, logits, grads, stats)."""
     p = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and "running_" not in k else v.clone())
          for k, v in sd.items()}
-    logits, stats = trad_forward(p, imgs, training=True, bf16_storage=bf16_storage)
+    logits, stats = trad_forward(p, imgs, training=True, bf16_storage=bf16_storage, relu_masks=relu_masks, record=record,
+                                 pool_indices=pool_indices)
     loss = focal_loss(logits, pngs, cls_weights, num_classes) if focal else ce_loss(logits, pngs, cls_weights, num_classes)
     if dice:
         loss = loss + dice_loss(logits, one_hot(pngs, num_classes))

@@ -62,3 +62,22 @@ def test_missing_library_is_a_hard_error(b2u, monkeypatch):
     monkeypatch.setattr(b2u._lib, "LIB_PATH", "/nonexistent/libb200unet.so")
     with pytest.raises(b2u._lib.B2UError):
         b2u._lib.lib()
+
+
+def test_fp32_validation_library_exports_its_subset(b2u):
+    """libb200unet_fp32.so (csrc/validation_fp32.cu): the same ABI names for the entry points UNetEngine uses, and nothing
+    undeclared except its identification symbol; selected explicitly, never by default."""
+    h = ctypes.CDLL(b2u._lib.LIB_PATH_FP32)
+    need = ["b2u_im2col_first", "b2u_pack_weights_multi", "b2u_conv_fprop", "b2u_conv_fprop_stats", "b2u_conv_fprop_scaled",
+            "b2u_conv_dgrad", "b2u_conv_wgrad", "b2u_conv_wgrad_workspace", "b2u_bias_grad", "b2u_maxpool2x2_fwd",
+            "b2u_maxpool2x2_bwd", "b2u_upsample2x_fwd", "b2u_upsample2x_bwd", "b2u_head_fwd", "b2u_head_bwd", "b2u_bn_fwd_train",
+            "b2u_bn_fwd_train_stats", "b2u_bn_fwd_eval", "b2u_bn_bwd", "b2u_bn_fold", "b2u_loss_fwd", "b2u_loss_bwd",
+            "b2u_fast_hist", "b2u_adam_step", "b2u_sgd_step", "b2u_last_error", "b2u_launch_count"]
+    for n in need:
+        assert hasattr(h, n) and n in b2u._lib.SIGNATURES, n
+    assert h.b2u_validation_fp32() == 1
+    assert not hasattr(ctypes.CDLL(b2u._lib.LIB_PATH), "b2u_validation_fp32")
+    assert not b2u._lib.validation_fp32() and b2u.ops.act_dtype() == torch.bfloat16      # the default is the product library
+    h.b2u_conv_fprop.restype = ctypes.c_int
+    rc = h.b2u_conv_fprop(None, 60, None, 0, None, None, None, 1, 8, 8, 64, 9, 1, 0, None)
+    assert rc == 1

@@ -5,6 +5,9 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_v
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200unet.so")
+# fp32 VALIDATION build of the same ABI (csrc/validation_fp32.cu): NHWC fp32 tensors, CUDA-core contractions; covers the
+# entry points UNetEngine uses.  Selected by set_validation_fp32(True) or B2U_FP32_VALIDATION=1; never the product path.
+LIB_PATH_FP32 = os.path.join(_HERE, "libb200unet_fp32.so")
 
 P, I, F, LL, SZ = c_void_p, c_int, c_float, c_longlong, c_size_t
 
@@ -85,27 +88,66 @@ SIGNATURES = {
 }
 
 _lib = None
+_handles = {}                     # library path -> loaded handle
+_validation = os.environ.get("B2U_FP32_VALIDATION", "0") not in ("", "0")
 
 
 class B2UError(RuntimeError):
     pass
 
 
+class _ValidationLib:
+    """The fp32 validation library exports a subset of the ABI; anything else fails loudly instead of silently running bf16."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    def __getattr__(self, name):
+        try:
+            fn = getattr(self._h, name)
+        except AttributeError:
+            raise B2UError(f"{name} is not part of the fp32 validation build (libb200unet_fp32.so)") from None
+        setattr(self, name, fn)
+        return fn
+
+
+def _load(path, validation):
+    if not os.path.exists(path):
+        raise B2UError(
+            f"{path} is missing: build it with `python unet-pytorch_b200/build.py` "
+            "(there is no CPU or PyTorch fallback for the hot path)")
+    h = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        if validation and not hasattr(h, name):
+            continue
+        fn = getattr(h, name)
+        fn.restype = res
+        fn.argtypes = args
+    return _ValidationLib(h) if validation else h
+
+
 def lib():
     """Loads the CUDA library; raises if it has not been built (python unet-pytorch_b200/build.py)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise B2UError(
-                f"{LIB_PATH} is missing: build it with `python unet-pytorch_b200/build.py` "
-                "(there is no CPU or PyTorch fallback for the hot path)")
-        h = ctypes.CDLL(LIB_PATH)
-        for name, (res, args) in SIGNATURES.items():
-            fn = getattr(h, name)
-            fn.restype = res
-            fn.argtypes = args
-        _lib = h
+        path = LIB_PATH_FP32 if _validation else LIB_PATH
+        if path not in _handles:
+            _handles[path] = _load(path, _validation)
+        _lib = _handles[path]
     return _lib
+
+
+def validation_fp32():
+    return _validation
+
+
+def set_validation_fp32(on):
+    """Routes every C-ABI call of this process to the fp32 validation build (True) or back to the product library (False).
+    Engines / modules must be constructed after the switch: their buffers and packed operands take the activation dtype
+    (ops.act_dtype()) of the library they were built for."""
+    global _lib, _validation
+    _validation = bool(on)
+    _lib = None
 
 
 class CallProfile:

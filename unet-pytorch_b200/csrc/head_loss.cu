@@ -23,6 +23,7 @@ namespace b2u {
 constexpr int kMaxCls = 32;
 constexpr int kHeadK = 64;
 
+#ifndef B2U_FP32_VALIDATION   // the fp32 validation build (validation_fp32.cu) brings its own head / operand kernels
 // ------------------------------------------------------------------------------------------
 // head forward: one thread per pixel; x row (64 bf16 = 128 B) in registers, weights in smem
 // ------------------------------------------------------------------------------------------
@@ -170,6 +171,7 @@ __global__ void head_wgrad_reduce_kernel(const float* __restrict__ partial, floa
   if (k < kHeadK) { if (dw) dw[c * kHeadK + k] = acc; }
   else if (db) db[c] = acc;
 }
+#endif  // !B2U_FP32_VALIDATION
 
 // ------------------------------------------------------------------------------------------
 // losses
@@ -509,6 +511,7 @@ loss_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ 
   }
 }
 
+#ifndef B2U_FP32_VALIDATION
 // final.weight [C][64] fp32 -> dgrad operand wd[ci][co] bf16, 64 x 64: columns [0,32) and [32,64) both hold W
 // (they multiply the hi and lo halves of the split dlogits), classes >= C are zero
 __global__ void pack_head_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wd, int C) {
@@ -532,6 +535,7 @@ __global__ void pack_head_fprop_kernel(const float* __restrict__ w, __nv_bfloat1
   }
   wf[i] = __float2bfloat16_rn(v);
 }
+#endif  // !B2U_FP32_VALIDATION
 
 // arg-max over classes (lowest index on ties, like numpy/torch): logits NCHW fp32 -> uint8 mask [N,H,W]
 __global__ void argmax_u8_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask, long long HW, long long P, int C) {
@@ -595,6 +599,7 @@ softmax_resize_argmax_kernel(const float* __restrict__ logits, uint8_t* __restri
 extern "C" {
 using namespace b2u;
 
+#ifndef B2U_FP32_VALIDATION
 int b2u_head_fwd(const void* x, const float* w, const float* b, float* logits, int N, int H, int W, int Cin, int ncls,
                  void* stream) {
   if (Cin != kHeadK || ncls <= 0 || ncls > kMaxCls) return set_error(B2U_ERR_SHAPE, "head_fwd: needs Cin == 64 and 1 <= classes <= 32 (got %d, %d)", Cin, ncls);
@@ -630,6 +635,8 @@ int b2u_head_bwd(const float* dlogits, const void* x, const float* w, void* dx, 
   }
   return 0;
 }
+
+#endif  // !B2U_FP32_VALIDATION
 
 static const int kLossBlocks = 4 * 148;
 size_t b2u_loss_workspace(int C) { return static_cast<size_t>(kLossBlocks) * (5 * C + 4) * sizeof(double); }
@@ -684,7 +691,11 @@ int b2u_loss_bwd(const float* logits, const long long* target, const float* oneh
 #define B2U_LBWD_C(OH_, NH_) do { if (C <= 8) B2U_LBWD(OH_, NH_, 8); else if (C <= 16) B2U_LBWD(OH_, NH_, 16); \
                                   else if (C <= 24) B2U_LBWD(OH_, NH_, 24); else B2U_LBWD(OH_, NH_, 32); } while (0)
   if (out_mode == 1) {
+#ifdef B2U_FP32_VALIDATION
+    return set_error(B2U_ERR_ARG, "loss_bwd: the bf16 [hi | lo] output is not part of the fp32 validation build");
+#else
     if (onehot) B2U_LBWD_C(true, true); else B2U_LBWD_C(false, true);
+#endif
   } else if (out_mode == 0) {
     if (onehot) B2U_LBWD_C(true, false); else B2U_LBWD_C(false, false);
   } else {
@@ -696,6 +707,7 @@ int b2u_loss_bwd(const float* logits, const long long* target, const float* oneh
   return 0;
 }
 
+#ifndef B2U_FP32_VALIDATION
 int b2u_pack_head_dgrad(const float* w, void* wd, int ncls, void* stream) {
   if (ncls <= 0 || ncls > kMaxCls) return set_error(B2U_ERR_SHAPE, "pack_head_dgrad: 1 <= classes <= 32");
   pack_head_dgrad_kernel<<<16, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, static_cast<__nv_bfloat16*>(wd), ncls);
@@ -709,6 +721,7 @@ int b2u_pack_head_fprop(const float* w, void* wf, int ncls, void* stream) {
   B2U_CHECK_LAUNCH("pack_head_fprop");
   return 0;
 }
+#endif  // !B2U_FP32_VALIDATION
 
 int b2u_argmax_u8(const float* logits, unsigned char* mask, int N, int C, int H, int W, void* stream) {
   if (N <= 0 || C <= 0 || C > 256 || H <= 0 || W <= 0) return set_error(B2U_ERR_SHAPE, "argmax: bad shape");

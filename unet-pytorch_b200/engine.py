@@ -149,7 +149,8 @@ class UNetEngine:
         self._ws = {}
 
     # ------------------------------------------------------------------ buffers
-    def _buf(self, key, shape, dtype=torch.bfloat16, zero=False):
+    def _buf(self, key, shape, dtype=None, zero=False):
+        dtype = ops.act_dtype() if dtype is None else dtype      # bf16; fp32 under the fp32 validation build
         t = self._bufs.get(key)
         if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
             t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
@@ -195,13 +196,13 @@ class UNetEngine:
                 ctot_p = c.c0_p + c.c1_p
                 if c.first:
                     if c.wf is None:
-                        c.wf = torch.zeros((c.cout_p, 64), dtype=torch.bfloat16, device=dev)
+                        c.wf = torch.zeros((c.cout_p, 64), dtype=ops.act_dtype(), device=dev)
                     count = (c.cout + 31) // 32                      # work blocks of this layer
                 else:
                     if c.wf is None:
-                        c.wf = torch.zeros((c.cout_p, 9 * ctot_p), dtype=torch.bfloat16, device=dev)
+                        c.wf = torch.zeros((c.cout_p, 9 * ctot_p), dtype=ops.act_dtype(), device=dev)
                     if need_dgrad and c.wd is None:
-                        c.wd = torch.zeros((ctot_p, 9 * c.cout_p), dtype=torch.bfloat16, device=dev)
+                        c.wd = torch.zeros((ctot_p, 9 * c.cout_p), dtype=ops.act_dtype(), device=dev)
                     count = ((c.cout + 31) // 32) * ((c.cin + 31) // 32)
                 wd_ptr = c.wd.data_ptr() if (need_dgrad and not c.first) else 0
                 blob += struct.pack("<QQQqiiiiiiii", w.data_ptr(), c.wf.data_ptr(), wd_ptr, start, c.cout, c.cin,
@@ -373,8 +374,11 @@ class UNetEngine:
             low = self._layer_fwd(c2, o1, params, A, training)
         wh = self._head_weight(params)
         # 1x1 classifier on the tensor cores: [hi | lo] bf16 split of the fp32 weights, fp32 NCHW logits from the epilogue
-        wf_head = ops.pack_head_fprop(wh, wf=self._buf("head:wf", (64, 64)))
-        logits = ops.head_fwd_tc(low, wf_head, params[self.head_name + ".bias"], self.num_classes)
+        if ops.act_dtype() == torch.float32:       # fp32 validation build: plain fp32 1x1 conv
+            logits = ops.head_fwd(low, wh, params[self.head_name + ".bias"])
+        else:
+            wf_head = ops.pack_head_fprop(wh, wf=self._buf("head:wf", (64, 64)))
+            logits = ops.head_fwd_tc(low, wf_head, params[self.head_name + ".bias"], self.num_classes)
         if save:
             self.saved = (A, feats, (N, H, W))
         return logits
@@ -483,7 +487,7 @@ class UNetEngine:
         C = self.num_classes
         fw, fb = has(hn + ".weight"), has(hn + ".bias")
         g = self._buf("g:" + self.dec[-1][1].name, last.shape) if need_dx[hn] else None
-        if dlogits.dtype == torch.bfloat16:
+        if dlogits.dtype == torch.bfloat16 and dlogits.dim() == 4 and dlogits.shape[-1] == 64 and ops.act_dtype() == torch.bfloat16:
             # [N,H,W,64] = [hi | lo] split dlogits from loss_bwd(nhwc64=True): the head's backward runs on the tensor
             # cores as a 1x1 dgrad (+ReLU mask) and a 1x1 wgrad (+bias) over 2 x 32 padded classes
             dl = dlogits.contiguous()

@@ -6,9 +6,24 @@ workspaces with torch's caching allocator; none of them has a CPU or PyTorch fal
 """
 import torch
 
+from . import _lib
 from ._lib import check, lib, ptr, stream_ptr
 
-BF16 = torch.bfloat16
+# dtype of every activation / gradient / packed-operand tensor ("void*" in include/b2u.h): bf16 on the product path, fp32
+# when the process runs the fp32 validation build (csrc/validation_fp32.cu)
+BF16 = torch.float32 if _lib.validation_fp32() else torch.bfloat16
+
+
+def act_dtype():
+    return BF16
+
+
+def set_validation_fp32(on):
+    """Switches the process between the product library (bf16 NHWC tensors, tcgen05 kernels) and the fp32 validation build
+    of the same ABI (BASELINE.json: rel-L2 <= 1e-5 against the fp32 reference).  Build engines / modules after the call."""
+    global BF16
+    _lib.set_validation_fp32(on)
+    BF16 = torch.float32 if on else torch.bfloat16
 
 
 def _req(t, dtype, name):
