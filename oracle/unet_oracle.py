@@ -354,11 +354,44 @@ def _double_conv(sd, prefix, x, training, stats, bf16, relu_masks=None, record=N
     return x
 
 
-def _pinned_max_pool(x, key, pool_indices, record):
-    """F.max_pool2d(x, 2); pool_indices (test aid, like relu_masks): {key: flat arg-max indices from return_indices=True} pins
-    which element of each window passes (two precisions may order a near-tie differently)."""
+_BRANCH = {"pin": None, "record": None}
+
+
+class branch:
+    """Context manager (test aid): inside it every ReLU / max-pool site of the BatchNorm families replays the decisions in `pin`
+    ({site: bool mask | arg-max indices}) and / or stores its own in `record`.  Sites are keyed by the BatchNorm name (conv -> BN
+    -> ReLU), the conv weight name (conv -> ReLU), the residual block's "<prefix>.out" (join + ReLU) and "p<i>" / "pool<k>" /
+    "pool" for the max-pools, i.e. the tensor names of the CUDA engine's program.  Pinning removes the only discontinuities of
+    the loss, so two precisions can be compared on one smooth branch."""
+
+    def __init__(self, pin=None, record=None):
+        self.new = {"pin": pin, "record": record}
+
+    def __enter__(self):
+        self.old = dict(_BRANCH)
+        _BRANCH.update(self.new)
+        return self
+
+    def __exit__(self, *exc):
+        _BRANCH.update(self.old)
+
+
+def _pinned_relu(y, key, pin=None, record=None):
+    """F.relu(y); pin (test aid): {key: bool mask} keeps exactly these elements instead, record receives this run's own mask."""
+    pin = _BRANCH["pin"] if pin is None else pin
+    record = _BRANCH["record"] if record is None else record
+    if record is not None:
+        record[key] = (y > 0).detach()
+    return F.relu(y) if pin is None else y * pin[key].to(y.dtype)
+
+
+def _pinned_max_pool(x, key, pool_indices=None, record=None, kernel=2, stride=2, ceil_mode=False):
+    """F.max_pool2d(x, kernel, stride, ceil_mode=...); pool_indices (test aid, like relu_masks): {key: flat arg-max indices from
+    return_indices=True} pins which element of each window passes (two precisions may order a near-tie differently)."""
+    pool_indices = _BRANCH["pin"] if pool_indices is None else pool_indices
+    record = _BRANCH["record"] if record is None else record
     if pool_indices is None:
-        y, idx = F.max_pool2d(x, 2, return_indices=True)
+        y, idx = F.max_pool2d(x, kernel, stride, ceil_mode=ceil_mode, return_indices=True)
     else:
         idx = pool_indices[key]
         y = x.flatten(2).gather(2, idx.flatten(2)).view(idx.shape)
@@ -459,7 +492,7 @@ def make_resnet_unet_params(num_classes, seed=11, gain=1.0, dec_gain=0.5):
     return sd
 
 
-def _rn_bn(sd, stats, name, z, training, relu, res=None, bf16=False):
+def _rn_bn(sd, stats, name, z, training, relu, res=None, bf16=False, pin=None, record=None):
     y = F.batch_norm(z, stats[name + ".running_mean"], stats[name + ".running_var"], sd[name + ".weight"], sd[name + ".bias"],
                      training, 0.1, 1e-5)
     if training:
@@ -467,7 +500,7 @@ def _rn_bn(sd, stats, name, z, training, relu, res=None, bf16=False):
     if res is not None:
         y = y + res
     if relu:
-        y = F.relu(y)
+        y = _pinned_relu(y, name, pin, record)
     return _r(y) if bf16 else y
 
 
@@ -480,29 +513,33 @@ def _rn_conv(sd, name, x, stride=1, padding=0, bias=None, bf16=False):
     return _r(z) if bf16 else z
 
 
-def resnet_unet_forward(sd, x, training=True, stats=None, bf16_storage=False):
-    """Unet.forward with backbone='resnet50' (nets/unet.py:62-78, nets/resnet.py:151-176, 77-97)."""
+def resnet_unet_forward(sd, x, training=True, stats=None, bf16_storage=False, pin=None, record=None):
+    """Unet.forward with backbone='resnet50' (nets/unet.py:62-78, nets/resnet.py:151-176, 77-97).
+    pin / record (test aids): ReLU masks keyed by BatchNorm name (encoder) or conv weight name (decoder) and the stem max-pool's
+    arg-max indices under "pool": replayed / recorded, see _pinned_relu."""
     b = bf16_storage
+    pr = dict(pin=pin, record=record)
     if stats is None:
         stats = {k: v.clone() for k, v in sd.items() if "running_" in k or "num_batches" in k}
     if b:
         x = _r(x)
     z = _rn_conv(sd, "resnet.conv1.weight", x, stride=2, padding=3, bf16=b)                         # resnet.py:166
-    feat1 = _rn_bn(sd, stats, "resnet.bn1", z, training, True, bf16=b)
-    x = F.max_pool2d(feat1, kernel_size=3, stride=2, padding=0, ceil_mode=True)                     # resnet.py:113,170
+    feat1 = _rn_bn(sd, stats, "resnet.bn1", z, training, True, bf16=b, **pr)
+    x = _pinned_max_pool(feat1, "pool", pin, record, kernel=3, stride=2, ceil_mode=True)            # resnet.py:113,170
     feats = [feat1]
     for li, (planes, blocks, stride) in enumerate(RESNET_LAYERS, start=1):
         for bi in range(blocks):
             p = f"resnet.layer{li}.{bi}"
             s = stride if bi == 0 else 1
-            out = _rn_bn(sd, stats, p + ".bn1", _rn_conv(sd, p + ".conv1.weight", x, bf16=b), training, True, bf16=b)
-            out = _rn_bn(sd, stats, p + ".bn2", _rn_conv(sd, p + ".conv2.weight", out, stride=s, padding=1, bf16=b), training, True, bf16=b)
+            out = _rn_bn(sd, stats, p + ".bn1", _rn_conv(sd, p + ".conv1.weight", x, bf16=b), training, True, bf16=b, **pr)
+            out = _rn_bn(sd, stats, p + ".bn2", _rn_conv(sd, p + ".conv2.weight", out, stride=s, padding=1, bf16=b), training, True, bf16=b,
+                         **pr)
             z3 = _rn_conv(sd, p + ".conv3.weight", out, bf16=b)
             idn = x
             if bi == 0:
                 idn = _rn_bn(sd, stats, p + ".downsample.1", _rn_conv(sd, p + ".downsample.0.weight", x, stride=s, bf16=b),
                              training, False, bf16=b)
-            x = _rn_bn(sd, stats, p + ".bn3", z3, training, True, res=idn, bf16=b)                  # resnet.py:89-95
+            x = _rn_bn(sd, stats, p + ".bn3", z3, training, True, res=idn, bf16=b, **pr)            # resnet.py:89-95
         feats.append(x)
 
     def up_stage(name, skip, low):
@@ -511,9 +548,10 @@ def resnet_unet_forward(sd, x, training=True, stats=None, bf16_storage=False):
             up = _r(up)
         y = torch.cat([skip, up], 1)
         for cv in ("conv1", "conv2"):
-            y = F.relu(_rn_conv(sd, f"{name}.{cv}.weight", y, padding=1, bias=sd[f"{name}.{cv}.bias"], bf16=False) if not b else
-                       F.conv2d(_r(y, fwd=False), sd[f"{name}.{cv}.weight"] + (sd[f"{name}.{cv}.weight"].to(torch.bfloat16).float() - sd[f"{name}.{cv}.weight"]).detach(),
-                                sd[f"{name}.{cv}.bias"], padding=1))
+            y = _pinned_relu(
+                _rn_conv(sd, f"{name}.{cv}.weight", y, padding=1, bias=sd[f"{name}.{cv}.bias"], bf16=False) if not b else
+                F.conv2d(_r(y, fwd=False), sd[f"{name}.{cv}.weight"] + (sd[f"{name}.{cv}.weight"].to(torch.bfloat16).float() - sd[f"{name}.{cv}.weight"]).detach(),
+                         sd[f"{name}.{cv}.bias"], padding=1), f"{name}.{cv}.weight", pin, record)
             if b:
                 y = _r(y)
         return y
@@ -529,16 +567,17 @@ def resnet_unet_forward(sd, x, training=True, stats=None, bf16_storage=False):
         if b:
             w = w + (w.to(torch.bfloat16).float() - w).detach()
             y = _r(y, fwd=False)
-        y = F.relu(F.conv2d(y, w, sd[f"up_conv.{i}.bias"], padding=1))
+        y = _pinned_relu(F.conv2d(y, w, sd[f"up_conv.{i}.bias"], padding=1), f"up_conv.{i}.weight", pin, record)
         if b:
             y = _r(y)
     return F.conv2d(y, sd["final.weight"], sd["final.bias"]), stats
 
 
-def resnet_unet_train_step(sd, imgs, pngs, cls_weights, num_classes, dice=True, focal=False, bf16_storage=False):
+def resnet_unet_train_step(sd, imgs, pngs, cls_weights, num_classes, dice=True, focal=False, bf16_storage=False, pin=None,
+                           record=None):
     p = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and "running_" not in k else v.clone())
          for k, v in sd.items()}
-    logits, stats = resnet_unet_forward(p, imgs, training=True, bf16_storage=bf16_storage)
+    logits, stats = resnet_unet_forward(p, imgs, training=True, bf16_storage=bf16_storage, pin=pin, record=record)
     loss = focal_loss(logits, pngs, cls_weights, num_classes) if focal else ce_loss(logits, pngs, cls_weights, num_classes)
     if dice:
         loss = loss + dice_loss(logits, one_hot(pngs, num_classes))
@@ -651,12 +690,12 @@ def ulu_forward(sd, x, variant, training=True, stats=None, bf16_storage=False, d
     skips = []
     for i in range(1, 5):
         if i > 1:
-            x = F.max_pool2d(x, 2, 2)
+            x = _pinned_max_pool(x, f"p{i}")
         x = _ulu_block(sd, stats, f"enc{i}", x, training, b)
         if se_rule is not None:
             x = _ulu_se(sd, f"se{i}", x, b)
         skips.append(x)
-    x = _ulu_block(sd, stats, "bridge", F.max_pool2d(x, 2, 2), training, b)
+    x = _ulu_block(sd, stats, "bridge", _pinned_max_pool(x, "p5"), training, b)
     if training and p_drop > 0 and drop_mask is not None:
         x = x * drop_mask[:, :, None, None]
         if b:
@@ -778,7 +817,7 @@ def _lw_res_block(sd, stats, p, x, training, b):
     y = _rn_bn(sd, stats, p + ".bn1", _rn_conv(sd, p + ".conv1.weight", x, padding=1, bias=sd[p + ".conv1.bias"], bf16=b), training, True, bf16=b)
     y = _rn_bn(sd, stats, p + ".bn2", _rn_conv(sd, p + ".conv2.weight", y, padding=1, bias=sd[p + ".conv2.bias"], bf16=b), training, False, bf16=b)
     y = _ulu_se(sd, p + ".se", y, b)
-    y = F.relu(y + x)
+    y = _pinned_relu(y + x, p + ".out")
     return _r(y) if b else y
 
 
@@ -803,7 +842,7 @@ def lw_forward(sd, x, training=True, stats=None, bf16_storage=False, drop_masks=
     for k in range(1, 6):
         x = _lw_conv_block(sd, stats, f"backbone.stage{k}.0", x, training, b)
         x = _lw_res_block(sd, stats, f"backbone.stage{k}.1", x, training, b)
-        x = drop(f"feat{k}", F.max_pool2d(x, 2, 2))
+        x = drop(f"feat{k}", _pinned_max_pool(x, f"pool{k}"))
         feats.append(x)
     low = feats[4]
     for k in (4, 3, 2, 1):

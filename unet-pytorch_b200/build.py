@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb200unet.so")
 OUT_FP32 = os.path.join(HERE, "libb200unet_fp32.so")
 # the loss / metric / optimizer kernels compute in fp32 already and are shared; -DB2U_FP32_VALIDATION drops the bf16 head
-SOURCES_FP32 = ["runtime.cu", "head_loss.cu", "hist.cu", "optim.cu", "validation_fp32.cu"]
+SOURCES_FP32 = ["runtime.cu", "head_loss.cu", "hist.cu", "optim.cu", "dw_se.cu", "validation_fp32.cu"]
 SOURCES = ["runtime.cu", "conv_igemm.cu", "conv_wgrad.cu", "elementwise.cu", "head_loss.cu", "hist.cu", "optim.cu", "bn.cu", "resnet_ops.cu", "dw_se.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

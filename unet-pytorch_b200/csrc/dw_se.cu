@@ -20,6 +20,7 @@ namespace b2u {
     b2u::note_launch();                                                                                  \
   } while (0)
 
+#ifndef B2U_FP32_VALIDATION   // the fp32 validation build (validation_fp32.cu) keeps only the SE fully connected kernels of this file
 __device__ __forceinline__ void d_unpack8(const uint4& v, float* f) {
   f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
   f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
@@ -327,6 +328,8 @@ __global__ void scale_nc_kernel(const uint4* __restrict__ x, const float* __rest
   y[i] = d_pack8(f);
 }
 
+#endif  // !B2U_FP32_VALIDATION
+
 // ------------------------------------------------------------------------------------------ SE fully connected part
 // one block per image: hidden = relu(W1 p + b1), scale = sigmoid(W2 hidden + b2)
 __global__ void se_fc_fwd_kernel(const float* __restrict__ pooled, const float* __restrict__ w1, const float* __restrict__ b1,
@@ -414,6 +417,7 @@ static inline dim3 rgrid(long long rows, int row_items, int block) {
 extern "C" {
 using namespace b2u;
 
+#ifndef B2U_FP32_VALIDATION
 int b2u_dwconv3x3_fwd(const void* x, const float* w, const float* bias, void* y, int N, int H, int W, int C, int flip,
                       void* stream) {
   if (N <= 0 || H <= 0 || W <= 0 || C % 8 != 0) return set_error(B2U_ERR_SHAPE, "dwconv3x3: bad shape");
@@ -460,6 +464,8 @@ int b2u_scale_nc(const void* x, const float* s, const float* a, void* y, int N, 
   return 0;
 }
 
+#endif  // !B2U_FP32_VALIDATION
+
 // SE fully connected part.  pooled/scale/dscale/dpooled are [N][Cp] (Cp >= C: channel padding of the activations),
 // hidden [N][R]; w1 [R][C], w2 [C][R] (nn.Linear layouts).
 int b2u_se_fc_fwd(const float* pooled, const float* w1, const float* b1, const float* w2, const float* b2, float* hidden,
@@ -485,6 +491,7 @@ int b2u_se_fc_bwd(const float* dscale, const float* pooled, const float* hidden,
   return 0;
 }
 
+#ifndef B2U_FP32_VALIDATION
 int b2u_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, float* db, void* ws, size_t ws_bytes, int N, int H, int W,
                         int C, void* stream) {
   if (N <= 0 || H <= 0 || W <= 0 || C % 8 != 0) return set_error(B2U_ERR_SHAPE, "dwconv3x3_wgrad: bad shape");
@@ -501,5 +508,6 @@ int b2u_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, float* db, voi
   B2U_CHECK_LAUNCH("dw_reduce_split");
   return 0;
 }
+#endif  // !B2U_FP32_VALIDATION
 
 }  // extern "C"

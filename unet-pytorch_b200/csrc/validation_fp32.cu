@@ -570,6 +570,255 @@ __global__ void v32_bn_fold_kernel(const float* __restrict__ gamma, const float*
                                static_cast<double>(beta ? beta[c] : 0.f));
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// ResNet50 encoder helpers (resnet_ops.cu in fp32): stem im2col, stride-2 helpers, 3x3 s2 ceil-mode max-pool, joins
+// ---------------------------------------------------------------------------------------------
+__global__ void v32_im2col_stem_kernel(const float* __restrict__ x, float* __restrict__ col, int N, int Cin, int H, int W, int Ho,
+                                       int Wo) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(N) * Ho * Wo * 192) return;
+  const int k = static_cast<int>(idx % 192);
+  long long t = idx / 192;
+  const int wo = static_cast<int>(t % Wo); t /= Wo;
+  const int ho = static_cast<int>(t % Ho);
+  const int n = static_cast<int>(t / Ho);
+  float v = 0.f;
+  if (k < 49 * Cin) {
+    const int tap = k / Cin, c = k - tap * Cin;
+    const int hh = 2 * ho + tap / 7 - 3, ww = 2 * wo + tap % 7 - 3;
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x[((static_cast<size_t>(n) * Cin + c) * H + hh) * W + ww];
+  }
+  col[idx] = v;
+}
+__global__ void v32_pack_weights_im2col_kernel(const float* __restrict__ w, float* __restrict__ wf, int Cout, int Cin, int taps,
+                                               int Kpad) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Cout * Kpad) return;
+  const int co = idx / Kpad, k = idx - co * Kpad;
+  float v = 0.f;
+  if (k < taps * Cin) { const int tap = k / Cin, c = k - tap * Cin; v = w[(static_cast<size_t>(co) * Cin + c) * taps + tap]; }
+  wf[idx] = v;
+}
+// dw[co][c][tap] = sum_p dz[p][co] * col[p][tap * cin + c]: one block per output element row, double accumulators
+__global__ void __launch_bounds__(256)
+v32_wgrad_im2col_kernel(const float* __restrict__ col, const float* __restrict__ dz, float* __restrict__ dw, long long P, int Kpad,
+                        int Cout, int cin, int taps) {
+  __shared__ double red[256];
+  const int co = blockIdx.x / (cin * taps), k = blockIdx.x % (cin * taps);    // k = tap * cin + c
+  double s = 0.0;
+  for (long long p = threadIdx.x; p < P; p += 256) s += static_cast<double>(dz[p * Cout + co]) * static_cast<double>(col[p * Kpad + k]);
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { const int tap = k / cin, c = k - tap * cin; dw[(static_cast<size_t>(co) * cin + c) * taps + tap] = static_cast<float>(red[0]); }
+}
+__global__ void v32_subsample2_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(N) * Ho * Wo * C) return;
+  const int c = static_cast<int>(idx % C);
+  long long t = idx / C;
+  const int wo = static_cast<int>(t % Wo); t /= Wo;
+  const int ho = static_cast<int>(t % Ho);
+  const int n = static_cast<int>(t / Ho);
+  y[idx] = x[((static_cast<size_t>(n) * H + 2 * ho) * W + 2 * wo) * C + c];
+}
+__global__ void v32_zero_insert2_kernel(const float* __restrict__ y, float* __restrict__ x, int N, int H, int W, int C) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(N) * H * W * C) return;
+  const int c = static_cast<int>(idx % C);
+  long long t = idx / C;
+  const int w = static_cast<int>(t % W); t /= W;
+  const int h = static_cast<int>(t % H);
+  const int n = static_cast<int>(t / H);
+  x[idx] = (!(h & 1) && !(w & 1)) ? y[((static_cast<size_t>(n) * Ho + h / 2) * Wo + w / 2) * C + c] : 0.f;
+}
+__global__ void v32_maxpool3_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int Ho, int Wo,
+                                        int C) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(N) * Ho * Wo * C) return;
+  const int c = static_cast<int>(idx % C);
+  long long t = idx / C;
+  const int wo = static_cast<int>(t % Wo); t /= Wo;
+  const int ho = static_cast<int>(t % Ho);
+  const int n = static_cast<int>(t / Ho);
+  float m = -INFINITY;
+  for (int r = 0; r < 3; ++r)
+    for (int q = 0; q < 3; ++q) {
+      const int h = 2 * ho + r, w = 2 * wo + q;
+      if (h < H && w < W) m = fmaxf(m, x[((static_cast<size_t>(n) * H + h) * W + w) * C + c]);
+    }
+  y[idx] = m;
+}
+// dx[h,w] = sum of dy over the windows containing (h,w) whose FIRST maximum (row-major scan, like ATen) is (h,w)
+__global__ void v32_maxpool3_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx, int N,
+                                        int H, int W, int Ho, int Wo, int C) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(N) * H * W * C) return;
+  const int c = static_cast<int>(idx % C);
+  long long t = idx / C;
+  const int w = static_cast<int>(t % W); t /= W;
+  const int h = static_cast<int>(t % H);
+  const int n = static_cast<int>(t / H);
+  const float* ximg = x + static_cast<size_t>(n) * H * W * C + c;
+  const float xv = x[idx];
+  const int ho_lo = h >= 2 ? (h - 1) / 2 : 0, ho_hi = min(h / 2, Ho - 1);
+  const int wo_lo = w >= 2 ? (w - 1) / 2 : 0, wo_hi = min(w / 2, Wo - 1);
+  float acc = 0.f;
+  for (int ho = ho_lo; ho <= ho_hi; ++ho)
+    for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+      bool first = true;
+      for (int r = 0; r < 3 && first; ++r)
+        for (int q = 0; q < 3; ++q) {
+          const int hh = 2 * ho + r, ww = 2 * wo + q;
+          if (hh >= H || ww >= W || (hh == h && ww == w)) continue;
+          const float f = ximg[(static_cast<size_t>(hh) * W + ww) * C];
+          const bool before = hh < h || (hh == h && ww < w);
+          if (!(before ? f < xv : f <= xv)) { first = false; break; }
+        }
+      if (first) acc += dy[((static_cast<size_t>(n) * Ho + ho) * Wo + wo) * C + c];
+    }
+  dx[idx] = acc;
+}
+// mode 0: a + b; 1: relu(a + b); 2: a * (b > 0)
+__global__ void v32_join_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n, int mode) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = a[i], y = b[i];
+  out[i] = mode == 0 ? x + y : (mode == 1 ? fmaxf(x + y, 0.f) : (y > 0.f ? x : 0.f));
+}
+// NCHW fp32 -> NHWC fp32 with the channel dimension zero-padded to Cpad
+__global__ void v32_nchw_to_nhwc_padded_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int C, long long HW, int Cpad) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(N) * HW * Cpad) return;
+  const int c = static_cast<int>(idx % Cpad);
+  const long long p = idx / Cpad;
+  const long long n = p / HW, hw = p % HW;
+  y[idx] = c < C ? x[(n * C + c) * HW + hw] : 0.f;
+}
+// F.interpolate(x, size, mode="bilinear", align_corners=True) on NCHW fp32 planes, and its adjoint (gather form)
+__global__ void v32_resize_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long NC, int Hi, int Wi, int Ho, int Wo,
+                                      float sh, float sw) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= NC * Ho * Wo) return;
+  const int wo = static_cast<int>(idx % Wo);
+  const int ho = static_cast<int>((idx / Wo) % Ho);
+  const long long nc = idx / (static_cast<long long>(Wo) * Ho);
+  int h0, h1, w0, w1; float lh, lw;
+  v32_src_index(ho, sh, Hi, h0, h1, lh);
+  v32_src_index(wo, sw, Wi, w0, w1, lw);
+  const float* img = x + nc * Hi * Wi;
+  y[idx] = (1.f - lh) * ((1.f - lw) * img[h0 * Wi + w0] + lw * img[h0 * Wi + w1]) +
+           lh * ((1.f - lw) * img[h1 * Wi + w0] + lw * img[h1 * Wi + w1]);
+}
+__global__ void v32_resize_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, long long NC, int Hi, int Wi, int Ho, int Wo,
+                                      float sh, float sw) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= NC * Hi * Wi) return;
+  const int j = static_cast<int>(idx % Wi);
+  const int i = static_cast<int>((idx / Wi) % Hi);
+  const long long nc = idx / (static_cast<long long>(Wi) * Hi);
+  const float* img = dy + nc * Ho * Wo;
+  // outputs whose source interval touches i: src in (i-1, i+1)  ->  o in ((i-1)/s, (i+1)/s)
+  const int oh_lo = sh > 0.f ? max(0, static_cast<int>((i - 1) / sh) - 1) : 0, oh_hi = sh > 0.f ? min(Ho - 1, static_cast<int>((i + 1) / sh) + 1) : Ho - 1;
+  const int ow_lo = sw > 0.f ? max(0, static_cast<int>((j - 1) / sw) - 1) : 0, ow_hi = sw > 0.f ? min(Wo - 1, static_cast<int>((j + 1) / sw) + 1) : Wo - 1;
+  float acc = 0.f;
+  for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+    int h0, h1; float lh;
+    v32_src_index(oh, sh, Hi, h0, h1, lh);
+    const float wh = (h0 == i ? 1.f - lh : 0.f) + (h1 == i ? lh : 0.f);
+    if (wh == 0.f) continue;
+    for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+      int w0, w1; float lw;
+      v32_src_index(ow, sw, Wi, w0, w1, lw);
+      const float ww = (w0 == j ? 1.f - lw : 0.f) + (w1 == j ? lw : 0.f);
+      if (ww != 0.f) acc = fmaf(wh * ww, img[static_cast<size_t>(oh) * Wo + ow], acc);
+    }
+  }
+  dx[idx] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// depthwise 3x3, per-(image, channel) reductions and scaling (dw_se.cu in fp32)
+// ---------------------------------------------------------------------------------------------
+__global__ void v32_dwconv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                  float* __restrict__ y, int N, int H, int W, int C, int flip) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(N) * H * W * C) return;
+  const int c = static_cast<int>(idx % C);
+  long long t = idx / C;
+  const int ww = static_cast<int>(t % W); t /= W;
+  const int hh = static_cast<int>(t % H);
+  const int n = static_cast<int>(t / H);
+  float acc = bias ? bias[c] : 0.f;
+  for (int tap = 0; tap < 9; ++tap) {
+    const int h = hh + tap / 3 - 1, v = ww + tap % 3 - 1;
+    if (h >= 0 && h < H && v >= 0 && v < W)
+      acc = fmaf(x[((static_cast<size_t>(n) * H + h) * W + v) * C + c], w[c * 9 + (flip ? 8 - tap : tap)], acc);
+  }
+  y[idx] = acc;
+}
+// dw[c][tap] = sum_p dy[p][c] x[p + tap][c]; column 9 = sum dy (bias): block = (channel, quantity), double accumulators
+__global__ void __launch_bounds__(256)
+v32_dwconv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, float* __restrict__ db,
+                        int N, int H, int W, int C) {
+  __shared__ double red[256];
+  const int c = blockIdx.x / 10, tap = blockIdx.x % 10;
+  const long long P = static_cast<long long>(N) * H * W;
+  double s = 0.0;
+  for (long long p = threadIdx.x; p < P; p += 256) {
+    const double g = dy[p * C + c];
+    if (tap == 9) { s += g; continue; }
+    const int ww = static_cast<int>(p % W), hh = static_cast<int>((p / W) % H);
+    const long long n = p / (static_cast<long long>(W) * H);
+    const int h = hh + tap / 3 - 1, v = ww + tap % 3 - 1;
+    if (h >= 0 && h < H && v >= 0 && v < W) s += g * static_cast<double>(x[((n * H + h) * W + v) * C + c]);
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (tap < 9) { if (dw) dw[c * 9 + tap] = static_cast<float>(red[0]); }
+    else if (db) db[c] = static_cast<float>(red[0]);
+  }
+}
+// out[n][c] = scale * sum over the image's pixels of a (b == NULL) or a * b
+__global__ void __launch_bounds__(256)
+v32_spatial_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long HW, int C,
+                          float scale) {
+  __shared__ double red[8][33];
+  const int n = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), lane = threadIdx.x >> 5;
+  double s = 0.0;
+  if (c < C)
+    for (long long p = lane; p < HW; p += 8) {
+      const size_t i = (static_cast<size_t>(n) * HW + p) * C + c;
+      s += b ? static_cast<double>(a[i]) * static_cast<double>(b[i]) : static_cast<double>(a[i]);
+    }
+  red[lane][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (lane == 0 && c < C) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    out[static_cast<size_t>(n) * C + c] = static_cast<float>(t * static_cast<double>(scale));
+  }
+}
+__global__ void v32_scale_nc_kernel(const float* __restrict__ x, const float* __restrict__ s, const float* __restrict__ a,
+                                    float* __restrict__ y, long long HW, int C, long long total) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % C);
+  const long long n = idx / (HW * C);
+  y[idx] = fmaf(x[idx], s[n * C + c], a ? a[n * C + c] : 0.f);
+}
+
 }  // namespace b2u
 
 // ----------------------------------------------------------------------------
@@ -823,6 +1072,131 @@ int b2u_bn_fold(const float* gamma, const float* beta, const float* running_mean
   v32_bn_fold_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(gamma, beta, running_mean, running_var, conv_bias,
                                                                                     scale, bias, C, eps);
   B2U_CHECK_LAUNCH("bn_fold_fp32");
+  return 0;
+}
+
+
+// ---- ResNet50 helpers, joins, resizes ----
+int b2u_im2col_stem(const float* x, void* col, int N, int Cin, int H, int W, void* stream) {
+  if (N <= 0 || Cin <= 0 || 49 * Cin > 192 || H < 1 || W < 1) return set_error(B2U_ERR_SHAPE, "im2col_stem: bad shape (Cin=%d)", Cin);
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  v32_im2col_stem_kernel<<<blocks_for(static_cast<long long>(N) * Ho * Wo * 192, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<float*>(col), N, Cin, H, W, Ho, Wo);
+  B2U_CHECK_LAUNCH("im2col_stem_fp32");
+  return 0;
+}
+int b2u_pack_weights_im2col(const float* w, void* wf, int Cout, int Cin, int taps, int Kpad, void* stream) {
+  if (Cout <= 0 || Cin <= 0 || taps <= 0 || taps * Cin > Kpad) return set_error(B2U_ERR_SHAPE, "pack_weights_im2col: bad shape");
+  v32_pack_weights_im2col_kernel<<<(Cout * Kpad + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, static_cast<float*>(wf), Cout,
+                                                                                                         Cin, taps, Kpad);
+  B2U_CHECK_LAUNCH("pack_weights_im2col_fp32");
+  return 0;
+}
+int b2u_conv_wgrad_im2col(const void* x0, int Kpad, const void* dz, int Cout, float* dw, void* /*ws*/, size_t /*ws_bytes*/, int N, int H,
+                          int W, int cin, int taps, void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || Cout <= 0 || cin <= 0 || taps * cin > Kpad) return set_error(B2U_ERR_SHAPE, "wgrad_im2col: bad shape");
+  v32_wgrad_im2col_kernel<<<Cout * cin * taps, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float*>(x0), static_cast<const float*>(dz), dw, static_cast<long long>(N) * H * W, Kpad, Cout, cin, taps);
+  B2U_CHECK_LAUNCH("wgrad_im2col_fp32");
+  return 0;
+}
+int b2u_subsample2(const void* x, void* y, int N, int H, int W, int C, void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0) return set_error(B2U_ERR_SHAPE, "subsample2: bad shape");
+  const long long total = static_cast<long long>(N) * ((H + 1) / 2) * ((W + 1) / 2) * C;
+  v32_subsample2_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(x),
+                                                                                              static_cast<float*>(y), N, H, W, C);
+  B2U_CHECK_LAUNCH("subsample2_fp32");
+  return 0;
+}
+int b2u_zero_insert2(const void* y, void* x, int N, int H, int W, int C, void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0) return set_error(B2U_ERR_SHAPE, "zero_insert2: bad shape");
+  v32_zero_insert2_kernel<<<blocks_for(static_cast<long long>(N) * H * W * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float*>(y), static_cast<float*>(x), N, H, W, C);
+  B2U_CHECK_LAUNCH("zero_insert2_fp32");
+  return 0;
+}
+int b2u_maxpool3x3s2_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream) {
+  if (N <= 0 || H < 3 || W < 3 || C <= 0) return set_error(B2U_ERR_SHAPE, "maxpool3x3s2: needs H,W >= 3");
+  const int Ho = (H - 3 + 1) / 2 + 1, Wo = (W - 3 + 1) / 2 + 1;
+  v32_maxpool3_fwd_kernel<<<blocks_for(static_cast<long long>(N) * Ho * Wo * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float*>(x), static_cast<float*>(y), N, H, W, Ho, Wo, C);
+  B2U_CHECK_LAUNCH("maxpool3x3s2_fwd_fp32");
+  return 0;
+}
+int b2u_maxpool3x3s2_bwd(const void* dy, const void* x, void* dx, int N, int H, int W, int C, void* stream) {
+  if (N <= 0 || H < 3 || W < 3 || C <= 0) return set_error(B2U_ERR_SHAPE, "maxpool3x3s2_bwd: needs H,W >= 3");
+  const int Ho = (H - 3 + 1) / 2 + 1, Wo = (W - 3 + 1) / 2 + 1;
+  v32_maxpool3_bwd_kernel<<<blocks_for(static_cast<long long>(N) * H * W * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float*>(dy), static_cast<const float*>(x), static_cast<float*>(dx), N, H, W, Ho, Wo, C);
+  B2U_CHECK_LAUNCH("maxpool3x3s2_bwd_fp32");
+  return 0;
+}
+static int v32_join(const void* a, const void* b, void* out, long long n, int mode, void* stream) {
+  if (n <= 0) return set_error(B2U_ERR_SHAPE, "join: empty tensor");
+  v32_join_kernel<<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(a), static_cast<const float*>(b),
+                                                                                   static_cast<float*>(out), n, mode);
+  B2U_CHECK_LAUNCH("join_fp32");
+  return 0;
+}
+/* the ABI names say bf16; in this build the element type is fp32 like every other activation */
+int b2u_add_bf16(const void* a, const void* b, void* out, long long n, void* stream) { return v32_join(a, b, out, n, 0, stream); }
+int b2u_add_relu_bf16(const void* a, const void* b, void* out, long long n, void* stream) { return v32_join(a, b, out, n, 1, stream); }
+int b2u_relu_bwd_bf16(const void* dy, const void* y, void* dx, long long n, void* stream) { return v32_join(dy, y, dx, n, 2, stream); }
+int b2u_nchw_f32_to_nhwc_bf16_padded(const float* x, void* y, int N, int C, int H, int W, int Cpad, void* stream) {
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || Cpad < C) return set_error(B2U_ERR_SHAPE, "nchw_to_nhwc_padded: bad shape");
+  const long long HW = static_cast<long long>(H) * W;
+  v32_nchw_to_nhwc_padded_kernel<<<blocks_for(N * HW * Cpad, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<float*>(y), N, C,
+                                                                                                              HW, Cpad);
+  B2U_CHECK_LAUNCH("nchw_to_nhwc_padded_fp32");
+  return 0;
+}
+int b2u_resize_bilinear_f32_fwd(const float* x, float* y, long long NC, int Hi, int Wi, int Ho, int Wo, void* stream) {
+  if (NC <= 0 || Hi <= 0 || Wi <= 0 || Ho <= 0 || Wo <= 0) return set_error(B2U_ERR_SHAPE, "resize_bilinear: bad shape");
+  v32_resize_fwd_kernel<<<blocks_for(NC * Ho * Wo, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, NC, Hi, Wi, Ho, Wo,
+                                                                                                     v32_ac_scale(Hi, Ho), v32_ac_scale(Wi, Wo));
+  B2U_CHECK_LAUNCH("resize_bilinear_fwd_fp32");
+  return 0;
+}
+int b2u_resize_bilinear_f32_bwd(const float* dy, float* dx, long long NC, int Hi, int Wi, int Ho, int Wo, void* stream) {
+  if (NC <= 0 || Hi <= 0 || Wi <= 0 || Ho <= 0 || Wo <= 0) return set_error(B2U_ERR_SHAPE, "resize_bilinear_bwd: bad shape");
+  v32_resize_bwd_kernel<<<blocks_for(NC * Hi * Wi, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, dx, NC, Hi, Wi, Ho, Wo,
+                                                                                                     v32_ac_scale(Hi, Ho), v32_ac_scale(Wi, Wo));
+  B2U_CHECK_LAUNCH("resize_bilinear_bwd_fp32");
+  return 0;
+}
+
+// ---- depthwise / squeeze-excite support ----
+int b2u_dwconv3x3_fwd(const void* x, const float* w, const float* bias, void* y, int N, int H, int W, int C, int flip, void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0) return set_error(B2U_ERR_SHAPE, "dwconv3x3: bad shape");
+  v32_dwconv_kernel<<<blocks_for(static_cast<long long>(N) * H * W * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float*>(x), w, bias, static_cast<float*>(y), N, H, W, C, flip);
+  B2U_CHECK_LAUNCH("dwconv3x3_fp32");
+  return 0;
+}
+size_t b2u_dwconv3x3_wgrad_workspace(int) { return 16; }
+int b2u_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, float* db, void* /*ws*/, size_t /*ws_bytes*/, int N, int H, int W, int C,
+                        void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0) return set_error(B2U_ERR_SHAPE, "dwconv3x3_wgrad: bad shape");
+  v32_dwconv_wgrad_kernel<<<C * 10, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(x), static_cast<const float*>(dy),
+                                                                               dw, db, N, H, W, C);
+  B2U_CHECK_LAUNCH("dwconv3x3_wgrad_fp32");
+  return 0;
+}
+int b2u_spatial_reduce_workspace_floats(int, int) { return 4; }
+int b2u_spatial_reduce(const void* a, const void* b, float* out, void* /*ws*/, size_t /*ws_bytes*/, int N, long long HW, int C, float scale,
+                       void* stream) {
+  if (N <= 0 || HW <= 0 || C <= 0) return set_error(B2U_ERR_SHAPE, "spatial_reduce: bad shape");
+  v32_spatial_reduce_kernel<<<dim3((C + 31) / 32, N), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float*>(a), static_cast<const float*>(b), out, HW, C, scale);
+  B2U_CHECK_LAUNCH("spatial_reduce_fp32");
+  return 0;
+}
+int b2u_scale_nc(const void* x, const float* s, const float* a, void* y, int N, long long HW, int C, void* stream) {
+  if (N <= 0 || HW <= 0 || C <= 0) return set_error(B2U_ERR_SHAPE, "scale_nc: bad shape");
+  const long long total = static_cast<long long>(N) * HW * C;
+  v32_scale_nc_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(x), s, a,
+                                                                                            static_cast<float*>(y), HW, C, total);
+  B2U_CHECK_LAUNCH("scale_nc_fp32");
   return 0;
 }
 

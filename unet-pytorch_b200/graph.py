@@ -317,7 +317,8 @@ class GraphEngine:
         return out
 
     # ------------------------------------------------------------------ buffers
-    def _buf(self, key, shape, dtype=torch.bfloat16):
+    def _buf(self, key, shape, dtype=None):
+        dtype = ops.act_dtype() if dtype is None else dtype      # bf16; fp32 under the fp32 validation build
         t = self._bufs.get(key)
         if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
             t = torch.empty(shape, dtype=dtype, device=self.device)
@@ -394,9 +395,9 @@ class GraphEngine:
                         self._bufs["w2:" + n] = src
                 wf, wd = self._packed.get(n, (None, None))
                 if wf is None:
-                    wf = torch.zeros((coutp, taps * (c0p + c1p)), dtype=torch.bfloat16, device=dev)
+                    wf = torch.zeros((coutp, taps * (c0p + c1p)), dtype=ops.act_dtype(), device=dev)
                 if need_dgrad and wd is None:
-                    wd = torch.zeros((c0p + c1p, taps * coutp), dtype=torch.bfloat16, device=dev)
+                    wd = torch.zeros((c0p + c1p, taps * coutp), dtype=ops.act_dtype(), device=dev)
                 self._packed[n] = (wf, wd)
                 blob += struct.pack("<QQQqiiiiiiii", src.data_ptr(), wf.data_ptr(), wd.data_ptr() if need_dgrad else 0,
                                     start, cout, c0 + c1, taps, 0, c0, c0p, c0p + c1p, coutp)
@@ -626,8 +627,11 @@ class GraphEngine:
                 T[ins["out"]] = _T(y, needs_grad=xin.needs_grad)
             elif op == "head":
                 xin = T[ins["x"]]
-                wf_head = ops.pack_head_fprop(self._head_weight(params, ins), wf=self._buf("head:wf", (64, 64)))
-                logits = ops.head_fwd_tc(xin.data, wf_head, params[ins["bias"]], self.num_classes)
+                if ops.act_dtype() == torch.float32:       # fp32 validation build: plain fp32 1x1 conv
+                    logits = ops.head_fwd(xin.data, self._head_weight(params, ins), params[ins["bias"]])
+                else:
+                    wf_head = ops.pack_head_fprop(self._head_weight(params, ins), wf=self._buf("head:wf", (64, 64)))
+                    logits = ops.head_fwd_tc(xin.data, wf_head, params[ins["bias"]], self.num_classes)
         if save:
             self.saved = (T, (N, H, W), set(trainable))
         return logits
@@ -669,7 +673,7 @@ class GraphEngine:
                 C = self.num_classes
                 fw, fb = has(ins["w"]), has(ins["bias"])
                 g = self._buf("g:" + ins["x"], xin.data.shape) if xin.needs_grad else None
-                if dlogits.dtype == torch.bfloat16:
+                if dlogits.dtype == torch.bfloat16 and ops.act_dtype() == torch.bfloat16:
                     dl = dlogits.contiguous()
                     if g is not None:
                         wd_head = ops.pack_head_dgrad(wh, wd=self._buf("head:wd", (64, 64)))
