@@ -12,6 +12,10 @@
  *     logits and parameters are fp32 in the reference's own layouts (NCHW, OIHW);
  *   - `stream` is a cudaStream_t (CUstream); launches are asynchronous on it;
  *   - return value 0 = ok, otherwise a B2U_ERR_* code; b2u_last_error() gives the message (thread-local).
+ *
+ * libb200unet_fp32.so (csrc/validation_fp32.cu) is the fp32 VALIDATION build of this same header: the entry points the
+ * host engines use, with every "void*" activation / gradient / packed operand as fp32 instead of bf16 and CUDA-core
+ * contractions (BASELINE tolerance "<= 1e-5 for an fp32 validation build"); test tooling only, never the product path.
  */
 #ifndef B2U_H_
 #define B2U_H_
