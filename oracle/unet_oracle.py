@@ -328,32 +328,6 @@ def make_trad_params(num_classes, seed=11, in_channels=3, gain=1.0):
     return sd
 
 
-def _double_conv(sd, prefix, x, training, stats, bf16, relu_masks=None, record=None):
-    """DoubleConv.forward (nets/TraditionalUnet.py:5-18); BatchNorm2d with torch defaults (eps 1e-5, momentum 0.1).
-    relu_masks (test aid): {BatchNorm name: bool NCHW}; the ReLU after that BatchNorm keeps exactly these elements, which pins
-    the piecewise-linear branch when two precisions disagree about the sign of a pre-activation that is ~0.
-    record (test aid): dict that receives this run's own ReLU masks."""
-    for idx in (0, 3):
-        w, b = sd[f"{prefix}.double_conv.{idx}.weight"], sd[f"{prefix}.double_conv.{idx}.bias"]
-        bn = f"{prefix}.double_conv.{idx + 1}"
-        if bf16:
-            w = w + (w.to(torch.bfloat16).to(w.dtype) - w).detach()
-            x = _r(x, fwd=False)
-        z = F.conv2d(x, w, b, padding=1)
-        if bf16:
-            z = _r(z)
-        rm, rv = stats[bn + ".running_mean"], stats[bn + ".running_var"]
-        y = F.batch_norm(z, rm, rv, sd[bn + ".weight"], sd[bn + ".bias"], training, 0.1, 1e-5)
-        if training:
-            stats[bn + ".num_batches_tracked"] = stats[bn + ".num_batches_tracked"] + 1
-        if record is not None:
-            record[bn] = (y > 0).detach()
-        x = F.relu(y) if relu_masks is None else y * relu_masks[bn].to(y.dtype)
-        if bf16:
-            x = _r(x)
-    return x
-
-
 _BRANCH = {"pin": None, "record": None}
 
 
@@ -400,7 +374,29 @@ def _pinned_max_pool(x, key, pool_indices=None, record=None, kernel=2, stride=2,
     return y
 
 
-def trad_forward(sd, x, training=True, stats=None, bf16_storage=False, relu_masks=None, record=None, pool_indices=None):
+def _double_conv(sd, prefix, x, training, stats, bf16):
+    """DoubleConv.forward (nets/TraditionalUnet.py:5-18); BatchNorm2d with torch defaults (eps 1e-5, momentum 0.1).
+    The ReLU sites are keyed by their BatchNorm's name for oracle.branch."""
+    for idx in (0, 3):
+        w, b = sd[f"{prefix}.double_conv.{idx}.weight"], sd[f"{prefix}.double_conv.{idx}.bias"]
+        bn = f"{prefix}.double_conv.{idx + 1}"
+        if bf16:
+            w = w + (w.to(torch.bfloat16).to(w.dtype) - w).detach()
+            x = _r(x, fwd=False)
+        z = F.conv2d(x, w, b, padding=1)
+        if bf16:
+            z = _r(z)
+        rm, rv = stats[bn + ".running_mean"], stats[bn + ".running_var"]
+        y = F.batch_norm(z, rm, rv, sd[bn + ".weight"], sd[bn + ".bias"], training, 0.1, 1e-5)
+        if training:
+            stats[bn + ".num_batches_tracked"] = stats[bn + ".num_batches_tracked"] + 1
+        x = _pinned_relu(y, bn)
+        if bf16:
+            x = _r(x)
+    return x
+
+
+def trad_forward(sd, x, training=True, stats=None, bf16_storage=False):
     """TraditionalUnet.forward (nets/TraditionalUnet.py:79-93).  stats: dict of BN buffers, updated in place when
     training (defaults to clones of the buffers in sd)."""
     if stats is None:
@@ -410,24 +406,22 @@ def trad_forward(sd, x, training=True, stats=None, bf16_storage=False, relu_mask
     feats = []
     for i, (prefix, _, _) in enumerate(TRAD_ENC):
         if i > 0:
-            x = _pinned_max_pool(x, f"pool{i}", pool_indices, record)           # Down, :24-27
-        x = _double_conv(sd, prefix, x, training, stats, bf16_storage, relu_masks, record)
+            x = _pinned_max_pool(x, f"pool{i}")                                  # Down, :24-27
+        x = _double_conv(sd, prefix, x, training, stats, bf16_storage)
         feats.append(x)
     for i, (prefix, _, _) in enumerate(TRAD_DEC):
         up = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)   # Up.up, :36
         if bf16_storage:
             up = _r(up)
-        x = _double_conv(sd, prefix, torch.cat([feats[2 - i], up], 1), training, stats, bf16_storage, relu_masks, record)   # :40-42
+        x = _double_conv(sd, prefix, torch.cat([feats[2 - i], up], 1), training, stats, bf16_storage)   # :40-42
     return F.conv2d(x, sd["outc.weight"], sd["outc.bias"]), stats                # :66, :92
 
 
-def trad_train_step(sd, imgs, pngs, cls_weights, num_classes, dice=True, focal=False, bf16_storage=False, relu_masks=None,
-                    record=None, pool_indices=None):
+def trad_train_step(sd, imgs, pngs, cls_weights, num_classes, dice=True, focal=False, bf16_storage=False):
     """One iteration of the TraditionalUnet_Train.py loop without the optimizer: returns (loss, logits, grads, stats)."""
     p = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and "running_" not in k else v.clone())
          for k, v in sd.items()}
-    logits, stats = trad_forward(p, imgs, training=True, bf16_storage=bf16_storage, relu_masks=relu_masks, record=record,
-                                 pool_indices=pool_indices)
+    logits, stats = trad_forward(p, imgs, training=True, bf16_storage=bf16_storage)
     loss = focal_loss(logits, pngs, cls_weights, num_classes) if focal else ce_loss(logits, pngs, cls_weights, num_classes)
     if dice:
         loss = loss + dice_loss(logits, one_hot(pngs, num_classes))
@@ -492,7 +486,7 @@ def make_resnet_unet_params(num_classes, seed=11, gain=1.0, dec_gain=0.5):
     return sd
 
 
-def _rn_bn(sd, stats, name, z, training, relu, res=None, bf16=False, pin=None, record=None):
+def _rn_bn(sd, stats, name, z, training, relu, res=None, bf16=False):
     y = F.batch_norm(z, stats[name + ".running_mean"], stats[name + ".running_var"], sd[name + ".weight"], sd[name + ".bias"],
                      training, 0.1, 1e-5)
     if training:
@@ -500,7 +494,7 @@ def _rn_bn(sd, stats, name, z, training, relu, res=None, bf16=False, pin=None, r
     if res is not None:
         y = y + res
     if relu:
-        y = _pinned_relu(y, name, pin, record)
+        y = _pinned_relu(y, name)
     return _r(y) if bf16 else y
 
 
@@ -513,33 +507,30 @@ def _rn_conv(sd, name, x, stride=1, padding=0, bias=None, bf16=False):
     return _r(z) if bf16 else z
 
 
-def resnet_unet_forward(sd, x, training=True, stats=None, bf16_storage=False, pin=None, record=None):
-    """Unet.forward with backbone='resnet50' (nets/unet.py:62-78, nets/resnet.py:151-176, 77-97).
-    pin / record (test aids): ReLU masks keyed by BatchNorm name (encoder) or conv weight name (decoder) and the stem max-pool's
-    arg-max indices under "pool": replayed / recorded, see _pinned_relu."""
+def resnet_unet_forward(sd, x, training=True, stats=None, bf16_storage=False):
+    """Unet.forward with backbone='resnet50' (nets/unet.py:62-78, nets/resnet.py:151-176, 77-97).  For oracle.branch the ReLU
+    sites are keyed by BatchNorm name (encoder) or conv weight name (decoder), the stem max-pool by "pool"."""
     b = bf16_storage
-    pr = dict(pin=pin, record=record)
     if stats is None:
         stats = {k: v.clone() for k, v in sd.items() if "running_" in k or "num_batches" in k}
     if b:
         x = _r(x)
     z = _rn_conv(sd, "resnet.conv1.weight", x, stride=2, padding=3, bf16=b)                         # resnet.py:166
-    feat1 = _rn_bn(sd, stats, "resnet.bn1", z, training, True, bf16=b, **pr)
-    x = _pinned_max_pool(feat1, "pool", pin, record, kernel=3, stride=2, ceil_mode=True)            # resnet.py:113,170
+    feat1 = _rn_bn(sd, stats, "resnet.bn1", z, training, True, bf16=b)
+    x = _pinned_max_pool(feat1, "pool", kernel=3, stride=2, ceil_mode=True)                         # resnet.py:113,170
     feats = [feat1]
     for li, (planes, blocks, stride) in enumerate(RESNET_LAYERS, start=1):
         for bi in range(blocks):
             p = f"resnet.layer{li}.{bi}"
             s = stride if bi == 0 else 1
-            out = _rn_bn(sd, stats, p + ".bn1", _rn_conv(sd, p + ".conv1.weight", x, bf16=b), training, True, bf16=b, **pr)
-            out = _rn_bn(sd, stats, p + ".bn2", _rn_conv(sd, p + ".conv2.weight", out, stride=s, padding=1, bf16=b), training, True, bf16=b,
-                         **pr)
+            out = _rn_bn(sd, stats, p + ".bn1", _rn_conv(sd, p + ".conv1.weight", x, bf16=b), training, True, bf16=b)
+            out = _rn_bn(sd, stats, p + ".bn2", _rn_conv(sd, p + ".conv2.weight", out, stride=s, padding=1, bf16=b), training, True, bf16=b)
             z3 = _rn_conv(sd, p + ".conv3.weight", out, bf16=b)
             idn = x
             if bi == 0:
                 idn = _rn_bn(sd, stats, p + ".downsample.1", _rn_conv(sd, p + ".downsample.0.weight", x, stride=s, bf16=b),
                              training, False, bf16=b)
-            x = _rn_bn(sd, stats, p + ".bn3", z3, training, True, res=idn, bf16=b, **pr)            # resnet.py:89-95
+            x = _rn_bn(sd, stats, p + ".bn3", z3, training, True, res=idn, bf16=b)            # resnet.py:89-95
         feats.append(x)
 
     def up_stage(name, skip, low):
@@ -551,7 +542,7 @@ def resnet_unet_forward(sd, x, training=True, stats=None, bf16_storage=False, pi
             y = _pinned_relu(
                 _rn_conv(sd, f"{name}.{cv}.weight", y, padding=1, bias=sd[f"{name}.{cv}.bias"], bf16=False) if not b else
                 F.conv2d(_r(y, fwd=False), sd[f"{name}.{cv}.weight"] + (sd[f"{name}.{cv}.weight"].to(torch.bfloat16).float() - sd[f"{name}.{cv}.weight"]).detach(),
-                         sd[f"{name}.{cv}.bias"], padding=1), f"{name}.{cv}.weight", pin, record)
+                         sd[f"{name}.{cv}.bias"], padding=1), f"{name}.{cv}.weight")
             if b:
                 y = _r(y)
         return y
@@ -567,17 +558,16 @@ def resnet_unet_forward(sd, x, training=True, stats=None, bf16_storage=False, pi
         if b:
             w = w + (w.to(torch.bfloat16).float() - w).detach()
             y = _r(y, fwd=False)
-        y = _pinned_relu(F.conv2d(y, w, sd[f"up_conv.{i}.bias"], padding=1), f"up_conv.{i}.weight", pin, record)
+        y = _pinned_relu(F.conv2d(y, w, sd[f"up_conv.{i}.bias"], padding=1), f"up_conv.{i}.weight")
         if b:
             y = _r(y)
     return F.conv2d(y, sd["final.weight"], sd["final.bias"]), stats
 
 
-def resnet_unet_train_step(sd, imgs, pngs, cls_weights, num_classes, dice=True, focal=False, bf16_storage=False, pin=None,
-                           record=None):
+def resnet_unet_train_step(sd, imgs, pngs, cls_weights, num_classes, dice=True, focal=False, bf16_storage=False):
     p = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and "running_" not in k else v.clone())
          for k, v in sd.items()}
-    logits, stats = resnet_unet_forward(p, imgs, training=True, bf16_storage=bf16_storage, pin=pin, record=record)
+    logits, stats = resnet_unet_forward(p, imgs, training=True, bf16_storage=bf16_storage)
     loss = focal_loss(logits, pngs, cls_weights, num_classes) if focal else ce_loss(logits, pngs, cls_weights, num_classes)
     if dice:
         loss = loss + dice_loss(logits, one_hot(pngs, num_classes))

@@ -13,21 +13,12 @@ import pytest
 import torch
 
 from oracle import unet_oracle as O
+from branch_util import compare_on_branch, rel
+from branch_util import global_rel as _global_rel
 
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-5
-
-
-def rel(a, b):
-    a, b = a.double().cpu(), b.double().cpu()
-    return ((a - b).norm() / (b.norm() + 1e-300)).item()
-
-
-def _global_rel(grads, ref):
-    num = sum((grads[k].double().cpu() - ref[k].double()).pow(2).sum().item() for k in ref)
-    den = sum(ref[k].double().pow(2).sum().item() for k in ref)
-    return (num / den) ** 0.5
 
 
 @pytest.fixture()
@@ -173,36 +164,15 @@ def test_traditional_unet_fp32_build_matches_reference(fp32_build, cuda_device, 
     assert abs(loss.item() - float(g["loss"])) <= TOL * abs(float(g["loss"]))
 
     # gradients against float64 on the same piecewise-linear branch
-    eng = model._engine_for(dev)
-    acts = eng.saved[0]
-    masks = {c.bn: (acts[c.name][..., :c.cout] > 0).permute(0, 3, 1, 2).cpu() for c in eng.convs}
-    pools = {}
-    for bi in range(1, len(eng.enc)):          # arg-max of every 2x2 window as the build saw it (first maximum, like ATen)
-        c = eng.enc[bi - 1][-1]
-        pools[f"pool{bi}"] = torch.nn.functional.max_pool2d(acts[c.name][..., :c.cout].permute(0, 3, 1, 2).cpu(), 2, return_indices=True)[1]
-    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
-    l64, z64, g64, _ = O.trad_train_step(sd64, imgs.double(), pngs, weights.double(), C, dice=dice, focal=focal, relu_masks=masks,
-                                        pool_indices=pools)
-    own_masks = {}
-    _, _, g64_own, _ = O.trad_train_step(sd64, imgs.double(), pngs, weights.double(), C, dice=dice, focal=focal, record=own_masks)
-    assert rel(outputs, z64) <= TOL and abs(loss.item() - l64.item()) <= TOL * abs(l64.item())
     grads = {k: p.grad for k, p in model.named_parameters()}
+    pre_bn_bias = lambda k: k.endswith(".double_conv.0.bias") or k.endswith(".double_conv.3.bias")
     # conv biases in front of BatchNorm have an exactly-zero gradient (the engine writes 0, autograd leaves ~1e-8 residue)
-    live = [k for k, v in g64.items() if not (k.endswith(".bias") and v.abs().max().item() < 1e-6)]
-    ours = _global_rel({k: grads[k] for k in live}, {k: g64[k] for k in live})
-    worst = max(rel(grads[k], g64[k]) for k in live)
-    ref32 = _global_rel({k: g32[k] for k in live}, {k: g64_own[k] for k in live})      # the fp32 reference against float64
-    print(f"traditional {tag}: build vs float64 {ours:.2e} (worst tensor {worst:.2e}); fp32 reference vs float64 {ref32:.2e}")
-    assert ours <= TOL and worst <= 5 * TOL
-    assert all(grads[k].abs().max().item() == 0.0 for k in g64 if k not in live)
-    # the build and float64 agree about (nearly) every ReLU sign: at most a handful of ~0 pre-activations differ
-    flips = sum(int((own_masks[k] != masks[k]).sum()) for k in masks)
-    total = sum(m.numel() for m in masks.values())
-    # a window whose float64 winner was ReLU-clamped to 0 is a tie at 0 with no gradient: only windows with a positive maximum count
-    pflips = sum(int(((own_masks[k] != pools[k]) & (torch.nn.functional.max_pool2d(
-        acts[eng.enc[int(k[4:]) - 1][-1].name][..., :eng.enc[int(k[4:]) - 1][-1].cout].permute(0, 3, 1, 2).cpu(), 2) > 0)).sum()) for k in pools)
-    print(f"traditional {tag}: {flips} of {total} ReLU signs and {pflips} of {sum(v.numel() for v in pools.values())} max-pool winners differ from float64")
-    assert flips <= 8 and pflips <= 8
+    assert all(grads[k].abs().max().item() == 0.0 for k in grads if pre_bn_bias(k))
+    d = compare_on_branch("traditional " + tag, lambda p, x, wts: O.trad_train_step(p, x, pngs, wts, C, dice=dice, focal=focal), sd, imgs,
+                          weights, grads, model._engine_for(dev), skip=pre_bn_bias)
+    assert rel(outputs, d["z64"]) <= TOL and abs(loss.item() - d["l64"].item()) <= TOL * abs(d["l64"].item())
+    assert d["ours"] <= TOL and d["worst"] <= 5 * TOL
+    assert d["relu_flips"] <= 8 and d["pool_flips"] <= 8
 
     # eval mode: BatchNorm folded into the conv epilogue (b2u_bn_fold + b2u_conv_fprop_scaled)
     model.eval()
@@ -212,57 +182,6 @@ def test_traditional_unet_fp32_build_matches_reference(fp32_build, cuda_device, 
     with torch.no_grad():
         ev_ref, _ = O.trad_forward(sd_after, imgs, training=False)
     assert rel(ev, ev_ref) <= TOL
-
-
-def _graph_branch(eng, shapes=None):
-    """ReLU masks and max-pool winners of the forward the GraphEngine just ran, keyed like oracle.branch: BatchNorm name for
-    conv -> BN -> ReLU sites, conv weight name for conv -> ReLU sites, "<prefix>.out" for residual joins, the pool tensor's name
-    for the max-pools.  shapes: {key: oracle tensor} trims the engine's zero-padded channels to the real ones."""
-    import torch.nn.functional as F
-    T = eng.saved[0]
-    pin = {}
-
-    def nchw(t):
-        return t.permute(0, 3, 1, 2).cpu()
-    for ins in eng.program:
-        if ins["op"] == "bn" and ins.get("relu", True):
-            pin[ins["bn"]] = nchw(T[ins["out"]].data[..., :ins["c"]] > 0)
-        elif ins["op"] == "conv" and ins.get("relu"):
-            pin[ins["w"]] = nchw(T[ins["out"]].data[..., :ins["cout"]] > 0)
-        elif ins["op"] == "addrelu":
-            pin[ins["out"]] = nchw(T[ins["out"]].data > 0)
-        elif ins["op"] == "pool3":
-            pin[ins["out"]] = F.max_pool2d(nchw(T[ins["x"]].data), 3, 2, ceil_mode=True, return_indices=True)[1]
-        elif ins["op"] == "pool2":
-            pin[ins["out"]] = F.max_pool2d(nchw(T[ins["x"]].data), 2, 2, return_indices=True)[1]
-    if shapes is not None:
-        pin = {k: v[:, :shapes[k].shape[1]].contiguous() for k, v in pin.items()}
-    return pin
-
-
-def _compare_on_branch(tag, step, sd, imgs, weights, model, eng, outputs, loss, skip=lambda k: False, pinned_bar=True):
-    """step(sd, imgs, weights) -> (loss, logits, grads, stats) of the oracle.  Runs it in float64 on its own branch (records the
-    site shapes and its own decisions), then in float64 and in fp32 on the branch the build took; returns the distances."""
-    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
-    own = {}
-    with O.branch(record=own):
-        step(sd64, imgs.double(), weights.double())
-    pin = _graph_branch(eng, shapes=own)
-    assert sorted(pin) == sorted(own), (sorted(set(pin) ^ set(own)))
-    with O.branch(pin=pin):
-        l64, z64, g64, _ = step(sd64, imgs.double(), weights.double())
-        _, _, g32p, _ = step(sd, imgs, weights)
-    assert rel(outputs, z64) <= TOL and abs(loss.item() - l64.item()) <= TOL * abs(l64.item())
-    grads = {k: p.grad for k, p in model.named_parameters()}
-    live = [k for k in g64 if not skip(k)]
-    ours = _global_rel({k: grads[k] for k in live}, {k: g64[k] for k in live})
-    ref32 = _global_rel({k: g32p[k] for k in live}, {k: g64[k] for k in live})
-    worst, worst32 = max(rel(grads[k], g64[k]) for k in live), max(rel(g32p[k], g64[k]) for k in live)
-    flips = sum(int((own[k] != pin[k]).sum()) for k in pin if own[k].dtype == torch.bool)
-    pflips = sum(int((own[k] != pin[k]).sum()) for k in pin if own[k].dtype != torch.bool)
-    print(f"{tag}: build vs float64 {ours:.2e} (worst tensor {worst:.2e}); torch fp32 on the same branch vs float64 {ref32:.2e} "
-          f"(worst {worst32:.2e}); {flips} ReLU signs and {pflips} max-pool winners differ from float64's own branch")
-    return ours, worst, ref32, worst32, flips, pflips
 
 
 def test_resnet50_unet_fp32_build_matches_reference(fp32_build, cuda_device, golden_dir):
@@ -293,14 +212,15 @@ def test_resnet50_unet_fp32_build_matches_reference(fp32_build, cuda_device, gol
         if not name.endswith("num_batches_tracked"):
             assert rel(b, s32[name]) <= (1e-4 if "layer4" in name else 2 * TOL), name
 
-    ours, worst, ref32, worst32, flips, _ = _compare_on_branch(
-        "resnet50", lambda p, x, wts: O.resnet_unet_train_step(p, x, pngs, wts, C, dice=True), sd, imgs, weights, model,
-        model._engine_for(dev), outputs, loss)
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    d = compare_on_branch("resnet50", lambda p, x, wts: O.resnet_unet_train_step(p, x, pngs, wts, C, dice=True), sd, imgs, weights, grads,
+                          model._engine_for(dev))
+    assert rel(outputs, d["z64"]) <= TOL and abs(loss.item() - d["l64"].item()) <= TOL * abs(d["l64"].item())
     # 53 BatchNorms deep, with 8 samples per channel in layer4, fp32 itself does not reach 1e-5 on the encoder's affine
     # parameters (measured: torch fp32 4.0e-5 / worst tensor 4.8e-4, this build 4.3e-5 / 5.1e-4, same tensors): the bar is 1e-5
     # or 1.5x torch's own fp32 distance from float64 on this branch, whichever is larger
-    assert ours <= max(TOL, 1.5 * ref32) and worst <= max(5 * TOL, 1.5 * worst32)
-    assert flips <= 32
+    assert d["ours"] <= max(TOL, 1.5 * d["ref32"]) and d["worst"] <= max(5 * TOL, 1.5 * d["worst32"])
+    assert d["relu_flips"] <= 32
 
 
 ULU_CASES = [("ultralight", "UltraLightweightUnet", "nc21_cedice"), ("ultralight_large", "UltraLightweightUnet_large", "nc4_focaldice"),
@@ -336,10 +256,10 @@ def test_ultralight_unet_fp32_build_matches_reference(fp32_build, cuda_device, g
     def step(p, x, wts):
         return O.ulu_train_step(p, x, pngs, wts, C, variant, dice=bool(dice), focal=bool(focal), drop_mask=mask)
     zero_bias = lambda k: k.endswith(".conv.0.bias") or k.endswith("wise.bias")       # biases in front of a BatchNorm: gradient 0
-    ours, worst, ref32, worst32, flips, pflips = _compare_on_branch(variant, step, sd, imgs, weights, model, eng, outputs, loss,
-                                                                    skip=zero_bias)
-    assert ours <= max(TOL, 1.5 * ref32) and worst <= max(5 * TOL, 1.5 * worst32)
-    assert flips <= 32 and pflips <= 32
+    d = compare_on_branch(variant, step, sd, imgs, weights, {k: p.grad for k, p in model.named_parameters()}, eng, skip=zero_bias)
+    assert rel(outputs, d["z64"]) <= TOL and abs(loss.item() - d["l64"].item()) <= TOL * abs(d["l64"].item())
+    assert d["ours"] <= max(TOL, 1.5 * d["ref32"]) and d["worst"] <= max(5 * TOL, 1.5 * d["worst32"])
+    assert d["relu_flips"] <= 32 and d["pool_flips"] <= 32
 
 
 @pytest.mark.parametrize("tag", ["nc4_focaldice", "nc21_cedice"])
@@ -373,10 +293,11 @@ def test_lightweight_unet_fp32_build_matches_reference(fp32_build, cuda_device, 
     def pre_bn_bias(k):
         base = k.rsplit(".", 1)[0]
         return k.endswith(".bias") and (base.endswith(".conv.0") or base.endswith(".conv1") or base.endswith(".conv2"))
-    ours, worst, ref32, worst32, flips, pflips = _compare_on_branch("lightweight " + tag, step, sd, imgs, weights, model, eng, outputs,
-                                                                    loss, skip=pre_bn_bias)
-    assert ours <= max(TOL, 1.5 * ref32) and worst <= max(5 * TOL, 1.5 * worst32)
-    assert flips <= 32 and pflips <= 32
+    d = compare_on_branch("lightweight " + tag, step, sd, imgs, weights, {k: p.grad for k, p in model.named_parameters()}, eng,
+                          skip=pre_bn_bias)
+    assert rel(outputs, d["z64"]) <= TOL and abs(loss.item() - d["l64"].item()) <= TOL * abs(d["l64"].item())
+    assert d["ours"] <= max(TOL, 1.5 * d["ref32"]) and d["worst"] <= max(5 * TOL, 1.5 * d["worst32"])
+    assert d["relu_flips"] <= 32 and d["pool_flips"] <= 32
 
 
 def test_fp32_build_refuses_what_it_does_not_cover(fp32_build, cuda_device):

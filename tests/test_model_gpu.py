@@ -780,3 +780,81 @@ def test_sync_batchnorm_two_gpus(cuda_device):
         # two bf16 runs with different summation orders: the tensors next to the output agree closely; through the 14
         # BatchNorm backward passes the difference is amplified like any other bf16 rounding
         assert near <= 2e-2 and gerr <= 0.15
+
+
+# ------------------------------------------------------------------------------------------------ bf16 on the pinned branch
+def _bn_family(b2u, golden_dir, family):
+    """(model, state dict, inputs, label map, class weights, oracle step, zero-gradient-bias predicate, dropout override)."""
+    import importlib
+    if family == "traditional":
+        C, n, h, w, seed = 4, 2, 64, 64, 3
+        sd = O.make_trad_params(C, seed=11)
+        imgs, pngs = O.make_inputs(n, C, h, w, seed=seed)
+        wts = torch.tensor([1, 15, 1.5, 2], dtype=torch.float32)
+        step = lambda p, x, ww: O.trad_train_step(p, x, pngs, ww, C, dice=True, focal=True)
+        return (b2u.TraditionalUnet(in_channels=3, num_classes=C), sd, imgs, pngs, wts, step, True, True,
+                lambda k: k.endswith(".double_conv.0.bias") or k.endswith(".double_conv.3.bias"), None)
+    if family == "resnet50":
+        C, n, h, w, seed = 21, 2, 64, 64, 7
+        sd = O.make_resnet_unet_params(C, seed=11)
+        imgs, pngs = O.make_inputs(n, C, h, w, seed=seed)
+        wts = torch.ones(C)
+        step = lambda p, x, ww: O.resnet_unet_train_step(p, x, pngs, ww, C, dice=True)
+        return b2u.Unet(num_classes=C, backbone="resnet50"), sd, imgs, pngs, wts, step, True, False, lambda k: False, None
+    if family == "lightweight":
+        g = np.load(os.path.join(golden_dir, "lightweight_nc21_cedice.npz"))
+        C, n, h, w, seed, dice, focal = [int(v) for v in g["meta"]]
+        sd = O.make_lw_params(C, seed=11)
+        imgs, pngs = O.make_inputs(n, C, h, w, seed=seed)
+        wts = torch.from_numpy(g["cls_w"])
+        masks = {k[5:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("drop:")}
+        step = lambda p, x, ww: O.lw_train_step(p, x, pngs, ww, C, dice=bool(dice), focal=bool(focal), drop_masks=masks)
+
+        def pre_bn_bias(k):
+            base = k.rsplit(".", 1)[0]
+            return k.endswith(".bias") and (base.endswith(".conv.0") or base.endswith(".conv1") or base.endswith(".conv2"))
+        return b2u.LightweightUnet(num_classes=C), sd, imgs, pngs, wts, step, bool(dice), bool(focal), pre_bn_bias, masks
+    variant, cls, tag = {"ultralight": ("ultralight", "UltraLightweightUnet", "nc21_cedice"),
+                         "ultralight_large": ("ultralight_large", "UltraLightweightUnet_large", "nc4_focaldice"),
+                         "ultralight_large_optimized": ("ultralight_large_optimized", "UltraLightweightUnet_large_optimized", "nc21_cedice")}[family]
+    g = np.load(os.path.join(golden_dir, f"{variant}_{tag}.npz"))
+    C, n, h, w, seed, dice, focal = [int(v) for v in g["meta"]]
+    sd = O.make_ulu_params(C, variant, seed=11)
+    imgs, pngs = O.make_inputs(n, C, h, w, seed=seed)
+    wts = torch.from_numpy(g["cls_w"])
+    mask = torch.from_numpy(g["drop_mask"]) if "drop_mask" in g.files else None
+    step = lambda p, x, ww: O.ulu_train_step(p, x, pngs, ww, C, variant, dice=bool(dice), focal=bool(focal), drop_mask=mask)
+    Net = getattr(importlib.import_module(f"unet_pytorch_b200.nets.{cls}"), cls)
+    return (Net(num_classes=C), sd, imgs, pngs, wts, step, bool(dice), bool(focal),
+            lambda k: k.endswith(".conv.0.bias") or k.endswith("wise.bias"), mask)
+
+
+@pytest.mark.parametrize("family", ["traditional", "resnet50", "lightweight", "ultralight", "ultralight_large", "ultralight_large_optimized"])
+def test_batchnorm_families_bf16_on_pinned_branch(b2u, cuda_device, golden_dir, family):
+    """The product (bf16) path of every BatchNorm family against the float64 oracle evaluated on the branch the CUDA run took
+    (its ReLU masks and max-pool winners, tests/branch_util.py).  Against the fp32 reference on ITS branch these nets' bf16
+    gradients differ by 9-16 % (tests above); this test separates the two causes -- sign/winner flips of ~0 pre-activations,
+    which bf16 storage makes by the thousand (0.3-2 % of all sites), and rounding proper -- by removing the first.  Measured
+    (profiles/r1_fp32_validation.txt): 2.2e-2 ... 7.7e-2 on the branch, i.e. flips account for one half to three quarters of the
+    9-16 %, and what remains is bf16 storage rounding amplified by the BatchNorm chain (the oracle's bf16-storage model shows
+    the same 3.4e-2 for TraditionalUnet on its own pinned branch); the fp32 validation build on the same fixtures is at
+    1.5e-6 ... 4e-5 (tests/test_fp32_validation_gpu.py), so the engines' logic is not part of it."""
+    from branch_util import compare_on_branch
+    dev = cuda_device
+    model, sd, imgs, pngs, wts, step, dice, focal, zero_bias, drop = _bn_family(b2u, golden_dir, family)
+    C = wts.numel()
+    model.load_state_dict(sd)
+    model = model.train().to(dev)
+    eng = model._engine_for(dev)
+    if drop is not None:
+        eng.dropout_override = drop
+    outputs = model(imgs.to(dev))
+    loss = (b2u.Focal_Loss if focal else b2u.CE_Loss)(outputs, pngs.to(dev), wts.to(dev), num_classes=C)
+    if dice:
+        loss = loss + b2u.Dice_loss(outputs, O.one_hot(pngs, C).to(dev))
+    loss.backward()
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    d = compare_on_branch(family + " bf16", step, sd, imgs, wts, grads, eng, skip=zero_bias)
+    zrel = rel(outputs, d["z64"])
+    print(f"{family} bf16: logits vs float64 on the branch {zrel:.2e}, loss {loss.item():.6f} vs {d['l64'].item():.6f}")
+    assert zrel <= 8e-2 and d["ours"] <= 1.2e-1        # ~1.5x the measured values: a regression guard, not a precision claim
