@@ -1,5 +1,5 @@
 """Per-tensor gradient distances of the fp32 validation build against the float64 oracle on the build's own ReLU branch
-(development aid for tests/test_fp32_validation_gpu.py; imports the oracle, so it lives with the test tooling)."""
+(development aid for test_fp32_validation_gpu.py; test tooling: it imports the oracle)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -34,9 +34,12 @@ for bi in range(1, len(eng.enc)):
     c = eng.enc[bi - 1][-1]
     pools[f"pool{bi}"] = torch.nn.functional.max_pool2d(acts[c.name][..., :c.cout].permute(0, 3, 1, 2).cpu(), 2, return_indices=True)[1]
 sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
-l64, z64, g64, _ = O.trad_train_step(sd64, imgs.double(), pngs, weights.double(), C, dice=dice, focal=focal, relu_masks=masks, pool_indices=pools)
+pin = dict(masks); pin.update(pools)
+with O.branch(pin=pin):
+    l64, z64, g64, _ = O.trad_train_step(sd64, imgs.double(), pngs, weights.double(), C, dice=dice, focal=focal)
 own = {}
-_, _, g64o, _ = O.trad_train_step(sd64, imgs.double(), pngs, weights.double(), C, dice=dice, focal=focal, record=own)
+with O.branch(record=own):
+    _, _, g64o, _ = O.trad_train_step(sd64, imgs.double(), pngs, weights.double(), C, dice=dice, focal=focal)
 print("logits vs f64", rel(out, z64), "flips", {k: int((own[k] != masks[k]).sum()) for k in masks if int((own[k] != masks[k]).sum())},
       "pool flips", {k: int((own[k] != pools[k]).sum()) for k in pools})
 # torch on the GPU in fp32 (cuDNN, TF32 off) as a third opinion
