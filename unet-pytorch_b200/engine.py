@@ -18,9 +18,10 @@ Gradients are written straight into caller-provided fp32 OIHW tensors (normally 
 `on_grads_ready(names)` is called after the launches that complete each layer's gradients so a data-parallel
 trainer can start that bucket's all-reduce while the remaining dgrad/wgrad kernels still run.
 """
-import struct
-
+import contextlib
 import functools
+import os
+import struct
 
 import torch
 
@@ -142,6 +143,15 @@ class UNetEngine:
         # db from the wgrad kernel's bias warps (3x3 layers) instead of a separate pass over dz: an A/B on one box
         # (scripts/ab_fuse_bias.py: 23.2-23.9 vs 23.4-23.5 ms/step) shows no gain, so the separate pass stays the default
         self.fuse_bias_grad = False
+        # Weight/bias gradients on a second stream (plain conv+ReLU nets): wgrad_L depends only on dz_L and the saved
+        # activation, not on the dgrad chain, so its launches are queued on a side stream behind an event and the
+        # HBM-bound glue of the main chain (pool / upsample adjoints, bias column sums) shares the SMs with tensor-core-bound
+        # kernels of the other stream instead of running alone.  Measured A/B on one B200 (bench.py, 30 steps, twice each):
+        # 22.72-22.80 ms/step with it, 22.95-22.97 without (+0.9 %): the GPU is power-capped, the extra concurrency costs
+        # 25-45 MHz of SM clock, and per-kernel CUDA-event times stop being the kernels' own durations (the roofline record
+        # of bench.py needs them), so it is OFF by default; B2U_WGRAD_STREAM=1 turns it on
+        self.wgrad_stream = os.environ.get("B2U_WGRAD_STREAM", "0") == "1"
+        self._side = None
         self._pack_key = self._pack_versions = self._pack_table = None
         self._pack_total = 0
         self._bufs = {}
@@ -398,6 +408,30 @@ class UNetEngine:
         Returns nothing; the input image gets no gradient (the reference never asks for one)."""
         if self.saved is None:
             raise RuntimeError("backward() without a saved forward()")
+        side = None
+        if self.wgrad_stream and not self.bn and dlogits.is_cuda:
+            if self._side is None or self._side.device != dlogits.device:
+                self._side = torch.cuda.Stream(device=dlogits.device)
+            side = self._side
+            # size the shared workspaces before the side stream starts using them (a reallocation mid-backward would hand
+            # the old block back to the allocator while a kernel of the other stream may still read it)
+            A, _, (N, H, W) = self.saved
+            need = 0
+            for c in self.convs:
+                t = A[c.name]
+                need = max(need, ops.lib().b2u_conv_wgrad_workspace(t.shape[0], t.shape[1], t.shape[2],
+                                                                     64 if c.first else c.c0_p + c.c1_p, c.cout_p, 1 if c.first else 9))
+            need = max(need, ops.lib().b2u_conv_wgrad_workspace(N, H, W, 64, 64, 1))
+            self._workspace("wgrad", need)
+            self._workspace("bias", ops.lib().b2u_bias_grad_workspace(max(c.cout_p for c in self.convs)))
+            side.wait_stream(torch.cuda.current_stream())
+        try:
+            self._backward(dlogits, params, grads, trainable, on_grads_ready, side)
+        finally:
+            if side is not None:
+                torch.cuda.current_stream().wait_stream(side)      # optimizer / next forward see every gradient
+
+    def _backward(self, dlogits, params, grads, trainable, on_grads_ready, side):
         A, feats, (N, H, W) = self.saved
         if trainable is None:
             trainable = set(grads.keys())
@@ -418,6 +452,16 @@ class UNetEngine:
         def ready(*names):
             if on_grads_ready is not None:
                 on_grads_ready([n for n in names if n in grads])
+
+        def grad_stream():
+            """Context for the launches that produce parameter gradients: the side stream, ordered after everything queued on
+            the main stream so far (the dz they read), or a no-op."""
+            if side is None:
+                return contextlib.nullcontext()
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            side.wait_event(ev)
+            return torch.cuda.stream(side)
 
         def has(n):
             return n in trainable and n in grads
@@ -441,6 +485,11 @@ class UNetEngine:
                 ready(wn, bnn)
             if not want[c.name]:
                 return dz
+            with grad_stream():
+                param_grads(c, x0, dz, x1)
+            return dz
+
+        def param_grads(c, x0, dz, x1):
             wn, bn_ = c.name + ".weight", c.name + ".bias"
             want_w, want_b = has(wn), has(bn_)
             fuse_b = (want_w and want_b and not c.padded and not c.bn and not c.first
@@ -478,7 +527,6 @@ class UNetEngine:
                     ops.bias_grad(dz, db=tmpb, ws=self._workspace("bias", ops.lib().b2u_bias_grad_workspace(c.cout_p)))
                     grads[bn_].copy_(tmpb[:c.cout])
             ready(wn, bn_)
-            return dz
 
         # ---- head
         hn = self.head_name
@@ -498,11 +546,12 @@ class UNetEngine:
                 dw64 = self._buf("head:dw", (64, 64, 1, 1), torch.float32)
                 db64 = self._buf("head:db", (64,), torch.float32)
                 need = ops.lib().b2u_conv_wgrad_workspace(dl.shape[0], dl.shape[1], dl.shape[2], 64, 64, 1)
-                ops.conv_wgrad(last, dl, taps=1, dw=dw64, db=db64, ws=self._workspace("wgrad", need))
-                if fw:      # rows [0,32) came from the hi half of dlogits, rows [32,64) from the lo half
-                    torch.add(dw64[:C, :self.head_cin], dw64[32:32 + C, :self.head_cin], out=grads[hn + ".weight"])
-                if fb:
-                    torch.add(db64[:C], db64[32:32 + C], out=grads[hn + ".bias"])
+                with grad_stream():
+                    ops.conv_wgrad(last, dl, taps=1, dw=dw64, db=db64, ws=self._workspace("wgrad", need))
+                    if fw:      # rows [0,32) came from the hi half of dlogits, rows [32,64) from the lo half
+                        torch.add(dw64[:C, :self.head_cin], dw64[32:32 + C, :self.head_cin], out=grads[hn + ".weight"])
+                    if fb:
+                        torch.add(db64[:C], db64[32:32 + C], out=grads[hn + ".bias"])
         else:
             dl = dlogits.contiguous()
             if dl.dtype != torch.float32:
@@ -516,7 +565,8 @@ class UNetEngine:
                          ws=self._workspace("head", ops.lib().b2u_head_bwd_workspace()))
             if fw and self.head_cin != 64:
                 grads[hn + ".weight"].copy_(dwt[:, :self.head_cin])
-        ready(hn + ".weight", hn + ".bias")
+        with grad_stream():          # (orders the side stream after the head's launches, whichever stream ran them)
+            ready(hn + ".weight", hn + ".bias")
         if g is None:
             return
 
