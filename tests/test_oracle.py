@@ -262,3 +262,29 @@ def test_predictor_tail_matches_reference(golden_dir):
     assert agree[confident].all() and agree.mean() >= 0.9999
     top2 = np.sort(pr, axis=-1)[..., -2:]
     assert np.abs((top2[..., 1] - top2[..., 0]) - g["margin"].astype(np.float32)).max() <= 2e-3      # fp16-stored margins
+
+
+def test_branch_record_and_replay():
+    """oracle.branch (test aid of the fp32 validation tests): replaying a run's own recorded ReLU masks / max-pool winners
+    reproduces that run exactly, and on one pinned branch torch's fp32 agrees with float64 far better than two free runs do
+    whenever they disagree about a decision."""
+    C = 4
+    sd = O.make_trad_params(C, seed=11)
+    imgs, pngs = O.make_inputs(1, C, 32, 32, seed=3)
+    w = torch.ones(C)
+    rec = {}
+    with O.branch(record=rec):
+        l0, z0, g0, _ = O.trad_train_step(sd, imgs, pngs, w, C, dice=True)
+    assert len(rec) == 14 + 3 and all(v.dtype in (torch.bool, torch.int64) for v in rec.values())
+    with O.branch(pin=rec):
+        l1, z1, g1, _ = O.trad_train_step(sd, imgs, pngs, w, C, dice=True)
+    assert torch.equal(z0, z1) and all(torch.equal(g0[k], g1[k]) for k in g0)
+    # outside the context nothing is pinned or recorded
+    assert O._BRANCH == {"pin": None, "record": None}
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    with O.branch(pin=rec):
+        _, z64, g64, _ = O.trad_train_step(sd64, imgs.double(), pngs, w.double(), C, dice=True)
+    num = sum((g0[k].double() - g64[k]).pow(2).sum().item() for k in g0 if g64[k].abs().max() > 1e-6)
+    den = sum(g64[k].pow(2).sum().item() for k in g0 if g64[k].abs().max() > 1e-6)
+    assert ((z0.double() - z64).norm() / z64.norm()).item() <= 1e-5
+    assert (num / den) ** 0.5 <= 2e-3          # torch's fp32 BatchNorm backward: ~1e-4 of float64 (DESIGN.md section 5.1)
