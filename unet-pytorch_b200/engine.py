@@ -147,11 +147,10 @@ class UNetEngine:
         # activation, not on the dgrad chain, so its launches are queued on a side stream behind an event and the
         # HBM-bound glue of the main chain (pool / upsample adjoints, bias column sums) shares the SMs with tensor-core-bound
         # kernels of the other stream instead of running alone.  Measured A/B on one B200 (bench.py, 30 steps, twice each):
-        # 22.72-22.80 ms/step with it, 22.95-22.97 without (+0.9 %): the GPU is power-capped, the extra concurrency costs
+        # 22.72-22.80 ms/step with it, 22.95-22.97 without (+0.9 %; a second box: 23.2 vs 23.1-23.4, i.e. noise): the GPU is power-capped, the extra concurrency costs
         # 25-45 MHz of SM clock, and per-kernel CUDA-event times stop being the kernels' own durations (the roofline record
         # of bench.py needs them), so it is OFF by default; B2U_WGRAD_STREAM=1 turns it on
-        self.wgrad_stream = os.environ.get("B2U_WGRAD_STREAM", "0") in ("1", "2")
-        self.side_bias_only = os.environ.get("B2U_WGRAD_STREAM", "0") == "2"     # experiment: only the HBM-bound bias sums overlap
+        self.wgrad_stream = os.environ.get("B2U_WGRAD_STREAM", "0") == "1"
         self._side = None
         self._pack_key = self._pack_versions = self._pack_table = None
         self._pack_total = 0
@@ -486,25 +485,16 @@ class UNetEngine:
                 ready(wn, bnn)
             if not want[c.name]:
                 return dz
-            if side is not None and self.side_bias_only:
-                param_grads(c, x0, dz, x1, part="w")
-                with grad_stream():
-                    param_grads(c, x0, dz, x1, part="b")
-            else:
-                with grad_stream():
-                    param_grads(c, x0, dz, x1)
+            with grad_stream():
+                param_grads(c, x0, dz, x1)
             return dz
 
-        def param_grads(c, x0, dz, x1, part="wb"):
+        def param_grads(c, x0, dz, x1):
             wn, bn_ = c.name + ".weight", c.name + ".bias"
             want_w, want_b = has(wn), has(bn_)
             fuse_b = (want_w and want_b and not c.padded and not c.bn and not c.first
                       and (self.fuse_bias_grad or c.cout_p == 64))     # Cout = 64: db is free in the swapped-role wgrad kernel
             taps = 1 if c.first else 9
-            if part == "w":
-                want_b = False
-            elif part == "b":
-                want_w = False
             if want_w:
                 ctot_p = 64 if c.first else c.c0_p + c.c1_p
                 need = ops.lib().b2u_conv_wgrad_workspace(dz.shape[0], dz.shape[1], dz.shape[2], ctot_p, c.cout_p, taps)
@@ -536,8 +526,7 @@ class UNetEngine:
                     tmpb = self._buf("dbias:" + c.name, (c.cout_p,), torch.float32)
                     ops.bias_grad(dz, db=tmpb, ws=self._workspace("bias", ops.lib().b2u_bias_grad_workspace(c.cout_p)))
                     grads[bn_].copy_(tmpb[:c.cout])
-            if part != "w":
-                ready(wn, bn_)
+            ready(wn, bn_)
 
         # ---- head
         hn = self.head_name
