@@ -64,7 +64,8 @@ int b2u_u8_to_i64(const unsigned char* x, long long* y, long long n, void* strea
 /* y = [relu](conv(cat(x0, x1), w) + bias).  Replaces nn.Conv2d(k=3,p=1 | k=1)+ReLU (nets/vgg.py:53-57,
  * nets/unet.py:11-12,18-21) and, with x1 != NULL, torch.cat([skip, up], 1) + conv (nets/unet.py:17-18).
  * taps = 9 (3x3, pad 1) or 1.  C0, C1, Cout multiples of 64.  bn_override: 0 = choose the tiling; bits 0..15 force the
- * N tile (64/128/192/256), bit 16 forces one 8x16-pixel M tile per CTA step (tests exercise every variant). */
+ * N tile (64/128/192/256), bit 16 forces one 8x16-pixel M tile per CTA step, bit 17 caps the stack at two M tiles (the
+ * unmasked N = 64 layers default to four) (tests exercise every variant). */
 int b2u_conv_fprop(const void* x0, int C0, const void* x1, int C1, const void* wf, const float* bias, void* y, int N,
                    int H, int W, int Cout, int taps, int relu, int bn_override, void* stream);
 /* b2u_conv_fprop that also emits the BatchNorm statistics of its output (conv -> nn.BatchNorm2d chains,

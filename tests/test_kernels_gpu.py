@@ -32,7 +32,8 @@ CONV_CASES = [
     (1, 8, 16, 64, 0, 64, 9, True),        # exactly one tile
     (2, 24, 40, 64, 0, 64, 9, True),       # Cout = 64 with ragged tiles in both directions (swapped-role wgrad)
     (3, 5, 7, 128, 64, 64, 9, False),      # Cout = 64, image smaller than a tile, two sources, three cin blocks
-    (2, 32, 48, 64, 0, 64, 9, True),
+    (2, 32, 48, 64, 0, 64, 9, True),       # exactly one stack of four M tiles
+    (1, 72, 40, 64, 64, 64, 9, True),      # four-tile stacks with a ragged last stack (72 = 2 x 32 + 8) and two sources
     (2, 24, 40, 128, 0, 128, 9, True),     # ragged tiles in both directions
     (1, 16, 16, 256, 0, 256, 9, False),
     (1, 16, 16, 512, 0, 512, 9, True),
@@ -59,7 +60,8 @@ def test_conv_fprop_dgrad_wgrad(b2u, cuda_device, N, H, W, C0, C1, Cout, taps, r
     ref = F.conv2d(xr, wr, b, padding=k // 2)
     ref = ref.relu() if relu else ref
     # every tiling the launcher can pick: default, one M tile per CTA step (bit 16), each legal N tile
-    variants = [0, 1 << 16] + [bn for bn in (64, 128, 192, 256) if Cout % bn == 0] + [(1 << 16) | 64]
+    # bit 17: at most two stacked M tiles (the unmasked N = 64 layers default to four when H >= 32)
+    variants = [0, 1 << 16, 2 << 16] + [bn for bn in (64, 128, 192, 256) if Cout % bn == 0] + [(1 << 16) | 64, (2 << 16) | 64]
     for bn in variants:
         y = ops.conv_fprop(x0, wf, b.to(dev), Cout, taps=taps, relu=relu, x1=x1, bn=bn)
         assert rel(nchw(y), ref) <= 6e-3, f"tiling variant {bn:#x}"
@@ -592,7 +594,7 @@ def test_softmax_resize_argmax_kernel(b2u, cuda_device, C, H, W, crop, out):
         assert (got[n] == ref.argmax(-1)).mean() >= 0.999
 
 
-@pytest.mark.parametrize("N,H,W,C0,C1,Cout,taps", [(2, 24, 40, 64, 0, 64, 9), (1, 16, 16, 128, 0, 256, 9), (2, 32, 32, 64, 64, 128, 9),
+@pytest.mark.parametrize("N,H,W,C0,C1,Cout,taps", [(2, 24, 40, 64, 0, 64, 9), (2, 40, 40, 64, 0, 64, 9), (1, 16, 16, 128, 0, 256, 9), (2, 32, 32, 64, 64, 128, 9),
                                                     (2, 16, 48, 64, 0, 64, 1), (1, 8, 8, 256, 0, 512, 1), (3, 5, 7, 64, 0, 192, 1),
                                                     (1, 40, 24, 64, 0, 128, 1)])
 def test_conv_epilogue_batchnorm_statistics(b2u, cuda_device, N, H, W, C0, C1, Cout, taps):

@@ -22,6 +22,7 @@
 //   * Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps 2..5 =
 //     epilogue (tcgen05.ld -> bias/ReLU/mask -> bf16 -> swizzled smem -> TMA store).
 //   * Persistent: grid = min(tiles, #SM), static round-robin tile schedule.
+//   * M tiles stacked vertically per CTA step (MT): 1 (tiny images), 2, or 4 for the unmasked N = 64 layers.
 #include "b2u_internal.h"
 #include "b2u_ptx.cuh"
 
@@ -507,6 +508,7 @@ int conv_m_tiles(int N, int H, int W, int Cout, int taps, int bn_override) {
   int mt = 1;
   if (taps == 9) mt = (bn == 128 || bn == 64) && tall ? 2 : 1;
   else           mt = bn == 64 ? 2 : 1;
+  if (taps == 9 && bn == 64 && tall && !((bn_override >> 16) & 2) && H >= 4 * kHb) mt = 4;    // unmasked launches (fprop)
   return N * ((H + kHb * mt - 1) / (kHb * mt)) * ((W + kWb - 1) / kWb);
 }
 
@@ -544,6 +546,13 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st) {
       case 128: return tall ? launch_cfg<128, 9, 2, 3, 2, 2>(a, st) : launch_cfg<128, 9, 1, 3, 3, 2>(a, st);
       case 64:
         // masked (dgrad + ReLU) Cin-side-64 layers are HBM-bound: the mask rows go through the cp.async stream
+        // unmasked N = 64 tiles are bound by shared-memory operand traffic: four stacked M tiles per CTA step --
+        // the weights of a step serve 512 pixels and the A box carries 2 halo rows per 32 instead of per 16, two pipeline
+        // stages instead of three, all 512 TMEM columns -- measured 0.344 -> 0.309 ms (64->64) and 0.954 -> 0.879 ms
+        // (64+128->64) at 16x512x512, bit-identical results (scripts/tile_variants_bench.py).  The masked variant keeps two
+        // tiles: its cp.async mask stream does not fit next to the larger A stages and register prefetch is slower
+        // (0.443 vs 0.415 ms).  tile_flags bit 1 forces the two-tile kernel (tests).
+        if (tall && !(a.tile_flags & 2) && a.H >= 4 * kHb && !(a.flags & 2)) return launch_cfg<64, 9, 4, 3, 2, 2>(a, st);
         if (tall && (a.flags & 2)) return launch_cfg<64, 9, 2, 3, 3, 2, 2>(a, st);
         return tall ? launch_cfg<64, 9, 2, 3, 3, 3>(a, st) : launch_cfg<64, 9, 1, 3, 4, 4>(a, st);
     }
