@@ -408,9 +408,11 @@ __global__ void se_fc_bwd_weights_kernel(const float* __restrict__ dpre2, const 
   if (i < R && db1) { float t = 0.f; for (int n = 0; n < N; ++n) t += dpre1[static_cast<size_t>(n) * R + i]; db1[i] = t; }
 }
 
+#ifndef B2U_FP32_VALIDATION
 static inline dim3 rgrid(long long rows, int row_items, int block) {
   return dim3(static_cast<unsigned>(rows), static_cast<unsigned>((row_items + block - 1) / block), 1);
 }
+#endif
 
 }  // namespace b2u
 

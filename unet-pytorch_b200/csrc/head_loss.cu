@@ -21,7 +21,9 @@ namespace b2u {
   } while (0)
 
 constexpr int kMaxCls = 32;
+#ifndef B2U_FP32_VALIDATION
 constexpr int kHeadK = 64;
+#endif
 
 #ifndef B2U_FP32_VALIDATION   // the fp32 validation build (validation_fp32.cu) brings its own head / operand kernels
 // ------------------------------------------------------------------------------------------
