@@ -81,3 +81,22 @@ def test_fp32_validation_library_exports_its_subset(b2u):
     h.b2u_conv_fprop.restype = ctypes.c_int
     rc = h.b2u_conv_fprop(None, 60, None, 0, None, None, None, 1, 8, 8, 64, 9, 1, 0, None)
     assert rc == 1
+
+
+def test_validation_switch_routes_and_restores(b2u):
+    """ops.set_validation_fp32: the process-wide switch between the product library and the fp32 validation build; entry
+    points the validation build lacks raise instead of falling through to another precision."""
+    ops, _lib = b2u.ops, b2u._lib
+    try:
+        ops.set_validation_fp32(True)
+        assert _lib.validation_fp32() and ops.act_dtype() == torch.float32
+        v = _lib.lib()
+        assert v.b2u_validation_fp32() == 1 and v.b2u_version() >= 100
+        with pytest.raises(_lib.B2UError):
+            v.b2u_head_fwd_tc
+        with pytest.raises(_lib.B2UError):
+            v.b2u_bn_sums                   # SyncBatchNorm building blocks are product-only
+    finally:
+        ops.set_validation_fp32(False)
+    assert not _lib.validation_fp32() and ops.act_dtype() == torch.bfloat16
+    assert not hasattr(_lib.lib(), "b2u_validation_fp32")
