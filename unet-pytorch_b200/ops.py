@@ -11,19 +11,19 @@ from ._lib import check, lib, ptr, stream_ptr
 
 # dtype of every activation / gradient / packed-operand tensor ("void*" in include/b2u.h): bf16 on the product path, fp32
 # when the process runs the fp32 validation build (csrc/validation_fp32.cu)
-BF16 = torch.float32 if _lib.validation_fp32() else torch.bfloat16
+ACT = torch.float32 if _lib.validation_fp32() else torch.bfloat16
 
 
 def act_dtype():
-    return BF16
+    return ACT
 
 
 def set_validation_fp32(on):
     """Switches the process between the product library (bf16 NHWC tensors, tcgen05 kernels) and the fp32 validation build
     of the same ABI (BASELINE.json: rel-L2 <= 1e-5 against the fp32 reference).  Build engines / modules after the call."""
-    global BF16
+    global ACT
     _lib.set_validation_fp32(on)
-    BF16 = torch.float32 if on else torch.bfloat16
+    ACT = torch.float32 if on else torch.bfloat16
 
 
 def _req(t, dtype, name):
@@ -88,7 +88,7 @@ def _ws(nbytes, device):
 def im2col_first(x_nchw):
     _req(x_nchw, torch.float32, "x")
     N, C, H, W = x_nchw.shape
-    col = torch.empty((N, H, W, 64), dtype=BF16, device=x_nchw.device)
+    col = torch.empty((N, H, W, 64), dtype=ACT, device=x_nchw.device)
     check(lib().b2u_im2col_first(ptr(x_nchw), ptr(col), N, C, H, W, stream_ptr()))
     return col
 
@@ -99,9 +99,9 @@ def pack_weights(w, want_dgrad=True, wf=None, wd=None):
     Cout, Cin, kh, kw = w.shape
     taps = kh * kw
     if wf is None:
-        wf = torch.empty((Cout, taps * Cin), dtype=BF16, device=w.device)
+        wf = torch.empty((Cout, taps * Cin), dtype=ACT, device=w.device)
     if want_dgrad and wd is None:
-        wd = torch.empty((Cin, taps * Cout), dtype=BF16, device=w.device)
+        wd = torch.empty((Cin, taps * Cout), dtype=ACT, device=w.device)
     check(lib().b2u_pack_weights(ptr(w), ptr(wf), ptr(wd) if want_dgrad else None, Cout, Cin, taps, stream_ptr()))
     return wf, (wd if want_dgrad else None)
 
@@ -111,13 +111,13 @@ def pack_weights_first(w, wf=None):
     Cout, Cin, kh, kw = w.shape
     assert kh == 3 and kw == 3
     if wf is None:
-        wf = torch.empty((Cout, 64), dtype=BF16, device=w.device)
+        wf = torch.empty((Cout, 64), dtype=ACT, device=w.device)
     check(lib().b2u_pack_weights_first(ptr(w), ptr(wf), Cout, Cin, stream_ptr()))
     return wf
 
 
 def nhwc_to_nchw_f32(x):
-    _req(x, BF16, "x")
+    _req(x, ACT, "x")
     N, H, W, C = x.shape
     y = torch.empty((N, C, H, W), dtype=torch.float32, device=x.device)
     check(lib().b2u_nhwc_bf16_to_nchw_f32(ptr(x), ptr(y), N, C, H, W, stream_ptr()))
@@ -127,7 +127,7 @@ def nhwc_to_nchw_f32(x):
 def nchw_to_nhwc_bf16(x):
     _req(x, torch.float32, "x")
     N, C, H, W = x.shape
-    y = torch.empty((N, H, W, C), dtype=BF16, device=x.device)
+    y = torch.empty((N, H, W, C), dtype=ACT, device=x.device)
     check(lib().b2u_nchw_f32_to_nhwc_bf16(ptr(x), ptr(y), N, C, H, W, stream_ptr()))
     return y
 
@@ -154,7 +154,7 @@ def nchw_to_nhwc_bf16_padded(x, cpad, out=None):
     _req(x, torch.float32, "x")
     N, C, H, W = x.shape
     if out is None:
-        out = torch.empty((N, H, W, cpad), dtype=BF16, device=x.device)
+        out = torch.empty((N, H, W, cpad), dtype=ACT, device=x.device)
     check(lib().b2u_nchw_f32_to_nhwc_bf16_padded(ptr(x), ptr(out), N, C, H, W, cpad, stream_ptr()))
     return out
 
@@ -163,11 +163,11 @@ def nchw_to_nhwc_bf16_padded(x, cpad, out=None):
 def conv_fprop(x0, wf, bias, Cout, taps=9, relu=True, x1=None, out=None, bn=0, stats=None):
     """stats: optional fp32 buffer [>= conv_stat_rows(...)][2][Cout]; the conv then also writes the per-tile sums of z and
     z^2 of its output (BatchNorm statistics, consumed by bn_fwd_train(stats=...))."""
-    _req(x0, BF16, "x0"); _req(x1, BF16, "x1"); _req(wf, BF16, "wf"); _req(bias, torch.float32, "bias")
+    _req(x0, ACT, "x0"); _req(x1, ACT, "x1"); _req(wf, ACT, "wf"); _req(bias, torch.float32, "bias")
     N, H, W, C0 = x0.shape
     C1 = 0 if x1 is None else x1.shape[3]
     if out is None:
-        out = torch.empty((N, H, W, Cout), dtype=BF16, device=x0.device)
+        out = torch.empty((N, H, W, Cout), dtype=ACT, device=x0.device)
     with _timed(f"conv_igemm|fprop|{N}x{H}x{W}|{C0}+{C1}->{Cout}|t{taps}", 2.0 * N * H * W * Cout * (C0 + C1) * taps):
         if stats is None:
             check(lib().b2u_conv_fprop(ptr(x0), C0, ptr(x1), C1, ptr(wf), ptr(bias), ptr(out), N, H, W, Cout, taps,
@@ -181,11 +181,11 @@ def conv_fprop(x0, wf, bias, Cout, taps=9, relu=True, x1=None, out=None, bn=0, s
 
 def conv_fprop_scaled(x0, wf, scale, bias, Cout, taps=9, relu=True, x1=None, out=None, bn=0):
     """y = [relu](conv(x) * scale[c] + bias[c]): conv + eval-mode BatchNorm (+ReLU) in one kernel (scale/bias from bn_fold)."""
-    _req(x0, BF16, "x0"); _req(x1, BF16, "x1"); _req(wf, BF16, "wf"); _req(bias, torch.float32, "bias"); _req(scale, torch.float32, "scale")
+    _req(x0, ACT, "x0"); _req(x1, ACT, "x1"); _req(wf, ACT, "wf"); _req(bias, torch.float32, "bias"); _req(scale, torch.float32, "scale")
     N, H, W, C0 = x0.shape
     C1 = 0 if x1 is None else x1.shape[3]
     if out is None:
-        out = torch.empty((N, H, W, Cout), dtype=BF16, device=x0.device)
+        out = torch.empty((N, H, W, Cout), dtype=ACT, device=x0.device)
     check(lib().b2u_conv_fprop_scaled(ptr(x0), C0, ptr(x1), C1, ptr(wf), ptr(scale), ptr(bias), ptr(out), N, H, W, Cout, taps,
                                       1 if relu else 0, bn, stream_ptr()))
     return out
@@ -207,12 +207,12 @@ def conv_stat_rows(N, H, W, Cout, taps=9, bn=0):
 
 
 def conv_dgrad(dz, wd, C0, taps=9, C1=0, mask=None, out0=None, out1=None, bn=0):
-    _req(dz, BF16, "dz"); _req(wd, BF16, "wd"); _req(mask, BF16, "mask")
+    _req(dz, ACT, "dz"); _req(wd, ACT, "wd"); _req(mask, ACT, "mask")
     N, H, W, Cz = dz.shape
     if out0 is None:
-        out0 = torch.empty((N, H, W, C0), dtype=BF16, device=dz.device)
+        out0 = torch.empty((N, H, W, C0), dtype=ACT, device=dz.device)
     if C1 > 0 and out1 is None:
-        out1 = torch.empty((N, H, W, C1), dtype=BF16, device=dz.device)
+        out1 = torch.empty((N, H, W, C1), dtype=ACT, device=dz.device)
     with _timed(f"conv_igemm|dgrad|{N}x{H}x{W}|{Cz}->{C0}+{C1}|t{taps}", 2.0 * N * H * W * Cz * (C0 + C1) * taps):
         check(lib().b2u_conv_dgrad(ptr(dz), Cz, ptr(wd), ptr(out0), C0, ptr(out1) if C1 > 0 else None, C1, ptr(mask),
                                    N, H, W, taps, bn, stream_ptr()))
@@ -221,7 +221,7 @@ def conv_dgrad(dz, wd, C0, taps=9, C1=0, mask=None, out0=None, out1=None, bn=0):
 
 def conv_wgrad(x0, dz, taps=9, x1=None, first_cin=0, dw=None, ws=None, flags=0, db=None, want_db=False):
     """Returns dw, or (dw, db) when the bias gradient is requested (db tensor given or want_db)."""
-    _req(x0, BF16, "x0"); _req(x1, BF16, "x1"); _req(dz, BF16, "dz")
+    _req(x0, ACT, "x0"); _req(x1, ACT, "x1"); _req(dz, ACT, "dz")
     N, H, W, C0 = x0.shape
     C1 = 0 if x1 is None else x1.shape[3]
     Cout = dz.shape[3]
@@ -243,7 +243,7 @@ def conv_wgrad(x0, dz, taps=9, x1=None, first_cin=0, dw=None, ws=None, flags=0, 
 
 
 def bias_grad(dz, db=None, ws=None):
-    _req(dz, BF16, "dz")
+    _req(dz, ACT, "dz")
     C = dz.shape[-1]
     P = dz.numel() // C
     need = lib().b2u_bias_grad_workspace(C)
@@ -257,16 +257,16 @@ def bias_grad(dz, db=None, ws=None):
 
 # ---------------------------------------------------------------------------------------------- pool / upsample
 def maxpool2x2(x, out=None):
-    _req(x, BF16, "x")
+    _req(x, ACT, "x")
     N, H, W, C = x.shape
     if out is None:
-        out = torch.empty((N, H // 2, W // 2, C), dtype=BF16, device=x.device)
+        out = torch.empty((N, H // 2, W // 2, C), dtype=ACT, device=x.device)
     check(lib().b2u_maxpool2x2_fwd(ptr(x), ptr(out), N, H, W, C, stream_ptr()))
     return out
 
 
 def maxpool2x2_bwd(dpool, y, dskip=None, relu_mask=True, out=None):
-    _req(dpool, BF16, "dpool"); _req(y, BF16, "y"); _req(dskip, BF16, "dskip")
+    _req(dpool, ACT, "dpool"); _req(y, ACT, "y"); _req(dskip, ACT, "dskip")
     N, H, W, C = y.shape
     if out is None:
         out = torch.empty_like(y)
@@ -276,20 +276,20 @@ def maxpool2x2_bwd(dpool, y, dskip=None, relu_mask=True, out=None):
 
 
 def upsample2x(x, out=None):
-    _req(x, BF16, "x")
+    _req(x, ACT, "x")
     N, H, W, C = x.shape
     if out is None:
-        out = torch.empty((N, 2 * H, 2 * W, C), dtype=BF16, device=x.device)
+        out = torch.empty((N, 2 * H, 2 * W, C), dtype=ACT, device=x.device)
     check(lib().b2u_upsample2x_fwd(ptr(x), ptr(out), N, H, W, C, stream_ptr()))
     return out
 
 
 def upsample2x_bwd(dup, ylow=None, out=None):
-    _req(dup, BF16, "dup"); _req(ylow, BF16, "ylow")
+    _req(dup, ACT, "dup"); _req(ylow, ACT, "ylow")
     N, H2, W2, C = dup.shape
     H, W = H2 // 2, W2 // 2
     if out is None:
-        out = torch.empty((N, H, W, C), dtype=BF16, device=dup.device)
+        out = torch.empty((N, H, W, C), dtype=ACT, device=dup.device)
     check(lib().b2u_upsample2x_bwd(ptr(dup), ptr(ylow), ptr(out), N, H, W, C, stream_ptr()))
     return out
 
@@ -299,7 +299,7 @@ def bn_fwd_train(z, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0
                  residual=None, stats=None, stat_rows=0):
     """Returns (y, save_mean, save_invstd); running statistics are updated in place (torch semantics).
     stats/stat_rows: per-tile column sums written by conv_fprop(stats=...) -- skips the statistics pass over z."""
-    _req(z, BF16, "z")
+    _req(z, ACT, "z")
     C = z.shape[-1]
     P = z.numel() // C
     need = lib().b2u_bn_workspace(C)
@@ -325,7 +325,7 @@ def bn_fwd_train_sync(z, gamma, beta, running_mean, running_var, group, eps=1e-5
     """SyncBatchNorm forward (train.py:335-336): this rank's column sums, one all-reduce of 2C floats over `group`, apply
     with the global statistics.  Every rank is assumed to hold the same number of rows (DistributedSampler batches)."""
     import torch.distributed as dist
-    _req(z, BF16, "z")
+    _req(z, ACT, "z")
     C = z.shape[-1]
     P = z.numel() // C
     need = lib().b2u_bn_workspace(C)
@@ -348,7 +348,7 @@ def bn_fwd_train_sync(z, gamma, beta, running_mean, running_var, group, eps=1e-5
 def bn_bwd_sync(dy, y, z, gamma, mean, invstd, group, relu=True, out=None, dgamma=None, dbeta=None, ws=None, gout=None, beta=None):
     """SyncBatchNorm backward: local (sum g, sum g xhat) = this rank's (dbeta, dgamma), all-reduced only for dz."""
     import torch.distributed as dist
-    _req(dy, BF16, "dy"); _req(y, BF16, "y"); _req(z, BF16, "z")
+    _req(dy, ACT, "dy"); _req(y, ACT, "y"); _req(z, ACT, "z")
     if y is None and relu and beta is None:
         raise ValueError("bn_bwd_sync: y=None needs beta to recompute the ReLU mask")
     C = z.shape[-1]
@@ -375,7 +375,7 @@ def bn_bwd_sync(dy, y, z, gamma, mean, invstd, group, relu=True, out=None, dgamm
 
 
 def bn_fwd_eval(z, gamma, beta, running_mean, running_var, eps=1e-5, relu=True, out=None, ws=None, residual=None):
-    _req(z, BF16, "z")
+    _req(z, ACT, "z")
     C = z.shape[-1]
     P = z.numel() // C
     need = lib().b2u_bn_workspace(C)
@@ -391,7 +391,7 @@ def bn_fwd_eval(z, gamma, beta, running_mean, running_var, eps=1e-5, relu=True, 
 def bn_bwd(dy, y, z, gamma, mean, invstd, relu=True, out=None, dgamma=None, dbeta=None, ws=None, gout=None, beta=None):
     """Returns (dz, dgamma, dbeta); gout (optional tensor) receives the ReLU-masked dy (residual-branch gradient).
     y=None (allowed when no residual was added before the ReLU; needs beta) recomputes the ReLU mask from z."""
-    _req(dy, BF16, "dy"); _req(y, BF16, "y"); _req(z, BF16, "z")
+    _req(dy, ACT, "dy"); _req(y, ACT, "y"); _req(z, ACT, "z")
     if y is None and relu and beta is None:
         raise ValueError("bn_bwd: y=None needs beta to recompute the ReLU mask")
     C = z.shape[-1]
@@ -416,7 +416,7 @@ def im2col_stem(x_nchw, out=None):
     N, C, H, W = x_nchw.shape
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     if out is None:
-        out = torch.empty((N, Ho, Wo, 192), dtype=BF16, device=x_nchw.device)
+        out = torch.empty((N, Ho, Wo, 192), dtype=ACT, device=x_nchw.device)
     check(lib().b2u_im2col_stem(ptr(x_nchw), ptr(out), N, C, H, W, stream_ptr()))
     return out
 
@@ -425,14 +425,14 @@ def pack_weights_im2col(w, kpad, wf=None):
     _req(w, torch.float32, "weight")
     Cout, Cin, kh, kw = w.shape
     if wf is None:
-        wf = torch.empty((Cout, kpad), dtype=BF16, device=w.device)
+        wf = torch.empty((Cout, kpad), dtype=ACT, device=w.device)
     check(lib().b2u_pack_weights_im2col(ptr(w), ptr(wf), Cout, Cin, kh * kw, kpad, stream_ptr()))
     return wf
 
 
 def conv_wgrad_im2col(col, dz, cin, taps, dw=None, ws=None):
     """wgrad of a conv executed as a 1x1 GEMM over im2col rows; dw: [Cout, cin, k, k] with k*k = taps."""
-    _req(col, BF16, "col"); _req(dz, BF16, "dz")
+    _req(col, ACT, "col"); _req(dz, ACT, "dz")
     N, H, W, Kpad = col.shape
     Cout = dz.shape[3]
     need = lib().b2u_conv_wgrad_workspace(N, H, W, Kpad, Cout, 1)
@@ -448,35 +448,35 @@ def conv_wgrad_im2col(col, dz, cin, taps, dw=None, ws=None):
 
 
 def subsample2(x, out=None):
-    _req(x, BF16, "x")
+    _req(x, ACT, "x")
     N, H, W, C = x.shape
     if out is None:
-        out = torch.empty((N, (H + 1) // 2, (W + 1) // 2, C), dtype=BF16, device=x.device)
+        out = torch.empty((N, (H + 1) // 2, (W + 1) // 2, C), dtype=ACT, device=x.device)
     check(lib().b2u_subsample2(ptr(x), ptr(out), N, H, W, C, stream_ptr()))
     return out
 
 
 def zero_insert2(y, H, W, out=None):
-    _req(y, BF16, "y")
+    _req(y, ACT, "y")
     N, _, _, C = y.shape
     if out is None:
-        out = torch.empty((N, H, W, C), dtype=BF16, device=y.device)
+        out = torch.empty((N, H, W, C), dtype=ACT, device=y.device)
     check(lib().b2u_zero_insert2(ptr(y), ptr(out), N, H, W, C, stream_ptr()))
     return out
 
 
 def maxpool3x3s2(x, out=None):
-    _req(x, BF16, "x")
+    _req(x, ACT, "x")
     N, H, W, C = x.shape
     Ho, Wo = (H - 2) // 2 + 1, (W - 2) // 2 + 1
     if out is None:
-        out = torch.empty((N, Ho, Wo, C), dtype=BF16, device=x.device)
+        out = torch.empty((N, Ho, Wo, C), dtype=ACT, device=x.device)
     check(lib().b2u_maxpool3x3s2_fwd(ptr(x), ptr(out), N, H, W, C, stream_ptr()))
     return out
 
 
 def maxpool3x3s2_bwd(dy, x, out=None):
-    _req(dy, BF16, "dy"); _req(x, BF16, "x")
+    _req(dy, ACT, "dy"); _req(x, ACT, "x")
     N, H, W, C = x.shape
     if out is None:
         out = torch.empty_like(x)
@@ -485,7 +485,7 @@ def maxpool3x3s2_bwd(dy, x, out=None):
 
 
 def add_bf16(a, b, out=None):
-    _req(a, BF16, "a"); _req(b, BF16, "b")
+    _req(a, ACT, "a"); _req(b, ACT, "b")
     if out is None:
         out = torch.empty_like(a)
     check(lib().b2u_add_bf16(ptr(a), ptr(b), ptr(out), a.numel(), stream_ptr()))
@@ -494,7 +494,7 @@ def add_bf16(a, b, out=None):
 
 def add_relu(a, b, out=None):
     """relu(a + b), bf16 (the residual join of nets/LightWeightUnet.py:52-53)."""
-    _req(a, BF16, "a"); _req(b, BF16, "b")
+    _req(a, ACT, "a"); _req(b, ACT, "b")
     if out is None:
         out = torch.empty_like(a)
     check(lib().b2u_add_relu_bf16(ptr(a), ptr(b), ptr(out), a.numel(), stream_ptr()))
@@ -502,7 +502,7 @@ def add_relu(a, b, out=None):
 
 
 def relu_bwd(dy, y, out=None):
-    _req(dy, BF16, "dy"); _req(y, BF16, "y")
+    _req(dy, ACT, "dy"); _req(y, ACT, "y")
     if out is None:
         out = torch.empty_like(dy)
     check(lib().b2u_relu_bwd_bf16(ptr(dy), ptr(y), ptr(out), dy.numel(), stream_ptr()))
@@ -533,7 +533,7 @@ def resize_bilinear_bwd(dy, size_in, out=None):
 # ---------------------------------------------------------------------------------------------- depthwise / SE
 def dwconv3x3(x, w, bias=None, flip=False, out=None):
     """w: fp32 [C, 9] (or [C,1,3,3]); flip=True is the data gradient."""
-    _req(x, BF16, "x"); _req(w, torch.float32, "w")
+    _req(x, ACT, "x"); _req(w, torch.float32, "w")
     N, H, W, C = x.shape
     if out is None:
         out = torch.empty_like(x)
@@ -542,7 +542,7 @@ def dwconv3x3(x, w, bias=None, flip=False, out=None):
 
 
 def dwconv3x3_wgrad(x, dy, dw=None, db=None, ws=None):
-    _req(x, BF16, "x"); _req(dy, BF16, "dy")
+    _req(x, ACT, "x"); _req(dy, ACT, "dy")
     N, H, W, C = x.shape
     need = lib().b2u_dwconv3x3_wgrad_workspace(C)
     if ws is None or ws.numel() * ws.element_size() < need:
@@ -558,7 +558,7 @@ def dwconv3x3_wgrad(x, dy, dw=None, db=None, ws=None):
 
 def spatial_reduce(a, b=None, scale=1.0, out=None, ws=None):
     """[N, C] fp32: scale * sum over H*W of a (or a*b)."""
-    _req(a, BF16, "a"); _req(b, BF16, "b")
+    _req(a, ACT, "a"); _req(b, ACT, "b")
     N, H, W, C = a.shape
     need = lib().b2u_spatial_reduce_workspace_floats(N, C) * 4
     if ws is None or ws.numel() * ws.element_size() < need:
@@ -571,7 +571,7 @@ def spatial_reduce(a, b=None, scale=1.0, out=None, ws=None):
 
 
 def scale_nc(x, s, add=None, out=None):
-    _req(x, BF16, "x"); _req(s, torch.float32, "s"); _req(add, torch.float32, "add")
+    _req(x, ACT, "x"); _req(s, torch.float32, "s"); _req(add, torch.float32, "add")
     N, H, W, C = x.shape
     if out is None:
         out = torch.empty_like(x)
@@ -600,7 +600,7 @@ def se_fc_bwd(dscale, pooled, hidden, scale, w1, w2, C, dp_scale, dw1=None, db1=
 
 # ---------------------------------------------------------------------------------------------- head
 def head_fwd(x, w, b, out=None):
-    _req(x, BF16, "x"); _req(w, torch.float32, "w"); _req(b, torch.float32, "b")
+    _req(x, ACT, "x"); _req(w, torch.float32, "w"); _req(b, torch.float32, "b")
     N, H, W, Cin = x.shape
     ncls = w.shape[0]
     if out is None:
@@ -610,7 +610,7 @@ def head_fwd(x, w, b, out=None):
 
 
 def head_bwd(dlogits, x, w, need_dx=True, need_dw=True, relu_mask=True, dx=None, dw=None, db=None, ws=None):
-    _req(dlogits, torch.float32, "dlogits"); _req(x, BF16, "x"); _req(w, torch.float32, "w")
+    _req(dlogits, torch.float32, "dlogits"); _req(x, ACT, "x"); _req(w, torch.float32, "w")
     N, H, W, Cin = x.shape
     ncls = w.shape[0]
     need = lib().b2u_head_bwd_workspace()
@@ -652,7 +652,7 @@ def loss_bwd(logits, fin, gscale, target=None, onehot=None, cls_w=None, alpha=0.
     _req(logits, torch.float32, "logits"); _req(gscale, torch.float32, "gscale")
     N, C, H, W = logits.shape
     if out is None:
-        out = torch.empty((N, H, W, 64), dtype=BF16, device=logits.device) if nhwc64 else torch.empty_like(logits)
+        out = torch.empty((N, H, W, 64), dtype=ACT, device=logits.device) if nhwc64 else torch.empty_like(logits)
     check(lib().b2u_loss_bwd(ptr(logits), ptr(target), ptr(onehot), ptr(cls_w), ptr(fin), ptr(gscale), ptr(out),
                              1 if nhwc64 else 0, N, C, H, W, 0.0 if alpha is None else alpha, gamma, stream_ptr()))
     return out
@@ -662,7 +662,7 @@ def pack_head_dgrad(w, wd=None):
     _req(w, torch.float32, "final.weight")
     ncls = w.shape[0]
     if wd is None:
-        wd = torch.empty((64, 64), dtype=BF16, device=w.device)
+        wd = torch.empty((64, 64), dtype=ACT, device=w.device)
     check(lib().b2u_pack_head_dgrad(ptr(w), ptr(wd), ncls, stream_ptr()))
     return wd
 
@@ -671,14 +671,14 @@ def pack_head_fprop(w, wf=None):
     _req(w, torch.float32, "final.weight")
     ncls = w.shape[0]
     if wf is None:
-        wf = torch.empty((64, 64), dtype=BF16, device=w.device)
+        wf = torch.empty((64, 64), dtype=ACT, device=w.device)
     check(lib().b2u_pack_head_fprop(ptr(w), ptr(wf), ncls, stream_ptr()))
     return wf
 
 
 def head_fwd_tc(x, wf, b, ncls, out=None):
     """The 1x1 classifier on the tensor cores (wf from pack_head_fprop): fp32 NCHW logits."""
-    _req(x, BF16, "x"); _req(wf, BF16, "wf"); _req(b, torch.float32, "b")
+    _req(x, ACT, "x"); _req(wf, ACT, "wf"); _req(b, torch.float32, "b")
     N, H, W, Cin = x.shape
     if Cin != 64:
         raise ValueError("head_fwd_tc: the head input must have 64 (padded) channels")
