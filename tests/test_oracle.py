@@ -288,3 +288,31 @@ def test_branch_record_and_replay():
     den = sum(g64[k].pow(2).sum().item() for k in g0 if g64[k].abs().max() > 1e-6)
     assert ((z0.double() - z64).norm() / z64.norm()).item() <= 1e-5
     assert (num / den) ** 0.5 <= 2e-3          # torch's fp32 BatchNorm backward: ~1e-4 of float64
+
+
+@pytest.mark.parametrize("family", ["resnet50", "ultralight_large", "lightweight"])
+def test_branch_sites_of_the_graph_families(family):
+    """Every ReLU / max-pool site of the other BatchNorm families is keyed for oracle.branch, and replaying a run's own
+    decisions is the identity (the GPU tests replay the CUDA engine's decisions under the same keys)."""
+    C = 4
+    if family == "resnet50":
+        sd = O.make_resnet_unet_params(C, seed=11)
+        step = lambda: O.resnet_unet_train_step(sd, imgs, pngs, torch.ones(C), C, dice=True)
+        n_relu, n_pool = 1 + 16 * 3 + 8 + 2, 1          # stem, 16 bottlenecks x 3, 4 decoder stages x 2, up_conv x 2; stem pool
+    elif family == "ultralight_large":
+        sd = O.make_ulu_params(C, family, seed=11)
+        step = lambda: O.ulu_train_step(sd, imgs, pngs, torch.ones(C), C, family, dice=True)
+        n_relu, n_pool = 9 * 2, 4                        # 9 LightConvBlocks x 2 BatchNorm+ReLU; 4 pools
+    else:
+        sd = O.make_lw_params(C, seed=11)
+        step = lambda: O.lw_train_step(sd, imgs, pngs, torch.ones(C), C, dice=True)
+        n_relu, n_pool = 10 * 3, 5                       # 10 x (ConvBlock ReLU + ResidualBlock bn1 ReLU + join ReLU); 5 pools
+    imgs, pngs = O.make_inputs(1, C, 64, 64, seed=2)
+    rec = {}
+    with O.branch(record=rec):
+        l0, z0, g0, _ = step()
+    assert sum(v.dtype == torch.bool for v in rec.values()) == n_relu
+    assert sum(v.dtype == torch.int64 for v in rec.values()) == n_pool
+    with O.branch(pin=rec):
+        l1, z1, g1, _ = step()
+    assert torch.allclose(z0, z1, rtol=0, atol=0) and all(torch.equal(g0[k], g1[k]) for k in g0)
