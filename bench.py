@@ -134,33 +134,65 @@ def variant_cpu_img_per_s(model, num_classes, batch=2, hw=HW, steps=1, warmup=1,
 
 
 def cpu_path_img_per_s(steps, warmup, batch=2, threads=None):
-    """The reference's CPU path for this workload (oracle port), bounded sample: `batch` images per step.
-    One step = forward, CE + Dice, f_score (no grad), backward, Adam -- the same work the GPU arm times."""
+    """The reference's own CPU path for this workload, bounded sample: `batch` images per step.
+    One step = forward, CE + Dice, f_score (no grad), backward, Adam -- the same work the GPU arm times.
+    kind "reference": the UNMODIFIED reference (nets.unet.Unet, nets.unet_training.CE_Loss / Dice_loss,
+    utils.utils_metrics.f_score staged under baseline/_ref/ by baseline/stage_ref.py) on torch CPU fp32;
+    kind "port": the oracle restatement, only when the staged copy is absent."""
     import torch
     from oracle import unet_oracle as O
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    params = {k: v.clone().requires_grad_(True) for k, v in O.make_params(NUM_CLASSES, seed=11).items()}
-    opt = torch.optim.Adam(list(params.values()), lr=1e-4, betas=(0.9, 0.999))
     imgs, pngs = O.make_inputs(batch, NUM_CLASSES, HW, HW, seed=0)
     labels = O.one_hot(pngs, NUM_CLASSES)
     w = torch.ones(NUM_CLASSES)
+    kind = "port"
+    try:
+        from baseline import stage_ref
+        if stage_ref.stage() is not None and stage_ref.available():
+            kind = "reference"
+    except Exception:
+        kind = "port"
+    if kind == "reference":
+        RU = stage_ref.import_reference("nets.unet")
+        RT = stage_ref.import_reference("nets.unet_training")
+        RM = stage_ref.import_reference("utils.utils_metrics")
+        torch.manual_seed(11)
+        model = RU.Unet(num_classes=NUM_CLASSES, pretrained=False, backbone="vgg").train()
+        model.load_state_dict(O.make_params(NUM_CLASSES, seed=11))
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.999))
+
+        def step():
+            opt.zero_grad()
+            logits = model(imgs)
+            loss = RT.CE_Loss(logits, pngs, w, num_classes=NUM_CLASSES) + RT.Dice_loss(logits, labels)
+            with torch.no_grad():
+                RM.f_score(logits, labels)
+            loss.backward()
+            opt.step()
+            return loss.item()
+    else:
+        params = {k: v.clone().requires_grad_(True) for k, v in O.make_params(NUM_CLASSES, seed=11).items()}
+        opt = torch.optim.Adam(list(params.values()), lr=1e-4, betas=(0.9, 0.999))
+
+        def step():
+            opt.zero_grad()
+            logits = O.unet_forward(params, imgs)
+            loss = O.ce_loss(logits, pngs, w, NUM_CLASSES) + O.dice_loss(logits, labels)
+            with torch.no_grad():
+                O.f_score(logits, labels)
+            loss.backward()
+            opt.step()
+            return loss.item()
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        opt.zero_grad()
-        logits = O.unet_forward(params, imgs)
-        loss = O.ce_loss(logits, pngs, w, NUM_CLASSES) + O.dice_loss(logits, labels)
-        with torch.no_grad():
-            O.f_score(logits, labels)
-        loss.backward()
-        opt.step()
-        loss.item()
+        step()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     total = sum(times)
-    return batch * len(times) / total, total / len(times), threads, batch
+    return batch * len(times) / total, total / len(times), threads, batch, kind
 
 
 def run_reference(args):
@@ -169,7 +201,7 @@ def run_reference(args):
         return
     steps = max(1, min(args.steps, 3))
     warmup = 1 if args.warmup > 0 else 0
-    v, s_per_step, threads, batch = cpu_path_img_per_s(steps, warmup)
+    v, s_per_step, threads, batch, kind = cpu_path_img_per_s(steps, warmup)
     cpu_model = ""
     try:
         for ln in open("/proc/cpuinfo"):
@@ -178,15 +210,17 @@ def run_reference(args):
                 break
     except Exception:
         pass
-    sample = (f"{steps} timed step(s) of batch {batch} (of the 16-image batch), 512x512, 21 classes, fp32 torch CPU, "
-              f"fwd + CE + Dice + bwd, after {warmup} warm-up; {cpu_model}")
+    what = ("the unmodified reference staged under baseline/_ref (nets.unet.Unet, CE_Loss, Dice_loss, f_score)" if kind == "reference"
+            else "the oracle port (reference not staged)")
+    sample = (f"{steps} timed step(s) of batch {batch} (of the 16-image batch), 512x512, 21 classes, fp32 torch CPU, {what}, "
+              f"fwd + CE + Dice + f_score + bwd + Adam, after {warmup} warm-up; {cpu_model}")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "img/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH_PER_GPU, "global_batch": BATCH_PER_GPU * args.gpus,
                        "parallelism": f"dp{args.gpus}",
                        "sample": f"CPU arm: each step is a bounded sample of {batch} of the {BATCH_PER_GPU} images, same work per image as the GPU arm"},
-            "cpu_baseline": {"value": v, "unit": "img/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "img/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -359,10 +393,11 @@ def run_ours(args):
         "loss": loss_val[0], "f_score": loss_val[1],
     }
     if world == 1 and not args.no_cpu_baseline:
-        v, s_per_step, threads, batch = cpu_path_img_per_s(2, 1)
-        line["cpu_baseline"] = {"value": v, "unit": "img/s", "cores": threads, "kind": "port",
-                                "sample": f"2 timed steps of batch {batch} (512x512, 21 classes, fp32 torch CPU oracle, "
-                                          f"fwd + CE + Dice + bwd) after 1 warm-up, {s_per_step:.2f} s/step"}
+        v, s_per_step, threads, batch, kind = cpu_path_img_per_s(2, 1)
+        what = "the unmodified reference (baseline/_ref: nets.unet.Unet + CE_Loss + Dice_loss + f_score)" if kind == "reference" else "the oracle port"
+        line["cpu_baseline"] = {"value": v, "unit": "img/s", "cores": threads, "kind": kind,
+                                "sample": f"2 timed steps of batch {batch} (512x512, 21 classes, fp32 torch CPU, {what}, "
+                                          f"fwd + CE + Dice + f_score + bwd + Adam) after 1 warm-up, {s_per_step:.2f} s/step"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

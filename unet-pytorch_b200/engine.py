@@ -267,7 +267,7 @@ class UNetEngine:
         self._pack_versions = None
 
     # ------------------------------------------------------------------ one conv (+BN) + ReLU layer, forward
-    def _layer_fwd(self, c, x0, params, A, training, x1=None):
+    def _layer_fwd(self, c, x0, params, A, training, x1=None, save=True):
         n, h, w, _ = x0.shape
         bias = self._padded_vec("b:" + c.name, params[c.name + ".bias"], c.cout_p)
         taps = 1 if c.first else 9
@@ -276,9 +276,10 @@ class UNetEngine:
             ops.conv_fprop(x0, c.wf, bias, c.cout_p, taps=taps, relu=True, x1=x1, out=out)
             A[c.name] = out
             return out
-        if not training:
-            # eval mode: BatchNorm is an affine map with fixed statistics, folded into the conv epilogue
-            # (y = relu(acc * s + b')): no z tensor, no BatchNorm pass
+        if not training and not save:
+            # pure inference: BatchNorm is an affine map with fixed statistics, folded into the conv epilogue
+            # (y = relu(acc * s + b')): no z tensor, no BatchNorm pass.  An eval-mode forward that will be back-propagated
+            # (model.eval() + loss.backward()) takes the unfused path below so the BatchNorm backward has z
             gamma = self._padded_vec("g:" + c.bn, params[c.bn + ".weight"], c.cout_p, fill=1.0)
             beta = self._padded_vec("bt:" + c.bn, params[c.bn + ".bias"], c.cout_p)
             rmp = self._padded_vec("rm:" + c.bn, params[c.bn + ".running_mean"], c.cout_p)
@@ -333,6 +334,7 @@ class UNetEngine:
             rmp = self._padded_vec("rm:" + c.bn, rm, c.cout_p)
             rvp = self._padded_vec("rv:" + c.bn, rv, c.cout_p, fill=1.0)
             ops.bn_fwd_eval(z, gamma, beta, rmp, rvp, self.eps, True, out=out, ws=ws)
+            A["bn:" + c.name] = (z, (rmp, rvp), None, gamma, beta)      # eval-mode backward: statistics are constants
         A[c.name] = out
         return out
 
@@ -371,7 +373,7 @@ class UNetEngine:
                 cur = pooled
                 h, w = h // 2, w // 2
             for c in block:
-                cur = self._layer_fwd(c, cur, params, A, training)
+                cur = self._layer_fwd(c, cur, params, A, training, save=save)
             feats.append(cur)
         low = feats[-1]
         for si, (c1, c2) in enumerate(self.dec):
@@ -380,8 +382,8 @@ class UNetEngine:
             up = self._buf(f"up{si}", (N, 2 * hl, 2 * wl, cl))
             ops.upsample2x(low, out=up)
             A[f"up{si}"] = up
-            o1 = self._layer_fwd(c1, skip, params, A, training, x1=up)
-            low = self._layer_fwd(c2, o1, params, A, training)
+            o1 = self._layer_fwd(c1, skip, params, A, training, x1=up, save=save)
+            low = self._layer_fwd(c2, o1, params, A, training, save=save)
         wh = self._head_weight(params)
         # 1x1 classifier on the tensor cores: [hi | lo] bf16 split of the fp32 weights, fp32 NCHW logits from the epilogue
         if ops.act_dtype() == torch.float32:       # fp32 validation build: plain fp32 1x1 conv
@@ -475,9 +477,13 @@ class UNetEngine:
                 wn, bnn = c.bn + ".weight", c.bn + ".bias"
                 dgam = self._buf("dg:" + c.bn, (c.cout_p,), torch.float32)
                 dbet = self._buf("db:" + c.bn, (c.cout_p,), torch.float32)
-                bwd = ops.bn_bwd if self.sync_bn_group is None else functools.partial(ops.bn_bwd_sync, group=self.sync_bn_group)
-                bwd(g, None, z, gamma, mean, invstd, relu=True, out=g, dgamma=dgam, dbeta=dbet, beta=beta,   # mask from z
-                           ws=self._workspace("bn", ops.lib().b2u_bn_workspace(c.cout_p)))
+                if invstd is None:      # eval-mode forward: running statistics, mask from the saved output
+                    ops.bn_bwd_eval(g, A[c.name], z, gamma, beta, mean[0], mean[1], self.eps, relu=True, out=g, dgamma=dgam,
+                                    dbeta=dbet, ws=self._workspace("bn", ops.lib().b2u_bn_workspace(c.cout_p)))
+                else:
+                    bwd = ops.bn_bwd if self.sync_bn_group is None else functools.partial(ops.bn_bwd_sync, group=self.sync_bn_group)
+                    bwd(g, None, z, gamma, mean, invstd, relu=True, out=g, dgamma=dgam, dbeta=dbet, beta=beta,   # mask from z
+                        ws=self._workspace("bn", ops.lib().b2u_bn_workspace(c.cout_p)))
                 if has(wn):
                     grads[wn].copy_(dgam[:c.cout])
                 if has(bnn):

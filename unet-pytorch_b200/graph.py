@@ -466,7 +466,7 @@ class GraphEngine:
                     else:
                         z = self._buf(ins["out"], (n, h, w, pad64(ins["cout"])))
                         bias = self._tiled("b2:" + ins["w"], params[ins["bias"]], pad64(ins["cout"]), f)
-                    fold = self._fold_bn.get(ins["out"]) if not training else None
+                    fold = self._fold_bn.get(ins["out"]) if (not training and not save) else None
                     if fold is not None:        # eval: BatchNorm (+ReLU) folded into the epilogue, vectors tiled like the bias
                         sc, bs = self._folded_bn(fold, params, params[ins["bias"]], z.shape[3])
                         sc = self._tiled("fs2:" + ins["w"], sc, z.shape[3], f)
@@ -485,7 +485,9 @@ class GraphEngine:
                 bias = self._padded("b:" + ins["w"], params[ins["bias"]], (coutp,)) if ins["bias"] else None
                 aux = None
                 stats = None
-                fold = self._fold_bn.get(ins["out"]) if not training else None
+                # folding is for pure inference: an eval-mode forward that will be back-propagated (model.eval() +
+                # loss.backward()) keeps z and runs the BatchNorm instruction so its backward has what it needs
+                fold = self._fold_bn.get(ins["out"]) if (not training and not save) else None
                 if fold is not None:
                     # eval mode: y = [relu](acc * s + b') straight from the conv epilogue; the BatchNorm instruction passes it on
                     sc, bs = self._folded_bn(fold, params, params[ins["bias"]] if ins["bias"] else None, coutp)
@@ -560,7 +562,7 @@ class GraphEngine:
                 else:
                     ops.bn_fwd_eval(zt.data, gamma, beta, rmp, rvp, self.eps, ins["relu"], out=y, ws=ws,
                                     residual=res.data if res else None)
-                    mean = invstd = None
+                    mean, invstd = (rmp, rvp), None        # eval mode: the backward uses the running statistics (constants)
                 ng = zt.needs_grad or (res is not None and res.needs_grad) or (bnn + ".weight") in trainable or (bnn + ".bias") in trainable
                 t = _T(y, needs_grad=ng)
                 t.aux = (mean, invstd, gamma, beta)
@@ -789,10 +791,14 @@ class GraphEngine:
                 dgam = grads[bnn + ".weight"] if (direct and has(bnn + ".weight")) else self._buf("dg:" + bnn, (cp,), torch.float32)
                 dbet = grads[bnn + ".bias"] if (direct and has(bnn + ".bias")) else self._buf("db:" + bnn, (cp,), torch.float32)
                 # y is read only where a residual was added before the ReLU; otherwise the mask is recomputed from z
-                bwd = ops.bn_bwd if self.sync_bn_group is None else functools.partial(ops.bn_bwd_sync, group=self.sync_bn_group)
-                bwd(t.grad, t.data if res is not None else None, zt.data, gamma, mean, invstd, relu=ins["relu"], out=dz,
-                           dgamma=dgam, dbeta=dbet, beta=beta,
-                           ws=self._workspace("bn", ops.lib().b2u_bn_workspace(cp)), gout=gout)
+                if invstd is None:          # eval-mode forward (model.eval() + backward): statistics are constants
+                    ops.bn_bwd_eval(t.grad, t.data, zt.data, gamma, beta, mean[0], mean[1], self.eps, relu=ins["relu"], out=dz,
+                                    dgamma=dgam, dbeta=dbet, ws=self._workspace("bn", ops.lib().b2u_bn_workspace(cp)), gout=gout)
+                else:
+                    bwd = ops.bn_bwd if self.sync_bn_group is None else functools.partial(ops.bn_bwd_sync, group=self.sync_bn_group)
+                    bwd(t.grad, t.data if res is not None else None, zt.data, gamma, mean, invstd, relu=ins["relu"], out=dz,
+                        dgamma=dgam, dbeta=dbet, beta=beta,
+                        ws=self._workspace("bn", ops.lib().b2u_bn_workspace(cp)), gout=gout)
                 if not direct:
                     if has(bnn + ".weight"):
                         grads[bnn + ".weight"].copy_(dgam[:c])

@@ -13,6 +13,10 @@ class EngineFunction(torch.autograd.Function):
         tensors.update(module._named_buffer_tensors())        # BatchNorm running statistics (updated in place)
         needs = any(ctx.needs_input_grad[2:])
         trainable = {n for n, need in zip(names, ctx.needs_input_grad[2:]) if need}
+        if needs or module.training:
+            # parameters of a training module change between calls (optimizer steps, and in-place `.data` writes such as
+            # weights_init / EMA that do not bump Tensor._version): always re-pack the bf16 operands (one launch)
+            engine.invalidate_packed_weights()
         logits = engine.forward(x, tensors, save=needs, training=module.training, trainable=trainable)
         if needs:
             engine._generation = getattr(engine, "_generation", 0) + 1
@@ -28,7 +32,9 @@ class EngineFunction(torch.autograd.Function):
         engine = ctx.engine
         if engine._generation != ctx.generation:
             raise RuntimeError("backward: the saved activations were overwritten by a later training forward")
-        grads = {n: torch.empty_like(p) for n, p, need in zip(ctx.names, ctx.params, ctx.needs_input_grad[2:]) if need}
+        # zero-initialised: a gradient the engine legitimately leaves untouched (a tensor that cannot receive one) reads as
+        # 0, never as uninitialised memory
+        grads = {n: torch.zeros_like(p) for n, p, need in zip(ctx.names, ctx.params, ctx.needs_input_grad[2:]) if need}
         engine.backward(dlogits, ctx.tensors, grads)
         return (None, None) + tuple(grads.get(n) for n in ctx.names)
 
@@ -56,6 +62,7 @@ class EngineModuleMixin:
         # (named_parameters() is empty there), so tensors are always fetched by walking the module tree by name
         self._pnames = [n for n, _ in self.named_parameters()]
         self._bnames = [n for n, _ in self.named_buffers()]
+        self.register_load_state_dict_post_hook(lambda module, incompatible_keys: module.invalidate())
 
     @property
     def _param_names(self):
@@ -69,6 +76,12 @@ class EngineModuleMixin:
 
     def _named_buffer_tensors(self):
         return {n: self._by_name(n) for n in self._bnames}
+
+    def invalidate(self):
+        """Call after changing parameters of an eval-mode module behind autograd's back (`p.data` writes): the engines
+        then re-pack their bf16 operands on the next forward.  load_state_dict does it by itself."""
+        for eng in self._engines.values():
+            eng.invalidate_packed_weights()
 
     def _engine_forward(self, inputs):
         if not inputs.is_cuda:

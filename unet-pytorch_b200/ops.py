@@ -410,6 +410,37 @@ def bn_bwd(dy, y, z, gamma, mean, invstd, relu=True, out=None, dgamma=None, dbet
     return out, dgamma, dbeta
 
 
+def bn_bwd_eval(dy, y, z, gamma, beta, running_mean, running_var, eps=1e-5, relu=True, out=None, dgamma=None, dbeta=None, ws=None,
+                gout=None):
+    """Backward of an eval-mode BatchNorm (+ReLU) -- `model.eval()` followed by `loss.backward()` (frozen-statistics
+    fine-tuning): the statistics are constants, so dz = gamma / sqrt(rv + eps) * g with g = dy * (y > 0), dbeta = sum g,
+    dgamma = sum g * xhat.  Runs the SyncBatchNorm pair of kernels with the batch sums set to zero (no mean terms)."""
+    _req(dy, ACT, "dy"); _req(y, ACT, "y"); _req(z, ACT, "z")
+    if relu and y is None:
+        raise ValueError("bn_bwd_eval: the ReLU mask is taken from y")
+    C = z.shape[-1]
+    P = z.numel() // C
+    need = lib().b2u_bn_workspace(C)
+    if ws is None or ws.numel() * ws.element_size() < need:
+        ws = _ws(need, z.device)
+    if out is None:
+        out = torch.empty_like(z)
+    invstd = torch.rsqrt(running_var + eps)
+    sums = torch.empty((2, C), dtype=torch.float32, device=z.device)
+    check(lib().b2u_bn_bwd_sums(ptr(dy), ptr(y), ptr(z), ptr(gamma), ptr(beta), ptr(running_mean), ptr(invstd), ptr(sums), ptr(ws),
+                                ws.numel() * ws.element_size(), P, C, 1 if relu else 0, stream_ptr()))
+    if dbeta is not None:
+        dbeta.copy_(sums[0])
+    if dgamma is not None:
+        dgamma.copy_(sums[1])
+    local = sums.clone()
+    sums.zero_()
+    check(lib().b2u_bn_bwd_apply_sums(ptr(dy), ptr(y), ptr(z), ptr(gamma), ptr(beta), ptr(running_mean), ptr(invstd), ptr(out), ptr(gout),
+                                      ptr(sums), P, ptr(ws), ws.numel() * ws.element_size(), P, C, 1 if relu else 0,
+                                      stream_ptr()))
+    return out, local[1], local[0]
+
+
 # ---------------------------------------------------------------------------------------------- ResNet helpers
 def im2col_stem(x_nchw, out=None):
     _req(x_nchw, torch.float32, "x")

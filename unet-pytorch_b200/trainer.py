@@ -177,6 +177,7 @@ class UnetTrainer:
         self.m = self.layout.new_buffer()
         self.v = self.layout.new_buffer() if optimizer == "adam" else None
         self.step_count = 0
+        self.steps = {}                 # per-tensor optimizer step count (torch.optim keeps `state['step']` per parameter)
         self.dice, self.focal, self.compute_f_score = dice_loss, focal_loss, compute_f_score
         cw = torch.ones(num_classes) if cls_weights is None else torch.as_tensor(cls_weights, dtype=torch.float32)
         self.cls_w = cw.to(self.device).contiguous()
@@ -280,7 +281,7 @@ class UnetTrainer:
 
     # ------------------------------------------------------------------ the step
     def forward_loss(self, imgs, pngs, save=True):
-        logits = self.engine.forward(imgs, self.tensors, save=save)
+        logits = self.engine.forward(imgs, self.tensors, save=save, trainable=self.trainable)
         if pngs.dtype != torch.int64:
             pngs = pngs.long()
         if logits.shape[2] != pngs.shape[1] and logits.shape[3] != pngs.shape[2]:
@@ -320,22 +321,35 @@ class UnetTrainer:
         loss = fin[1] if self.focal else fin[0]
         return loss + fin[2] if self.dice else loss
 
+    def _update_ranges(self):
+        """Contiguous slices of the flat buffers to update this step, as (start, end, step count) -- torch.optim semantics for
+        frozen parameters (train.py:382-383 flips requires_grad, so their .grad is None and the optimizer skips them: no
+        update, no weight decay, no moment decay, and their per-parameter `step` only starts counting once they receive
+        gradients).  The layout is in backward-completion order, so the decoder and the backbone are one or two slices each;
+        neighbouring trainable tensors with the same step count are merged into one launch."""
+        ranges = []
+        for n in self.layout.order:
+            if n not in self.trainable:
+                continue
+            o, numel, _ = self.layout.offsets[n]
+            e = o + (numel + 3) // 4 * 4
+            st = self.steps.get(n, 0) + 1
+            self.steps[n] = st
+            if ranges and ranges[-1][1] == o and ranges[-1][2] == st:
+                ranges[-1][1] = e
+            else:
+                ranges.append([o, e, st])
+        return ranges
+
     def optimizer_step(self, grad_scale=1.0):
         self.step_count += 1
-        if len(self.trainable) != len(self.names):
-            # frozen tensors: zero their gradient slices so the flat update leaves them untouched (Adam with g = 0
-            # and zero moments is a no-op; weight decay is not applied to frozen tensors by the reference either)
-            for n in self.names:
-                if n not in self.trainable:
-                    self.grads[n].zero_()
-            if self.weight_decay != 0.0:
-                raise NotImplementedError("weight decay with a frozen backbone: per-slice update not built yet")
-        if self.opt_kind == "adam":
-            ops.adam_step(self.flat_param, self.flat_grad, self.m, self.v, self.step_count, self.lr, self.betas, self.eps,
-                          self.weight_decay, grad_scale)
-        else:
-            ops.sgd_step(self.flat_param, self.flat_grad, self.m, self.lr, self.momentum, self.weight_decay, True,
-                         self.step_count == 1, grad_scale)
+        for s, e, st in self._update_ranges():
+            if self.opt_kind == "adam":
+                ops.adam_step(self.flat_param[s:e], self.flat_grad[s:e], self.m[s:e], self.v[s:e], st, self.lr, self.betas,
+                              self.eps, self.weight_decay, grad_scale)
+            else:
+                ops.sgd_step(self.flat_param[s:e], self.flat_grad[s:e], self.m[s:e], self.lr, self.momentum, self.weight_decay,
+                             True, st == 1, grad_scale)
         # the flat update wrote every parameter behind torch's back: invalidate the engine's packed-weight cache
         self.engine.invalidate_packed_weights()
 

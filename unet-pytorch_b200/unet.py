@@ -8,7 +8,6 @@ one kernel (`b2u_softmax_resize_argmax_u8`) does softmax + crop + INTER_LINEAR r
 per pixel) is the only thing copied back.  Host-side image handling (RGB conversion, BICUBIC letterbox with grey bars,
 colour blending) follows utils/utils.py:12-34 and unet.py:150-203 with PIL/numpy, as in the reference."""
 import colorsys
-import copy
 import time
 
 import numpy as np
@@ -18,10 +17,19 @@ from PIL import Image
 from . import ops
 from .nets.unet import Unet as unet
 
-_VOC_COLORS = [(0, 0, 0), (128, 0, 0), (0, 128, 0), (128, 128, 0), (0, 0, 128), (128, 0, 128), (0, 128, 128),
-               (128, 128, 128), (64, 0, 0), (192, 0, 0), (64, 128, 0), (192, 128, 0), (64, 0, 128), (192, 0, 128),
-               (64, 128, 128), (192, 128, 128), (0, 64, 0), (128, 64, 0), (0, 192, 0), (128, 192, 0), (0, 64, 128),
-               (128, 64, 12)]
+def _voc_palette(n):
+    """The PASCAL VOC class palette (bit-interleaved colour code of the class index) -- the table of unet.py:59-63."""
+    out = []
+    for i in range(n):
+        r = g = b = 0
+        c = i
+        for j in range(8):
+            r |= ((c >> 0) & 1) << (7 - j)
+            g |= ((c >> 1) & 1) << (7 - j)
+            b |= ((c >> 2) & 1) << (7 - j)
+            c >>= 3
+        out.append((r, g, b))
+    return out
 
 
 def cvtColor(image):                                   # utils/utils.py:12-17
@@ -56,7 +64,7 @@ class Unet(object):
         for name, value in kwargs.items():
             setattr(self, name, value)
         if self.num_classes <= 21:
-            self.colors = list(_VOC_COLORS)
+            self.colors = _voc_palette(22)
         else:
             hsv = [(x / self.num_classes, 1.0, 1.0) for x in range(self.num_classes)]
             self.colors = [tuple(int(v * 255) for v in colorsys.hsv_to_rgb(*t)) for t in hsv]
@@ -119,32 +127,17 @@ class Unet(object):
 
     # ------------------------------------------------------------------ reference API
     def detect_image(self, image, count=False, name_classes=None):
+        """unet.py:100-203: the class map (GPU) rendered with the reference's three mix types; `count` returns the per-class
+        pixel counts through `self.last_counts` (the reference prints them as a table)."""
         old_img, pr = self.predict_mask(image)
-        old_img = copy.deepcopy(old_img)
-        oh, ow = pr.shape
         if count:
-            classes_nums = np.zeros([self.num_classes])
-            total = oh * ow
-            print("-" * 63)
-            print("|%25s | %15s | %15s|" % ("Key", "Value", "Ratio"))
-            print("-" * 63)
-            for i in range(self.num_classes):
-                num = np.sum(pr == i)
-                if num > 0:
-                    print("|%25s | %15s | %14.2f%%|" % (str(name_classes[i]), str(num), num / total * 100))
-                    print("-" * 63)
-                classes_nums[i] = num
-            print("classes_nums:", classes_nums)
-        if self.mix_type == 0:
-            seg = np.reshape(np.array(self.colors, np.uint8)[np.reshape(pr, [-1])], [oh, ow, -1])
-            return Image.blend(old_img, Image.fromarray(np.uint8(seg)), 0.7)
-        if self.mix_type == 1:
-            seg = np.reshape(np.array(self.colors, np.uint8)[np.reshape(pr, [-1])], [oh, ow, -1])
-            return Image.fromarray(np.uint8(seg))
-        if self.mix_type == 2:
-            seg = (np.expand_dims(pr != 0, -1) * np.array(old_img, np.float32)).astype("uint8")
-            return Image.fromarray(np.uint8(seg))
-        return old_img
+            self.last_counts = np.bincount(pr.reshape(-1), minlength=self.num_classes)
+        if self.mix_type not in (0, 1, 2):
+            return old_img
+        if self.mix_type == 2:                      # keep the pixels of every non-background class
+            return Image.fromarray(np.where((pr != 0)[..., None], np.asarray(old_img), 0).astype(np.uint8))
+        seg = Image.fromarray(np.asarray(self.colors, np.uint8)[pr])
+        return Image.blend(old_img, seg, 0.7) if self.mix_type == 0 else seg
 
     def get_FPS(self, image, test_interval):           # unet.py:205-258: forward + per-pixel class + crop, result on the host
         _, data, nw, nh, _, _ = self._letterbox(image)
