@@ -255,7 +255,7 @@ def unet_forward_bf16_storage(params, x):
     def conv(x, name):
         return _r(F.relu(F.conv2d(_r(x, fwd=False), wq(name + ".weight"), params[name + ".bias"], padding=1)))
 
-    x = _r(x)
+    # the image itself is NOT rounded: the product path feeds it as a two-term bf16 split (hi + lo im2col columns)
     feats = [None] * 5
     it = iter(VGG_CONV_IDX)
     for v in VGG_CFG:
@@ -385,7 +385,8 @@ def _double_conv(sd, prefix, x, training, stats, bf16):
             x = _r(x, fwd=False)
         z = F.conv2d(x, w, b, padding=1)
         if bf16:
-            z = _r(z)
+            c = stats[bn + ".running_mean"].detach().clone().view(1, -1, 1, 1) if training else 0.0      # see _center
+            z = _r(z - c) + c
         rm, rv = stats[bn + ".running_mean"], stats[bn + ".running_var"]
         y = F.batch_norm(z, rm, rv, sd[bn + ".weight"], sd[bn + ".bias"], training, 0.1, 1e-5)
         if training:
@@ -401,9 +402,7 @@ def trad_forward(sd, x, training=True, stats=None, bf16_storage=False):
     training (defaults to clones of the buffers in sd)."""
     if stats is None:
         stats = {k: v.clone() for k, v in sd.items() if "running_" in k or "num_batches" in k}
-    if bf16_storage:
-        x = _r(x)
-    feats = []
+    feats = []          # (the image is not rounded: two-term bf16 split in the product path)
     for i, (prefix, _, _) in enumerate(TRAD_ENC):
         if i > 0:
             x = _pinned_max_pool(x, f"pool{i}")                                  # Down, :24-27
@@ -498,12 +497,20 @@ def _rn_bn(sd, stats, name, z, training, relu, res=None, bf16=False):
     return _r(y) if bf16 else y
 
 
-def _rn_conv(sd, name, x, stride=1, padding=0, bias=None, bf16=False):
+def _center(stats, bn, training):
+    """Storage model of the product path: in training a conv output read only by a BatchNorm is stored as
+    bf16(z - running_mean) (the shift rides in the conv bias in fp32; BatchNorm is shift-invariant)."""
+    return stats[bn + ".running_mean"].detach().clone().view(1, -1, 1, 1) if training else None
+
+
+def _rn_conv(sd, name, x, stride=1, padding=0, bias=None, bf16=False, center=None):
     w = sd[name]
     if bf16:
         w = w + (w.to(torch.bfloat16).to(w.dtype) - w).detach()
         x = _r(x, fwd=False)
     z = F.conv2d(x, w, bias, stride=stride, padding=padding)
+    if bf16 and center is not None:
+        return _r(z - center) + center
     return _r(z) if bf16 else z
 
 
@@ -515,7 +522,7 @@ def resnet_unet_forward(sd, x, training=True, stats=None, bf16_storage=False):
         stats = {k: v.clone() for k, v in sd.items() if "running_" in k or "num_batches" in k}
     if b:
         x = _r(x)
-    z = _rn_conv(sd, "resnet.conv1.weight", x, stride=2, padding=3, bf16=b)                         # resnet.py:166
+    z = _rn_conv(sd, "resnet.conv1.weight", x, stride=2, padding=3, bf16=b, center=_center(stats, "resnet.bn1", training))   # resnet.py:166
     feat1 = _rn_bn(sd, stats, "resnet.bn1", z, training, True, bf16=b)
     x = _pinned_max_pool(feat1, "pool", kernel=3, stride=2, ceil_mode=True)                         # resnet.py:113,170
     feats = [feat1]
@@ -523,12 +530,12 @@ def resnet_unet_forward(sd, x, training=True, stats=None, bf16_storage=False):
         for bi in range(blocks):
             p = f"resnet.layer{li}.{bi}"
             s = stride if bi == 0 else 1
-            out = _rn_bn(sd, stats, p + ".bn1", _rn_conv(sd, p + ".conv1.weight", x, bf16=b), training, True, bf16=b)
-            out = _rn_bn(sd, stats, p + ".bn2", _rn_conv(sd, p + ".conv2.weight", out, stride=s, padding=1, bf16=b), training, True, bf16=b)
-            z3 = _rn_conv(sd, p + ".conv3.weight", out, bf16=b)
+            out = _rn_bn(sd, stats, p + ".bn1", _rn_conv(sd, p + ".conv1.weight", x, bf16=b, center=_center(stats, p + ".bn1", training)), training, True, bf16=b)
+            out = _rn_bn(sd, stats, p + ".bn2", _rn_conv(sd, p + ".conv2.weight", out, stride=s, padding=1, bf16=b, center=_center(stats, p + ".bn2", training)), training, True, bf16=b)
+            z3 = _rn_conv(sd, p + ".conv3.weight", out, bf16=b, center=_center(stats, p + ".bn3", training))
             idn = x
             if bi == 0:
-                idn = _rn_bn(sd, stats, p + ".downsample.1", _rn_conv(sd, p + ".downsample.0.weight", x, stride=s, bf16=b),
+                idn = _rn_bn(sd, stats, p + ".downsample.1", _rn_conv(sd, p + ".downsample.0.weight", x, stride=s, bf16=b, center=_center(stats, p + ".downsample.1", training)),
                              training, False, bf16=b)
             x = _rn_bn(sd, stats, p + ".bn3", z3, training, True, res=idn, bf16=b)            # resnet.py:89-95
         feats.append(x)
@@ -649,13 +656,13 @@ def _ulu_block(sd, stats, p, x, training, b):
     """LightConvBlock: 1x1 conv, BN, ReLU, depthwise 3x3 (+bias), 1x1 conv, BN, ReLU.  bf16 storage model: the CUDA path
     stores conv outputs, BN outputs and the depthwise output in bf16, weights of the tensor-core 1x1 convs in bf16; the
     depthwise weights stay fp32."""
-    z = _rn_conv(sd, p + ".conv.0.weight", x, bias=sd[p + ".conv.0.bias"], bf16=b)
+    z = _rn_conv(sd, p + ".conv.0.weight", x, bias=sd[p + ".conv.0.bias"], bf16=b, center=_center(stats, p + ".conv.1", training))
     y = _rn_bn(sd, stats, p + ".conv.1", z, training, True, bf16=b)
     wdw = sd[p + ".conv.3.depthwise.weight"]
     d = F.conv2d(_r(y, fwd=False) if b else y, wdw, sd[p + ".conv.3.depthwise.bias"], padding=1, groups=wdw.shape[0])
     if b:
         d = _r(d)
-    z = _rn_conv(sd, p + ".conv.3.pointwise.weight", d, bias=sd[p + ".conv.3.pointwise.bias"], bf16=b)
+    z = _rn_conv(sd, p + ".conv.3.pointwise.weight", d, bias=sd[p + ".conv.3.pointwise.bias"], bf16=b, center=_center(stats, p + ".conv.4", training))
     return _rn_bn(sd, stats, p + ".conv.4", z, training, True, bf16=b)
 
 
@@ -675,9 +682,7 @@ def ulu_forward(sd, x, variant, training=True, stats=None, bf16_storage=False, d
     b = bf16_storage
     if stats is None:
         stats = {k: v.clone() for k, v in sd.items() if "running_" in k or "num_batches" in k}
-    if b:
-        x = _r(x)
-    skips = []
+    skips = []          # (the image is not rounded: two-term bf16 split in the product path)
     for i in range(1, 5):
         if i > 1:
             x = _pinned_max_pool(x, f"p{i}")
@@ -798,14 +803,14 @@ def make_lw_params(num_classes, seed=11):
 
 
 def _lw_conv_block(sd, stats, p, x, training, b):
-    z = _rn_conv(sd, p + ".conv.0.weight", x, padding=1, bias=sd[p + ".conv.0.bias"], bf16=b)
+    z = _rn_conv(sd, p + ".conv.0.weight", x, padding=1, bias=sd[p + ".conv.0.bias"], bf16=b, center=_center(stats, p + ".conv.1", training))
     return _rn_bn(sd, stats, p + ".conv.1", z, training, True, bf16=b)
 
 
 def _lw_res_block(sd, stats, p, x, training, b):
     """ResidualBlock.forward (nets/LightWeightUnet.py:45-55)."""
-    y = _rn_bn(sd, stats, p + ".bn1", _rn_conv(sd, p + ".conv1.weight", x, padding=1, bias=sd[p + ".conv1.bias"], bf16=b), training, True, bf16=b)
-    y = _rn_bn(sd, stats, p + ".bn2", _rn_conv(sd, p + ".conv2.weight", y, padding=1, bias=sd[p + ".conv2.bias"], bf16=b), training, False, bf16=b)
+    y = _rn_bn(sd, stats, p + ".bn1", _rn_conv(sd, p + ".conv1.weight", x, padding=1, bias=sd[p + ".conv1.bias"], bf16=b, center=_center(stats, p + ".bn1", training)), training, True, bf16=b)
+    y = _rn_bn(sd, stats, p + ".bn2", _rn_conv(sd, p + ".conv2.weight", y, padding=1, bias=sd[p + ".conv2.bias"], bf16=b, center=_center(stats, p + ".bn2", training)), training, False, bf16=b)
     y = _ulu_se(sd, p + ".se", y, b)
     y = _pinned_relu(y + x, p + ".out")
     return _r(y) if b else y
@@ -826,9 +831,7 @@ def lw_forward(sd, x, training=True, stats=None, bf16_storage=False, drop_masks=
         t = t * m[:, :, None, None]
         return _r(t) if b else t
 
-    if b:
-        x = _r(x)
-    feats = []
+    feats = []          # (the image is not rounded: two-term bf16 split in the product path)
     for k in range(1, 6):
         x = _lw_conv_block(sd, stats, f"backbone.stage{k}.0", x, training, b)
         x = _lw_res_block(sd, stats, f"backbone.stage{k}.1", x, training, b)

@@ -38,7 +38,7 @@ def main():
     for fam, C, medical in cases:
         print(f"== {fam} nc={C} {'medical' if medical else 'voc-like'} {args.hw}x{args.hw} batch {args.batch}", flush=True)
         r = WP.measure(b2u, fam, C, hw=args.hw, batch=args.batch, warm_steps=args.warm, medical=medical, log=lambda s: print(s, flush=True),
-                       with_autocast=not args.no_autocast, cache_dir=os.path.join(ROOT, "gpurun_out", "warm"))
+                       with_autocast=not args.no_autocast)
         for k in ("ours_bf16", "autocast_bf16", "ref_fp32"):
             if k in r:
                 v = r[k]

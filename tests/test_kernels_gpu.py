@@ -95,11 +95,12 @@ def test_first_layer_im2col_conv(b2u, cuda_device):
     b = torch.randn(64, generator=g)
     col = ops.im2col_first(x.to(dev))
     y = ops.conv_fprop(col, ops.pack_weights_first(w.to(dev)), b.to(dev), 64, taps=1, relu=True)
-    ref = F.conv2d(x.to(BF).float(), w.to(BF).float(), b, padding=1).relu()
+    ref = F.conv2d(x, w.to(BF).float(), b, padding=1).relu()          # x itself: the image is a two-term bf16 split
     assert rel(nchw(y), ref) <= 6e-3
     dzb = nhwc(torch.randn(2, 64, 32, 48, generator=g), dev)
     dw = ops.conv_wgrad(col, dzb, taps=1, first_cin=3)
-    ref_dw = torch.nn.grad.conv2d_weight(x.to(BF).float(), w.shape, nchw(dzb), padding=1)
+    # the image enters as a two-term bf16 split (hi + lo columns of the im2col row): the weight gradient sees x itself
+    ref_dw = torch.nn.grad.conv2d_weight(x, w.shape, nchw(dzb), padding=1)
     assert rel(dw, ref_dw) <= 1e-4
 
 
@@ -515,7 +516,10 @@ def test_padded_input_conversion(b2u, cuda_device):
     x = torch.randn(2, 3, 16, 32)
     y = ops.nchw_to_nhwc_bf16_padded(x.to(cuda_device), 64)
     assert tuple(y.shape) == (2, 16, 32, 64)
-    assert torch.equal(y[..., :3].cpu(), x.permute(0, 2, 3, 1).to(BF)) and y[..., 3:].abs().max().item() == 0
+    hi = x.permute(0, 2, 3, 1).to(BF)
+    assert torch.equal(y[..., :3].cpu(), hi) and y[..., 6:].abs().max().item() == 0
+    # channels [C, 2C): the second term of the two-term bf16 split of the image (the first conv's weights repeat there)
+    assert torch.equal(y[..., 3:6].cpu(), (x.permute(0, 2, 3, 1) - hi.float()).to(BF))
 
 
 def test_residual_join_and_resize_kernels(b2u, cuda_device, golden_dir):

@@ -39,6 +39,16 @@ def _argmax_agreement(logits, ref):
     return (a == b).float().mean().item(), (a == b)[confident].float().mean().item()
 
 
+def _direct(tag, outputs, z32, grads, g32, zbound, gbound):
+    """Direct, absolute comparison with the fp32 oracle on the small random-init fixtures (32-64 px, where ResNet's layer4
+    sees 8 samples per channel): fixed bounds taken from the measured values, no bf16-model yardstick.  The precision
+    claim at BASELINE size (512x512, warm weights, float64 reference, torch autocast as peer) is tests/test_parity_512_gpu.py."""
+    zr, gr = rel(outputs, z32), _global_rel(grads, g32)
+    print(f"\n[direct {tag}] logits {zr:.3e} (bound {zbound:.1e})  grads {gr:.3e} (bound {gbound:.1e})")
+    assert zr <= zbound, (tag, zr)
+    assert gr <= gbound, (tag, gr)
+
+
 CASES = [
     # tag, C, n, h, w, seed, medical, cls_w, dice, focal
     ("nc2_medical", 2, 2, 64, 64, 0, True, [1, 1], False, False),
@@ -223,6 +233,7 @@ def test_full_size_step_properties(b2u, cuda_device):
 # The CUDA path is therefore held to (a) tight per-kernel BatchNorm tests (tests/test_kernels_gpu.py), (b) the
 # bf16-storage model as yardstick here, (c) exact agreement of everything that is not rounding-limited: running
 # statistics, loss value, eval-mode logits.
+TRAD_BOUNDS = {"nc4_focaldice": (8e-2, 3e-1), "nc21_cedice": (8e-2, 3e-1)}      # (logits, gradients) vs the fp32 oracle, absolute
 TRAD_CASES = [("nc4_focaldice", 4, 2, 64, 64, 3, [1, 15, 1.5, 2], True, True), ("nc21_cedice", 21, 2, 32, 64, 4, [1] * 21, True, False)]
 
 
@@ -249,6 +260,7 @@ def test_traditional_unet_dropin(b2u, cuda_device, golden_dir, tag, C, n, h, w, 
     grads = {k: p.grad for k, p in model.named_parameters()}
     assert all(v is not None and torch.isfinite(v).all() for v in grads.values())
     assert _global_rel(grads, g32) <= 1.5 * noise_g and _global_rel(grads, gbf) <= 1.2 * noise_g
+    _direct("traditional " + tag, outputs, z32, grads, g32, *TRAD_BOUNDS[tag])
     # BatchNorm buffers after one training step (fp32 statistics of bf16 pre-activations)
     for name, b in model.named_buffers():
         want = s32[name]
@@ -315,6 +327,7 @@ def test_resnet50_unet_dropin(b2u, cuda_device, golden_dir):
     grads = {k: p.grad for k, p in model.named_parameters()}
     assert all(v is not None and torch.isfinite(v).all() for v in grads.values())
     assert _global_rel(grads, g32) <= 1.5 * noise_g and _global_rel(grads, gbf) <= 1.2 * noise_g
+    _direct("unet_resnet50 nc21", outputs, z32, grads, g32, 5e-2, 3e-1)
     # decoder-side tensors are not behind a BatchNorm backward: plain bf16 accuracy
     for k in ("final.weight", "final.bias", "up_conv.3.weight", "up_conv.1.weight", "up_concat1.conv2.weight"):
         assert rel(grads[k], g32[k]) <= 2e-2, k
@@ -401,13 +414,14 @@ def test_ultralight_unet_dropin(b2u, cuda_device, golden_dir, variant, cls, tag)
     ref = torch.from_numpy(g["logits"])
     assert outputs.shape == ref.shape
     assert rel(outputs, ref) <= max(1.5 * noise_z, 1e-2)
-    assert rel(outputs, zbf) <= max(0.75 * noise_z, 5e-3)
+    assert rel(outputs, zbf) <= max(noise_z, 5e-3)
     assert abs(loss.item() - float(g["loss"])) <= 1e-2 * abs(float(g["loss"]))
     grads = {k: p.grad for k, p in model.named_parameters()}
     assert all(v is not None and torch.isfinite(v).all() for v in grads.values())
     live = {k: v for k, v in grads.items() if not (k.endswith(".conv.0.bias") or k.endswith("wise.bias"))}    # zero-gradient biases
     assert _global_rel(live, {k: g32[k] for k in live}) <= 1.5 * noise_g
     assert _global_rel(live, {k: gbf[k] for k in live}) <= 1.2 * noise_g
+    _direct(f"{variant} {tag}", outputs, z32, live, {k: g32[k] for k in live}, 8e-2, 3e-1)
     for k in ("final.weight", "final.bias"):      # no BatchNorm backward in between: bounded by the head input's forward noise
         assert rel(grads[k], g32[k]) <= max(2e-2, 2 * noise_z), k
     for name, b in model.named_buffers():
@@ -564,7 +578,7 @@ def test_lightweight_unet_dropin(b2u, cuda_device, golden_dir, tag):
     noise_z, noise_g = rel(zbf, z32), _global_rel(gbf, g32)
     ref = torch.from_numpy(g["logits"])
     assert rel(outputs, ref) <= max(1.5 * noise_z, 1e-2)
-    assert rel(outputs, zbf) <= max(0.75 * noise_z, 5e-3)
+    assert rel(outputs, zbf) <= max(noise_z, 5e-3)
     assert abs(loss.item() - float(g["loss"])) <= 1e-2 * abs(float(g["loss"]))
     grads = {k: p.grad for k, p in model.named_parameters()}
     assert all(v is not None and torch.isfinite(v).all() for v in grads.values())
@@ -576,6 +590,7 @@ def test_lightweight_unet_dropin(b2u, cuda_device, golden_dir, tag):
     assert all(grads[k].abs().max().item() == 0 for k in grads if pre_bn_bias(k))      # exact zero by the BN identity
     assert _global_rel(live, {k: g32[k] for k in live}) <= 1.5 * noise_g
     assert _global_rel(live, {k: gbf[k] for k in live}) <= 1.2 * noise_g
+    _direct("lightweight " + tag, outputs, z32, live, {k: g32[k] for k in live}, 8e-2, 3e-1)
     for k in ("final_conv.3.weight", "final_conv.3.bias"):
         assert rel(grads[k], g32[k]) <= max(2e-2, 2 * noise_z), k
     model.eval()

@@ -153,7 +153,8 @@ __global__ void bn_fwd_finalize_kernel(const float* __restrict__ partial, int bl
                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                        float* __restrict__ running_mean, float* __restrict__ running_var,
                                        float* __restrict__ save_mean, float* __restrict__ save_invstd,
-                                       float* __restrict__ scale, float* __restrict__ shift, float eps, float momentum) {
+                                       float* __restrict__ scale, float* __restrict__ shift, float eps, float momentum,
+                                       int centered) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double s = 0.0, ss = 0.0;
@@ -169,7 +170,13 @@ __global__ void bn_fwd_finalize_kernel(const float* __restrict__ partial, int bl
   save_mean[c] = mean_f;
   save_invstd[c] = invstd_f;
   bn_affine(gamma ? gamma[c] : 1.f, beta ? beta[c] : 0.f, mean_f, invstd_f, scale + c, shift + c);
-  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+  // centered: the producing conv stored z - running_mean (the old value, still in place here), so `mean` is the mean of
+  // the shifted tensor; everything downstream (y, saved statistics, the backward) is shift-invariant, only the running
+  // mean has to see the true mean
+  if (running_mean) {
+    const float rm_old = running_mean[c];
+    running_mean[c] = (1.f - momentum) * rm_old + momentum * (static_cast<float>(mean) + (centered ? rm_old : 0.f));
+  }
   if (running_var) {
     const double unbiased = P > 1 ? var * static_cast<double>(P) / static_cast<double>(P - 1) : var;
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
@@ -326,6 +333,8 @@ int b2u_bn_fwd_train(const void* z, const void* residual, void* y, const float* 
                      int C, float eps, float momentum, int relu, void* stream) {
   int rc = bn_check(P, C, ws, ws_bytes, "bn_fwd_train");
   if (rc) return rc;
+  const int centered = (relu >> 1) & 1;      // bit 1 of `relu`: z is stored centred on the running mean (see finalize)
+  relu &= 1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* partial = static_cast<float*>(ws);
   float* coef = partial + static_cast<size_t>(kBnBlocks) * 2 * C;
@@ -333,7 +342,7 @@ int b2u_bn_fwd_train(const void* z, const void* residual, void* y, const float* 
                                                                         nullptr, nullptr, nullptr, partial, P, C / 8, 0);
   B2U_CHECK_LAUNCH("bn_colsum");
   bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, kBnBlocks, C, P, gamma, beta, running_mean, running_var,
-                                                          save_mean, save_invstd, coef, coef + C, eps, momentum);
+                                                          save_mean, save_invstd, coef, coef + C, eps, momentum, centered);
   B2U_CHECK_LAUNCH("bn_fwd_finalize");
   const long long G = (P + kBnApplyRows - 1) / kBnApplyRows;
   bn_apply_kernel<<<static_cast<unsigned>((G * (C / 8) + 255) / 256), 256, 0, st>>>(static_cast<const uint4*>(z), static_cast<const uint4*>(residual),
@@ -350,6 +359,8 @@ int b2u_bn_fwd_train_stats(const void* z, const void* residual, void* y, const f
                            float momentum, int relu, void* stream) {
   int rc = bn_check(P, C, ws, ws_bytes, "bn_fwd_train_stats");
   if (rc) return rc;
+  const int centered = (relu >> 1) & 1;      // bit 1 of `relu`: z is stored centred on the running mean (see finalize)
+  relu &= 1;
   if (!stat_partial || stat_rows <= 0) return set_error(B2U_ERR_ARG, "bn_fwd_train_stats: statistics missing");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* partial = static_cast<float*>(ws);
@@ -357,7 +368,7 @@ int b2u_bn_fwd_train_stats(const void* z, const void* residual, void* y, const f
   bn_rows_reduce_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(stat_partial, partial, stat_rows, 2 * C);
   B2U_CHECK_LAUNCH("bn_rows_reduce");
   bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, 1, C, P, gamma, beta, running_mean, running_var,
-                                                          save_mean, save_invstd, coef, coef + C, eps, momentum);
+                                                          save_mean, save_invstd, coef, coef + C, eps, momentum, centered);
   B2U_CHECK_LAUNCH("bn_fwd_finalize");
   const long long G = (P + kBnApplyRows - 1) / kBnApplyRows;
   bn_apply_kernel<<<static_cast<unsigned>((G * (C / 8) + 255) / 256), 256, 0, st>>>(static_cast<const uint4*>(z), static_cast<const uint4*>(residual),
@@ -389,11 +400,13 @@ int b2u_bn_fwd_train_sums(const void* z, const void* residual, void* y, const fl
                           void* stream) {
   int rc = bn_check(P, C, ws, ws_bytes, "bn_fwd_train_sums");
   if (rc) return rc;
+  const int centered = (relu >> 1) & 1;      // bit 1 of `relu`: z is stored centred on the running mean (see finalize)
+  relu &= 1;
   if (!sums || P_stat < P) return set_error(B2U_ERR_ARG, "bn_fwd_train_sums: sums missing or P_stat < P");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* coef = static_cast<float*>(ws) + static_cast<size_t>(kBnBlocks) * 2 * C;
   bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, 1, C, P_stat, gamma, beta, running_mean, running_var,
-                                                          save_mean, save_invstd, coef, coef + C, eps, momentum);
+                                                          save_mean, save_invstd, coef, coef + C, eps, momentum, centered);
   B2U_CHECK_LAUNCH("bn_fwd_finalize");
   const long long G = (P + kBnApplyRows - 1) / kBnApplyRows;
   bn_apply_kernel<<<static_cast<unsigned>((G * (C / 8) + 255) / 256), 256, 0, st>>>(static_cast<const uint4*>(z), static_cast<const uint4*>(residual),

@@ -507,6 +507,10 @@ wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, i
     const float* src = first_layer ? partial + static_cast<size_t>(co) * cin_pitch + t * cin_real + ci
                                    : partial + (static_cast<size_t>(co) * taps + t) * cin_pitch + ci;
     for (int s = sl; s < splits; s += 4) acc += __ldg(src + s * split_stride);
+    // first layer with the two-term image split (im2col_first): columns [9 cin, 18 cin) carry the lo halves of the same
+    // pixels, so their partial sums belong to the same weight
+    if (first_layer == 2)
+      for (int s = sl; s < splits; s += 4) acc += __ldg(src + taps * cin_real + s * split_stride);
   }
   sred[sl][threadIdx.x & 63] = acc;
   __syncthreads();
@@ -757,7 +761,7 @@ int b2u_conv_wgrad(const void* x0, int C0, const void* x1, int C1, const void* d
     wgrad_reduce9_kernel<<<dim3(ctot / 64, Cout), 160, 0, st>>>(static_cast<const float*>(ws), dw, pl.splits, Cout, ctot);
   else
     wgrad_reduce_kernel<<<(total * rtaps + 63) / 64, 256, 0, st>>>(static_cast<const float*>(ws), dw, pl.splits, Cout, rtaps, ctot,
-                                                                   cin_real, first_cin > 0 ? 1 : 0);
+                                                                   cin_real, first_cin > 0 ? (18 * first_cin <= 64 ? 2 : 1) : 0);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(B2U_ERR_CUDA, "wgrad_reduce launch: %s", cudaGetErrorString(e));
   note_launch();

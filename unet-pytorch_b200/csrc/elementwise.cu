@@ -47,6 +47,11 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 
 // ---------------------------------------------------------------------------------------------
 // first-layer im2col: col[n,h,w,k] = x[n,c,h+r-1,w+s-1] for k = (r*3+s)*Cin + c < 9*Cin, else 0
+//
+// Where the row has room (18*Cin <= 64, i.e. the reference's 3-channel images) the image enters as a TWO-TERM bf16 split:
+// columns [0, 9Cin) hold hi = bf16(x), columns [9Cin, 18Cin) hold lo = bf16(x - hi), and the packed weights repeat in
+// the second column range, so the MMA sees the image to ~2^-17 for free.  Rounding the image to one bf16 is, alone, a
+// 5e-2 error source of the BatchNorm families' gradients on warm 512x512 fixtures (profiles/r2_precision_sites.txt).
 // ---------------------------------------------------------------------------------------------
 // Block = one 64-pixel row segment.  Phase 1: the 9*Cin <= 64 (tap, channel) planes are read with the pixel index
 // fastest across lanes (128-byte coalesced fp32 loads), two k per thread, into a [64 px][33 words] tile of bf16 pairs
@@ -63,13 +68,18 @@ im2col_first_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col
   const int row = blockIdx.x / segs;          // n * H + h
   const int n = row / H, h = row - n * H;
   const int w0 = seg * kI2cPix;
-  const int K = 9 * Cin, KP = (K + 1) / 2;    // k pairs that hold data
+  const int K = 9 * Cin;
+  const bool split = 2 * K <= 64;             // room for the lo halves
+  const int KP = ((split ? 2 * K : K) + 1) / 2;    // k pairs that hold data
   const float* img = x + static_cast<size_t>(n) * Cin * H * W;
   auto fetch = [&](int k, int pw) -> float {
+    const bool lo = split && k >= K;
+    if (lo) k -= K;
     if (k >= K) return 0.f;
     const int tap = k / Cin, c = k - tap * Cin;
     const int hh = h + tap / 3 - 1, ww = w0 + pw + tap % 3 - 1;
-    return (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(img + (static_cast<size_t>(c) * H + hh) * W + ww) : 0.f;
+    const float v = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(img + (static_cast<size_t>(c) * H + hh) * W + ww) : 0.f;
+    return lo ? v - __bfloat162float(__float2bfloat16_rn(v)) : v;
   };
   for (int i = threadIdx.x; i < KP * kI2cPix; i += 256) {
     const int kp = i / kI2cPix, pw = i - kp * kI2cPix;
@@ -115,8 +125,10 @@ __global__ void pack_weights_first_kernel(const float* __restrict__ w, __nv_bflo
   if (idx >= Cout * 64) return;
   const int co = idx / 64, k = idx % 64;
   float v = 0.f;
-  if (k < 9 * Cin) {
-    const int tap = k / Cin, c = k % Cin;
+  const int K = 9 * Cin;
+  const int kk = (2 * K <= 64 && k >= K) ? k - K : k;      // the lo half of the image split sees the same weights
+  if (kk < K) {
+    const int tap = kk / Cin, c = kk % Cin;
     v = w[(static_cast<size_t>(co) * Cin + c) * 9 + tap];
   }
   wf[idx] = __float2bfloat16_rn(v);
@@ -152,7 +164,9 @@ pack_weights_multi_kernel(const PackEntry* __restrict__ table, int n) {
       const int co = lb * 32 + i / 64, k = i % 64;
       if (co >= e.Cout) continue;
       float v = 0.f;
-      if (k < 9 * e.Cin) { const int tap = k / e.Cin, c = k % e.Cin; v = e.w[(static_cast<size_t>(co) * e.Cin + c) * 9 + tap]; }
+      const int K = 9 * e.Cin;
+      const int kk = (2 * K <= 64 && k >= K) ? k - K : k;      // lo half of the image split (im2col_first): same weights
+      if (kk < K) { const int tap = kk / e.Cin, c = kk % e.Cin; v = e.w[(static_cast<size_t>(co) * e.Cin + c) * 9 + tap]; }
       e.wf[static_cast<size_t>(co) * 64 + k] = __float2bfloat16_rn(v);
     }
     return;
@@ -584,9 +598,11 @@ __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_b
 }
 
 // NCHW fp32 -> NHWC bf16 with the channel dimension zero-padded to Cpad (multiple of 8): one thread = one pixel x 8
-// output channels; plane reads are coalesced across the pixels of a warp
+// output channels; plane reads are coalesced across the pixels of a warp.  When the row has room (Cpad >= 2C) channels
+// [C, 2C) receive lo = bf16(x - bf16(x)), the second term of a two-term bf16 split of the image; the engines repeat the
+// first conv's weights over that range (graph.py), so the tensor cores see the image to ~2^-17.
 __global__ void nchw_f32_to_nhwc_bf16_padded_kernel(const float* __restrict__ x, uint4* __restrict__ y, int C, long long HW,
-                                                    int Cpad8) {
+                                                    int Cpad8, int split) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // pixel index within the image
   const int n = blockIdx.z, q = blockIdx.y;
   if (i >= HW) return;
@@ -594,7 +610,10 @@ __global__ void nchw_f32_to_nhwc_bf16_padded_kernel(const float* __restrict__ x,
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int c = q * 8 + k;
-    f[k] = c < C ? __ldg(x + (static_cast<size_t>(n) * C + c) * HW + i) : 0.f;
+    const bool lo = split && c >= C && c < 2 * C;
+    const int cs = lo ? c - C : c;
+    const float v = cs < C ? __ldg(x + (static_cast<size_t>(n) * C + cs) * HW + i) : 0.f;
+    f[k] = lo ? v - __bfloat162float(__float2bfloat16_rn(v)) : (c < C ? v : 0.f);
   }
   y[(static_cast<size_t>(n) * HW + i) * Cpad8 + q] = pack8(f);
 }
@@ -608,7 +627,8 @@ int b2u_nchw_f32_to_nhwc_bf16_padded(const float* x, void* y, int N, int C, int 
   if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || Cpad < C || Cpad % 8 != 0) return set_error(B2U_ERR_SHAPE, "nchw->nhwc padded: bad shape");
   const long long HW = static_cast<long long>(H) * W;
   dim3 grid(static_cast<unsigned>((HW + 255) / 256), Cpad / 8, N);
-  nchw_f32_to_nhwc_bf16_padded_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<uint4*>(y), C, HW, Cpad / 8);
+  nchw_f32_to_nhwc_bf16_padded_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<uint4*>(y), C, HW, Cpad / 8,
+                                                                                           Cpad >= 2 * C ? 1 : 0);
   B2U_CHECK_LAUNCH("nchw_f32_to_nhwc_bf16_padded");
   return 0;
 }

@@ -137,6 +137,7 @@ class UNetEngine:
         # BatchNorm statistics from the conv epilogue (one pass over z less); only where the reduction is long enough for the
         # extra epilogue work to hide behind the main loop (scripts/ab_fuse_bnstats.py)
         self.fuse_bn_stats = True
+        self.center_pre_bn = os.environ.get("B2U_CENTER_PRE_BN", "1") == "1"      # pre-BatchNorm tensors stored centred on the running mean
         self.sync_bn_group = None        # torch.distributed group: BatchNorm statistics over all ranks (SyncBatchNorm)
         self.bn_stats_min_k = 1024
         self.bn_stats_min_cout = 256
@@ -291,6 +292,15 @@ class UNetEngine:
             A[c.name] = out
             return out
         z = self._buf("z:" + c.name, (n, h, w, c.cout_p))
+        rm, rv = params[c.bn + ".running_mean"], params[c.bn + ".running_var"]
+        # Training: z is stored CENTRED on the running mean -- the shift rides in the conv bias (fp32, before the bf16
+        # rounding), BatchNorm is shift-invariant, and only the running-mean update adds it back.  A channel whose mean is large
+        # against its spread otherwise loses |mean|/std * 2^-9 of relative accuracy in bf16 (the dominant error site of the
+        # depthwise nets on warm weights, profiles/r2_precision_sites.txt); at initialisation the running mean is 0: no change.
+        centered = training and self.center_pre_bn and ops.act_dtype() == torch.bfloat16
+        if centered:
+            rmp0 = self._padded_vec("rm:" + c.bn, rm, c.cout_p)
+            bias = torch.sub(bias, rmp0, out=self._buf("bc:" + c.name, (c.cout_p,), torch.float32))
         # training: the conv epilogue also emits the BatchNorm statistics of z (per-tile sums), so BatchNorm skips its
         # statistics pass over z
         stats, rows = None, 0
@@ -303,12 +313,11 @@ class UNetEngine:
         beta = self._padded_vec("bt:" + c.bn, params[c.bn + ".bias"], c.cout_p)
         out = self._buf(c.name, (n, h, w, c.cout_p))
         ws = self._workspace("bn", ops.lib().b2u_bn_workspace(c.cout_p))
-        rm, rv = params[c.bn + ".running_mean"], params[c.bn + ".running_var"]
         if training and self.sync_bn_group is not None:
             rmp = self._padded_vec("rm:" + c.bn, rm, c.cout_p)
             rvp = self._padded_vec("rv:" + c.bn, rv, c.cout_p, fill=1.0)
             _, mean, invstd = ops.bn_fwd_train_sync(z, gamma, beta, rmp, rvp, self.sync_bn_group, self.eps, self.momentum, True,
-                                                    out=out, ws=ws)
+                                                    out=out, ws=ws, centered=centered)
             if c.cout_p != c.cout or rmp is not rm:
                 rm.copy_(rmp[:c.cout]); rv.copy_(rvp[:c.cout])
             nbt = params.get(c.bn + ".num_batches_tracked")
@@ -318,12 +327,12 @@ class UNetEngine:
         elif training:
             if c.cout_p == c.cout:
                 _, mean, invstd = ops.bn_fwd_train(z, gamma, beta, rm, rv, self.eps, self.momentum, True, out=out, ws=ws,
-                                                   stats=stats, stat_rows=rows)
+                                                   stats=stats, stat_rows=rows, centered=centered)
             else:
                 rmp = self._padded_vec("rm:" + c.bn, rm, c.cout_p)
                 rvp = self._padded_vec("rv:" + c.bn, rv, c.cout_p, fill=1.0)
                 _, mean, invstd = ops.bn_fwd_train(z, gamma, beta, rmp, rvp, self.eps, self.momentum, True, out=out, ws=ws,
-                                                   stats=stats, stat_rows=rows)
+                                                   stats=stats, stat_rows=rows, centered=centered)
                 rm.copy_(rmp[:c.cout])
                 rv.copy_(rvp[:c.cout])
             nbt = params.get(c.bn + ".num_batches_tracked")

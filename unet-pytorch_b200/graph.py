@@ -26,9 +26,9 @@ ReLU handling: a tensor produced by a conv with fused ReLU is marked `fused_relu
 applies the mask (y > 0) on the way (dgrad epilogue / upsample adjoint / head dgrad), so its gradient is always wrt
 the pre-activation.  BatchNorm outputs are plain: the bn instruction's own backward applies its ReLU mask.
 """
-import struct
-
 import functools
+import os
+import struct
 
 import torch
 
@@ -40,12 +40,13 @@ def pad64(c):
 
 
 class _T:
-    __slots__ = ("data", "grad", "fused_relu", "needs_grad", "aux", "stats", "folded")
+    __slots__ = ("data", "grad", "fused_relu", "needs_grad", "aux", "stats", "folded", "centered")
 
     def __init__(self, data, fused_relu=False, needs_grad=False):
         self.data, self.grad, self.fused_relu, self.needs_grad, self.aux = data, None, fused_relu, needs_grad, None
         self.stats = None      # (fp32 per-tile column sums, rows) when the producing conv emitted BatchNorm statistics
         self.folded = False    # eval mode: this conv output already is the BatchNorm (+ReLU) output
+        self.centered = False  # training: stored as z - running_mean of the BatchNorm that reads it
 
 
 def resnet50_unet_program(num_classes):
@@ -241,6 +242,11 @@ class GraphEngine:
         self.saved = None
         self.has_stem = any(i["op"] == "stem" for i in program)
         self.pk = {i["w"]: i for i in program if i["op"] == "conv" and i.get("pk")}     # pixel-packed 1x1 convs
+        # convs that read the image: the input instruction stores the image as a two-term bf16 split (hi in channels [0, C),
+        # lo = x - hi in [C, 2C)), so their weights are repeated over the second channel range and the MMA sees the image
+        # to ~2^-17 (a single bf16 rounding of the image alone costs these nets 5e-2 of gradient accuracy)
+        inputs = {i["out"]: i["c"] for i in program if i["op"] == "input"}
+        self.image_convs = {i["w"]: inputs[i["x"]] for i in program if i["op"] == "conv" and i["x"] in inputs and 2 * inputs[i["x"]] <= 64}
         self.dropout_override = None
         # db from the wgrad kernel's bias warps instead of a separate pass over dz: measured on one box (scripts/ab_fuse_bias.py)
         # it does not change the step time (the extra smem reads slow the bias-owning work units), so it stays off
@@ -250,6 +256,11 @@ class GraphEngine:
         # Unet-ResNet50 but loses 0.7-1.3 ms on the full-resolution, short-K layers of the other BatchNorm nets
         self.fuse_bn_stats = True
         self.sync_bn_group = None       # torch.distributed group: BatchNorm statistics over all ranks (SyncBatchNorm)
+        # Training: a conv output read only by a BatchNorm is stored CENTRED on that BatchNorm's running mean (the shift rides
+        # in the conv bias, in fp32, before the bf16 rounding; BatchNorm is shift-invariant; the running-mean update adds it
+        # back).  Without it a channel with |mean| >> std loses |mean|/std * 2^-9 of relative accuracy in bf16 -- the dominant
+        # error site of the depthwise nets on warm weights (profiles/r2_precision_sites.txt).
+        self.center_pre_bn = os.environ.get("B2U_CENTER_PRE_BN", "1") == "1"
         self.bn_stats_min_k = 1024
         self.bn_stats_min_cout = 256
         readers = {}
@@ -260,6 +271,7 @@ class GraphEngine:
         self._pre_bn = {name for name, ops_ in readers.items() if ops_ == ["bn"]}      # tensors read only as a BN input
         # eval-mode folding: conv output -> the BatchNorm (without residual) that is its only reader
         self._fold_bn = {i["z"]: i for i in program if i["op"] == "bn" and i["z"] in self._pre_bn and not i["res"]}
+        self._bn_reader = {i["z"]: i for i in program if i["op"] == "bn" and i["z"] in self._pre_bn}      # conv output -> its BatchNorm
 
     # ------------------------------------------------------------------ static description
     def param_shapes(self):
@@ -354,6 +366,13 @@ class GraphEngine:
         return ops.bn_fold(gamma, beta, rmp, rvp, cb, self.eps, scale=self._buf("fs:" + bnn, (cp,), torch.float32),
                            bias=self._buf("fb:" + bnn, (cp,), torch.float32))
 
+    def _center_shift(self, ins, params, training, width):
+        """Padded running mean of the BatchNorm that is the only reader of this conv's output (training, bf16 path), or None."""
+        bn_ins = self._bn_reader.get(ins["out"])
+        if bn_ins is None or not training or not self.center_pre_bn or ops.act_dtype() != torch.bfloat16:
+            return None
+        return self._padded("rm:" + bn_ins["bn"], params[bn_ins["bn"] + ".running_mean"], (width,))
+
     def _tiled(self, key, t, width, f):
         """fp32 vector zero-padded to `width` and repeated f times (bias of a pixel-packed conv)."""
         b = self._bufs.get(key)
@@ -382,6 +401,14 @@ class GraphEngine:
                 cout, c0, c1, taps = self.convs[n]
                 c0p, c1p, coutp = pad64(c0), (pad64(c1) if c1 else 0), pad64(cout)
                 src = params[n]
+                if n in self.image_convs and n not in self.pk:      # [w | w] over the hi / lo halves of the image split
+                    ci = self.image_convs[n]
+                    k = 3 if taps == 9 else 1
+                    src = self._bufs.get("w2:" + n)
+                    if src is None or tuple(src.shape) != (cout, 2 * ci, k, k):
+                        src = torch.zeros((cout, 2 * ci, k, k), dtype=torch.float32, device=dev)
+                        self._bufs["w2:" + n] = src
+                    c0 = 2 * ci
                 if n in self.pk:            # the view problem: block-diagonal weights over f pixels (built below)
                     f, kind = self.pk[n]["pix"], self.pk[n]["pk"]
                     if kind == "to":        # dense 64-padded inputs -> packed `cout` (= mid) channels
@@ -404,6 +431,10 @@ class GraphEngine:
                 start += ((cout + 31) // 32) * ((c0 + c1 + 31) // 32)
             self._pack_table = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
             self._pack_total, self._pack_key = start, key
+        for n, ci in self.image_convs.items():   # refresh [w | w]
+            if n not in self.pk:
+                w2, w = self._bufs["w2:" + n], params[n]
+                w2[:, :ci].copy_(w); w2[:, ci:].copy_(w)
         for n, ins in self.pk.items():          # refresh the block-diagonal fp32 weights kron(I_f, W) of the packed convs
             f, w2, w = ins["pix"], self._bufs["w2:" + n], params[n]
             midp = 64 // f
@@ -412,6 +443,8 @@ class GraphEngine:
                 c0p, c1p = pad64(c0r), (pad64(c1r) if c1r else 0)
                 for k in range(f):
                     w2[k * midp:k * midp + mid, k * c0p:k * c0p + c0r].copy_(w[:, :c0r])
+                    if n in self.image_convs:      # lo half of the image split: same weights
+                        w2[k * midp:k * midp + mid, k * c0p + c0r:k * c0p + 2 * c0r].copy_(w[:, :c0r])
                     if c1r:
                         w2[k * midp:k * midp + mid, f * c0p + k * c1p:f * c0p + k * c1p + c1r].copy_(w[:, c0r:])
             else:
@@ -447,8 +480,11 @@ class GraphEngine:
             if op == "stem":
                 col = ops.im2col_stem(x, out=self._buf("stem.col", (N, H // 2, W // 2, 192)))
                 z = self._buf(ins["out"], (N, H // 2, W // 2, 64))
-                ops.conv_fprop(col, self._stem_wf, None, 64, taps=1, relu=False, out=z)
+                shift = self._center_shift(ins, params, training, 64)
+                sbias = torch.neg(shift, out=self._buf("bc:" + ins["w"], (64,), torch.float32)) if shift is not None else None
+                ops.conv_fprop(col, self._stem_wf, sbias, 64, taps=1, relu=False, out=z)
                 t = _T(z, needs_grad=ins["w"] in trainable)
+                t.centered = shift is not None
                 t.aux = col
                 T[ins["out"]] = t
             elif op == "input":
@@ -466,6 +502,9 @@ class GraphEngine:
                     else:
                         z = self._buf(ins["out"], (n, h, w, pad64(ins["cout"])))
                         bias = self._tiled("b2:" + ins["w"], params[ins["bias"]], pad64(ins["cout"]), f)
+                    shift = self._center_shift(ins, params, training, z.shape[3])
+                    if shift is not None:
+                        bias = torch.sub(bias, self._tiled("c2:" + ins["w"], shift, z.shape[3], f), out=self._buf("bc:" + ins["w"], (bias.numel(),), torch.float32))
                     fold = self._fold_bn.get(ins["out"]) if (not training and not save) else None
                     if fold is not None:        # eval: BatchNorm (+ReLU) folded into the epilogue, vectors tiled like the bias
                         sc, bs = self._folded_bn(fold, params, params[ins["bias"]], z.shape[3])
@@ -479,10 +518,15 @@ class GraphEngine:
                     ng = xin.needs_grad or (x1 is not None and x1.needs_grad) or ins["w"] in trainable or (ins["bias"] in trainable)
                     t = _T(z, needs_grad=ng)
                     t.folded = fold is not None
+                    t.centered = shift is not None
                     T[ins["out"]] = t
                     continue
                 coutp = pad64(ins["cout"])
                 bias = self._padded("b:" + ins["w"], params[ins["bias"]], (coutp,)) if ins["bias"] else None
+                shift = self._center_shift(ins, params, training, coutp)
+                if shift is not None:
+                    cb = self._buf("bc:" + ins["w"], (coutp,), torch.float32)
+                    bias = torch.sub(bias, shift, out=cb) if bias is not None else torch.neg(shift, out=cb)
                 aux = None
                 stats = None
                 # folding is for pure inference: an eval-mode forward that will be back-propagated (model.eval() +
@@ -530,6 +574,7 @@ class GraphEngine:
                 t = _T(z, fused_relu=ins["relu"], needs_grad=ng)
                 t.aux = aux
                 t.stats = stats
+                t.centered = shift is not None
                 T[ins["out"]] = t
             elif op == "bn":
                 zt = T[ins["z"]]
@@ -549,11 +594,12 @@ class GraphEngine:
                     if self.sync_bn_group is not None:
                         _, mean, invstd = ops.bn_fwd_train_sync(zt.data, gamma, beta, rmp, rvp, self.sync_bn_group, self.eps,
                                                                 self.momentum, ins["relu"], out=y, ws=ws,
-                                                                residual=res.data if res else None)
+                                                                residual=res.data if res else None, centered=zt.centered)
                     else:
                         _, mean, invstd = ops.bn_fwd_train(zt.data, gamma, beta, rmp, rvp, self.eps, self.momentum, ins["relu"],
                                                            out=y, ws=ws, residual=res.data if res else None,
-                                                           stats=zt.stats[0] if zt.stats else None, stat_rows=zt.stats[1] if zt.stats else 0)
+                                                           stats=zt.stats[0] if zt.stats else None, stat_rows=zt.stats[1] if zt.stats else 0,
+                                                           centered=zt.centered)
                     if cp != c:
                         rm.copy_(rmp[:c]); rv.copy_(rvp[:c])
                     nbt = params.get(bnn + ".num_batches_tracked")
@@ -841,6 +887,8 @@ class GraphEngine:
                                     gw[:, :c0r].copy_(blk[:, k * c0p:k * c0p + c0r])
                                 else:
                                     gw[:, :c0r].add_(blk[:, k * c0p:k * c0p + c0r])
+                                if ins["w"] in self.image_convs:      # + the lo half of the image split
+                                    gw[:, :c0r].add_(blk[:, k * c0p + c0r:k * c0p + 2 * c0r])
                                 if c1r:
                                     src = blk[:, f * c0p + k * c1p:f * c0p + k * c1p + c1r]
                                     if k == 0:
@@ -893,6 +941,8 @@ class GraphEngine:
                         ops.conv_wgrad(xw, dz, taps=taps, x1=x1.data if x1 else None, dw=tmp, ws=ws)
                         gw = grads[ins["w"]]
                         gw[:, :c0r].copy_(tmp[:cout, :c0r])
+                        if ins["w"] in self.image_convs:          # + the lo half of the image split
+                            gw[:, :c0r].add_(tmp[:cout, c0r:2 * c0r])
                         if c1r:
                             gw[:, c0r:].copy_(tmp[:cout, c0p:c0p + c1r])
                 if has(ins["bias"]) and ins["out"] in self._pre_bn:

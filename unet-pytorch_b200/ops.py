@@ -296,9 +296,12 @@ def upsample2x_bwd(dup, ylow=None, out=None):
 
 # ---------------------------------------------------------------------------------------------- batch norm
 def bn_fwd_train(z, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1, relu=True, out=None, ws=None,
-                 residual=None, stats=None, stat_rows=0):
+                 residual=None, stats=None, stat_rows=0, centered=False):
     """Returns (y, save_mean, save_invstd); running statistics are updated in place (torch semantics).
-    stats/stat_rows: per-tile column sums written by conv_fprop(stats=...) -- skips the statistics pass over z."""
+    stats/stat_rows: per-tile column sums written by conv_fprop(stats=...) -- skips the statistics pass over z.
+    centered: z holds conv(x) + bias - running_mean (the producing conv folded the shift into its bias, so the bf16 rounding of
+    z is relative to the channel's spread, not its mean); only the running-mean update needs to know."""
+    rflag = (1 if relu else 0) | (2 if centered else 0)
     _req(z, ACT, "z")
     C = z.shape[-1]
     P = z.numel() // C
@@ -311,17 +314,17 @@ def bn_fwd_train(z, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0
     invstd = torch.empty((C,), dtype=torch.float32, device=z.device)
     if stats is None:
         check(lib().b2u_bn_fwd_train(ptr(z), ptr(residual), ptr(out), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(mean),
-                                     ptr(invstd), ptr(ws), ws.numel() * ws.element_size(), P, C, eps, momentum, 1 if relu else 0,
+                                     ptr(invstd), ptr(ws), ws.numel() * ws.element_size(), P, C, eps, momentum, rflag,
                                      stream_ptr()))
     else:
         check(lib().b2u_bn_fwd_train_stats(ptr(z), ptr(residual), ptr(out), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
                                            ptr(mean), ptr(invstd), ptr(stats), stat_rows, ptr(ws), ws.numel() * ws.element_size(), P, C,
-                                           eps, momentum, 1 if relu else 0, stream_ptr()))
+                                           eps, momentum, rflag, stream_ptr()))
     return out, mean, invstd
 
 
 def bn_fwd_train_sync(z, gamma, beta, running_mean, running_var, group, eps=1e-5, momentum=0.1, relu=True, out=None, ws=None,
-                      residual=None):
+                      residual=None, centered=False):
     """SyncBatchNorm forward (train.py:335-336): this rank's column sums, one all-reduce of 2C floats over `group`, apply
     with the global statistics.  Every rank is assumed to hold the same number of rows (DistributedSampler batches)."""
     import torch.distributed as dist
@@ -341,7 +344,7 @@ def bn_fwd_train_sync(z, gamma, beta, running_mean, running_var, group, eps=1e-5
     invstd = torch.empty((C,), dtype=torch.float32, device=z.device)
     check(lib().b2u_bn_fwd_train_sums(ptr(z), ptr(residual), ptr(out), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
                                       ptr(mean), ptr(invstd), ptr(sums), P * world, ptr(ws), ws.numel() * ws.element_size(), P, C, eps,
-                                      momentum, 1 if relu else 0, stream_ptr()))
+                                      momentum, (1 if relu else 0) | (2 if centered else 0), stream_ptr()))
     return out, mean, invstd
 
 
