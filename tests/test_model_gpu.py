@@ -233,7 +233,7 @@ def test_full_size_step_properties(b2u, cuda_device):
 # The CUDA path is therefore held to (a) tight per-kernel BatchNorm tests (tests/test_kernels_gpu.py), (b) the
 # bf16-storage model as yardstick here, (c) exact agreement of everything that is not rounding-limited: running
 # statistics, loss value, eval-mode logits.
-TRAD_BOUNDS = {"nc4_focaldice": (8e-2, 3e-1), "nc21_cedice": (8e-2, 3e-1)}      # (logits, gradients) vs the fp32 oracle, absolute
+TRAD_BOUNDS = {"nc4_focaldice": (7e-2, 3e-1), "nc21_cedice": (7e-2, 3.5e-1)}      # (logits, gradients) vs the fp32 oracle, absolute
 TRAD_CASES = [("nc4_focaldice", 4, 2, 64, 64, 3, [1, 15, 1.5, 2], True, True), ("nc21_cedice", 21, 2, 32, 64, 4, [1] * 21, True, False)]
 
 
@@ -327,7 +327,7 @@ def test_resnet50_unet_dropin(b2u, cuda_device, golden_dir):
     grads = {k: p.grad for k, p in model.named_parameters()}
     assert all(v is not None and torch.isfinite(v).all() for v in grads.values())
     assert _global_rel(grads, g32) <= 1.5 * noise_g and _global_rel(grads, gbf) <= 1.2 * noise_g
-    _direct("unet_resnet50 nc21", outputs, z32, grads, g32, 5e-2, 3e-1)
+    _direct("unet_resnet50 nc21", outputs, z32, grads, g32, 1e-2, 2e-1)
     # decoder-side tensors are not behind a BatchNorm backward: plain bf16 accuracy
     for k in ("final.weight", "final.bias", "up_conv.3.weight", "up_conv.1.weight", "up_concat1.conv2.weight"):
         assert rel(grads[k], g32[k]) <= 2e-2, k
@@ -382,6 +382,9 @@ ULU_CASES = [("ultralight", "UltraLightweightUnet", "nc21_cedice"), ("ultralight
              ("ultralight_large_optimized", "UltraLightweightUnet_large_optimized", "nc21_cedice")]
 
 
+ULU_BOUNDS = {"ultralight": (3e-2, 1.2e-1), "ultralight_large": (5e-2, 2e-1), "ultralight_large_optimized": (8e-2, 3e-1)}   # (logits, gradients), absolute
+
+
 @pytest.mark.parametrize("variant,cls,tag", ULU_CASES)
 def test_ultralight_unet_dropin(b2u, cuda_device, golden_dir, variant, cls, tag):
     """nets/UltraLightweightUnet*.py drop-ins against the reference's golden forward/backward (train-mode BatchNorm,
@@ -421,7 +424,7 @@ def test_ultralight_unet_dropin(b2u, cuda_device, golden_dir, variant, cls, tag)
     live = {k: v for k, v in grads.items() if not (k.endswith(".conv.0.bias") or k.endswith("wise.bias"))}    # zero-gradient biases
     assert _global_rel(live, {k: g32[k] for k in live}) <= 1.5 * noise_g
     assert _global_rel(live, {k: gbf[k] for k in live}) <= 1.2 * noise_g
-    _direct(f"{variant} {tag}", outputs, z32, live, {k: g32[k] for k in live}, 8e-2, 3e-1)
+    _direct(f"{variant} {tag}", outputs, z32, live, {k: g32[k] for k in live}, *ULU_BOUNDS[variant])
     for k in ("final.weight", "final.bias"):      # no BatchNorm backward in between: bounded by the head input's forward noise
         assert rel(grads[k], g32[k]) <= max(2e-2, 2 * noise_z), k
     for name, b in model.named_buffers():
@@ -590,7 +593,7 @@ def test_lightweight_unet_dropin(b2u, cuda_device, golden_dir, tag):
     assert all(grads[k].abs().max().item() == 0 for k in grads if pre_bn_bias(k))      # exact zero by the BN identity
     assert _global_rel(live, {k: g32[k] for k in live}) <= 1.5 * noise_g
     assert _global_rel(live, {k: gbf[k] for k in live}) <= 1.2 * noise_g
-    _direct("lightweight " + tag, outputs, z32, live, {k: g32[k] for k in live}, 8e-2, 3e-1)
+    _direct("lightweight " + tag, outputs, z32, live, {k: g32[k] for k in live}, 4e-2, 2.2e-1)
     for k in ("final_conv.3.weight", "final_conv.3.bias"):
         assert rel(grads[k], g32[k]) <= max(2e-2, 2 * noise_z), k
     model.eval()
@@ -676,7 +679,9 @@ def test_device_input_pipeline_uint8(b2u, cuda_device):
     b.stage(raw.pin_memory(), lab.pin_memory())
     rb = b.train_step().cpu()
     assert torch.allclose(ra, rb, rtol=2e-3, atol=1e-5)
-    assert _global_rel(b.grads, {k: v.cpu() for k, v in a.grads.items()}) <= 5e-3
+    # x * (1/255) on the device vs round(x * 255) / 255 on the host differ by one fp32 ulp, which the two-term image split now
+    # carries into the network; the step amplifies it like any other 1-ulp difference
+    assert _global_rel(b.grads, {k: v.cpu() for k, v in a.grads.items()}) <= 1e-2
 
 
 def test_reference_training_wrappers(b2u, cuda_device):

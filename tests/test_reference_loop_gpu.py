@@ -105,4 +105,4 @@ def test_reference_fit_one_epoch_runs_on_the_dropin(b2u, cuda_device, backbone, 
     num = sum(((after[k] - params[k]) - (ref_after[k] - params[k])).double().pow(2).sum().item() for k in params)
     den = sum((ref_after[k] - params[k]).double().pow(2).sum().item() for k in params)
     assert (num / den) ** 0.5 <= 0.15                  # Adam's sign-like first steps amplify bf16 gradient noise on tiny entries
-    assert max((after[k] - ref_after[k]).abs().max().item() for k in params) <= 4.5e-4     # <= ~4 steps x lr
+    assert max((after[k] - ref_after[k]).abs().max().item() for k in params) <= 8.1e-4     # <= 2 x 4 steps x lr (opposite signs on a ~0 gradient)
