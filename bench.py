@@ -97,6 +97,183 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+
+class OperandBytes:
+    """Counts, for ONE step, the bytes of every tensor operand that goes through the ops.* wrappers (inputs, outputs, `out=`
+    buffers; workspaces excluded; each tensor once per call) -- the ALGORITHMIC HBM traffic of the step as the engine issues
+    it: what `achieved HBM GB/s` of the memory-bound model families is quoted on."""
+    SKIP_KW = {"ws"}
+
+    def __init__(self, ops):
+        self.ops, self.total, self.saved = ops, 0, {}
+
+    def _count(self, args, kwargs, ret):
+        import torch
+        seen = set()
+
+        def visit(x):
+            if isinstance(x, torch.Tensor) and x.is_cuda:
+                if x.data_ptr() not in seen:
+                    seen.add(x.data_ptr())
+                    self.total += x.numel() * x.element_size()
+            elif isinstance(x, (tuple, list)):
+                for y in x:
+                    visit(y)
+        visit(args)
+        for k, v in kwargs.items():
+            if k not in self.SKIP_KW:
+                visit(v)
+        visit(ret)
+
+    def __enter__(self):
+        import types
+        for name in dir(self.ops):
+            fn = getattr(self.ops, name)
+            if isinstance(fn, types.FunctionType) and fn.__module__ == self.ops.__name__ and not name.startswith("_") and name not in (
+                    "act_dtype", "set_timer", "set_validation_fp32", "conv_stat_rows", "lib", "check", "ptr", "stream_ptr"):
+                self.saved[name] = fn
+
+                def wrapped(*a, __fn=fn, **kw):
+                    r = __fn(*a, **kw)
+                    self._count(a, kw, r)
+                    return r
+                setattr(self.ops, name, wrapped)
+        return self
+
+    def __exit__(self, *exc):
+        for name, fn in self.saved.items():
+            setattr(self.ops, name, fn)
+
+
+def _ev_ms(fn, iters, warm):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def side_measurements(b2u, ops, dev, peaks):
+    """BASELINE configs[2..4] next to the headline line, compact: ~40 s.
+      train          Unet-ResNet50 (21 classes), LightweightUnet, UltraLightweightUnet_large (2 classes): batch 16, 512x512, full
+                     training step; img/s and achieved HBM GB/s of the step's algorithmic operand bytes (OperandBytes)
+      fps            predict.py fps mode (unet.py:240-257): uint8 frame(s) H2D -> /255 -> forward -> per-pixel class -> uint8 mask
+                     D2H, batch 1 (eager launches, and replayed from a CUDA graph) and batch 64
+      fast_hist      get_miou's confusion matrix over 1000 distinct 512x512 uint8 mask pairs (524 MB > L2), n = 21 and 2
+      gpu_library_baseline   the same headline step written with stock torch.nn and run by PyTorch eager + cuDNN (bf16 autocast,
+                     channels_last, cudnn.benchmark, fused Adam) on this GPU: the library kernels to beat"""
+    import numpy as np
+    import torch
+    out = {}
+    # ---- other families
+    train = {}
+    for model, C in (("unet_resnet50", 21), ("lightweight", 2), ("ultralight_large", 2)):
+        tr = b2u.UnetTrainer(num_classes=C, device=dev, model=model, lr=1e-4)
+        imgs, pngs = b2u.synthetic.make_inputs(BATCH_PER_GPU, C, HW, HW, seed=3)
+        imgs, pngs = imgs.to(dev), pngs.to(dev)
+        ms = _ev_ms(lambda: tr.train_step(imgs, pngs), 8, 3)
+        with OperandBytes(ops) as ob:
+            tr.train_step(imgs, pngs)
+        torch.cuda.synchronize()
+        gb = ob.total / 1e9
+        train[model] = {"classes": C, "img_per_s": BATCH_PER_GPU * 1e3 / ms, "ms_per_step": ms, "algorithmic_gb_per_step": gb,
+                        "achieved_hbm_gbps": gb / (ms / 1e3), "frac_of_hbm_peak": gb / (ms / 1e3) / peaks["hbm"]}
+        tr.engine.release()
+        del tr
+        torch.cuda.empty_cache()
+    out["train_batch16_512"] = train
+    # ---- fps mode
+    C = NUM_CLASSES
+    model = b2u.Unet(num_classes=C)
+    model.load_state_dict(b2u.synthetic.make_params(C))
+    model = model.to(dev).eval()
+    fps = {}
+    for B in (1, 64):
+        frames = torch.randint(0, 256, (B, HW, HW, 3), dtype=torch.uint8).pin_memory()
+        dframes = torch.empty_like(frames, device=dev)
+        x32 = torch.empty((B, 3, HW, HW), dtype=torch.float32, device=dev)
+        mask = torch.empty((B, HW, HW), dtype=torch.uint8, device=dev)
+        host = torch.empty((B, HW, HW), dtype=torch.uint8).pin_memory()
+
+        def body():
+            with torch.no_grad():
+                ops.u8hwc_to_nchw_f32(dframes, out=x32)
+                ops.argmax_hist(model(x32), pred=mask)
+
+        def frame():
+            dframes.copy_(frames, non_blocking=True)
+            body()
+            host.copy_(mask, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        ms = _ev_ms(frame, 30 if B == 1 else 4, 3)
+        fps[f"b{B}"] = {"fps": B * 1e3 / ms, "ms_per_call": ms, "h2d_bytes": frames.numel(), "d2h_bytes": host.numel()}
+        if B == 1:
+            try:        # the ~30 launches of a batch-1 frame replayed from one CUDA graph
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    body()
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    body()
+                ref_mask = mask.clone()
+
+                def gframe():
+                    dframes.copy_(frames, non_blocking=True)
+                    graph.replay()
+                    host.copy_(mask, non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+                msg = _ev_ms(gframe, 30, 3)
+                fps["b1_cuda_graph"] = {"fps": 1e3 / msg, "ms_per_call": msg, "same_mask": bool(torch.equal(mask, ref_mask))}
+            except Exception as e:      # measurement aid only
+                fps["b1_cuda_graph"] = {"error": str(e)[:200]}
+    out["fps_mode_uint8_frames"] = fps
+    for e in model._engines.values():
+        e.release()
+    del model
+    torch.cuda.empty_cache()
+    # ---- fast_hist over 1000 distinct masks
+    hist_res = {}
+    for n in (21, 2):
+        g = torch.Generator(device=dev).manual_seed(n)
+        gt = torch.randint(0, n, (1000, HW, HW), dtype=torch.uint8, device=dev, generator=g)
+        pred = torch.where(torch.rand((1000, HW, HW), device=dev, generator=g) < 0.2,
+                           torch.randint(0, n, (1000, HW, HW), dtype=torch.uint8, device=dev, generator=g), gt)
+        gt = torch.where(torch.rand((1000, HW, HW), device=dev, generator=g) < 0.03, torch.full_like(gt, 255), gt)
+        hist = torch.zeros(n * n + 1, dtype=torch.int64, device=dev)
+        ms_one = _ev_ms(lambda: ops.fast_hist_accumulate(gt.reshape(-1), pred.reshape(-1), n, hist), 5, 2)
+        pairs = [(gt[i].reshape(-1), pred[i].reshape(-1)) for i in range(1000)]
+        table = ops.HistTable(pairs, dev)            # device pointer table, built once per evaluation set
+        ms_tab = _ev_ms(lambda: ops.fast_hist_batch(table, n, hist), 5, 2)
+        hist.zero_()
+        ops.fast_hist_batch(table, n, hist)
+        got = hist.cpu().numpy()
+        keep = gt < n
+        want = torch.bincount(gt[keep].long() * n + pred[keep].long(), minlength=n * n).cpu().numpy()
+        gbytes = 2 * gt.numel() / 1e9
+        hist_res[f"n{n}"] = {"masks": 1000, "bit_exact_vs_bincount": bool(got[-1] == 0 and np.array_equal(got[:-1], want)),
+                             "one_call_ms": ms_one, "one_call_gbps": gbytes / (ms_one / 1e3), "frac_of_hbm_peak": gbytes / (ms_one / 1e3) / peaks["hbm"],
+                             "pointer_table_ms": ms_tab, "pointer_table_gbps": gbytes / (ms_tab / 1e3), "masks_per_s": 1e6 / ms_tab}
+        del gt, pred, pairs, keep, table
+        torch.cuda.empty_cache()
+    out["fast_hist_1k_masks_512"] = hist_res
+    # ---- library yardstick
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import torch_eager_baseline as TE
+        out["gpu_library_baseline"] = TE.measure(steps=8, batch=BATCH_PER_GPU)
+    except Exception as e:
+        out["gpu_library_baseline"] = {"error": str(e)[:200]}
+    return out
+
+
 def variant_cpu_img_per_s(model, num_classes, batch=2, hw=HW, steps=1, warmup=1, threads=None):
     """cpu_baseline leg of the side measurements (scripts/variants_bench.py): the oracle port of another model family's
     forward + CE + Dice + backward on this box's host cores, `batch` images per step -> img/s."""
@@ -337,12 +514,24 @@ def run_ours(args):
     barrier()
     ms_e2e_u8 = max_over_ranks(u0.elapsed_time(u1))
 
+    # data-parallel invariant: after all these steps every rank must hold bit-identical parameters (train.py:346: DDP)
+    dp_diff = None
     if world > 1:
+        ref_p = trainer.flat_param.clone()
+        dist.broadcast(ref_p, src=0)
+        d = (trainer.flat_param - ref_p).abs().max().reshape(1)
+        dist.all_reduce(d, op=dist.ReduceOp.MAX)
+        dp_diff = float(d.item())
         dist.barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    variants = None
+    if world == 1 and not args.no_variants:
+        trainer.engine.release()
+        torch.cuda.empty_cache()
+        variants = side_measurements(b2u, ops, dev, peaks)
 
     imgs_total = B * world * K
     value = imgs_total / (ms_total / 1e3)
@@ -392,6 +581,10 @@ def run_ours(args):
         "model_tflops": value * TRAIN_GFLOP_PER_IMG / 1e3 / world,
         "loss": loss_val[0], "f_score": loss_val[1],
     }
+    if dp_diff is not None:
+        line["dp_param_max_diff"] = dp_diff          # max over ranks of |param - rank 0's param| after the run: must be 0
+    if variants is not None:
+        line["variants"] = variants
     if world == 1 and not args.no_cpu_baseline:
         v, s_per_step, threads, batch, kind = cpu_path_img_per_s(2, 1)
         what = "the unmodified reference (baseline/_ref: nets.unet.Unet + CE_Loss + Dice_loss + f_score)" if kind == "reference" else "the oracle port"
@@ -411,6 +604,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="images per GPU per step (BASELINE: 16)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the side measurements of BASELINE configs[2..4] (variants key)")
     ap.add_argument("--detail", default=None, help="write the per-layer conv kernel timing table (JSON) here")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -230,6 +230,16 @@ int b2u_softmax_resize_argmax_u8(const float* logits, unsigned char* mask, int N
                                  int ch, int cw, int oh, int ow, void* stream);
 /* fast_hist (utils/utils_metrics.py:34-43): hist (n*n+1 uint64, accumulated) ; dtype 0=u8 1=i32 2=i64 */
 int b2u_fast_hist(const void* a, const void* b, long long len, int n, int dtype, unsigned long long* hist, void* stream);
+/* compute_mIoU's loop over an evaluation set (utils/utils_metrics.py:74-95) in ONE launch: items = count x {const uint8* a;
+ * const uint8* b; int64 len; int64 first_chunk} (32 B each) in DEVICE memory, every pointer 16-byte aligned; first_chunk = running
+ * sum of b2u_fast_hist_chunks(len) over the previous items, total_chunks = the sum over all of them; hist as above */
+int b2u_fast_hist_batch(const void* items, int count, long long total_chunks, int n, unsigned long long* hist, void* stream);
+long long b2u_fast_hist_chunks(long long len);
+/* get_miou.py:45-65 without the mask round trip: pred = argmax_c logits (fp32 NCHW; lowest index on ties, unet.py:246-250),
+ * optionally stored as a uint8 mask [N][H][W], and (gt, pred) counted into hist (n*n+1 uint64, accumulated) in the same pass;
+ * gt: uint8 [N][H][W] (values >= n ignored) or NULL (mask only); H*W %% 4 == 0 */
+int b2u_argmax_hist(const float* logits, const unsigned char* gt, unsigned char* pred, int N, int C, int H, int W, int n,
+                    unsigned long long* hist, void* stream);
 
 /* ---- optimizer (torch.optim.Adam / SGD step of train.py:402-405 on flat fp32 buffers) ----------------------- */
 int b2u_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,

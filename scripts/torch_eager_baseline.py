@@ -49,22 +49,18 @@ def loss_fn(logits, png, C):
     return ce + dice
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--steps", type=int, default=20); ap.add_argument("--batch", type=int, default=16)
-    ap.add_argument("--fp32", action="store_true")
-    args = ap.parse_args()
-    dev = torch.device("cuda:0")
+def measure(steps=20, batch=16, fp32=False):
+    dev = torch.device("cuda", torch.cuda.current_device())
     torch.backends.cudnn.benchmark = True
     C = 21
     model = VGGUnet(C).to(dev).to(memory_format=torch.channels_last)
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
-    x = torch.rand(args.batch, 3, 512, 512, device=dev).contiguous(memory_format=torch.channels_last)
-    png = torch.randint(0, C + 1, (args.batch, 512, 512), device=dev)
+    x = torch.rand(batch, 3, 512, 512, device=dev).contiguous(memory_format=torch.channels_last)
+    png = torch.randint(0, C + 1, (batch, 512, 512), device=dev)
 
     def step():
         opt.zero_grad(set_to_none=True)
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=not args.fp32):
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=not fp32):
             out = model(x)
         loss = loss_fn(out, png, C)
         loss.backward()
@@ -75,13 +71,21 @@ def main():
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     b.record(); torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / args.steps
-    print(json.dumps({"what": "torch eager + cuDNN, Unet-VGG16 21 classes 512x512 train step", "dtype": "fp32" if args.fp32 else "bf16 autocast",
-                      "batch": args.batch, "ms_per_step": ms, "img_per_s": args.batch * 1e3 / ms, "torch": torch.__version__,
-                      "cudnn": torch.backends.cudnn.version(), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
+    ms = a.elapsed_time(b) / steps
+    return {"what": "torch eager + cuDNN, Unet-VGG16 21 classes 512x512 train step", "dtype": "fp32" if fp32 else "bf16 autocast",
+            "batch": batch, "ms_per_step": ms, "img_per_s": batch * 1e3 / ms, "torch": torch.__version__,
+            "cudnn": torch.backends.cudnn.version(), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=20); ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--fp32", action="store_true")
+    args = ap.parse_args()
+    print(json.dumps(measure(args.steps, args.batch, args.fp32)))
 
 
 if __name__ == "__main__":

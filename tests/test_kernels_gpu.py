@@ -257,6 +257,58 @@ def test_fast_hist_full_size_properties(b2u, cuda_device):
     assert whole.sum() == int((gt < n).sum())
 
 
+@pytest.mark.parametrize("n", [2, 4, 21, 30])
+def test_fast_hist_lanes_kernel_wraps_and_batches(b2u, cuda_device, n):
+    """The lane-private byte counters wrap (255 -> 0) into the per-warp 32-bit table: a mask that sends > 255 pixels of ONE bin
+    through every lane must stay exact; the batched entry point (pointer table, one launch) equals the per-mask loop,
+    including ragged lengths and all-ignored masks."""
+    ops, dev = b2u.ops, cuda_device
+    L = 148 * 384 * 16 * 20 + 5                        # ~320 pixels per lane, all in one bin
+    a = torch.full((L,), n - 1, dtype=torch.uint8, device=dev)
+    b = torch.full((L,), n - 1, dtype=torch.uint8, device=dev)
+    a[7::1001] = 255                                    # a few ignored pixels
+    hist = ops.fast_hist_accumulate(a, b, n, torch.zeros(n * n + 1, dtype=torch.int64, device=dev)).cpu().numpy()
+    want = np.zeros(n * n + 1, np.int64)
+    want[n * n - 1] = int((a != 255).sum().item())
+    assert np.array_equal(hist, want)
+    rng = np.random.default_rng(5 + n)
+    sizes = [512 * 512, 16 * 33 + 9, 0 + 16, 100003, 512 * 384]
+    pairs, ref = [], np.zeros((n, n), np.int64)
+    for i, sz in enumerate(sizes):
+        ga = rng.integers(0, n, size=sz).astype(np.uint8)
+        ga[rng.random(sz) < (1.0 if i == 2 else 0.03)] = 255
+        pb = rng.integers(0, n, size=sz).astype(np.uint8)
+        ref += O.fast_hist(ga, pb, n)
+        pairs.append((torch.from_numpy(ga).to(dev), torch.from_numpy(pb).to(dev)))
+    got = ops.fast_hist_batch(pairs, n, torch.zeros(n * n + 1, dtype=torch.int64, device=dev)).cpu().numpy()
+    assert got[-1] == 0 and np.array_equal(got[:-1].reshape(n, n), ref)
+    loop = torch.zeros(n * n + 1, dtype=torch.int64, device=dev)
+    for ga, pb in pairs:
+        ops.fast_hist_accumulate(ga, pb, n, loop)
+    assert np.array_equal(loop.cpu().numpy(), got)
+
+
+@pytest.mark.parametrize("C,n", [(21, 21), (2, 2), (4, 4)])
+def test_argmax_hist_fused(b2u, cuda_device, C, n):
+    """logits -> class mask + confusion matrix in one pass == numpy argmax (lowest index on ties) + the reference's bincount
+    formulation (utils/utils_metrics.py:34-43), exactly."""
+    ops, dev = b2u.ops, cuda_device
+    g = torch.Generator().manual_seed(C)
+    logits = torch.randn(3, C, 64, 96, generator=g)
+    logits[0, :, :8] = 0.25                              # ties everywhere: class 0 must win
+    logits[1, 1, 5:9] = logits[1, 0, 5:9]                # two-way ties
+    gt = torch.randint(0, n, (3, 64, 96), generator=g, dtype=torch.uint8)
+    gt[torch.rand(3, 64, 96, generator=g) < 0.05] = 255
+    hist, pred = ops.argmax_hist(logits.to(dev), gt.to(dev), n, want_pred=True)
+    want_pred = logits.numpy().argmax(1).astype(np.uint8)
+    assert np.array_equal(pred.cpu().numpy(), want_pred)
+    assert np.array_equal(pred.cpu().numpy(), ops.argmax_u8(logits.to(dev)).cpu().numpy())
+    h = hist.cpu().numpy()
+    assert h[-1] == 0 and np.array_equal(h[:-1].reshape(n, n), O.fast_hist(gt.numpy().reshape(-1), want_pred.reshape(-1), n))
+    _, only_mask = ops.argmax_hist(logits.to(dev), want_pred=True)
+    assert np.array_equal(only_mask.cpu().numpy(), want_pred)
+
+
 def test_optimizer_steps_match_torch(b2u, cuda_device):
     ops, dev = b2u.ops, cuda_device
     g = torch.Generator().manual_seed(6)

@@ -83,6 +83,9 @@ SIGNATURES = {
     "b2u_argmax_u8": (I, [P, P, I, I, I, I, P]),
     "b2u_softmax_resize_argmax_u8": (I, [P, P, I, I, I, I, I, I, I, I, I, I, P]),
     "b2u_fast_hist": (I, [P, P, LL, I, I, P, P]),
+    "b2u_fast_hist_batch": (I, [P, I, LL, I, P, P]),
+    "b2u_fast_hist_chunks": (LL, [LL]),
+    "b2u_argmax_hist": (I, [P, P, P, I, I, I, I, I, P, P]),
     "b2u_adam_step": (I, [P, P, P, P, LL, F, F, F, F, F, I, F, P]),
     "b2u_sgd_step": (I, [P, P, P, LL, F, F, F, I, I, F, P]),
 }

@@ -757,6 +757,47 @@ def fast_hist_accumulate(a, b, n, hist):
     return hist
 
 
+class HistTable:
+    """Device-resident pointer table of (a, b) uint8 CUDA mask pairs for fast_hist_batch (keeps the masks alive)."""
+
+    def __init__(self, pairs, device):
+        import struct
+        blob, chunks = [], 0
+        chunk_fn = lib().b2u_fast_hist_chunks
+        for a, b in pairs:
+            _req(a, torch.uint8, "a"); _req(b, torch.uint8, "b")
+            if a.numel() != b.numel():
+                raise ValueError("fast_hist_batch: a and b must have the same number of elements")
+            if a.data_ptr() % 16 or b.data_ptr() % 16:
+                raise ValueError("fast_hist_batch: masks must be 16-byte aligned")
+            blob.append(struct.pack("<QQqq", a.data_ptr(), b.data_ptr(), a.numel(), chunks))
+            chunks += chunk_fn(a.numel())
+        self.pairs, self.count, self.chunks = list(pairs), len(blob), chunks
+        self.table = torch.frombuffer(bytearray(b"".join(blob)), dtype=torch.uint8).to(device) if blob else None
+
+
+def fast_hist_batch(pairs, n, hist):
+    """hist += confusion matrices of many (a, b) uint8 CUDA mask pairs in ONE launch.  pairs: list of (a, b) or a HistTable."""
+    _req(hist, torch.int64, "hist")
+    tab = pairs if isinstance(pairs, HistTable) else HistTable(pairs, hist.device)
+    if tab.count:
+        check(lib().b2u_fast_hist_batch(ptr(tab.table), tab.count, tab.chunks, n, ptr(hist), stream_ptr()))
+    return hist
+
+
+def argmax_hist(logits, gt=None, n=0, hist=None, pred=None, want_pred=False):
+    """Per-pixel class decision of fp32 NCHW logits (+ optional uint8 mask) fused with fast_hist against `gt` (uint8 [N, H, W]).
+    Returns (hist, pred)."""
+    _req(logits, torch.float32, "logits"); _req(gt, torch.uint8, "gt"); _req(hist, torch.int64, "hist"); _req(pred, torch.uint8, "pred")
+    N, C, H, W = logits.shape
+    if want_pred and pred is None:
+        pred = torch.empty((N, H, W), dtype=torch.uint8, device=logits.device)
+    if gt is not None and hist is None:
+        hist = torch.zeros(n * n + 1, dtype=torch.int64, device=logits.device)
+    check(lib().b2u_argmax_hist(ptr(logits), ptr(gt), ptr(pred), N, C, H, W, n, ptr(hist), stream_ptr()))
+    return hist, pred
+
+
 # ---------------------------------------------------------------------------------------------- optimizer
 def adam_step(param, grad, m, v, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
     for t, nme in ((param, "param"), (grad, "grad"), (m, "exp_avg"), (v, "exp_avg_sq")):

@@ -110,15 +110,24 @@ class Unet(object):
         the GPU and is folded into one device-resident confusion matrix (`fast_hist`), read back once at the end.
         images: iterable of PIL images; gts: iterable of label maps (PIL 'L'/'P' images or uint8 arrays, 255 = ignore).
         Returns (hist int64 [n, n], IoUs, PA_Recall, Precision) like compute_mIoU."""
-        from .utils.utils_metrics import fast_hist_device, per_class_iu, per_class_PA_Recall, per_class_Precision
+        from .utils.utils_metrics import per_class_iu, per_class_PA_Recall, per_class_Precision
         n = self.num_classes
         hist = torch.zeros(n * n + 1, dtype=torch.int64, device=self.device)
+        pairs = []
+
+        def flush():
+            if pairs:
+                ops.fast_hist_batch(pairs, n, hist)       # one launch for the whole group of masks
+                pairs.clear()
         for image, gt in zip(images, gts):
             pred = self.predict_mask_device(image)
             g = torch.from_numpy(np.ascontiguousarray(np.array(gt, dtype=np.uint8))).to(self.device, non_blocking=True)
             if g.numel() != pred.numel():          # utils_metrics.py:88-93: mismatching pairs are skipped
                 continue
-            fast_hist_device(g.reshape(-1), pred.reshape(-1), n, hist=hist)
+            pairs.append((g.reshape(-1), pred.reshape(-1).contiguous()))
+            if len(pairs) == 256:
+                flush()
+        flush()
         h = hist.cpu().numpy()
         if h[-1] != 0:
             raise ValueError("predictions outside [0, num_classes)")
