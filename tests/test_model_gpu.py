@@ -802,6 +802,60 @@ def test_sync_batchnorm_two_gpus(cuda_device):
         assert near <= 2e-2 and gerr <= 0.15
 
 
+def _dp_trainer_worker(rank, world, port, sd, imgs, pngs, C, out):
+    import torch.distributed as dist
+    import unet_pytorch_b200 as b2u
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        n = imgs.shape[0] // world
+        xs, ys = imgs[rank * n:(rank + 1) * n].to(dev), pngs[rank * n:(rank + 1) * n].to(dev)
+        # rank 1 starts from DIFFERENT weights: the constructor's broadcast (DDP semantics, train.py:346) must overwrite them
+        start = sd if rank == 0 else {k: v + 0.01 for k, v in sd.items()}
+        tr = b2u.UnetTrainer(num_classes=C, device=dev, state_dict=start, lr=1e-4, bucket_mb=1)
+        res = tr.train_step(xs, ys).cpu()
+        grads = {k: (v / world).cpu() for k, v in tr.grads.items()}       # the flat buffer holds the SUM over ranks
+        for _ in range(2):
+            tr.train_step(xs, ys)
+        ref_p = tr.flat_param.clone()
+        dist.broadcast(ref_p, src=0)
+        diff = (tr.flat_param - ref_p).abs().max().reshape(1)
+        dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+        out[rank] = (res.tolist(), grads if rank == 0 else None, float(diff.item()), len(tr.layout.buckets))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_trainer_two_gpus_vs_mean_of_shards(cuda_device):
+    """UnetTrainer on two NCCL ranks, 2 images each: the synchronised gradient is the MEAN of the per-shard gradients (each
+    shard normalises CE / Dice over itself, utils_fit.py:70-81 -- NOT the gradient of the global batch), per the fp32 oracle;
+    after three Adam steps both ranks hold bit-identical parameters."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    C = 21
+    sd = O.make_params(C, seed=11)
+    imgs, pngs = O.make_inputs(4, C, 64, 64, seed=13)
+    w = torch.ones(C)
+    shard = [O.train_step(sd, imgs[r * 2:(r + 1) * 2], pngs[r * 2:(r + 1) * 2], w, C, dice=True) for r in range(2)]
+    mean = {k: (shard[0][2][k] + shard[1][2][k]) / 2 for k in sd}
+    whole = O.train_step(sd, imgs, pngs, w, C, dice=True)[2]
+    out = mp.Manager().dict()
+    mp.spawn(_dp_trainer_worker, args=(2, 29653, sd, imgs, pngs, C, out), nprocs=2, join=True)
+    (res0, grads, diff0, nb), (res1, _, diff1, _) = out[0], out[1]
+    assert nb >= 4                                            # several buckets were in flight
+    assert diff0 == 0.0 and diff1 == 0.0                      # replicas stay bit-identical
+    for r, res in ((0, res0), (1, res1)):                     # every rank reports ITS shard's loss
+        assert abs(res[0] - shard[r][0].item()) <= 1e-2 * abs(shard[r][0].item())
+    gerr = _global_rel(grads, mean)
+    assert gerr <= 1e-2
+    # and it is measurably not the single-global-batch gradient where the two differ
+    gap = _global_rel(mean, whole)
+    print(f"\n[dp2] grad vs mean-of-shards oracle {gerr:.2e}; mean-of-shards vs global-batch gradient {gap:.2e}")
+
+
 # ------------------------------------------------------------------------------------------------ bf16 on the pinned branch
 def _bn_family(b2u, golden_dir, family):
     """(model, state dict, inputs, label map, class weights, oracle step, zero-gradient-bias predicate, dropout override)."""
