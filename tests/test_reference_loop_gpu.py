@@ -106,3 +106,36 @@ def test_reference_fit_one_epoch_runs_on_the_dropin(b2u, cuda_device, backbone, 
     den = sum((ref_after[k] - params[k]).double().pow(2).sum().item() for k in params)
     assert (num / den) ** 0.5 <= 0.15                  # Adam's sign-like first steps amplify bf16 gradient noise on tiny entries
     assert max((after[k] - ref_after[k]).abs().max().item() for k in params) <= 8.1e-4     # <= 2 x 4 steps x lr (opposite signs on a ~0 gradient)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cin", [1, 4])
+def test_lightweight_unet_non_rgb_inputs(b2u, cuda_device, cin):
+    """LightweightUnet(num_classes, in_channels=...) (nets/LightWeightUnet.py:133): the reference accepts any channel count; the
+    graph engine zero-pads the image to one 64-channel block (two-term bf16 split while 2C <= 64)."""
+    S = _staged()
+    if S is None:
+        pytest.skip("baseline/_ref is not staged")
+    torch.manual_seed(3)
+    ref = S.import_reference("nets.LightWeightUnet").LightweightUnet(num_classes=3, in_channels=cin)
+    for m in ref.modules():
+        if isinstance(m, torch.nn.Dropout2d):
+            m.p = 0.0
+    ref = ref.to(cuda_device).train()
+    ours = b2u.LightweightUnet(num_classes=3, in_channels=cin)
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(cuda_device).train()
+    for ins in ours._engine_for(cuda_device).program:
+        if ins["op"] == "drop":
+            ins["p"] = 0.0
+    x = torch.rand(2, cin, 64, 64, device=cuda_device)
+    zr = ref(x)
+    zo = ours(x)
+    assert zo.shape == zr.shape
+    assert ((zo - zr).norm() / zr.norm()).item() <= 3e-2
+    zr.square().mean().backward()
+    zo.square().mean().backward()
+    w = "backbone.stage1.0.conv.0.weight"
+    gr = dict(ref.named_parameters())[w].grad
+    go = dict(ours.named_parameters())[w].grad
+    assert go.shape == gr.shape and ((go - gr).norm() / gr.norm()).item() <= 0.25

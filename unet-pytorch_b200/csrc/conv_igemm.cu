@@ -21,8 +21,17 @@
 //     buffered so the epilogue of tile i overlaps the main loop of tile i+1.
 //   * Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps 2..5 =
 //     epilogue (tcgen05.ld -> bias/ReLU/mask -> bf16 -> swizzled smem -> TMA store).
-//   * Persistent: grid = min(tiles, #SM), static round-robin tile schedule.
+//   * Persistent: grid = min(tiles, #SM).  Tiles are handed out DYNAMICALLY: the producer thread takes the next tile id
+//     with one atomicAdd on a per-launch counter and passes it to the MMA and epilogue warps through a 4-deep
+//     shared-memory queue (mbarrier full/empty pairs), so a CTA that lost its SM for a while to another kernel (the NCCL
+//     all-reduce of the data-parallel step) simply takes fewer tiles instead of holding the whole grid back.  The
+//     cp.async mask-stream variants (MD > 0), whose prefetch runs across tile boundaries, keep the static round robin
+//     (the same queue carries the static sequence).
 //   * M tiles stacked vertically per CTA step (MT): 1 (tiny images), 2, or 4 for the unmasked N = 64 layers.
+#include <atomic>
+#include <cstdlib>
+#include <mutex>
+
 #include "b2u_internal.h"
 #include "b2u_ptx.cuh"
 
@@ -48,6 +57,7 @@ struct ConvParams {
   const float* scale;   // [Cout] or null: per-channel multiplier of the accumulator (folded eval-mode BatchNorm)
   const __nv_bfloat16* mask;  // NHWC [N,H,W,mask_c] or null; keeps y where mask > 0
   int mask_c;
+  int* sched;        // dynamic tile scheduler: [0] next tile id, [1] CTAs done (self-resetting); null = static round robin
 };
 
 template <int BN, int TAPS, int MT, int RB, int SA, int SB, int MD = 0>
@@ -68,9 +78,11 @@ struct ConvCfg {
   static constexpr int kOffStat = kOffBias + 2 * 256 * 4;    // [4 row quarters][64 channels][2] fp32 scratch of the BatchNorm-statistics pass
   static constexpr int kOffMask = kOffStat + 4 * 64 * 2 * 4; // MD thread-private mask tiles [128 rows][128 B]
   static constexpr int kOffBar = kOffMask + MD * kTileM * 128;  // (bias of the current N tile is double buffered by tile parity)
-  static constexpr int kNumBar = 2 * SA + 2 * SB + 4;
+  static constexpr int kQ = 4;                                  // depth of the tile-id queue (producer -> MMA / epilogue warps)
+  static constexpr int kNumBar = 2 * SA + 2 * SB + 4 + 2 * kQ;
   static constexpr int kOffTmem = kOffBar + kNumBar * 8;
-  static constexpr int kSmemBytes = kOffTmem + 16 + 1024;  // + alignment slack
+  static constexpr int kOffTq = kOffTmem + 16;
+  static constexpr int kSmemBytes = kOffTq + kQ * 4 + 1024;  // + alignment slack
   static constexpr uint32_t kSBO = 8 * kRowBytes;
   static constexpr int kAccCols = MT * BN;                     // accumulator columns per pipeline stage
   static constexpr int kTmemCols = 2 * kAccCols <= 128 ? 128 : (2 * kAccCols <= 256 ? 256 : 512);
@@ -106,6 +118,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   auto b_empty = [&](int i) { return bars + 8u * (2 * SA + SB + i); };
   auto t_full = [&](int i) { return bars + 8u * (2 * SA + 2 * SB + i); };
   auto t_empty = [&](int i) { return bars + 8u * (2 * SA + 2 * SB + 2 + i); };
+  auto q_full = [&](int i) { return bars + 8u * (2 * SA + 2 * SB + 4 + i); };
+  auto q_empty = [&](int i) { return bars + 8u * (2 * SA + 2 * SB + 4 + Cfg::kQ + i); };
+  volatile int* tq = reinterpret_cast<volatile int*>(smem_gen + Cfg::kOffTq);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kOffTmem);
 
   const int warp = threadIdx.x >> 5;
@@ -120,6 +135,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     for (int i = 0; i < SA; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
     for (int i = 0; i < SB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(t_full(i), 1); mbar_init(t_empty(i), 4); }
+    for (int i = 0; i < Cfg::kQ; ++i) { mbar_init(q_full(i), 1); mbar_init(q_empty(i), 5); }      // readers: MMA thread + 4 epilogue warps
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -141,7 +157,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     if (lane == 0) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int qs = 0, static_next = blockIdx.x;
+      uint32_t qp = 0;
+      for (;;) {
+        // next tile: one atomic per tile (dynamic) or the round robin (static); published to the consumers through the queue
+        int tile;
+        if (p.sched != nullptr) tile = atomicAdd(p.sched, 1);
+        else { tile = static_next; static_next += gridDim.x; }
+        if (tile >= total_tiles) tile = -1;
+        mbar_wait(q_empty(qs), qp ^ 1u);
+        tq[qs] = tile;
+        mbar_arrive(q_full(qs));
+        if (++qs == Cfg::kQ) { qs = 0; qp ^= 1u; }
+        if (tile < 0) break;
         const int n_tile = tile % p.num_n_tiles;
         int m_tile = tile / p.num_n_tiles;
         const int tw = m_tile % p.tiles_w; m_tile /= p.tiles_w;
@@ -180,7 +208,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const uint64_t b_desc0 = umma_smem_desc(sB, 16, Cfg::kSBO, 2u);
       int sa = 0, sb = 0, as = 0;
       uint32_t pa = 0, pb = 0, pacc = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int qs = 0;
+      uint32_t qp = 0;
+      for (;;) {
+        mbar_wait(q_full(qs), qp);
+        const int tile = tq[qs];
+        mbar_arrive(q_empty(qs));
+        if (++qs == Cfg::kQ) { qs = 0; qp ^= 1u; }
+        if (tile < 0) break;
         mbar_wait(t_empty(as), pacc ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * Cfg::kAccCols);
@@ -262,7 +297,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll
       for (int i = 0; i < (MD > 0 ? MD : 1); ++i) mask_issue();
     }
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int qs = 0;
+    uint32_t qp = 0;
+    for (;;) {
+      mbar_wait(q_full(qs), qp);
+      const int tile = tq[qs];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_empty(qs));
+      if (++qs == Cfg::kQ) { qs = 0; qp ^= 1u; }
+      if (tile < 0) break;
       const int n_tile = tile % p.num_n_tiles;
       int m_tile = tile / p.num_n_tiles;
       const int tw = m_tile % p.tiles_w; m_tile /= p.tiles_w;
@@ -440,11 +483,46 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+  if (threadIdx.x == 0 && p.sched != nullptr) {
+    // the last CTA to leave re-arms the scheduler slot for its next use (every CTA took its final tile id before this point)
+    __threadfence();
+    if (atomicAdd(p.sched + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+      p.sched[0] = 0;
+      p.sched[1] = 0;
+      __threadfence();
+    }
+  }
 }
 
 // ----------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------
+// Scheduler slots: a ring of self-resetting {next tile, CTAs done} pairs per device; consecutive launches take consecutive
+// slots, so kernels that overlap on two streams never share one.  B2U_STATIC_TILES=1 forces the static round robin.
+constexpr int kSchedSlots = 256;
+static int* sched_slot() {
+  static int* base[64] = {nullptr};
+  static std::atomic<unsigned> next{0};
+  static std::mutex mu;
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("B2U_STATIC_TILES"); off = (e && e[0] == '1') ? 1 : 0; }
+  if (off == 1) return nullptr;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return nullptr;
+  if (base[dev] == nullptr) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (base[dev] == nullptr) {
+      int* ptr = nullptr;
+      if (cudaMalloc(&ptr, kSchedSlots * 2 * sizeof(int)) != cudaSuccess) return nullptr;
+      cudaMemset(ptr, 0, kSchedSlots * 2 * sizeof(int));
+      cudaDeviceSynchronize();
+      base[dev] = ptr;
+    }
+  }
+  return base[dev] + 2 * (next.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
+}
+
 template <int BN, int TAPS, int MT, int RB, int SA, int SB, int MD = 0>
 static int launch_cfg(const ConvLaunch& a, cudaStream_t st) {
   using Cfg = ConvCfg<BN, TAPS, MT, RB, SA, SB, MD>;
@@ -491,6 +569,7 @@ static int launch_cfg(const ConvLaunch& a, cudaStream_t st) {
   p.scale = a.scale;
   p.mask = a.mask;
   p.mask_c = a.mask_c;
+  p.sched = MD > 0 ? nullptr : sched_slot();      // the mask-stream variants prefetch across tile boundaries: static order
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
   kern<<<grid, 192, Cfg::kSmemBytes, st>>>(tmA0, tmA1, tmB, tmC0, tmC1, p);

@@ -62,6 +62,7 @@ template <int CIN>
 __global__ void __launch_bounds__(256)
 im2col_first_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int cin_rt, int H, int W) {
   __shared__ uint32_t tile[kI2cPix][33];
+  __nv_bfloat16 (*tile16)[66] = reinterpret_cast<__nv_bfloat16 (*)[66]>(tile);      // the same rows as bf16 elements
   const int Cin = CIN > 0 ? CIN : cin_rt;
   const int segs = (W + kI2cPix - 1) / kI2cPix;
   const int seg = blockIdx.x % segs;
@@ -70,21 +71,20 @@ im2col_first_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col
   const int w0 = seg * kI2cPix;
   const int K = 9 * Cin;
   const bool split = 2 * K <= 64;             // room for the lo halves
-  const int KP = ((split ? 2 * K : K) + 1) / 2;    // k pairs that hold data
+  const int KT = split ? 2 * K : K;           // bf16 columns that hold data
+  const int KP = (KT + 1) / 2;                // ... as 32-bit pairs
   const float* img = x + static_cast<size_t>(n) * Cin * H * W;
-  auto fetch = [&](int k, int pw) -> float {
-    const bool lo = split && k >= K;
-    if (lo) k -= K;
-    if (k >= K) return 0.f;
+  // one image read per (tap, channel, pixel): hi = bf16(x) goes to column k, lo = bf16(x - hi) to column K + k
+  for (int i = threadIdx.x; i < K * kI2cPix; i += 256) {
+    const int k = i / kI2cPix, pw = i - k * kI2cPix;
     const int tap = k / Cin, c = k - tap * Cin;
     const int hh = h + tap / 3 - 1, ww = w0 + pw + tap % 3 - 1;
     const float v = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(img + (static_cast<size_t>(c) * H + hh) * W + ww) : 0.f;
-    return lo ? v - __bfloat162float(__float2bfloat16_rn(v)) : v;
-  };
-  for (int i = threadIdx.x; i < KP * kI2cPix; i += 256) {
-    const int kp = i / kI2cPix, pw = i - kp * kI2cPix;
-    tile[pw][kp] = pack_bf16x2(fetch(2 * kp, pw), fetch(2 * kp + 1, pw));
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    tile16[pw][k] = hi;
+    if (split) tile16[pw][K + k] = __float2bfloat16_rn(v - __bfloat162float(hi));
   }
+  if ((KT & 1) && threadIdx.x < kI2cPix) tile16[threadIdx.x][KT] = __float2bfloat16_rn(0.f);      // odd count: the pair's other half
   __syncthreads();
   uint4* out = reinterpret_cast<uint4*>(col) + (static_cast<size_t>(row) * W + w0) * 8;
   for (int i = threadIdx.x; i < kI2cPix * 8; i += 256) {

@@ -241,6 +241,7 @@ class GraphEngine:
         self._pack_total = 0
         self.saved = None
         self.has_stem = any(i["op"] == "stem" for i in program)
+        self.in_channels = next((i["c"] for i in program if i["op"] == "input"), 3)      # the stem (ResNet) takes RGB
         self.pk = {i["w"]: i for i in program if i["op"] == "conv" and i.get("pk")}     # pixel-packed 1x1 convs
         # convs that read the image: the input instruction stores the image as a two-term bf16 split (hi in channels [0, C),
         # lo = x - hi in [C, 2C)), so their weights are repeated over the second channel range and the MMA sees the image
@@ -465,8 +466,8 @@ class GraphEngine:
             raise ValueError("GraphEngine.forward: input must be a CUDA tensor (no CPU fallback)")
         x = x.float().contiguous() if x.dtype != torch.float32 else x.contiguous()
         N, C, H, W = x.shape
-        if C != 3 or H % 32 or W % 32:
-            raise ValueError("expected a 3-channel image with height and width multiples of 32")
+        if C != self.in_channels or H % 32 or W % 32:
+            raise ValueError(f"expected a {self.in_channels}-channel image with height and width multiples of 32")
         if training is None:
             training = save
         if trainable is None:
@@ -488,7 +489,7 @@ class GraphEngine:
                 t.aux = col
                 T[ins["out"]] = t
             elif op == "input":
-                T[ins["out"]] = _T(ops.nchw_to_nhwc_bf16_padded(x, 64, out=self._buf("x", (N, H, W, 64))))
+                T[ins["out"]] = _T(ops.nchw_to_nhwc_bf16_padded(x, 64, out=self._buf("x", (N, H, W, 64))))      # hi | lo split when 2C <= 64
             elif op == "conv":
                 xin = T[ins["x"]]
                 x1 = T[ins["x1"]] if ins["x1"] else None
@@ -1016,8 +1017,8 @@ class LightweightUnetEngine(GraphEngine):
     def __init__(self, num_classes, in_channels=3, device=None):
         if not 1 <= num_classes <= 32:
             raise ValueError("num_classes must be in [1, 32]")
-        if in_channels != 3:
-            raise NotImplementedError("the CUDA input conversion takes 3-channel images")
+        if not 1 <= in_channels <= 64:
+            raise ValueError("in_channels must be in [1, 64] (the image is zero-padded to one 64-channel block)")
         program, convs = lightweight_unet_program(num_classes, in_channels)
         super().__init__(program, convs, num_classes, device=device)
         self.logit_stride = 2       # logits are H/2 x W/2; the losses resize them (nets/unet_training.py:12-13)
