@@ -139,3 +139,60 @@ def test_lightweight_unet_non_rgb_inputs(b2u, cuda_device, cin):
     gr = dict(ref.named_parameters())[w].grad
     go = dict(ours.named_parameters())[w].grad
     assert go.shape == gr.shape and ((go - gr).norm() / gr.norm()).item() <= 0.25
+
+
+@pytest.mark.gpu
+def test_repvgg_improved_segnet_train_and_deploy(b2u, cuda_device):
+    """nets/RepVGG_Unet.py::ImprovedSegNet (SURVEY 8(f) rank 4): the training form (two conv + BatchNorm branches per RepVGGBlock)
+    against the staged reference in fp32 on the GPU -- logits, loss gradients, BatchNorm running statistics -- and the deploy form
+    after `switch_to_deploy()` (one re-parameterised conv3x3 + bias + ReLU per block, eval mode) against the reference's own
+    deployed model."""
+    S = _staged()
+    if S is None:
+        pytest.skip("baseline/_ref is not staged")
+    dev = cuda_device
+    C = 4
+    torch.manual_seed(5)
+    ref = S.import_reference("nets.RepVGG_Unet").ImprovedSegNet(num_classes=C)
+    ref.dropout.p = 0.0
+    ref = ref.to(dev).train()
+    ours = b2u.ImprovedSegNet(num_classes=C)
+    assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(dev).train()
+    for ins in ours._engine_for(dev).program:
+        if ins["op"] == "drop":
+            ins["p"] = 0.0
+    imgs, pngs = O.make_inputs(4, C, 64, 64, seed=17)
+    imgs, pngs = imgs.to(dev), pngs.to(dev)
+    T = S.import_reference("nets.unet_training")
+    w = torch.ones(C, device=dev)
+    labels = O.one_hot(pngs.cpu(), C).to(dev)
+    zr = ref(imgs)
+    (T.CE_Loss(zr, pngs, w, num_classes=C) + T.Dice_loss(zr, labels)).backward()
+    zo = ours(imgs)
+    (b2u.CE_Loss(zo, pngs, w, num_classes=C) + b2u.Dice_loss(zo, labels)).backward()
+    zerr = ((zo - zr).norm() / zr.norm()).item()
+    gr = {k: p.grad for k, p in ref.named_parameters()}
+    go = {k: p.grad for k, p in ours.named_parameters()}
+    live = [k for k in gr if gr[k] is not None and gr[k].norm().item() > 1e-9]
+    num = sum((go[k] - gr[k]).double().pow(2).sum().item() for k in live)
+    den = sum(gr[k].double().pow(2).sum().item() for k in live)
+    gerr = (num / den) ** 0.5
+    print(f"\n[ImprovedSegNet train] logits {zerr:.2e} grads {gerr:.2e}")
+    assert zerr <= 5e-2 and gerr <= 3e-1                 # tiny random-init fixture (see test_model_gpu._direct)
+    for (k, a), (_, b) in zip(ours.named_buffers(), ref.named_buffers()):
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            assert ((a - b).norm() / (b.norm() + 1e-12)).item() <= 3e-2, k
+    # deploy: fold every RepVGGBlock, eval mode
+    ref.eval(); ref.switch_to_deploy()
+    ours.eval(); ours.switch_to_deploy()
+    for k in ref.state_dict():
+        assert torch.allclose(ours.state_dict()[k], ref.state_dict()[k], rtol=1e-5, atol=1e-6), k
+    with torch.no_grad():
+        dr = ref(imgs)
+        do = ours(imgs)
+    derr = ((do - dr).norm() / dr.norm()).item()
+    print(f"[ImprovedSegNet deploy] logits {derr:.2e}")
+    assert derr <= 2e-2
+    assert (do.argmax(1) == dr.argmax(1)).float().mean().item() >= 0.97

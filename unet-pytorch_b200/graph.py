@@ -223,6 +223,62 @@ def lightweight_unet_program(num_classes, in_channels=3):
     return P, convs
 
 
+def improved_segnet_program(num_classes, deploy=False):
+    """ImprovedSegNet(use_repvgg=True) of nets/RepVGG_Unet.py:149-206 (8(f) rank 4, "RepVGG deploy re-param"): the topology of
+    UltraLightweightUnet_large_optimized (widths 44-88-176-352-704, SE after the encoder stages, Dropout2d(0.15) on the bridge,
+    cat[upsampled, skip]) with LightweightConvBlock = 1x1 conv (+bias) -> BN -> ReLU -> RepVGGBlock(mid -> out), mid = max(16, out // 2).
+    RepVGGBlock (training form, :25-60): relu(bn1(conv3x3(x)) + bn2(conv1x1(x))) -- both convs bias-free; the identity branch only
+    exists when mid == out, which none of these blocks has.  Deploy form (:67-73): one conv3x3 + bias + ReLU (`reparam_conv`)."""
+    widths = (44, 88, 176, 352, 704)
+    P, convs = [], {}
+
+    def conv(out, x, w, ci, co, taps, bias=None, relu=False, x1=None, c1=0):
+        convs[w] = (co, ci, c1, taps)
+        P.append(dict(op="conv", out=out, x=x, x1=x1, w=w, bias=bias, cin=ci, c1=c1, cout=co, taps=taps, stride=1, relu=relu))
+
+    def bn(out, z, name, c, relu=True, res=None):
+        P.append(dict(op="bn", out=out, z=z, bn=name, c=c, relu=relu, res=res))
+
+    def block(p, x, cin, cout, x1=None, c1=0):
+        mid = max(16, cout // 2)
+        if mid == cout:
+            raise NotImplementedError("RepVGGBlock identity branch (in == out channels) is not used by ImprovedSegNet")
+        conv(p + ".z0", x, p + ".conv.0.weight", cin, mid, 1, bias=p + ".conv.0.bias", x1=x1, c1=c1)
+        bn(p + ".y0", p + ".z0", p + ".conv.1", mid)
+        rep = p + ".conv.3"
+        if deploy:
+            conv(p + ".out", p + ".y0", rep + ".reparam_conv.weight", mid, cout, 9, bias=rep + ".reparam_conv.bias", relu=True)
+            return p + ".out"
+        conv(p + ".z1", p + ".y0", rep + ".conv2.weight", mid, cout, 1)                 # 1x1 branch
+        bn(p + ".y1", p + ".z1", rep + ".bn2", cout, relu=False)
+        conv(p + ".z3", p + ".y0", rep + ".conv1.weight", mid, cout, 9)                 # 3x3 branch
+        bn(p + ".out", p + ".z3", rep + ".bn1", cout, relu=True, res=p + ".y1")         # relu(bn1(.) + bn2(.))
+        return p + ".out"
+
+    P.append(dict(op="input", out="x", c=3))
+    x, cin, skips = "x", 3, []
+    for i, w_ in enumerate(widths[:4], start=1):
+        if i > 1:
+            P.append(dict(op="pool2", out=f"p{i}", x=x))
+            x = f"p{i}"
+        x = block(f"enc{i}", x, cin, w_)
+        P.append(dict(op="se", out=f"se{i}.out", x=x, se=f"se{i}", c=w_, r=max(8, w_ // 4)))
+        x = f"se{i}.out"
+        skips.append((x, w_))
+        cin = w_
+    P.append(dict(op="pool2", out="p5", x=x))
+    x = block("bridge", "p5", cin, widths[4])
+    P.append(dict(op="drop", out="bridge.drop", x=x, p=0.15))
+    x, clow = "bridge.drop", widths[4]
+    for k in (4, 3, 2, 1):
+        skip, cs = skips[k - 1]
+        P.append(dict(op="up", out=f"up{k}", x=x))
+        x = block(f"dec{k}", f"up{k}", clow, cs, x1=skip, c1=cs)
+        clow = cs
+    P.append(dict(op="head", out="logits", x=x, w="final.weight", bias="final.bias", cin=widths[0]))
+    return P, convs
+
+
 ULU_VARIANTS = {
     # name: (widths, minimum mid channels, SE reduction rule, bridge dropout)
     "ultralight": ((32, 64, 128, 256, 512), 8, None, 0.0),                                     # UltraLightweightUnet.py
@@ -1022,3 +1078,14 @@ class LightweightUnetEngine(GraphEngine):
         program, convs = lightweight_unet_program(num_classes, in_channels)
         super().__init__(program, convs, num_classes, device=device)
         self.logit_stride = 2       # logits are H/2 x W/2; the losses resize them (nets/unet_training.py:12-13)
+
+
+class ImprovedSegNetEngine(GraphEngine):
+    """nets/RepVGG_Unet.py::ImprovedSegNet(use_repvgg=True); deploy=True runs the re-parameterised single-conv blocks."""
+
+    def __init__(self, num_classes, deploy=False, device=None):
+        if not 1 <= num_classes <= 32:
+            raise ValueError("num_classes must be in [1, 32]")
+        program, convs = improved_segnet_program(num_classes, deploy=deploy)
+        super().__init__(program, convs, num_classes, device=device)
+        self.deploy = deploy

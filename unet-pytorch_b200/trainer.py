@@ -17,7 +17,7 @@ import torch.distributed as dist
 
 from . import ops
 from .engine import TraditionalUnetEngine, VGGUnetEngine, vgg_unet_param_shapes
-from .graph import LightweightUnetEngine, ResNet50UnetEngine, UltraLightUnetEngine
+from .graph import ImprovedSegNetEngine, LightweightUnetEngine, ResNet50UnetEngine, UltraLightUnetEngine
 
 
 def _backward_order(names):
@@ -134,10 +134,11 @@ class GradientSync:
 class UnetTrainer:
     """model: "unet_vgg" / "unet_resnet50" (nets/unet.py::Unet with backbone 'vgg' / 'resnet50'), "traditional"
     (nets/TraditionalUnet.py) or "ultralight" / "ultralight_large" / "ultralight_large_optimized"
-    (nets/UltraLightweightUnet*.py) or "lightweight" (nets/LightWeightUnet.py; logits at H/2, resized inside the loss)."""
+    (nets/UltraLightweightUnet*.py) or "lightweight" (nets/LightWeightUnet.py; logits at H/2, resized inside the loss) or
+    "improved_segnet" (nets/RepVGG_Unet.py::ImprovedSegNet, RepVGG blocks in their training form)."""
 
     ENGINES = {"unet_vgg": VGGUnetEngine, "traditional": TraditionalUnetEngine, "unet_resnet50": ResNet50UnetEngine,
-               "lightweight": LightweightUnetEngine,
+               "lightweight": LightweightUnetEngine, "improved_segnet": ImprovedSegNetEngine,
                "ultralight": functools.partial(UltraLightUnetEngine, variant="ultralight"),
                "ultralight_large": functools.partial(UltraLightUnetEngine, variant="ultralight_large"),
                "ultralight_large_optimized": functools.partial(UltraLightUnetEngine, variant="ultralight_large_optimized")}
