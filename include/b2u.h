@@ -76,6 +76,17 @@ int b2u_conv_stat_rows(int N, int H, int W, int Cout, int taps, int bn_override)
 int b2u_conv_fprop_stats(const void* x0, int C0, const void* x1, int C1, const void* wf, const float* bias, void* y, int N,
                          int H, int W, int Cout, int taps, int relu, int bn_override, float* stat_partial, int stat_rows,
                          void* stream);
+/* First conv of a decoder stage with the up-sampling and the concat folded into its operand load: replaces
+ * self.conv1(torch.cat([inputs1, self.up(inputs2)], 1)) of unetUp.forward (nets/unet.py:16-18; likewise Up.forward of
+ * nets/TraditionalUnet.py:36-43) = nn.UpsamplingBilinear2d(scale_factor=2) + torch.cat + nn.Conv2d(k=3,p=1) [+ReLU].
+ * skip: [N,H,W,C0]; low: the LOW-RESOLUTION tensor [N,H/2,W/2,C1], interpolated (bilinear, align_corners=True) by producer
+ * warps directly into the tensor core's A-operand stage -- neither the concat nor the up-sampled tensor is read from HBM.
+ * up_out (nullable): receives the up-sampled tensor [N,H,W,C1] as a by-product (training keeps it as the operand of this
+ * conv's weight gradient; inference passes NULL and the tensor never exists).  scale (nullable): folded eval-mode
+ * BatchNorm as in b2u_conv_fprop_scaled.  stat_partial/stat_rows (nullable/0): as in b2u_conv_fprop_stats. */
+int b2u_decoder_conv_fprop(const void* skip, int C0, const void* low, int C1, const void* wf, const float* scale,
+                           const float* bias, void* y, void* up_out, int N, int H, int W, int Cout, int relu, int bn_override,
+                           float* stat_partial, int stat_rows, void* stream);
 /* dgrad of the same conv (autograd of nn.Conv2d, utils/utils_fit.py:92): dz has Cz channels; the C0+C1 input-channel
  * gradients go to dx0 / dx1 (dx1 NULL: single input).  mask (NHWC bf16, C0 channels, single output only) applies the
  * ReLU backward of the tensor that fed the conv: dx0 = 0 where mask <= 0. */

@@ -87,6 +87,58 @@ def test_conv_fprop_dgrad_wgrad(b2u, cuda_device, N, H, W, C0, C1, Cout, taps, r
     assert rel(ops.bias_grad(dzb), dzr.sum((0, 2, 3))) <= 1e-4
 
 
+DECODER_CASES = [
+    # N, H, W, C0 (skip), C1 (low), Cout -- H, W of the conv (the low tensor is H/2 x W/2)
+    (1, 8, 16, 64, 64, 64),        # one tile, one M tile per step
+    (2, 16, 32, 64, 128, 64),      # up_concat1.conv1 proportions, two stacked M tiles
+    (1, 32, 48, 64, 128, 64),      # exactly one stack of four M tiles
+    (1, 72, 40, 128, 64, 64),      # four-tile stacks, ragged in both directions, two skip blocks
+    (2, 24, 40, 128, 256, 128),    # N tile 128, ragged
+    (1, 8, 8, 64, 64, 128),        # N tile 128, one M tile
+    (1, 16, 16, 256, 512, 256),    # up_concat3.conv1 proportions, N tile 256
+    (1, 4, 4, 512, 512, 512),      # image smaller than a tile: the 2x2 low tensor, two N tiles
+    (1, 12, 20, 64, 64, 192),      # N tile 192
+    (3, 6, 10, 64, 64, 64),        # odd low-resolution sizes (3 x 5)
+]
+
+
+@pytest.mark.parametrize("N,H,W,C0,C1,Cout", DECODER_CASES)
+def test_decoder_conv_fused_upsample(b2u, cuda_device, N, H, W, C0, C1, Cout):
+    """b2u_decoder_conv_fprop (bilinear 2x up-sampling + concat folded into the conv's operand load, nets/unet.py:16-18)
+    against the two-kernel path it replaces: BIT-identical outputs, the by-product up-sampled tensor bit-identical to
+    b2u_upsample2x_fwd, and both within 6e-3 of torch's fp32 upsample + cat + conv on the same bf16 operands."""
+    ops, dev = b2u.ops, cuda_device
+    g = torch.Generator().manual_seed(17)
+    skip = nhwc(torch.randn(N, C0, H, W, generator=g), dev)
+    low = nhwc(torch.randn(N, C1, H // 2, W // 2, generator=g), dev)
+    w = torch.randn(Cout, C0 + C1, 3, 3, generator=g) / ((C0 + C1) * 9) ** 0.5
+    b = torch.randn(Cout, generator=g).to(dev)
+    wf, _ = ops.pack_weights(w.to(dev))
+    up = ops.upsample2x(low)
+    variants = [0, 1 << 16, 2 << 16] + [bn for bn in (64, 128, 192, 256) if Cout % bn == 0] + [(1 << 16) | 64, (2 << 16) | 64]
+    ref = F.conv2d(torch.cat([nchw(skip), F.interpolate(nchw(low), scale_factor=2, mode="bilinear", align_corners=True)], 1),
+                   w.to(BF).float(), b.cpu(), padding=1).relu()
+    for bn in variants:
+        two = ops.conv_fprop(skip, wf, b, Cout, relu=True, x1=up, bn=bn)
+        up_out = torch.full_like(up, float("nan"))
+        one = ops.decoder_conv_fprop(skip, low, wf, b, Cout, relu=True, up_out=up_out, bn=bn)
+        assert torch.equal(one.view(torch.int16), two.view(torch.int16)), f"tiling variant {bn:#x}"
+        assert torch.equal(up_out.view(torch.int16), up.view(torch.int16)), f"by-product, tiling variant {bn:#x}"
+        assert rel(nchw(one), ref) <= 6e-3
+        # inference form: no by-product
+        assert torch.equal(ops.decoder_conv_fprop(skip, low, wf, b, Cout, relu=True, bn=bn).view(torch.int16), two.view(torch.int16))
+    # BatchNorm statistics from the epilogue and the folded eval-mode BatchNorm ride on the same kernel
+    rows = ops.conv_stat_rows(N, H, W, Cout)
+    st1 = torch.zeros(rows * 2 * Cout, device=dev); st2 = torch.zeros_like(st1)
+    z2 = ops.conv_fprop(skip, wf, b, Cout, relu=False, x1=up, stats=st2)
+    z1 = ops.decoder_conv_fprop(skip, low, wf, b, Cout, relu=False, stats=st1)
+    assert torch.equal(z1.view(torch.int16), z2.view(torch.int16)) and torch.equal(st1, st2)
+    sc = (torch.rand(Cout, generator=g) + 0.5).to(dev)
+    y2 = ops.conv_fprop_scaled(skip, wf, sc, b, Cout, relu=True, x1=up)
+    y1 = ops.decoder_conv_fprop(skip, low, wf, b, Cout, relu=True, scale=sc)
+    assert torch.equal(y1.view(torch.int16), y2.view(torch.int16))
+
+
 def test_first_layer_im2col_conv(b2u, cuda_device):
     ops, dev = b2u.ops, cuda_device
     g = torch.Generator().manual_seed(2)

@@ -208,6 +208,36 @@ def test_eval_forward_is_deterministic_and_repeatable(b2u, cuda_device):
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("model,C", [("unet_vgg", 21), ("traditional", 4), ("unet_resnet50", 21)])
+def test_fused_upsample_equals_separate_pass(b2u, cuda_device, model, C):
+    """nets/unet.py:16-18 in one kernel: the decoder conv that interpolates its low-resolution source itself
+    (engine.fuse_upsample, the default) gives BIT-identical logits, loss and gradients to the build that runs
+    b2u_upsample2x_fwd as a separate pass; training needs no upsample launch, inference allocates no up-sampled tensor."""
+    dev = cuda_device
+    imgs, pngs = O.make_inputs(2, C, 96, 64, seed=5)
+    runs = {}
+    for fuse in (True, False):
+        tr = b2u.UnetTrainer(model=model, num_classes=C, device=dev, lr=0.0) if model != "unet_vgg" else \
+            b2u.UnetTrainer(num_classes=C, device=dev, lr=0.0, state_dict=O.make_params(C, seed=11))
+        tr.engine.fuse_upsample = fuse
+        b2u.ops.lib().b2u_reset_launch_count()
+        out = tr.train_step(imgs.to(dev), pngs.to(dev)).cpu()
+        torch.cuda.synchronize()
+        launches = b2u.ops.lib().b2u_launch_count()
+        logits = tr.engine.forward(imgs.to(dev), tr.params, save=False, training=False)
+        runs[fuse] = (out, {k: v.clone() for k, v in tr.grads.items()}, logits.clone(), launches)
+        if fuse:
+            tr.engine.release()
+            tr.engine.forward(imgs.to(dev), tr.params, save=False, training=False)
+            assert not any(k.startswith("up") for k in tr.engine._bufs), "inference must not materialise the up-sampled tensors"
+    assert torch.equal(runs[True][0], runs[False][0])
+    assert torch.equal(runs[True][2], runs[False][2])
+    for k in runs[True][1]:
+        assert torch.equal(runs[True][1][k], runs[False][1][k]), k
+    n_dec = 3 if model == "traditional" else 4
+    assert runs[False][3] - runs[True][3] == n_dec          # one launch less per decoder stage
+
+
 def test_full_size_step_properties(b2u, cuda_device):
     """BASELINE config-2 tile sizes (512x512, 21 classes) at batch 2: parity against the same restatement executed
     by torch on the GPU in fp32 (TF32 off) -- the CPU oracle needs minutes at this size -- plus finite loss."""

@@ -81,6 +81,11 @@ def warm_up(model, T, C, hw, batch, steps, device, lr=1e-3, medical=False, nbatc
     model.train()
     torch.backends.cudnn.allow_tf32 = True          # the warm-up only has to produce plausible mid-training weights
     torch.backends.cuda.matmul.allow_tf32 = True
+    # ask for reproducible kernels so every run (and box) trains towards the same fixture; ops without a deterministic
+    # implementation only warn
+    det = (torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark, torch.are_deterministic_algorithms_enabled())
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = True, False
+    torch.use_deterministic_algorithms(True, warn_only=True)
     opt = torch.optim.Adam(model.parameters(), lr=lr)
     w = torch.ones(C, device=device)
     data = [make_batch(batch, C, hw, 1000 + i, medical, device) for i in range(nbatches)]
@@ -97,6 +102,8 @@ def warm_up(model, T, C, hw, batch, steps, device, lr=1e-3, medical=False, nbatc
                 log(f"    warm step {it + 1}/{steps}: loss {last:.4f}")
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = det[0], det[1]
+    torch.use_deterministic_algorithms(det[2])
     return last
 
 

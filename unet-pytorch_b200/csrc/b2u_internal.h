@@ -30,6 +30,8 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t row
 struct ConvLaunch {
   const void* x0 = nullptr; int C0 = 0;     // source 0 (NHWC bf16)
   const void* x1 = nullptr; int C1 = 0;     // optional source 1 (virtual concat), same N,H,W
+  const void* up_low = nullptr;             // instead of x1: source 1 = this [N,H/2,W/2,C1] tensor, bilinearly up-sampled 2x inside the kernel
+  void* up_out = nullptr;                   // with up_low, nullable: by-product copy of the up-sampled tensor [N,H,W,C1]
   const void* wpacked = nullptr;            // bf16 [Cout][taps*(C0+C1)]
   const float* bias = nullptr;              // fp32 [Cout] or null
   const float* scale = nullptr;             // fp32 [Cout] or null: y = acc * scale + bias (eval-mode BatchNorm folded into the conv)

@@ -28,12 +28,22 @@
 //     cp.async mask-stream variants (MD > 0), whose prefetch runs across tile boundaries, keep the static round robin
 //     (the same queue carries the static sequence).
 //   * M tiles stacked vertically per CTA step (MT): 1 (tiny images), 2, or 4 for the unmasked N = 64 layers.
+//   * UP = 1 (the first conv of a decoder stage, nets/unet.py:16-18: conv1(cat([skip, up(low)]))): source 1 is the
+//     LOW-RESOLUTION tensor [N, H/2, W/2, C1].  Four extra warps (6..9) interpolate its 64-channel blocks (bilinear 2x,
+//     align_corners=True, the arithmetic of b2u_bilinear.cuh) straight into the 128B-swizzled A stage the tensor core reads,
+//     taking the A slots of the channel blocks >= C0 in the same ring the TMA thread fills for the skip tensor: neither the
+//     concat nor the upsampled tensor goes through HBM on the way into the conv.  Low-resolution rows are fetched one
+//     row segment ahead (12 16-byte loads in flight per thread), so their L2 latency hides behind the interpolation of the
+//     previous segment.  In training the weight gradient of this conv needs the upsampled tensor as an operand: the
+//     warps that build the centre-tap box of N tile 0 also store its interior rows to `up_out` (a by-product of the conv,
+//     not a separate pass); inference passes up_out = null and the tensor never exists.
 #include <atomic>
 #include <cstdlib>
 #include <mutex>
 
 #include "b2u_internal.h"
 #include "b2u_ptx.cuh"
+#include "b2u_bilinear.cuh"
 
 namespace b2u {
 
@@ -58,9 +68,14 @@ struct ConvParams {
   const __nv_bfloat16* mask;  // NHWC [N,H,W,mask_c] or null; keeps y where mask > 0
   int mask_c;
   int* sched;        // dynamic tile scheduler: [0] next tile id, [1] CTAs done (self-resetting); null = static round robin
+  const __nv_bfloat16* up_low;  // UP kernels: source 1 = this [N, H/2, W/2, C1] tensor, upsampled 2x on the fly
+  __nv_bfloat16* up_out;        // UP kernels, nullable: receives the upsampled tensor [N, H, W, C1] (operand of the weight gradient)
+  float up_sh, up_sw;           // (H/2 - 1) / (H - 1), (W/2 - 1) / (W - 1)
 };
 
-template <int BN, int TAPS, int MT, int RB, int SA, int SB, int MD = 0>
+constexpr int kUpWarps = 4;         // interpolation warps of the UP kernels (thread = (box column, 16-byte channel chunk))
+
+template <int BN, int TAPS, int MT, int RB, int SA, int SB, int MD = 0, int UP = 0>
 struct ConvCfg {
   // MD: depth of the cp.async ReLU-mask pipeline (0: mask rows are prefetched into registers one sub-tile ahead)
   // MT: M tiles (8x16 pixel patches, stacked vertically) per CTA step, sharing every B tile
@@ -91,14 +106,16 @@ struct ConvCfg {
   static_assert(TAPS == 9 || RB == 1, "1x1 convs have a single tap");
   static_assert(kABytes % 1024 == 0 && kBTap % 1024 == 0, "stage buffers must keep 1024B alignment");
   static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
+  static_assert(UP == 0 || (TAPS == 9 && MD == 0), "the interpolating producer exists for the unmasked 3x3 forward tiles");
+  static constexpr int kThreads = 192 + (UP ? kUpWarps * 32 : 0);
 };
 
-template <int BN, int TAPS, int MT, int RB, int SA, int SB, int MD = 0>
-__global__ void __launch_bounds__(192, 1)
+template <int BN, int TAPS, int MT, int RB, int SA, int SB, int MD = 0, int UP = 0>
+__global__ void __launch_bounds__(192 + (UP ? kUpWarps * 32 : 0), 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC0,
                   const __grid_constant__ CUtensorMap tmC1, const ConvParams p) {
-  using Cfg = ConvCfg<BN, TAPS, MT, RB, SA, SB, MD>;
+  using Cfg = ConvCfg<BN, TAPS, MT, RB, SA, SB, MD, UP>;
   constexpr int S_TAPS = TAPS == 9 ? 3 : 1;
   constexpr int R_TAPS = TAPS == 9 ? 3 : 1;
 
@@ -135,7 +152,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     for (int i = 0; i < SA; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
     for (int i = 0; i < SB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(t_full(i), 1); mbar_init(t_empty(i), 4); }
-    for (int i = 0; i < Cfg::kQ; ++i) { mbar_init(q_full(i), 1); mbar_init(q_empty(i), 5); }      // readers: MMA thread + 4 epilogue warps
+    for (int i = 0; i < Cfg::kQ; ++i) { mbar_init(q_full(i), 1); mbar_init(q_empty(i), 5 + (UP ? kUpWarps : 0)); }      // readers: MMA thread + 4 epilogue warps (+ interpolation warps)
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -180,10 +197,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           const CUtensorMap* tm = c < chunks0 ? &tmA0 : &tmA1;
           const int cc = c < chunks0 ? c * KB : c * KB - p.C0;
           for (int s = 0; s < S_TAPS; ++s) {
+            // (the wait is kept for the slots the interpolation warps fill: a parity wait must never run more than one
+            // phase ahead of its barrier)
             mbar_wait(a_empty(sa), pa ^ 1u);
-            mbar_expect_tx(a_full(sa), Cfg::kABytes);
-            if (TAPS == 9) tma_load_4d(sA + sa * Cfg::kABytes, tm, a_full(sa), cc, w0 + s - 1, h0 - 1, img);
-            else           tma_load_4d(sA + sa * Cfg::kABytes, tm, a_full(sa), cc, w0, h0, img);
+            if (!(UP && c >= chunks0)) {
+              mbar_expect_tx(a_full(sa), Cfg::kABytes);
+              if (TAPS == 9) tma_load_4d(sA + sa * Cfg::kABytes, tm, a_full(sa), cc, w0 + s - 1, h0 - 1, img);
+              else           tma_load_4d(sA + sa * Cfg::kABytes, tm, a_full(sa), cc, w0, h0, img);
+            }
             if (++sa == SA) { sa = 0; pa ^= 1u; }
             for (int rb = 0; rb < R_TAPS / RB; ++rb) {
               mbar_wait(b_empty(sb), pb ^ 1u);
@@ -253,6 +274,115 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         tc_commit(t_full(as));
         if (++as == 2) { as = 0; pacc ^= 1u; }
       }
+    }
+  } else if (UP && warp >= 6) {
+    // ===================== interpolation producers (UP kernels: warps 6..9, 128 threads) =====================
+    // thread = (box column `col`, 16-byte chunk `ch` of the 64-channel block); box pixel q = row * 16 + col lands at byte
+    // q * 128 + ((ch ^ (q & 7)) << 4), exactly where a 128B-swizzled TMA box would put it.  A box of 8 MT + 2 rows is
+    // built in MT row segments (10 rows, then 8 at a time); output rows 2m+1 .. 2m+10 read the low-resolution rows
+    // m .. m+5 (b2u_bilinear.cuh), all 12 16-byte loads of a segment are issued one segment ahead of their use.
+    const int ut = threadIdx.x - 192;
+    const int col = ut >> 3, ch = ut & 7;
+    const int HL = p.H >> 1, WL = p.W >> 1;
+    const int c8 = p.C1 >> 3;                              // 16-byte vectors per low-resolution pixel
+    constexpr int R = Cfg::kARows / kWb;                   // box rows
+    constexpr int NSEG = MT;
+    constexpr int SEG_ROWS = 6;
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t boxes = 0;                                    // A slots handed out so far (all channel blocks, ring order)
+    int qs = 0;
+    uint32_t qp = 0;
+    for (;;) {
+      mbar_wait(q_full(qs), qp);
+      const int tile = tq[qs];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_empty(qs));
+      if (++qs == Cfg::kQ) { qs = 0; qp ^= 1u; }
+      if (tile < 0) break;
+      const int n_tile = tile % p.num_n_tiles;
+      int m_tile = tile / p.num_n_tiles;
+      const int tw = m_tile % p.tiles_w; m_tile /= p.tiles_w;
+      const int th = m_tile % p.tiles_h;
+      const int img = m_tile / p.tiles_h;
+      const int w0 = tw * kWb, hb = th * (kHb * MT) - 1;
+      const int total = (chunks - chunks0) * 3 * NSEG;
+      const uint4* lowimg = reinterpret_cast<const uint4*>(p.up_low) + static_cast<size_t>(img) * HL * WL * c8 + ch;
+      uint4* upimg = p.up_out != nullptr && n_tile == 0
+                         ? reinterpret_cast<uint4*>(p.up_out) + static_cast<size_t>(img) * p.H * p.W * c8 + ch : nullptr;
+
+      // segment u -> (up-sampled channel block cu, horizontal tap s, row segment seg)
+      auto seg_load = [&](int u, uint4 (&buf)[2 * SEG_ROWS]) {
+        const int seg = u % NSEG, bs = u / NSEG, s = bs % 3, cu = bs / 3;
+        const int wo = w0 + s - 1 + col;
+        int c0i, c1i; float lw;
+        src_index(wo >= 0 && wo < p.W ? wo : 0, p.up_sw, WL, c0i, c1i, lw);
+        const int m = (hb + (seg == 0 ? 0 : 2 + 8 * seg) - 1) >> 1;
+        const uint4* base = lowimg + cu * 8;
+#pragma unroll
+        for (int k = 0; k < SEG_ROWS; ++k) {
+          int j = m + k;
+          j = j < 0 ? 0 : (j > HL - 1 ? HL - 1 : j);         // rows outside the image carry zero weight
+          const uint4* rowp = base + static_cast<size_t>(j) * WL * c8;
+          buf[2 * k] = __ldg(rowp + static_cast<size_t>(c0i) * c8);
+          buf[2 * k + 1] = __ldg(rowp + static_cast<size_t>(c1i) * c8);
+        }
+      };
+      auto seg_compute = [&](int u, const uint4 (&buf)[2 * SEG_ROWS]) {
+        const int seg = u % NSEG, bs = u / NSEG, s = bs % 3, cu = bs / 3;
+        const uint32_t bidx = boxes + static_cast<uint32_t>(chunks0 * 3 + bs);
+        const uint32_t slot = bidx % SA;
+        if (seg == 0) mbar_wait(a_empty(slot), ((bidx / SA) & 1u) ^ 1u);
+        const uint32_t box = sA + slot * Cfg::kABytes;
+        const int wo = w0 + s - 1 + col;
+        const bool colok = wo >= 0 && wo < p.W;
+        int c0i, c1i; float lw;
+        src_index(colok ? wo : 0, p.up_sw, WL, c0i, c1i, lw);
+        const float w0l = 1.f - lw;
+        const int r0 = seg == 0 ? 0 : 2 + 8 * seg;
+        const int m = (hb + r0 - 1) >> 1;
+        float va[8], vb[8];
+        hlerp8(buf[0], buf[1], w0l, lw, va);
+#pragma unroll
+        for (int t = 0; t < 10; ++t) {
+          if (t >= 8 && seg != 0) break;
+          if ((t & 1) == 0) {
+            if (t > 0) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) va[k] = vb[k];
+            }
+            hlerp8(buf[2 * (t / 2 + 1)], buf[2 * (t / 2 + 1) + 1], w0l, lw, vb);
+          }
+          const int r = r0 + t, o = hb + r;
+          const bool inside = colok && o >= 0 && o < p.H;       // outside the image: the conv's zero padding
+          float wa, wb;
+          pair_weights(o, m + t / 2, p.up_sh, HL, p.H, wa, wb);
+          const uint4 v = inside ? vlerp8(va, vb, wa, wb) : zero4;
+          const int q = r * kWb + col;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(box + q * 128 + ((ch ^ (q & 7)) << 4)), "r"(v.x), "r"(v.y),
+                       "r"(v.z), "r"(v.w) : "memory");
+          // by-product for the weight gradient: the centre-tap box covers exactly this tile's pixels in its rows 1 .. R-2
+          if (upimg != nullptr && s == 1 && inside && r >= 1 && r <= R - 2)
+            upimg[(static_cast<size_t>(o) * p.W + wo) * c8 + cu * 8] = v;
+        }
+        if (seg == NSEG - 1) {
+          fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          named_bar_sync(4, kUpWarps * 32);
+          if (ut == 0) mbar_arrive(a_full(slot));
+        }
+      };
+
+      uint4 bufA[2 * SEG_ROWS], bufB[2 * SEG_ROWS];
+      if (total > 0) seg_load(0, bufA);
+      // walk past the skip tensor's slots in ring order (a parity wait must stay within one phase of its barrier)
+      for (uint32_t i = 0, bidx = boxes; i < static_cast<uint32_t>(chunks0 * 3); ++i, ++bidx)
+        mbar_wait(a_empty(bidx % SA), ((bidx / SA) & 1u) ^ 1u);
+      for (int u = 0; u < total; u += 2) {
+        if (u + 1 < total) seg_load(u + 1, bufB);
+        seg_compute(u, bufA);
+        if (u + 2 < total) seg_load(u + 2, bufA);
+        if (u + 1 < total) seg_compute(u + 1, bufB);
+      }
+      boxes += static_cast<uint32_t>(chunks * 3);
     }
   } else {
     // ===================== epilogue (4 warps, 128 threads) =====================
@@ -523,10 +653,10 @@ static int* sched_slot() {
   return base[dev] + 2 * (next.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
 }
 
-template <int BN, int TAPS, int MT, int RB, int SA, int SB, int MD = 0>
+template <int BN, int TAPS, int MT, int RB, int SA, int SB, int MD = 0, int UP = 0>
 static int launch_cfg(const ConvLaunch& a, cudaStream_t st) {
-  using Cfg = ConvCfg<BN, TAPS, MT, RB, SA, SB, MD>;
-  auto kern = conv_igemm_kernel<BN, TAPS, MT, RB, SA, SB, MD>;
+  using Cfg = ConvCfg<BN, TAPS, MT, RB, SA, SB, MD, UP>;
+  auto kern = conv_igemm_kernel<BN, TAPS, MT, RB, SA, SB, MD, UP>;
   static bool attr_done[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -540,10 +670,10 @@ static int launch_cfg(const ConvLaunch& a, cudaStream_t st) {
   CUtensorMap tmA0, tmA1, tmB, tmC0, tmC1;
   int rc;
   if ((rc = make_tmap_nhwc(&tmA0, a.x0, a.N, a.H, a.W, a.C0, KB, kWb, a_box_h, swz))) return rc;
-  if (a.C1 > 0) {
+  if (a.C1 > 0 && !UP) {
     if ((rc = make_tmap_nhwc(&tmA1, a.x1, a.N, a.H, a.W, a.C1, KB, kWb, a_box_h, swz))) return rc;
   } else {
-    tmA1 = tmA0;
+    tmA1 = tmA0;       // UP: source 1 is read by the interpolation warps, not by TMA
   }
   const int ctot = a.C0 + a.C1;
   if ((rc = make_tmap_2d(&tmB, a.wpacked, (uint64_t)TAPS * ctot, a.Cout, KB, BN, swz))) return rc;
@@ -570,9 +700,14 @@ static int launch_cfg(const ConvLaunch& a, cudaStream_t st) {
   p.mask = a.mask;
   p.mask_c = a.mask_c;
   p.sched = MD > 0 ? nullptr : sched_slot();      // the mask-stream variants prefetch across tile boundaries: static order
+  p.up_low = UP ? static_cast<const __nv_bfloat16*>(a.up_low) : nullptr;
+  p.up_out = UP ? static_cast<__nv_bfloat16*>(a.up_out) : nullptr;
+  // the scale factors of b2u_upsample2x_fwd (ATen's align_corners=True ratio for a 2x enlargement)
+  p.up_sh = a.H > 1 ? static_cast<float>(a.H / 2 - 1) / static_cast<float>(a.H - 1) : 0.f;
+  p.up_sw = a.W > 1 ? static_cast<float>(a.W / 2 - 1) / static_cast<float>(a.W - 1) : 0.f;
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, 192, Cfg::kSmemBytes, st>>>(tmA0, tmA1, tmB, tmC0, tmC1, p);
+  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmA0, tmA1, tmB, tmC0, tmC1, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(B2U_ERR_CUDA, "conv_igemm launch: %s", cudaGetErrorString(e));
   note_launch();
@@ -618,6 +753,20 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st) {
 
   // tall = two stacked M tiles per CTA step (halves the weight traffic per pixel); pointless for tiny images
   const bool tall = a.H > kHb && !(a.tile_flags & 1);
+  if (a.up_low != nullptr) {
+    // decoder conv over [skip, upsample2x(low)]: same tiles as the plain 3x3 forward, plus the interpolation warps
+    if (a.taps != 9 || a.C1 <= 0 || (a.H & 1) || (a.W & 1) || (a.flags & 6) || a.y1 != nullptr)
+      return set_error(B2U_ERR_SHAPE, "decoder conv: needs a 3x3 forward conv over even H, W with an up-sampled source");
+    switch (bn) {
+      case 256: return launch_cfg<256, 9, 1, 1, 3, 4, 0, 1>(a, st);
+      case 192: return launch_cfg<192, 9, 1, 1, 3, 5, 0, 1>(a, st);
+      case 128: return tall ? launch_cfg<128, 9, 2, 3, 2, 2, 0, 1>(a, st) : launch_cfg<128, 9, 1, 3, 3, 2, 0, 1>(a, st);
+      case 64:
+        if (tall && !(a.tile_flags & 2) && a.H >= 4 * kHb) return launch_cfg<64, 9, 4, 3, 2, 2, 0, 1>(a, st);
+        return tall ? launch_cfg<64, 9, 2, 3, 3, 3, 0, 1>(a, st) : launch_cfg<64, 9, 1, 3, 4, 4, 0, 1>(a, st);
+    }
+    return set_error(B2U_ERR_SHAPE, "conv: unsupported N tile %d", bn);
+  }
   if (a.taps == 9) {
     switch (bn) {
       case 256: return launch_cfg<256, 9, 1, 1, 3, 4>(a, st);
@@ -700,6 +849,29 @@ int b2u_conv_fprop_scaled(const void* x0, int C0, const void* x1, int C1, const 
   a.flags = relu ? 1 : 0;
   a.bn_override = bn_override & 0xffff;
   a.tile_flags = bn_override >> 16;
+  return b2u::launch_conv(a, static_cast<cudaStream_t>(stream));
+}
+
+// First conv of a decoder stage (nets/unet.py:16-18: conv1(cat([skip, up(low)])) with up = nn.UpsamplingBilinear2d(2)):
+// `low` is the LOW-RESOLUTION tensor [N, H/2, W/2, C1]; it is interpolated inside the kernel, on the way into the
+// A-operand stage, so neither the concat nor the up-sampled tensor is read from HBM.  up_out (nullable) receives the
+// up-sampled tensor [N, H, W, C1] as a by-product (training: operand of this conv's weight gradient).
+// scale (nullable): folded eval-mode BatchNorm as in b2u_conv_fprop_scaled; stat_partial (nullable): as in b2u_conv_fprop_stats.
+int b2u_decoder_conv_fprop(const void* skip, int C0, const void* low, int C1, const void* wf, const float* scale,
+                           const float* bias, void* y, void* up_out, int N, int H, int W, int Cout, int relu, int bn_override,
+                           float* stat_partial, int stat_rows, void* stream) {
+  if (skip == nullptr || low == nullptr) return b2u::set_error(B2U_ERR_ARG, "decoder_conv_fprop: skip and low tensors are required");
+  if (stat_partial != nullptr && stat_rows < b2u::conv_m_tiles(N, H, W, Cout, 9, bn_override))
+    return b2u::set_error(B2U_ERR_ARG, "decoder_conv_fprop: statistics buffer too small");
+  b2u::ConvLaunch a;
+  a.x0 = skip; a.C0 = C0; a.x1 = nullptr; a.C1 = C1;
+  a.up_low = low; a.up_out = up_out;
+  a.wpacked = wf; a.bias = bias; a.scale = scale; a.y0 = y;
+  a.N = N; a.H = H; a.W = W; a.Cout = Cout; a.taps = 9;
+  a.flags = relu ? 1 : 0;
+  a.bn_override = bn_override & 0xffff;
+  a.tile_flags = bn_override >> 16;
+  a.stat_partial = stat_partial;
   return b2u::launch_conv(a, static_cast<cudaStream_t>(stream));
 }
 

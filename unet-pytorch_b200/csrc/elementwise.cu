@@ -11,6 +11,7 @@
 //   nhwc<->nchw    : layout converters for the module boundary
 #include "b2u_internal.h"
 #include "b2u_ptx.cuh"
+#include "b2u_bilinear.cuh"
 
 namespace b2u {
 
@@ -34,16 +35,7 @@ static inline dim3 row_grid(long long rows, int row_items, int block) {
   } while (0)
 
 __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
-__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
-  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
-  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
-}
-__device__ __forceinline__ uint4 pack8(const float* f) {
-  uint4 v;
-  v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
-  v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
-  return v;
-}
+// unpack8 / pack8 and the bilinear index arithmetic live in b2u_bilinear.cuh (shared with conv_igemm.cu)
 
 // ---------------------------------------------------------------------------------------------
 // first-layer im2col: col[n,h,w,k] = x[n,c,h+r-1,w+s-1] for k = (r*3+s)*Cin + c < 9*Cin, else 0
@@ -268,22 +260,7 @@ __global__ void maxpool2x2_bwd_kernel(const uint4* __restrict__ dpool, const uin
 // ---------------------------------------------------------------------------------------------
 // bilinear 2x upsample, align_corners=True
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void src_index(int o, float scale, int in_size, int& i0, int& i1, float& lam) {
-  const float src = scale * static_cast<float>(o);   // ATen area_pixel_compute_source_index(align_corners=True)
-  i0 = static_cast<int>(src);
-  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
-  lam = src - static_cast<float>(i0);
-}
-// For scale 2 with align_corners=True, output index o reads low-res indices i0(o), i1(o) that always lie in
-// {j, j + 1} with j = floor((o - 1) / 2) (checked exhaustively in float arithmetic for every size up to 1024), so
-// output rows 2i+1 and 2i+2 interpolate between the same two source rows i and i+1.  weight_of(o, i) is the weight of
-// low-res index i in output o under ATen's formula.
-__device__ __forceinline__ float weight_of(int o, int i, float scale, int in_size, int out_size) {
-  if (o < 0 || o >= out_size) return 0.f;
-  int i0, i1; float lam;
-  src_index(o, scale, in_size, i0, i1, lam);
-  return (i0 == i ? 1.f - lam : 0.f) + (i1 == i ? lam : 0.f);
-}
+// src_index / weight_of / pair_weights / hlerp8 / vlerp8: b2u_bilinear.cuh
 
 constexpr int kUpRows = 8;      // low-res rows per strip
 
@@ -307,19 +284,12 @@ upsample2x_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H,
     a = __ldg(img + (static_cast<size_t>(hc) * W + w0) * C8);
     b = __ldg(img + (static_cast<size_t>(hc) * W + w1) * C8);
   };
-  auto hlerp = [&](const uint4& a, const uint4& b, float* v) {
-    float fa[8], fb[8];
-    unpack8(a, fa); unpack8(b, fb);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = w0l * fa[k] + lw * fb[k];
-  };
+  auto hlerp = [&](const uint4& a, const uint4& b, float* v) { hlerp8(a, b, w0l, lw, v); };
   auto emit = [&](int o, int i, const float* va, const float* vb) {     // output row o from source rows i, i+1
     if (o >= Ho) return;
-    const float wa = weight_of(o, i, sh, H, Ho), wb = weight_of(o, i + 1, sh, H, Ho);
-    float v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = fmaf(wb, vb[k], wa * va[k]);
-    out[static_cast<size_t>(o) * Wo * C8] = pack8(v);
+    float wa, wb;
+    pair_weights(o, i, sh, H, Ho, wa, wb);
+    out[static_cast<size_t>(o) * Wo * C8] = vlerp8(va, vb, wa, wb);
   };
   uint4 na, nb;
   fetch(i_begin, na, nb);

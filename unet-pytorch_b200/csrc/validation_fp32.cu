@@ -893,6 +893,19 @@ int b2u_conv_fprop_scaled(const void* x0, int C0, const void* x1, int C1, const 
   return v32_fprop(x0, C0, x1, C1, wf, scale, bias, y, N, H, W, Cout, taps, relu, stream);
 }
 
+int b2u_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream);
+// the validation build keeps the two steps apart: it up-samples into up_out (required here) and convolves the pair
+int b2u_decoder_conv_fprop(const void* skip, int C0, const void* low, int C1, const void* wf, const float* scale, const float* bias,
+                           void* y, void* up_out, int N, int H, int W, int Cout, int relu, int /*bn_override*/,
+                           float* /*stat_partial*/, int /*stat_rows*/, void* stream) {
+  if (!skip || !low) return set_error(B2U_ERR_ARG, "decoder_conv_fprop: skip and low tensors are required");
+  if (!up_out) return set_error(B2U_ERR_ARG, "decoder_conv_fprop (fp32 validation build): up_out buffer is required");
+  if ((H & 1) || (W & 1)) return set_error(B2U_ERR_SHAPE, "decoder_conv_fprop: H and W must be even");
+  const int rc = b2u_upsample2x_fwd(low, up_out, N, H / 2, W / 2, C1, stream);
+  if (rc) return rc;
+  return v32_fprop(skip, C0, up_out, C1, wf, scale, bias, y, N, H, W, Cout, 9, relu, stream);
+}
+
 int b2u_conv_dgrad(const void* dz, int Cz, const void* wd, void* dx0, int C0, void* dx1, int C1, const void* mask, int N, int H,
                    int W, int taps, int /*bn_override*/, void* stream) {
   if (mask && dx1) return set_error(B2U_ERR_ARG, "dgrad: mask is only supported with a single output");

@@ -144,6 +144,9 @@ class UNetEngine:
         # db from the wgrad kernel's bias warps (3x3 layers) instead of a separate pass over dz: an A/B on one box
         # (scripts/ab_fuse_bias.py: 23.2-23.9 vs 23.4-23.5 ms/step) shows no gain, so the separate pass stays the default
         self.fuse_bias_grad = False
+        # bilinear 2x up-sampling + concat folded into the decoder conv's operand load (b2u_decoder_conv_fprop);
+        # B2U_FUSE_UPSAMPLE=0 restores the separate b2u_upsample2x_fwd pass (A/B runs, tests compare the two bit for bit)
+        self.fuse_upsample = os.environ.get("B2U_FUSE_UPSAMPLE", "1") == "1"
         # Weight/bias gradients on a second stream (plain conv+ReLU nets): wgrad_L depends only on dz_L and the saved
         # activation, not on the dgrad chain, so its launches are queued on a side stream behind an event and the
         # HBM-bound glue of the main chain (pool / upsample adjoints, bias column sums) shares the SMs with tensor-core-bound
@@ -268,13 +271,23 @@ class UNetEngine:
         self._pack_versions = None
 
     # ------------------------------------------------------------------ one conv (+BN) + ReLU layer, forward
-    def _layer_fwd(self, c, x0, params, A, training, x1=None, save=True):
+    def _layer_fwd(self, c, x0, params, A, training, x1=None, save=True, low=None, up_out=None):
+        """low (instead of x1): the second source is upsample2x(low), interpolated inside the conv kernel
+        (ops.decoder_conv_fprop); up_out then optionally receives the up-sampled tensor as a by-product."""
         n, h, w, _ = x0.shape
         bias = self._padded_vec("b:" + c.name, params[c.name + ".bias"], c.cout_p)
         taps = 1 if c.first else 9
+
+        def conv(bias_, relu, out, stats=None, scale=None):
+            if low is not None:
+                return ops.decoder_conv_fprop(x0, low, c.wf, bias_, c.cout_p, relu=relu, out=out, up_out=up_out, scale=scale, stats=stats)
+            if scale is not None:
+                return ops.conv_fprop_scaled(x0, c.wf, scale, bias_, c.cout_p, taps=taps, relu=relu, x1=x1, out=out)
+            return ops.conv_fprop(x0, c.wf, bias_, c.cout_p, taps=taps, relu=relu, x1=x1, out=out, stats=stats)
+
         if not c.bn:
             out = self._buf(c.name, (n, h, w, c.cout_p))
-            ops.conv_fprop(x0, c.wf, bias, c.cout_p, taps=taps, relu=True, x1=x1, out=out)
+            conv(bias, True, out)
             A[c.name] = out
             return out
         if not training and not save:
@@ -288,7 +301,7 @@ class UNetEngine:
             sc, bs = ops.bn_fold(gamma, beta, rmp, rvp, bias, self.eps, scale=self._buf("fs:" + c.bn, (c.cout_p,), torch.float32),
                                  bias=self._buf("fb:" + c.bn, (c.cout_p,), torch.float32))
             out = self._buf(c.name, (n, h, w, c.cout_p))
-            ops.conv_fprop_scaled(x0, c.wf, sc, bs, c.cout_p, taps=taps, relu=True, x1=x1, out=out)
+            conv(bs, True, out, scale=sc)
             A[c.name] = out
             return out
         z = self._buf("z:" + c.name, (n, h, w, c.cout_p))
@@ -304,11 +317,11 @@ class UNetEngine:
         # training: the conv epilogue also emits the BatchNorm statistics of z (per-tile sums), so BatchNorm skips its
         # statistics pass over z
         stats, rows = None, 0
-        kdim = taps * (x0.shape[3] + (x1.shape[3] if x1 is not None else 0))
+        kdim = taps * (x0.shape[3] + (x1.shape[3] if x1 is not None else 0) + (low.shape[3] if low is not None else 0))
         if training and self.fuse_bn_stats and self.sync_bn_group is None and (kdim >= self.bn_stats_min_k or c.cout_p >= self.bn_stats_min_cout):
             rows = ops.conv_stat_rows(n, h, w, c.cout_p, taps)
             stats = self._workspace("bnstat", rows * 2 * c.cout_p * 4)[:rows * 2 * c.cout_p * 4].view(torch.float32)
-        ops.conv_fprop(x0, c.wf, bias, c.cout_p, taps=taps, relu=False, x1=x1, out=z, stats=stats)
+        conv(bias, False, z, stats=stats)
         gamma = self._padded_vec("g:" + c.bn, params[c.bn + ".weight"], c.cout_p, fill=1.0)
         beta = self._padded_vec("bt:" + c.bn, params[c.bn + ".bias"], c.cout_p)
         out = self._buf(c.name, (n, h, w, c.cout_p))
@@ -388,10 +401,18 @@ class UNetEngine:
         for si, (c1, c2) in enumerate(self.dec):
             skip = feats[len(self.enc) - 2 - si]
             _, hl, wl, cl = low.shape
-            up = self._buf(f"up{si}", (N, 2 * hl, 2 * wl, cl))
-            ops.upsample2x(low, out=up)
+            if self.fuse_upsample:
+                # the decoder conv interpolates `low` inside its producer warps (nets/unet.py:16-18 in one kernel); the
+                # up-sampled tensor is written only when a backward pass will need it as the weight gradient's operand
+                # (the fp32 validation build always takes the buffer: it keeps the two steps apart)
+                keep = save or ops.act_dtype() == torch.float32
+                up = self._buf(f"up{si}", (N, 2 * hl, 2 * wl, cl)) if keep else None
+                o1 = self._layer_fwd(c1, skip, params, A, training, save=save, low=low, up_out=up)
+            else:
+                up = self._buf(f"up{si}", (N, 2 * hl, 2 * wl, cl))
+                ops.upsample2x(low, out=up)
+                o1 = self._layer_fwd(c1, skip, params, A, training, x1=up, save=save)
             A[f"up{si}"] = up
-            o1 = self._layer_fwd(c1, skip, params, A, training, x1=up, save=save)
             low = self._layer_fwd(c2, o1, params, A, training, save=save)
         wh = self._head_weight(params)
         # 1x1 classifier on the tensor cores: [hi | lo] bf16 split of the fp32 weights, fp32 NCHW logits from the epilogue

@@ -40,13 +40,14 @@ def pad64(c):
 
 
 class _T:
-    __slots__ = ("data", "grad", "fused_relu", "needs_grad", "aux", "stats", "folded", "centered")
+    __slots__ = ("data", "grad", "fused_relu", "needs_grad", "aux", "stats", "folded", "centered", "low")
 
     def __init__(self, data, fused_relu=False, needs_grad=False):
         self.data, self.grad, self.fused_relu, self.needs_grad, self.aux = data, None, fused_relu, needs_grad, None
         self.stats = None      # (fp32 per-tile column sums, rows) when the producing conv emitted BatchNorm statistics
         self.folded = False    # eval mode: this conv output already is the BatchNorm (+ReLU) output
         self.centered = False  # training: stored as z - running_mean of the BatchNorm that reads it
+        self.low = None        # an "up" output not materialised yet: the low-resolution tensor the reading conv interpolates itself
 
 
 def resnet50_unet_program(num_classes):
@@ -329,6 +330,13 @@ class GraphEngine:
         # eval-mode folding: conv output -> the BatchNorm (without residual) that is its only reader
         self._fold_bn = {i["z"]: i for i in program if i["op"] == "bn" and i["z"] in self._pre_bn and not i["res"]}
         self._bn_reader = {i["z"]: i for i in program if i["op"] == "bn" and i["z"] in self._pre_bn}      # conv output -> its BatchNorm
+        # "up" outputs read exactly once, as the SECOND source of a stride-1 3x3 conv (unetUp, nets/unet.py:16-18): that conv
+        # interpolates the low-resolution tensor in its producer warps (b2u_decoder_conv_fprop) and the "up" instruction
+        # launches nothing.  B2U_FUSE_UPSAMPLE=0 restores the separate pass.
+        self.fuse_upsample = os.environ.get("B2U_FUSE_UPSAMPLE", "1") == "1"
+        ups = {i["out"] for i in program if i["op"] == "up"}
+        self._lazy_up = {i["x1"] for i in program if i["op"] == "conv" and i.get("x1") in ups and len(readers.get(i["x1"], [])) == 1
+                         and i["taps"] == 9 and i["stride"] == 1 and not i.get("pk")}
 
     # ------------------------------------------------------------------ static description
     def param_shapes(self):
@@ -580,6 +588,17 @@ class GraphEngine:
                     continue
                 coutp = pad64(ins["cout"])
                 bias = self._padded("b:" + ins["w"], params[ins["bias"]], (coutp,)) if ins["bias"] else None
+                low = up_out = None
+                if x1 is not None and x1.data is None:
+                    # second source = upsample2x(low), interpolated inside the conv; the up-sampled tensor is written (as a
+                    # by-product) only when a backward pass needs it as the weight gradient's operand
+                    low = x1.low
+                    if save or ops.act_dtype() == torch.float32:
+                        up_out = self._buf(ins["x1"], (n, h, w, low.shape[3]))
+                    if bias is None:
+                        bias = self._bufs.get("b0:" + ins["w"])
+                        if bias is None or bias.numel() != coutp:
+                            bias = self._bufs["b0:" + ins["w"]] = torch.zeros((coutp,), dtype=torch.float32, device=self.device)
                 shift = self._center_shift(ins, params, training, coutp)
                 if shift is not None:
                     cb = self._buf("bc:" + ins["w"], (coutp,), torch.float32)
@@ -592,7 +611,11 @@ class GraphEngine:
                 if fold is not None:
                     # eval mode: y = [relu](acc * s + b') straight from the conv epilogue; the BatchNorm instruction passes it on
                     sc, bs = self._folded_bn(fold, params, params[ins["bias"]] if ins["bias"] else None, coutp)
-                    if ins["stride"] == 1:
+                    if ins["stride"] == 1 and low is not None:
+                        z = self._buf(ins["out"], (n, h, w, coutp))
+                        ops.decoder_conv_fprop(xin.data, low, wf, bs, coutp, relu=fold["relu"], out=z, up_out=up_out, scale=sc)
+                        x1.data = up_out
+                    elif ins["stride"] == 1:
                         z = self._buf(ins["out"], (n, h, w, coutp))
                         ops.conv_fprop_scaled(xin.data, wf, sc, bs, coutp, taps=ins["taps"], relu=fold["relu"],
                                               x1=x1.data if x1 else None, out=z)
@@ -610,15 +633,20 @@ class GraphEngine:
                     continue
                 if ins["stride"] == 1:
                     z = self._buf(ins["out"], (n, h, w, coutp))
-                    kdim = ins["taps"] * (xin.data.shape[3] + (x1.data.shape[3] if x1 else 0))
+                    kdim = ins["taps"] * (xin.data.shape[3] + (low.shape[3] if low is not None else x1.data.shape[3] if x1 else 0))
                     if (training and self.fuse_bn_stats and self.sync_bn_group is None and ins["out"] in self._pre_bn
                             and (kdim >= self.bn_stats_min_k or coutp >= self.bn_stats_min_cout)):
                         # the BatchNorm that reads this output takes its statistics from this conv's epilogue (no pass over
                         # z); one buffer per conv output: another conv may run before that BatchNorm (downsample branches)
                         rows = ops.conv_stat_rows(n, h, w, coutp, ins["taps"])
                         stats = (self._workspace("bnstat:" + ins["out"], rows * 2 * coutp * 4)[:rows * 2 * coutp * 4].view(torch.float32), rows)
-                    ops.conv_fprop(xin.data, wf, bias, coutp, taps=ins["taps"], relu=ins["relu"],
-                                   x1=x1.data if x1 else None, out=z, stats=stats[0] if stats else None)
+                    if low is not None:
+                        ops.decoder_conv_fprop(xin.data, low, wf, bias, coutp, relu=ins["relu"], out=z, up_out=up_out,
+                                               stats=stats[0] if stats else None)
+                        x1.data = up_out
+                    else:
+                        ops.conv_fprop(xin.data, wf, bias, coutp, taps=ins["taps"], relu=ins["relu"],
+                                       x1=x1.data if x1 else None, out=z, stats=stats[0] if stats else None)
                 elif ins["taps"] == 9:      # 3x3 stride 2 = stride-1 conv, keep even pixels
                     full = self._buf(ins["out"] + ":full", (n, h, w, coutp))
                     ops.conv_fprop(xin.data, wf, bias, coutp, taps=9, relu=ins["relu"], out=full)
@@ -728,6 +756,11 @@ class GraphEngine:
             elif op == "up":
                 xin = T[ins["x"]]
                 n, h, w, c = xin.data.shape
+                if self.fuse_upsample and ins["out"] in self._lazy_up:
+                    t = _T(None, needs_grad=xin.needs_grad)          # the reading conv interpolates xin itself
+                    t.low = xin.data
+                    T[ins["out"]] = t
+                    continue
                 y = ops.upsample2x(xin.data, out=self._buf(ins["out"], (n, 2 * h, 2 * w, c)))
                 T[ins["out"]] = _T(y, needs_grad=xin.needs_grad)
             elif op == "head":

@@ -191,6 +191,27 @@ def conv_fprop_scaled(x0, wf, scale, bias, Cout, taps=9, relu=True, x1=None, out
     return out
 
 
+def decoder_conv_fprop(skip, low, wf, bias, Cout, relu=True, out=None, up_out=None, scale=None, stats=None, bn=0):
+    """conv3x3(cat([skip, upsample2x(low)])) with the bilinear up-sampling done by the conv's producer warps (nets/unet.py:16-18).
+    low: [N, H/2, W/2, C1].  up_out (optional [N,H,W,C1]): by-product copy of the up-sampled tensor for the weight gradient.
+    scale: folded eval-mode BatchNorm; stats: per-tile BatchNorm sums as in conv_fprop."""
+    _req(skip, ACT, "skip"); _req(low, ACT, "low"); _req(wf, ACT, "wf"); _req(bias, torch.float32, "bias")
+    _req(scale, torch.float32, "scale"); _req(stats, torch.float32, "stats"); _req(up_out, ACT, "up_out")
+    N, H, W, C0 = skip.shape
+    Nl, HL, WL, C1 = low.shape
+    if Nl != N or 2 * HL != H or 2 * WL != W:
+        raise ValueError(f"decoder_conv_fprop: low {tuple(low.shape)} is not half the resolution of skip {tuple(skip.shape)}")
+    if up_out is not None and tuple(up_out.shape) != (N, H, W, C1):
+        raise ValueError("decoder_conv_fprop: up_out must be [N, H, W, C1]")
+    if out is None:
+        out = torch.empty((N, H, W, Cout), dtype=ACT, device=skip.device)
+    with _timed(f"conv_igemm|fprop|{N}x{H}x{W}|{C0}+{C1}->{Cout}|t9", 2.0 * N * H * W * Cout * (C0 + C1) * 9):
+        check(lib().b2u_decoder_conv_fprop(ptr(skip), C0, ptr(low), C1, ptr(wf), ptr(scale), ptr(bias), ptr(out), ptr(up_out),
+                                           N, H, W, Cout, 1 if relu else 0, bn, ptr(stats),
+                                           0 if stats is None else stats.numel() // (2 * Cout), stream_ptr()))
+    return out
+
+
 def bn_fold(gamma, beta, running_mean, running_var, conv_bias, eps=1e-5, scale=None, bias=None):
     C = running_mean.numel()
     if scale is None:
