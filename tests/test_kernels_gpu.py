@@ -99,6 +99,8 @@ DECODER_CASES = [
     (1, 4, 4, 512, 512, 512),      # image smaller than a tile: the 2x2 low tensor, two N tiles
     (1, 12, 20, 64, 64, 192),      # N tile 192
     (3, 6, 10, 64, 64, 64),        # odd low-resolution sizes (3 x 5)
+    (8, 128, 256, 64, 64, 64),     # 512 / 1024 / 2048 tiles: every CTA of the persistent grid walks several tiles (slot hand-off phases)
+    (4, 64, 128, 64, 128, 256),    # the same for the wide N tiles (256 tiles; 512 with N tile 128; 1024 with N tile 64)
 ]
 
 

@@ -94,7 +94,7 @@ struct ConvCfg {
   static constexpr int kOffMask = kOffStat + 4 * 64 * 2 * 4; // MD thread-private mask tiles [128 rows][128 B]
   static constexpr int kOffBar = kOffMask + MD * kTileM * 128;  // (bias of the current N tile is double buffered by tile parity)
   static constexpr int kQ = 4;                                  // depth of the tile-id queue (producer -> MMA / epilogue warps)
-  static constexpr int kNumBar = 2 * SA + 2 * SB + 4 + 2 * kQ;
+  static constexpr int kNumBar = 2 * SA + 2 * SB + 4 + 2 * kQ + (UP ? SA : 0);   // UP: one "slot is yours" barrier per A slot
   static constexpr int kOffTmem = kOffBar + kNumBar * 8;
   static constexpr int kOffTq = kOffTmem + 16;
   static constexpr int kSmemBytes = kOffTq + kQ * 4 + 1024;  // + alignment slack
@@ -137,6 +137,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   auto t_empty = [&](int i) { return bars + 8u * (2 * SA + 2 * SB + 2 + i); };
   auto q_full = [&](int i) { return bars + 8u * (2 * SA + 2 * SB + 4 + i); };
   auto q_empty = [&](int i) { return bars + 8u * (2 * SA + 2 * SB + 4 + Cfg::kQ + i); };
+  auto u_go = [&](int i) { return bars + 8u * (2 * SA + 2 * SB + 4 + 2 * Cfg::kQ + i); };   // TMA thread -> interpolation warps
   volatile int* tq = reinterpret_cast<volatile int*>(smem_gen + Cfg::kOffTq);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kOffTmem);
 
@@ -153,6 +154,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     for (int i = 0; i < SB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(t_full(i), 1); mbar_init(t_empty(i), 4); }
     for (int i = 0; i < Cfg::kQ; ++i) { mbar_init(q_full(i), 1); mbar_init(q_empty(i), 5 + (UP ? kUpWarps : 0)); }      // readers: MMA thread + 4 epilogue warps (+ interpolation warps)
+    if (UP) for (int i = 0; i < SA; ++i) mbar_init(u_go(i), 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -197,10 +199,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           const CUtensorMap* tm = c < chunks0 ? &tmA0 : &tmA1;
           const int cc = c < chunks0 ? c * KB : c * KB - p.C0;
           for (int s = 0; s < S_TAPS; ++s) {
-            // (the wait is kept for the slots the interpolation warps fill: a parity wait must never run more than one
-            // phase ahead of its barrier)
+            // This thread is the only one that follows the a_empty phases (a parity wait is exact only within one phase of
+            // its barrier, and the interpolation warps skip the skip tensor's slots): a free slot of an up-sampled channel
+            // block is handed to them through u_go, which by construction never runs more than one phase ahead of them.
             mbar_wait(a_empty(sa), pa ^ 1u);
-            if (!(UP && c >= chunks0)) {
+            if (UP && c >= chunks0) {
+              mbar_arrive(u_go(sa));
+            } else {
               mbar_expect_tx(a_full(sa), Cfg::kABytes);
               if (TAPS == 9) tma_load_4d(sA + sa * Cfg::kABytes, tm, a_full(sa), cc, w0 + s - 1, h0 - 1, img);
               else           tma_load_4d(sA + sa * Cfg::kABytes, tm, a_full(sa), cc, w0, h0, img);
@@ -290,6 +295,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     constexpr int SEG_ROWS = 6;
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
     uint32_t boxes = 0;                                    // A slots handed out so far (all channel blocks, ring order)
+    uint32_t go_phase = 0;                                 // bit i: parity of the next u_go(i) phase to wait for
     int qs = 0;
     uint32_t qp = 0;
     for (;;) {
@@ -331,7 +337,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const int seg = u % NSEG, bs = u / NSEG, s = bs % 3, cu = bs / 3;
         const uint32_t bidx = boxes + static_cast<uint32_t>(chunks0 * 3 + bs);
         const uint32_t slot = bidx % SA;
-        if (seg == 0) mbar_wait(a_empty(slot), ((bidx / SA) & 1u) ^ 1u);
+        if (seg == 0) {                                     // the TMA thread saw the slot's previous contents consumed
+          mbar_wait(u_go(slot), (go_phase >> slot) & 1u);
+          go_phase ^= 1u << slot;
+        }
         const uint32_t box = sA + slot * Cfg::kABytes;
         const int wo = w0 + s - 1 + col;
         const bool colok = wo >= 0 && wo < p.W;
@@ -373,9 +382,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
       uint4 bufA[2 * SEG_ROWS], bufB[2 * SEG_ROWS];
       if (total > 0) seg_load(0, bufA);
-      // walk past the skip tensor's slots in ring order (a parity wait must stay within one phase of its barrier)
-      for (uint32_t i = 0, bidx = boxes; i < static_cast<uint32_t>(chunks0 * 3); ++i, ++bidx)
-        mbar_wait(a_empty(bidx % SA), ((bidx / SA) & 1u) ^ 1u);
       for (int u = 0; u < total; u += 2) {
         if (u + 1 < total) seg_load(u + 1, bufB);
         seg_compute(u, bufA);
