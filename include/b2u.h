@@ -83,7 +83,9 @@ int b2u_conv_fprop_stats(const void* x0, int C0, const void* x1, int C1, const v
  * warps directly into the tensor core's A-operand stage -- neither the concat nor the up-sampled tensor is read from HBM.
  * up_out (nullable): receives the up-sampled tensor [N,H,W,C1] as a by-product (training keeps it as the operand of this
  * conv's weight gradient; inference passes NULL and the tensor never exists).  scale (nullable): folded eval-mode
- * BatchNorm as in b2u_conv_fprop_scaled.  stat_partial/stat_rows (nullable/0): as in b2u_conv_fprop_stats. */
+ * BatchNorm as in b2u_conv_fprop_scaled.  stat_partial/stat_rows (nullable/0): as in b2u_conv_fprop_stats, with the row
+ * count of b2u_conv_stat_rows(..., bn_override | 1 << 18): this kernel cuts the image into 8 (w) x 16 (h) pixel tiles (one
+ * halo box per channel block serves all nine taps), the plain convs into 16 x 8. */
 int b2u_decoder_conv_fprop(const void* skip, int C0, const void* low, int C1, const void* wf, const float* scale,
                            const float* bias, void* y, void* up_out, int N, int H, int W, int Cout, int relu, int bn_override,
                            float* stat_partial, int stat_rows, void* stream);

@@ -155,14 +155,24 @@ def test_lightweight_state_dict_and_program_contract(b2u):
 
 
 def test_conv_tile_count_helper(b2u):
-    """b2u_conv_stat_rows (host-only arithmetic): M tiles of 8x16 pixels, two stacked tiles per step for the small-N configs."""
+    """b2u_conv_stat_rows (host-only arithmetic): plain convs use M tiles of 16 (w) x 8 (h) pixels, two stacked per step for
+    the small-N configs (four for the unmasked N = 64 tiles from 32 rows on); the decoder conv (bit 18 of bn_override) uses
+    8 (w) x 16 (h) tiles, stacks of two, or three from 48 rows on."""
     lib = b2u._lib.lib()
     assert lib.b2u_conv_stat_rows(2, 24, 40, 256, 9, 0) == 2 * 3 * 3
     assert lib.b2u_conv_stat_rows(2, 24, 40, 64, 9, 0) == 2 * 2 * 3            # tall: 16-row steps
+    assert lib.b2u_conv_stat_rows(2, 100, 40, 64, 9, 0) == 2 * 4 * 3           # 32-row steps
+    assert lib.b2u_conv_stat_rows(2, 100, 40, 64, 9, 2 << 16) == 2 * 7 * 3     # bit 17: at most two stacked tiles
     assert lib.b2u_conv_stat_rows(1, 8, 16, 64, 9, 0) == 1                     # H <= 8: one tile per step
     assert lib.b2u_conv_stat_rows(3, 5, 7, 64, 1, 0) == 3                      # 1x1, N tile 64: always two stacked tiles
     assert lib.b2u_conv_stat_rows(3, 5, 7, 192, 1, 0) == 3
     assert lib.b2u_conv_stat_rows(0, 5, 7, 192, 1, 0) == 0
+    dec = 1 << 18
+    assert lib.b2u_conv_stat_rows(2, 24, 40, 256, 9, dec) == 2 * 2 * 5
+    assert lib.b2u_conv_stat_rows(2, 24, 40, 64, 9, dec) == 2 * 1 * 5          # 32-row steps
+    assert lib.b2u_conv_stat_rows(2, 100, 40, 64, 9, dec) == 2 * 3 * 5         # 48-row steps
+    assert lib.b2u_conv_stat_rows(2, 100, 40, 64, 9, dec | (2 << 16)) == 2 * 4 * 5
+    assert lib.b2u_conv_stat_rows(1, 8, 16, 64, 9, dec) == 2
 
 
 def test_predictor_host_helpers(b2u):

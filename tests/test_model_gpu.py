@@ -211,12 +211,13 @@ def test_eval_forward_is_deterministic_and_repeatable(b2u, cuda_device):
 @pytest.mark.parametrize("model,C", [("unet_vgg", 21), ("traditional", 4), ("unet_resnet50", 21)])
 def test_fused_upsample_equals_separate_pass(b2u, cuda_device, model, C):
     """nets/unet.py:16-18 in one kernel: the decoder conv that interpolates its low-resolution source itself
-    (engine.fuse_upsample, the default) gives BIT-identical logits, loss and gradients to the build that runs
-    b2u_upsample2x_fwd as a separate pass; training needs no upsample launch, inference allocates no up-sampled tensor."""
+    (engine.fuse_upsample: 1 = the stages where it pays, the default; 2 = every stage) gives BIT-identical logits, loss and
+    gradients to the build that runs b2u_upsample2x_fwd as a separate pass (0); a fused stage needs no upsample launch, and in
+    inference it allocates no up-sampled tensor."""
     dev = cuda_device
     imgs, pngs = O.make_inputs(2, C, 96, 64, seed=5)
     runs = {}
-    for fuse in (True, False):
+    for fuse in (2, 1, 0):
         tr = b2u.UnetTrainer(model=model, num_classes=C, device=dev, lr=0.0) if model != "unet_vgg" else \
             b2u.UnetTrainer(num_classes=C, device=dev, lr=0.0, state_dict=O.make_params(C, seed=11))
         tr.engine.fuse_upsample = fuse
@@ -226,16 +227,21 @@ def test_fused_upsample_equals_separate_pass(b2u, cuda_device, model, C):
         launches = b2u.ops.lib().b2u_launch_count()
         logits = tr.engine.forward(imgs.to(dev), tr.params, save=False, training=False)
         runs[fuse] = (out, {k: v.clone() for k, v in tr.grads.items()}, logits.clone(), launches)
-        if fuse:
+        if fuse == 2:
             tr.engine.release()
             tr.engine.forward(imgs.to(dev), tr.params, save=False, training=False)
-            assert not any(k.startswith("up") for k in tr.engine._bufs), "inference must not materialise the up-sampled tensors"
-    assert torch.equal(runs[True][0], runs[False][0])
-    assert torch.equal(runs[True][2], runs[False][2])
-    for k in runs[True][1]:
-        assert torch.equal(runs[True][1][k], runs[False][1][k]), k
+            lazy = getattr(tr.engine, "_lazy_up", None)       # GraphEngine: the up-sampled tensors read by decoder convs
+            ups = [k for k in tr.engine._bufs if (k in lazy if lazy is not None else k.startswith("up"))]
+            assert not ups, "inference must not materialise the up-sampled tensors"
+    for fuse in (2, 1):
+        assert torch.equal(runs[fuse][0], runs[0][0])
+        assert torch.equal(runs[fuse][2], runs[0][2])
+        for k in runs[0][1]:
+            assert torch.equal(runs[fuse][1][k], runs[0][1][k]), k
     n_dec = 3 if model == "traditional" else 4
-    assert runs[False][3] - runs[True][3] == n_dec          # one launch less per decoder stage
+    wide = {"unet_vgg": 3, "traditional": 1, "unet_resnet50": 3}[model]      # stages with >= 128 output channels
+    assert runs[0][3] - runs[2][3] == n_dec          # one launch less per fused decoder stage
+    assert runs[0][3] - runs[1][3] == wide
 
 
 def test_full_size_step_properties(b2u, cuda_device):

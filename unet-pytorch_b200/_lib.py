@@ -4,7 +4,9 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200unet.so")
+# B2U_LIB_PATH: an alternative build of the SAME library (A/B runs of two kernel generations on one box); there still is no
+# fallback -- the named file must exist and export the whole ABI
+LIB_PATH = os.environ.get("B2U_LIB_PATH") or os.path.join(_HERE, "libb200unet.so")
 # fp32 VALIDATION build of the same ABI (csrc/validation_fp32.cu): NHWC fp32 tensors, CUDA-core contractions; covers the
 # entry points UNetEngine uses.  Selected by set_validation_fp32(True) or B2U_FP32_VALIDATION=1; never the product path.
 LIB_PATH_FP32 = os.path.join(_HERE, "libb200unet_fp32.so")

@@ -10,12 +10,15 @@
 // channel ranges to two tensors.
 //
 // Mapping to the hardware (B200):
-//   * GEMM M = 128 output pixels = a 16(w) x 8(h) spatial patch of one image, N = BN output
+//   * GEMM M = 128 output pixels = an 8(w) x 16(h) spatial patch of one image, N = BN output
 //     channels, K = taps x input channels in blocks of 64.
-//   * A operand: one TMA box per (channel block, horizontal tap s): (8+2) x 16 pixels x 64
-//     channels, zero-filled outside the image by TMA (this IS the padding).  The three
-//     vertical taps r re-use that box: the UMMA descriptor start address is advanced by
-//     r*16 rows (a multiple of the 8-row swizzle atom), so A is fetched 3x, not 9x.
+//   * A operand: ONE TMA box per channel block: (16 MT + 2) x (8 + 2) pixels x 64 channels, zero-filled outside the
+//     image by TMA (this IS the padding), 128-byte swizzled, and all NINE taps read it in place: accumulator row
+//     m = h * 8 + w of tap (r, s) is box pixel (h + r) * 10 + (w + s), so the UMMA descriptor of a tap is the box
+//     address + (r * 10 + s) * 128 B with a stride of one box row (1280 B) between the 8-pixel groups.  The tensor core
+//     applies the 128B swizzle to absolute shared-memory address bits, so an operand may start at any 128-byte row and
+//     use any group stride (scripts/umma_unaligned_probe.cu measures exactly that): the input is fetched 1.3-1.4 x per
+//     conv (halo only) instead of once per horizontal tap (3.2-3.75 x).
 //   * B operand: packed weights [Cout][taps*C] (K-major), one TMA box per tap.
 //   * tcgen05.mma (cta_group::1, M=128, N=BN, K=16), fp32 accumulators in TMEM, double
 //     buffered so the epilogue of tile i overlaps the main loop of tile i+1.
@@ -27,16 +30,17 @@
 //     all-reduce of the data-parallel step) simply takes fewer tiles instead of holding the whole grid back.  The
 //     cp.async mask-stream variants (MD > 0), whose prefetch runs across tile boundaries, keep the static round robin
 //     (the same queue carries the static sequence).
-//   * M tiles stacked vertically per CTA step (MT): 1 (tiny images), 2, or 4 for the unmasked N = 64 layers.
+//   * M tiles stacked vertically per CTA step (MT): 1 (small images), 2, or 3 for the unmasked N = 64 layers.
 //   * UP = 1 (the first conv of a decoder stage, nets/unet.py:16-18: conv1(cat([skip, up(low)]))): source 1 is the
-//     LOW-RESOLUTION tensor [N, H/2, W/2, C1].  Four extra warps (6..9) interpolate its 64-channel blocks (bilinear 2x,
-//     align_corners=True, the arithmetic of b2u_bilinear.cuh) straight into the 128B-swizzled A stage the tensor core reads,
+//     LOW-RESOLUTION tensor [N, H/2, W/2, C1].  Five extra warps (6..10) interpolate its 64-channel blocks (bilinear 2x,
+//     align_corners=True, the arithmetic of b2u_bilinear.cuh) straight into the 128B-swizzled A box the tensor core reads,
 //     taking the A slots of the channel blocks >= C0 in the same ring the TMA thread fills for the skip tensor: neither the
-//     concat nor the upsampled tensor goes through HBM on the way into the conv.  Low-resolution rows are fetched one
+//     concat nor the upsampled tensor goes through HBM on the way into the conv, and because one box serves all nine
+//     taps every up-sampled pixel is interpolated once per tile (plus halo).  Low-resolution rows are fetched one
 //     row segment ahead (12 16-byte loads in flight per thread), so their L2 latency hides behind the interpolation of the
 //     previous segment.  In training the weight gradient of this conv needs the upsampled tensor as an operand: the
-//     warps that build the centre-tap box of N tile 0 also store its interior rows to `up_out` (a by-product of the conv,
-//     not a separate pass); inference passes up_out = null and the tensor never exists.
+//     warps of N tile 0 also store the box interior to `up_out` (a by-product of the conv, not a separate pass);
+//     inference passes up_out = null and the tensor never exists.
 #include <atomic>
 #include <cstdlib>
 #include <mutex>
@@ -47,9 +51,15 @@
 
 namespace b2u {
 
-constexpr int kWb = 16;   // patch width  (pixels)
-constexpr int kHb = 8;    // patch height (pixels)
-constexpr int kTileM = kWb * kHb;
+// Two tile geometries (ConvCfg::kWb x kHb pixels = one M = 128 accumulator tile):
+//   plain convs (UP = 0): 16 (w) x 8 (h); one TMA box of (8 MT + 2) x 16 pixels per (channel block, horizontal tap), the
+//     three vertical taps re-use it through the descriptor start address (+ r image rows).  Its 2 KB image-row runs
+//     suit the HBM-bound launches (masked data gradients, 1x1 head) and four stacked tiles fit for the N = 64 layers;
+//   decoder convs (UP = 1): 8 (w) x 16 (h); ONE box of (16 MT + 2) x 10 pixels per channel block serves all nine taps
+//     (descriptor start + (r * 10 + s) * 128 B, group stride = one box row), so an interpolated pixel is built once.
+// Same-box A/B of the two geometries on the plain convs of the headline step: 22.2-22.3 ms vs 22.6 ms per step in
+// favour of 16 x 8 (the N = 64 and masked launches lose 15-25 % with 1 KB runs), so each keeps its own.
+constexpr int kTileM = 128;
 constexpr int KB = 64;    // channels per K block = one 128-byte swizzle row
 
 struct ConvParams {
@@ -73,7 +83,7 @@ struct ConvParams {
   float up_sh, up_sw;           // (H/2 - 1) / (H - 1), (W/2 - 1) / (W - 1)
 };
 
-constexpr int kUpWarps = 4;         // interpolation warps of the UP kernels (thread = (box column, 16-byte channel chunk))
+constexpr int kUpWarps = 5;         // interpolation warps of the UP kernels: 160 threads = 2 row groups x 10 box columns x 8 16-byte chunks
 
 template <int BN, int TAPS, int MT, int RB, int SA, int SB, int MD = 0, int UP = 0>
 struct ConvCfg {
@@ -81,8 +91,14 @@ struct ConvCfg {
   // MT: M tiles (8x16 pixel patches, stacked vertically) per CTA step, sharing every B tile
   // RB: vertical taps per B pipeline stage (3: one barrier round trip per 12*MT MMAs, for the small-N tiles)
   static constexpr int kRowBytes = KB * 2;                      // swizzle span (128 B)
-  static constexpr int kARows = (TAPS == 9 ? kHb * MT + 2 : kHb * MT) * kWb;
-  static constexpr int kABytes = kARows * kRowBytes;
+  static constexpr int kWb = UP ? 8 : 16;                       // tile width / height in pixels
+  static constexpr int kHb = UP ? 16 : 8;
+  static constexpr bool kOneBox = UP != 0;                      // one halo box per channel block serves all nine taps
+  static constexpr int kPitch = kOneBox ? kWb + 2 : kWb;        // pixels per box row (one box: a halo column each side)
+  static constexpr int kBoxRows = TAPS == 9 ? kHb * MT + 2 : kHb * MT;
+  static constexpr int kARows = kBoxRows * kPitch;
+  static constexpr int kABoxBytes = kARows * kRowBytes;         // bytes one TMA box delivers
+  static constexpr int kABytes = (kABoxBytes + 1023) / 1024 * 1024;   // slot size: the swizzle pattern is anchored at 1024 B
   static constexpr int kBTap = BN * kRowBytes;                  // one tap's weight tile
   static constexpr int kBBytes = RB * kBTap;
   static constexpr int kStageBytes = kTileM * 64 * 2;
@@ -97,8 +113,10 @@ struct ConvCfg {
   static constexpr int kNumBar = 2 * SA + 2 * SB + 4 + 2 * kQ + (UP ? SA : 0);   // UP: one "slot is yours" barrier per A slot
   static constexpr int kOffTmem = kOffBar + kNumBar * 8;
   static constexpr int kOffTq = kOffTmem + 16;
-  static constexpr int kSmemBytes = kOffTq + kQ * 4 + 1024;  // + alignment slack
-  static constexpr uint32_t kSBO = 8 * kRowBytes;
+  static constexpr int kOffRowW = kOffTq + kQ * 4;             // UP: per box row, the two vertical interpolation weights (float2), two tile parities
+  static constexpr int kSmemBytes = kOffRowW + (UP ? 2 * kBoxRows * 8 : 0) + 1024;  // + alignment slack
+  static constexpr uint32_t kSBO = 8 * kRowBytes;             // B operand: 8-row groups are contiguous
+  static constexpr uint32_t kSBO_A = kOneBox ? kPitch * kRowBytes : 8 * kRowBytes;   // A operand: one box: next 8-pixel group = next box row
   static constexpr int kAccCols = MT * BN;                     // accumulator columns per pipeline stage
   static constexpr int kTmemCols = 2 * kAccCols <= 128 ? 128 : (2 * kAccCols <= 256 ? 256 : 512);
   static_assert(BN % 64 == 0 && BN <= 256, "N tile must be 64/128/192/256");
@@ -118,6 +136,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   using Cfg = ConvCfg<BN, TAPS, MT, RB, SA, SB, MD, UP>;
   constexpr int S_TAPS = TAPS == 9 ? 3 : 1;
   constexpr int R_TAPS = TAPS == 9 ? 3 : 1;
+  constexpr int kWb = Cfg::kWb, kHb = Cfg::kHb;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -198,7 +217,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         for (int c = 0; c < chunks; ++c) {
           const CUtensorMap* tm = c < chunks0 ? &tmA0 : &tmA1;
           const int cc = c < chunks0 ? c * KB : c * KB - p.C0;
-          for (int s = 0; s < S_TAPS; ++s) {
+          if (Cfg::kOneBox) {
             // This thread is the only one that follows the a_empty phases (a parity wait is exact only within one phase of
             // its barrier, and the interpolation warps skip the skip tensor's slots): a free slot of an up-sampled channel
             // block is handed to them through u_go, which by construction never runs more than one phase ahead of them.
@@ -206,11 +225,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             if (UP && c >= chunks0) {
               mbar_arrive(u_go(sa));
             } else {
-              mbar_expect_tx(a_full(sa), Cfg::kABytes);
-              if (TAPS == 9) tma_load_4d(sA + sa * Cfg::kABytes, tm, a_full(sa), cc, w0 + s - 1, h0 - 1, img);
-              else           tma_load_4d(sA + sa * Cfg::kABytes, tm, a_full(sa), cc, w0, h0, img);
+              mbar_expect_tx(a_full(sa), Cfg::kABoxBytes);
+              tma_load_4d(sA + sa * Cfg::kABytes, tm, a_full(sa), cc, w0 - 1, h0 - 1, img);
             }
             if (++sa == SA) { sa = 0; pa ^= 1u; }
+          }
+          for (int s = 0; s < S_TAPS; ++s) {
+            if (!Cfg::kOneBox) {
+              mbar_wait(a_empty(sa), pa ^ 1u);
+              mbar_expect_tx(a_full(sa), Cfg::kABoxBytes);
+              if (TAPS == 9) tma_load_4d(sA + sa * Cfg::kABytes, tm, a_full(sa), cc, w0 + s - 1, h0 - 1, img);
+              else           tma_load_4d(sA + sa * Cfg::kABytes, tm, a_full(sa), cc, w0, h0, img);
+              if (++sa == SA) { sa = 0; pa ^= 1u; }
+            }
             for (int rb = 0; rb < R_TAPS / RB; ++rb) {
               mbar_wait(b_empty(sb), pb ^ 1u);
               mbar_expect_tx(b_full(sb), Cfg::kBBytes);
@@ -230,7 +257,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN, 0, 0);
       // descriptor templates: only the 14-bit start-address field changes per MMA (smem < 256 KB, no carry)
-      const uint64_t a_desc0 = umma_smem_desc(sA, 16, Cfg::kSBO, 2u);
+      const uint64_t a_desc0 = umma_smem_desc(sA, 16, Cfg::kSBO_A, 2u);
       const uint64_t b_desc0 = umma_smem_desc(sB, 16, Cfg::kSBO, 2u);
       int sa = 0, sb = 0, as = 0;
       uint32_t pa = 0, pb = 0, pacc = 0;
@@ -247,10 +274,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * Cfg::kAccCols);
         uint32_t acc = 0;
         for (int c = 0; c < chunks; ++c) {
-          for (int s = 0; s < S_TAPS; ++s) {
+          uint64_t a_desc = 0;
+          if (Cfg::kOneBox) {
             mbar_wait(a_full(sa), pa);
             tc_fence_after();
-            const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((sa * Cfg::kABytes) >> 4);
+            a_desc = a_desc0 + static_cast<uint64_t>((sa * Cfg::kABytes) >> 4);
+          }
+          for (int s = 0; s < S_TAPS; ++s) {
+            if (!Cfg::kOneBox) {
+              mbar_wait(a_full(sa), pa);
+              tc_fence_after();
+              a_desc = a_desc0 + static_cast<uint64_t>((sa * Cfg::kABytes) >> 4);
+            }
+            // horizontal tap: its own box (start 0), or s pixels into the one halo box
+            const int s_off = Cfg::kOneBox ? s : 0;
             for (int rb = 0; rb < R_TAPS / RB; ++rb) {
               mbar_wait(b_full(sb), pb);
               tc_fence_after();
@@ -262,7 +299,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                 for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
                   for (int k = 0; k < KB / 16; ++k) {
-                    const uint64_t ad = a_desc + static_cast<uint64_t>(((mt * kHb + r) * (kWb * Cfg::kRowBytes) + k * 32) >> 4);
+                    // tap row r of stacked tile mt: box pixel (mt * kHb + r) * pitch (+ s), 16 channels further per k
+                    const uint64_t ad = a_desc + static_cast<uint64_t>((((mt * kHb + r) * Cfg::kPitch + s_off) * Cfg::kRowBytes + k * 32) >> 4);
                     const uint64_t bd = b_desc + static_cast<uint64_t>((rr * Cfg::kBTap + k * 32) >> 4);
                     tc_mma_bf16(d_tmem + mt * BN, ad, bd, idesc, (k == 0 ? acc : 1u));
                   }
@@ -272,6 +310,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               tc_commit(b_empty(sb));
               if (++sb == SB) { sb = 0; pb ^= 1u; }
             }
+            if (!Cfg::kOneBox) {
+              tc_commit(a_empty(sa));
+              if (++sa == SA) { sa = 0; pa ^= 1u; }
+            }
+          }
+          if (Cfg::kOneBox) {
             tc_commit(a_empty(sa));
             if (++sa == SA) { sa = 0; pa ^= 1u; }
           }
@@ -281,21 +325,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       }
     }
   } else if (UP && warp >= 6) {
-    // ===================== interpolation producers (UP kernels: warps 6..9, 128 threads) =====================
-    // thread = (box column `col`, 16-byte chunk `ch` of the 64-channel block); box pixel q = row * 16 + col lands at byte
-    // q * 128 + ((ch ^ (q & 7)) << 4), exactly where a 128B-swizzled TMA box would put it.  A box of 8 MT + 2 rows is
-    // built in MT row segments (10 rows, then 8 at a time); output rows 2m+1 .. 2m+10 read the low-resolution rows
-    // m .. m+5 (b2u_bilinear.cuh), all 12 16-byte loads of a segment are issued one segment ahead of their use.
+    // ===================== interpolation producers (UP kernels: warps 6..10, 160 threads) =====================
+    // thread = (row group g, box column `col` of 10, 16-byte chunk `ch` of the 64-channel block); box pixel q = row * 10 + col
+    // lands at byte q * 128 + ((ch ^ (q & 7)) << 4), exactly where a 128B-swizzled TMA box would put it.  A box of
+    // 16 MT + 2 rows is built in 2 MT row segments (10 rows, then 8 at a time), even segments by group 0, odd ones by group 1;
+    // output rows 2m+1 .. 2m+10 read the low-resolution rows m .. m+5 (b2u_bilinear.cuh), and all 12 16-byte loads of
+    // a segment are issued one segment ahead of their use.
     const int ut = threadIdx.x - 192;
-    const int col = ut >> 3, ch = ut & 7;
+    const int ch = ut & 7, col = (ut >> 3) % Cfg::kPitch, grp = (ut >> 3) / Cfg::kPitch;
     const int HL = p.H >> 1, WL = p.W >> 1;
     const int c8 = p.C1 >> 3;                              // 16-byte vectors per low-resolution pixel
-    constexpr int R = Cfg::kARows / kWb;                   // box rows
-    constexpr int NSEG = MT;
+    constexpr int R = Cfg::kBoxRows;
     constexpr int SEG_ROWS = 6;
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
     uint32_t boxes = 0;                                    // A slots handed out so far (all channel blocks, ring order)
     uint32_t go_phase = 0;                                 // bit i: parity of the next u_go(i) phase to wait for
+    int tpar = 0;
     int qs = 0;
     uint32_t qp = 0;
     for (;;) {
@@ -310,50 +355,59 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const int tw = m_tile % p.tiles_w; m_tile /= p.tiles_w;
       const int th = m_tile % p.tiles_h;
       const int img = m_tile / p.tiles_h;
-      const int w0 = tw * kWb, hb = th * (kHb * MT) - 1;
-      const int total = (chunks - chunks0) * 3 * NSEG;
+      const int wo = tw * kWb - 1 + col, hb = th * (kHb * MT) - 1;       // this thread's image column; image row of box row 0 (odd)
+      const bool colok = wo >= 0 && wo < p.W;
+      int c0i, c1i; float lw;
+      src_index(colok ? wo : 0, p.up_sw, WL, c0i, c1i, lw);
+      const float w0l = 1.f - lw;
+      const int total = (chunks - chunks0) * MT;           // segments of this thread in the tile
       const uint4* lowimg = reinterpret_cast<const uint4*>(p.up_low) + static_cast<size_t>(img) * HL * WL * c8 + ch;
-      uint4* upimg = p.up_out != nullptr && n_tile == 0
-                         ? reinterpret_cast<uint4*>(p.up_out) + static_cast<size_t>(img) * p.H * p.W * c8 + ch : nullptr;
+      const uint4* lowc0 = lowimg + static_cast<size_t>(c0i) * c8;     // this thread's two low-resolution columns
+      const uint4* lowc1 = lowimg + static_cast<size_t>(c1i) * c8;
+      const size_t lowrow = static_cast<size_t>(WL) * c8, uprow = static_cast<size_t>(p.W) * c8;
+      // interior of the box = this tile: by-product store of the up-sampled tensor (N tile 0 only, so once per pixel)
+      uint4* upimg = p.up_out != nullptr && n_tile == 0 && colok && col >= 1 && col <= kWb
+                         ? reinterpret_cast<uint4*>(p.up_out) + (static_cast<size_t>(img) * p.H * p.W + wo) * c8 + ch : nullptr;
+      // vertical weights of the tile's box rows, once per tile (they are the same for every thread and channel block):
+      // row r -> weights of low-resolution rows j, j + 1 with j = floor((hb + r - 1) / 2); both zero outside the image
+      float2* roww = reinterpret_cast<float2*>(smem_gen + Cfg::kOffRowW) + tpar * R;
+      if (ut < R) {
+        float wa, wb;
+        pair_weights(hb + ut, (hb + ut - 1) >> 1, p.up_sh, HL, p.H, wa, wb);
+        roww[ut] = make_float2(wa, wb);
+      }
+      named_bar_sync(5, kUpWarps * 32);     // (double buffered by tile parity: a fast warp may be one tile ahead of a slow one)
+      tpar ^= 1;
 
-      // segment u -> (up-sampled channel block cu, horizontal tap s, row segment seg)
+      // segment u of this thread -> (up-sampled channel block cu, row segment 2 * (u % MT) + grp)
       auto seg_load = [&](int u, uint4 (&buf)[2 * SEG_ROWS]) {
-        const int seg = u % NSEG, bs = u / NSEG, s = bs % 3, cu = bs / 3;
-        const int wo = w0 + s - 1 + col;
-        int c0i, c1i; float lw;
-        src_index(wo >= 0 && wo < p.W ? wo : 0, p.up_sw, WL, c0i, c1i, lw);
-        const int m = (hb + (seg == 0 ? 0 : 2 + 8 * seg) - 1) >> 1;
-        const uint4* base = lowimg + cu * 8;
+        const int cu = u / MT, sidx = 2 * (u % MT) + grp;
+        const int m = (hb + (sidx == 0 ? 0 : 2 + 8 * sidx) - 1) >> 1;
 #pragma unroll
         for (int k = 0; k < SEG_ROWS; ++k) {
           int j = m + k;
           j = j < 0 ? 0 : (j > HL - 1 ? HL - 1 : j);         // rows outside the image carry zero weight
-          const uint4* rowp = base + static_cast<size_t>(j) * WL * c8;
-          buf[2 * k] = __ldg(rowp + static_cast<size_t>(c0i) * c8);
-          buf[2 * k + 1] = __ldg(rowp + static_cast<size_t>(c1i) * c8);
+          buf[2 * k] = __ldg(lowc0 + j * lowrow + cu * 8);
+          buf[2 * k + 1] = __ldg(lowc1 + j * lowrow + cu * 8);
         }
       };
       auto seg_compute = [&](int u, const uint4 (&buf)[2 * SEG_ROWS]) {
-        const int seg = u % NSEG, bs = u / NSEG, s = bs % 3, cu = bs / 3;
-        const uint32_t bidx = boxes + static_cast<uint32_t>(chunks0 * 3 + bs);
+        const int cu = u / MT, sidx = 2 * (u % MT) + grp;
+        const uint32_t bidx = boxes + static_cast<uint32_t>(chunks0 + cu);
         const uint32_t slot = bidx % SA;
-        if (seg == 0) {                                     // the TMA thread saw the slot's previous contents consumed
+        if (u % MT == 0) {                                  // the TMA thread saw the slot's previous contents consumed
           mbar_wait(u_go(slot), (go_phase >> slot) & 1u);
           go_phase ^= 1u << slot;
         }
-        const uint32_t box = sA + slot * Cfg::kABytes;
-        const int wo = w0 + s - 1 + col;
-        const bool colok = wo >= 0 && wo < p.W;
-        int c0i, c1i; float lw;
-        src_index(colok ? wo : 0, p.up_sw, WL, c0i, c1i, lw);
-        const float w0l = 1.f - lw;
-        const int r0 = seg == 0 ? 0 : 2 + 8 * seg;
-        const int m = (hb + r0 - 1) >> 1;
+        const int r0 = sidx == 0 ? 0 : 2 + 8 * sidx;
+        const uint32_t q0 = static_cast<uint32_t>(r0 * Cfg::kPitch + col);
+        const uint32_t box = sA + slot * Cfg::kABytes + q0 * 128;
+        uint4* upp = upimg != nullptr ? upimg + (hb + r0) * static_cast<ptrdiff_t>(uprow) + cu * 8 : nullptr;
         float va[8], vb[8];
         hlerp8(buf[0], buf[1], w0l, lw, va);
 #pragma unroll
         for (int t = 0; t < 10; ++t) {
-          if (t >= 8 && seg != 0) break;
+          if (t >= 8 && sidx != 0) break;
           if ((t & 1) == 0) {
             if (t > 0) {
 #pragma unroll
@@ -363,17 +417,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           }
           const int r = r0 + t, o = hb + r;
           const bool inside = colok && o >= 0 && o < p.H;       // outside the image: the conv's zero padding
-          float wa, wb;
-          pair_weights(o, m + t / 2, p.up_sh, HL, p.H, wa, wb);
-          const uint4 v = inside ? vlerp8(va, vb, wa, wb) : zero4;
-          const int q = r * kWb + col;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(box + q * 128 + ((ch ^ (q & 7)) << 4)), "r"(v.x), "r"(v.y),
+          const float2 w2 = roww[r];
+          const uint4 v = inside ? vlerp8(va, vb, w2.x, w2.y) : zero4;
+          const uint32_t q = q0 + t * Cfg::kPitch;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(box + t * Cfg::kPitch * 128 + ((ch ^ (q & 7)) << 4)), "r"(v.x), "r"(v.y),
                        "r"(v.z), "r"(v.w) : "memory");
-          // by-product for the weight gradient: the centre-tap box covers exactly this tile's pixels in its rows 1 .. R-2
-          if (upimg != nullptr && s == 1 && inside && r >= 1 && r <= R - 2)
-            upimg[(static_cast<size_t>(o) * p.W + wo) * c8 + cu * 8] = v;
+          if (upp != nullptr && inside && r >= 1 && r <= R - 2) upp[t * uprow] = v;
         }
-        if (seg == NSEG - 1) {
+        if (u % MT == MT - 1) {
           fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
           named_bar_sync(4, kUpWarps * 32);
           if (ut == 0) mbar_arrive(a_full(slot));
@@ -388,7 +439,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         if (u + 2 < total) seg_load(u + 2, bufA);
         if (u + 1 < total) seg_compute(u + 1, bufB);
       }
-      boxes += static_cast<uint32_t>(chunks * 3);
+      boxes += static_cast<uint32_t>(chunks);
     }
   } else {
     // ===================== epilogue (4 warps, 128 threads) =====================
@@ -662,6 +713,7 @@ static int* sched_slot() {
 template <int BN, int TAPS, int MT, int RB, int SA, int SB, int MD = 0, int UP = 0>
 static int launch_cfg(const ConvLaunch& a, cudaStream_t st) {
   using Cfg = ConvCfg<BN, TAPS, MT, RB, SA, SB, MD, UP>;
+  constexpr int kWb = Cfg::kWb, kHb = Cfg::kHb;
   auto kern = conv_igemm_kernel<BN, TAPS, MT, RB, SA, SB, MD, UP>;
   static bool attr_done[64] = {false};
   int dev = 0;
@@ -672,12 +724,11 @@ static int launch_cfg(const ConvLaunch& a, cudaStream_t st) {
     attr_done[dev] = true;
   }
   const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B;
-  const int a_box_h = TAPS == 9 ? kHb * MT + 2 : kHb * MT;
   CUtensorMap tmA0, tmA1, tmB, tmC0, tmC1;
   int rc;
-  if ((rc = make_tmap_nhwc(&tmA0, a.x0, a.N, a.H, a.W, a.C0, KB, kWb, a_box_h, swz))) return rc;
+  if ((rc = make_tmap_nhwc(&tmA0, a.x0, a.N, a.H, a.W, a.C0, KB, Cfg::kPitch, Cfg::kBoxRows, swz))) return rc;
   if (a.C1 > 0 && !UP) {
-    if ((rc = make_tmap_nhwc(&tmA1, a.x1, a.N, a.H, a.W, a.C1, KB, kWb, a_box_h, swz))) return rc;
+    if ((rc = make_tmap_nhwc(&tmA1, a.x1, a.N, a.H, a.W, a.C1, KB, Cfg::kPitch, Cfg::kBoxRows, swz))) return rc;
   } else {
     tmA1 = tmA0;       // UP: source 1 is read by the interpolation warps, not by TMA
   }
@@ -721,15 +772,30 @@ static int launch_cfg(const ConvLaunch& a, cudaStream_t st) {
 }
 
 // number of M tiles launch_conv will use for this problem = rows of ConvLaunch::stat_partial
+// M tiles stacked vertically per CTA step: the single rule both the launcher and conv_m_tiles follow.
+//   plain 3x3 (16 x 8 tiles): N tile 128 / 64 stack two when the image is taller than one tile (halves the weight traffic
+//        per pixel); the unmasked N = 64 layers, bound by shared-memory operand traffic, stack four from 32 rows on
+//   decoder 3x3 (8 x 16 tiles): the same with three instead of four (two 83 KB boxes do not fit), from 48 rows on
+//   1x1: N tile 64 stacks two
+// tile_flags bit 0 forces one tile, bit 1 caps the stack at two.
+static int stacked_tiles(int bn, int taps, int H, int tile_flags, bool masked, bool decoder) {
+  if (taps != 9) return bn == 64 ? 2 : 1;
+  const int hb = decoder ? 16 : 8;
+  const bool tall = H > hb && !(tile_flags & 1);
+  if (!tall || (bn != 128 && bn != 64)) return 1;
+  if (bn == 64 && !masked && !(tile_flags & 2) && H >= (decoder ? 3 : 4) * hb) return decoder ? 3 : 4;
+  return 2;
+}
+
+// number of M tiles launch_conv will use for this problem = rows of ConvLaunch::stat_partial (forward launches: unmasked);
+// bit 18 of bn_override: the decoder conv's tiles (b2u_decoder_conv_fprop)
 int conv_m_tiles(int N, int H, int W, int Cout, int taps, int bn_override) {
   int bn = bn_override & 0xffff;
   if (!bn) bn = Cout % 256 == 0 ? 256 : (Cout % 192 == 0 ? 192 : (Cout % 128 == 0 ? 128 : 64));
-  const bool tall = H > kHb && !((bn_override >> 16) & 1);
-  int mt = 1;
-  if (taps == 9) mt = (bn == 128 || bn == 64) && tall ? 2 : 1;
-  else           mt = bn == 64 ? 2 : 1;
-  if (taps == 9 && bn == 64 && tall && !((bn_override >> 16) & 2) && H >= 4 * kHb) mt = 4;    // unmasked launches (fprop)
-  return N * ((H + kHb * mt - 1) / (kHb * mt)) * ((W + kWb - 1) / kWb);
+  const bool decoder = ((bn_override >> 18) & 1) && taps == 9;
+  const int mt = stacked_tiles(bn, taps, H, (bn_override >> 16) & 3, false, decoder);
+  const int hb = decoder ? 16 : 8, wb = decoder ? 8 : 16;
+  return N * ((H + hb * mt - 1) / (hb * mt)) * ((W + wb - 1) / wb);
 }
 
 int launch_conv(const ConvLaunch& a, cudaStream_t st) {
@@ -757,19 +823,18 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st) {
   else if (a.Cout % 128 == 0) bn = 128;
   else bn = 64;
 
-  // tall = two stacked M tiles per CTA step (halves the weight traffic per pixel); pointless for tiny images
-  const bool tall = a.H > kHb && !(a.tile_flags & 1);
+  const int mt = stacked_tiles(bn, a.taps, a.H, a.tile_flags, (a.flags & 2) != 0, a.up_low != nullptr);
   if (a.up_low != nullptr) {
-    // decoder conv over [skip, upsample2x(low)]: same tiles as the plain 3x3 forward, plus the interpolation warps
+    // decoder conv over [skip, upsample2x(low)]: 8 x 16 tiles, one halo box per channel block, interpolation warps
     if (a.taps != 9 || a.C1 <= 0 || (a.H & 1) || (a.W & 1) || (a.flags & 6) || a.y1 != nullptr)
       return set_error(B2U_ERR_SHAPE, "decoder conv: needs a 3x3 forward conv over even H, W with an up-sampled source");
     switch (bn) {
-      case 256: return launch_cfg<256, 9, 1, 1, 3, 4, 0, 1>(a, st);
-      case 192: return launch_cfg<192, 9, 1, 1, 3, 5, 0, 1>(a, st);
-      case 128: return tall ? launch_cfg<128, 9, 2, 3, 2, 2, 0, 1>(a, st) : launch_cfg<128, 9, 1, 3, 3, 2, 0, 1>(a, st);
+      case 256: return launch_cfg<256, 9, 1, 1, 2, 4, 0, 1>(a, st);
+      case 192: return launch_cfg<192, 9, 1, 1, 2, 5, 0, 1>(a, st);
+      case 128: return mt == 2 ? launch_cfg<128, 9, 2, 3, 2, 2, 0, 1>(a, st) : launch_cfg<128, 9, 1, 3, 3, 2, 0, 1>(a, st);
       case 64:
-        if (tall && !(a.tile_flags & 2) && a.H >= 4 * kHb) return launch_cfg<64, 9, 4, 3, 2, 2, 0, 1>(a, st);
-        return tall ? launch_cfg<64, 9, 2, 3, 3, 3, 0, 1>(a, st) : launch_cfg<64, 9, 1, 3, 4, 4, 0, 1>(a, st);
+        if (mt == 3) return launch_cfg<64, 9, 3, 3, 2, 2, 0, 1>(a, st);
+        return mt == 2 ? launch_cfg<64, 9, 2, 3, 2, 3, 0, 1>(a, st) : launch_cfg<64, 9, 1, 3, 3, 4, 0, 1>(a, st);
     }
     return set_error(B2U_ERR_SHAPE, "conv: unsupported N tile %d", bn);
   }
@@ -777,7 +842,7 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st) {
     switch (bn) {
       case 256: return launch_cfg<256, 9, 1, 1, 3, 4>(a, st);
       case 192: return launch_cfg<192, 9, 1, 1, 3, 5>(a, st);
-      case 128: return tall ? launch_cfg<128, 9, 2, 3, 2, 2>(a, st) : launch_cfg<128, 9, 1, 3, 3, 2>(a, st);
+      case 128: return mt == 2 ? launch_cfg<128, 9, 2, 3, 2, 2>(a, st) : launch_cfg<128, 9, 1, 3, 3, 2>(a, st);
       case 64:
         // masked (dgrad + ReLU) Cin-side-64 layers are HBM-bound: the mask rows go through the cp.async stream
         // unmasked N = 64 tiles are bound by shared-memory operand traffic: four stacked M tiles per CTA step --
@@ -786,9 +851,9 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st) {
         // (64+128->64) at 16x512x512, bit-identical results (scripts/tile_variants_bench.py).  The masked variant keeps two
         // tiles: its cp.async mask stream does not fit next to the larger A stages and register prefetch is slower
         // (0.443 vs 0.415 ms).  tile_flags bit 1 forces the two-tile kernel (tests).
-        if (tall && !(a.tile_flags & 2) && a.H >= 4 * kHb && !(a.flags & 2)) return launch_cfg<64, 9, 4, 3, 2, 2>(a, st);
-        if (tall && (a.flags & 2)) return launch_cfg<64, 9, 2, 3, 3, 2, 2>(a, st);
-        return tall ? launch_cfg<64, 9, 2, 3, 3, 3>(a, st) : launch_cfg<64, 9, 1, 3, 4, 4>(a, st);
+        if (mt == 4) return launch_cfg<64, 9, 4, 3, 2, 2>(a, st);
+        if (mt == 2 && (a.flags & 2)) return launch_cfg<64, 9, 2, 3, 3, 2, 2>(a, st);
+        return mt == 2 ? launch_cfg<64, 9, 2, 3, 3, 3>(a, st) : launch_cfg<64, 9, 1, 3, 4, 4>(a, st);
     }
   } else {
     switch (bn) {
@@ -867,8 +932,8 @@ int b2u_decoder_conv_fprop(const void* skip, int C0, const void* low, int C1, co
                            const float* bias, void* y, void* up_out, int N, int H, int W, int Cout, int relu, int bn_override,
                            float* stat_partial, int stat_rows, void* stream) {
   if (skip == nullptr || low == nullptr) return b2u::set_error(B2U_ERR_ARG, "decoder_conv_fprop: skip and low tensors are required");
-  if (stat_partial != nullptr && stat_rows < b2u::conv_m_tiles(N, H, W, Cout, 9, bn_override))
-    return b2u::set_error(B2U_ERR_ARG, "decoder_conv_fprop: statistics buffer too small");
+  if (stat_partial != nullptr && stat_rows < b2u::conv_m_tiles(N, H, W, Cout, 9, bn_override | (1 << 18)))
+    return b2u::set_error(B2U_ERR_ARG, "decoder_conv_fprop: statistics buffer too small (b2u_conv_stat_rows with bit 18 of bn_override)");
   b2u::ConvLaunch a;
   a.x0 = skip; a.C0 = C0; a.x1 = nullptr; a.C1 = C1;
   a.up_low = low; a.up_out = up_out;
@@ -876,7 +941,7 @@ int b2u_decoder_conv_fprop(const void* skip, int C0, const void* low, int C1, co
   a.N = N; a.H = H; a.W = W; a.Cout = Cout; a.taps = 9;
   a.flags = relu ? 1 : 0;
   a.bn_override = bn_override & 0xffff;
-  a.tile_flags = bn_override >> 16;
+  a.tile_flags = (bn_override >> 16) & 3;
   a.stat_partial = stat_partial;
   return b2u::launch_conv(a, static_cast<cudaStream_t>(stream));
 }

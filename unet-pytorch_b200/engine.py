@@ -144,9 +144,13 @@ class UNetEngine:
         # db from the wgrad kernel's bias warps (3x3 layers) instead of a separate pass over dz: an A/B on one box
         # (scripts/ab_fuse_bias.py: 23.2-23.9 vs 23.4-23.5 ms/step) shows no gain, so the separate pass stays the default
         self.fuse_bias_grad = False
-        # bilinear 2x up-sampling + concat folded into the decoder conv's operand load (b2u_decoder_conv_fprop);
-        # B2U_FUSE_UPSAMPLE=0 restores the separate b2u_upsample2x_fwd pass (A/B runs, tests compare the two bit for bit)
-        self.fuse_upsample = os.environ.get("B2U_FUSE_UPSAMPLE", "1") == "1"
+        # bilinear 2x up-sampling + concat folded into the decoder conv's operand load (b2u_decoder_conv_fprop).  Measured at
+        # the four unetUp shapes of the headline step (scripts/ab_fused_upsample.py, profiles/r2_fused_upsample.json): with
+        # N tiles of 128 / 256 output channels the fused conv beats upsample + conv (0.42 / 0.65 / 0.70 ms against 0.42 / 0.67 /
+        # 0.77); with the N = 64 tile (64+128 -> 64 at 512 x 512) the five interpolation warps cannot keep up with a main loop
+        # that short (1.32 against 1.07 ms), so that stage keeps the separate pass.  B2U_FUSE_UPSAMPLE: 0 = never,
+        # 1 = where it pays (default), 2 = every decoder stage (tests compare all three bit for bit).
+        self.fuse_upsample = int(os.environ.get("B2U_FUSE_UPSAMPLE", "1"))
         # Weight/bias gradients on a second stream (plain conv+ReLU nets): wgrad_L depends only on dz_L and the saved
         # activation, not on the dgrad chain, so its launches are queued on a side stream behind an event and the
         # HBM-bound glue of the main chain (pool / upsample adjoints, bias column sums) shares the SMs with tensor-core-bound
@@ -319,7 +323,7 @@ class UNetEngine:
         stats, rows = None, 0
         kdim = taps * (x0.shape[3] + (x1.shape[3] if x1 is not None else 0) + (low.shape[3] if low is not None else 0))
         if training and self.fuse_bn_stats and self.sync_bn_group is None and (kdim >= self.bn_stats_min_k or c.cout_p >= self.bn_stats_min_cout):
-            rows = ops.conv_stat_rows(n, h, w, c.cout_p, taps)
+            rows = ops.conv_stat_rows(n, h, w, c.cout_p, taps, bn=(1 << 18) if low is not None else 0)      # bit 18: the decoder conv's tiles
             stats = self._workspace("bnstat", rows * 2 * c.cout_p * 4)[:rows * 2 * c.cout_p * 4].view(torch.float32)
         conv(bias, False, z, stats=stats)
         gamma = self._padded_vec("g:" + c.bn, params[c.bn + ".weight"], c.cout_p, fill=1.0)
@@ -401,7 +405,7 @@ class UNetEngine:
         for si, (c1, c2) in enumerate(self.dec):
             skip = feats[len(self.enc) - 2 - si]
             _, hl, wl, cl = low.shape
-            if self.fuse_upsample:
+            if self.fuse_upsample == 2 or (self.fuse_upsample == 1 and c1.cout_p >= 128):
                 # the decoder conv interpolates `low` inside its producer warps (nets/unet.py:16-18 in one kernel); the
                 # up-sampled tensor is written only when a backward pass will need it as the weight gradient's operand
                 # (the fp32 validation build always takes the buffer: it keeps the two steps apart)

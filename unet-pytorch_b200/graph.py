@@ -332,11 +332,12 @@ class GraphEngine:
         self._bn_reader = {i["z"]: i for i in program if i["op"] == "bn" and i["z"] in self._pre_bn}      # conv output -> its BatchNorm
         # "up" outputs read exactly once, as the SECOND source of a stride-1 3x3 conv (unetUp, nets/unet.py:16-18): that conv
         # interpolates the low-resolution tensor in its producer warps (b2u_decoder_conv_fprop) and the "up" instruction
-        # launches nothing.  B2U_FUSE_UPSAMPLE=0 restores the separate pass.
-        self.fuse_upsample = os.environ.get("B2U_FUSE_UPSAMPLE", "1") == "1"
+        # launches nothing.  B2U_FUSE_UPSAMPLE: 0 = never, 1 = where it pays (N tiles of >= 128 output channels, see engine.py),
+        # 2 = every such conv.
+        self.fuse_upsample = int(os.environ.get("B2U_FUSE_UPSAMPLE", "1"))
         ups = {i["out"] for i in program if i["op"] == "up"}
-        self._lazy_up = {i["x1"] for i in program if i["op"] == "conv" and i.get("x1") in ups and len(readers.get(i["x1"], [])) == 1
-                         and i["taps"] == 9 and i["stride"] == 1 and not i.get("pk")}
+        self._lazy_up = {i["x1"]: pad64(i["cout"]) for i in program if i["op"] == "conv" and i.get("x1") in ups
+                         and len(readers.get(i["x1"], [])) == 1 and i["taps"] == 9 and i["stride"] == 1 and not i.get("pk")}
 
     # ------------------------------------------------------------------ static description
     def param_shapes(self):
@@ -638,7 +639,7 @@ class GraphEngine:
                             and (kdim >= self.bn_stats_min_k or coutp >= self.bn_stats_min_cout)):
                         # the BatchNorm that reads this output takes its statistics from this conv's epilogue (no pass over
                         # z); one buffer per conv output: another conv may run before that BatchNorm (downsample branches)
-                        rows = ops.conv_stat_rows(n, h, w, coutp, ins["taps"])
+                        rows = ops.conv_stat_rows(n, h, w, coutp, ins["taps"], bn=(1 << 18) if low is not None else 0)
                         stats = (self._workspace("bnstat:" + ins["out"], rows * 2 * coutp * 4)[:rows * 2 * coutp * 4].view(torch.float32), rows)
                     if low is not None:
                         ops.decoder_conv_fprop(xin.data, low, wf, bias, coutp, relu=ins["relu"], out=z, up_out=up_out,
@@ -756,7 +757,7 @@ class GraphEngine:
             elif op == "up":
                 xin = T[ins["x"]]
                 n, h, w, c = xin.data.shape
-                if self.fuse_upsample and ins["out"] in self._lazy_up:
+                if ins["out"] in self._lazy_up and (self.fuse_upsample == 2 or (self.fuse_upsample == 1 and self._lazy_up[ins["out"]] >= 128)):
                     t = _T(None, needs_grad=xin.needs_grad)          # the reading conv interpolates xin itself
                     t.low = xin.data
                     T[ins["out"]] = t
