@@ -75,6 +75,12 @@ def test_conv_fprop_dgrad_wgrad(b2u, cuda_device, N, H, W, C0, C1, Cout, taps, r
         mask = nhwc(torch.randn(N, C0, H, W, generator=g), dev)
         d0 = ops.conv_dgrad(dzb, wd, C0, taps=taps, mask=mask)
         assert rel(nchw(d0), ref_dx * (nchw(mask) > 0)) <= 6e-3
+        # the same launch leaving the column sums of what it stores: the bias gradient of the conv below without a pass over dz
+        rows = ops.conv_dgrad_stat_rows(N, H, W, C0, taps, masked=True)
+        st = torch.full((rows * 2 * C0,), float("nan"), device=dev)
+        d0s = ops.conv_dgrad(dzb, wd, C0, taps=taps, mask=mask, stats=st)
+        assert torch.equal(d0s.view(torch.int16), d0.view(torch.int16))
+        assert rel(ops.bias_from_stats(st, rows, C0), nchw(d0).double().sum((0, 2, 3))) <= 1e-5
     ref_dw = torch.nn.grad.conv2d_weight(xr, w.shape, dzr, padding=k // 2)
     for flags in (0, 1):          # merged N=192 vertical taps and the three-instruction variant
         dw, db = ops.conv_wgrad(x0, dzb, taps=taps, x1=x1, flags=flags, want_db=True)

@@ -41,6 +41,9 @@ SIGNATURES = {
     "b2u_bn_fwd_train_stats": (I, [P, P, P, P, P, P, P, P, P, P, I, P, SZ, LL, I, F, F, I, P]),
     "b2u_decoder_conv_fprop": (I, [P, I, P, I, P, P, P, P, P, I, I, I, I, I, I, P, I, P]),
     "b2u_conv_dgrad": (I, [P, I, P, P, I, P, I, P, I, I, I, I, I, P]),
+    "b2u_conv_dgrad_stat_rows": (I, [I, I, I, I, I, I, I]),
+    "b2u_conv_dgrad_stats": (I, [P, I, P, P, I, P, I, P, I, I, I, I, I, P, I, P]),
+    "b2u_bias_from_stats": (I, [P, I, I, P, P]),
     "b2u_conv_wgrad_workspace": (SZ, [I, I, I, I, I, I]),
     "b2u_conv_wgrad": (I, [P, I, P, I, P, I, P, P, P, SZ, I, I, I, I, I, I, P]),
     "b2u_bias_grad_workspace": (SZ, [I]),

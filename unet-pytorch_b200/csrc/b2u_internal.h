@@ -47,6 +47,7 @@ struct ConvLaunch {
 };
 int launch_conv(const ConvLaunch& a, cudaStream_t st);
 int conv_m_tiles(int N, int H, int W, int Cout, int taps, int bn_override);   // rows of ConvLaunch::stat_partial
+int stacked_tiles(int bn, int taps, int H, int tile_flags, bool masked, bool decoder);   // M tiles per CTA step
 
 struct WgradLaunch {
   const void* x0 = nullptr; int C0 = 0;

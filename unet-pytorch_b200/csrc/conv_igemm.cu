@@ -778,7 +778,7 @@ static int launch_cfg(const ConvLaunch& a, cudaStream_t st) {
 //   decoder 3x3 (8 x 16 tiles): the same with three instead of four (two 83 KB boxes do not fit), from 48 rows on
 //   1x1: N tile 64 stacks two
 // tile_flags bit 0 forces one tile, bit 1 caps the stack at two.
-static int stacked_tiles(int bn, int taps, int H, int tile_flags, bool masked, bool decoder) {
+int stacked_tiles(int bn, int taps, int H, int tile_flags, bool masked, bool decoder) {
   if (taps != 9) return bn == 64 ? 2 : 1;
   const int hb = decoder ? 16 : 8;
   const bool tall = H > hb && !(tile_flags & 1);
@@ -962,6 +962,38 @@ int b2u_conv_dgrad(const void* dz, int Cz, const void* wd, void* dx0, int C0, vo
   }
   a.bn_override = bn_override & 0xffff;
   a.tile_flags = bn_override >> 16;
+  return b2u::launch_conv(a, static_cast<cudaStream_t>(stream));
+}
+
+// b2u_conv_dgrad that also leaves the per-tile column sums of what it stores (after the ReLU mask) in stat_partial
+// [b2u_conv_dgrad_stat_rows(...)][2][C0 + C1]: dx is the pre-activation gradient of the layer below, so its column sums ARE
+// that layer's bias gradient (b2u_bias_from_stats) and the separate pass over dz (b2u_bias_grad) disappears.
+int b2u_conv_dgrad_stat_rows(int N, int H, int W, int Ctot, int taps, int bn_override, int masked) {
+  if (N <= 0 || H <= 0 || W <= 0 || Ctot <= 0) return 0;
+  int bn = bn_override & 0xffff;
+  if (!bn) bn = Ctot % 256 == 0 ? 256 : (Ctot % 192 == 0 ? 192 : (Ctot % 128 == 0 ? 128 : 64));
+  const int mt = b2u::stacked_tiles(bn, taps, H, (bn_override >> 16) & 3, masked != 0, false);
+  return N * ((H + 8 * mt - 1) / (8 * mt)) * ((W + 15) / 16);
+}
+
+int b2u_conv_dgrad_stats(const void* dz, int Cz, const void* wd, void* dx0, int C0, void* dx1, int C1, const void* mask,
+                         int N, int H, int W, int taps, int bn_override, float* stat_partial, int stat_rows, void* stream) {
+  const int ctot = C0 + (dx1 ? C1 : 0);
+  if (stat_partial == nullptr || stat_rows < b2u_conv_dgrad_stat_rows(N, H, W, ctot, taps, bn_override, mask != nullptr))
+    return b2u::set_error(B2U_ERR_ARG, "conv_dgrad_stats: statistics buffer too small");
+  b2u::ConvLaunch a;
+  a.x0 = dz; a.C0 = Cz;
+  a.wpacked = wd; a.bias = nullptr;
+  a.y0 = dx0; a.y1 = dx1; a.split_c = C0;
+  a.N = N; a.H = H; a.W = W; a.Cout = ctot; a.taps = taps;
+  a.flags = 0;
+  if (mask) {
+    if (dx1) return b2u::set_error(B2U_ERR_ARG, "dgrad: mask is only supported with a single output");
+    a.flags = 2; a.mask = static_cast<const __nv_bfloat16*>(mask); a.mask_c = C0;
+  }
+  a.bn_override = bn_override & 0xffff;
+  a.tile_flags = (bn_override >> 16) & 3;
+  a.stat_partial = stat_partial;
   return b2u::launch_conv(a, static_cast<cudaStream_t>(stream));
 }
 

@@ -513,13 +513,13 @@ __global__ void bias_grad_partial_kernel(const uint4* __restrict__ dz, float* __
 }
 // out[i] = sum_r partial[r][i]: 256 threads = 32 columns x 8 row lanes, fixed summation order (deterministic)
 __global__ void __launch_bounds__(256)
-reduce_rows_kernel(const float* __restrict__ partial, float* __restrict__ out, int rows, int L) {
+reduce_rows_kernel(const float* __restrict__ partial, float* __restrict__ out, int rows, int L, int stride) {
   __shared__ float sred[8][33];
   const int col = threadIdx.x & 31, lane_r = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + col;
   float acc = 0.f;
   if (i < L)
-    for (int r = lane_r; r < rows; r += 8) acc += __ldg(partial + static_cast<size_t>(r) * L + i);
+    for (int r = lane_r; r < rows; r += 8) acc += __ldg(partial + static_cast<size_t>(r) * stride + i);
   sred[lane_r][col] = acc;
   __syncthreads();
   if (lane_r == 0 && i < L) {
@@ -740,7 +740,16 @@ int b2u_bias_grad(const void* dz, float* db, void* ws, size_t ws_bytes, long lon
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   bias_grad_partial_kernel<<<blocks, 256, 256 * 8 * sizeof(float), st>>>(static_cast<const uint4*>(dz), static_cast<float*>(ws), P, C / 8);
   B2U_CHECK_LAUNCH("bias_grad_partial");
-  reduce_rows_kernel<<<(C + 31) / 32, 256, 0, st>>>(static_cast<const float*>(ws), db, blocks, C);
+  reduce_rows_kernel<<<(C + 31) / 32, 256, 0, st>>>(static_cast<const float*>(ws), db, blocks, C, C);
+  B2U_CHECK_LAUNCH("reduce_rows");
+  return 0;
+}
+
+// db[c] = sum over the rows of stat_partial[rows][2][C] of its first quantity: the bias gradient from the per-tile column sums
+// a data-gradient launch left behind (b2u_conv_dgrad_stats) -- no pass over dz
+int b2u_bias_from_stats(const float* stat_partial, int rows, int C, float* db, void* stream) {
+  if (rows <= 0 || C <= 0 || !stat_partial || !db) return set_error(B2U_ERR_ARG, "bias_from_stats: bad arguments");
+  reduce_rows_kernel<<<(C + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(stat_partial, db, rows, C, 2 * C);
   B2U_CHECK_LAUNCH("reduce_rows");
   return 0;
 }

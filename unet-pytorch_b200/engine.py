@@ -151,6 +151,12 @@ class UNetEngine:
         # that short (1.32 against 1.07 ms), so that stage keeps the separate pass.  B2U_FUSE_UPSAMPLE: 0 = never,
         # 1 = where it pays (default), 2 = every decoder stage (tests compare all three bit for bit).
         self.fuse_upsample = int(os.environ.get("B2U_FUSE_UPSAMPLE", "1"))
+        # Bias gradients of the wide layers (Cout >= 128; the Cout = 64 ones get theirs from the swapped-role wgrad kernel) from
+        # the data-gradient launch that PRODUCES their dz: its epilogue leaves per-tile column sums of the masked gradient it
+        # stores (b2u_conv_dgrad_stats, the BatchNorm-statistics machinery) and b2u_bias_from_stats folds them, instead of
+        # b2u_bias_grad re-reading dz from HBM (1.2 GB per headline step).  Those dgrads have K >= 1152, long enough to hide the
+        # extra epilogue work.  Layers whose dz comes from the pool / upsample adjoints keep the separate pass.
+        self.bias_from_dgrad = os.environ.get("B2U_BIAS_FROM_DGRAD", "1") == "1"
         # Weight/bias gradients on a second stream (plain conv+ReLU nets): wgrad_L depends only on dz_L and the saved
         # activation, not on the dgrad chain, so its launches are queued on a side stream behind an event and the
         # HBM-bound glue of the main chain (pool / upsample adjoints, bias column sums) shares the SMs with tensor-core-bound
@@ -502,6 +508,21 @@ class UNetEngine:
         def has(n):
             return n in trainable and n in grads
 
+        db_stats = {}      # conv name -> (per-tile column sums of its dz, rows), left behind by the dgrad that produced dz
+
+        def dgrad_to(below, dz, wd, C0, mask, out0):
+            """Masked data gradient that becomes `below`'s dz; also records dz's column sums when `below` wants a bias gradient
+            that would otherwise need a pass over dz."""
+            stats = None
+            if (self.bias_from_dgrad and not bn and ops.act_dtype() == torch.bfloat16 and want[below.name] and has(below.name + ".bias")
+                    and not below.padded and not below.first and below.cout_p >= 128 and not self.fuse_bias_grad):
+                n_, h_, w_, _ = out0.shape
+                rows = ops.conv_dgrad_stat_rows(n_, h_, w_, C0, 9, masked=mask is not None)
+                nbytes = rows * 2 * C0 * 4
+                stats = self._workspace("dbstat:" + below.name, nbytes)[:nbytes].view(torch.float32)
+                db_stats[below.name] = (stats, rows)
+            ops.conv_dgrad(dz, wd, C0, mask=mask, out0=out0, stats=stats)
+
         def layer_bwd(c, x0, g, x1=None):
             """g: gradient wrt the layer's output (BN nets: wrt y, unmasked; plain nets: wrt the pre-activation, already
             masked).  Runs BN backward if any, wgrad, bias grad; returns dz (the conv's output gradient)."""
@@ -559,6 +580,9 @@ class UNetEngine:
                 # a bias in front of BatchNorm: dz = a (g - mean(g) - xhat mean(g xhat)) sums to zero over the batch
                 # exactly, so the gradient is 0 (the reference's autograd returns fp32 cancellation residue ~1e-8)
                 grads[bn_].zero_()
+            elif want_b and not fuse_b and c.name in db_stats:
+                st_, rows_ = db_stats.pop(c.name)
+                ops.bias_from_stats(st_, rows_, c.cout_p, db=grads[bn_])
             elif want_b and not fuse_b:
                 if c.cout_p == c.cout:
                     ops.bias_grad(dz, db=grads[bn_], ws=self._workspace("bias", ops.lib().b2u_bias_grad_workspace(c.cout_p)))
@@ -624,7 +648,7 @@ class UNetEngine:
             if not need_dx[c2.name]:
                 return
             g1 = self._buf("g:" + c1.name, o1.shape)
-            ops.conv_dgrad(dz, c2.wd, c2.c0_p, mask=None if bn else o1, out0=g1)
+            dgrad_to(c1, dz, c2.wd, c2.c0_p, None if bn else o1, g1)
             dz1 = layer_bwd(c1, skip, g1, x1=up)
             if not need_dx[c1.name]:
                 return
@@ -657,7 +681,7 @@ class UNetEngine:
                     return
                 if ci > 0:
                     nxt = self._buf("g:" + block[ci - 1].name, xin.shape)
-                    ops.conv_dgrad(dz, c.wd, c.c0_p, mask=None if bn else xin, out0=nxt)
+                    dgrad_to(block[ci - 1], dz, c.wd, c.c0_p, None if bn else xin, nxt)
                     g = nxt
                 else:
                     dpool = self._buf(f"g:pool{bi}", xin.shape)

@@ -227,17 +227,36 @@ def conv_stat_rows(N, H, W, Cout, taps=9, bn=0):
     return lib().b2u_conv_stat_rows(N, H, W, Cout, taps, bn)
 
 
-def conv_dgrad(dz, wd, C0, taps=9, C1=0, mask=None, out0=None, out1=None, bn=0):
-    _req(dz, ACT, "dz"); _req(wd, ACT, "wd"); _req(mask, ACT, "mask")
+def conv_dgrad(dz, wd, C0, taps=9, C1=0, mask=None, out0=None, out1=None, bn=0, stats=None):
+    """stats: optional fp32 buffer of conv_dgrad_stat_rows(...) x 2 x (C0 + C1) floats; the launch then also leaves the per-tile
+    column sums of the (masked) gradient it stores -- the bias gradient of the conv below, see bias_from_stats."""
+    _req(dz, ACT, "dz"); _req(wd, ACT, "wd"); _req(mask, ACT, "mask"); _req(stats, torch.float32, "stats")
     N, H, W, Cz = dz.shape
     if out0 is None:
         out0 = torch.empty((N, H, W, C0), dtype=ACT, device=dz.device)
     if C1 > 0 and out1 is None:
         out1 = torch.empty((N, H, W, C1), dtype=ACT, device=dz.device)
     with _timed(f"conv_igemm|dgrad|{N}x{H}x{W}|{Cz}->{C0}+{C1}|t{taps}", 2.0 * N * H * W * Cz * (C0 + C1) * taps):
-        check(lib().b2u_conv_dgrad(ptr(dz), Cz, ptr(wd), ptr(out0), C0, ptr(out1) if C1 > 0 else None, C1, ptr(mask),
-                                   N, H, W, taps, bn, stream_ptr()))
+        if stats is None:
+            check(lib().b2u_conv_dgrad(ptr(dz), Cz, ptr(wd), ptr(out0), C0, ptr(out1) if C1 > 0 else None, C1, ptr(mask),
+                                       N, H, W, taps, bn, stream_ptr()))
+        else:
+            check(lib().b2u_conv_dgrad_stats(ptr(dz), Cz, ptr(wd), ptr(out0), C0, ptr(out1) if C1 > 0 else None, C1, ptr(mask),
+                                             N, H, W, taps, bn, ptr(stats), stats.numel() // (2 * (C0 + C1)), stream_ptr()))
     return (out0, out1) if C1 > 0 else out0
+
+
+def conv_dgrad_stat_rows(N, H, W, Ctot, taps=9, bn=0, masked=False):
+    return lib().b2u_conv_dgrad_stat_rows(N, H, W, Ctot, taps, bn, 1 if masked else 0)
+
+
+def bias_from_stats(stats, rows, C, db=None):
+    """db[c] = column sums recorded by conv_dgrad(stats=...) folded over the tiles (deterministic order)."""
+    _req(stats, torch.float32, "stats")
+    if db is None:
+        db = torch.empty((C,), dtype=torch.float32, device=stats.device)
+    check(lib().b2u_bias_from_stats(ptr(stats), rows, C, ptr(db), stream_ptr()))
+    return db
 
 
 def conv_wgrad(x0, dz, taps=9, x1=None, first_cin=0, dw=None, ws=None, flags=0, db=None, want_db=False):
