@@ -83,7 +83,7 @@ int b2u_conv_fprop_stats(const void* x0, int C0, const void* x1, int C1, const v
 int b2u_conv_dgrad_stat_rows(int N, int H, int W, int Ctot, int taps, int bn_override, int masked);
 int b2u_conv_dgrad_stats(const void* dz, int Cz, const void* wd, void* dx0, int C0, void* dx1, int C1, const void* mask,
                          int N, int H, int W, int taps, int bn_override, float* stat_partial, int stat_rows, void* stream);
-int b2u_bias_from_stats(const float* stat_partial, int rows, int C, float* db, void* stream);
+int b2u_bias_from_stats(float* stat_partial /* second-quantity slots are used as scratch */, int rows, int C, float* db, void* stream);
 /* First conv of a decoder stage with the up-sampling and the concat folded into its operand load: replaces
  * self.conv1(torch.cat([inputs1, self.up(inputs2)], 1)) of unetUp.forward (nets/unet.py:16-18; likewise Up.forward of
  * nets/TraditionalUnet.py:36-43) = nn.UpsamplingBilinear2d(scale_factor=2) + torch.cat + nn.Conv2d(k=3,p=1) [+ReLU].

@@ -746,10 +746,42 @@ int b2u_bias_grad(const void* dz, float* db, void* ws, size_t ws_bytes, long lon
 }
 
 // db[c] = sum over the rows of stat_partial[rows][2][C] of its first quantity: the bias gradient from the per-tile column sums
-// a data-gradient launch left behind (b2u_conv_dgrad_stats) -- no pass over dz
-int b2u_bias_from_stats(const float* stat_partial, int rows, int C, float* db, void* stream) {
+// a data-gradient launch left behind (b2u_conv_dgrad_stats) -- no pass over dz.  Thousands of tile rows are folded in two
+// deterministic stages: chunks of 128 rows in parallel (their sums parked in the second-quantity slot of row `chunk`, which
+// nothing else reads), then the <= 64 chunk sums.
+__global__ void __launch_bounds__(256)
+stat_rows_fold_kernel(float* __restrict__ stat, int rows, int C, int chunk) {
+  __shared__ float sred[8][33];
+  const int col = threadIdx.x & 31, lane_r = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + col;
+  const int r0 = blockIdx.y * chunk, r1 = min(rows, r0 + chunk);
+  float acc = 0.f;
+  if (i < C)
+    for (int r = r0 + lane_r; r < r1; r += 8) acc += __ldg(stat + static_cast<size_t>(r) * 2 * C + i);
+  sred[lane_r][col] = acc;
+  __syncthreads();
+  if (lane_r == 0 && i < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sred[k][col];
+    stat[static_cast<size_t>(blockIdx.y) * 2 * C + C + i] = t;
+  }
+}
+
+int b2u_bias_from_stats(float* stat_partial, int rows, int C, float* db, void* stream) {
   if (rows <= 0 || C <= 0 || !stat_partial || !db) return set_error(B2U_ERR_ARG, "bias_from_stats: bad arguments");
-  reduce_rows_kernel<<<(C + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(stat_partial, db, rows, C, 2 * C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (rows <= 256) {
+    reduce_rows_kernel<<<(C + 31) / 32, 256, 0, st>>>(stat_partial, db, rows, C, 2 * C);
+    B2U_CHECK_LAUNCH("reduce_rows");
+    return 0;
+  }
+  int chunk = 128;
+  while ((rows + chunk - 1) / chunk > 64) chunk *= 2;
+  const int chunks = (rows + chunk - 1) / chunk;
+  stat_rows_fold_kernel<<<dim3((C + 31) / 32, chunks), 256, 0, st>>>(stat_partial, rows, C, chunk);
+  B2U_CHECK_LAUNCH("stat_rows_fold");
+  reduce_rows_kernel<<<(C + 31) / 32, 256, 0, st>>>(stat_partial + C, db, chunks, C, 2 * C);
   B2U_CHECK_LAUNCH("reduce_rows");
   return 0;
 }
