@@ -465,6 +465,13 @@ def run_ours(args):
     launches = int(lib.b2u_launch_count())
     clocks = sampler.stop() if rank == 0 else None
     loss_val = out.tolist()
+    if args.kernels_only:
+        if rank == 0:
+            print(json.dumps({"kernels_only": True, "note": "profiling pass, not a bench value", "steps": K, "warmup": W,
+                              "ms_per_step": ms_total / K, "gpu_launches": launches}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # per-launch timing of the tensor-core kernels (separate pass: the events add launch gaps)
     timer = ops.KernelTimer()
@@ -549,9 +556,11 @@ def run_ours(args):
             json.dump({"steps_timed": tsteps, "rows": rows}, f, indent=1)
 
     traffic = {}
-    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp))
+    for name in ("r2_traffic.json", "r1_traffic.json"):      # the latest committed ncu capture of this command
+        tp = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tp):
+            traffic = json.load(open(tp))
+            break
 
     def roof(rec, traffic=None):
         if rec["ms"] <= 0:
@@ -575,7 +584,7 @@ def run_ours(args):
                           "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e_u8 / K,
                           "note": "raw uint8 NHWC images + uint8 label maps; /255, CHW, int64 map on the device"},
         "gpu_launches": launches,
-        # traffic: DRAM bytes per launch from the committed ncu capture of this same command (profiles/r1_traffic.json)
+        # traffic: DRAM bytes per launch from the committed ncu capture of this same command (profiles/r2_traffic.json)
         "roofline": roof(ig, traffic.get("conv_igemm", {}).get("dram_bytes_per_launch")),
         "roofline_wgrad": roof(wg, traffic.get("conv_wgrad", {}).get("dram_bytes_per_launch")),
         "model_tflops": value * TRAIN_GFLOP_PER_IMG / 1e3 / world,
@@ -605,6 +614,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the side measurements of BASELINE configs[2..4] (variants key)")
+    ap.add_argument("--kernels-only", action="store_true",
+                    help="profiling pass (ncu): warm-up + the K device-resident steps, nothing else; prints a reduced line that is NOT a bench value")
     ap.add_argument("--detail", default=None, help="write the per-layer conv kernel timing table (JSON) here")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
