@@ -159,12 +159,12 @@ class UNetEngine:
         self.bias_from_dgrad = os.environ.get("B2U_BIAS_FROM_DGRAD", "1") == "1"
         # Weight/bias gradients on a second stream (plain conv+ReLU nets): wgrad_L depends only on dz_L and the saved
         # activation, not on the dgrad chain, so its launches are queued on a side stream behind an event and the
-        # HBM-bound glue of the main chain (pool / upsample adjoints, bias column sums) shares the SMs with tensor-core-bound
-        # kernels of the other stream instead of running alone.  Measured A/B on one B200 (bench.py, 30 steps, twice each):
-        # 22.72-22.80 ms/step with it, 22.95-22.97 without (+0.9 %; a second box: 23.2 vs 23.1-23.4, i.e. noise): the GPU is power-capped, the extra concurrency costs
-        # 25-45 MHz of SM clock, and per-kernel CUDA-event times stop being the kernels' own durations (the roofline record
-        # of bench.py needs them), so it is OFF by default; B2U_WGRAD_STREAM=1 turns it on
-        self.wgrad_stream = os.environ.get("B2U_WGRAD_STREAM", "0") == "1"
+        # HBM-bound glue of the main chain (pool / upsample adjoints, column-sum folds) shares the SMs with tensor-core-bound
+        # kernels of the other stream instead of running alone.  Same-box A/B (bench.py --kernels-only, 12 steps, twice each,
+        # round 2 final build): 21.79 / 21.67 ms per step with it, 22.05 / 21.87 without (-1 %; round 1 measured -0.9 %).
+        # Per-launch CUDA-event times are not a kernel's own duration while two streams overlap, so the roofline pass of
+        # bench.py (ops.KernelTimer) runs single-stream: backward() checks ops.timing_active().  B2U_WGRAD_STREAM=0 turns it off.
+        self.wgrad_stream = os.environ.get("B2U_WGRAD_STREAM", "1") == "1"
         self._side = None
         self._pack_key = self._pack_versions = self._pack_table = None
         self._pack_total = 0
@@ -451,7 +451,7 @@ class UNetEngine:
         if self.saved is None:
             raise RuntimeError("backward() without a saved forward()")
         side = None
-        if self.wgrad_stream and not self.bn and dlogits.is_cuda:
+        if self.wgrad_stream and not self.bn and dlogits.is_cuda and not ops.timing_active():
             if self._side is None or self._side.device != dlogits.device:
                 self._side = torch.cuda.Stream(device=dlogits.device)
             side = self._side

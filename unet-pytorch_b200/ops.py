@@ -64,6 +64,12 @@ def set_timer(timer):
     _TIMER = timer
 
 
+def timing_active():
+    """True while a KernelTimer brackets individual launches with events: the engines then keep every launch on one stream,
+    so that an event pair measures that kernel alone."""
+    return _TIMER is not None
+
+
 class _timed:
     def __init__(self, tag, flops):
         self.tag, self.flops = tag, flops
