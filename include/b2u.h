@@ -84,6 +84,17 @@ int b2u_conv_dgrad_stat_rows(int N, int H, int W, int Ctot, int taps, int bn_ove
 int b2u_conv_dgrad_stats(const void* dz, int Cz, const void* wd, void* dx0, int C0, void* dx1, int C1, const void* mask,
                          int N, int H, int W, int taps, int bn_override, float* stat_partial, int stat_rows, void* stream);
 int b2u_bias_from_stats(float* stat_partial /* second-quantity slots are used as scratch */, int rows, int C, float* db, void* stream);
+/* ReLU backward from a BIT mask (r2).  b2u_conv_fprop_relu_bits = b2u_conv_fprop (or, with low != NULL and x1 == NULL,
+ * b2u_decoder_conv_fprop) with ReLU, which also writes bits_out [N,H,W,Cout/64] 64-bit words: bit c % 64 of word c / 64 =
+ * (y[n,h,w,c] > 0) -- what autograd's ReLU backward (nn.ReLU, nets/vgg.py:57, nets/unet.py:14) needs to know about y.
+ * b2u_conv_dgrad_bits = b2u_conv_dgrad with one output whose mask is that tensor: 8 bytes per pixel and 64-channel block
+ * instead of 128 bytes of y, and the launch tiles like an unmasked one (four stacked M tiles for the 64-channel layers).
+ * stat_partial (nullable): per-tile column sums as in b2u_conv_dgrad_stats, rows = b2u_conv_dgrad_stat_rows(masked = 0). */
+int b2u_conv_fprop_relu_bits(const void* x0, int C0, const void* x1, int C1, const void* low, const void* wf, const float* bias,
+                             void* y, void* up_out, unsigned long long* bits_out, int N, int H, int W, int Cout, int taps,
+                             int bn_override, void* stream);
+int b2u_conv_dgrad_bits(const void* dz, int Cz, const void* wd, void* dx0, int C0, const unsigned long long* mask_bits,
+                        int N, int H, int W, int taps, int bn_override, float* stat_partial, int stat_rows, void* stream);
 /* First conv of a decoder stage with the up-sampling and the concat folded into its operand load: replaces
  * self.conv1(torch.cat([inputs1, self.up(inputs2)], 1)) of unetUp.forward (nets/unet.py:16-18; likewise Up.forward of
  * nets/TraditionalUnet.py:36-43) = nn.UpsamplingBilinear2d(scale_factor=2) + torch.cat + nn.Conv2d(k=3,p=1) [+ReLU].

@@ -93,6 +93,69 @@ def test_conv_fprop_dgrad_wgrad(b2u, cuda_device, N, H, W, C0, C1, Cout, taps, r
     assert rel(ops.bias_grad(dzb), dzr.sum((0, 2, 3))) <= 1e-4
 
 
+def _bits_of(y):
+    """(y > 0) packed like the kernels do: int64 [N, H, W, C // 64], bit c % 64 of word c // 64."""
+    N, H, W, C = y.shape
+    b = (y.float() > 0).view(N, H, W, C // 64, 64).to(torch.int64)
+    sh = torch.arange(64, device=y.device, dtype=torch.int64)
+    return (b << sh).sum(-1)          # bit 63 wraps into the sign bit: exactly the two's-complement word
+
+
+@pytest.mark.parametrize("N,H,W,C0,C1,Cout,taps", [(1, 8, 16, 64, 0, 64, 9), (2, 40, 24, 64, 0, 64, 9), (1, 72, 40, 64, 64, 64, 9),
+                                                     (2, 24, 40, 128, 0, 128, 9), (1, 16, 16, 256, 0, 512, 9), (2, 16, 24, 64, 0, 64, 1),
+                                                     (1, 16, 32, 64, 128, 192, 9)])
+def test_relu_bit_masks(b2u, cuda_device, N, H, W, C0, C1, Cout, taps):
+    """ReLU backward from bit masks: b2u_conv_fprop_relu_bits writes (y > 0) as one bit per channel next to a bit-identical y,
+    and b2u_conv_dgrad_bits masks with those bits exactly like b2u_conv_dgrad does with y itself (bit-identical dx, same
+    column sums), while tiling like an unmasked launch."""
+    ops, dev = b2u.ops, cuda_device
+    g = torch.Generator().manual_seed(23)
+    k = 3 if taps == 9 else 1
+    x = nhwc(torch.randn(N, C0 + C1, H, W, generator=g), dev)
+    w = torch.randn(Cout, C0 + C1, k, k, generator=g) / ((C0 + C1) * taps) ** 0.5
+    b = torch.randn(Cout, generator=g).to(dev)
+    wf, _ = ops.pack_weights(w.to(dev))
+    x0 = x[..., :C0].contiguous(); x1 = x[..., C0:].contiguous() if C1 else None
+    y = ops.conv_fprop(x0, wf, b, Cout, taps=taps, relu=True, x1=x1)
+    bits = torch.zeros(N, H, W, Cout // 64, dtype=torch.int64, device=dev)
+    yb = ops.conv_fprop_relu_bits(x0, wf, b, Cout, bits, taps=taps, x1=x1)
+    assert torch.equal(yb.view(torch.int16), y.view(torch.int16))
+    assert torch.equal(bits, _bits_of(y))
+    assert 0.2 < (y > 0).float().mean().item() < 0.8                      # a real mask, not all ones / zeros
+    # the backward of a conv that READS y: dz has Cz channels, dx has Cout (= y's) channels
+    Cz = 128
+    wn = torch.randn(Cz, Cout, k, k, generator=g) / (Cout * taps) ** 0.5
+    _, wd = ops.pack_weights(wn.to(dev))
+    dz = nhwc(torch.randn(N, Cz, H, W, generator=g), dev)
+    ref = ops.conv_dgrad(dz, wd, Cout, taps=taps, mask=y)
+    got = ops.conv_dgrad_bits(dz, wd, Cout, bits, taps=taps)
+    assert torch.equal(got.view(torch.int16), ref.view(torch.int16))
+    rows = ops.conv_dgrad_stat_rows(N, H, W, Cout, taps, masked=False)
+    st = torch.full((rows * 2 * Cout,), float("nan"), device=dev)
+    got2 = ops.conv_dgrad_bits(dz, wd, Cout, bits, taps=taps, stats=st)
+    assert torch.equal(got2.view(torch.int16), ref.view(torch.int16))
+    assert rel(ops.bias_from_stats(st, rows, Cout), nchw(ref).double().sum((0, 2, 3))) <= 1e-5
+
+
+def test_relu_bit_masks_decoder_conv(b2u, cuda_device):
+    """The decoder conv (fused up-sampling) writes the same bit mask as the plain conv over the materialised up-sampled tensor."""
+    ops, dev = b2u.ops, cuda_device
+    g = torch.Generator().manual_seed(29)
+    N, H, W, C0, C1, Cout = 2, 40, 24, 64, 128, 128
+    skip = nhwc(torch.randn(N, C0, H, W, generator=g), dev)
+    low = nhwc(torch.randn(N, C1, H // 2, W // 2, generator=g), dev)
+    w = torch.randn(Cout, C0 + C1, 3, 3, generator=g) / ((C0 + C1) * 9) ** 0.5
+    b = torch.randn(Cout, generator=g).to(dev)
+    wf, _ = ops.pack_weights(w.to(dev))
+    up = ops.upsample2x(low)
+    y = ops.conv_fprop(skip, wf, b, Cout, relu=True, x1=up)
+    bits = torch.zeros(N, H, W, Cout // 64, dtype=torch.int64, device=dev)
+    up_out = torch.empty_like(up)
+    yb = ops.conv_fprop_relu_bits(skip, wf, b, Cout, bits, low=low, up_out=up_out)
+    assert torch.equal(yb.view(torch.int16), y.view(torch.int16)) and torch.equal(up_out.view(torch.int16), up.view(torch.int16))
+    assert torch.equal(bits, _bits_of(y))
+
+
 DECODER_CASES = [
     # N, H, W, C0 (skip), C1 (low), Cout -- H, W of the conv (the low tensor is H/2 x W/2)
     (1, 8, 16, 64, 64, 64),        # one tile, one M tile per step

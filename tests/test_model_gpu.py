@@ -253,6 +253,28 @@ def test_fused_upsample_equals_separate_pass(b2u, cuda_device, model, C):
     assert runs[0][3] - runs[1][3] == wide
 
 
+def test_relu_bit_masks_and_dgrad_bias_sums_change_nothing(b2u, cuda_device):
+    """Three round-2 traffic savers of the plain conv + ReLU nets -- ReLU backward from bit masks (engine.relu_bits), bias
+    gradients from the producing data gradient's column sums (engine.bias_from_dgrad), weight gradients on a second stream
+    (engine.wgrad_stream) -- against the straightforward order: the loss and the data path are bit-identical, bias gradients agree
+    to fp32 summation order."""
+    dev, C = cuda_device, 21
+    imgs, pngs = O.make_inputs(2, C, 96, 64, seed=8)
+    runs = []
+    for on in (True, False):
+        tr = b2u.UnetTrainer(num_classes=C, device=dev, lr=0.0, state_dict=O.make_params(C, seed=11))
+        tr.engine.relu_bits = tr.engine.bias_from_dgrad = tr.engine.wgrad_stream = on
+        out = tr.train_step(imgs.to(dev), pngs.to(dev)).cpu()
+        torch.cuda.synchronize()
+        runs.append((out, {k: v.clone() for k, v in tr.grads.items()}))
+    assert torch.equal(runs[0][0], runs[1][0])
+    for k, g in runs[1][1].items():
+        if k.endswith(".weight"):
+            assert torch.equal(runs[0][1][k], g), k
+        else:
+            assert torch.allclose(runs[0][1][k], g, rtol=1e-4, atol=1e-6 * g.abs().max().item() + 1e-12), k
+
+
 def test_full_size_step_properties(b2u, cuda_device):
     """BASELINE config-2 tile sizes (512x512, 21 classes) at batch 2: parity against the same restatement executed
     by torch on the GPU in fp32 (TF32 off) -- the CPU oracle needs minutes at this size -- plus finite loss."""

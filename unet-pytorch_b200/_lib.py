@@ -41,6 +41,8 @@ SIGNATURES = {
     "b2u_bn_fwd_train_stats": (I, [P, P, P, P, P, P, P, P, P, P, I, P, SZ, LL, I, F, F, I, P]),
     "b2u_decoder_conv_fprop": (I, [P, I, P, I, P, P, P, P, P, I, I, I, I, I, I, P, I, P]),
     "b2u_conv_dgrad": (I, [P, I, P, P, I, P, I, P, I, I, I, I, I, P]),
+    "b2u_conv_fprop_relu_bits": (I, [P, I, P, I, P, P, P, P, P, P, I, I, I, I, I, I, P]),
+    "b2u_conv_dgrad_bits": (I, [P, I, P, P, I, P, I, I, I, I, I, P, I, P]),
     "b2u_conv_dgrad_stat_rows": (I, [I, I, I, I, I, I, I]),
     "b2u_conv_dgrad_stats": (I, [P, I, P, P, I, P, I, P, I, I, I, I, I, P, I, P]),
     "b2u_bias_from_stats": (I, [P, I, I, P, P]),

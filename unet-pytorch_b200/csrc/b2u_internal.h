@@ -38,8 +38,10 @@ struct ConvLaunch {
   void* y0 = nullptr; void* y1 = nullptr;   // outputs (NHWC bf16); y1 receives channels >= split_c
   int split_c = 0;
   const __nv_bfloat16* mask = nullptr; int mask_c = 0;
+  const unsigned long long* mask_bits = nullptr;   // flags bit3: the mask as [N,H,W,Cout/64] 64-bit words, one bit per channel
+  unsigned long long* bits_out = nullptr;          // forward + ReLU: receives (y > 0) in that layout
   int N = 0, H = 0, W = 0, Cout = 0, taps = 9;
-  int flags = 0;                            // bit0 relu, bit1 mask, bit2 classifier head (fp32 NCHW logits)
+  int flags = 0;                            // bit0 relu, bit1 mask, bit2 classifier head (fp32 NCHW logits), bit3 bit mask
   float* stat_partial = nullptr;            // optional [m tiles][2][Cout] fp32: per-tile column sums (z, z^2) of the stored output
   float* head_out = nullptr; int head_cls = 0;   // bit2: logits [N][head_cls][H][W]; Cout must be 64 = [hi(32) | lo(32)] weights
   int bn_override = 0;

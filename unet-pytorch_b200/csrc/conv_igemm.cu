@@ -69,7 +69,7 @@ struct ConvParams {
   int tiles_w, tiles_h;
   int num_m_tiles, num_n_tiles;
   int split_c;       // output channels >= split_c go to the second output tensor map
-  int flags;         // bit0 relu, bit1 mask, bit2 classifier head
+  int flags;         // bit0 relu, bit1 mask, bit2 classifier head, bit3 the mask is a bit mask (mask_bits)
   float* stat_partial;  // [m tiles][2][Cout] or null: per-tile sums of z and z^2 over the tile's in-image pixels (BatchNorm statistics)
   float* head_out;   // bit2: fp32 NCHW logits [N][head_cls][H][W]
   int head_cls;
@@ -78,6 +78,8 @@ struct ConvParams {
   const __nv_bfloat16* mask;  // NHWC [N,H,W,mask_c] or null; keeps y where mask > 0
   int mask_c;
   int* sched;        // dynamic tile scheduler: [0] next tile id, [1] CTAs done (self-resetting); null = static round robin
+  const unsigned long long* mask_bits;   // flags bit3: the ReLU mask as one bit per channel, [N,H,W,Cout/64] 64-bit words (bit c%64 of word c/64)
+  unsigned long long* bits_out;          // forward + ReLU, nullable: receives (y > 0) in that layout for the backward pass
   const __nv_bfloat16* up_low;  // UP kernels: source 1 = this [N, H/2, W/2, C1] tensor, upsampled 2x on the fly
   __nv_bfloat16* up_out;        // UP kernels, nullable: receives the upsampled tensor [N, H, W, C1] (operand of the weight gradient)
   float up_sh, up_sw;           // (H/2 - 1) / (H - 1), (W/2 - 1) / (W - 1)
@@ -513,7 +515,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll
         for (int q = 0; q < 8; ++q) mreg[q] = inb_ ? __ldg(mrow + q) : make_uint4(0, 0, 0, 0);
       };
-      if (MD == 0 && (p.flags & 2)) fetch_mask(0);
+      // bit-mask form of the same: 8 bytes per pixel and 64-channel block instead of 128 (ConvParams::mask_bits)
+      const int words = p.Cout >> 6;
+      unsigned long long mbits = 0ull;
+      auto fetch_bits = [&](int jj_) {
+        const int mt_ = jj_ / (BN / 64), j_ = jj_ % (BN / 64);
+        const int gh_ = h0 + mt_ * kHb + ph;
+        mbits = (gh_ < p.H && gw < p.W)
+                    ? __ldg(p.mask_bits + ((static_cast<size_t>(img) * p.H + gh_) * p.W + gw) * words + (n0 >> 6) + j_) : 0ull;
+      };
+      if (MD == 0 && (p.flags & 2)) { if (p.flags & 8) fetch_bits(0); else fetch_mask(0); }
       // this tile's bias slice; the parity double buffer + the barrier keep a fast warp from overwriting values a
       // slow warp of the previous tile still reads
       float* sB = sBias + bpar * 256;
@@ -561,7 +572,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
         const int cbase = n0 + j * 64;
         uint32_t packed[32];
-        if (p.flags & 2) {
+        if (MD == 0 && (p.flags & 8)) {
+          // ReLU backward from the bit mask the forward conv left behind: keep column c where bit c of this pixel's word is set
+          const uint32_t bw[2] = {static_cast<uint32_t>(mbits), static_cast<uint32_t>(mbits >> 32)};
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            float lo = __uint_as_float(v[2 * e]) + sB[j * 64 + 2 * e];
+            float hi = __uint_as_float(v[2 * e + 1]) + sB[j * 64 + 2 * e + 1];
+            const uint32_t two = bw[e >> 4] >> ((2 * e) & 31);
+            lo = (two & 1u) ? lo : 0.f;
+            hi = (two & 2u) ? hi : 0.f;
+            packed[e] = pack_bf16x2(lo, hi);
+          }
+          if (jj + 1 < MT * (BN / 64)) fetch_bits(jj + 1);
+        } else if (p.flags & 2) {
           if (MD > 0) {
             asm volatile("cp.async.wait_group %0;" ::"n"(MD > 0 ? MD - 1 : 0) : "memory");
             const uint32_t src = sMask + use_slot * (kTileM * 128) + row * 128;
@@ -604,6 +628,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               packed[e] = pack_bf16x2(lo, hi);
             }
           }
+        }
+        if (p.bits_out != nullptr) {
+          // (y > 0) of the 64 values this thread just rounded, one bit per channel: the ReLU mask of the backward pass at
+          // 1/16 of the bytes of y (a rounded value is positive iff its 15 magnitude bits are not all zero: y >= 0 here)
+          uint32_t bw[2] = {0u, 0u};
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const uint32_t t = packed[e] & 0x7FFF7FFFu;
+            const uint32_t two = ((t & 0xFFFFu) ? 1u : 0u) | ((t >> 16) ? 2u : 0u);
+            bw[e >> 4] |= two << ((2 * e) & 31);
+          }
+          const int gh = h0 + mt * kHb + ph;
+          if (gh < p.H && gw < p.W)
+            p.bits_out[((static_cast<size_t>(img) * p.H + gh) * p.W + gw) * words + (n0 >> 6) + j] =
+                (static_cast<unsigned long long>(bw[1]) << 32) | bw[0];
         }
         // staging buffer `sbuf` was last read by the TMA store issued two sub-tiles ago
         if (issuer) tma_store_wait_read<1>();
@@ -756,6 +795,8 @@ static int launch_cfg(const ConvLaunch& a, cudaStream_t st) {
   p.scale = a.scale;
   p.mask = a.mask;
   p.mask_c = a.mask_c;
+  p.mask_bits = a.mask_bits;
+  p.bits_out = a.bits_out;
   p.sched = MD > 0 ? nullptr : sched_slot();      // the mask-stream variants prefetch across tile boundaries: static order
   p.up_low = UP ? static_cast<const __nv_bfloat16*>(a.up_low) : nullptr;
   p.up_out = UP ? static_cast<__nv_bfloat16*>(a.up_out) : nullptr;
@@ -804,7 +845,11 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st) {
   if (a.taps != 9 && a.taps != 1) return set_error(B2U_ERR_SHAPE, "conv: taps must be 9 or 1");
   if (a.Cout <= 0) return set_error(B2U_ERR_SHAPE, "conv: Cout %d must be positive", a.Cout);
   if (a.Cout % 64 != 0) return set_error(B2U_ERR_SHAPE, "conv: Cout %d must be a multiple of 64", a.Cout);
-  if ((a.flags & 2) && (a.mask == nullptr || a.mask_c % 8 != 0 || a.mask_c < a.Cout))
+  if ((a.flags & 8) && (!(a.flags & 2) || a.mask_bits == nullptr || a.y1 != nullptr))
+    return set_error(B2U_ERR_ARG, "conv: the bit-mask flag needs mask_bits and a single output");
+  if (a.bits_out != nullptr && (!(a.flags & 1) || (a.flags & 6) || a.y1 != nullptr || a.scale != nullptr))
+    return set_error(B2U_ERR_ARG, "conv: bits_out is written by a forward conv + ReLU with one output");
+  if ((a.flags & 2) && !(a.flags & 8) && (a.mask == nullptr || a.mask_c % 8 != 0 || a.mask_c < a.Cout))
     return set_error(B2U_ERR_SHAPE, "conv: mask flag needs a mask tensor with >= Cout channels, %% 8 == 0");
   if (ctot <= 0 || a.C0 % 64 != 0 || a.C1 % 64 != 0)
     return set_error(B2U_ERR_SHAPE, "conv: input channels (%d,%d) must be multiples of 64", a.C0, a.C1);
@@ -823,7 +868,9 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st) {
   else if (a.Cout % 128 == 0) bn = 128;
   else bn = 64;
 
-  const int mt = stacked_tiles(bn, a.taps, a.H, a.tile_flags, (a.flags & 2) != 0, a.up_low != nullptr);
+  // a bit mask costs 8 bytes per pixel and block: those launches tile like unmasked ones (no cp.async mask stream)
+  const bool bf16_mask = (a.flags & 2) && !(a.flags & 8);
+  const int mt = stacked_tiles(bn, a.taps, a.H, a.tile_flags, bf16_mask, a.up_low != nullptr);
   if (a.up_low != nullptr) {
     // decoder conv over [skip, upsample2x(low)]: 8 x 16 tiles, one halo box per channel block, interpolation warps
     if (a.taps != 9 || a.C1 <= 0 || (a.H & 1) || (a.W & 1) || (a.flags & 6) || a.y1 != nullptr)
@@ -852,7 +899,7 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st) {
         // tiles: its cp.async mask stream does not fit next to the larger A stages and register prefetch is slower
         // (0.443 vs 0.415 ms).  tile_flags bit 1 forces the two-tile kernel (tests).
         if (mt == 4) return launch_cfg<64, 9, 4, 3, 2, 2>(a, st);
-        if (mt == 2 && (a.flags & 2)) return launch_cfg<64, 9, 2, 3, 3, 2, 2>(a, st);
+        if (mt == 2 && bf16_mask) return launch_cfg<64, 9, 2, 3, 3, 2, 2>(a, st);
         return mt == 2 ? launch_cfg<64, 9, 2, 3, 3, 3>(a, st) : launch_cfg<64, 9, 1, 3, 4, 4>(a, st);
     }
   } else {
@@ -860,7 +907,7 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st) {
       case 256: return launch_cfg<256, 1, 1, 1, 3, 3>(a, st);
       case 192: return launch_cfg<192, 1, 1, 1, 4, 4>(a, st);
       case 128: return launch_cfg<128, 1, 1, 1, 4, 4>(a, st);
-      case 64:  return (a.flags & 2) ? launch_cfg<64, 1, 2, 1, 3, 4, 3>(a, st) : launch_cfg<64, 1, 2, 1, 3, 4>(a, st);
+      case 64:  return bf16_mask ? launch_cfg<64, 1, 2, 1, 3, 4, 3>(a, st) : launch_cfg<64, 1, 2, 1, 3, 4>(a, st);
     }
   }
   return set_error(B2U_ERR_SHAPE, "conv: unsupported N tile %d", bn);
@@ -991,6 +1038,46 @@ int b2u_conv_dgrad_stats(const void* dz, int Cz, const void* wd, void* dx0, int 
     if (dx1) return b2u::set_error(B2U_ERR_ARG, "dgrad: mask is only supported with a single output");
     a.flags = 2; a.mask = static_cast<const __nv_bfloat16*>(mask); a.mask_c = C0;
   }
+  a.bn_override = bn_override & 0xffff;
+  a.tile_flags = (bn_override >> 16) & 3;
+  a.stat_partial = stat_partial;
+  return b2u::launch_conv(a, static_cast<cudaStream_t>(stream));
+}
+
+// Forward conv + bias + ReLU that also leaves the ReLU decisions behind as a BIT mask: bits_out [N,H,W,Cout/64] 64-bit words,
+// bit c % 64 of word c / 64 = (y[n,h,w,c] > 0).  The backward pass then reads 8 bytes per pixel and 64-channel block where
+// it would re-read 128 bytes of y (b2u_conv_dgrad_bits).  low != NULL (and x1 == NULL): the decoder conv of
+// b2u_decoder_conv_fprop (source 1 = upsample2x(low), up_out = its by-product copy).
+int b2u_conv_fprop_relu_bits(const void* x0, int C0, const void* x1, int C1, const void* low, const void* wf, const float* bias,
+                             void* y, void* up_out, unsigned long long* bits_out, int N, int H, int W, int Cout, int taps,
+                             int bn_override, void* stream) {
+  if (bits_out == nullptr) return b2u::set_error(B2U_ERR_ARG, "conv_fprop_relu_bits: bits_out is required");
+  if (low != nullptr && x1 != nullptr) return b2u::set_error(B2U_ERR_ARG, "conv_fprop_relu_bits: give x1 or low, not both");
+  b2u::ConvLaunch a;
+  a.x0 = x0; a.C0 = C0; a.x1 = x1; a.C1 = (x1 || low) ? C1 : 0;
+  a.up_low = low; a.up_out = low ? up_out : nullptr;
+  a.wpacked = wf; a.bias = bias; a.y0 = y; a.bits_out = bits_out;
+  a.N = N; a.H = H; a.W = W; a.Cout = Cout; a.taps = taps;
+  a.flags = 1;
+  a.bn_override = bn_override & 0xffff;
+  a.tile_flags = (bn_override >> 16) & 3;
+  return b2u::launch_conv(a, static_cast<cudaStream_t>(stream));
+}
+
+// b2u_conv_dgrad (single output) with the ReLU mask given as the bit mask of b2u_conv_fprop_relu_bits: dx0 = 0 where the
+// bit is clear.  stat_partial (nullable): per-tile column sums as in b2u_conv_dgrad_stats, rows =
+// b2u_conv_dgrad_stat_rows(..., masked = 0) -- a bit-masked launch tiles like an unmasked one.
+int b2u_conv_dgrad_bits(const void* dz, int Cz, const void* wd, void* dx0, int C0, const unsigned long long* mask_bits,
+                        int N, int H, int W, int taps, int bn_override, float* stat_partial, int stat_rows, void* stream) {
+  if (mask_bits == nullptr) return b2u::set_error(B2U_ERR_ARG, "conv_dgrad_bits: mask_bits is required");
+  if (stat_partial != nullptr && stat_rows < b2u_conv_dgrad_stat_rows(N, H, W, C0, taps, bn_override, 0))
+    return b2u::set_error(B2U_ERR_ARG, "conv_dgrad_bits: statistics buffer too small");
+  b2u::ConvLaunch a;
+  a.x0 = dz; a.C0 = Cz;
+  a.wpacked = wd; a.bias = nullptr;
+  a.y0 = dx0; a.split_c = C0;
+  a.N = N; a.H = H; a.W = W; a.Cout = C0; a.taps = taps;
+  a.flags = 2 | 8; a.mask_bits = mask_bits;
   a.bn_override = bn_override & 0xffff;
   a.tile_flags = (bn_override >> 16) & 3;
   a.stat_partial = stat_partial;

@@ -157,6 +157,12 @@ class UNetEngine:
         # b2u_bias_grad re-reading dz from HBM (1.2 GB per headline step).  Those dgrads have K >= 1152, long enough to hide the
         # extra epilogue work.  Layers whose dz comes from the pool / upsample adjoints keep the separate pass.
         self.bias_from_dgrad = os.environ.get("B2U_BIAS_FROM_DGRAD", "1") == "1"
+        # ReLU backward from bit masks (plain conv + ReLU nets, training forward): every conv epilogue also writes (y > 0) as one
+        # bit per channel ([N,H,W,C/64] 64-bit words, 1/16 of the bytes of y) and the masked data gradients / the head backward
+        # read those 8 bytes per pixel and block instead of 128 bytes of y -- 2.8 GB less HBM traffic per headline step, and the
+        # HBM-bound 64-channel data gradients at 512 x 512 then tile like unmasked launches (four stacked M tiles, no cp.async
+        # mask stream).  B2U_RELU_BITS=0 restores the bf16 masks (the pool / upsample adjoints always read y: they need values).
+        self.relu_bits = os.environ.get("B2U_RELU_BITS", "0") == "1"
         # Weight/bias gradients on a second stream (plain conv+ReLU nets): wgrad_L depends only on dz_L and the saved
         # activation, not on the dgrad chain, so its launches are queued on a side stream behind an event and the
         # HBM-bound glue of the main chain (pool / upsample adjoints, column-sum folds) shares the SMs with tensor-core-bound
@@ -297,7 +303,12 @@ class UNetEngine:
 
         if not c.bn:
             out = self._buf(c.name, (n, h, w, c.cout_p))
-            conv(bias, True, out)
+            if save and self.relu_bits and ops.act_dtype() == torch.bfloat16:
+                bits = self._buf("bits:" + c.name, (n, h, w, c.cout_p // 64), torch.int64)
+                ops.conv_fprop_relu_bits(x0, c.wf, bias, c.cout_p, bits, taps=taps, x1=x1, low=low, up_out=up_out, out=out)
+                A["bits:" + c.name] = bits
+            else:
+                conv(bias, True, out)
             A[c.name] = out
             return out
         if not training and not save:
@@ -512,16 +523,20 @@ class UNetEngine:
 
         def dgrad_to(below, dz, wd, C0, mask, out0):
             """Masked data gradient that becomes `below`'s dz; also records dz's column sums when `below` wants a bias gradient
-            that would otherwise need a pass over dz."""
+            that would otherwise need a pass over dz.  The ReLU mask is `below`'s bit mask when the forward left one."""
+            bits = A.get("bits:" + below.name) if mask is not None else None
             stats = None
             if (self.bias_from_dgrad and not bn and ops.act_dtype() == torch.bfloat16 and want[below.name] and has(below.name + ".bias")
                     and not below.padded and not below.first and below.cout_p >= 128 and not self.fuse_bias_grad):
                 n_, h_, w_, _ = out0.shape
-                rows = ops.conv_dgrad_stat_rows(n_, h_, w_, C0, 9, masked=mask is not None)
+                rows = ops.conv_dgrad_stat_rows(n_, h_, w_, C0, 9, masked=mask is not None and bits is None)
                 nbytes = rows * 2 * C0 * 4
                 stats = self._workspace("dbstat:" + below.name, nbytes)[:nbytes].view(torch.float32)
                 db_stats[below.name] = (stats, rows)
-            ops.conv_dgrad(dz, wd, C0, mask=mask, out0=out0, stats=stats)
+            if bits is not None:
+                ops.conv_dgrad_bits(dz, wd, C0, bits, out0=out0, stats=stats)
+            else:
+                ops.conv_dgrad(dz, wd, C0, mask=mask, out0=out0, stats=stats)
 
         def layer_bwd(c, x0, g, x1=None):
             """g: gradient wrt the layer's output (BN nets: wrt y, unmasked; plain nets: wrt the pre-activation, already
@@ -605,7 +620,11 @@ class UNetEngine:
             dl = dlogits.contiguous()
             if need_dx[hn]:
                 wd_head = ops.pack_head_dgrad(wh, wd=self._buf("head:wd", (64, 64)))
-                ops.conv_dgrad(dl, wd_head, 64, taps=1, mask=None if bn else last, out0=g)
+                hbits = None if bn else A.get("bits:" + self.dec[-1][1].name)
+                if hbits is not None:
+                    ops.conv_dgrad_bits(dl, wd_head, 64, hbits, taps=1, out0=g)
+                else:
+                    ops.conv_dgrad(dl, wd_head, 64, taps=1, mask=None if bn else last, out0=g)
             if fw or fb:
                 dw64 = self._buf("head:dw", (64, 64, 1, 1), torch.float32)
                 db64 = self._buf("head:db", (64,), torch.float32)

@@ -252,6 +252,38 @@ def conv_dgrad(dz, wd, C0, taps=9, C1=0, mask=None, out0=None, out1=None, bn=0, 
     return (out0, out1) if C1 > 0 else out0
 
 
+def conv_fprop_relu_bits(x0, wf, bias, Cout, bits, taps=9, x1=None, low=None, up_out=None, out=None, bn=0):
+    """conv + bias + ReLU that also writes the ReLU decisions as a bit mask: bits int64 [N, H, W, Cout // 64], bit c % 64 of
+    word c // 64 = (y > 0).  low: the decoder form (second source = upsample2x(low), see decoder_conv_fprop)."""
+    _req(x0, ACT, "x0"); _req(x1, ACT, "x1"); _req(low, ACT, "low"); _req(wf, ACT, "wf"); _req(bias, torch.float32, "bias")
+    _req(bits, torch.int64, "bits"); _req(up_out, ACT, "up_out")
+    N, H, W, C0 = x0.shape
+    C1 = x1.shape[3] if x1 is not None else (low.shape[3] if low is not None else 0)
+    if tuple(bits.shape) != (N, H, W, Cout // 64):
+        raise ValueError("conv_fprop_relu_bits: bits must be int64 [N, H, W, Cout // 64]")
+    if out is None:
+        out = torch.empty((N, H, W, Cout), dtype=ACT, device=x0.device)
+    with _timed(f"conv_igemm|fprop|{N}x{H}x{W}|{C0}+{C1}->{Cout}|t{taps}", 2.0 * N * H * W * Cout * (C0 + C1) * taps):
+        check(lib().b2u_conv_fprop_relu_bits(ptr(x0), C0, ptr(x1), C1, ptr(low), ptr(wf), ptr(bias), ptr(out), ptr(up_out), ptr(bits),
+                                             N, H, W, Cout, taps, bn, stream_ptr()))
+    return out
+
+
+def conv_dgrad_bits(dz, wd, C0, bits, taps=9, out0=None, bn=0, stats=None):
+    """conv_dgrad (one output) with the ReLU mask given as the bit mask conv_fprop_relu_bits wrote for the tensor that fed the
+    conv; stats as in conv_dgrad (rows from conv_dgrad_stat_rows(masked=False))."""
+    _req(dz, ACT, "dz"); _req(wd, ACT, "wd"); _req(bits, torch.int64, "bits"); _req(stats, torch.float32, "stats")
+    N, H, W, Cz = dz.shape
+    if tuple(bits.shape) != (N, H, W, C0 // 64):
+        raise ValueError("conv_dgrad_bits: bits must be int64 [N, H, W, C0 // 64]")
+    if out0 is None:
+        out0 = torch.empty((N, H, W, C0), dtype=ACT, device=dz.device)
+    with _timed(f"conv_igemm|dgrad|{N}x{H}x{W}|{Cz}->{C0}+0|t{taps}", 2.0 * N * H * W * Cz * C0 * taps):
+        check(lib().b2u_conv_dgrad_bits(ptr(dz), Cz, ptr(wd), ptr(out0), C0, ptr(bits), N, H, W, taps, bn, ptr(stats),
+                                        0 if stats is None else stats.numel() // (2 * C0), stream_ptr()))
+    return out0
+
+
 def conv_dgrad_stat_rows(N, H, W, Ctot, taps=9, bn=0, masked=False):
     return lib().b2u_conv_dgrad_stat_rows(N, H, W, Ctot, taps, bn, 1 if masked else 0)
 
