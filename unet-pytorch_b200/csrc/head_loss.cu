@@ -280,6 +280,7 @@ loss_stats_map_kernel(const float* __restrict__ logits, const long long* __restr
   float Ps[CM], Pf[CM];
 #pragma unroll
   for (int c = 0; c < CM; ++c) { Ps[c] = Pf[c] = 0.f; }
+  const bool small = P < 0x7fffffffLL && static_cast<long long>(C) * HW < 0x7fffffffLL;
 
   // warp-uniform loop (every lane stays in it, `inb` guards the tail) so the class-wise aggregation below can use
   // full-warp collectives
@@ -288,14 +289,25 @@ loss_stats_map_kernel(const float* __restrict__ logits, const long long* __restr
     const long long p = p0 + lane;
     const bool inb = p < P;
     const long long pc_ = inb ? p : P - 1;
-    const long long n = pc_ / HW, hw = pc_ % HW;
+    // (32-bit index arithmetic whenever the plane fits: a 64-bit division and 21 64-bit multiplies per pixel were a third of
+    // this kernel's instructions)
+    long long n, hw;
+    if (small) { const unsigned pu = static_cast<unsigned>(pc_), hwu = static_cast<unsigned>(HW); n = pu / hwu; hw = pu - static_cast<unsigned>(n) * hwu; }
+    else { n = pc_ / HW; hw = pc_ % HW; }
     const float* z = logits + n * C * HW + hw;
     float v[CM];
     float m = -INFINITY;
+    if (small) {
+      const int hwi = static_cast<int>(HW);
 #pragma unroll
-    for (int c = 0; c < CM; ++c) if (c < C) { v[c] = __ldg(z + c * HW); m = fmaxf(m, v[c]); }
-    const long long y = target[pc_];
-    const bool valid = inb && y >= 0 && y < C;
+      for (int c = 0; c < CM; ++c) if (c < C) { v[c] = __ldg(z + c * hwi); m = fmaxf(m, v[c]); }
+    } else {
+#pragma unroll
+      for (int c = 0; c < CM; ++c) if (c < C) { v[c] = __ldg(z + c * HW); m = fmaxf(m, v[c]); }
+    }
+    const long long y64 = target[pc_];
+    const bool valid = inb && y64 >= 0 && y64 < C;
+    const int y = valid ? static_cast<int>(y64) : -1;
     const float zy = valid ? __ldg(z + y * HW) : 0.f;
     float sum = 0.f;
 #pragma unroll
@@ -315,14 +327,16 @@ loss_stats_map_kernel(const float* __restrict__ logits, const long long* __restr
       const float nll = m + logf(sum) - zy;
       const float wy = swt[y];
       a_ce += wy * nll; a_w += wy;
-      const float logpt = -wy * nll;
-      const float pt = expf(logpt);
-      a_focal += -powf(fmaxf(1.f - pt, 0.f), focal_gamma) * (focal_alpha * logpt);
-      py = expf(zy - m) * inv;
+      if (focal_alpha != 0.f) {          // (host passes alpha = 0 when the focal term is not requested: powf / expf are ~100 instructions)
+        const float logpt = -wy * nll;
+        const float pt = expf(logpt);
+        a_focal += -powf(fmaxf(1.f - pt, 0.f), focal_gamma) * (focal_alpha * logpt);
+      }
+      py = __expf(zy - m) * inv;
     }
     // own-class sums: lanes holding the same class are grouped (label maps are blob-structured, so a warp usually holds
     // one or two classes) and one lane per group updates the warp's table -- integer arithmetic, order-independent
-    const unsigned gm = __match_any_sync(0xffffffffu, valid ? static_cast<int>(y) : -1);
+    const unsigned gm = __match_any_sync(0xffffffffu, y);
     if (valid) {
       const unsigned fx = __reduce_add_sync(gm, __float2uint_rn(py * 16777216.f));      // 2^-24 fixed point, <= 2^29
       const unsigned hard = __popc(__ballot_sync(gm, py > thr));
@@ -425,15 +439,26 @@ loss_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ 
   if (!NHWC64 && p_raw >= P) return;
   const bool inb = p_raw < P;                  // NHWC64: every lane stays for the warp's cooperative store
   const long long p = inb ? p_raw : P - 1;
-  const long long n = p / HW, hw = p % HW;
+  // 32-bit index arithmetic whenever the tensor fits (see loss_stats_map_kernel)
+  const bool small = P < 0x7fffffffLL && static_cast<long long>(C) * HW < 0x7fffffffLL;
+  long long n, hw;
+  if (small) { const unsigned pu = static_cast<unsigned>(p), hwu = static_cast<unsigned>(HW); n = pu / hwu; hw = pu - static_cast<unsigned>(n) * hwu; }
+  else { n = p / HW; hw = p % HW; }
   const float* z = logits + n * C * HW + hw;
   float* dzp = dlogits + n * C * HW + hw;
   float v[CM];
   float m = -INFINITY;
+  if (small) {
+    const int hwi = static_cast<int>(HW);
 #pragma unroll
-  for (int c = 0; c < CM; ++c) if (c < C) { v[c] = __ldg(z + c * HW); m = fmaxf(m, v[c]); }
-  const long long y = target ? target[p] : -1;
-  const bool valid = target && y >= 0 && y < C;
+    for (int c = 0; c < CM; ++c) if (c < C) { v[c] = __ldg(z + c * hwi); m = fmaxf(m, v[c]); }
+  } else {
+#pragma unroll
+    for (int c = 0; c < CM; ++c) if (c < C) { v[c] = __ldg(z + c * HW); m = fmaxf(m, v[c]); }
+  }
+  const long long y64 = target ? target[p] : -1;
+  const bool valid = target && y64 >= 0 && y64 < C;
+  const int y = valid ? static_cast<int>(y64) : -1;
   float zy = 0.f;
 #pragma unroll
   for (int c = 0; c < CM; ++c) if (c < C) { if (valid && c == y) zy = v[c]; }

@@ -41,8 +41,9 @@ class _LossFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, logits, target, onehot, cls_w, w_ce, w_focal, w_dice, beta, smooth, alpha, gamma):
-        fin = ops.loss_fwd(logits, target=target, onehot=onehot, cls_w=cls_w, beta=beta, smooth=smooth, alpha=alpha,
-                           gamma=gamma)
+        # (alpha = 0 zeroes the focal term exactly; the kernel then skips its powf / expf -- only Focal_Loss asks for it)
+        fin = ops.loss_fwd(logits, target=target, onehot=onehot, cls_w=cls_w, beta=beta, smooth=smooth,
+                           alpha=alpha if w_focal != 0.0 else 0.0, gamma=gamma)
         ctx.save_for_backward(logits, target, onehot, cls_w, fin)
         ctx.cfg = (w_ce, w_focal, w_dice, alpha, gamma)
         # only the requested terms: an unrequested CE is 0/0 = nan when no label map was given

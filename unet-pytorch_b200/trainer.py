@@ -288,7 +288,8 @@ class UnetTrainer:
         if logits.shape[2] != pngs.shape[1] and logits.shape[3] != pngs.shape[2]:
             # LightweightUnet: logits at H/2 x W/2 are resized to the label size inside the loss (unet_training.py:12-13)
             logits = ops.resize_bilinear(logits, tuple(pngs.shape[1:]))
-        fin = ops.loss_fwd(logits, target=pngs.contiguous(), onehot=None, cls_w=self.cls_w)
+        # alpha = 0 makes the focal term exactly zero and lets the kernel skip its powf / expf when the loop does not ask for it
+        fin = ops.loss_fwd(logits, target=pngs.contiguous(), onehot=None, cls_w=self.cls_w, alpha=0.5 if self.focal else 0.0)
         return logits, pngs, fin
 
     def train_step(self, imgs=None, pngs=None):
