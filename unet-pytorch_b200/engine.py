@@ -157,6 +157,7 @@ class UNetEngine:
         # b2u_bias_grad re-reading dz from HBM (1.2 GB per headline step).  Those dgrads have K >= 1152, long enough to hide the
         # extra epilogue work.  Layers whose dz comes from the pool / upsample adjoints keep the separate pass.
         self.bias_from_dgrad = os.environ.get("B2U_BIAS_FROM_DGRAD", "1") == "1"
+        self.bias_in_wgrad_rest = os.environ.get("B2U_BIAS_WGRAD_REST", "0") == "1"
         # ReLU backward from bit masks (plain conv + ReLU nets, training forward): every conv epilogue also writes (y > 0) as one
         # bit per channel ([N,H,W,C/64] 64-bit words, 1/16 of the bytes of y) and the masked data gradients / the head backward
         # read those 8 bytes per pixel and block instead of 128 bytes of y -- 2.8 GB less HBM traffic per headline step, and the
@@ -569,8 +570,11 @@ class UNetEngine:
         def param_grads(c, x0, dz, x1):
             wn, bn_ = c.name + ".weight", c.name + ".bias"
             want_w, want_b = has(wn), has(bn_)
+            # Cout = 64: db is free in the swapped-role wgrad kernel.  bias_in_wgrad_rest: the wide layers whose dz comes from the
+            # pool / upsample adjoints (no producing dgrad to take column sums from) let the wgrad kernel's bias warps sum the dz
+            # tiles while they sit in shared memory, instead of a separate pass over dz
             fuse_b = (want_w and want_b and not c.padded and not c.bn and not c.first
-                      and (self.fuse_bias_grad or c.cout_p == 64))     # Cout = 64: db is free in the swapped-role wgrad kernel
+                      and (self.fuse_bias_grad or c.cout_p == 64 or (self.bias_in_wgrad_rest and c.name not in db_stats)))
             taps = 1 if c.first else 9
             if want_w:
                 ctot_p = 64 if c.first else c.c0_p + c.c1_p
