@@ -11,6 +11,7 @@ ready front to back, and one kernel launch updates every parameter.  Like DDP in
 normalises its loss over its own shard and the ranks' gradients are averaged.
 """
 import functools
+import os
 
 import torch
 import torch.distributed as dist
@@ -88,6 +89,14 @@ class GradientSync:
         self.enabled = (self.world > 1) if enabled is None else enabled
         self.cuda = flat_grad.is_cuda
         self.stream = torch.cuda.Stream(device=flat_grad.device) if (self.cuda and self.enabled) else None
+        # Wire format of the gradient buckets.  "fp32" (default) is what DistributedDataParallel sends for the reference
+        # (train.py:346).  "bf16" halves the bytes on NVLink (49.8 MB instead of 99.6 MB for Unet-VGG16, the payload SURVEY.md
+        # 8(d)/(e) plans with): each bucket is rounded to bf16 on the communication stream, summed by NCCL in bf16 and widened
+        # back into the fp32 gradient buffer; every rank still receives bit-identical sums.  B2U_GRAD_WIRE=bf16 selects it.
+        self.wire = os.environ.get("B2U_GRAD_WIRE", "fp32").lower()
+        if self.wire not in ("fp32", "bf16"):
+            raise ValueError("B2U_GRAD_WIRE must be fp32 or bf16")
+        self._wire_bufs = {}
         self._pending = None
         self._handles = []
         self.reset()
@@ -106,7 +115,15 @@ class GradientSync:
             ev.record(torch.cuda.current_stream())
             self.stream.wait_event(ev)
             with torch.cuda.stream(self.stream):
-                dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+                if self.wire == "bf16":
+                    tmp = self._wire_bufs.get(bi)
+                    if tmp is None:
+                        tmp = self._wire_bufs[bi] = torch.empty(e - s, dtype=torch.bfloat16, device=self.flat.device)
+                    tmp.copy_(view)
+                    dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=self.group)
+                    view.copy_(tmp)
+                else:
+                    dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
         else:
             self._handles.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
